@@ -1,0 +1,170 @@
+/* xhved.h -- C ABI of the B200-native ViL-mLSTM + S-MVAE hot path of XLSTM-HVED.
+ *
+ * The reference (Quanato607/XLSTM-HVED) is pure Python/PyTorch and has no FFI
+ * layer; this library is what sits underneath the reference's unchanged Python
+ * module API (see INTEGRATION.md for the binding a maintainer adds).  Every
+ * entry point takes raw DEVICE pointers, explicit sizes and a cudaStream_t
+ * (passed as void*), never allocates, keeps no global state, is re-entrant per
+ * stream, and returns 0 on success, a positive cudaError_t, or a negative
+ * XHVED_ERR_* validation code.  Kernels are sm_100a only.
+ *
+ * Reference symbols each group replaces (paths relative to the reference root):
+ *   xhved_poe_* / xhved_reparam_*   buildingblocks.py:846-886 (ProductOfExperts, ProductOfExperts2),
+ *                                   loss.py:42-83 (duplicates), RA_HVED.py:741-753 (reparametrize, clip),
+ *                                   loss.py:29-40,85-115 (KL_divergence / compute_KLD)
+ *   xhved_mlstm_*                   UxLSTM/nnunetv2/nets/vision_lstm.py:48-130 (parallel_stabilized_simple)
+ *   xhved_vil_pre_*                 vision_lstm.py:224-268 (LayerNorm), 415-435 (ViLLayer.forward up to q,k,v),
+ *                                   178-221 (CausalConv1d), 133-175 (LinearHeadwiseExpand), 302-318 (gates)
+ *   xhved_vil_post_*                vision_lstm.py:271-287 (MultiHeadLayerNorm), 437-453 (skip, z gate, proj_down,
+ *                                   un-flip), vision_lstm_util.py:171-175 (residual), UxLSTMEnc_3d.py:54-63
+ *
+ * Tile-native layout ("tiles"): a [R rows][C cols] bf16 tile stores element (r,c) at byte
+ * ((c/8)*R + r)*16 + (c%8)*2.  q/k/v/h/dh tiles have R = 128 (one chunk of tokens) and C = dhp
+ * (head dim padded to a multiple of 16); tile index = (b*NH + head)*nc + chunk, nc = ceil(S/128).
+ * "Padded gates" are fp32 (BH, nc*128) with i = -1e30, f = +1e30 in the padding rows.
+ */
+#ifndef XHVED_H_
+#define XHVED_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XHVED_ERR_BAD_SHAPE (-1)
+#define XHVED_ERR_UNSUPPORTED_DH (-2)
+#define XHVED_ERR_BAD_ARG (-3)
+#define XHVED_ERR_UNSUPPORTED_DIM (-4)
+
+int xhved_version(void);
+
+/* ---------------------------------------------------------------- S-MVAE product of experts (K4)
+ * mu, logvar: (5, n) fp32, expert e at base + e*expert_stride (elements); expert 0 is the prior
+ * (RA_HVED.py:576-580).  For every requested subset s (bit m of subset_masks[s] set = modality m
+ * present; the prior is always included, buildingblocks.py:854-855):
+ *   T_e = 1/(exp(logvar_e) + eps);  out_mu = sum mu_e T_e / sum T_e;  out_logvar = log(1 / sum T_e)
+ * drop (optional, device, (n/per_sample, 4) uint8): per-sample missing flags of ProductOfExperts2
+ * (buildingblocks.py:875-886): expert m+1 of sample b is removed where drop[b][m] != 0.
+ * noise/out_z (optional, (n_subsets, n)): z = out_mu + noise * exp(0.5 out_logvar) (RA_HVED.py:741-747).
+ * kld_out (optional, device float[n_subsets], must be zeroed by the caller): accumulates
+ *   sum over elements of (-1 - lv + (exp(lv) + mu^2)/(1+1e-8)); the caller scales by 0.5/n (loss.py:29-40).
+ * subset_masks is a HOST array of n_subsets (<= 15) entries. */
+int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
+                  int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, float* out_mu, float* out_logvar,
+                  const float* noise, float* out_z, float* kld_out, void* stream);
+
+/* Backward of xhved_poe_fwd (optionally through z and the KL term): g_mu, g_logvar, g_z (each optional,
+ * (n_subsets, n)); kld_scale[s] (host, optional) = dLoss/d(kld_out[s]).  Writes d_mu, d_logvar (5, n)
+ * at stride expert_stride (summed over subsets; the prior slot receives its gradient too). */
+int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
+                  int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, const float* g_mu, const float* g_logvar,
+                  const float* noise, const float* g_z, const float* kld_scale, float* d_mu, float* d_logvar, void* stream);
+
+/* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
+int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
+int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);
+
+/* ---------------------------------------------------------------- mLSTM cell (K1)
+ * Chunkwise forward over BH = B*NH sequences of nc chunks.  dh = true head dim (scale 1/sqrt(dh)),
+ * dhp in {16,32,64,128}.  Outputs: h_tiles (bf16 tiles), m and den (fp32, (BH, nc*128)): the row
+ * stabiliser (vision_lstm.py:111) and sum_s C_ts (the argument of :123).
+ * Scratch / saved-for-backward buffers, all caller allocated:
+ *   ws_dstate  fp32  BH*nc*dhp*(dhp+16)      ws_g, ws_amax  fp32  BH*nc
+ *   states     bf16  BH*nc*dhp*(dhp+16)  (state ENTERING each chunk, tile-native [dhp][dhp+16])
+ *   m_prev     fp32  BH*nc               (its log-scale) */
+int xhved_mlstm_fwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig_padded, const float* fg_padded,
+                    int BH, int nc, int dh, int dhp, float eps, void* h_tiles, float* m, float* den, float* ws_dstate,
+                    float* ws_g, float* ws_amax, void* states, float* m_prev, void* stream);
+
+/* Backward.  dh_tiles: bf16 tiles of dL/dh.  states/m_prev/m/den/h_tiles as produced by the forward.
+ * Outputs: dq, dk, dv fp32 (BH, nc*128, dhp) row-major; dig, dfg fp32 (BH, nc*128).
+ * Scratch: ws_dstate/ws_g/ws_amax as in the forward, rstates bf16 BH*nc*dhp*(dhp+16), mu_next fp32 BH*nc,
+ * ws_dc fp32 (BH, nc*128).  The (~1e-6 relative) gradient through the row-max stabiliser is dropped. */
+int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig_padded, const float* fg_padded,
+                    const void* h_tiles, const void* dh_tiles, const float* m, const float* den, const void* states,
+                    const float* m_prev, int BH, int nc, int dh, int dhp, float eps, float* dq, float* dk, float* dv, float* dig,
+                    float* dfg, float* ws_dstate, float* ws_g, float* ws_amax, void* rstates, float* mu_next, float* ws_dc,
+                    void* stream);
+
+/* Layout conversion for the stand-alone cell entry point (parallel_stabilized_simple drop-in). */
+int xhved_mlstm_pack(const float* src /* (BH,S,dh) */, int BH, int S, int dh, int dhp, void* tiles, void* stream);
+int xhved_mlstm_pack_gates(const float* ig, const float* fg /* (BH,S) */, int BH, int S, float* ig_padded, float* fg_padded, void* stream);
+int xhved_mlstm_unpack(const void* tiles, int BH, int S, int dh, int dhp, float* dst /* (BH,S,dh) */, void* stream);
+/* fp32 (BH, nc*128, dhp) row-major -> (BH, S, dh) contiguous (gradients of the stand-alone entry point) */
+int xhved_mlstm_unpad_rows(const float* src, int BH, int S, int dh, int dhp, float* dst, void* stream);
+
+/* Diagnostic: D[128][N] = A * B^T through tcgen05 with tile-native operands (see mlstm_fwd.cu). */
+int xhved_umma_selftest(const void* a_tile, const void* b_tile, int N, int K, int a_mn, int b_mn, float* d, void* stream);
+
+/* ---------------------------------------------------------------- ViL block around the cell (K2, K3)
+ * Parameter block: pointers to the reference's parameters (fp32, contiguous), named by state_dict key
+ * relative to the ViLBlock. */
+typedef struct xhved_vil_params {
+  const float* norm_weight;      /* norm.weight                         (C)        */
+  const float* proj_up_weight;   /* layer.proj_up.weight                (2E, C)    */
+  const float* conv_weight;      /* layer.conv1d.conv.weight            (E, 1, 4)  */
+  const float* conv_bias;        /* layer.conv1d.conv.bias              (E)        */
+  const float* q_weight;         /* layer.q_proj.weight                 (E/QB, QB, QB) */
+  const float* k_weight;         /* layer.k_proj.weight                            */
+  const float* v_weight;         /* layer.v_proj.weight                            */
+  const float* igate_weight;     /* layer.mlstm_cell.igate.weight       (NH, 3E)   */
+  const float* igate_bias;       /* layer.mlstm_cell.igate.bias         (NH)       */
+  const float* fgate_weight;     /* layer.mlstm_cell.fgate.weight       (NH, 3E)   */
+  const float* fgate_bias;       /* layer.mlstm_cell.fgate.bias         (NH)       */
+  const float* outnorm_weight;   /* layer.mlstm_cell.outnorm.weight     (E)        */
+  const float* learnable_skip;   /* layer.learnable_skip                (E)        */
+  const float* proj_down_weight; /* layer.proj_down.weight              (C, E)     */
+} xhved_vil_params;
+
+/* Gradients of the same parameters (fp32, accumulated with atomics: zero them first). */
+typedef struct xhved_vil_grads {
+  float* norm_weight;
+  float* proj_up_weight;
+  float* conv_weight;
+  float* conv_bias;
+  float* q_weight;
+  float* k_weight;
+  float* v_weight;
+  float* igate_weight;
+  float* igate_bias;
+  float* fgate_weight;
+  float* fgate_bias;
+  float* outnorm_weight;
+  float* learnable_skip;
+  float* proj_down_weight;
+} xhved_vil_grads;
+
+/* Token geometry: x[b, n, c] = x_base[b*stride_b + n*stride_n + c*stride_c] (elements).  The NCDHW
+ * bottleneck feature (UxLSTMEnc_3d.py:59) is stride_n = 1, stride_c = S; a (B,S,C) token tensor is
+ * stride_n = C, stride_c = 1.  reverse != 0 = SequenceTraversal.ROWWISE_FROM_BOT_RIGHT. */
+typedef struct xhved_vil_shape {
+  int B, S, C;          /* tokens: batch, sequence, model dim; E = 2C inner dim                */
+  int NH, QB;           /* cell heads (= qkv_block_size, vision_lstm.py:402-405) and block size */
+  int reverse;
+  int64_t x_stride_b, x_stride_n, x_stride_c;
+  int64_t y_stride_b, y_stride_n, y_stride_c;
+} xhved_vil_shape;
+
+/* K2: LayerNorm -> proj_up -> causal conv -> SiLU -> q,k,v (tiles) + gates (padded) + act, z.
+ * act, z: fp32 (B, nc, E, 128) token-minor, traversal order. */
+int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, const xhved_vil_shape* sh, void* q_tiles, void* k_tiles,
+                      void* v_tiles, float* ig_padded, float* fg_padded, float* act, float* z, void* stream);
+/* K3: outnorm(h) + skip*act, * silu(z), proj_down, + x residual -> y (same geometry family as x). */
+int xhved_vil_post_fwd(const float* x, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
+                       const xhved_vil_shape* sh, float* y, void* stream);
+/* K3 backward: from dy computes dh (bf16 tiles), d_act_skip, dz (fp32 (B,nc,E,128)), dx_residual is dy itself;
+ * accumulates outnorm / skip / proj_down gradients. */
+int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
+                       const xhved_vil_shape* sh, void* dh_tiles, float* d_act, float* dz, const xhved_vil_grads* g, void* stream);
+/* K2 backward: from dq, dk, dv (fp32 (BH, nc*128, dhp)), dig, dfg (padded), d_act (skip path), dz computes
+ * dx (added to the residual gradient dy -> dx, same geometry as x) and accumulates parameter gradients. */
+int xhved_vil_pre_bwd(const float* x, const float* dy, const float* dq, const float* dk, const float* dv, const float* dig,
+                      const float* dfg, const float* d_act, const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh,
+                      float* dx, const xhved_vil_grads* g, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XHVED_H_ */

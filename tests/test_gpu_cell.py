@@ -1,0 +1,76 @@
+"""GPU parity of the chunkwise tcgen05 mLSTM cell against the oracle (through the C ABI)."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_linf
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+# bf16 operands (q,k,v,P,state) vs the fp64 reference: BASELINE.json north_star tolerance
+TOL_H_L2 = 2e-2
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("N,K", [(32, 32), (128, 16), (48, 128)])
+def test_umma_tile_native_views(a_mn, b_mn, N, K):
+    from xlstm_hved_b200 import ops
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A = torch.randn(128, K, generator=g).bfloat16()
+    Bm = torch.randn(N, K, generator=g).bfloat16()
+    a_tile = ops.to_tile_native(A.t().contiguous() if a_mn else A).cuda()
+    b_tile = ops.to_tile_native(Bm.t().contiguous() if b_mn else Bm).cuda()
+    d = ops.umma_selftest(a_tile, b_tile, N, K, a_mn, b_mn).cpu()
+    ref = A.double() @ Bm.double().t()
+    assert rel_linf(d, ref) < 1e-5
+
+
+def _run_cell(q, k, v, ig, fg):
+    from xlstm_hved_b200 import ops
+    B, NH = q.shape[:2]
+    buf = ops.mlstm_pack_inputs(q.cuda().float(), k.cuda().float(), v.cuda().float(), ig.cuda().float(), fg.cuda().float())
+    ops.mlstm_fwd_tiles(buf)
+    torch.cuda.synchronize()
+    return ops.mlstm_unpack_h(buf, B, NH).cpu(), buf
+
+
+@pytest.mark.parametrize("name", ["bottleneck_s320_dh16", "randn_f4_s200_dh16", "randn_f0_s256_dh32",
+                                  "randn_fm2_s130_dh8", "randn_f4_s256_dh64"])
+def test_cell_forward_matches_reference_golden(name):
+    c = load_golden("cell.pt")[name]
+    h, buf = _run_cell(c["q"], c["k"], c["v"], c["ig"], c["fg"])
+    err = rel_l2(h, c["h"])
+    print(name, "rel_l2", err, "rel_linf", rel_linf(h, c["h"]), "fp32 reference rel_l2", rel_l2(c["h_fp32_ref"], c["h"]))
+    assert err < TOL_H_L2
+    # the stabiliser is the reference's row max (vision_lstm.py:111), bit-for-bit up to fp32 rounding
+    q, k, v, ig, fg = [c[n].double() for n in ("q", "k", "v", "ig", "fg")]
+    _, m_ref, den_ref = restate.mlstm_parallel(q, k, v, ig, fg, return_aux=True)
+    B, NH, S, _ = q.shape
+    m = buf.m.view(B, NH, -1)[:, :, :S].cpu()
+    assert (m.double() - m_ref).abs().max() < 1e-3 * (1 + m_ref.abs().max())
+
+
+@pytest.mark.parametrize("B,NH,S,DH,fmean", [(1, 4, 4096, 16, 0.41), (2, 4, 1000, 16, 4.0), (1, 4, 777, 32, -2.0),
+                                              (1, 2, 640, 64, 0.0), (1, 1, 384, 128, 3.0)])
+def test_cell_forward_matches_oracle_seeded(B, NH, S, DH, fmean):
+    g = torch.Generator().manual_seed(S + DH)
+    q, k, v = [torch.randn(B, NH, S, DH, generator=g) for _ in range(3)]
+    ig = torch.randn(B, NH, S, 1, generator=g)
+    fg = fmean + torch.randn(B, NH, S, 1, generator=g)
+    h, _ = _run_cell(q, k, v, ig, fg)
+    ref = restate.mlstm_chunkwise(q.double(), k.double(), v.double(), ig.double(), fg.double(), chunk=256)
+    err = rel_l2(h, ref)
+    print((B, NH, S, DH, fmean), "rel_l2", err, "rel_linf", rel_linf(h, ref))
+    assert err < TOL_H_L2
+
+
+def test_cell_long_sequence_32768():
+    """BASELINE config 5: the 32^3 stage (32768 tokens) -- only the chunkwise form can run it."""
+    B, NH, S, DH = 1, 4, 32768, 16
+    g = torch.Generator().manual_seed(5)
+    q, k, v = [0.5 * torch.randn(B, NH, S, DH, generator=g) for _ in range(3)]
+    ig = torch.randn(B, NH, S, 1, generator=g)
+    fg = 2.0 + torch.randn(B, NH, S, 1, generator=g)
+    h, _ = _run_cell(q, k, v, ig, fg)
+    ref = restate.mlstm_chunkwise(q.double(), k.double(), v.double(), ig.double(), fg.double(), chunk=512)
+    assert rel_l2(h, ref) < TOL_H_L2

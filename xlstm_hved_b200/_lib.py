@@ -1,0 +1,106 @@
+"""ctypes binding of libxhved.so (the C ABI declared in include/xhved.h).
+
+There is NO CPU fallback: if the library is missing or no CUDA device is
+present, every op raises.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_float, c_int, c_int64, c_uint32, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxhved.so")
+
+_ERR = {-1: "XHVED_ERR_BAD_SHAPE", -2: "XHVED_ERR_UNSUPPORTED_DH", -3: "XHVED_ERR_BAD_ARG", -4: "XHVED_ERR_UNSUPPORTED_DIM"}
+
+_PARAM_FIELDS = ["norm_weight", "proj_up_weight", "conv_weight", "conv_bias", "q_weight", "k_weight", "v_weight",
+                 "igate_weight", "igate_bias", "fgate_weight", "fgate_bias", "outnorm_weight", "learnable_skip",
+                 "proj_down_weight"]
+
+
+class VilParams(Structure):
+    _fields_ = [(n, c_void_p) for n in _PARAM_FIELDS]
+
+
+class VilGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in _PARAM_FIELDS]
+
+
+class VilShape(Structure):
+    _fields_ = [("B", c_int), ("S", c_int), ("C", c_int), ("NH", c_int), ("QB", c_int), ("reverse", c_int),
+                ("x_stride_b", c_int64), ("x_stride_n", c_int64), ("x_stride_c", c_int64),
+                ("y_stride_b", c_int64), ("y_stride_n", c_int64), ("y_stride_c", c_int64)]
+
+
+# every symbol include/xhved.h declares -> argtypes (None = not yet bound with a signature)
+SYMBOLS = {
+    "xhved_version": [],
+    "xhved_poe_fwd": [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint32), c_int, c_void_p, c_int64, c_float, c_void_p,
+                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "xhved_poe_bwd": [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint32), c_int, c_void_p, c_int64, c_float, c_void_p,
+                      c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_void_p],
+    "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
+    "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,
+    "xhved_mlstm_bwd": [c_void_p] * 11 + [c_int] * 4 + [c_float] + [c_void_p] * 12,
+    "xhved_mlstm_pack": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "xhved_mlstm_pack_gates": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "xhved_mlstm_unpack": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "xhved_mlstm_unpad_rows": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "xhved_umma_selftest": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "xhved_vil_pre_fwd": [c_void_p, POINTER(VilParams), POINTER(VilShape)] + [c_void_p] * 8,
+    "xhved_vil_post_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p],
+    "xhved_vil_post_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p,
+                           c_void_p, POINTER(VilGrads), c_void_p],
+    "xhved_vil_pre_bwd": [c_void_p] * 9 + [POINTER(VilParams), POINTER(VilShape), c_void_p, POINTER(VilGrads), c_void_p],
+}
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libxhved.so and bind every declared symbol.  Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m xlstm_hved_b200.build` "
+                "(this package has no CPU or PyTorch fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        missing = []
+        for name, argtypes in SYMBOLS.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                missing.append(name)
+                continue
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        if missing:
+            raise RuntimeError(f"{LIB_PATH} lacks symbols declared in include/xhved.h: {missing}; rebuild it")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{what}: {_ERR.get(rc, rc)}")
+    raise RuntimeError(f"{what}: CUDA error {rc} ({torch.cuda.get_device_name() if torch.cuda.is_available() else 'no device'})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 ops need CUDA tensors (no CPU fallback)")
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,88 @@
+// Shared device helpers for the chunkwise mLSTM kernels (forward and backward).
+#pragma once
+#include "umma.cuh"
+
+namespace xhved {
+
+constexpr int kL = 128;        // chunk length == UMMA M == TMEM lanes
+constexpr int kThreads = 128;  // one thread per chunk row
+
+// Extended ("ext") column count: a [value | 1 | 0...] / [C | n | 0...] block is DHP+16 wide.
+__host__ __device__ constexpr int ext_cols(int dhp) { return dhp + 16; }
+__host__ __device__ constexpr uint32_t next_pow2_cols(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
+
+// ---- 128-wide block scans (4 warps).  `red` is 8 floats of shared scratch. ----
+__device__ __forceinline__ float block_cumsum128(float x, float* red, float* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) red[warp] = x;
+  __syncthreads();
+  float off = 0.f, tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float r = red[w];
+    if (w < warp) off += r;
+    tot += r;
+  }
+  __syncthreads();
+  if (total) *total = tot;
+  return x + off;
+}
+__device__ __forceinline__ float block_cummax128(float x, float* red, float* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x = fmaxf(x, y);
+  }
+  if (lane == 31) red[warp] = x;
+  __syncthreads();
+  float off = -INFINITY, tot = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float r = red[w];
+    if (w < warp) off = fmaxf(off, r);
+    tot = fmaxf(tot, r);
+  }
+  __syncthreads();
+  if (total) *total = tot;
+  return fmaxf(x, off);
+}
+// reverse (suffix) inclusive cumulative sum over the 128 threads
+__device__ __forceinline__ float block_rcumsum128(float x, float* red, float* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float y = __shfl_down_sync(0xffffffffu, x, o);
+    if (lane + o < 32) x += y;
+  }
+  if (lane == 0) red[warp] = x;
+  __syncthreads();
+  float off = 0.f, tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float r = red[w];
+    if (w > warp) off += r;
+    tot += r;
+  }
+  __syncthreads();
+  if (total) *total = tot;
+  return x + off;
+}
+
+// byte offset of the 16-byte group (row r, column group cg) in a tile-native tile with R rows
+__device__ __forceinline__ uint32_t tile_off16(int R, int r, int cg) { return (static_cast<uint32_t>(cg) * R + r) * 16u; }
+
+// write the two "ext" column groups [1,0,...,0 | 0...0] of row r behind a 128-row tile of dhp columns
+__device__ __forceinline__ void write_ext_ones(unsigned char* tile, int dhp, int r) {
+  uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);  // bf16(1.0) in element 0
+  uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(tile + tile_off16(kL, r, dhp / 8)) = one;
+  *reinterpret_cast<uint4*>(tile + tile_off16(kL, r, dhp / 8 + 1)) = zero;
+}
+
+}  // namespace xhved

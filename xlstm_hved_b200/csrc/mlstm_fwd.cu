@@ -1,0 +1,490 @@
+// Chunkwise stabilised mLSTM cell, forward -- sm_100a (tcgen05 + TMEM + bulk async copies).
+//
+// Computes exactly what the reference's parallel_stabilized_simple does
+// (UxLSTM/nnunetv2/nets/vision_lstm.py:48-130) in the chunkwise form of
+// SURVEY.md 8a-note, chunk L = 128 = UMMA M:
+//
+//   phase 1  chunk_state   (b,head,chunk)-parallel: dC_c = sum_j exp(a_j - amax_c) (k_j/sqrt(DH)) [v_j | 1]^T
+//   phase 2  state_scan    (b,head)-parallel, sequential over chunks: carried (C|n, m) entering every chunk
+//   phase 3  chunk_out     (b,head,chunk)-parallel: S = Q K^T, P = S o D', O = P V + w (Q [C|n]),  h = O / N
+//
+// q/k/v/h tiles are bf16 in the tile-native layout (umma.cuh); gates, stabiliser m,
+// normaliser input den and all accumulators are fp32.
+#include "mlstm_common.cuh"
+#include "xhved.h"
+
+namespace xhved {
+
+// ------------------------------------------------------------------ phase 1
+template <int DHP>
+__global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsigned char* __restrict__ k_tiles,
+                                                                      const unsigned char* __restrict__ v_tiles,
+                                                                      const float* __restrict__ ig, const float* __restrict__ fg,
+                                                                      int nc, float scale, float* __restrict__ dstate,
+                                                                      float* __restrict__ g_out, float* __restrict__ amax_out) {
+  constexpr int NE = ext_cols(DHP);
+  constexpr uint32_t TILE = kL * DHP * 2;
+  constexpr uint32_t TMEM_COLS = next_pow2_cols(NE);
+  // smem: [K tile, read as a 128-row MN-major A operand => 32 KB window][Vext tile]
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sK = smem;
+  unsigned char* sV = smem + 32768;
+  __shared__ __align__(8) uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x;  // (b*NH + h) * nc + c
+  const size_t grow = static_cast<size_t>(tile) * kL + tid;
+
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  write_ext_ones(sV, DHP, tid);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, 2 * TILE);
+    bulk_g2s(sK, k_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+    bulk_g2s(sV, v_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+  }
+  // gates: b_j = chunk-local inclusive cumsum of log sigmoid(f), a_j = g - b_j + i_j
+  const float iv = ig[grow];
+  const float lf = log_sigmoid(fg[grow]);
+  float g;
+  const float b = block_cumsum128(lf, red, &g);
+  const float a = g - b + iv;
+  float amax;
+  block_cummax128(a, red, &amax);
+  const float wgt = __expf(a - amax) * scale;
+
+  mbar_wait(&bar_load, 0);
+  // scale K rows in place: k~_j = exp(a_j - amax) * k_j / sqrt(DH)
+#pragma unroll
+  for (int cg = 0; cg < DHP / 8; ++cg) {
+    uint4* p = reinterpret_cast<uint4*>(sK + tile_off16(kL, tid, cg));
+    uint4 u = *p;
+    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    u.x = pack_bf16x2(f0.x * wgt, f0.y * wgt);
+    u.y = pack_bf16x2(f1.x * wgt, f1.y * wgt);
+    u.z = pack_bf16x2(f2.x * wgt, f2.y * wgt);
+    u.w = pack_bf16x2(f3.x * wgt, f3.y * wgt);
+    *p = u;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // D[d][e'] = sum_j K~[j][d] * Vext[j][e']   (A, B both MN-major views of row-j tiles)
+    umma_gemm(tmem, smem_u32(sK), /*lbo*/ 128, /*sbo*/ kL * 16, smem_u32(sV), 128, kL * 16,
+              umma_idesc(128, NE, true, true), kL, false);
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  if (warp * 32 < DHP) {
+    float* out = dstate + (static_cast<size_t>(tile) * DHP + tid) * NE;
+#pragma unroll
+    for (int c0 = 0; c0 < NE; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      if (tid < DHP) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  if (tid == 0) {
+    g_out[tile] = g;
+    amax_out[tile] = amax;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ phase 2
+// One CTA per (b,head).  Thread owns elements idx = tid + k*blockDim of the DHP x NE state.
+// Writes, for every chunk c, the state ENTERING chunk c as a bf16 tile-native tile
+// [DHP rows (key dim d)][NE cols (value dim e | n | 0)] plus its log-scale m_prev[c].
+// `reverse` runs the same recurrence from the last chunk to the first (backward pass).
+template <int DHP, int PER_THREAD>
+__global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __restrict__ dstate, const float* __restrict__ g_in,
+                                                                const float* __restrict__ amax_in, int nc, int reverse,
+                                                                unsigned char* __restrict__ states, float* __restrict__ m_prev) {
+  constexpr int NE = ext_cols(DHP);
+  constexpr int NEL = DHP * NE;
+  const int bh = blockIdx.x, tid = threadIdx.x;
+  float acc[PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < PER_THREAD; ++k) acc[k] = 0.f;
+  float m = -INFINITY;
+  for (int step = 0; step < nc; ++step) {
+    const int c = reverse ? nc - 1 - step : step;
+    const size_t tile = static_cast<size_t>(bh) * nc + c;
+    // emit the state entering this chunk
+    unsigned char* st = states + tile * (NEL * 2);
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+      const int idx = tid + k * 256;
+      if (idx < NEL) {
+        const int d = idx / NE, e = idx % NE;
+        *reinterpret_cast<__nv_bfloat16*>(st + tile_off16(DHP, d, e / 8) + (e % 8) * 2) = __float2bfloat16(acc[k]);
+      }
+    }
+    if (tid == 0) m_prev[tile] = m;
+    // fold this chunk in
+    const float g = g_in[tile], amax = amax_in[tile];
+    const float m_new = fmaxf(g + m, amax);
+    const float decay = __expf(g + m - m_new);   // exp(-inf) = 0 on the first step
+    const float wnew = __expf(amax - m_new);
+    const float* src = dstate + tile * NEL;
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+      const int idx = tid + k * 256;
+      if (idx < NEL) acc[k] = decay * acc[k] + wnew * src[idx];
+    }
+    m = m_new;
+  }
+}
+
+// ------------------------------------------------------------------ phase 3
+template <int DHP>
+__global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
+    const unsigned char* __restrict__ q_tiles, const unsigned char* __restrict__ k_tiles, const unsigned char* __restrict__ v_tiles,
+    const float* __restrict__ ig, const float* __restrict__ fg, const unsigned char* __restrict__ states,
+    const float* __restrict__ m_prev, int nc, float scale, float eps, unsigned char* __restrict__ h_tiles,
+    float* __restrict__ m_out, float* __restrict__ den_out) {
+  constexpr int NE = ext_cols(DHP);
+  constexpr uint32_t TILE = kL * DHP * 2;
+  constexpr uint32_t ST_BYTES = DHP * NE * 2;
+  constexpr uint32_t P_BYTES = kL * kL * 2;
+  // TMEM columns: S at [0,128); afterwards O_intra at [0,DHP), O_inter at [DHP, DHP+NE)
+  constexpr uint32_t TMEM_COLS = next_pow2_cols((2 * DHP + 16) > 128 ? (2 * DHP + 16) : 128);
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + TILE;
+  unsigned char* sV = sK + TILE;
+  unsigned char* sP = sV + TILE;
+  unsigned char* sS = sP + P_BYTES;
+  float* vcol = reinterpret_cast<float*>(sS + ST_BYTES);  // (i_s - b_s) * log2e
+  __shared__ __align__(8) uint64_t bar_load, bar_mma1, bar_mma2;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int c = tile % nc;
+  const size_t grow = static_cast<size_t>(tile) * kL + tid;
+  const bool has_state = c > 0;
+
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma1, 1);
+    mbar_init(&bar_mma2, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, 3 * TILE + (has_state ? ST_BYTES : 0));
+    bulk_g2s(sQ, q_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+    bulk_g2s(sK, k_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+    bulk_g2s(sV, v_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+    if (has_state) bulk_g2s(sS, states + static_cast<size_t>(tile) * ST_BYTES, ST_BYTES, &bar_load);
+  }
+  // ---- gate scans: b_t, m_t (vision_lstm.py:82-111 as a 1-D scan) ----
+  const float iv = ig[grow];
+  const float lf = log_sigmoid(fg[grow]);
+  const float b = block_cumsum128(lf, red, nullptr);
+  const float vc = iv - b;
+  const float m_intra = b + block_cummax128(vc, red, nullptr);
+  const float mp = has_state ? m_prev[tile] : -INFINITY;
+  const float m_inter = b + mp;
+  const float m = fmaxf(m_intra, m_inter);
+  const float w = has_state ? __expf(m_inter - m) : 0.f;
+  vcol[tid] = vc * kLog2e;
+  const float urow = (b - m) * kLog2e + log2f(scale);
+
+  mbar_wait(&bar_load, 0);
+  tc_fence_before();
+  __syncthreads();   // vcol + tmem_slot visible
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // S[t][s] = sum_d Q[t][d] K[s][d]
+    umma_gemm(tmem, smem_u32(sQ), kL * 16, 128, smem_u32(sK), kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
+    umma_commit(&bar_mma1);
+  }
+  mbar_wait(&bar_mma1, 0);
+  tc_fence_after();
+  // ---- P = S o D' (causal), row sums; P -> smem as the next A operand ----
+  float rowsum = 0.f;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+#pragma unroll 1
+  for (int blk = 0; blk < 4; ++blk) {
+    if (blk <= warp) {
+      float sv[32];
+      tmem_ld32(tmem + lane_base + blk * 32, sv);
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        float p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int s = blk * 32 + j8 * 8 + j;
+          const float d = fast_exp2(urow + vcol[s]);
+          p[j] = (s <= tid) ? sv[j8 * 8 + j] * d : 0.f;
+          rowsum += p[j];
+        }
+        uint4 u;
+        u.x = pack_bf16x2(p[0], p[1]);
+        u.y = pack_bf16x2(p[2], p[3]);
+        u.z = pack_bf16x2(p[4], p[5]);
+        u.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, blk * 4 + j8)) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, blk * 4 + j8)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    // O_intra[t][e] = sum_s P[t][s] V[s][e]      (B = MN-major view of V)
+    umma_gemm(tmem, smem_u32(sP), kL * 16, 128, smem_u32(sV), 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
+    // O_inter[t][e'] = sum_d Q[t][d] [C|n][d][e'] (B = MN-major view of the state tile)
+    if (has_state)
+      umma_gemm(tmem + DHP, smem_u32(sQ), kL * 16, 128, smem_u32(sS), 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, false);
+    umma_commit(&bar_mma2);
+  }
+  mbar_wait(&bar_mma2, 0);
+  tc_fence_after();
+  // ---- epilogue: h = (O_intra + w O_inter) / (max(|den|, exp(-m)) + eps)   (vision_lstm.py:123-128) ----
+  float den = rowsum;
+  float inter_n = 0.f;
+  if (has_state) {
+    float t16[16];
+    tmem_ld16(tmem + lane_base + 2 * DHP, t16);
+    inter_n = t16[0];
+    den += w * inter_n;
+  }
+  const float nrm = fmaxf(fabsf(den), __expf(-m)) + eps;
+  const float rn = 1.f / nrm;
+  unsigned char* hdst = h_tiles + static_cast<size_t>(tile) * TILE;
+#pragma unroll
+  for (int c0 = 0; c0 < DHP; c0 += 16) {
+    float o[16];
+    tmem_ld16(tmem + lane_base + c0, o);
+    if (has_state) {
+      float oi[16];
+      tmem_ld16(tmem + lane_base + DHP + c0, oi);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] += w * oi[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] *= rn;
+    uint4 u0, u1;
+    u0.x = pack_bf16x2(o[0], o[1]);
+    u0.y = pack_bf16x2(o[2], o[3]);
+    u0.z = pack_bf16x2(o[4], o[5]);
+    u0.w = pack_bf16x2(o[6], o[7]);
+    u1.x = pack_bf16x2(o[8], o[9]);
+    u1.y = pack_bf16x2(o[10], o[11]);
+    u1.z = pack_bf16x2(o[12], o[13]);
+    u1.w = pack_bf16x2(o[14], o[15]);
+    *reinterpret_cast<uint4*>(hdst + tile_off16(kL, tid, c0 / 8)) = u0;
+    *reinterpret_cast<uint4*>(hdst + tile_off16(kL, tid, c0 / 8 + 1)) = u1;
+  }
+  m_out[grow] = m;
+  den_out[grow] = den;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ pack / unpack (standalone cell API)
+// fp32 (BH, S, DH) row-major -> bf16 tile-native tiles (BH*nc tiles of 128 x DHP), zero padded.
+__global__ void mlstm_pack_kernel(const float* __restrict__ src, int S, int DH, int DHP, int nc, unsigned char* __restrict__ tiles) {
+  const int tile = blockIdx.x, r = threadIdx.x;
+  const int bh = tile / nc, c = tile % nc;
+  const int t = c * kL + r;
+  unsigned char* dst = tiles + static_cast<size_t>(tile) * (kL * DHP * 2);
+  const float* row = src + (static_cast<size_t>(bh) * S + t) * DH;
+  for (int cg = 0; cg < DHP / 8; ++cg) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int d = cg * 8 + j;
+      f[j] = (t < S && d < DH) ? row[d] : 0.f;
+    }
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]);
+    u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]);
+    u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dst + tile_off16(kL, r, cg)) = u;
+  }
+}
+// gates (BH, S) -> (BH, nc*128); padding rows get i = -1e30 (no weight), f = +1e30 (log sigmoid = 0)
+__global__ void mlstm_pack_gates_kernel(const float* __restrict__ ig, const float* __restrict__ fg, int S, int nc,
+                                        float* __restrict__ igp, float* __restrict__ fgp) {
+  const int tile = blockIdx.x, r = threadIdx.x;
+  const int bh = tile / nc, c = tile % nc;
+  const int t = c * kL + r;
+  const size_t o = static_cast<size_t>(tile) * kL + r;
+  igp[o] = t < S ? ig[static_cast<size_t>(bh) * S + t] : -1e30f;
+  fgp[o] = t < S ? fg[static_cast<size_t>(bh) * S + t] : 1e30f;
+}
+// bf16 tiles -> fp32 (BH, S, DH)
+__global__ void mlstm_unpack_kernel(const unsigned char* __restrict__ tiles, int S, int DH, int DHP, int nc, float* __restrict__ dst) {
+  const int tile = blockIdx.x, r = threadIdx.x;
+  const int bh = tile / nc, c = tile % nc;
+  const int t = c * kL + r;
+  if (t >= S) return;
+  const unsigned char* src = tiles + static_cast<size_t>(tile) * (kL * DHP * 2);
+  float* row = dst + (static_cast<size_t>(bh) * S + t) * DH;
+  for (int cg = 0; cg < DHP / 8; ++cg) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + tile_off16(kL, r, cg));
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    const float f[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (cg * 8 + j < DH) row[cg * 8 + j] = f[j];
+  }
+}
+
+// ------------------------------------------------------------------ host launchers
+template <int DHP>
+static int launch_fwd(const void* q, const void* k, const void* v, const float* ig, const float* fg, int BH, int nc, int dh,
+                      float eps, void* h, float* m, float* den, float* ws_dstate, float* ws_g, float* ws_amax, void* states,
+                      float* m_prev, cudaStream_t st) {
+  constexpr int NE = ext_cols(DHP);
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  const int ntiles = BH * nc;
+  // phase 1
+  {
+    const size_t smem = 32768 + kL * NE * 2;
+    cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_state_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mlstm_chunk_state_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)k, (const unsigned char*)v, ig, fg, nc, scale,
+                                                                  ws_dstate, ws_g, ws_amax);
+  }
+  // phase 2
+  {
+    constexpr int PT = (DHP * NE + 255) / 256;
+    mlstm_state_scan_kernel<DHP, PT><<<BH, 256, 0, st>>>(ws_dstate, ws_g, ws_amax, nc, 0, (unsigned char*)states, m_prev);
+  }
+  // phase 3
+  {
+    const size_t smem = 3 * kL * DHP * 2 + kL * kL * 2 + DHP * NE * 2 + kL * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_out_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mlstm_chunk_out_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v,
+                                                                ig, fg, (const unsigned char*)states, m_prev, nc, scale, eps,
+                                                                (unsigned char*)h, m, den);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace xhved
+
+using namespace xhved;
+
+extern "C" int xhved_mlstm_fwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig, const float* fg,
+                               int BH, int nc, int dh, int dhp, float eps, void* h_tiles, float* m, float* den, float* ws_dstate,
+                               float* ws_g, float* ws_amax, void* states, float* m_prev, void* stream) {
+  if (BH <= 0 || nc <= 0 || dh <= 0 || dh > dhp) return XHVED_ERR_BAD_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dhp) {
+    case 16: return launch_fwd<16>(q_tiles, k_tiles, v_tiles, ig, fg, BH, nc, dh, eps, h_tiles, m, den, ws_dstate, ws_g, ws_amax, states, m_prev, st);
+    case 32: return launch_fwd<32>(q_tiles, k_tiles, v_tiles, ig, fg, BH, nc, dh, eps, h_tiles, m, den, ws_dstate, ws_g, ws_amax, states, m_prev, st);
+    case 64: return launch_fwd<64>(q_tiles, k_tiles, v_tiles, ig, fg, BH, nc, dh, eps, h_tiles, m, den, ws_dstate, ws_g, ws_amax, states, m_prev, st);
+    case 128: return launch_fwd<128>(q_tiles, k_tiles, v_tiles, ig, fg, BH, nc, dh, eps, h_tiles, m, den, ws_dstate, ws_g, ws_amax, states, m_prev, st);
+    default: return XHVED_ERR_UNSUPPORTED_DH;
+  }
+}
+
+extern "C" int xhved_mlstm_pack(const float* src, int BH, int S, int dh, int dhp, void* tiles, void* stream) {
+  if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp || dhp % 16) return XHVED_ERR_BAD_SHAPE;
+  const int nc = (S + kL - 1) / kL;
+  mlstm_pack_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>(src, S, dh, dhp, nc, (unsigned char*)tiles);
+  return (int)cudaGetLastError();
+}
+extern "C" int xhved_mlstm_pack_gates(const float* ig, const float* fg, int BH, int S, float* ig_padded, float* fg_padded, void* stream) {
+  if (BH <= 0 || S <= 0) return XHVED_ERR_BAD_SHAPE;
+  const int nc = (S + kL - 1) / kL;
+  mlstm_pack_gates_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>(ig, fg, S, nc, ig_padded, fg_padded);
+  return (int)cudaGetLastError();
+}
+extern "C" int xhved_mlstm_unpack(const void* tiles, int BH, int S, int dh, int dhp, float* dst, void* stream) {
+  if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp || dhp % 16) return XHVED_ERR_BAD_SHAPE;
+  const int nc = (S + kL - 1) / kL;
+  mlstm_unpack_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>((const unsigned char*)tiles, S, dh, dhp, nc, dst);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ UMMA self test (diagnostic entry point)
+// D[128][N] = A * B^T with A, B given as tile-native tiles; a_mn / b_mn choose the MN-major view.
+//   a_mn = 0: A tile is [128 rows (m)][K cols];   a_mn = 1: A tile is [K rows][128 cols (m)]
+//   b_mn = 0: B tile is [N rows (n)][K cols];     b_mn = 1: B tile is [K rows][N cols (n)]
+__global__ void __launch_bounds__(kThreads) umma_selftest_kernel(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, int N,
+                                                                  int K, int a_mn, int b_mn, float* __restrict__ d) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t a_bytes = 128 * K * 2, b_bytes = N * K * 2;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + a_bytes;
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, a_bytes + b_bytes);
+    bulk_g2s(sA, a, a_bytes, &bar_load);
+    bulk_g2s(sB, b, b_bytes, &bar_load);
+  }
+  mbar_wait(&bar_load, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t a_rows = a_mn ? K : 128, b_rows = b_mn ? K : N;
+    const uint32_t a_lbo = a_mn ? 128 : a_rows * 16, a_sbo = a_mn ? a_rows * 16 : 128;
+    const uint32_t b_lbo = b_mn ? 128 : b_rows * 16, b_sbo = b_mn ? b_rows * 16 : 128;
+    umma_gemm(tmem, smem_u32(sA), a_lbo, a_sbo, smem_u32(sB), b_lbo, b_sbo, umma_idesc(128, N, a_mn != 0, b_mn != 0), K, false);
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    for (int i = 0; i < 16; ++i) d[tid * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+extern "C" int xhved_umma_selftest(const void* a_tile, const void* b_tile, int N, int K, int a_mn, int b_mn, float* d, void* stream) {
+  if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 128) return XHVED_ERR_BAD_SHAPE;
+  const size_t smem = 128 * K * 2 + N * K * 2;
+  cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  umma_selftest_kernel<<<1, kThreads, smem, static_cast<cudaStream_t>(stream)>>>((const unsigned char*)a_tile, (const unsigned char*)b_tile, N, K,
+                                                                              a_mn, b_mn, d);
+  return (int)cudaGetLastError();
+}
