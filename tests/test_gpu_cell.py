@@ -74,3 +74,36 @@ def test_cell_long_sequence_32768():
     h, _ = _run_cell(q, k, v, ig, fg)
     ref = restate.mlstm_chunkwise(q.double(), k.double(), v.double(), ig.double(), fg.double(), chunk=512)
     assert rel_l2(h, ref) < TOL_H_L2
+
+
+TOL_G_L2 = 3e-2   # gradients: same norm-relative metric; bf16 operands on both MMA sides
+
+
+@pytest.mark.parametrize("name", ["bottleneck_s320_dh16", "randn_f4_s200_dh16", "randn_f0_s256_dh32",
+                                  "randn_fm2_s130_dh8", "randn_f4_s256_dh64"])
+def test_cell_backward_matches_reference_autograd_golden(name):
+    from xlstm_hved_b200 import ops
+    c = load_golden("cell.pt")[name]
+    leaves = [c[n].float().cuda().requires_grad_() for n in ("q", "k", "v", "ig", "fg")]
+    h = ops.parallel_stabilized_simple(*leaves)
+    grads = torch.autograd.grad(h, leaves, c["dh"].float().cuda())
+    for g, n in zip(grads, ("dq", "dk", "dv", "dig", "dfg")):
+        err = rel_l2(g, c[n])
+        print(name, n, "rel_l2", err, "rel_linf", rel_linf(g, c[n]))
+        assert err < TOL_G_L2, n
+
+
+def test_cell_backward_long_multi_chunk_vs_oracle():
+    from xlstm_hved_b200 import ops
+    B, NH, S, DH = 1, 2, 1500, 16
+    g = torch.Generator().manual_seed(11)
+    q, k, v = [0.5 * torch.randn(B, NH, S, DH, generator=g) for _ in range(3)]
+    ig, fg = torch.randn(B, NH, S, 1, generator=g), 1.0 + torch.randn(B, NH, S, 1, generator=g)
+    dh = torch.randn(B, NH, S, DH, generator=g)
+    leaves = [t.double().requires_grad_() for t in (q, k, v, ig, fg)]
+    ref = torch.autograd.grad(restate.mlstm_chunkwise(*leaves, chunk=250), leaves, dh.double())
+    cl = [t.cuda().requires_grad_() for t in (q, k, v, ig, fg)]
+    got = torch.autograd.grad(ops.parallel_stabilized_simple(*cl), cl, dh.cuda())
+    for a, b, n in zip(got, ref, ("dq", "dk", "dv", "dig", "dfg")):
+        print(n, rel_l2(a, b), rel_linf(a, b))
+        assert rel_l2(a, b) < TOL_G_L2, n

@@ -1,0 +1,429 @@
+// Chunkwise stabilised mLSTM cell, backward -- sm_100a (tcgen05 + TMEM + bulk async copies).
+//
+// Gradient of the reference's parallel_stabilized_simple (vision_lstm.py:48-130) in chunkwise form
+// (formulas: SURVEY.md 8a-note, restated on the CPU in oracle/restate.py::mlstm_backward):
+//
+//   r_t = 1/N_t,  G_t = [dh_t r_t | db_t | 0]          (row-extended output gradient; V is extended by a ones column)
+//   dP = G Vext^T,  D'' = scale*D',  P = S o D'',  dS = dP o D''
+//   dQ = dS K + w (G [C|n]^T)            dK = dS^T Q + fac (Vext R^T)          dV = P^T G + fac (K R)
+//   di_s = k_s.dK_s,  dc_u = q_u.dQ_u - k_u.dK_u,  dlogsigmoid(f) = reverse cumsum(dc),  df = dlf * sigmoid(-f)
+//
+//   phase B1  chunk_rstate  per chunk:  dR_c = sum_t exp(b_t - m_t - lambda_c) (q_t/sqrt(DH)) G_t^T
+//   phase B2  state_scan (reverse)      R entering every chunk from the right, with its log-scale mu
+//   phase B3  chunk_grad    per chunk:  the eight MMAs above, gate-gradient dot products
+//   phase B4  gate_finish   per (b,head): reverse cumsum over the whole sequence
+//
+// The gradient through the row-max stabiliser m_t is dropped (relative effect ~1e-6, see tests).
+#include "mlstm_common.cuh"
+#include "xhved.h"
+
+namespace xhved {
+
+int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
+                      float* m_prev, cudaStream_t st);
+
+// Build the row-extended gradient G_t in place over the dH tile (sG: [128][NE] tile-native) using the H tile.
+template <int DHP>
+__device__ __forceinline__ void build_G_row(unsigned char* sG, const unsigned char* sH, int t, float m, float den, float eps) {
+  const float flo = __expf(-m);
+  const float nrm = fmaxf(fabsf(den), flo) + eps;
+  const float r = 1.f / nrm;
+  float dhh = 0.f;
+#pragma unroll
+  for (int cg = 0; cg < DHP / 8; ++cg) {
+    uint4* pg = reinterpret_cast<uint4*>(sG + tile_off16(kL, t, cg));
+    const uint4 ug = *pg;
+    const uint4 uh = *reinterpret_cast<const uint4*>(sH + tile_off16(kL, t, cg));
+    const float2 g0 = unpack_bf16x2(ug.x), g1 = unpack_bf16x2(ug.y), g2 = unpack_bf16x2(ug.z), g3 = unpack_bf16x2(ug.w);
+    const float2 h0 = unpack_bf16x2(uh.x), h1 = unpack_bf16x2(uh.y), h2 = unpack_bf16x2(uh.z), h3 = unpack_bf16x2(uh.w);
+    dhh += g0.x * h0.x + g0.y * h0.y + g1.x * h1.x + g1.y * h1.y + g2.x * h2.x + g2.y * h2.y + g3.x * h3.x + g3.y * h3.y;
+    uint4 o;
+    o.x = pack_bf16x2(g0.x * r, g0.y * r);
+    o.y = pack_bf16x2(g1.x * r, g1.y * r);
+    o.z = pack_bf16x2(g2.x * r, g2.y * r);
+    o.w = pack_bf16x2(g3.x * r, g3.y * r);
+    *pg = o;
+  }
+  const float dn = -dhh * r;
+  const float db = (fabsf(den) > flo) ? (den >= 0.f ? dn : -dn) : 0.f;
+  *reinterpret_cast<uint4*>(sG + tile_off16(kL, t, DHP / 8)) = make_uint4(pack_bf16x2(db, 0.f), 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(sG + tile_off16(kL, t, DHP / 8 + 1)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ------------------------------------------------------------------ phase B1
+template <int DHP>
+__global__ void __launch_bounds__(kThreads) mlstm_chunk_rstate_kernel(const unsigned char* __restrict__ q_tiles,
+                                                                       const unsigned char* __restrict__ dh_tiles,
+                                                                       const unsigned char* __restrict__ h_tiles,
+                                                                       const float* __restrict__ fg, const float* __restrict__ m_in,
+                                                                       const float* __restrict__ den_in, float scale, float eps,
+                                                                       float* __restrict__ dstate, float* __restrict__ g_out,
+                                                                       float* __restrict__ lam_out) {
+  constexpr int NE = ext_cols(DHP);
+  constexpr uint32_t TILE = kL * DHP * 2;
+  constexpr uint32_t TMEM_COLS = next_pow2_cols(NE);
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sQ = smem;                     // 32 KB window (read as a 128-row MN-major A operand)
+  unsigned char* sG = smem + 32768;             // [128][NE]
+  unsigned char* sH = sG + kL * NE * 2;         // [128][DHP]
+  __shared__ __align__(8) uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red[8];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const size_t grow = static_cast<size_t>(tile) * kL + tid;
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, 3 * TILE);
+    bulk_g2s(sQ, q_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+    bulk_g2s(sG, dh_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+    bulk_g2s(sH, h_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
+  }
+  const float lf = log_sigmoid(fg[grow]);
+  const float m = m_in[grow], den = den_in[grow];
+  float g;
+  const float b = block_cumsum128(lf, red, &g);
+  float lam;
+  block_cummax128(b - m, red, &lam);
+  const float wgt = __expf(b - m - lam) * scale;
+  mbar_wait(&bar_load, 0);
+  build_G_row<DHP>(sG, sH, tid, m, den, eps);
+#pragma unroll
+  for (int cg = 0; cg < DHP / 8; ++cg) {
+    uint4* p = reinterpret_cast<uint4*>(sQ + tile_off16(kL, tid, cg));
+    uint4 u = *p;
+    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    u.x = pack_bf16x2(f0.x * wgt, f0.y * wgt);
+    u.y = pack_bf16x2(f1.x * wgt, f1.y * wgt);
+    u.z = pack_bf16x2(f2.x * wgt, f2.y * wgt);
+    u.w = pack_bf16x2(f3.x * wgt, f3.y * wgt);
+    *p = u;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // dR[d][e'] = sum_t Q~[t][d] * G[t][e']
+    umma_gemm(tmem, smem_u32(sQ), 128, kL * 16, smem_u32(sG), 128, kL * 16, umma_idesc(128, NE, true, true), kL, false);
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  if (warp * 32 < DHP) {
+    float* out = dstate + (static_cast<size_t>(tile) * DHP + tid) * NE;
+#pragma unroll
+    for (int c0 = 0; c0 < NE; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      if (tid < DHP) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  if (tid == 0) {
+    g_out[tile] = g;
+    lam_out[tile] = lam;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ phase B3
+template <int DHP>
+struct BwdSmem {
+  static constexpr int NE = ext_cols(DHP);
+  static constexpr uint32_t TILE = kL * DHP * 2;
+  static constexpr uint32_t EXT = kL * NE * 2;
+  static constexpr uint32_t SQ = 0;
+  static constexpr uint32_t SK = SQ + TILE;
+  static constexpr uint32_t SV = SK + TILE;          // Vext [128][NE]
+  static constexpr uint32_t SG = SV + EXT;           // G    [128][NE]
+  static constexpr uint32_t SP = SG + EXT;           // P    [128][128]   (first holds the H tile)
+  static constexpr uint32_t SDS = SP + kL * kL * 2;  // dS   [128][128]
+  static constexpr uint32_t SC = SDS + kL * kL * 2;  // [C|n] entering the chunk   [DHP][NE]
+  static constexpr uint32_t SR = SC + DHP * NE * 2;  // R entering from the right  [DHP][NE]
+  static constexpr uint32_t VCOL = SR + DHP * NE * 2;
+  static constexpr uint32_t TOTAL = VCOL + kL * 4;
+};
+
+template <int DHP>
+__global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
+    const unsigned char* __restrict__ q_tiles, const unsigned char* __restrict__ k_tiles, const unsigned char* __restrict__ v_tiles,
+    const unsigned char* __restrict__ h_tiles, const unsigned char* __restrict__ dh_tiles, const float* __restrict__ ig,
+    const float* __restrict__ fg, const float* __restrict__ m_in, const float* __restrict__ den_in,
+    const unsigned char* __restrict__ states, const float* __restrict__ m_prev, const unsigned char* __restrict__ rstates,
+    const float* __restrict__ mu_next, int nc, float scale, float eps, float* __restrict__ dq, float* __restrict__ dk,
+    float* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out) {
+  using L = BwdSmem<DHP>;
+  constexpr int NE = L::NE;
+  constexpr uint32_t TILE = L::TILE, ST_BYTES = DHP * NE * 2;
+  constexpr uint32_t TMEM_COLS = DHP <= 32 ? 256u : 512u;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *sQ = smem + L::SQ, *sK = smem + L::SK, *sV = smem + L::SV, *sG = smem + L::SG, *sP = smem + L::SP,
+                *sdS = smem + L::SDS, *sC = smem + L::SC, *sR = smem + L::SR;
+  float* vcol = reinterpret_cast<float*>(smem + L::VCOL);
+  __shared__ __align__(8) uint64_t bar_load, bar_mma1, bar_mma2;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int c = tile % nc;
+  const size_t grow = static_cast<size_t>(tile) * kL + tid;
+  const bool has_prev = c > 0, has_next = c < nc - 1;
+
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma1, 1);
+    mbar_init(&bar_mma2, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  write_ext_ones(sV, DHP, tid);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, 5 * TILE + (has_prev ? ST_BYTES : 0) + (has_next ? ST_BYTES : 0));
+    const size_t to = static_cast<size_t>(tile) * TILE;
+    bulk_g2s(sQ, q_tiles + to, TILE, &bar_load);
+    bulk_g2s(sK, k_tiles + to, TILE, &bar_load);
+    bulk_g2s(sV, v_tiles + to, TILE, &bar_load);
+    bulk_g2s(sG, dh_tiles + to, TILE, &bar_load);
+    bulk_g2s(sP, h_tiles + to, TILE, &bar_load);
+    if (has_prev) bulk_g2s(sC, states + static_cast<size_t>(tile) * ST_BYTES, ST_BYTES, &bar_load);
+    if (has_next) bulk_g2s(sR, rstates + static_cast<size_t>(tile) * ST_BYTES, ST_BYTES, &bar_load);
+  }
+  // ---- gate quantities ----
+  const float iv = ig[grow];
+  const float lf = log_sigmoid(fg[grow]);
+  const float m = m_in[grow], den = den_in[grow];
+  float g;
+  const float b = block_cumsum128(lf, red, &g);
+  vcol[tid] = (iv - b) * kLog2e;
+  const float urow = (b - m) * kLog2e + log2f(scale);
+  const float w = has_prev ? __expf(b + m_prev[tile] - m) : 0.f;
+  const float fac = has_next ? __expf(g - b + iv + mu_next[tile]) : 0.f;
+
+  mbar_wait(&bar_load, 0);
+  build_G_row<DHP>(sG, sP, tid, m, den, eps);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // S[t][s] = Q K^T            -> cols [0,128)
+    umma_gemm(tmem, smem_u32(sQ), kL * 16, 128, smem_u32(sK), kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
+    // dP[t][s] = G Vext^T        -> cols [128,256)
+    umma_gemm(tmem + 128, smem_u32(sG), kL * 16, 128, smem_u32(sV), kL * 16, 128, umma_idesc(128, kL, false, false), NE, false);
+    umma_commit(&bar_mma1);
+  }
+  mbar_wait(&bar_mma1, 0);
+  tc_fence_after();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+#pragma unroll 1
+  for (int blk = 0; blk < 4; ++blk) {
+    if (blk <= warp) {
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float sv[16], dp[16];
+        tmem_ld16(tmem + lane_base + blk * 32 + half * 16, sv);
+        tmem_ld16(tmem + lane_base + 128 + blk * 32 + half * 16, dp);
+#pragma unroll
+        for (int j8 = 0; j8 < 2; ++j8) {
+          float p[8], ds[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int s = blk * 32 + half * 16 + j8 * 8 + j;
+            const float d = (s <= tid) ? fast_exp2(urow + vcol[s]) : 0.f;
+            p[j] = sv[j8 * 8 + j] * d;
+            ds[j] = dp[j8 * 8 + j] * d;
+          }
+          const int cg = blk * 4 + half * 2 + j8;
+          *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, cg)) =
+              make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+          *reinterpret_cast<uint4*>(sdS + tile_off16(kL, tid, cg)) =
+              make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, blk * 4 + j8)) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sdS + tile_off16(kL, tid, blk * 4 + j8)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aG = smem_u32(sG), aP = smem_u32(sP), aS = smem_u32(sdS),
+                   aC = smem_u32(sC), aR = smem_u32(sR);
+    // dQ_intra[t][d] = sum_s dS[t][s] K[s][d]
+    umma_gemm(tmem + 0 * DHP, aS, kL * 16, 128, aK, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
+    // dQ_inter[t][d] = sum_e' G[t][e'] Cn[d][e']
+    if (has_prev) umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+    // dK_intra[s][d] = sum_t dS[t][s] Q[t][d]
+    umma_gemm(tmem + 2 * DHP, aS, 128, kL * 16, aQ, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
+    // dK_inter[s][d] = sum_e' Vext[s][e'] R[d][e']
+    if (has_next) umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+    // dV_intra[s][e] = sum_t P[t][s] G[t][e]
+    umma_gemm(tmem + 4 * DHP, aP, 128, kL * 16, aG, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
+    // dV_inter[s][e] = sum_d K[s][d] R[d][e]
+    if (has_next) umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
+    umma_commit(&bar_mma2);
+  }
+  mbar_wait(&bar_mma2, 0);
+  tc_fence_after();
+  // ---- epilogue: combine intra/inter, write dq/dk/dv rows, gate-gradient dot products ----
+  float q_dq = 0.f, k_dk = 0.f;
+  float* dq_row = dq + grow * DHP;
+  float* dk_row = dk + grow * DHP;
+  float* dv_row = dv + grow * DHP;
+#pragma unroll 1
+  for (int c0 = 0; c0 < DHP; c0 += 16) {
+    float a[16], bb[16];
+    // dQ
+    tmem_ld16(tmem + lane_base + 0 * DHP + c0, a);
+    if (has_prev) {
+      tmem_ld16(tmem + lane_base + 1 * DHP + c0, bb);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] += w * bb[i];
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const uint4 u = *reinterpret_cast<const uint4*>(sQ + tile_off16(kL, tid, c0 / 8 + half));
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      const float* x = a + half * 8;
+      q_dq += f0.x * x[0] + f0.y * x[1] + f1.x * x[2] + f1.y * x[3] + f2.x * x[4] + f2.y * x[5] + f3.x * x[6] + f3.y * x[7];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dq_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+    // dK
+    tmem_ld16(tmem + lane_base + 2 * DHP + c0, a);
+    if (has_next) {
+      tmem_ld16(tmem + lane_base + 3 * DHP + c0, bb);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] += fac * bb[i];
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const uint4 u = *reinterpret_cast<const uint4*>(sK + tile_off16(kL, tid, c0 / 8 + half));
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      const float* x = a + half * 8;
+      k_dk += f0.x * x[0] + f0.y * x[1] + f1.x * x[2] + f1.y * x[3] + f2.x * x[4] + f2.y * x[5] + f3.x * x[6] + f3.y * x[7];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dk_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+    // dV
+    tmem_ld16(tmem + lane_base + 4 * DHP + c0, a);
+    if (has_next) {
+      tmem_ld16(tmem + lane_base + 5 * DHP + c0, bb);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] += fac * bb[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dv_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+  }
+  dig[grow] = k_dk;
+  dc_out[grow] = q_dq - k_dk;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ phase B4
+// dlf_u = sum_{t >= u} dc_t over the whole (padded) sequence; dfg = dlf * sigmoid(-fg)
+__global__ void __launch_bounds__(kThreads) mlstm_gate_finish_kernel(const float* __restrict__ dc, const float* __restrict__ fg, int nc,
+                                                                      float* __restrict__ dfg) {
+  __shared__ float red[8];
+  const int bh = blockIdx.x, tid = threadIdx.x;
+  float carry = 0.f;
+  for (int c = nc - 1; c >= 0; --c) {
+    const size_t o = (static_cast<size_t>(bh) * nc + c) * kL + tid;
+    float tot;
+    const float r = block_rcumsum128(dc[o], red, &tot) + carry;
+    const float f = fg[o];
+    dfg[o] = r * (1.f / (1.f + __expf(f)));
+    carry += tot;
+  }
+}
+
+// fp32 (BH, nc*128, dhp) -> (BH, S, dh)
+__global__ void mlstm_unpad_rows_kernel(const float* __restrict__ src, int S, int Sp, int dh, int dhp, float* __restrict__ dst, size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int d = i % dh;
+  const size_t row = i / dh;
+  const int t = row % S;
+  const size_t bh = row / S;
+  dst[i] = src[(bh * Sp + t) * dhp + d];
+}
+
+template <int DHP>
+static int launch_bwd(const void* q, const void* k, const void* v, const float* ig, const float* fg, const void* h, const void* dh_t,
+                      const float* m, const float* den, const void* states, const float* m_prev, int BH, int nc, int dh, float eps,
+                      float* dq, float* dk, float* dv, float* dig, float* dfg, float* ws_dstate, float* ws_g, float* ws_lam,
+                      void* rstates, float* mu_next, float* ws_dc, cudaStream_t st) {
+  constexpr int NE = ext_cols(DHP);
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  const int ntiles = BH * nc;
+  {
+    const size_t smem = 32768 + kL * NE * 2 + kL * DHP * 2;
+    cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_rstate_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mlstm_chunk_rstate_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)dh_t, (const unsigned char*)h,
+                                                                   fg, m, den, scale, eps, ws_dstate, ws_g, ws_lam);
+  }
+  if (int rc = launch_state_scan(DHP, ws_dstate, ws_g, ws_lam, BH, nc, 1, rstates, mu_next, st)) return rc;
+  {
+    const size_t smem = BwdSmem<DHP>::TOTAL;
+    cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_grad_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mlstm_chunk_grad_kernel<DHP><<<ntiles, kThreads, smem, st>>>(
+        (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, (const unsigned char*)h, (const unsigned char*)dh_t, ig, fg,
+        m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, scale, eps, dq, dk, dv, dig, ws_dc);
+  }
+  mlstm_gate_finish_kernel<<<BH, kThreads, 0, st>>>(ws_dc, fg, nc, dfg);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace xhved
+
+using namespace xhved;
+
+extern "C" int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig, const float* fg,
+                               const void* h_tiles, const void* dh_tiles, const float* m, const float* den, const void* states,
+                               const float* m_prev, int BH, int nc, int dh, int dhp, float eps, float* dq, float* dk, float* dv, float* dig,
+                               float* dfg, float* ws_dstate, float* ws_g, float* ws_amax, void* rstates, float* mu_next, float* ws_dc,
+                               void* stream) {
+  if (BH <= 0 || nc <= 0 || dh <= 0 || dh > dhp) return XHVED_ERR_BAD_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dhp) {
+    case 16: return launch_bwd<16>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
+    case 32: return launch_bwd<32>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
+    case 64: return launch_bwd<64>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
+    default: return XHVED_ERR_UNSUPPORTED_DH;   // dhp = 128 backward: not built yet (shared-memory budget)
+  }
+}
+
+extern "C" int xhved_mlstm_unpad_rows(const float* src, int BH, int S, int dh, int dhp, float* dst, void* stream) {
+  if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp) return XHVED_ERR_BAD_SHAPE;
+  const int Sp = (S + kL - 1) / kL * kL;
+  const size_t total = static_cast<size_t>(BH) * S * dh;
+  mlstm_unpad_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, S, Sp, dh, dhp, dst, total);
+  return (int)cudaGetLastError();
+}

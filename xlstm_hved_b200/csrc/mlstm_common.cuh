@@ -74,9 +74,6 @@ __device__ __forceinline__ float block_rcumsum128(float x, float* red, float* to
   return x + off;
 }
 
-// byte offset of the 16-byte group (row r, column group cg) in a tile-native tile with R rows
-__device__ __forceinline__ uint32_t tile_off16(int R, int r, int cg) { return (static_cast<uint32_t>(cg) * R + r) * 16u; }
-
 // write the two "ext" column groups [1,0,...,0 | 0...0] of row r behind a 128-row tile of dhp columns
 __device__ __forceinline__ void write_ext_ones(unsigned char* tile, int dhp, int r) {
   uint4 one = make_uint4(0x00003F80u, 0u, 0u, 0u);  // bf16(1.0) in element 0

@@ -361,6 +361,9 @@ __global__ void mlstm_unpack_kernel(const unsigned char* __restrict__ tiles, int
 }
 
 // ------------------------------------------------------------------ host launchers
+int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
+                      float* m_prev, cudaStream_t st);
+
 template <int DHP>
 static int launch_fwd(const void* q, const void* k, const void* v, const float* ig, const float* fg, int BH, int nc, int dh,
                       float eps, void* h, float* m, float* den, float* ws_dstate, float* ws_g, float* ws_amax, void* states,
@@ -377,10 +380,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
                                                                   ws_dstate, ws_g, ws_amax);
   }
   // phase 2
-  {
-    constexpr int PT = (DHP * NE + 255) / 256;
-    mlstm_state_scan_kernel<DHP, PT><<<BH, 256, 0, st>>>(ws_dstate, ws_g, ws_amax, nc, 0, (unsigned char*)states, m_prev);
-  }
+  if (int rc = launch_state_scan(DHP, ws_dstate, ws_g, ws_amax, BH, nc, 0, states, m_prev, st)) return rc;
   // phase 3
   {
     const size_t smem = 3 * kL * DHP * 2 + kL * kL * 2 + DHP * NE * 2 + kL * sizeof(float);
@@ -389,6 +389,19 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
     mlstm_chunk_out_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v,
                                                                 ig, fg, (const unsigned char*)states, m_prev, nc, scale, eps,
                                                                 (unsigned char*)h, m, den);
+  }
+  return (int)cudaGetLastError();
+}
+
+// state scan launcher shared with the backward pass (reverse = 1 there)
+int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
+                      float* m_prev, cudaStream_t st) {
+  switch (dhp) {
+    case 16: mlstm_state_scan_kernel<16, (16 * 32 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 32: mlstm_state_scan_kernel<32, (32 * 48 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 64: mlstm_state_scan_kernel<64, (64 * 80 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 128: mlstm_state_scan_kernel<128, (128 * 144 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    default: return XHVED_ERR_UNSUPPORTED_DH;
   }
   return (int)cudaGetLastError();
 }

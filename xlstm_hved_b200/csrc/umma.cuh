@@ -155,6 +155,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // ---------------------------------------------------------------- small helpers
+// byte offset of the 16-byte group (row r, column group cg) in a tile-native tile with R rows
+__device__ __forceinline__ uint32_t tile_off16(int R, int r, int cg) { return (static_cast<uint32_t>(cg) * R + r) * 16u; }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

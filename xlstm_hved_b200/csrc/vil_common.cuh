@@ -1,0 +1,41 @@
+// Helpers shared by the ViL pre/post kernels (K2/K3): token geometry, parameter staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "umma.cuh"
+#include "xhved.h"
+
+namespace xhved {
+
+constexpr int kTok = 128;  // tokens per CTA == cell chunk length
+
+struct VilGeom {
+  int B, S, nc, Sp, NH, DH, DHP, reverse;
+  int64_t xsb, xsn, xsc, ysb, ysn, ysc;
+};
+
+__host__ inline int vil_validate(const xhved_vil_shape* sh, VilGeom* g) {
+  if (!sh || sh->B <= 0 || sh->S <= 0) return XHVED_ERR_BAD_SHAPE;
+  const int C = sh->C, E = 2 * C;
+  if (C != 16 && C != 32 && C != 64) return XHVED_ERR_UNSUPPORTED_DIM;
+  if (sh->QB != 4 || sh->NH != 4) return XHVED_ERR_UNSUPPORTED_DIM;  // vision_lstm.py:357,402-405
+  g->B = sh->B, g->S = sh->S, g->nc = (sh->S + kTok - 1) / kTok, g->Sp = g->nc * kTok;
+  g->NH = sh->NH, g->DH = E / sh->NH, g->DHP = g->DH <= 16 ? 16 : g->DH, g->reverse = sh->reverse;
+  g->xsb = sh->x_stride_b, g->xsn = sh->x_stride_n, g->xsc = sh->x_stride_c;
+  g->ysb = sh->y_stride_b, g->ysn = sh->y_stride_n, g->ysc = sh->y_stride_c;
+  return 0;
+}
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// d/dx silu(x) = s + x s (1 - s), s = sigmoid(x)
+__device__ __forceinline__ float dsilu(float x) {
+  const float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+
+__device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace xhved

@@ -174,3 +174,135 @@ def to_tile_native(mat: torch.Tensor) -> torch.Tensor:
     """[R, C] -> bf16 tile-native bytes ((c/8)*R + r, c%8).  Layout helper for tests / diagnostics."""
     R, C = mat.shape
     return mat.to(torch.bfloat16).reshape(R, C // 8, 8).permute(1, 0, 2).contiguous()
+
+
+class CellGradBuffers:
+    def __init__(self, buf: CellBuffers):
+        dev = buf.q.device
+        nt = buf.BH * buf.nc
+        ne = buf.dhp + 16
+        e = lambda *s, dtype=torch.float32: torch.empty(*s, device=dev, dtype=dtype)
+        self.dq = e(buf.BH, buf.Sp, buf.dhp)
+        self.dk = e(buf.BH, buf.Sp, buf.dhp)
+        self.dv = e(buf.BH, buf.Sp, buf.dhp)
+        self.dig = e(buf.BH, buf.Sp)
+        self.dfg = e(buf.BH, buf.Sp)
+        self.rstates = e(nt, buf.dhp * ne, dtype=torch.bfloat16)
+        self.mu_next = e(nt)
+        self.ws_dc = e(buf.BH, buf.Sp)
+
+
+def mlstm_bwd_tiles(buf: CellBuffers, dh_tiles: torch.Tensor, eps: float = 1e-6) -> CellGradBuffers:
+    """Backward of mlstm_fwd_tiles; dh_tiles: bf16 tile-native gradient of h."""
+    lib = _lib.load_library()
+    gb = CellGradBuffers(buf)
+    check(lib.xhved_mlstm_bwd(ptr(buf.q), ptr(buf.k), ptr(buf.v), ptr(buf.ig), ptr(buf.fg), ptr(buf.h), ptr(dh_tiles), ptr(buf.m),
+                              ptr(buf.den), ptr(buf.states), ptr(buf.m_prev), buf.BH, buf.nc, buf.dh, buf.dhp, eps, ptr(gb.dq),
+                              ptr(gb.dk), ptr(gb.dv), ptr(gb.dig), ptr(gb.dfg), ptr(buf.ws_dstate), ptr(buf.ws_g), ptr(buf.ws_amax),
+                              ptr(gb.rstates), ptr(gb.mu_next), ptr(gb.ws_dc), stream()), "xhved_mlstm_bwd")
+    return gb
+
+
+def _unpad_rows(src, BH, S, dh, dhp, shape):
+    lib = _lib.load_library()
+    dst = torch.empty(shape, device=src.device, dtype=torch.float32)
+    check(lib.xhved_mlstm_unpad_rows(ptr(src), BH, S, dh, dhp, ptr(dst), stream()), "xhved_mlstm_unpad_rows")
+    return dst
+
+
+class MLSTMCellFunction(torch.autograd.Function):
+    """parallel_stabilized_simple (vision_lstm.py:48-130) on the chunkwise tcgen05 kernels."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, ig, fg, eps):
+        B, NH, S, DH = q.shape
+        buf = mlstm_pack_inputs(q, k, v, ig, fg)
+        mlstm_fwd_tiles(buf, eps)
+        ctx.buf, ctx.eps, ctx.shape = buf, eps, (B, NH, S, DH)
+        return mlstm_unpack_h(buf, B, NH)
+
+    @staticmethod
+    def backward(ctx, dh):
+        lib = _lib.load_library()
+        buf = ctx.buf
+        B, NH, S, DH = ctx.shape
+        dh_tiles = torch.empty_like(buf.h)
+        check(lib.xhved_mlstm_pack(ptr(_f32c(dh)), buf.BH, S, DH, buf.dhp, ptr(dh_tiles), stream()), "xhved_mlstm_pack")
+        gb = mlstm_bwd_tiles(buf, dh_tiles, ctx.eps)
+        dq = _unpad_rows(gb.dq, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
+        dk = _unpad_rows(gb.dk, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
+        dv = _unpad_rows(gb.dv, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
+        dig = gb.dig.view(B, NH, buf.Sp)[:, :, :S].unsqueeze(-1).contiguous()
+        dfg = gb.dfg.view(B, NH, buf.Sp)[:, :, :S].unsqueeze(-1).contiguous()
+        return dq, dk, dv, dig, dfg, None
+
+
+def parallel_stabilized_simple(queries, keys, values, igate_preact, fgate_preact, lower_triangular_matrix=None,
+                               stabilize_rowwise: bool = True, eps: float = 1e-6):
+    """Drop-in for vision_lstm.py:48-57 (same signature).  The causal mask argument is accepted and ignored
+    (the kernels are causal by construction); only the row-wise stabiliser the reference uses is built."""
+    if not stabilize_rowwise:
+        raise NotImplementedError("stabilize_rowwise=False is never used by XLSTM-HVED and is not built")
+    if not queries.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    out_dtype = queries.dtype
+    h = MLSTMCellFunction.apply(queries.float(), keys.float(), values.float(), igate_preact.float(), fgate_preact.float(), eps)
+    return h.to(out_dtype)
+
+
+# ----------------------------------------------------------------------------- ViL block (K2 + K1 + K3)
+VIL_PARAM_KEYS = ["norm.weight", "layer.proj_up.weight", "layer.conv1d.conv.weight", "layer.conv1d.conv.bias",
+                  "layer.q_proj.weight", "layer.k_proj.weight", "layer.v_proj.weight",
+                  "layer.mlstm_cell.igate.weight", "layer.mlstm_cell.igate.bias",
+                  "layer.mlstm_cell.fgate.weight", "layer.mlstm_cell.fgate.bias",
+                  "layer.mlstm_cell.outnorm.weight", "layer.learnable_skip", "layer.proj_down.weight"]
+
+
+def _param_struct(tensors, cls):
+    st = cls()
+    for name, t in zip(_lib._PARAM_FIELDS, tensors):
+        setattr(st, name, t.data_ptr() if t is not None else None)
+    return st
+
+
+def _token_strides(x_tok: torch.Tensor):
+    """x_tok: a (B,S,C) view (any strides, e.g. the transpose of an NCDHW feature)."""
+    return x_tok.stride(0), x_tok.stride(1), x_tok.stride(2)
+
+
+class VilWorkspace:
+    """Per-call device buffers of the fused ViL block."""
+
+    def __init__(self, B, S, C, device):
+        E = 2 * C
+        self.cell = CellBuffers(B * 4, S, E // 4, device)
+        nc = self.cell.nc
+        self.act = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
+        self.z = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
+
+
+def _shape_struct(x_tok, y_tok, reverse):
+    B, S, C = x_tok.shape
+    sh = _lib.VilShape()
+    sh.B, sh.S, sh.C, sh.NH, sh.QB, sh.reverse = B, S, C, 4, 4, int(bool(reverse))
+    sh.x_stride_b, sh.x_stride_n, sh.x_stride_c = _token_strides(x_tok)
+    sh.y_stride_b, sh.y_stride_n, sh.y_stride_c = _token_strides(y_tok)
+    return sh
+
+
+def vil_block_fwd(x_tok: torch.Tensor, params, reverse: bool, eps: float = 1e-6):
+    """x_tok: (B,S,C) fp32 view; params: the 14 tensors in VIL_PARAM_KEYS order.  Returns (y_tok, workspace)."""
+    lib = _lib.load_library()
+    B, S, C = x_tok.shape
+    ws = VilWorkspace(B, S, C, x_tok.device)
+    # output takes the memory format of the input (NCDHW-backed token view stays NCDHW-backed)
+    y = torch.empty_strided(x_tok.shape, x_tok.stride(), device=x_tok.device, dtype=torch.float32)
+    ps = _param_struct(params, _lib.VilParams)
+    sh = _shape_struct(x_tok, y, reverse)
+    c = ws.cell
+    check(lib.xhved_vil_pre_fwd(ptr(x_tok), ctypes.byref(ps), ctypes.byref(sh), ptr(c.q), ptr(c.k), ptr(c.v), ptr(c.ig), ptr(c.fg),
+                                ptr(ws.act), ptr(ws.z), stream()), "xhved_vil_pre_fwd")
+    mlstm_fwd_tiles(c, eps)
+    check(lib.xhved_vil_post_fwd(ptr(x_tok), ptr(c.h), ptr(ws.act), ptr(ws.z), ctypes.byref(ps), ctypes.byref(sh), ptr(y), stream()),
+          "xhved_vil_post_fwd")
+    return y, ws
