@@ -344,3 +344,43 @@ def poe_backward(mu, logvar, mod_list, g_mu, g_lv, eps: float = 1e-8):
         dT = g_mu * (mu[i] - mu_hat) / Ssum - g_lv / Ssum
         dlv[m] = -dT * T[i] * T[i] * torch.exp(logvar[i])
     return dmu, dlv
+
+
+# --------------------------------------------------------------------------
+# Precision model of the CUDA cell (what "ideal bf16 operands" costs)
+# --------------------------------------------------------------------------
+def _bf16(x):
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def mlstm_forward_backward_bf16_operands(q, k, v, ig, fg, dh, eps: float = 1e-6):
+    """vision_lstm.py:48-130 and its gradient with exactly the operands the sm_100a kernels feed to the
+    tensor cores rounded to bf16 (q, k, v, P = S o D', h, dh/N, db, dS) and everything else exact.
+    Used by the tests to separate kernel bugs (kernel != this) from the unavoidable cost of bf16
+    operands in ill-conditioned regimes (this != fp64 reference)."""
+    B, NH, S, DH = q.shape
+    scale = 1.0 / math.sqrt(DH)
+    q, k, v, dh = _bf16(q), _bf16(k), _bf16(v), _bf16(dh)
+    lf = F.logsigmoid(fg)
+    c = torch.cumsum(lf, dim=-2)
+    logD = c - c.transpose(-2, -1) + ig.transpose(-2, -1)
+    tri = torch.tril(torch.ones(S, S, dtype=torch.bool, device=q.device))
+    logD = torch.where(tri, logD, torch.full_like(logD, -float("inf")))
+    m = logD.max(dim=-1, keepdim=True).values
+    Dm = torch.exp(logD - m) * scale
+    C = (q @ k.transpose(-2, -1)) * Dm
+    den = C.sum(-1, keepdim=True)
+    Cb = _bf16(C)
+    floor = torch.exp(-m)
+    N = torch.maximum(den.abs(), floor) + eps
+    h = _bf16((Cb @ v) / N)
+    dhh = (dh * h).sum(-1, keepdim=True)
+    dn = -dhh / N
+    db = _bf16(torch.where(den.abs() > floor, dn * torch.sign(den), torch.zeros_like(dn)))
+    Gv = _bf16(dh / N)
+    dS = _bf16((Gv @ v.transpose(-2, -1) + db) * Dm)
+    dq, dk, dv = dS @ k, dS.transpose(-2, -1) @ q, Cb.transpose(-2, -1) @ Gv
+    di = (k * dk).sum(-1)
+    dc = (q * dq).sum(-1) - di
+    dlf = torch.flip(torch.cumsum(torch.flip(dc, dims=[-1]), dim=-1), dims=[-1])
+    return h, (dq, dk, dv, di.unsqueeze(-1), dlf.unsqueeze(-1) * torch.sigmoid(-fg))

@@ -76,7 +76,14 @@ def test_cell_long_sequence_32768():
     assert rel_l2(h, ref) < TOL_H_L2
 
 
-TOL_G_L2 = 3e-2   # gradients: same norm-relative metric; bf16 operands on both MMA sides
+# Gradient tolerances.  The kernels round q, k, v (and P, dS, dh/N) to bf16 for the tensor cores.  In the
+# bottleneck regime that costs ~4e-3; for unit-variance random q,k the normaliser sum_s C_ts has mixed signs and
+# rows with |den| near the exp(-m) floor amplify the INPUT rounding of q,k (oracle emulation: 8e-2 on dq for
+# randn_f4_s200_dh16 with nothing but q,k,v rounded).  So: (a) kernel == bf16-operand emulation tightly,
+# (b) kernel vs fp64 reference within the emulation's own error for that regime.
+TOL_G_VS_EMULATION = 1.5e-2
+TOL_G_VS_FP64 = {"bottleneck_s320_dh16": 2e-2, "randn_f0_s256_dh32": 3e-2, "randn_fm2_s130_dh8": 4e-2,
+                 "randn_f4_s256_dh64": 4e-2, "randn_f4_s200_dh16": 1.5e-1}
 
 
 @pytest.mark.parametrize("name", ["bottleneck_s320_dh16", "randn_f4_s200_dh16", "randn_f0_s256_dh32",
@@ -87,18 +94,21 @@ def test_cell_backward_matches_reference_autograd_golden(name):
     leaves = [c[n].float().cuda().requires_grad_() for n in ("q", "k", "v", "ig", "fg")]
     h = ops.parallel_stabilized_simple(*leaves)
     grads = torch.autograd.grad(h, leaves, c["dh"].float().cuda())
-    for g, n in zip(grads, ("dq", "dk", "dv", "dig", "dfg")):
-        err = rel_l2(g, c[n])
-        print(name, n, "rel_l2", err, "rel_linf", rel_linf(g, c[n]))
-        assert err < TOL_G_L2, n
+    _, emu = restate.mlstm_forward_backward_bf16_operands(*[c[n].double() for n in ("q", "k", "v", "ig", "fg", "dh")])
+    for g, e, n in zip(grads, emu, ("dq", "dk", "dv", "dig", "dfg")):
+        err, err_emu = rel_l2(g, c[n]), rel_l2(g, e)
+        print(name, n, "vs fp64 reference", err, "vs bf16-operand emulation", err_emu, "emulation vs reference", rel_l2(e, c[n]))
+        assert err_emu < TOL_G_VS_EMULATION, n
+        assert err < TOL_G_VS_FP64[name], n
 
 
 def test_cell_backward_long_multi_chunk_vs_oracle():
     from xlstm_hved_b200 import ops
     B, NH, S, DH = 1, 2, 1500, 16
     g = torch.Generator().manual_seed(11)
-    q, k, v = [0.5 * torch.randn(B, NH, S, DH, generator=g) for _ in range(3)]
-    ig, fg = torch.randn(B, NH, S, 1, generator=g), 1.0 + torch.randn(B, NH, S, 1, generator=g)
+    q, k, v = [0.06 * torch.randn(B, NH, S, DH, generator=g), 0.06 * torch.randn(B, NH, S, DH, generator=g),
+               0.12 * torch.randn(B, NH, S, DH, generator=g)]                      # bottleneck statistics
+    ig, fg = -0.67 + 0.48 * torch.randn(B, NH, S, 1, generator=g), 0.41 + 1.03 * torch.randn(B, NH, S, 1, generator=g)
     dh = torch.randn(B, NH, S, DH, generator=g)
     leaves = [t.double().requires_grad_() for t in (q, k, v, ig, fg)]
     ref = torch.autograd.grad(restate.mlstm_chunkwise(*leaves, chunk=250), leaves, dh.double())
@@ -106,4 +116,13 @@ def test_cell_backward_long_multi_chunk_vs_oracle():
     got = torch.autograd.grad(ops.parallel_stabilized_simple(*cl), cl, dh.cuda())
     for a, b, n in zip(got, ref, ("dq", "dk", "dv", "dig", "dfg")):
         print(n, rel_l2(a, b), rel_linf(a, b))
-        assert rel_l2(a, b) < TOL_G_L2, n
+        assert rel_l2(a, b) < 2e-2, n
+    # adversarial regime (unit-variance q,k, long memory): kernel must still agree with the bf16-operand emulation
+    q, k, v = [torch.randn(B, NH, S, DH, generator=g) for _ in range(3)]
+    ig, fg = torch.randn(B, NH, S, 1, generator=g), 1.0 + torch.randn(B, NH, S, 1, generator=g)
+    cl = [t.cuda().requires_grad_() for t in (q, k, v, ig, fg)]
+    got = torch.autograd.grad(ops.parallel_stabilized_simple(*cl), cl, dh.cuda())
+    _, emu = restate.mlstm_forward_backward_bf16_operands(*[t.double() for t in (q, k, v, ig, fg, dh)])
+    for a, b, n in zip(got, emu, ("dq", "dk", "dv", "dig", "dfg")):
+        print("adversarial", n, rel_l2(a, b))
+        assert rel_l2(a, b) < 3e-2, n

@@ -21,7 +21,7 @@ struct PreSmem {
   // float offsets
   static constexpr int W_UP = 0;                      // (2E, C)
   static constexpr int XM = W_UP + 2 * E * C;         // (131, E+1)
-  static constexpr int CONV_W = XM + XM_ROWS * XM_LD; // (E, 4)
+  static constexpr int CONV_W = XM + (XM_ROWS * XM_LD + 3) / 4 * 4; // (E, 4), 16-byte aligned
   static constexpr int CONV_B = CONV_W + E * 4;
   static constexpr int WQ = CONV_B + E;               // (E/4, 4, 4) = E*4
   static constexpr int WK = WQ + E * 4;
