@@ -159,10 +159,11 @@ int xhved_vil_post_fwd(const float* x, const void* h_tiles, const float* act, co
 int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
                        const xhved_vil_shape* sh, void* dh_tiles, float* d_act, float* dz, const xhved_vil_grads* g, void* stream);
 /* K2 backward: from dq, dk, dv (fp32 (BH, nc*128, dhp)), dig, dfg (padded), d_act (skip path), dz computes
- * dx (added to the residual gradient dy -> dx, same geometry as x) and accumulates parameter gradients. */
+ * dx = dy + d(branch)/dx (dy and dx both use the y_* strides of sh) and accumulates parameter gradients.
+ * Scratch: ws_dconv, ws_dxmv fp32 (B, nc, E, 128) each. */
 int xhved_vil_pre_bwd(const float* x, const float* dy, const float* dq, const float* dk, const float* dv, const float* dig,
                       const float* dfg, const float* d_act, const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh,
-                      float* dx, const xhved_vil_grads* g, void* stream);
+                      float* dx, const xhved_vil_grads* g, float* ws_dconv, float* ws_dxmv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,3 +39,31 @@ __device__ __forceinline__ void stage(float* dst, const float* __restrict__ src,
 }
 
 }  // namespace xhved
+
+namespace xhved {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// warp-reduce a per-token value and add it into a shared accumulator slot (one smem atomic per warp)
+__device__ __forceinline__ void warp_acc(float* slot, float v) {
+  v = warp_sum_f(v);
+  if ((threadIdx.x & 31) == 0) atomicAdd(slot, v);
+}
+
+// out[a][b] += sum_tok A[tok*lda + a] * Bm[tok*ldb + b]   (a < na, b < nb; ntok rows staged in shared memory)
+// Each thread owns outputs idx = tid, tid + nthreads, ...; consecutive threads take consecutive b.
+__device__ __forceinline__ void outer_accumulate(const float* sA, int lda, int na, const float* sB, int ldb, int nb, int ntok,
+                                                 float* __restrict__ gout) {
+  for (int idx = threadIdx.x; idx < na * nb; idx += blockDim.x) {
+    const int a = idx / nb, b = idx % nb;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < ntok; ++t) acc += sA[t * lda + a] * sB[t * ldb + b];
+    atomicAdd(gout + idx, acc);
+  }
+}
+
+}  // namespace xhved

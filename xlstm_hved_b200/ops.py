@@ -306,3 +306,56 @@ def vil_block_fwd(x_tok: torch.Tensor, params, reverse: bool, eps: float = 1e-6)
     check(lib.xhved_vil_post_fwd(ptr(x_tok), ptr(c.h), ptr(ws.act), ptr(ws.z), ctypes.byref(ps), ctypes.byref(sh), ptr(y), stream()),
           "xhved_vil_post_fwd")
     return y, ws
+
+
+def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float = 1e-6):
+    """Backward of vil_block_fwd.  Returns (dx_tok, [14 parameter gradients in VIL_PARAM_KEYS order])."""
+    lib = _lib.load_library()
+    c = ws.cell
+    dev = x_tok.device
+    if dy_tok.dtype != torch.float32:
+        dy_tok = dy_tok.float()
+    grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
+    ps = _param_struct(params, _lib.VilParams)
+    gs = _param_struct(grads, _lib.VilGrads)
+    dx = torch.empty_strided(dy_tok.shape, dy_tok.stride(), device=dev, dtype=torch.float32)
+    sh = _shape_struct(x_tok, dy_tok, reverse)          # y_* strides describe dy and dx
+    dh_tiles = torch.empty_like(c.h)
+    d_act = torch.empty_like(ws.act)
+    dz = torch.empty_like(ws.z)
+    check(lib.xhved_vil_post_bwd(ptr(dy_tok), ptr(c.h), ptr(ws.act), ptr(ws.z), ctypes.byref(ps), ctypes.byref(sh), ptr(dh_tiles),
+                                 ptr(d_act), ptr(dz), ctypes.byref(gs), stream()), "xhved_vil_post_bwd")
+    gb = mlstm_bwd_tiles(c, dh_tiles, eps)
+    ws_dconv = torch.empty_like(ws.act)
+    ws_dxmv = torch.empty_like(ws.act)
+    check(lib.xhved_vil_pre_bwd(ptr(x_tok), ptr(dy_tok), ptr(gb.dq), ptr(gb.dk), ptr(gb.dv), ptr(gb.dig), ptr(gb.dfg), ptr(d_act),
+                                ptr(dz), ctypes.byref(ps), ctypes.byref(sh), ptr(dx), ctypes.byref(gs), ptr(ws_dconv), ptr(ws_dxmv),
+                                stream()), "xhved_vil_pre_bwd")
+    return dx, grads
+
+
+class VilBlockFunction(torch.autograd.Function):
+    """ViLBlock.forward (vision_lstm.py:494-502) as three fused launches + the chunkwise cell, with backward."""
+
+    @staticmethod
+    def forward(ctx, x_tok, reverse, eps, *params):
+        params = [p.detach() if p.dtype == torch.float32 and p.is_contiguous() else p.detach().float().contiguous() for p in params]
+        y, ws = vil_block_fwd(x_tok, params, reverse, eps)
+        ctx.reverse, ctx.eps, ctx.ws = reverse, eps, ws
+        ctx.save_for_backward(x_tok, *params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_tok, *params = ctx.saved_tensors
+        dx, grads = vil_block_bwd(x_tok, dy, params, ctx.reverse, ctx.ws, ctx.eps)
+        return (dx, None, None, *grads)
+
+
+def vil_block(x_tok: torch.Tensor, params, reverse: bool = False, eps: float = 1e-6) -> torch.Tensor:
+    """x_tok: (B,S,C) view of fp32 CUDA memory (any strides); params in VIL_PARAM_KEYS order."""
+    if not x_tok.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    if x_tok.dtype != torch.float32:
+        x_tok = x_tok.float()
+    return VilBlockFunction.apply(x_tok, bool(reverse), eps, *params)
