@@ -72,7 +72,7 @@ int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z,
  * stabiliser (vision_lstm.py:111) and sum_s C_ts (the argument of :123).
  * Scratch / saved-for-backward buffers, all caller allocated:
  *   ws_dstate  fp32  BH*nc*dhp*(dhp+16)      ws_g, ws_amax  fp32  BH*nc
- *   states     bf16  BH*nc*dhp*(dhp+16)  (state ENTERING each chunk, tile-native [dhp][dhp+16])
+ *   states     bf16  2*BH*nc*dhp*(dhp+16)  (state ENTERING each chunk as a hi/lo pair of tile-native [dhp][dhp+16] tiles)
  *   m_prev     fp32  BH*nc               (its log-scale) */
 int xhved_mlstm_fwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig_padded, const float* fg_padded,
                     int BH, int nc, int dh, int dhp, float eps, void* h_tiles, float* m, float* den, float* ws_dstate,
@@ -80,7 +80,7 @@ int xhved_mlstm_fwd(const void* q_tiles, const void* k_tiles, const void* v_tile
 
 /* Backward.  dh_tiles: bf16 tiles of dL/dh.  states/m_prev/m/den/h_tiles as produced by the forward.
  * Outputs: dq, dk, dv fp32 (BH, nc*128, dhp) row-major; dig, dfg fp32 (BH, nc*128).
- * Scratch: ws_dstate/ws_g/ws_amax as in the forward, rstates bf16 BH*nc*dhp*(dhp+16), mu_next fp32 BH*nc,
+ * Scratch: ws_dstate/ws_g/ws_amax as in the forward, rstates bf16 2*BH*nc*dhp*(dhp+16), mu_next fp32 BH*nc,
  * ws_dc fp32 (BH, nc*128).  The (~1e-6 relative) gradient through the row-max stabiliser is dropped. */
 int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig_padded, const float* fg_padded,
                     const void* h_tiles, const void* dh_tiles, const float* m, const float* den, const void* states,

@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_rstate_kernel(const unsi
   constexpr uint32_t TILE = kL * DHP * 2;
   constexpr uint32_t TMEM_COLS = next_pow2_cols(NE);
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sQ = smem;                     // 32 KB window (read as a 128-row MN-major A operand)
-  unsigned char* sG = smem + 32768;             // [128][NE]
+  unsigned char* sQ = smem;                     // Q~ hi: 32 KB window (read as a 128-row MN-major A operand)
+  unsigned char* sQlo = smem + 32768;           // Q~ lo
+  unsigned char* sG = smem + 65536;             // [128][NE]
   unsigned char* sH = sG + kL * NE * 2;         // [128][DHP]
   __shared__ __align__(8) uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_slot;
@@ -95,17 +96,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_rstate_kernel(const unsi
   const float wgt = __expf(b - m - lam) * scale;
   mbar_wait(&bar_load, 0);
   build_G_row<DHP>(sG, sH, tid, m, den, eps);
-#pragma unroll
-  for (int cg = 0; cg < DHP / 8; ++cg) {
-    uint4* p = reinterpret_cast<uint4*>(sQ + tile_off16(kL, tid, cg));
-    uint4 u = *p;
-    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-    u.x = pack_bf16x2(f0.x * wgt, f0.y * wgt);
-    u.y = pack_bf16x2(f1.x * wgt, f1.y * wgt);
-    u.z = pack_bf16x2(f2.x * wgt, f2.y * wgt);
-    u.w = pack_bf16x2(f3.x * wgt, f3.y * wgt);
-    *p = u;
-  }
+  scale_row_hilo<DHP>(sQ, sQlo, tid, wgt);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -114,6 +105,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_rstate_kernel(const unsi
   if (tid == 0) {
     // dR[d][e'] = sum_t Q~[t][d] * G[t][e']
     umma_gemm(tmem, smem_u32(sQ), 128, kL * 16, smem_u32(sG), 128, kL * 16, umma_idesc(128, NE, true, true), kL, false);
+    umma_gemm(tmem, smem_u32(sQlo), 128, kL * 16, smem_u32(sG), 128, kL * 16, umma_idesc(128, NE, true, true), kL, true);
     umma_commit(&bar_mma);
   }
   mbar_wait(&bar_mma, 0);
@@ -151,9 +143,10 @@ struct BwdSmem {
   static constexpr uint32_t SG = SV + EXT;           // G    [128][NE]
   static constexpr uint32_t SP = SG + EXT;           // P    [128][128]   (first holds the H tile)
   static constexpr uint32_t SDS = SP + kL * kL * 2;  // dS   [128][128]
-  static constexpr uint32_t SC = SDS + kL * kL * 2;  // [C|n] entering the chunk   [DHP][NE]
-  static constexpr uint32_t SR = SC + DHP * NE * 2;  // R entering from the right  [DHP][NE]
-  static constexpr uint32_t VCOL = SR + DHP * NE * 2;
+  static constexpr uint32_t ST = DHP * NE * 2;       // one state tile
+  static constexpr uint32_t SC = SDS + kL * kL * 2;  // [C|n] entering the chunk   [DHP][NE]  hi, lo
+  static constexpr uint32_t SR = SC + 2 * ST;        // R entering from the right  [DHP][NE]  hi, lo
+  static constexpr uint32_t VCOL = SR + 2 * ST;
   static constexpr uint32_t TOTAL = VCOL + kL * 4;
 };
 
@@ -167,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
     float* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out) {
   using L = BwdSmem<DHP>;
   constexpr int NE = L::NE;
-  constexpr uint32_t TILE = L::TILE, ST_BYTES = DHP * NE * 2;
+  constexpr uint32_t TILE = L::TILE, ST1 = L::ST, ST_BYTES = 2 * L::ST;   // hi + lo tiles
   constexpr uint32_t TMEM_COLS = DHP <= 32 ? 256u : 512u;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *sQ = smem + L::SQ, *sK = smem + L::SK, *sV = smem + L::SV, *sG = smem + L::SG, *sP = smem + L::SP,
@@ -275,15 +268,24 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
     // dQ_intra[t][d] = sum_s dS[t][s] K[s][d]
     umma_gemm(tmem + 0 * DHP, aS, kL * 16, 128, aK, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
     // dQ_inter[t][d] = sum_e' G[t][e'] Cn[d][e']
-    if (has_prev) umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+    if (has_prev) {
+      umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+      umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+    }
     // dK_intra[s][d] = sum_t dS[t][s] Q[t][d]
     umma_gemm(tmem + 2 * DHP, aS, 128, kL * 16, aQ, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
     // dK_inter[s][d] = sum_e' Vext[s][e'] R[d][e']
-    if (has_next) umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+    if (has_next) {
+      umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+      umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+    }
     // dV_intra[s][e] = sum_t P[t][s] G[t][e]
     umma_gemm(tmem + 4 * DHP, aP, 128, kL * 16, aG, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
     // dV_inter[s][e] = sum_d K[s][d] R[d][e]
-    if (has_next) umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
+    if (has_next) {
+      umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
+      umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR + ST1, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, true);
+    }
     umma_commit(&bar_mma2);
   }
   mbar_wait(&bar_mma2, 0);
@@ -382,7 +384,7 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   const int ntiles = BH * nc;
   {
-    const size_t smem = 32768 + kL * NE * 2 + kL * DHP * 2;
+    const size_t smem = 65536 + kL * NE * 2 + kL * DHP * 2;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_rstate_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     mlstm_chunk_rstate_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)dh_t, (const unsigned char*)h,

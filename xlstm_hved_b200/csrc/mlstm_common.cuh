@@ -82,4 +82,25 @@ __device__ __forceinline__ void write_ext_ones(unsigned char* tile, int dhp, int
   *reinterpret_cast<uint4*>(tile + tile_off16(kL, r, dhp / 8 + 1)) = zero;
 }
 
+// Scale row r of a [128][DHP] tile by w, writing the product as a bf16 hi + lo pair (hi in place, lo to `lo`).
+template <int DHP>
+__device__ __forceinline__ void scale_row_hilo(unsigned char* hi, unsigned char* lo, int r, float w) {
+#pragma unroll
+  for (int cg = 0; cg < DHP / 8; ++cg) {
+    uint4* p = reinterpret_cast<uint4*>(hi + tile_off16(kL, r, cg));
+    const uint4 u = *p;
+    const float2 f[4] = {unpack_bf16x2(u.x), unpack_bf16x2(u.y), unpack_bf16x2(u.z), unpack_bf16x2(u.w)};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = f[i].x * w, b = f[i].y * w;
+      oh[i] = pack_bf16x2(a, b);
+      const float2 back = unpack_bf16x2(oh[i]);
+      ol[i] = pack_bf16x2(a - back.x, b - back.y);
+    }
+    *p = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(lo + tile_off16(kL, r, cg)) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
 }  // namespace xhved

@@ -25,10 +25,11 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
   constexpr int NE = ext_cols(DHP);
   constexpr uint32_t TILE = kL * DHP * 2;
   constexpr uint32_t TMEM_COLS = next_pow2_cols(NE);
-  // smem: [K tile, read as a 128-row MN-major A operand => 32 KB window][Vext tile]
+  // smem: [K~ hi | K~ lo, each read as a 128-row MN-major A operand => 32 KB window][Vext tile]
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sK = smem;
-  unsigned char* sV = smem + 32768;
+  unsigned char* sKlo = smem + 32768;
+  unsigned char* sV = smem + 65536;
   __shared__ __align__(8) uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8];
@@ -61,18 +62,9 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
   const float wgt = __expf(a - amax) * scale;
 
   mbar_wait(&bar_load, 0);
-  // scale K rows in place: k~_j = exp(a_j - amax) * k_j / sqrt(DH)
-#pragma unroll
-  for (int cg = 0; cg < DHP / 8; ++cg) {
-    uint4* p = reinterpret_cast<uint4*>(sK + tile_off16(kL, tid, cg));
-    uint4 u = *p;
-    float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-    u.x = pack_bf16x2(f0.x * wgt, f0.y * wgt);
-    u.y = pack_bf16x2(f1.x * wgt, f1.y * wgt);
-    u.z = pack_bf16x2(f2.x * wgt, f2.y * wgt);
-    u.w = pack_bf16x2(f3.x * wgt, f3.y * wgt);
-    *p = u;
-  }
+  // scale K rows: k~_j = exp(a_j - amax) * k_j / sqrt(DH), kept as a bf16 hi + lo pair (~16 mantissa bits) so
+  // that the carried state stays consistent with the intra-chunk products (gate gradients)
+  scale_row_hilo<DHP>(sK, sKlo, tid, wgt);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -82,6 +74,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
     // D[d][e'] = sum_j K~[j][d] * Vext[j][e']   (A, B both MN-major views of row-j tiles)
     umma_gemm(tmem, smem_u32(sK), /*lbo*/ 128, /*sbo*/ kL * 16, smem_u32(sV), 128, kL * 16,
               umma_idesc(128, NE, true, true), kL, false);
+    umma_gemm(tmem, smem_u32(sKlo), 128, kL * 16, smem_u32(sV), 128, kL * 16, umma_idesc(128, NE, true, true), kL, true);
     umma_commit(&bar_mma);
   }
   mbar_wait(&bar_mma, 0);
@@ -109,7 +102,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
 
 // ------------------------------------------------------------------ phase 2
 // One CTA per (b,head).  Thread owns elements idx = tid + k*blockDim of the DHP x NE state.
-// Writes, for every chunk c, the state ENTERING chunk c as a bf16 tile-native tile
+// Writes, for every chunk c, the state ENTERING chunk c as a PAIR of bf16 tile-native tiles (hi, lo = residual)
 // [DHP rows (key dim d)][NE cols (value dim e | n | 0)] plus its log-scale m_prev[c].
 // `reverse` runs the same recurrence from the last chunk to the first (backward pass).
 template <int DHP, int PER_THREAD>
@@ -127,13 +120,17 @@ __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __re
     const int c = reverse ? nc - 1 - step : step;
     const size_t tile = static_cast<size_t>(bh) * nc + c;
     // emit the state entering this chunk
-    unsigned char* st = states + tile * (NEL * 2);
+    unsigned char* st = states + tile * (NEL * 4);      // [hi tile | lo tile]
 #pragma unroll
     for (int k = 0; k < PER_THREAD; ++k) {
       const int idx = tid + k * 256;
       if (idx < NEL) {
         const int d = idx / NE, e = idx % NE;
-        *reinterpret_cast<__nv_bfloat16*>(st + tile_off16(DHP, d, e / 8) + (e % 8) * 2) = __float2bfloat16(acc[k]);
+        const __nv_bfloat16 hi = __float2bfloat16(acc[k]);
+        const __nv_bfloat16 lo = __float2bfloat16(acc[k] - __bfloat162float(hi));
+        const uint32_t off = tile_off16(DHP, d, e / 8) + (e % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(st + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(st + NEL * 2 + off) = lo;
       }
     }
     if (tid == 0) m_prev[tile] = m;
@@ -161,7 +158,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
     float* __restrict__ m_out, float* __restrict__ den_out) {
   constexpr int NE = ext_cols(DHP);
   constexpr uint32_t TILE = kL * DHP * 2;
-  constexpr uint32_t ST_BYTES = DHP * NE * 2;
+  constexpr uint32_t ST_BYTES = 2 * DHP * NE * 2;   // hi + lo tiles
   constexpr uint32_t P_BYTES = kL * kL * 2;
   // TMEM columns: S at [0,128); afterwards O_intra at [0,DHP), O_inter at [DHP, DHP+NE)
   constexpr uint32_t TMEM_COLS = next_pow2_cols((2 * DHP + 16) > 128 ? (2 * DHP + 16) : 128);
@@ -260,8 +257,11 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
     // O_intra[t][e] = sum_s P[t][s] V[s][e]      (B = MN-major view of V)
     umma_gemm(tmem, smem_u32(sP), kL * 16, 128, smem_u32(sV), 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
     // O_inter[t][e'] = sum_d Q[t][d] [C|n][d][e'] (B = MN-major view of the state tile)
-    if (has_state)
+    if (has_state) {
       umma_gemm(tmem + DHP, smem_u32(sQ), kL * 16, 128, smem_u32(sS), 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, false);
+      umma_gemm(tmem + DHP, smem_u32(sQ), kL * 16, 128, smem_u32(sS) + ST_BYTES / 2, 128, DHP * 16, umma_idesc(128, NE, false, true),
+                DHP, true);
+    }
     umma_commit(&bar_mma2);
   }
   mbar_wait(&bar_mma2, 0);
@@ -373,7 +373,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
   const int ntiles = BH * nc;
   // phase 1
   {
-    const size_t smem = 32768 + kL * NE * 2;
+    const size_t smem = 65536 + kL * NE * 2;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_state_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     mlstm_chunk_state_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)k, (const unsigned char*)v, ig, fg, nc, scale,
@@ -383,7 +383,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
   if (int rc = launch_state_scan(DHP, ws_dstate, ws_g, ws_amax, BH, nc, 0, states, m_prev, st)) return rc;
   // phase 3
   {
-    const size_t smem = 3 * kL * DHP * 2 + kL * kL * 2 + DHP * NE * 2 + kL * sizeof(float);
+    const size_t smem = 3 * kL * DHP * 2 + kL * kL * 2 + 2 * DHP * NE * 2 + kL * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_out_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     mlstm_chunk_out_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v,

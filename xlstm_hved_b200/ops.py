@@ -133,7 +133,7 @@ class CellBuffers:
         self.ws_dstate = e(nt, self.dhp * ne)
         self.ws_g = e(nt)
         self.ws_amax = e(nt)
-        self.states = e(nt, self.dhp * ne, dtype=bf)
+        self.states = e(nt, 2 * self.dhp * ne, dtype=bf)     # hi/lo pair
         self.m_prev = e(nt)
 
 
@@ -187,7 +187,7 @@ class CellGradBuffers:
         self.dv = e(buf.BH, buf.Sp, buf.dhp)
         self.dig = e(buf.BH, buf.Sp)
         self.dfg = e(buf.BH, buf.Sp)
-        self.rstates = e(nt, buf.dhp * ne, dtype=torch.bfloat16)
+        self.rstates = e(nt, 2 * buf.dhp * ne, dtype=torch.bfloat16)
         self.mu_next = e(nt)
         self.ws_dc = e(buf.BH, buf.Sp)
 
