@@ -207,8 +207,11 @@ struct PreBwdASmem {
   static constexpr int A_WQ = 0, A_WK = E * 4, A_WV = 2 * E * 4, A_CW = 3 * E * 4, A_CB = 4 * E * 4, A_GB = 4 * E * 4 + E;
   static constexpr int ACC_N = A_GB + 8;
   static constexpr int DG = ACC + (ACC_N + 3) / 4 * 4;  // (128, 9): dig[4] | dfg[4] per token
-  static constexpr int ST = DG + kTok * 9;             // (128, E+1) staging of q / k / v per token
-  static constexpr int TOTAL = ST + kTok * (E + 1);
+  // (128, E) staging of q / k / v per token, column-skewed by the row index (conflict-free).  When it fits
+  // (C >= 64) it ALIASES the proj_up weights, which are dead once x_mlstm has been recomputed.
+  static constexpr bool ALIAS = 2 * E * C >= kTok * E;
+  static constexpr int ST = ALIAS ? F::W_UP : DG + kTok * 9;
+  static constexpr int TOTAL = ALIAS ? DG + kTok * 9 : ST + kTok * E;
 };
 
 template <int C>
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(160) vil_pre_bwd_a_kernel(const float* __restr
   }
   __syncthreads();
   float* acc = sm + LB::ACC;
-  float* stg = sm + LB::ST + (is_main ? tid : 0) * (E + 1);
+  float* stg = sm + LB::ST + (is_main ? tid : 0) * E;
   const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
   const float* xm0 = sm + L::XM + (is_main ? tid : 0) * L::XM_LD;
 
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(160) vil_pre_bwd_a_kernel(const float* __restr
           }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) stg[e8 + j] = rowvalid ? (part == 0 ? q8[j] : part == 1 ? k8[j] : v8[j]) : 0.f;
+        for (int j = 0; j < 8; ++j) stg[(e8 + j + tid) & (E - 1)] = rowvalid ? (part == 0 ? q8[j] : part == 1 ? k8[j] : v8[j]) : 0.f;
         if (part == 0) {
           // upstream gradients of q,k,v for these 8 channels (+ the gate paths, vision_lstm.py:305-318)
           const int head = e8 / g.DH, d0 = e8 % g.DH;
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(160) vil_pre_bwd_a_kernel(const float* __restr
       const int hh = idx / E, e = idx % E;
       float a = 0.f;
 #pragma unroll 4
-      for (int t = 0; t < kTok; ++t) a += sm[LB::DG + t * 9 + hh] * sm[LB::ST + t * (E + 1) + e];
+      for (int t = 0; t < kTok; ++t) a += sm[LB::DG + t * 9 + hh] * sm[LB::ST + t * E + ((e + t) & (E - 1))];
       float* dst = (hh < 4 ? gr.igate_weight + hh * 3 * E : gr.fgate_weight + (hh - 4) * 3 * E) + part * E + e;
       atomicAdd(dst, a);
     }
@@ -393,8 +396,8 @@ struct PreBwdBSmem {
   static constexpr int CONV_W = W_UP + 2 * E * C;      // (E, 4)
   static constexpr int NW = CONV_W + E * 4;
   static constexpr int ACC_NW = NW + C;
-  static constexpr int DIN = ACC_NW + C;               // (128, 2E+1)  d[x_mlstm | z]
-  static constexpr int XN = DIN + kTok * (2 * E + 1);  // (128, C+1)   normalised input
+  static constexpr int DIN = ACC_NW + C;               // (128, E+1)   one half of d[x_mlstm | z] at a time
+  static constexpr int XN = DIN + kTok * (E + 1);      // (128, C+1)   normalised input
   static constexpr int TOTAL = XN + kTok * (C + 1);
 };
 
@@ -428,32 +431,41 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_kernel(const float* __rest
 #pragma unroll
   for (int c = 0; c < C; ++c) dxn[c] = 0.f;
   const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
-  float* din = sm + L::DIN + tid * (2 * E + 1);
+  float* din = sm + L::DIN + tid * (E + 1);
+  // two halves of the proj_up output: o in [0,E) = d x_mlstm, o in [E,2E) = dz; the staging buffer is reused
 #pragma unroll 1
-  for (int o = 0; o < 2 * E; ++o) {
-    float d;
-    if (o < E) {
-      // y_{t'} uses x_t with weight w[3 - (t' - t)], t' = t..t+3  (vision_lstm.py:213-221)
-      d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tid);
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+    for (int oo = 0; oo < E; ++oo) {
+      const int o = half * E + oo;
+      float d;
+      if (half == 0) {
+        // y_{t'} uses x_t with weight w[3 - (t' - t)], t' = t..t+3  (vision_lstm.py:213-221)
+        d = __ldg(dxmv + tm_chunk + static_cast<size_t>(oo) * kTok + tid);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int tp = tau + k;
-        if (tp < g.S) {
-          const size_t off = (static_cast<size_t>(b) * g.nc + tp / kTok) * E * kTok + static_cast<size_t>(o) * kTok + (tp % kTok);
-          d += sm[L::CONV_W + o * 4 + 3 - k] * __ldg(dconv + off);
+        for (int k = 0; k < 4; ++k) {
+          const int tp = tau + k;
+          if (tp < g.S) {
+            const size_t off = (static_cast<size_t>(b) * g.nc + tp / kTok) * E * kTok + static_cast<size_t>(oo) * kTok + (tp % kTok);
+            d += sm[L::CONV_W + oo * 4 + 3 - k] * __ldg(dconv + off);
+          }
         }
+      } else {
+        d = __ldg(dz + tm_chunk + static_cast<size_t>(oo) * kTok + tid);
       }
-    } else {
-      d = __ldg(dz + tm_chunk + static_cast<size_t>(o - E) * kTok + tid);
-    }
-    d = valid ? d : 0.f;
-    din[o] = d;
-    const float* w = sm + L::W_UP + o * C;
+      d = valid ? d : 0.f;
+      din[oo] = d;
+      const float* w = sm + L::W_UP + o * C;
 #pragma unroll
-    for (int c = 0; c < C; c += 4) {
-      const float4 w4 = *reinterpret_cast<const float4*>(w + c);
-      dxn[c] += w4.x * d, dxn[c + 1] += w4.y * d, dxn[c + 2] += w4.z * d, dxn[c + 3] += w4.w * d;
+      for (int c = 0; c < C; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + c);
+        dxn[c] += w4.x * d, dxn[c + 1] += w4.y * d, dxn[c + 2] += w4.z * d, dxn[c + 3] += w4.w * d;
+      }
     }
+    __syncthreads();
+    // d proj_up[o][c] += sum_tok din[tok][o] * xn[tok][c]
+    outer_accumulate(sm + L::DIN, E + 1, E, sm + L::XN, C + 1, C, kTok, gr.proj_up_weight + half * E * C);
+    __syncthreads();
   }
   // LayerNorm backward (weight 1+w, no bias): xn = xhat*(1+w)
   float mean_g = 0.f, mean_gx = 0.f;
@@ -478,8 +490,6 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_kernel(const float* __rest
   }
   __syncthreads();
   for (int c = tid; c < C; c += kTok) atomicAdd(gr.norm_weight + c, sm[L::ACC_NW + c]);
-  // d proj_up[o][c] += sum_tok din[tok][o] * xn[tok][c]
-  outer_accumulate(sm + L::DIN, 2 * E + 1, 2 * E, sm + L::XN, C + 1, C, kTok, gr.proj_up_weight);
 }
 
 template <int C>
