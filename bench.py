@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- XLSTM-HVED hot path (ViL-mLSTM block pair + S-MVAE fusion) on B200, fwd+bwd, volumes/s.
+
+One "step" = one pass of the hot path, forward and backward, over a batch of synthetic 128^3 4-modality volumes
+(BASELINE.json configs[1], "single ViL mLSTM block microbench on bottleneck tokens (bidirectional, fwd+bwd)",
+plus the S-MVAE product-of-experts fusion / sampling / KL of the same volumes, which north_star puts on the path):
+
+  per volume:  bottleneck feature (32,16,16,16) = 4096 tokens of dim 32 -> ViLBlock(TOP_LEFT) -> ViLBlock(BOT_RIGHT)
+               (bf16 tensor-core operands, fp32 accumulation), backward to the input and all 28 parameter tensors;
+               4 latent levels (348,160 elements, 4 modality posteriors each) -> PoE(all modalities) -> z -> KL,
+               backward to the posteriors.
+  N > 1:       the batch is sharded (weak scaling, fixed volumes per GPU); the parameter gradients of the two blocks
+               are summed with one flat-bucket NCCL all-reduce per step.
+
+Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = same through the public API
+with host (pinned) inputs copied every step, roofline for the dominant kernel (CUDA-event timed, separate pass),
+cpu_baseline = the oracle port of the reference's algorithm on the host cores (bounded sample).
+`--impl reference` times that CPU port as its own arm.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LEVELS = ((1, 64), (2, 32), (4, 16), (8, 8))      # (latent channels, edge) per level for a 128^3 volume
+DIM, SPATIAL = 32, (16, 16, 16)
+S_TOK = 4096
+NH, DH = 4, 16
+SUBSET_FULL = (0, 1, 2, 3)
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe in B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def randomise_params(block, seed):
+    """utils.init_weights semantics (utils.py:191-215): xavier-normal Linear weights, N(0,1) biases."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in block.named_parameters():
+            if name.endswith(("proj_up.weight", "proj_down.weight", "igate.weight", "fgate.weight")):
+                std = math.sqrt(2.0 / (p.shape[0] + p.shape[1]))
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+            elif name.endswith(("igate.bias", "fgate.bias")):
+                p.copy_(torch.randn(p.shape, generator=g))
+
+
+def synth_inputs(B, seed, device, pin=False):
+    """Seeded synthetic inputs with the statistics observed at the real bottleneck / posteriors."""
+    g = torch.Generator().manual_seed(seed)
+    mk = (lambda *s: torch.empty(*s).pin_memory()) if pin else (lambda *s: torch.empty(*s))
+    x = mk(B, DIM, *SPATIAL).copy_(torch.randn(B, DIM, *SPATIAL, generator=g))
+    mus, lvs = [], []
+    for C, d in LEVELS:
+        mus.append(mk(4, B, C, d, d, d).copy_(1.3 * torch.randn(4, B, C, d, d, d, generator=g)))
+        lvs.append(mk(4, B, C, d, d, d).copy_((1.4 * torch.randn(4, B, C, d, d, d, generator=g)).clamp_(-50, 50)))
+    if device is not None:
+        x = x.to(device)
+        mus = [m.to(device) for m in mus]
+        lvs = [l.to(device) for l in lvs]
+    return x, mus, lvs
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class HotPath:
+    """The hot path of B volumes on one GPU, through the package's public API."""
+
+    def __init__(self, B, device, world):
+        import xlstm_hved_b200 as xh
+        self.xh, self.B, self.device, self.world = xh, B, device, world
+        self.blk_f = xh.ViLBlock(DIM, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
+        self.blk_r = xh.ViLBlock(DIM, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)
+        randomise_params(self.blk_f, 1)
+        randomise_params(self.blk_r, 2)
+        self.blk_f.to(device)
+        self.blk_r.to(device)
+        self.params = list(self.blk_f.parameters()) + list(self.blk_r.parameters())
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=device)
+        g = torch.Generator().manual_seed(7)
+        self.gy = torch.randn(B, DIM, *SPATIAL, generator=g).to(device)          # upstream gradient of the block output
+        self.gz = [torch.randn(1, B, C, d, d, d, generator=g).to(device) for C, d in LEVELS]
+        # device-side (5,B,...) expert tensors: slab 0 is the prior (zeros), slabs 1..4 are filled per step
+        self.mu5 = [torch.zeros(5, B, C, d, d, d, device=device) for C, d in LEVELS]
+        self.lv5 = [torch.zeros(5, B, C, d, d, d, device=device) for C, d in LEVELS]
+        self.x = torch.zeros(B, DIM, *SPATIAL, device=device)
+
+    def load(self, x, mus, lvs):
+        """Copy one batch into the device buffers (H2D when the sources are pinned host tensors)."""
+        self.x.copy_(x, non_blocking=True)
+        for l in range(4):
+            self.mu5[l][1:].copy_(mus[l], non_blocking=True)
+            self.lv5[l][1:].copy_(lvs[l], non_blocking=True)
+
+    def step(self):
+        ops = self.xh.ops
+        # ---- S-MVAE: fusion + sampling + KL in one launch per level, backward in one launch per level
+        kld_total = None
+        for l in range(4):
+            noise = torch.empty_like(self.gz[l]).normal_()                     # RA_HVED.py:743-744 semantics
+            n = self.mu5[l][0].numel()
+            _, _, z, kld = ops.poe_fwd(self.mu5[l], self.lv5[l], [SUBSET_FULL], noise=noise, want_kld=True)
+            ops.poe_bwd(self.mu5[l], self.lv5[l], [SUBSET_FULL], noise=noise, g_z=self.gz[l], kld_scale=[0.2 * 0.5 / n / 4])
+            kld_total = kld[0] * (0.5 / n / 4) if kld_total is None else kld_total + kld[0] * (0.5 / n / 4)
+        # ---- ViL block pair on the NCDHW feature (token view, no transposed copies), forward + backward
+        x = self.x.detach().requires_grad_()
+        tok = x.reshape(self.B, DIM, -1).transpose(-1, -2)
+        y = self.blk_r(self.blk_f(tok))
+        for p in self.params:
+            p.grad = None
+        y.backward(self.gy.reshape(self.B, DIM, -1).transpose(-1, -2))
+        if self.world > 1:
+            import torch.distributed as dist
+            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat)
+            dist.all_reduce(self.flat)
+        return kld_total + y.detach()[0, 0, 0]
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from xlstm_hved_b200 import _lib
+    lib = _lib.load_library()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    hp = HotPath(B, device, world)
+    x, mus, lvs = synth_inputs(B, 1000 + rank, device)
+    hp.load(x, mus, lvs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(W):
+        hp.step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(hp.step, K)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host (pinned) inputs copied in every step, result read back every step
+    hx, hmus, hlvs = synth_inputs(B, 2000 + rank, None, pin=True)
+    h2d = hx.numel() * 4 + sum(m.numel() * 4 for m in hmus) + sum(l.numel() * 4 for l in hlvs)
+    out_host = torch.empty(1).pin_memory()
+
+    def e2e_step():
+        hp.load(hx, hmus, hlvs)
+        out_host.copy_(hp.step().reshape(1), non_blocking=False)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, K)
+    hp.load(x, mus, lvs)
+
+    # ---- per-kernel attribution (separate pass, CUDA events on the launching stream)
+    nk = lib.xhved_profile_kernel_count()
+    names = [lib.xhved_profile_kernel_name(i).decode() for i in range(nk)]
+    ms_arr, cnt_arr = (ctypes.c_float * nk)(), (ctypes.c_int * nk)()
+    lib.xhved_profile_enable(1)
+    lib.xhved_profile_read(ms_arr, cnt_arr, nk)
+    for _ in range(K):
+        hp.step()
+    lib.xhved_profile_read(ms_arr, cnt_arr, nk)
+    lib.xhved_profile_enable(0)
+    kern = {names[i]: (ms_arr[i], cnt_arr[i]) for i in range(nk) if cnt_arr[i]}
+    launches = sum(c for _, c in kern.values())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    tokens_heads = B * NH * S_TOK
+    # algorithmic (useful, causal-half) FLOP per launch of each cell kernel, chunk L = 128
+    L = 128
+    flops = {
+        "mlstm_chunk_grad": tokens_heads * (5 * L * DH + 6 * DH * DH),      # S, dP, dQ, dK, dV causal halves + 3 inter products
+        "mlstm_chunk_out": tokens_heads * (2 * L * DH + 2 * DH * DH),       # S, PV causal halves + q.[C|n]
+        "mlstm_chunk_state": tokens_heads * (2 * DH * DH),
+        "mlstm_chunk_rstate": tokens_heads * (2 * DH * DH),
+    }
+    n_lat = sum(C * d ** 3 for C, d in LEVELS) * B
+    bytes_ = {
+        "poe_fwd": n_lat * (40 + 8 + 4 + 4),      # 5 x (mu, logvar) in, mu/logvar out, noise in, z out
+        "poe_bwd": n_lat * (40 + 4 + 4 + 40),     # experts, noise, g_z in; 5 x (dmu, dlogvar) out
+    }
+    top = max(kern.items(), key=lambda kv: kv[1][0])
+    tname, (tms, tcnt) = top
+    per_launch_ms = tms / tcnt
+    if tname in flops:
+        ach = flops[tname] / (per_launch_ms * 1e-3) / 1e12
+        roof = {"kernel": tname, "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["tf"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tf"], 5), "traffic": None, "peak_source": peaks["src"] + ", sustained bf16",
+                "algorithmic_flop_per_launch": flops[tname], "avg_launch_ms": round(per_launch_ms, 5)}
+    else:
+        # per-level launches move different byte counts: use the per-step total over the 4 levels
+        per_step_ms = tms / K
+        nbytes = bytes_.get(tname)
+        ach = (nbytes / (per_step_ms * 1e-3) / 1e9) if nbytes else None
+        roof = {"kernel": tname, "bound": "hbm", "achieved": round(ach, 1) if ach else None, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": round(ach / peaks["hbm"], 4) if ach else None, "traffic": None, "peak_source": peaks["src"],
+                "algorithmic_bytes_per_step": nbytes, "ms_per_step": round(per_step_ms, 5)}
+    shares = {k: round(v[0] / sum(m for m, _ in kern.values()), 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    secondary = {}
+    for k in ("mlstm_chunk_out", "poe_fwd", "poe_bwd"):
+        if k in kern and k != tname:
+            if k in flops:
+                a = flops[k] / (kern[k][0] / kern[k][1] * 1e-3) / 1e12
+                secondary[k] = {"bound": "tensor", "achieved_tflops": round(a, 3), "frac": round(a / peaks["tf"], 5)}
+            else:
+                a = bytes_[k] / (kern[k][0] / K * 1e-3) / 1e9
+                secondary[k] = {"bound": "hbm", "achieved_gbs": round(a, 1), "frac": round(a / peaks["hbm"], 4)}
+
+    cpu = cpu_reference_arm(steps=args.cpu_steps, warmup=1) if world == 1 and not args.no_cpu else None
+    vols = world * B * K
+    line = {
+        "metric": "128^3 4-modality volumes/sec fwd+bwd (ViL-mLSTM block pair + S-MVAE fusion hot path)",
+        "value": round(vols / (ms_total * 1e-3), 2), "unit": "volumes/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 tensor-core operands, fp32 accumulate/gates/PoE", "data": "synthetic (seeded, bottleneck statistics)",
+        "config": {"workload": "configs[1]: bidirectional ViLBlock pair on bottleneck tokens (dim 32, S=4096, NH=4, DH=16) fwd+bwd "
+                               "+ S-MVAE PoE/reparam/KL fwd+bwd over the 4 latent levels of the same volumes",
+                   "volumes_per_gpu": B, "global_batch": world * B, "tokens_per_volume": S_TOK,
+                   "latent_elements_per_volume": sum(C * d ** 3 for C, d in LEVELS),
+                   "l2_policy": f"inputs larger than L2 (PoE posteriors {h2d / 2**20:.0f} MiB per step > 126 MiB)",
+                   "collective": "1 flat-bucket NCCL all-reduce of the 28 ViL parameter gradients per step" if world > 1 else "none"},
+        "e2e": {"value": round(vols / (ms_e2e * 1e-3), 2), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / K, 4)},
+        "gpu_launches": launches, "kernel_time_share": shares, "roofline": roof, "roofline_secondary": secondary,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU / reference arm
+def cpu_hot_path_one_volume(params_f, params_r, x, mus, lvs, gy, gzs):
+    """The reference's algorithm for the same hot path on the CPU (oracle port: fp32, O(S^2) parallel cell with the
+    reference's op sequence, PoE as buildingblocks.py:853-866), forward + backward through autograd."""
+    from oracle import restate
+    x = x.clone().requires_grad_()
+    tok = x.reshape(1, DIM, -1).transpose(-1, -2)
+    y = restate.vil_block(tok, params_f, reverse=False, cell=restate.mlstm_parallel_reference_cost)
+    y = restate.vil_block(y, params_r, reverse=True, cell=restate.mlstm_parallel_reference_cost)
+    loss = (y * gy.reshape(1, DIM, -1).transpose(-1, -2)).sum()
+    for l in range(4):
+        mm = mus[l].clone().requires_grad_()
+        ll = lvs[l].clone().requires_grad_()
+        mu5 = torch.cat([torch.zeros_like(mm[:1]), mm], 0)
+        lv5 = torch.cat([torch.zeros_like(ll[:1]), restate.clip_logvar(ll)], 0)
+        a, b = restate.poe(mu5, lv5, SUBSET_FULL)
+        z = restate.reparametrize(a, b, torch.randn_like(a))
+        loss = loss + (z * gzs[l][0]).sum() + 0.2 * restate.kl_to_prior(a, b) / 4
+    loss.backward()
+    return float(loss)
+
+
+def cpu_reference_arm(steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    import xlstm_hved_b200 as xh
+    keys = xh.ops.VIL_PARAM_KEYS
+    blocks = []
+    for seed, direction in ((1, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT), (2, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)):
+        blk = xh.ViLBlock(DIM, direction)
+        randomise_params(blk, seed)
+        sd = blk.state_dict()
+        blocks.append({k: sd[k].clone().requires_grad_() for k in keys})
+    x, mus, lvs = synth_inputs(1, 1000, None)
+    g = torch.Generator().manual_seed(7)
+    gy = torch.randn(1, DIM, *SPATIAL, generator=g)
+    gzs = [torch.randn(1, 1, C, d, d, d, generator=g) for C, d in LEVELS]
+    for _ in range(warmup):
+        cpu_hot_path_one_volume(blocks[0], blocks[1], x, mus, lvs, gy, gzs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_hot_path_one_volume(blocks[0], blocks[1], x, mus, lvs, gy, gzs)
+    dt = time.perf_counter() - t0
+    return {"value": round(steps / dt, 4), "unit": "volumes/s", "cores": cores, "threads": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} volume(s), one per step, same hot path fwd+bwd (oracle port of the reference's O(S^2) parallel cell "
+                      f"+ PoE, fp32, torch CPU), {dt / steps:.2f} s/volume", "seconds_per_volume": round(dt / steps, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W = args.steps, args.warmup
+    K = min(K, 6)                       # bounded: one volume per step, a few seconds each on the host cores
+    cpu = cpu_reference_arm(steps=K, warmup=min(W, 1))
+    line = {
+        "impl": "reference",
+        "metric": "128^3 4-modality volumes/sec fwd+bwd (ViL-mLSTM block pair + S-MVAE fusion hot path)",
+        "value": cpu["value"], "unit": "volumes/s", "n_gpus": world, "steps": K, "warmup": min(W, 1),
+        "ms_per_step": round(1e3 / cpu["value"], 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32 (reference precision)", "data": "synthetic (seeded, bottleneck statistics)",
+        "config": {"workload": "configs[1]: bidirectional ViLBlock pair on bottleneck tokens (dim 32, S=4096, NH=4, DH=16) fwd+bwd "
+                               "+ S-MVAE PoE/reparam/KL fwd+bwd over the 4 latent levels; bounded sample: 1 volume per step",
+                   "volumes_per_step": 1},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="volumes per GPU per step")
+    ap.add_argument("--cpu-steps", type=int, default=2, help="volumes timed for cpu_baseline")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,14 @@ int xhved_mlstm_unpack(const void* tiles, int BH, int S, int dh, int dhp, float*
 /* fp32 (BH, nc*128, dhp) row-major -> (BH, S, dh) contiguous (gradients of the stand-alone entry point) */
 int xhved_mlstm_unpad_rows(const float* src, int BH, int S, int dh, int dhp, float* dst, void* stream);
 
+/* Optional per-kernel timing with CUDA events on the launching stream (off by default; used by bench.py to
+ * attribute time to kernels).  xhved_profile_read synchronises the device, returns accumulated milliseconds
+ * and launch counts per kernel id since the last read, and resets. */
+int xhved_profile_enable(int on);
+int xhved_profile_kernel_count(void);
+const char* xhved_profile_kernel_name(int id);
+int xhved_profile_read(float* ms, int* launches, int n);
+
 /* Diagnostic: D[128][N] = A * B^T through tcgen05 with tile-native operands (see mlstm_fwd.cu). */
 int xhved_umma_selftest(const void* a_tile, const void* b_tile, int N, int K, int a_mn, int b_mn, float* d, void* stream);
 

@@ -1,0 +1,101 @@
+"""End-to-end drop-in parity: the UNMODIFIED reference model (baseline/_ref or /root/reference, when present) next
+to the same model with patch_model() applied, on the GPU.  North-star bar: identical (p>0.5) mask per channel and
+identical channel argmax on >= 99.9% of voxels (the model outputs sigmoid probabilities of 3 nested regions,
+RA_HVED.py:483-484); PoE mu/logvar within 1e-3.  Skipped where no reference tree exists; the boundary fixtures
+(tests/golden/model_boundary.pt) cover the same tensors without it."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, rel_linf
+from oracle import ref_loader
+
+pytestmark = pytest.mark.gpu
+
+
+def test_model_boundary_fixture_vil_and_poe():
+    """Tensors recorded at the hot-path boundary of a real reference forward (48^3 volume, subset 12)."""
+    import xlstm_hved_b200 as xh
+    c = load_golden("model_boundary.pt")
+    wrap = xh.ViLLayer3D(dim=32).cuda()
+    wrap.load_state_dict(c["vil_state_dict"], strict=True)
+    with torch.no_grad():
+        y = wrap(c["vil"]["x"].cuda())
+    br, br_ref = y.cpu() - c["vil"]["x"], c["vil"]["y"] - c["vil"]["x"]
+    assert rel_l2(br, br_ref) < 2e-2
+    poe = xh.ProductOfExperts()
+    for rec in c["poe"]:
+        a, b = poe(rec["mu"].cuda(), rec["logvar"].cuda(), tuple(rec["subset"]))
+        assert rel_linf(a, rec["pd_mu"]) < 1e-3 and rel_linf(b, rec["pd_logvar"]) < 1e-3
+
+
+@pytest.fixture(scope="module")
+def model():
+    if ref_loader.find_reference() is None:
+        pytest.skip("no reference tree on this machine (baseline/_ref absent)")
+    m = ref_loader.build_model(f_maps=4, seed=1)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("size,subset", [((128, 128, 128), 14), ((64, 96, 64), 7)])
+def test_full_model_segmentation_parity(model, size, subset):
+    import xlstm_hved_b200 as xh
+    ns = ref_loader.load_reference()
+    torch.manual_seed(5)
+    x = torch.rand(1, 4, *size, device="cuda")
+    present = ns.RA_HVED.SUBSETS_MODALITIES[subset]
+    for m in range(4):
+        if m not in present:
+            x[:, m] = 0                                     # evaluation.py:306-307
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        seg_ref, _ = model(x, [subset], valid=True)
+        counts = xh.patch_model(model)
+        try:
+            seg_new, _ = model(x, [subset], valid=True)
+        finally:
+            xh.unpatch_model(model)
+    assert counts["ViLBlock"] == 1 and counts["ProductOfExperts"] == 1
+    same_mask = ((seg_ref > 0.5) == (seg_new > 0.5)).float().mean().item()
+    same_arg = (seg_ref.argmax(1) == seg_new.argmax(1)).float().mean().item()
+    print(size, subset, "mask agreement", same_mask, "argmax agreement", same_arg, "max |dp|", (seg_ref - seg_new).abs().max().item())
+    assert same_mask >= 0.999 and same_arg >= 0.999
+
+
+def test_full_model_training_gradients_parity(model):
+    """seg + recon + KL losses, sampling on: parameter gradients of the patched model vs the stock one."""
+    import xlstm_hved_b200 as xh
+    ns = ref_loader.load_reference()
+    model.train()
+    try:
+        x = torch.rand(1, 4, 64, 64, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+
+        def run():
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(11)                          # same epsilon draws on both paths
+            with contextlib.redirect_stdout(io.StringIO()):
+                seg, (mu_list, lv_list), recon = model(x, [14], recon=True)
+                kld = sum(ns.loss.compute_KLD(mu_list[l], lv_list[l], [14]) for l in range(4)) / 4
+            loss = seg.mean() + 0.2 * ((recon[0] - x) ** 2).mean() + 0.2 * kld
+            loss.backward()
+            return loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+        loss_ref, g_ref = run()
+        xh.patch_model(model)
+        try:
+            loss_new, g_new = run()
+        finally:
+            xh.unpatch_model(model)
+        assert abs(loss_ref - loss_new) < 1e-3 * abs(loss_ref)
+        assert set(g_ref) == set(g_new)
+        worst = 0.0
+        for n in g_ref:
+            if g_ref[n].norm() == 0:
+                continue
+            e = rel_l2(g_new[n], g_ref[n])
+            worst = max(worst, e)
+            assert e < 5e-2, (n, e)
+        print("loss", loss_ref, loss_new, "worst parameter-gradient rel_l2", worst)
+    finally:
+        model.eval()

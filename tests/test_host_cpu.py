@@ -1,0 +1,62 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/xhved.h declares, the mirror
+modules keep the reference's state_dict keys, patching binds and restores, and nothing computes without CUDA."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from xlstm_hved_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "xhved.h")).read()
+    declared = set(re.findall(r"\b(xhved_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load_library()                       # raises if the .so is missing or lacks a symbol
+    assert lib.xhved_version() >= 100
+    names = [lib.xhved_profile_kernel_name(i).decode() for i in range(lib.xhved_profile_kernel_count())]
+    assert "mlstm_chunk_grad" in names and "poe_fwd" in names
+
+
+def test_mirror_modules_keep_reference_state_dict_keys():
+    import xlstm_hved_b200 as xh
+    c = load_golden("vil_wrapper.pt")
+    wrap = xh.ViLLayer3D(dim=32)
+    assert set(wrap.state_dict().keys()) == set(c["state_dict"].keys())
+    wrap.load_state_dict(c["state_dict"], strict=True)
+    for k, v in wrap.state_dict().items():
+        assert v.shape == c["state_dict"][k].shape, k
+    blk = load_golden("vil_block.pt")["dim64_s140_rev"]
+    b = xh.ViLBlock(dim=64, direction=xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)
+    b.load_state_dict(blk["state_dict"], strict=True)
+
+
+def test_no_cpu_fallback():
+    import xlstm_hved_b200 as xh
+    with pytest.raises(RuntimeError):
+        xh.parallel_stabilized_simple(*[torch.zeros(1, 1, 4, 16) for _ in range(3)], torch.zeros(1, 1, 4, 1), torch.zeros(1, 1, 4, 1))
+    with pytest.raises(RuntimeError):
+        xh.ViLLayer3D(dim=32)(torch.zeros(1, 32, 2, 2, 2))
+    with pytest.raises(RuntimeError):
+        xh.ProductOfExperts()(torch.zeros(5, 1, 1, 2, 2, 2), torch.zeros(5, 1, 1, 2, 2, 2), (0, 1))
+
+
+def test_patch_and_unpatch_reference_model():
+    from oracle import ref_loader
+    if ref_loader.find_reference() is None:
+        pytest.skip("reference tree not present on this machine")
+    import xlstm_hved_b200 as xh
+    model = ref_loader.build_model()
+    counts = xh.patch_model(model)
+    assert counts["ViLBlock"] == 1 and counts["ProductOfExperts"] == 1 and counts["ProductOfExperts2"] == 1
+    assert "forward" in model.mViL.vil.__dict__
+    keys = set(model.state_dict().keys())
+    xh.unpatch_model(model)
+    assert "forward" not in model.mViL.vil.__dict__ and set(model.state_dict().keys()) == keys
+    ns = ref_loader.load_reference()
+    assert ns.RA_HVED.reparametrize.__module__ == "RA_HVED"
+    with torch.no_grad():
+        seg, _ = model.eval()(torch.rand(1, 4, 32, 32, 32), [14], valid=True)   # stock path still runs
+    assert seg.shape == (1, 3, 32, 32, 32)

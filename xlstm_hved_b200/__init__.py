@@ -3,6 +3,7 @@
 CUDA only: importing is cheap, but every op needs libxhved.so (python -m xlstm_hved_b200.build)
 and a CUDA device; there is no CPU / PyTorch-eager fallback.
 """
-from . import ops  # noqa: F401
-
-__all__ = ["ops"]
+from . import modules, ops  # noqa: F401
+from .modules import (ProductOfExperts, ProductOfExperts2, SequenceTraversal, ViLBlock, ViLLayer, ViLLayer3D,  # noqa: F401
+                      clip, compute_KLD, parallel_stabilized_simple, reparametrize)
+from .patch import patch_model, unpatch_model  # noqa: F401

@@ -50,6 +50,10 @@ SYMBOLS = {
     "xhved_mlstm_pack_gates": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_unpack": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_mlstm_unpad_rows": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "xhved_profile_enable": [c_int],
+    "xhved_profile_kernel_count": [],
+    "xhved_profile_kernel_name": [c_int],
+    "xhved_profile_read": [POINTER(c_float), POINTER(c_int), c_int],
     "xhved_umma_selftest": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_vil_pre_fwd": [c_void_p, POINTER(VilParams), POINTER(VilShape)] + [c_void_p] * 8,
     "xhved_vil_post_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p],
@@ -78,7 +82,7 @@ def load_library() -> ctypes.CDLL:
                 missing.append(name)
                 continue
             fn.argtypes = argtypes
-            fn.restype = c_int
+            fn.restype = ctypes.c_char_p if name == "xhved_profile_kernel_name" else c_int
         if missing:
             raise RuntimeError(f"{LIB_PATH} lacks symbols declared in include/xhved.h: {missing}; rebuild it")
         _lib = lib

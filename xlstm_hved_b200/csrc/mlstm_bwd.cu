@@ -15,6 +15,7 @@
 //
 // The gradient through the row-max stabiliser m_t is dropped (relative effect ~1e-6, see tests).
 #include "mlstm_common.cuh"
+#include "prof.cuh"
 #include "xhved.h"
 
 namespace xhved {
@@ -387,6 +388,7 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
     const size_t smem = 65536 + kL * NE * 2 + kL * DHP * 2;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_rstate_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ProfScope ps(K_CHUNK_RSTATE, st);
     mlstm_chunk_rstate_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)dh_t, (const unsigned char*)h,
                                                                    fg, m, den, scale, eps, ws_dstate, ws_g, ws_lam);
   }
@@ -395,11 +397,15 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
     const size_t smem = BwdSmem<DHP>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_grad_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ProfScope ps(K_CHUNK_GRAD, st);
     mlstm_chunk_grad_kernel<DHP><<<ntiles, kThreads, smem, st>>>(
         (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, (const unsigned char*)h, (const unsigned char*)dh_t, ig, fg,
         m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, scale, eps, dq, dk, dv, dig, ws_dc);
   }
-  mlstm_gate_finish_kernel<<<BH, kThreads, 0, st>>>(ws_dc, fg, nc, dfg);
+  {
+    ProfScope ps(K_GATE_FINISH, st);
+    mlstm_gate_finish_kernel<<<BH, kThreads, 0, st>>>(ws_dc, fg, nc, dfg);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -426,6 +432,7 @@ extern "C" int xhved_mlstm_unpad_rows(const float* src, int BH, int S, int dh, i
   if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp) return XHVED_ERR_BAD_SHAPE;
   const int Sp = (S + kL - 1) / kL * kL;
   const size_t total = static_cast<size_t>(BH) * S * dh;
+  ProfScope ps(K_UNPACK, static_cast<cudaStream_t>(stream));
   mlstm_unpad_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, S, Sp, dh, dhp, dst, total);
   return (int)cudaGetLastError();
 }

@@ -11,6 +11,7 @@
 // q/k/v/h tiles are bf16 in the tile-native layout (umma.cuh); gates, stabiliser m,
 // normaliser input den and all accumulators are fp32.
 #include "mlstm_common.cuh"
+#include "prof.cuh"
 #include "xhved.h"
 
 namespace xhved {
@@ -376,6 +377,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
     const size_t smem = 65536 + kL * NE * 2;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_state_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ProfScope ps(K_CHUNK_STATE, st);
     mlstm_chunk_state_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)k, (const unsigned char*)v, ig, fg, nc, scale,
                                                                   ws_dstate, ws_g, ws_amax);
   }
@@ -386,6 +388,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
     const size_t smem = 3 * kL * DHP * 2 + kL * kL * 2 + 2 * DHP * NE * 2 + kL * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_out_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ProfScope ps(K_CHUNK_OUT, st);
     mlstm_chunk_out_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v,
                                                                 ig, fg, (const unsigned char*)states, m_prev, nc, scale, eps,
                                                                 (unsigned char*)h, m, den);
@@ -396,6 +399,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
 // state scan launcher shared with the backward pass (reverse = 1 there)
 int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
                       float* m_prev, cudaStream_t st) {
+  ProfScope ps(K_STATE_SCAN, st);
   switch (dhp) {
     case 16: mlstm_state_scan_kernel<16, (16 * 32 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
     case 32: mlstm_state_scan_kernel<32, (32 * 48 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
@@ -427,18 +431,21 @@ extern "C" int xhved_mlstm_fwd(const void* q_tiles, const void* k_tiles, const v
 extern "C" int xhved_mlstm_pack(const float* src, int BH, int S, int dh, int dhp, void* tiles, void* stream) {
   if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp || dhp % 16) return XHVED_ERR_BAD_SHAPE;
   const int nc = (S + kL - 1) / kL;
+  ProfScope ps(K_PACK, static_cast<cudaStream_t>(stream));
   mlstm_pack_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>(src, S, dh, dhp, nc, (unsigned char*)tiles);
   return (int)cudaGetLastError();
 }
 extern "C" int xhved_mlstm_pack_gates(const float* ig, const float* fg, int BH, int S, float* ig_padded, float* fg_padded, void* stream) {
   if (BH <= 0 || S <= 0) return XHVED_ERR_BAD_SHAPE;
   const int nc = (S + kL - 1) / kL;
+  ProfScope ps(K_PACK, static_cast<cudaStream_t>(stream));
   mlstm_pack_gates_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>(ig, fg, S, nc, ig_padded, fg_padded);
   return (int)cudaGetLastError();
 }
 extern "C" int xhved_mlstm_unpack(const void* tiles, int BH, int S, int dh, int dhp, float* dst, void* stream) {
   if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp || dhp % 16) return XHVED_ERR_BAD_SHAPE;
   const int nc = (S + kL - 1) / kL;
+  ProfScope ps(K_UNPACK, static_cast<cudaStream_t>(stream));
   mlstm_unpack_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>((const unsigned char*)tiles, S, dh, dhp, nc, dst);
   return (int)cudaGetLastError();
 }

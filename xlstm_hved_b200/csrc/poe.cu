@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "prof.cuh"
 #include "xhved.h"
 
 namespace xhved {
@@ -302,6 +303,7 @@ extern "C" int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, in
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
   const bool v4 = (n % 4 == 0) && (expert_stride % 4 == 0) && (!drop || per_sample % 4 == 0) && aligned16(mu) && aligned16(logvar) &&
                   aligned16(out_mu) && aligned16(out_logvar) && (!noise || (aligned16(noise) && aligned16(out_z)));
+  ProfScope ps(K_POE_FWD, st_);
   if (v4)
     poe_fwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar,
                                                         noise, out_z, kld_out);
@@ -323,6 +325,7 @@ extern "C" int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, in
   const bool v4 = (n % 4 == 0) && (expert_stride % 4 == 0) && (!drop || per_sample % 4 == 0) && aligned16(mu) && aligned16(logvar) &&
                   aligned16(d_mu) && aligned16(d_logvar) && (!g_mu || aligned16(g_mu)) && (!g_logvar || aligned16(g_logvar)) &&
                   (!g_z || (aligned16(g_z) && aligned16(noise)));
+  ProfScope ps(K_POE_BWD, st_);
   if (v4)
     poe_bwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise,
                                                         g_z, kld_scale != nullptr, d_mu, d_logvar);
@@ -335,6 +338,7 @@ extern "C" int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, in
 extern "C" int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream) {
   if (n <= 0 || !mu || !logvar || !noise || !z) return XHVED_ERR_BAD_ARG;
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  ProfScope ps(K_REPARAM_FWD, st_);
   if (n % 4 == 0 && aligned16(mu) && aligned16(logvar) && aligned16(noise) && aligned16(z))
     reparam_fwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(mu, logvar, noise, n, z);
   else
@@ -345,6 +349,7 @@ extern "C" int xhved_reparam_bwd(const float* logvar, const float* noise, const 
                                  void* stream) {
   if (n <= 0 || !logvar || !noise || !g_z || !d_mu || !d_logvar) return XHVED_ERR_BAD_ARG;
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  ProfScope ps(K_REPARAM_BWD, st_);
   if (n % 4 == 0 && aligned16(logvar) && aligned16(noise) && aligned16(g_z) && aligned16(d_mu) && aligned16(d_logvar))
     reparam_bwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(logvar, noise, g_z, n, d_mu, d_logvar);
   else

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "umma.cuh"
+#include "prof.cuh"
 #include "xhved.h"
 
 namespace xhved {

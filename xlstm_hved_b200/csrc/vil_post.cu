@@ -91,6 +91,7 @@ static int launch_post_fwd(const float* x, const void* h, const float* act, cons
   const size_t smem = PostSmem<C>::TOTAL * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(vil_post_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  ProfScope ps(K_VIL_POST_FWD, st);
   vil_post_fwd_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y);
   return (int)cudaGetLastError();
 }
@@ -206,6 +207,7 @@ static int launch_post_bwd(const float* dy, const void* h, const float* act, con
   const size_t smem = PostBwdSmem<C>::TOTAL * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  ProfScope ps(K_VIL_POST_BWD, st);
   vil_post_bwd_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g, (unsigned char*)dh, d_act, dz, *gr);
   return (int)cudaGetLastError();
 }

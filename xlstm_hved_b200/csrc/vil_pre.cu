@@ -190,6 +190,7 @@ static int launch_pre_fwd(const float* x, const xhved_vil_params* p, const VilGe
   const size_t smem = PreSmem<C>::TOTAL * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(vil_pre_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  ProfScope ps(K_VIL_PRE_FWD, st);
   vil_pre_fwd_kernel<C><<<g.B * g.nc, 160, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z);
   return (int)cudaGetLastError();
 }
@@ -500,12 +501,14 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* dq, cons
     const size_t smem = PreBwdASmem<C>::TOTAL * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ProfScope ps(K_VIL_PRE_BWD_A, st);
     vil_pre_bwd_a_kernel<C><<<g.B * g.nc, 160, smem, st>>>(x, *p, g, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv, *gr);
   }
   {
     const size_t smem = PreBwdBSmem<C>::TOTAL * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_b_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    ProfScope ps(K_VIL_PRE_BWD_B, st);
     vil_pre_bwd_b_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr);
   }
   return (int)cudaGetLastError();

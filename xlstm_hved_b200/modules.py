@@ -1,0 +1,308 @@
+"""Host-side mirror of the reference's module API for the hot path (same class names, constructor arguments,
+parameter names / state_dict keys and forward signatures), backed by the sm_100a kernels.
+
+Reference classes mirrored (paths relative to the reference root):
+  UxLSTM/nnunetv2/nets/vision_lstm.py : SequenceTraversal (15-17), LinearHeadwiseExpand (133-175), CausalConv1d
+      (178-221), LayerNorm (224-268), MultiHeadLayerNorm (271-287), MatrixLSTMCell (290-348), ViLLayer (351-477),
+      ViLBlock (480-506), parallel_stabilized_simple (48-130)
+  UxLSTM/nnunetv2/nets/UxLSTMEnc_3d.py : ViLLayer (42-87)  -> here ``ViLLayer3D``
+  buildingblocks.py : ProductOfExperts (846-866), ProductOfExperts2 (868-886)
+  RA_HVED.py        : reparametrize (741-747), clip (749-753), SUBSETS_MODALITIES (733-738)
+  loss.py           : KL_divergence (29-40), compute_KLD (85-115)
+
+The containers below own the parameters exactly as the reference does, so ``load_state_dict(strict=True)``
+round-trips checkpoints of the reference modules.  Compute happens only at the fused entry points
+(ViLBlock / ViLLayer3D / parallel_stabilized_simple / ProductOfExperts(2) / reparametrize / compute_KLD); the
+small sub-modules are parameter holders and refuse to run stand-alone rather than fall back to PyTorch math.
+"""
+from __future__ import annotations
+
+import math
+from enum import Enum
+
+import torch
+from torch import nn
+
+from . import ops
+from .ops import SUBSETS_MODALITIES, parallel_stabilized_simple  # noqa: F401  (re-exported drop-in)
+
+
+class SequenceTraversal(Enum):
+    ROWWISE_FROM_TOP_LEFT = "rowwise_from_top_left"
+    ROWWISE_FROM_BOT_RIGHT = "rowwise_from_bot_right"
+
+
+def _is_reverse(direction) -> bool:
+    value = getattr(direction, "value", direction)
+    if value == SequenceTraversal.ROWWISE_FROM_TOP_LEFT.value:
+        return False
+    if value == SequenceTraversal.ROWWISE_FROM_BOT_RIGHT.value:
+        return True
+    raise NotImplementedError(direction)       # vision_lstm.py:423-424
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError(f"{type(self).__name__} is a parameter holder of the fused ViL block; "
+                           "call ViLBlock / ViLLayer3D (there is no per-op PyTorch fallback)")
+
+
+class LinearHeadwiseExpand(_Holder):
+    def __init__(self, dim, num_heads, bias=False):
+        super().__init__()
+        assert dim % num_heads == 0 and not bias
+        self.dim, self.num_heads = dim, num_heads
+        d = dim // num_heads
+        self.weight = nn.Parameter(torch.empty(num_heads, d, d))
+        self.bias = None
+        nn.init.normal_(self.weight.data, mean=0.0, std=math.sqrt(2 / 5 / d))
+
+
+class CausalConv1d(_Holder):
+    def __init__(self, dim, kernel_size=4, bias=True):
+        super().__init__()
+        assert kernel_size == 4 and bias, "the fused kernel implements the reference's k=4, bias=True conv"
+        self.dim, self.kernel_size, self.bias, self.pad = dim, kernel_size, bias, kernel_size - 1
+        self.conv = nn.Conv1d(dim, dim, kernel_size=kernel_size, padding=self.pad, groups=dim, bias=bias)
+
+
+class LayerNorm(_Holder):
+    def __init__(self, ndim=-1, weight=True, bias=False, eps=1e-5, residual_weight=True):
+        super().__init__()
+        assert weight and not bias and residual_weight and eps == 1e-5
+        self.weight = nn.Parameter(torch.zeros(ndim))
+        self.bias = None
+        self.eps, self.residual_weight, self.ndim = eps, residual_weight, ndim
+
+
+class MultiHeadLayerNorm(LayerNorm):
+    pass
+
+
+class MatrixLSTMCell(_Holder):
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.dim, self.num_heads = dim, num_heads
+        self.igate = nn.Linear(3 * dim, num_heads)
+        self.fgate = nn.Linear(3 * dim, num_heads)
+        self.outnorm = MultiHeadLayerNorm(ndim=dim, weight=True, bias=False)
+        self.causal_mask_cache = {}
+        self.reset_parameters()
+
+    def reset_parameters(self):                      # vision_lstm.py:341-348
+        nn.init.zeros_(self.fgate.weight)
+        with torch.no_grad():
+            self.fgate.bias.copy_(torch.linspace(3.0, 6.0, self.fgate.bias.shape[0]))
+        nn.init.zeros_(self.igate.weight)
+        nn.init.normal_(self.igate.bias, mean=0.0, std=0.1)
+
+
+class ViLLayer(_Holder):
+    """Inner layer (vision_lstm.py:351-477): owns the projections, conv, cell and skip parameters."""
+
+    def __init__(self, dim, direction, expansion=2, qkv_block_size=4, proj_bias=False, conv_bias=True, kernel_size=4):
+        super().__init__()
+        if dim % qkv_block_size != 0:
+            qkv_block_size = 2
+        assert expansion == 2 and not proj_bias and conv_bias and kernel_size == 4
+        self.dim, self.direction, self.expansion, self.qkv_block_size = dim, direction, expansion, qkv_block_size
+        self.proj_bias, self.conv_bias, self.kernel_size = proj_bias, conv_bias, kernel_size
+        inner = expansion * dim
+        nh = inner // qkv_block_size
+        self.proj_up = nn.Linear(dim, 2 * inner, bias=False)
+        self.q_proj = LinearHeadwiseExpand(inner, nh)
+        self.k_proj = LinearHeadwiseExpand(inner, nh)
+        self.v_proj = LinearHeadwiseExpand(inner, nh)
+        self.conv1d = CausalConv1d(inner, kernel_size=kernel_size, bias=conv_bias)
+        self.mlstm_cell = MatrixLSTMCell(inner, num_heads=qkv_block_size)
+        self.learnable_skip = nn.Parameter(torch.ones(inner))
+        self.proj_down = nn.Linear(inner, dim, bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):                      # vision_lstm.py:455-477
+        nn.init.normal_(self.proj_up.weight, mean=0.0, std=math.sqrt(2 / (5 * self.dim)))
+        nn.init.normal_(self.proj_down.weight, mean=0.0, std=2 / math.sqrt(self.dim))
+        nn.init.ones_(self.learnable_skip)
+        for proj in (self.q_proj, self.k_proj, self.v_proj):
+            nn.init.normal_(proj.weight, mean=0.0, std=math.sqrt(2 / (5 * self.dim)))
+        self.mlstm_cell.reset_parameters()
+
+
+class DropPath(nn.Sequential):
+    """vision_lstm_util.py:133-209 with the only configuration the hot path uses (drop_prob = 0)."""
+
+    def __init__(self, *args, drop_prob: float = 0.0, scale_by_keep: bool = True, stochastic_drop_prob: bool = False):
+        super().__init__(*args)
+        assert 0.0 <= drop_prob < 1.0
+        self._drop_prob = drop_prob
+        self.scale_by_keep, self.stochastic_drop_prob = scale_by_keep, stochastic_drop_prob
+
+    @property
+    def drop_prob(self):
+        return self._drop_prob
+
+
+def vil_block_params(block):
+    """The 14 parameter tensors of a (reference or mirror) ViLBlock in kernel order (ops.VIL_PARAM_KEYS)."""
+    lay, cell = block.layer, block.layer.mlstm_cell
+    return [block.norm.weight, lay.proj_up.weight, lay.conv1d.conv.weight, lay.conv1d.conv.bias, lay.q_proj.weight,
+            lay.k_proj.weight, lay.v_proj.weight, cell.igate.weight, cell.igate.bias, cell.fgate.weight, cell.fgate.bias,
+            cell.outnorm.weight, lay.learnable_skip, lay.proj_down.weight]
+
+
+def vil_block_forward(block, x: torch.Tensor) -> torch.Tensor:
+    """ViLBlock.forward (vision_lstm.py:499-502): x + layer(norm(x)) for a (B,S,C) token tensor or view."""
+    dp = getattr(block.drop_path, "drop_prob", 0.0)
+    if dp != 0.0 and block.training:
+        raise NotImplementedError("stochastic depth (drop_path > 0 in training) is never used by XLSTM-HVED")
+    if block.layer.qkv_block_size != 4 or getattr(block.norm, "bias", None) is not None:
+        raise NotImplementedError("fused ViL block: qkv_block_size must be 4 and the norm bias-free (reference defaults)")
+    return ops.vil_block(x, vil_block_params(block), reverse=_is_reverse(block.direction))
+
+
+class ViLBlock(nn.Module):
+    def __init__(self, dim, direction, drop_path=0.0, norm_bias=False):
+        super().__init__()
+        assert not norm_bias
+        self.dim, self.direction, self.norm_bias = dim, direction, norm_bias
+        self.drop_path = DropPath(drop_prob=drop_path)
+        self.norm = LayerNorm(ndim=dim, weight=True, bias=norm_bias)
+        self.layer = ViLLayer(dim=dim, direction=direction)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return vil_block_forward(self, x)
+
+
+def vil_wrapper_forward(wrapper, x: torch.Tensor) -> torch.Tensor:
+    """Outer 3-D ViLLayer.forward (UxLSTMEnc_3d.py:54-63, 77-87): NCDHW feature -> token view -> block -> NCDHW.
+    No transposed copies are made: the kernels read and write the strided token view in place."""
+    if wrapper.channel_token:
+        raise NotImplementedError("channel_token=True is never used by XLSTM-HVED (RA_HVED.py:314)")
+    with torch.autocast(device_type="cuda", enabled=False):
+        if x.dtype != torch.float32:
+            x = x.float()                                  # the reference up-casts fp16 (UxLSTMEnc_3d.py:78-79)
+        B, d_model = x.shape[:2]
+        assert d_model == wrapper.dim
+        img_dims = x.shape[2:]
+        x = x.contiguous()
+        x_flat = x.reshape(B, d_model, -1).transpose(-1, -2)
+        x_vil = wrapper.vil(x_flat)
+        return x_vil.transpose(-1, -2).reshape(B, d_model, *img_dims)
+
+
+class ViLLayer3D(nn.Module):
+    """Mirror of UxLSTMEnc_3d.ViLLayer (42-87).  ``norm`` is never used in forward but owns two parameters that
+    must stay in the state_dict (UxLSTMEnc_3d.py:47)."""
+
+    def __init__(self, dim, d_state=16, d_conv=4, expand=2, channel_token=False):
+        super().__init__()
+        self.dim = dim
+        self.norm = nn.LayerNorm(dim)
+        self.vil = ViLBlock(dim=dim, direction=SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
+        self.channel_token = channel_token
+
+    def forward(self, x):
+        return vil_wrapper_forward(self, x)
+
+
+# --------------------------------------------------------------------------------------------- S-MVAE
+class _PoEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu5, logvar5, subset, drop, eps):
+        pm, pl, _, _ = ops.poe_fwd(mu5, logvar5, [subset], drop=drop, eps=eps)
+        ctx.save_for_backward(mu5, logvar5)
+        ctx.subset, ctx.drop, ctx.eps = subset, drop, eps
+        return pm[0], pl[0]
+
+    @staticmethod
+    def backward(ctx, g_mu, g_lv):
+        mu5, logvar5 = ctx.saved_tensors
+        d_mu, d_lv = ops.poe_bwd(mu5, logvar5, [ctx.subset], g_mu=g_mu.contiguous()[None], g_logvar=g_lv.contiguous()[None],
+                                 drop=ctx.drop, eps=ctx.eps)
+        return d_mu, d_lv, None, None, None
+
+
+def _stack5(t):
+    if isinstance(t, (list, tuple)):
+        t = torch.stack(list(t), 0)
+    if t.shape[0] != 5:
+        raise ValueError("expected (5, B, ...) experts with the prior at index 0 (RA_HVED.py:576-580)")
+    return t.float().contiguous()
+
+
+def product_of_experts(mu_list, logvar_list, mod_list, eps=1e-8):
+    """ProductOfExperts.forward (buildingblocks.py:853-866)."""
+    return _PoEFunction.apply(_stack5(mu_list), _stack5(logvar_list), tuple(int(m) for m in mod_list), None, eps)
+
+
+def product_of_experts_drop(mu, logvar, drop, eps=1e-8):
+    """ProductOfExperts2.forward (buildingblocks.py:875-886), including its in-place zeroing of ``mu``."""
+    mu5, lv5 = _stack5(mu), _stack5(logvar)
+    out = _PoEFunction.apply(mu5, lv5, (0, 1, 2, 3), drop.to(torch.uint8).contiguous(), eps)
+    if isinstance(mu, torch.Tensor):
+        with torch.no_grad():                              # the reference overwrites mu[m+1] (879-880)
+            for m in range(drop.shape[1]):
+                mu[m + 1][drop[:, m].bool()] = 0
+    return out
+
+
+class ProductOfExperts(nn.Module):
+    def forward(self, mu_list, logvar_list, mod_list, eps=1e-8):
+        return product_of_experts(mu_list, logvar_list, mod_list, eps)
+
+
+class ProductOfExperts2(nn.Module):
+    def forward(self, mu, logvar, drop, eps=1e-8):
+        return product_of_experts_drop(mu, logvar, drop, eps)
+
+
+class _ReparamFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, noise):
+        ctx.save_for_backward(logvar, noise)
+        return ops.reparam_fwd(mu, logvar, noise)
+
+    @staticmethod
+    def backward(ctx, g):
+        logvar, noise = ctx.saved_tensors
+        d_mu, d_lv = ops.reparam_bwd(logvar, noise, g.contiguous())
+        return d_mu, d_lv, None
+
+
+def reparametrize(mu, logvar, valid=False):
+    """RA_HVED.py:741-747.  The noise comes from the same torch call, generator, shape and order as the
+    reference's ``std.data.new(std.size()).normal_()`` so seeded runs draw identical samples."""
+    if valid:
+        return mu
+    noise = torch.empty_like(mu, dtype=torch.float32).normal_()
+    return _ReparamFunction.apply(mu.float().contiguous(), logvar.float().contiguous(), noise)
+
+
+def clip(input):
+    """RA_HVED.py:749-753 (stays a plain clamp: it is applied while the experts are concatenated)."""
+    return torch.clamp(input, min=-50.0, max=50.0)
+
+
+class _KLDFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu5, logvar5, subsets):
+        _, _, _, kld = ops.poe_fwd(mu5, logvar5, subsets, want_kld=True)
+        n = mu5[0].numel()
+        ctx.save_for_backward(mu5, logvar5)
+        ctx.subsets, ctx.scale = subsets, 0.5 / (n * len(subsets))
+        return kld.sum() * ctx.scale
+
+    @staticmethod
+    def backward(ctx, g):
+        mu5, logvar5 = ctx.saved_tensors
+        d_mu, d_lv = ops.poe_bwd(mu5, logvar5, ctx.subsets, kld_scale=[ctx.scale] * len(ctx.subsets))
+        return d_mu * g, d_lv * g, None
+
+
+def compute_KLD(mu_list, logvar_list, subset_index_list=[14], choices=[0, 1, 2, 3]):
+    """loss.py:85-115: mean over the requested subsets of KL(PoE posterior || prior).  Inputs are the (B,5,...)
+    tensors the model returns (RA_HVED.py:582-583); fusion, KL and the reduction run in one launch."""
+    mu5 = mu_list.transpose(1, 0).float().contiguous()
+    lv5 = logvar_list.transpose(1, 0).float().contiguous()
+    subsets = [SUBSETS_MODALITIES[i] for i in range(len(SUBSETS_MODALITIES)) if i in subset_index_list]
+    return _KLDFunction.apply(mu5, lv5, subsets)
