@@ -82,6 +82,7 @@ def test_full_model_training_gradients_parity(model):
             return loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
 
         loss_ref, g_ref = run()
+        _, g_ref2 = run()                                  # run-to-run noise of the reference itself (atomics)
         xh.patch_model(model)
         try:
             loss_new, g_new = run()
@@ -89,13 +90,17 @@ def test_full_model_training_gradients_parity(model):
             xh.unpatch_model(model)
         assert abs(loss_ref - loss_new) < 1e-3 * abs(loss_ref)
         assert set(g_ref) == set(g_new)
-        worst = 0.0
+        worst, checked = 0.0, 0
         for n in g_ref:
-            if g_ref[n].norm() == 0:
+            # gradients that are mathematically zero (conv biases in front of InstanceNorm ...) are pure rounding
+            # noise even between two runs of the stock model: only parameters the reference reproduces are compared
+            if g_ref[n].norm() == 0 or rel_l2(g_ref2[n], g_ref[n]) > 1e-3:
                 continue
             e = rel_l2(g_new[n], g_ref[n])
-            worst = max(worst, e)
+            worst, checked = max(worst, e), checked + 1
             assert e < 5e-2, (n, e)
-        print("loss", loss_ref, loss_new, "worst parameter-gradient rel_l2", worst)
+        vil = [n for n in g_ref if n.startswith("mViL.vil.")]
+        assert len(vil) == 14 and checked > 100
+        print("loss", loss_ref, loss_new, "parameters checked", checked, "worst parameter-gradient rel_l2", worst)
     finally:
         model.eval()

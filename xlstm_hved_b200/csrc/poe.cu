@@ -55,15 +55,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int V>
+template <int V, int NS>
 __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t n,
                                                        int64_t stride, PoeSubsets ss, const uint8_t* __restrict__ drop,
                                                        int64_t per_sample, float eps, float* __restrict__ out_mu,
                                                        float* __restrict__ out_lv, const float* __restrict__ noise,
                                                        float* __restrict__ out_z, float* __restrict__ kld_out) {
-  float kld_acc[15];
+  float kld_acc[NS];
 #pragma unroll
-  for (int s = 0; s < 15; ++s) kld_acc[s] = 0.f;
+  for (int s = 0; s < NS; ++s) kld_acc[s] = 0.f;
   const int64_t nvec = n / V;
   for (int64_t iv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
        iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
       }
     }
 #pragma unroll
-    for (int s = 0; s < 15; ++s) {
+    for (int s = 0; s < NS; ++s) {
       if (s < ss.n) {
         const uint32_t mask = ss.mask[s];
         float om[V], ol[V];
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
     __shared__ float red[8][15];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int s = 0; s < 15; ++s) {
+    for (int s = 0; s < NS; ++s) {
       if (s < ss.n) {
         const float v = warp_sum(kld_acc[s]);
         if (lane == 0) red[warp][s] = v;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
   }
 }
 
-template <int V>
+template <int V, int NS>
 __global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t n,
                                                        int64_t stride, PoeSubsets ss, const uint8_t* __restrict__ drop,
                                                        int64_t per_sample, float eps, const float* __restrict__ g_mu,
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ 
       }
     }
 #pragma unroll
-    for (int s = 0; s < 15; ++s) {
+    for (int s = 0; s < NS; ++s) {
       if (s < ss.n) {
         const uint32_t mask = (ss.mask[s] << 1) | 1u;  // bit e = expert e, prior always in
         float gm[V], gl[V];
@@ -304,12 +304,17 @@ extern "C" int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, in
   const bool v4 = (n % 4 == 0) && (expert_stride % 4 == 0) && (!drop || per_sample % 4 == 0) && aligned16(mu) && aligned16(logvar) &&
                   aligned16(out_mu) && aligned16(out_logvar) && (!noise || (aligned16(noise) && aligned16(out_z)));
   ProfScope ps(K_POE_FWD, st_);
-  if (v4)
-    poe_fwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar,
-                                                        noise, out_z, kld_out);
-  else
-    poe_fwd_kernel<1><<<grid_for(n), 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar, noise,
-                                                    out_z, kld_out);
+#define XHVED_POE_FWD(V, NS, GRID) \
+  poe_fwd_kernel<V, NS><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar, noise, out_z, kld_out)
+  if (v4) {
+    if (n_subsets == 1) XHVED_POE_FWD(4, 1, grid_for(n / 4));
+    else if (n_subsets <= 4) XHVED_POE_FWD(4, 4, grid_for(n / 4));
+    else XHVED_POE_FWD(4, 15, grid_for(n / 4));
+  } else {
+    if (n_subsets == 1) XHVED_POE_FWD(1, 1, grid_for(n));
+    else XHVED_POE_FWD(1, 15, grid_for(n));
+  }
+#undef XHVED_POE_FWD
   return (int)cudaGetLastError();
 }
 
@@ -326,12 +331,18 @@ extern "C" int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, in
                   aligned16(d_mu) && aligned16(d_logvar) && (!g_mu || aligned16(g_mu)) && (!g_logvar || aligned16(g_logvar)) &&
                   (!g_z || (aligned16(g_z) && aligned16(noise)));
   ProfScope ps(K_POE_BWD, st_);
-  if (v4)
-    poe_bwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise,
-                                                        g_z, kld_scale != nullptr, d_mu, d_logvar);
-  else
-    poe_bwd_kernel<1><<<grid_for(n), 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise, g_z,
-                                                    kld_scale != nullptr, d_mu, d_logvar);
+#define XHVED_POE_BWD(V, NS, GRID)                                                                                                  \
+  poe_bwd_kernel<V, NS><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise, g_z, \
+                                               kld_scale != nullptr, d_mu, d_logvar)
+  if (v4) {
+    if (n_subsets == 1) XHVED_POE_BWD(4, 1, grid_for(n / 4));
+    else if (n_subsets <= 4) XHVED_POE_BWD(4, 4, grid_for(n / 4));
+    else XHVED_POE_BWD(4, 15, grid_for(n / 4));
+  } else {
+    if (n_subsets == 1) XHVED_POE_BWD(1, 1, grid_for(n));
+    else XHVED_POE_BWD(1, 15, grid_for(n));
+  }
+#undef XHVED_POE_BWD
   return (int)cudaGetLastError();
 }
 
