@@ -155,10 +155,11 @@ typedef struct xhved_vil_shape {
   int64_t y_stride_b, y_stride_n, y_stride_c;
 } xhved_vil_shape;
 
-/* K2: LayerNorm -> proj_up -> causal conv -> SiLU -> q,k,v (tiles) + gates (padded) + act, z.
- * act, z: fp32 (B, nc, E, 128) token-minor, traversal order. */
+/* K2: LayerNorm -> proj_up -> causal conv -> SiLU -> q,k,v (tiles) + gates (padded) + act, z, xm.
+ * act (conv activation), z (gate branch), xm (pre-conv x_mlstm, kept for the backward): fp32 (B, nc, E, 128) token-minor,
+ * traversal order. */
 int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, const xhved_vil_shape* sh, void* q_tiles, void* k_tiles,
-                      void* v_tiles, float* ig_padded, float* fg_padded, float* act, float* z, void* stream);
+                      void* v_tiles, float* ig_padded, float* fg_padded, float* act, float* z, float* xm, void* stream);
 /* K3: outnorm(h) + skip*act, * silu(z), proj_down, + x residual -> y (same geometry family as x). */
 int xhved_vil_post_fwd(const float* x, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
                        const xhved_vil_shape* sh, float* y, void* stream);

@@ -176,3 +176,68 @@ __device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.f) - l
 constexpr float kLog2e = 1.4426950408889634f;
 
 }  // namespace xhved
+
+namespace xhved {
+
+// ---------------------------------------------------------------- bulk store smem -> global (TMA unit)
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------- fp32 -> bf16 hi/lo staging
+// 8 consecutive fp32 values -> one 16-byte bf16 group (hi) and its residual group (lo)
+__device__ __forceinline__ void split8_hilo(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    const float2 b = unpack_bf16x2(h[i]);
+    l[i] = pack_bf16x2(v[2 * i] - b.x, v[2 * i + 1] - b.y);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y, v[4] = c.x, v[5] = c.y, v[6] = d.x, v[7] = d.y;
+}
+
+// Stage a row-major fp32 matrix W[rows][cols] (global) as tile-native bf16 hi (+ optional lo) tiles with R = rows_tile
+// rows (rows beyond `rows` are zero-filled).  Cooperative over the CTA.  cols % 8 == 0.
+__device__ __forceinline__ void stage_weight_tile(const float* __restrict__ W, int rows, int cols, int rows_tile, unsigned char* hi,
+                                                  unsigned char* lo) {
+  const int groups = rows_tile * (cols / 8);
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const int r = g % rows_tile, cg = g / rows_tile;
+    float v[8];
+    if (r < rows) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(r) * cols + cg * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(r) * cols + cg * 8 + 4));
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+    uint4 h, l;
+    split8_hilo(v, h, l);
+    *reinterpret_cast<uint4*>(hi + tile_off16(rows_tile, r, cg)) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + tile_off16(rows_tile, r, cg)) = l;
+  }
+}
+
+// 3-product high-precision GEMM: D = (Ahi + Alo)(Bhi + Blo)^T without the lo*lo term (~16 mantissa bits)
+__device__ __forceinline__ void umma_gemm_hilo(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_hi,
+                                               uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K) {
+  umma_gemm(d_tmem, a_hi, a_lbo, a_sbo, b_hi, b_lbo, b_sbo, idesc, K, false);
+  umma_gemm(d_tmem, a_lo, a_lbo, a_sbo, b_hi, b_lbo, b_sbo, idesc, K, true);
+  umma_gemm(d_tmem, a_hi, a_lbo, a_sbo, b_lo, b_lbo, b_sbo, idesc, K, true);
+}
+
+}  // namespace xhved

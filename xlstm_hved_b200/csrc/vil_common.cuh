@@ -10,6 +10,7 @@
 namespace xhved {
 
 constexpr int kTok = 128;  // tokens per CTA == cell chunk length
+__host__ __device__ constexpr uint32_t next_pow2_tmem(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
 struct VilGeom {
   int B, S, nc, Sp, NH, DH, DHP, reverse;

@@ -29,66 +29,122 @@ __device__ __forceinline__ void load_h_row(const unsigned char* tile, int r, flo
   }
 }
 
+// ------------------------------------------------------------------ forward (tcgen05 version)
+// Per token: per-head normalisation, skip, SiLU(z) gate on CUDA cores -> the gated row is staged as a bf16 hi/lo tile and
+// proj_down runs as a 3-product UMMA (tokens x C); the epilogue adds the residual and writes NCDHW.
+template <int C>
+struct PostTC {
+  static constexpr int E = 2 * C;
+  static constexpr uint32_t HG_BYTES = kTok * E * 2, WD_BYTES = C * E * 2;
+  static constexpr uint32_t HGHI = 0, HGLO = HG_BYTES, WDHI = 2 * HG_BYTES, WDLO = WDHI + WD_BYTES, PAR = WDLO + WD_BYTES;
+  static constexpr int P_OW = 0, P_SK = E, P_N = 2 * E;
+  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  static constexpr uint32_t TMEM_COLS = next_pow2_tmem(C);
+};
+
+// the gated activation of one head for token `tid` (vision_lstm.py:271-287, 437, 440); also returns xhat and the statistics
+template <int DH>
+__device__ __forceinline__ void gated_head(const unsigned char* h_tile, int tid, const float* ow, const float* sk, const float* act,
+                                           const float* z, size_t tm_stride, float* hg, float* xhat, float* rstd_out) {
+  float hv[DH];
+  load_h_row<DH>(h_tile, tid, hv);
+  float mean = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) mean += hv[d];
+  mean *= (1.f / DH);
+  float var = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) var += (hv[d] - mean) * (hv[d] - mean);
+  const float rstd = rsqrtf(var * (1.f / DH) + 1e-5f);
+#pragma unroll
+  for (int d = 0; d < DH; ++d) {
+    const float xh = (hv[d] - mean) * rstd;
+    const float a = __ldg(act + d * tm_stride), zz = __ldg(z + d * tm_stride);
+    hg[d] = (xh * (1.f + ow[d]) + sk[d] * a) * silu(zz);
+    if (xhat) xhat[d] = xh;
+  }
+  if (rstd_out) *rstd_out = rstd;
+}
+
 template <int C>
 __global__ void __launch_bounds__(kTok) vil_post_fwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ h_tiles,
                                                              const float* __restrict__ act, const float* __restrict__ z,
                                                              xhved_vil_params p, VilGeom g, float* __restrict__ y) {
-  using L = PostSmem<C>;
+  using L = PostTC<C>;
   constexpr int E = L::E, DH = E / 4, DHP = DH < 16 ? 16 : DH;
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* par = reinterpret_cast<float*>(smem + L::PAR);
+  __shared__ __align__(8) uint64_t bar1;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
-  for (int i = tid; i < E * C; i += kTok) {
-    const int c = i / E, e = i % E;
-    sm[L::WDT + e * C + c] = __ldg(p.proj_down_weight + i);
+  if (tid == 0) {
+    mbar_init(&bar1, 1);
+    mbar_fence_init();
   }
-  stage(sm + L::OW, p.outnorm_weight, E);
-  stage(sm + L::SK, p.learnable_skip, E);
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
+  stage(par + L::P_OW, p.outnorm_weight, E);
+  stage(par + L::P_SK, p.learnable_skip, E);
+  stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
   __syncthreads();
   const int tau = ch * kTok + tid;
-  if (tau >= g.S) return;
+  const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
   const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
-
-  float out[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) out[c] = 0.f;
 #pragma unroll 1
   for (int head = 0; head < 4; ++head) {
     const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
-    float hv[DH];
-    load_h_row<DH>(h_tiles + tile * (kTok * DHP * 2), tid, hv);
-    float mean = 0.f;
+    float hg[DH];
+    gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tid, par + L::P_OW + head * DH, par + L::P_SK + head * DH,
+                   act + tm_base + static_cast<size_t>(head * DH) * kTok, z + tm_base + static_cast<size_t>(head * DH) * kTok, kTok, hg,
+                   nullptr, nullptr);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) mean += hv[d];
-    mean *= (1.f / DH);
-    float var = 0.f;
+    for (int cg = 0; cg < DH / 8; ++cg) {
+      float v8[8];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) var += (hv[d] - mean) * (hv[d] - mean);
-    const float rstd = rsqrtf(var * (1.f / DH) + 1e-5f);
+      for (int i = 0; i < 8; ++i) v8[i] = valid ? hg[cg * 8 + i] : 0.f;
+      uint4 hi, lo;
+      split8_hilo(v8, hi, lo);
+      *reinterpret_cast<uint4*>(smem + L::HGHI + tile_off16(kTok, tid, head * (DH / 8) + cg)) = hi;
+      *reinterpret_cast<uint4*>(smem + L::HGLO + tile_off16(kTok, tid, head * (DH / 8) + cg)) = lo;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // out[tok][c] = sum_e hg[tok][e] W_down[c][e]
+    umma_gemm_hilo(tmem, smem_u32(smem + L::HGHI), smem_u32(smem + L::HGLO), kTok * 16, 128, smem_u32(smem + L::WDHI),
+                   smem_u32(smem + L::WDLO), C * 16, 128, umma_idesc(128, C, false, false), E);
+    umma_commit(&bar1);
+  }
+  mbar_wait(&bar1, 0);
+  tc_fence_after();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      const int e = head * DH + d;
-      const float hn = (hv[d] - mean) * rstd * (1.f + sm[L::OW + e]);
-      const float a = __ldg(act + tm_base + static_cast<size_t>(e) * kTok);
-      const float zz = __ldg(z + tm_base + static_cast<size_t>(e) * kTok);
-      const float hg = (hn + sm[L::SK + e] * a) * silu(zz);
-      const float* w = sm + L::WDT + e * C;
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    float o[16];
+    tmem_ld16(tmem + lane_base + c0, o);
+    if (valid) {
 #pragma unroll
-      for (int c = 0; c < C; c += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(w + c);
-        out[c] += w4.x * hg, out[c + 1] += w4.y * hg, out[c + 2] += w4.z * hg, out[c + 3] += w4.w * hg;
+      for (int i = 0; i < 16; ++i) {
+        const int c = c0 + i;
+        y[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) + o[i];
       }
     }
   }
-#pragma unroll
-  for (int c = 0; c < C; ++c) y[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) + out[c];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
 template <int C>
 static int launch_post_fwd(const float* x, const void* h, const float* act, const float* z, const xhved_vil_params* p, const VilGeom& g,
                            float* y, cudaStream_t st) {
-  const size_t smem = PostSmem<C>::TOTAL * sizeof(float);
+  const size_t smem = PostTC<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_FWD, st);
@@ -96,19 +152,19 @@ static int launch_post_fwd(const float* x, const void* h, const float* act, cons
   return (int)cudaGetLastError();
 }
 
-
-// ------------------------------------------------------------------ backward
+// ------------------------------------------------------------------ backward (tcgen05 version)
+// d(gated) = dy W_down (3-product UMMA), elementwise backward of gate / skip / per-head norm on CUDA cores,
+// d proj_down = gated^T dy over the CTA's tokens as a UMMA (bf16 operands), dh written as bf16 tiles by bulk store.
 template <int C>
-struct PostBwdSmem {
-  static constexpr int E = 2 * C;
-  static constexpr int WDT = 0;                 // proj_down transposed (E, C)
-  static constexpr int OW = WDT + E * C;
-  static constexpr int SK = OW + E;
-  static constexpr int ACC_SK = SK + E;         // per-CTA partial of d learnable_skip
-  static constexpr int ACC_OW = ACC_SK + E;     // per-CTA partial of d outnorm.weight
-  static constexpr int HG = ACC_OW + E;         // (128, E+1) gated activations
-  static constexpr int DY = HG + kTok * (E + 1);  // (128, C+1)
-  static constexpr int TOTAL = DY + kTok * (C + 1);
+struct PostBwdTC {
+  static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH;
+  static constexpr uint32_t DY_BYTES = kTok * C * 2, WD_BYTES = C * E * 2, DHT_BYTES = kTok * 4 * DHP * 2;
+  static constexpr uint32_t HG = 0;                       // [128][E] bf16, read as a 128-row MN-major A operand: 32 KB window
+  static constexpr uint32_t DYHI = 32768, DYLO = DYHI + DY_BYTES, WDHI = DYLO + DY_BYTES, WDLO = WDHI + WD_BYTES;
+  static constexpr uint32_t DHT = WDLO + WD_BYTES, PAR = DHT + DHT_BYTES;
+  static constexpr int P_OW = 0, P_SK = E, P_ASK = 2 * E, P_AOW = 3 * E, P_N = 4 * E;
+  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  static constexpr uint32_t TMEM_COLS = next_pow2_tmem(E + C);
 };
 
 template <int C>
@@ -116,95 +172,160 @@ __global__ void __launch_bounds__(kTok) vil_post_bwd_kernel(const float* __restr
                                                              const float* __restrict__ act, const float* __restrict__ z,
                                                              xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
                                                              float* __restrict__ d_act, float* __restrict__ dz, xhved_vil_grads gr) {
-  using L = PostBwdSmem<C>;
-  constexpr int E = L::E, DH = E / 4, DHP = DH < 16 ? 16 : DH;
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
+  using L = PostBwdTC<C>;
+  constexpr int E = L::E, DH = L::DH, DHP = L::DHP;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* par = reinterpret_cast<float*>(smem + L::PAR);
+  __shared__ __align__(8) uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
-  for (int i = tid; i < E * C; i += kTok) {
-    const int c = i / E, e = i % E;
-    sm[L::WDT + e * C + c] = __ldg(p.proj_down_weight + i);
+  if (tid == 0) {
+    mbar_init(&bar1, 1);
+    mbar_init(&bar2, 1);
+    mbar_fence_init();
   }
-  stage(sm + L::OW, p.outnorm_weight, E);
-  stage(sm + L::SK, p.learnable_skip, E);
-  for (int i = tid; i < 2 * E; i += kTok) sm[L::ACC_SK + i] = 0.f;
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
+  stage(par + L::P_OW, p.outnorm_weight, E);
+  stage(par + L::P_SK, p.learnable_skip, E);
+  for (int i = tid; i < 2 * E; i += kTok) par[L::P_ASK + i] = 0.f;
+  stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
   const int tau = ch * kTok + tid;
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-  float dyr[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    dyr[c] = valid ? __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) : 0.f;
-    sm[L::DY + tid * (C + 1) + c] = dyr[c];
+  for (int cg = 0; cg < C / 8; ++cg) {
+    float v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = valid ? __ldg(dy + b * g.ysb + n * g.ysn + (cg * 8 + i) * g.ysc) : 0.f;
+    uint4 hi, lo;
+    split8_hilo(v8, hi, lo);
+    *reinterpret_cast<uint4*>(smem + L::DYHI + tile_off16(kTok, tid, cg)) = hi;
+    *reinterpret_cast<uint4*>(smem + L::DYLO + tile_off16(kTok, tid, cg)) = lo;
   }
+  fence_proxy_async();
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // dhg[tok][e] = sum_c dy[tok][c] W_down[c][e]     (B = MN-major view of the [C][E] weight tile)
+    umma_gemm_hilo(tmem, smem_u32(smem + L::DYHI), smem_u32(smem + L::DYLO), kTok * 16, 128, smem_u32(smem + L::WDHI),
+                   smem_u32(smem + L::WDLO), 128, C * 16, umma_idesc(128, E, false, true), C);
+    umma_commit(&bar1);
+  }
+  mbar_wait(&bar1, 0);
+  tc_fence_after();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
   const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
   for (int head = 0; head < 4; ++head) {
     const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
-    float hv[DH], gg[DH];
-    load_h_row<DH>(h_tiles + tile * (kTok * DHP * 2), tid, hv);
-    float mean = 0.f;
+    float hg[DH], xhat[DH], rstd;
+    const float* ow = par + L::P_OW + head * DH;
+    const float* sk = par + L::P_SK + head * DH;
+    const float* actp = act + tm_base + static_cast<size_t>(head * DH) * kTok;
+    const float* zp = z + tm_base + static_cast<size_t>(head * DH) * kTok;
+    gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tid, ow, sk, actp, zp, kTok, hg, xhat, &rstd);
+    float dhg[DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) mean += hv[d];
-    mean *= (1.f / DH);
-    float var = 0.f;
+    for (int c0 = 0; c0 < DH; c0 += 8) {
+      // 8-column TMEM reads keep the register footprint small
+      float t16[16];
+      if ((c0 & 8) == 0) {
+        if (DH >= 16) {
+          tmem_ld16(tmem + lane_base + head * DH + c0, t16);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) var += (hv[d] - mean) * (hv[d] - mean);
-    const float rstd = rsqrtf(var * (1.f / DH) + 1e-5f);
-    float mean_g = 0.f, mean_gx = 0.f;
+          for (int i = 0; i < 16; ++i) dhg[c0 + i] = t16[i];
+        } else {
+          // DH = 8: two heads share a 16-column read
+          tmem_ld16(tmem + lane_base + (head & ~1) * DH, t16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dhg[i] = t16[(head & 1) * 8 + i];
+        }
+      }
+    }
+    float gg[DH], mean_g = 0.f, mean_gx = 0.f;
 #pragma unroll
     for (int d = 0; d < DH; ++d) {
       const int e = head * DH + d;
-      const float xhat = (hv[d] - mean) * rstd;
-      const float ow1 = 1.f + sm[L::OW + e];
-      const float a = __ldg(act + tm_base + static_cast<size_t>(e) * kTok);
-      const float zz = __ldg(z + tm_base + static_cast<size_t>(e) * kTok);
+      const float a = __ldg(actp + d * kTok), zz = __ldg(zp + d * kTok);
       const float sz = silu(zz);
-      const float hs = xhat * ow1 + sm[L::SK + e] * a;
-      float dhg = 0.f;
-      const float* w = sm + L::WDT + e * C;
-#pragma unroll
-      for (int c = 0; c < C; c += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(w + c);
-        dhg += w4.x * dyr[c] + w4.y * dyr[c + 1] + w4.z * dyr[c + 2] + w4.w * dyr[c + 3];
-      }
-      const float dhs = dhg * sz;
-      sm[L::HG + tid * (E + 1) + e] = valid ? hs * sz : 0.f;
-      dz[tm_base + static_cast<size_t>(e) * kTok] = dhg * hs * dsilu(zz);
-      d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sm[L::SK + e];
-      warp_acc(sm + L::ACC_SK + e, dhs * a);
-      warp_acc(sm + L::ACC_OW + e, dhs * xhat);
-      gg[d] = dhs * ow1;
-      hv[d] = xhat;
+      const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
+      const float dhs = valid ? dhg[d] * sz : 0.f;
+      dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsilu(zz) : 0.f;
+      d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sk[d];
+      warp_acc(par + L::P_ASK + e, dhs * a);
+      warp_acc(par + L::P_AOW + e, dhs * xhat[d]);
+      gg[d] = dhs * (1.f + ow[d]);
       mean_g += gg[d];
-      mean_gx += gg[d] * xhat;
+      mean_gx += gg[d] * xhat[d];
     }
     mean_g *= (1.f / DH);
     mean_gx *= (1.f / DH);
-    float o[DHP];
 #pragma unroll
-    for (int d = 0; d < DHP; ++d) o[d] = (d < DH && valid) ? rstd * (gg[d < DH ? d : 0] - mean_g - hv[d < DH ? d : 0] * mean_gx) : 0.f;
-    unsigned char* dst = dh_tiles + tile * (kTok * DHP * 2);
+    for (int cg = 0; cg < DHP / 8; ++cg) {
+      uint4 u = zero;
+      if (cg * 8 < DH) {
+        float o8[8], hg8[8];
 #pragma unroll
-    for (int cg = 0; cg < DHP / 8; ++cg)
-      *reinterpret_cast<uint4*>(dst + tile_off16(kTok, tid, cg)) =
-          make_uint4(pack_bf16x2(o[cg * 8], o[cg * 8 + 1]), pack_bf16x2(o[cg * 8 + 2], o[cg * 8 + 3]),
-                     pack_bf16x2(o[cg * 8 + 4], o[cg * 8 + 5]), pack_bf16x2(o[cg * 8 + 6], o[cg * 8 + 7]));
+        for (int i = 0; i < 8; ++i) {
+          const int d = cg * 8 + i;
+          o8[i] = rstd * (gg[d] - mean_g - xhat[d] * mean_gx);
+          hg8[i] = valid ? hg[d] : 0.f;
+        }
+        u = pack8_bf16(o8);
+        *reinterpret_cast<uint4*>(smem + L::HG + tile_off16(kTok, tid, head * (DH / 8) + cg)) = pack8_bf16(hg8);
+      }
+      *reinterpret_cast<uint4*>(smem + L::DHT + tile_off16(kTok, tid, head * (DHP / 8) + cg)) = u;
+    }
   }
+  fence_proxy_async();
+  tc_fence_before();
   __syncthreads();
-  for (int e = tid; e < E; e += kTok) {
-    atomicAdd(gr.learnable_skip + e, sm[L::ACC_SK + e]);
-    atomicAdd(gr.outnorm_weight + e, sm[L::ACC_OW + e]);
+  tc_fence_after();
+  if (tid == 0) {
+    // d proj_down^T[e][c] = sum_tok hg[tok][e] dy[tok][c]   (both operands MN-major views of token-row tiles)
+    umma_gemm(tmem + E, smem_u32(smem + L::HG), 128, kTok * 16, smem_u32(smem + L::DYHI), 128, kTok * 16, umma_idesc(128, C, true, true),
+              kTok, false);
+    umma_commit(&bar2);
+    constexpr uint32_t HT = kTok * DHP * 2;
+#pragma unroll 1
+    for (int head = 0; head < 4; ++head) {
+      const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
+      bulk_s2g(dh_tiles + tile * HT, smem + L::DHT + head * HT, HT);
+    }
+    bulk_commit();
   }
-  // d proj_down[c][e] += sum_tok dy[tok][c] * hg[tok][e]
-  outer_accumulate(sm + L::DY, C + 1, C, sm + L::HG, E + 1, E, kTok, gr.proj_down_weight);
+  for (int e = tid; e < E; e += kTok) {
+    atomicAdd(gr.learnable_skip + e, par[L::P_ASK + e]);
+    atomicAdd(gr.outnorm_weight + e, par[L::P_AOW + e]);
+  }
+  mbar_wait(&bar2, 0);
+  tc_fence_after();
+  if (warp * 32 < E) {
+#pragma unroll
+    for (int c0 = 0; c0 < C; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + E + c0, v);
+      if (tid < E) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(gr.proj_down_weight + static_cast<size_t>(c0 + i) * E + tid, v[i]);
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_read();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
 template <int C>
 static int launch_post_bwd(const float* dy, const void* h, const float* act, const float* z, const xhved_vil_params* p, const VilGeom& g,
                            void* dh, float* d_act, float* dz, const xhved_vil_grads* gr, cudaStream_t st) {
-  const size_t smem = PostBwdSmem<C>::TOTAL * sizeof(float);
+  const size_t smem = PostBwdTC<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_BWD, st);

@@ -7,8 +7,7 @@
 // (UxLSTMEnc_3d.py:59).  Outputs land in the cell's tile-native bf16 layout, so the cell kernels can bulk-copy
 // MMA-ready operand tiles.
 //
-// One CTA = 128 consecutive tokens (in traversal order) = one cell chunk for all heads; 160 threads: thread r <
-// 128 owns token r, threads 128..130 recompute the 3-token conv halo.
+// One CTA = 128 consecutive tokens (in traversal order) = one cell chunk for all heads; thread r owns token r.
 #include "vil_common.cuh"
 
 namespace xhved {
@@ -62,139 +61,243 @@ __device__ __forceinline__ float dot_row(const float* xn, const float* wrow) {
   return acc;
 }
 
+// ------------------------------------------------------------------ forward (tcgen05 version)
+// proj_up runs as a 3-product bf16 hi/lo UMMA (tokens x 2E, ~fp32 accuracy), the gate pre-activations as a UMMA over the
+// bf16 q|k|v tile that is afterwards bulk-stored to the cell's operand tiles; conv / SiLU / the 4x4 block-diagonal
+// projections stay on CUDA cores.  128 threads, thread = token.
 template <int C>
-__global__ void __launch_bounds__(160) vil_pre_fwd_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
-                                                           unsigned char* __restrict__ q_tiles, unsigned char* __restrict__ k_tiles,
-                                                           unsigned char* __restrict__ v_tiles, float* __restrict__ igp,
-                                                           float* __restrict__ fgp, float* __restrict__ act_out,
-                                                           float* __restrict__ z_out) {
-  using L = PreSmem<C>;
-  constexpr int E = L::E;
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
+struct PreTC {
+  static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
+  static constexpr uint32_t X_BYTES = kTok * C * 2, W_BYTES = 2 * E * C * 2, QKV_BYTES = kTok * NQ * 2;
+  static constexpr uint32_t XHI = 0, XLO = X_BYTES, WHI = 2 * X_BYTES, WLO = 2 * X_BYTES + W_BYTES;
+  static constexpr uint32_t OPER = (2 * X_BYTES + 2 * W_BYTES) > QKV_BYTES ? (2 * X_BYTES + 2 * W_BYTES) : QKV_BYTES;
+  static constexpr uint32_t QKV = 0;                              // aliases the proj_up operands once they are consumed
+  static constexpr uint32_t WG_BYTES = 16 * NQ * 2;
+  static constexpr uint32_t WGHI = OPER, WGLO = WGHI + WG_BYTES;
+  static constexpr uint32_t XM = WGLO + WG_BYTES;                 // fp32 (131, E+1)
+  static constexpr int XM_LD = E + 1;
+  static constexpr uint32_t PAR = XM + ((kTok + 3) * XM_LD * 4 + 15) / 16 * 16;   // fp32 small parameters
+  static constexpr int P_CW = 0, P_CB = E * 4, P_WQ = P_CB + E, P_WK = P_WQ + E * 4, P_WV = P_WK + E * 4, P_NW = P_WV + E * 4,
+                       P_HX = P_NW + C, P_N = P_HX + 3 * C;
+  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  static constexpr uint32_t TMEM_COLS = next_pow2_tmem(2 * E + 16);
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
+                                                            unsigned char* __restrict__ q_tiles, unsigned char* __restrict__ k_tiles,
+                                                            unsigned char* __restrict__ v_tiles, float* __restrict__ igp,
+                                                            float* __restrict__ fgp, float* __restrict__ act_out,
+                                                            float* __restrict__ z_out, float* __restrict__ xm_out) {
+  using L = PreTC<C>;
+  constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* par = reinterpret_cast<float*>(smem + L::PAR);
+  float* xm_s = reinterpret_cast<float*>(smem + L::XM);
+  __shared__ __align__(8) uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
 
-  stage(sm + L::W_UP, p.proj_up_weight, 2 * E * C);
-  stage(sm + L::CONV_W, p.conv_weight, E * 4);
-  stage(sm + L::CONV_B, p.conv_bias, E);
-  stage(sm + L::WQ, p.q_weight, E * 4);
-  stage(sm + L::WK, p.k_weight, E * 4);
-  stage(sm + L::WV, p.v_weight, E * 4);
-  stage(sm + L::WI, p.igate_weight, 4 * 3 * E);
-  stage(sm + L::WF, p.fgate_weight, 4 * 3 * E);
-  stage(sm + L::NW, p.norm_weight, C);
-
-  // token owned by this thread (traversal order tau); halo threads own tau0-3..tau0-1
-  const bool is_main = tid < kTok, is_halo = tid >= kTok && tid < kTok + 3;
-  const int tau = is_main ? ch * kTok + tid : ch * kTok - 3 + (tid - kTok);
-  const bool valid = (is_main || is_halo) && tau >= 0 && tau < g.S;
+  if (tid == 0) {
+    mbar_init(&bar1, 1);
+    mbar_init(&bar2, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
+  // ---- stage parameters
+  stage(par + L::P_CW, p.conv_weight, E * 4);
+  stage(par + L::P_CB, p.conv_bias, E);
+  stage(par + L::P_WQ, p.q_weight, E * 4);
+  stage(par + L::P_WK, p.k_weight, E * 4);
+  stage(par + L::P_WV, p.v_weight, E * 4);
+  stage(par + L::P_NW, p.norm_weight, C);
+  stage_weight_tile(p.proj_up_weight, 2 * E, C, 2 * E, smem + L::WHI, smem + L::WLO);
+  // gate weights as a [16][NQ] tile in the padded q|k|v column order: column (part*4 + head)*DHP + d
+  for (int gi = tid; gi < 16 * (NQ / 8); gi += kTok) {
+    const int hh = gi % 16, cg = gi / 16;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = cg * 8 + i, part = j / (4 * DHP), head = (j / DHP) % 4, d = j % DHP;
+      const float* W = hh < 4 ? p.igate_weight + hh * 3 * E : p.fgate_weight + (hh - 4) * 3 * E;
+      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + head * DH + d) : 0.f;
+    }
+    uint4 h, l;
+    split8_hilo(v, h, l);
+    *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
+    *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
+  }
+  // ---- load the token, LayerNorm, stage it as a bf16 hi/lo row
+  const int tau = ch * kTok + tid;
+  const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-  float xin[C];
+  float xin[C], xn[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
-  __syncthreads();
-
-  float xn[C];
-  layernorm_token<C>(xin, sm + L::NW, xn, nullptr);
-  const int xm_row = is_main ? tid + 3 : tid - kTok;
-  if (is_main || is_halo) {
-    float* xm = sm + L::XM + xm_row * L::XM_LD;
-#pragma unroll 1
-    for (int e = 0; e < E; ++e) xm[e] = valid ? dot_row<C>(xn, sm + L::W_UP + e * C) : 0.f;
-  }
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;   // token-minor (B, nc, E, 128)
-  if (is_main) {
-#pragma unroll 1
-    for (int e = 0; e < E; ++e) z_out[tm_base + static_cast<size_t>(e) * kTok + tid] = valid ? dot_row<C>(xn, sm + L::W_UP + (E + e) * C) : 0.f;
-  }
-  __syncthreads();
-  if (!is_main) return;
-
-  // conv + SiLU + block-diagonal q,k,v + gates, 8 channels at a time
-  float ig_acc[4], fg_acc[4];
+  float hx[C];
+  const int htau = ch * kTok - 3 + tid;              // halo token of threads 0..2
+  const bool hvalid = tid < 3 && htau >= 0;
+  if (tid < 3) {
+    const int hn_ = g.reverse ? g.S - 1 - htau : htau;
 #pragma unroll
-  for (int h = 0; h < 4; ++h) ig_acc[h] = __ldg(p.igate_bias + h), fg_acc[h] = __ldg(p.fgate_bias + h);
-  const float* xm0 = sm + L::XM + tid * L::XM_LD;   // rows tid..tid+3 <-> tokens tau-3..tau
-  const bool rowvalid = tau < g.S;
+    for (int c = 0; c < C; ++c) hx[c] = hvalid ? __ldg(x + b * g.xsb + hn_ * g.xsn + c * g.xsc) : 0.f;
+  }
+  __syncthreads();   // parameters (norm weight) staged
+  layernorm_token<C>(xin, par + L::P_NW, xn, nullptr);
+#pragma unroll
+  for (int cg = 0; cg < C / 8; ++cg) {
+    float v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
+    uint4 h, l;
+    split8_hilo(v8, h, l);
+    *reinterpret_cast<uint4*>(smem + L::XHI + tile_off16(kTok, tid, cg)) = h;
+    *reinterpret_cast<uint4*>(smem + L::XLO + tile_off16(kTok, tid, cg)) = l;
+  }
+  if (tid < 3) {
+    float hn2[C];
+    layernorm_token<C>(hx, par + L::P_NW, hn2, nullptr);
+#pragma unroll
+    for (int c = 0; c < C; ++c) par[L::P_HX + tid * C + c] = hvalid ? hn2[c] : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // D[tok][o] = sum_c xn[tok][c] W_up[o][c]
+    umma_gemm_hilo(tmem, smem_u32(smem + L::XHI), smem_u32(smem + L::XLO), kTok * 16, 128, smem_u32(smem + L::WHI),
+                   smem_u32(smem + L::WLO), 2 * E * 16, 128, umma_idesc(128, 2 * E, false, false), C);
+    umma_commit(&bar1);
+  }
+  // ---- conv halo (3 previous tokens): x_mlstm only, spread over the CTA while the MMA runs
+  for (int idx = tid; idx < 3 * E; idx += kTok) {
+    const int row = idx / E, e = idx % E;
+    const float* w = p.proj_up_weight + static_cast<size_t>(e) * C;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+      const float* hxn = par + L::P_HX + row * C + c;
+      acc += hxn[0] * w4.x + hxn[1] * w4.y + hxn[2] * w4.z + hxn[3] * w4.w;
+    }
+    xm_s[row * L::XM_LD + e] = acc;
+  }
+  mbar_wait(&bar1, 0);
+  tc_fence_after();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;   // token-minor (B, nc, E, 128)
+#pragma unroll 1
+  for (int c0 = 0; c0 < 2 * E; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem + lane_base + c0, v);
+    if (c0 < E) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        xm_s[(tid + 3) * L::XM_LD + c0 + i] = v[i];
+        xm_out[tm_base + static_cast<size_t>(c0 + i) * kTok] = v[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) z_out[tm_base + static_cast<size_t>(c0 - E + i) * kTok] = v[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();   // x_mlstm of all tokens visible; proj_up operands dead -> QKV tile may overwrite them
+  // ---- conv + SiLU + block-diagonal q,k,v, 8 channels at a time
+  const float* xm0 = xm_s + tid * L::XM_LD;   // rows tid..tid+3 <-> tokens tau-3..tau
 #pragma unroll 1
   for (int e8 = 0; e8 < E; e8 += 8) {
     float a8[8], xm8[8], q8[8], k8[8], v8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = e8 + j;
-      const float4 w = *reinterpret_cast<const float4*>(sm + L::CONV_W + e * 4);
-      const float conv = sm[L::CONV_B + e] + w.x * xm0[e] + w.y * xm0[L::XM_LD + e] + w.z * xm0[2 * L::XM_LD + e] +
+      const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
+      const float conv = par[L::P_CB + e] + w.x * xm0[e] + w.y * xm0[L::XM_LD + e] + w.z * xm0[2 * L::XM_LD + e] +
                          w.w * xm0[3 * L::XM_LD + e];
       a8[j] = silu(conv);
       xm8[j] = xm0[3 * L::XM_LD + e];
-      act_out[tm_base + static_cast<size_t>(e) * kTok + tid] = rowvalid ? a8[j] : 0.f;
+      act_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? a8[j] : 0.f;
     }
 #pragma unroll
     for (int blk = 0; blk < 2; ++blk) {
       const int wb = ((e8 >> 2) + blk) * 16;   // (block, out, in) 4x4
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        float aq = 0.f, ak = 0.f, av = 0.f;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          aq += sm[L::WQ + wb + o * 4 + d] * a8[blk * 4 + d];
-          ak += sm[L::WK + wb + o * 4 + d] * a8[blk * 4 + d];
-          av += sm[L::WV + wb + o * 4 + d] * xm8[blk * 4 + d];
-        }
-        q8[blk * 4 + o] = aq, k8[blk * 4 + o] = ak, v8[blk * 4 + o] = av;
+        const float4 wq = *reinterpret_cast<const float4*>(par + L::P_WQ + wb + o * 4);
+        const float4 wk = *reinterpret_cast<const float4*>(par + L::P_WK + wb + o * 4);
+        const float4 wv = *reinterpret_cast<const float4*>(par + L::P_WV + wb + o * 4);
+        const float* a = a8 + blk * 4;
+        const float* xv = xm8 + blk * 4;
+        q8[blk * 4 + o] = wq.x * a[0] + wq.y * a[1] + wq.z * a[2] + wq.w * a[3];
+        k8[blk * 4 + o] = wk.x * a[0] + wk.y * a[1] + wk.z * a[2] + wk.w * a[3];
+        v8[blk * 4 + o] = wv.x * xv[0] + wv.y * xv[1] + wv.z * xv[2] + wv.w * xv[3];
       }
     }
+    const int head = e8 / DH, d0 = e8 % DH;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const uint4 uq = valid ? pack8_bf16(q8) : zero, uk = valid ? pack8_bf16(k8) : zero, uv = valid ? pack8_bf16(v8) : zero;
+    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((0 * 4 + head) * DHP + d0) / 8)) = uq;
+    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((1 * 4 + head) * DHP + d0) / 8)) = uk;
+    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((2 * 4 + head) * DHP + d0) / 8)) = uv;
+    if (DHP > DH) {   // DH = 8 padded to 16: zero the second column group of every head
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = e8 + j;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        ig_acc[h] += sm[L::WI + h * 3 * E + e] * q8[j] + sm[L::WI + h * 3 * E + E + e] * k8[j] + sm[L::WI + h * 3 * E + 2 * E + e] * v8[j];
-        fg_acc[h] += sm[L::WF + h * 3 * E + e] * q8[j] + sm[L::WF + h * 3 * E + E + e] * k8[j] + sm[L::WF + h * 3 * E + 2 * E + e] * v8[j];
-      }
-    }
-    // 8 consecutive channels = one 16-byte group of one head's tile row
-    const int head = e8 / g.DH, d0 = e8 % g.DH;
-    const size_t tile = (static_cast<size_t>(b) * g.NH + head) * g.nc + ch;
-    const size_t off = tile * (kTok * g.DHP * 2) + tile_off16(kTok, tid, d0 / 8);
-    uint4 uq = make_uint4(0, 0, 0, 0), uk = uq, uv = uq;
-    if (rowvalid) {
-      uq = make_uint4(pack_bf16x2(q8[0], q8[1]), pack_bf16x2(q8[2], q8[3]), pack_bf16x2(q8[4], q8[5]), pack_bf16x2(q8[6], q8[7]));
-      uk = make_uint4(pack_bf16x2(k8[0], k8[1]), pack_bf16x2(k8[2], k8[3]), pack_bf16x2(k8[4], k8[5]), pack_bf16x2(k8[6], k8[7]));
-      uv = make_uint4(pack_bf16x2(v8[0], v8[1]), pack_bf16x2(v8[2], v8[3]), pack_bf16x2(v8[4], v8[5]), pack_bf16x2(v8[6], v8[7]));
-    }
-    *reinterpret_cast<uint4*>(q_tiles + off) = uq;
-    *reinterpret_cast<uint4*>(k_tiles + off) = uk;
-    *reinterpret_cast<uint4*>(v_tiles + off) = uv;
-    if (g.DHP > g.DH && d0 + 8 == g.DH) {   // zero the padding column groups (DH = 8 padded to 16)
-      const uint4 zz = make_uint4(0, 0, 0, 0);
-      for (int cg = g.DH / 8; cg < g.DHP / 8; ++cg) {
-        const size_t o2 = tile * (kTok * g.DHP * 2) + tile_off16(kTok, tid, cg);
-        *reinterpret_cast<uint4*>(q_tiles + o2) = zz;
-        *reinterpret_cast<uint4*>(k_tiles + o2) = zz;
-        *reinterpret_cast<uint4*>(v_tiles + o2) = zz;
-      }
+      for (int part = 0; part < 3; ++part)
+        *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((part * 4 + head) * DHP + 8) / 8)) = zero;
     }
   }
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    const size_t o = (static_cast<size_t>(b) * g.NH + h) * g.Sp + ch * kTok + tid;
-    igp[o] = rowvalid ? ig_acc[h] : -1e30f;
-    fgp[o] = rowvalid ? fg_acc[h] : 1e30f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    // gates[tok][hh] = sum_j qkv[tok][j] Wg[hh][j]   (bf16 q,k,v exactly as the cell sees them; hi/lo weights)
+    const uint32_t aq = smem_u32(smem + L::QKV);
+    umma_gemm(tmem + 2 * E, aq, kTok * 16, 128, smem_u32(smem + L::WGHI), 16 * 16, 128, umma_idesc(128, 16, false, false), NQ, false);
+    umma_gemm(tmem + 2 * E, aq, kTok * 16, 128, smem_u32(smem + L::WGLO), 16 * 16, 128, umma_idesc(128, 16, false, false), NQ, true);
+    umma_commit(&bar2);
+    // q/k/v head tiles are contiguous column blocks of the staged tile: bulk-store them to the cell's operand tiles
+    constexpr uint32_t HT = kTok * DHP * 2;
+#pragma unroll 1
+    for (int head = 0; head < 4; ++head) {
+      const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
+      bulk_s2g(q_tiles + tile * HT, smem + L::QKV + (0 * 4 + head) * HT, HT);
+      bulk_s2g(k_tiles + tile * HT, smem + L::QKV + (1 * 4 + head) * HT, HT);
+      bulk_s2g(v_tiles + tile * HT, smem + L::QKV + (2 * 4 + head) * HT, HT);
+    }
+    bulk_commit();
   }
+  mbar_wait(&bar2, 0);
+  tc_fence_after();
+  {
+    float gt[16];
+    tmem_ld16(tmem + lane_base + 2 * E, gt);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tid;
+      igp[o] = valid ? gt[h] + __ldg(p.igate_bias + h) : -1e30f;
+      fgp[o] = valid ? gt[4 + h] + __ldg(p.fgate_bias + h) : 1e30f;
+    }
+  }
+  if (tid == 0) bulk_wait_read();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
 template <int C>
 static int launch_pre_fwd(const float* x, const xhved_vil_params* p, const VilGeom& g, void* q, void* k, void* v, float* ig, float* fg,
-                          float* act, float* z, cudaStream_t st) {
-  const size_t smem = PreSmem<C>::TOTAL * sizeof(float);
+                          float* act, float* z, float* xm, cudaStream_t st) {
+  const size_t smem = PreTC<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_pre_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_PRE_FWD, st);
-  vil_pre_fwd_kernel<C><<<g.B * g.nc, 160, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z);
+  vil_pre_fwd_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z, xm);
   return (int)cudaGetLastError();
 }
-
 
 // ------------------------------------------------------------------ backward, kernel A
 // Recomputes the forward up to q,k,v for 128 tokens (+3 halo), then pulls dq,dk,dv,dig,dfg and the skip-path
@@ -493,6 +596,151 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_kernel(const float* __rest
   for (int c = tid; c < C; c += kTok) atomicAdd(gr.norm_weight + c, sm[L::ACC_NW + c]);
 }
 
+// ------------------------------------------------------------------ backward, tcgen05 versions
+// Kernel B (tensor-core): d[x_mlstm | z] rows are staged as bf16 hi/lo tiles; dxn = din W_up (3-product UMMA) and
+// d proj_up = din^T xn (UMMA over the CTA's tokens); LayerNorm backward and the residual add in the epilogue.
+template <int C>
+struct PreBwdBTC {
+  static constexpr int E = 2 * C;
+  static constexpr uint32_t DIN_BYTES = kTok * 2 * E * 2, W_BYTES = 2 * E * C * 2, XN_BYTES = kTok * C * 2;
+  static constexpr uint32_t DINHI = 0, DINLO = DIN_BYTES, WHI = 2 * DIN_BYTES, WLO = WHI + W_BYTES, XNT = WLO + W_BYTES, PAR = XNT + XN_BYTES;
+  static constexpr int P_CW = 0, P_NW = E * 4, P_ANW = P_NW + C, P_N = P_ANW + C;
+  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  static constexpr int MT = (2 * E + 127) / 128;                       // M tiles of the weight-gradient GEMM
+  static constexpr uint32_t TMEM_COLS = next_pow2_tmem(C + MT * C);
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTok) vil_pre_bwd_b_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 xhved_vil_params p, VilGeom g, const float* __restrict__ dconv,
+                                                                 const float* __restrict__ dxmv, const float* __restrict__ dz,
+                                                                 float* __restrict__ dx, xhved_vil_grads gr) {
+  using L = PreBwdBTC<C>;
+  constexpr int E = L::E;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* par = reinterpret_cast<float*>(smem + L::PAR);
+  __shared__ __align__(8) uint64_t bar1;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
+  if (tid == 0) {
+    mbar_init(&bar1, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
+  stage(par + L::P_CW, p.conv_weight, E * 4);
+  stage(par + L::P_NW, p.norm_weight, C);
+  for (int i = tid; i < C; i += kTok) par[L::P_ANW + i] = 0.f;
+  stage_weight_tile(p.proj_up_weight, 2 * E, C, 2 * E, smem + L::WHI, smem + L::WLO);
+  const int tau = ch * kTok + tid;
+  const bool valid = tau < g.S;
+  const int n = g.reverse ? g.S - 1 - tau : tau;
+  float xin[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
+  __syncthreads();
+  float xn[C], rstd;
+  layernorm_token<C>(xin, par + L::P_NW, xn, &rstd);
+#pragma unroll
+  for (int cg = 0; cg < C / 8; ++cg) {
+    float v8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
+    *reinterpret_cast<uint4*>(smem + L::XNT + tile_off16(kTok, tid, cg)) = pack8_bf16(v8);
+  }
+  // d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
+  const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
+#pragma unroll 1
+  for (int o8 = 0; o8 < 2 * E; o8 += 8) {
+    float d8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int o = o8 + i;
+      float d;
+      if (o8 < E) {
+        d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tid);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int tp = tau + k;
+          if (tp < g.S) {
+            const size_t off = (static_cast<size_t>(b) * g.nc + tp / kTok) * E * kTok + static_cast<size_t>(o) * kTok + (tp % kTok);
+            d += par[L::P_CW + o * 4 + 3 - k] * __ldg(dconv + off);
+          }
+        }
+      } else {
+        d = __ldg(dz + tm_chunk + static_cast<size_t>(o - E) * kTok + tid);
+      }
+      d8[i] = valid ? d : 0.f;
+    }
+    uint4 hi, lo;
+    split8_hilo(d8, hi, lo);
+    *reinterpret_cast<uint4*>(smem + L::DINHI + tile_off16(kTok, tid, o8 / 8)) = hi;
+    *reinterpret_cast<uint4*>(smem + L::DINLO + tile_off16(kTok, tid, o8 / 8)) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // dxn[tok][c] = sum_o din[tok][o] W_up[o][c]          (B = MN-major view of the [2E][C] weight tile)
+    umma_gemm_hilo(tmem, smem_u32(smem + L::DINHI), smem_u32(smem + L::DINLO), kTok * 16, 128, smem_u32(smem + L::WHI),
+                   smem_u32(smem + L::WLO), 128, 2 * E * 16, umma_idesc(128, C, false, true), 2 * E);
+    // d proj_up[o][c] = sum_tok din[tok][o] xn[tok][c]     (both operands MN-major views of token-row tiles)
+#pragma unroll
+    for (int mt = 0; mt < L::MT; ++mt)
+      umma_gemm(tmem + C + mt * C, smem_u32(smem + L::DINHI) + mt * 16 * kTok * 16, 128, kTok * 16, smem_u32(smem + L::XNT), 128, kTok * 16,
+                umma_idesc(128, C, true, true), kTok, false);
+    umma_commit(&bar1);
+  }
+  mbar_wait(&bar1, 0);
+  tc_fence_after();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  float dxn[C];
+#pragma unroll
+  for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16(tmem + lane_base + c0, dxn + c0);
+  float mean_g = 0.f, mean_gx = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float w1 = 1.f + par[L::P_NW + c];
+    const float xhat = xn[c] / w1;
+    warp_acc(par + L::P_ANW + c, valid ? dxn[c] * xhat : 0.f);
+    dxn[c] *= w1;
+    xn[c] = xhat;
+    mean_g += dxn[c];
+    mean_gx += dxn[c] * xhat;
+  }
+  mean_g *= (1.f / C);
+  mean_gx *= (1.f / C);
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float v = rstd * (dxn[c] - mean_g - xn[c] * mean_gx);
+      dx[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) + v;
+    }
+  }
+  // weight-gradient rows: thread o (and o + 128 for the second M tile)
+#pragma unroll
+  for (int mt = 0; mt < L::MT; ++mt) {
+    const int o = mt * 128 + tid;
+#pragma unroll
+    for (int c0 = 0; c0 < C; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + C + mt * C + c0, v);
+      if (o < 2 * E) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(gr.proj_up_weight + static_cast<size_t>(o) * C + c0 + i, v[i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kTok) atomicAdd(gr.norm_weight + c, par[L::P_ANW + c]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
+}
+
 template <int C>
 static int launch_pre_bwd(const float* x, const float* dy, const float* dq, const float* dk, const float* dv, const float* dig,
                           const float* dfg, const float* d_act, const float* dz, const xhved_vil_params* p, const VilGeom& g, float* dx,
@@ -505,11 +753,11 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* dq, cons
     vil_pre_bwd_a_kernel<C><<<g.B * g.nc, 160, smem, st>>>(x, *p, g, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv, *gr);
   }
   {
-    const size_t smem = PreBwdBSmem<C>::TOTAL * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_b_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = PreBwdBTC<C>::TOTAL;
+    cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_b_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_B, st);
-    vil_pre_bwd_b_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr);
+    vil_pre_bwd_b_tc_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr);
   }
   return (int)cudaGetLastError();
 }
@@ -519,15 +767,15 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* dq, cons
 using namespace xhved;
 
 extern "C" int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, const xhved_vil_shape* sh, void* q_tiles, void* k_tiles,
-                                 void* v_tiles, float* ig_padded, float* fg_padded, float* act, float* z, void* stream) {
+                                 void* v_tiles, float* ig_padded, float* fg_padded, float* act, float* z, float* xm, void* stream) {
   VilGeom g;
   if (int rc = vil_validate(sh, &g)) return rc;
-  if (!x || !p || !q_tiles || !k_tiles || !v_tiles || !ig_padded || !fg_padded || !act || !z) return XHVED_ERR_BAD_ARG;
+  if (!x || !p || !q_tiles || !k_tiles || !v_tiles || !ig_padded || !fg_padded || !act || !z || !xm) return XHVED_ERR_BAD_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (sh->C) {
-    case 16: return launch_pre_fwd<16>(x, p, g, q_tiles, k_tiles, v_tiles, ig_padded, fg_padded, act, z, st);
-    case 32: return launch_pre_fwd<32>(x, p, g, q_tiles, k_tiles, v_tiles, ig_padded, fg_padded, act, z, st);
-    case 64: return launch_pre_fwd<64>(x, p, g, q_tiles, k_tiles, v_tiles, ig_padded, fg_padded, act, z, st);
+    case 16: return launch_pre_fwd<16>(x, p, g, q_tiles, k_tiles, v_tiles, ig_padded, fg_padded, act, z, xm, st);
+    case 32: return launch_pre_fwd<32>(x, p, g, q_tiles, k_tiles, v_tiles, ig_padded, fg_padded, act, z, xm, st);
+    case 64: return launch_pre_fwd<64>(x, p, g, q_tiles, k_tiles, v_tiles, ig_padded, fg_padded, act, z, xm, st);
     default: return XHVED_ERR_UNSUPPORTED_DIM;
   }
 }

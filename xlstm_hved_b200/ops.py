@@ -279,6 +279,7 @@ class VilWorkspace:
         nc = self.cell.nc
         self.act = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
         self.z = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
+        self.xm = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
 
 
 def _shape_struct(x_tok, y_tok, reverse):
@@ -301,7 +302,7 @@ def vil_block_fwd(x_tok: torch.Tensor, params, reverse: bool, eps: float = 1e-6)
     sh = _shape_struct(x_tok, y, reverse)
     c = ws.cell
     check(lib.xhved_vil_pre_fwd(ptr(x_tok), ctypes.byref(ps), ctypes.byref(sh), ptr(c.q), ptr(c.k), ptr(c.v), ptr(c.ig), ptr(c.fg),
-                                ptr(ws.act), ptr(ws.z), stream()), "xhved_vil_pre_fwd")
+                                ptr(ws.act), ptr(ws.z), ptr(ws.xm), stream()), "xhved_vil_pre_fwd")
     mlstm_fwd_tiles(c, eps)
     check(lib.xhved_vil_post_fwd(ptr(x_tok), ptr(c.h), ptr(ws.act), ptr(ws.z), ctypes.byref(ps), ctypes.byref(sh), ptr(y), stream()),
           "xhved_vil_post_fwd")
