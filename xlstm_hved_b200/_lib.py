@@ -59,7 +59,7 @@ SYMBOLS = {
     "xhved_vil_post_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p],
     "xhved_vil_post_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p,
                            c_void_p, POINTER(VilGrads), c_void_p],
-    "xhved_vil_pre_bwd": [c_void_p] * 9 + [POINTER(VilParams), POINTER(VilShape), c_void_p, POINTER(VilGrads), c_void_p, c_void_p, c_void_p],
+    "xhved_vil_pre_bwd": [c_void_p] * 13 + [POINTER(VilParams), POINTER(VilShape), c_void_p, POINTER(VilGrads), c_void_p, c_void_p, c_void_p],
 }
 
 _lib = None

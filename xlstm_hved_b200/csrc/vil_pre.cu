@@ -741,11 +741,286 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_tc_kernel(const float* __r
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
+// Kernel A (tensor-core, C <= 32): the forward's saved x_mlstm and bf16 q|k|v tiles are reloaded (no recompute of
+// proj_up); gate-path gradients (dig,dfg -> q,k,v), gate-weight and block-diagonal weight gradients run as UMMAs over the
+// CTA's tokens; conv / SiLU / 4x4 block backward on CUDA cores.
 template <int C>
-static int launch_pre_bwd(const float* x, const float* dy, const float* dq, const float* dk, const float* dv, const float* dig,
-                          const float* dfg, const float* d_act, const float* dz, const xhved_vil_params* p, const VilGeom& g, float* dx,
-                          const xhved_vil_grads* gr, float* ws_dconv, float* ws_dxmv, cudaStream_t st) {
+struct PreBwdATC {
+  static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
+  static constexpr uint32_t DG_BYTES = kTok * 16 * 2, WG_BYTES = 16 * NQ * 2, QKV_BYTES = kTok * NQ * 2, T_BYTES = kTok * E * 2;
+  static constexpr uint32_t DGHI = 0, DGLO = DG_BYTES, WGHI = 2 * DG_BYTES, WGLO = WGHI + WG_BYTES;   // inside a 32 KB window
+  static constexpr uint32_t QKV = 32768, GQK = QKV + QKV_BYTES;                                      // GQK: [128][2E], 32 KB window
+  static constexpr uint32_t GV = GQK + 32768, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;               // GV window covers ACT, XMT (+pad)
+  static constexpr uint32_t PAR = (XMT + T_BYTES) > (GV + 32768) ? (XMT + T_BYTES) : (GV + 32768);
+  static constexpr int P_CW = 0, P_CB = E * 4, P_WQ = P_CB + E, P_WK = P_WQ + E * 4, P_WV = P_WK + E * 4, A_CW = P_WV + E * 4,
+                       A_CB = A_CW + E * 4, A_GB = A_CB + E, P_N = A_GB + 8;
+  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  static constexpr uint32_t T_GQ = 0, T_DWG = NQ, T_DWQK = 2 * NQ, T_DWV = 2 * NQ + E;
+  static_assert(2 * NQ + 2 * E <= 512 && WGLO + WG_BYTES <= 32768 && 2 * E <= 128, "tensor-core pre-backward A supports C <= 32");
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
+                                                                 const unsigned char* __restrict__ q_tiles,
+                                                                 const unsigned char* __restrict__ k_tiles,
+                                                                 const unsigned char* __restrict__ v_tiles, const float* __restrict__ dq,
+                                                                 const float* __restrict__ dk, const float* __restrict__ dv,
+                                                                 const float* __restrict__ dig, const float* __restrict__ dfg,
+                                                                 const float* __restrict__ d_act, float* __restrict__ dconv_out,
+                                                                 float* __restrict__ dxmv_out, xhved_vil_grads gr) {
+  using L = PreBwdATC<C>;
+  constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
+  constexpr uint32_t HT = kTok * DHP * 2;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* par = reinterpret_cast<float*>(smem + L::PAR);
+  __shared__ __align__(8) uint64_t bar_load, bar1, bar2;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar1, 1);
+    mbar_init(&bar2, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, 12 * HT);
+#pragma unroll 1
+    for (int head = 0; head < 4; ++head) {
+      const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
+      bulk_g2s(smem + L::QKV + (0 * 4 + head) * HT, q_tiles + tile * HT, HT, &bar_load);
+      bulk_g2s(smem + L::QKV + (1 * 4 + head) * HT, k_tiles + tile * HT, HT, &bar_load);
+      bulk_g2s(smem + L::QKV + (2 * 4 + head) * HT, v_tiles + tile * HT, HT, &bar_load);
+    }
+  }
+  stage(par + L::P_CW, p.conv_weight, E * 4);
+  stage(par + L::P_CB, p.conv_bias, E);
+  stage(par + L::P_WQ, p.q_weight, E * 4);
+  stage(par + L::P_WK, p.k_weight, E * 4);
+  stage(par + L::P_WV, p.v_weight, E * 4);
+  for (int i = tid; i < E * 4 + E + 8; i += kTok) par[L::A_CW + i] = 0.f;
+  for (int gi = tid; gi < 16 * (NQ / 8); gi += kTok) {
+    const int hh = gi % 16, cg = gi / 16;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = cg * 8 + i, part = j / (4 * DHP), head = (j / DHP) % 4, d = j % DHP;
+      const float* W = hh < 4 ? p.igate_weight + hh * 3 * E : p.fgate_weight + (hh - 4) * 3 * E;
+      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + head * DH + d) : 0.f;
+    }
+    uint4 h, l;
+    split8_hilo(v, h, l);
+    *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
+    *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
+  }
+  const int tau = ch * kTok + tid;
+  const bool valid = tau < g.S;
+  float dg[8];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tid;
+    dg[h] = valid ? __ldg(dig + o) : 0.f;
+    dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
+  }
   {
+    uint4 hi, lo;
+    split8_hilo(dg, hi, lo);
+    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tid, 0)) = hi;
+    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tid, 0)) = lo;
+    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tid, 1)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tid, 1)) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  mbar_wait(&bar_load, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
+    umma_gemm_hilo(tmem + L::T_GQ, smem_u32(smem + L::DGHI), smem_u32(smem + L::DGLO), kTok * 16, 128, smem_u32(smem + L::WGHI),
+                   smem_u32(smem + L::WGLO), 128, 16 * 16, umma_idesc(128, NQ, false, true), 16);
+    // d Wg[hh][j] = sum_tok [dig|dfg][tok][hh] qkv[tok][j]               (A: hi + lo, B: the bf16 q|k|v the cell consumed)
+    umma_gemm(tmem + L::T_DWG, smem_u32(smem + L::DGHI), 128, kTok * 16, smem_u32(smem + L::QKV), 128, kTok * 16,
+              umma_idesc(128, NQ, true, true), kTok, false);
+    umma_gemm(tmem + L::T_DWG, smem_u32(smem + L::DGLO), 128, kTok * 16, smem_u32(smem + L::QKV), 128, kTok * 16,
+              umma_idesc(128, NQ, true, true), kTok, true);
+    umma_commit(&bar1);
+  }
+  mbar_wait(&bar1, 0);
+  tc_fence_after();
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
+  float* acc = par;
+#pragma unroll 1
+  for (int e8 = 0; e8 < E; e8 += 8) {
+    const int head = e8 / DH, d0 = e8 % DH;
+    float a8[8], xm8[8], cv8[8], xr[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k
+      const int tp = tau - 3 + k;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const size_t off = (static_cast<size_t>(b) * g.nc + (tp >= 0 ? tp / kTok : 0)) * E * kTok + static_cast<size_t>(e8 + j) * kTok +
+                           (tp >= 0 ? tp % kTok : 0);
+        xr[k][j] = (tp >= 0 && tp < g.S) ? __ldg(xm + off) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e8 + j;
+      const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
+      cv8[j] = par[L::P_CB + e] + w.x * xr[0][j] + w.y * xr[1][j] + w.z * xr[2][j] + w.w * xr[3][j];
+      a8[j] = silu(cv8[j]);
+      xm8[j] = xr[3][j];
+    }
+    // upstream gradients of q,k,v: cell gradients + gate path (TMEM)
+    float gq[8], gk[8], gv[8], t8[8];
+    const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tid) * DHP + d0;
+    tmem_ld8(tmem + lane_base + L::T_GQ + (0 * 4 + head) * DHP + d0, t8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gq[j] = valid ? __ldg(dq + row + j) + t8[j] : 0.f;
+    tmem_ld8(tmem + lane_base + L::T_GQ + (1 * 4 + head) * DHP + d0, t8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gk[j] = valid ? __ldg(dk + row + j) + t8[j] : 0.f;
+    tmem_ld8(tmem + lane_base + L::T_GQ + (2 * 4 + head) * DHP + d0, t8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] = valid ? __ldg(dv + row + j) + t8[j] : 0.f;
+    float da8[8], dxv8[8];
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+      const int wb = ((e8 >> 2) + blk) * 16;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        float sa = 0.f, sv = 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          sa += par[L::P_WQ + wb + o * 4 + d] * gq[blk * 4 + o] + par[L::P_WK + wb + o * 4 + d] * gk[blk * 4 + o];
+          sv += par[L::P_WV + wb + o * 4 + d] * gv[blk * 4 + o];
+        }
+        da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
+      }
+    }
+    float dc8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e8 + j;
+      const float dact = da8[j] + (valid ? __ldg(d_act + tm_base + static_cast<size_t>(e) * kTok) : 0.f);
+      dc8[j] = valid ? dact * dsilu(cv8[j]) : 0.f;
+      dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc8[j];
+      dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? dxv8[j] : 0.f;
+      warp_acc(acc + L::A_CB + e, dc8[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) warp_acc(acc + L::A_CW + e * 4 + k, dc8[j] * xr[k][j]);
+    }
+    // operands of the block-diagonal weight-gradient GEMMs (bf16)
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(gq);
+    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tid, (E + e8) / 8)) = pack8_bf16(gk);
+    *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(gv);
+    *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(a8);
+    *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(xm8);
+  }
+#pragma unroll
+  for (int h = 0; h < 8; ++h) warp_acc(acc + L::A_GB + h, dg[h]);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    // d[q_proj|k_proj] as a dense (2E x E) product g_{q|k}^T act; only its 4x4 diagonal blocks are read back
+    umma_gemm(tmem + L::T_DWQK, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
+              umma_idesc(128, E, true, true), kTok, false);
+    umma_gemm(tmem + L::T_DWV, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16,
+              umma_idesc(128, E, true, true), kTok, false);
+    umma_commit(&bar2);
+  }
+  // gate-weight gradient rows hh = 0..7 live in the lanes of warp 0
+  if (warp == 0) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < NQ; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + L::T_DWG + c0, v);
+      if (tid < 8) {
+        float* W = tid < 4 ? gr.igate_weight + tid * 3 * E : gr.fgate_weight + (tid - 4) * 3 * E;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int j = c0 + i, part = j / (4 * DHP), head = (j / DHP) % 4, d = j % DHP;
+          if (d < DH) atomicAdd(W + part * E + head * DH + d, v[i]);
+        }
+      }
+    }
+  }
+  for (int i = tid; i < E * 4; i += kTok) atomicAdd(gr.conv_weight + i, acc[L::A_CW + i]);
+  for (int i = tid; i < E; i += kTok) atomicAdd(gr.conv_bias + i, acc[L::A_CB + i]);
+  if (tid < 4) atomicAdd(gr.igate_bias + tid, acc[L::A_GB + tid]);
+  else if (tid < 8) atomicAdd(gr.fgate_bias + tid - 4, acc[L::A_GB + tid]);
+  mbar_wait(&bar2, 0);
+  tc_fence_after();
+  {
+    // row r of the (2E x E) product: r < E -> q_proj row e_out = r, r >= E -> k_proj; its diagonal block = 4 columns
+    // (TMEM loads take a warp-uniform column address: walk all column groups and keep the one holding the block)
+    const int r = tid, e_out = r % E, blk = e_out / 4;
+    if (warp * 32 < 2 * E) {
+      float keep[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c0 = 0; c0 < E; c0 += 8) {
+        float v[8];
+        tmem_ld8(tmem + lane_base + L::T_DWQK + c0, v);
+        if (((4 * blk) & ~7) == c0) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d) keep[d] = ((4 * blk) & 7) ? v[4 + d] : v[d];
+        }
+      }
+      if (r < 2 * E) {
+        float* W = (r < E ? gr.q_weight : gr.k_weight) + blk * 16 + (e_out % 4) * 4;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) atomicAdd(W + d, keep[d]);
+      }
+    }
+    if (warp * 32 < E) {
+      float keep[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c0 = 0; c0 < E; c0 += 8) {
+        float v[8];
+        tmem_ld8(tmem + lane_base + L::T_DWV + c0, v);
+        if (((4 * blk) & ~7) == c0) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d) keep[d] = ((4 * blk) & 7) ? v[4 + d] : v[d];
+        }
+      }
+      if (r < E) {
+        float* W = gr.v_weight + blk * 16 + (e_out % 4) * 4;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) atomicAdd(W + d, keep[d]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int C>
+static int launch_pre_bwd(const float* x, const float* dy, const float* xm, const void* q, const void* k, const void* v, const float* dq,
+                          const float* dk, const float* dv, const float* dig, const float* dfg, const float* d_act, const float* dz,
+                          const xhved_vil_params* p, const VilGeom& g, float* dx, const xhved_vil_grads* gr, float* ws_dconv,
+                          float* ws_dxmv, cudaStream_t st) {
+  if constexpr (C <= 32) {
+    const size_t smem = PreBwdATC<C>::TOTAL;
+    cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ProfScope ps(K_VIL_PRE_BWD_A, st);
+    vil_pre_bwd_a_tc_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(*p, g, xm, (const unsigned char*)q, (const unsigned char*)k,
+                                                               (const unsigned char*)v, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv, *gr);
+  } else {
+    // dim 64: the CUDA-core kernel A (recomputes the forward from x); TMEM cannot hold its gate products in one pass
     const size_t smem = PreBwdASmem<C>::TOTAL * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -780,17 +1055,20 @@ extern "C" int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, cons
   }
 }
 
-extern "C" int xhved_vil_pre_bwd(const float* x, const float* dy, const float* dq, const float* dk, const float* dv, const float* dig,
-                                 const float* dfg, const float* d_act, const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh,
-                                 float* dx, const xhved_vil_grads* g, float* ws_dconv, float* ws_dxmv, void* stream) {
+extern "C" int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const void* q_tiles, const void* k_tiles,
+                                 const void* v_tiles, const float* dq, const float* dk, const float* dv, const float* dig, const float* dfg,
+                                 const float* d_act, const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx,
+                                 const xhved_vil_grads* g, float* ws_dconv, float* ws_dxmv, void* stream) {
   VilGeom geo;
   if (int rc = vil_validate(sh, &geo)) return rc;
-  if (!x || !dy || !dq || !dk || !dv || !dig || !dfg || !d_act || !dz || !p || !dx || !g || !ws_dconv || !ws_dxmv) return XHVED_ERR_BAD_ARG;
+  if (!x || !dy || !xm || !q_tiles || !k_tiles || !v_tiles || !dq || !dk || !dv || !dig || !dfg || !d_act || !dz || !p || !dx || !g ||
+      !ws_dconv || !ws_dxmv)
+    return XHVED_ERR_BAD_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (sh->C) {
-    case 16: return launch_pre_bwd<16>(x, dy, dq, dk, dv, dig, dfg, d_act, dz, p, geo, dx, g, ws_dconv, ws_dxmv, st);
-    case 32: return launch_pre_bwd<32>(x, dy, dq, dk, dv, dig, dfg, d_act, dz, p, geo, dx, g, ws_dconv, ws_dxmv, st);
-    case 64: return launch_pre_bwd<64>(x, dy, dq, dk, dv, dig, dfg, d_act, dz, p, geo, dx, g, ws_dconv, ws_dxmv, st);
+    case 16: return launch_pre_bwd<16>(x, dy, xm, q_tiles, k_tiles, v_tiles, dq, dk, dv, dig, dfg, d_act, dz, p, geo, dx, g, ws_dconv, ws_dxmv, st);
+    case 32: return launch_pre_bwd<32>(x, dy, xm, q_tiles, k_tiles, v_tiles, dq, dk, dv, dig, dfg, d_act, dz, p, geo, dx, g, ws_dconv, ws_dxmv, st);
+    case 64: return launch_pre_bwd<64>(x, dy, xm, q_tiles, k_tiles, v_tiles, dq, dk, dv, dig, dfg, d_act, dz, p, geo, dx, g, ws_dconv, ws_dxmv, st);
     default: return XHVED_ERR_UNSUPPORTED_DIM;
   }
 }

@@ -329,8 +329,8 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float =
     gb = mlstm_bwd_tiles(c, dh_tiles, eps)
     ws_dconv = torch.empty_like(ws.act)
     ws_dxmv = torch.empty_like(ws.act)
-    check(lib.xhved_vil_pre_bwd(ptr(x_tok), ptr(dy_tok), ptr(gb.dq), ptr(gb.dk), ptr(gb.dv), ptr(gb.dig), ptr(gb.dfg), ptr(d_act),
-                                ptr(dz), ctypes.byref(ps), ctypes.byref(sh), ptr(dx), ctypes.byref(gs), ptr(ws_dconv), ptr(ws_dxmv),
+    check(lib.xhved_vil_pre_bwd(ptr(x_tok), ptr(dy_tok), ptr(ws.xm), ptr(c.q), ptr(c.k), ptr(c.v), ptr(gb.dq), ptr(gb.dk), ptr(gb.dv),
+                                ptr(gb.dig), ptr(gb.dfg), ptr(d_act), ptr(dz), ctypes.byref(ps), ctypes.byref(sh), ptr(dx), ctypes.byref(gs), ptr(ws_dconv), ptr(ws_dxmv),
                                 stream()), "xhved_vil_pre_bwd")
     return dx, grads
 
