@@ -55,6 +55,48 @@ __device__ __forceinline__ void warp_acc(float* slot, float v) {
   if ((threadIdx.x & 31) == 0) atomicAdd(slot, v);
 }
 
+// Reduce 32 per-lane values across the warp at once: after the call lane i holds sum over lanes of v[i] (in v[0]).
+// 31 shuffles instead of 32 x 5 for 32 separate butterfly reductions.
+__device__ __forceinline__ float warp_transpose_sum32(float* v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = (up ? v[i + n / 2] : v[i]) + recv;
+    }
+  }
+  return v[0];
+}
+// N (power of two <= 32) per-lane values -> lane i holds the warp sum of v[i & (N-1)]
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum(float* v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = N / 2, n = N; s >= 1; s >>= 1, n >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[i] = (up ? v[i + n / 2] : v[i]) + recv;
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int s = N; s < 32; s <<= 1) r += __shfl_xor_sync(0xffffffffu, r, s);
+  return r;
+}
+// N per-token values -> N shared accumulators (slot i <- warp sum of v[i]); one conflict-free smem atomic per lane
+template <int N>
+__device__ __forceinline__ void warp_acc_vec(float* slots, float* v) {
+  const float r = warp_transpose_sum<N>(v);
+  if ((threadIdx.x & 31) < N) atomicAdd(slots + (threadIdx.x & 31), r);
+}
+
 // out[a][b] += sum_tok A[tok*lda + a] * Bm[tok*ldb + b]   (a < na, b < nb; ntok rows staged in shared memory)
 // Each thread owns outputs idx = tid, tid + nthreads, ...; consecutive threads take consecutive b.
 __device__ __forceinline__ void outer_accumulate(const float* sA, int lda, int na, const float* sB, int ldb, int nb, int ntok,

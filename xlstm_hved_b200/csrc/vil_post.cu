@@ -168,10 +168,11 @@ struct PostBwdTC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kTok) vil_post_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
-                                                             const float* __restrict__ act, const float* __restrict__ z,
-                                                             xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
-                                                             float* __restrict__ d_act, float* __restrict__ dz, xhved_vil_grads gr) {
+__global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
+                                                                 const float* __restrict__ act, const float* __restrict__ z,
+                                                                 xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
+                                                                 float* __restrict__ d_act, float* __restrict__ dz, xhved_vil_grads gr) {
+  // 512 threads: thread = (token, head)
   using L = PostBwdTC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(kTok) vil_post_bwd_kernel(const float* __restr
   __shared__ __align__(8) uint64_t bar1, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int tok = tid & (kTok - 1), head = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
   if (tid == 0) {
     mbar_init(&bar1, 1);
@@ -189,20 +191,19 @@ __global__ void __launch_bounds__(kTok) vil_post_bwd_kernel(const float* __restr
   if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
   stage(par + L::P_OW, p.outnorm_weight, E);
   stage(par + L::P_SK, p.learnable_skip, E);
-  for (int i = tid; i < 2 * E; i += kTok) par[L::P_ASK + i] = 0.f;
+  for (int i = tid; i < 2 * E; i += blockDim.x) par[L::P_ASK + i] = 0.f;
   stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
-  const int tau = ch * kTok + tid;
+  const int tau = ch * kTok + tok;
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-#pragma unroll
-  for (int cg = 0; cg < C / 8; ++cg) {
+  for (int cg = head; cg < C / 8; cg += 4) {
     float v8[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v8[i] = valid ? __ldg(dy + b * g.ysb + n * g.ysn + (cg * 8 + i) * g.ysc) : 0.f;
     uint4 hi, lo;
     split8_hilo(v8, hi, lo);
-    *reinterpret_cast<uint4*>(smem + L::DYHI + tile_off16(kTok, tid, cg)) = hi;
-    *reinterpret_cast<uint4*>(smem + L::DYLO + tile_off16(kTok, tid, cg)) = lo;
+    *reinterpret_cast<uint4*>(smem + L::DYHI + tile_off16(kTok, tok, cg)) = hi;
+    *reinterpret_cast<uint4*>(smem + L::DYLO + tile_off16(kTok, tok, cg)) = lo;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -215,72 +216,65 @@ __global__ void __launch_bounds__(kTok) vil_post_bwd_kernel(const float* __restr
                    smem_u32(smem + L::WDLO), 128, C * 16, umma_idesc(128, E, false, true), C);
     umma_commit(&bar1);
   }
+  // recompute the gated activation of this (token, head) while the MMA runs
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
+  const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
+  float hg[DH], xhat[DH], rstd;
+  const float* ow = par + L::P_OW + head * DH;
+  const float* sk = par + L::P_SK + head * DH;
+  const float* actp = act + tm_base + static_cast<size_t>(head * DH) * kTok;
+  const float* zp = z + tm_base + static_cast<size_t>(head * DH) * kTok;
+  gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tok, ow, sk, actp, zp, kTok, hg, xhat, &rstd);
   mbar_wait(&bar1, 0);
   tc_fence_after();
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  float dhg[DH];
+  if (DH >= 16) {
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 16) tmem_ld16(tmem + lane_base + head * DH + c0, dhg + c0);
+  } else {
+    tmem_ld8(tmem + lane_base + head * DH, dhg);
+  }
+  float gg[DH], r1[DH], r2[DH], mean_g = 0.f, mean_gx = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) {
+    const int e = head * DH + d;
+    const float a = __ldg(actp + d * kTok), zz = __ldg(zp + d * kTok);
+    const float sz = silu(zz);
+    const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
+    const float dhs = valid ? dhg[d] * sz : 0.f;
+    dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsilu(zz) : 0.f;
+    d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sk[d];
+    r1[d] = dhs * a;
+    r2[d] = dhs * xhat[d];
+    gg[d] = dhs * (1.f + ow[d]);
+    mean_g += gg[d];
+    mean_gx += gg[d] * xhat[d];
+  }
+  mean_g *= (1.f / DH);
+  mean_gx *= (1.f / DH);
   const uint4 zero = make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-  for (int head = 0; head < 4; ++head) {
-    const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
-    float hg[DH], xhat[DH], rstd;
-    const float* ow = par + L::P_OW + head * DH;
-    const float* sk = par + L::P_SK + head * DH;
-    const float* actp = act + tm_base + static_cast<size_t>(head * DH) * kTok;
-    const float* zp = z + tm_base + static_cast<size_t>(head * DH) * kTok;
-    gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tid, ow, sk, actp, zp, kTok, hg, xhat, &rstd);
-    float dhg[DH];
 #pragma unroll
-    for (int c0 = 0; c0 < DH; c0 += 8) {
-      // 8-column TMEM reads keep the register footprint small
-      float t16[16];
-      if ((c0 & 8) == 0) {
-        if (DH >= 16) {
-          tmem_ld16(tmem + lane_base + head * DH + c0, t16);
+  for (int cg = 0; cg < DHP / 8; ++cg) {
+    uint4 u = zero;
+    if (cg * 8 < DH) {
+      float o8[8], hg8[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dhg[c0 + i] = t16[i];
-        } else {
-          // DH = 8: two heads share a 16-column read
-          tmem_ld16(tmem + lane_base + (head & ~1) * DH, t16);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dhg[i] = t16[(head & 1) * 8 + i];
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int d = cg * 8 + i;
+        o8[i] = rstd * (gg[d] - mean_g - xhat[d] * mean_gx);
+        hg8[i] = valid ? hg[d] : 0.f;
       }
+      u = pack8_bf16(o8);
+      *reinterpret_cast<uint4*>(smem + L::HG + tile_off16(kTok, tok, head * (DH / 8) + cg)) = pack8_bf16(hg8);
     }
-    float gg[DH], mean_g = 0.f, mean_gx = 0.f;
+    *reinterpret_cast<uint4*>(smem + L::DHT + tile_off16(kTok, tok, head * (DHP / 8) + cg)) = u;
+  }
+  // d learnable_skip / d outnorm.weight of this head's channels
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      const int e = head * DH + d;
-      const float a = __ldg(actp + d * kTok), zz = __ldg(zp + d * kTok);
-      const float sz = silu(zz);
-      const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
-      const float dhs = valid ? dhg[d] * sz : 0.f;
-      dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsilu(zz) : 0.f;
-      d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sk[d];
-      warp_acc(par + L::P_ASK + e, dhs * a);
-      warp_acc(par + L::P_AOW + e, dhs * xhat[d]);
-      gg[d] = dhs * (1.f + ow[d]);
-      mean_g += gg[d];
-      mean_gx += gg[d] * xhat[d];
-    }
-    mean_g *= (1.f / DH);
-    mean_gx *= (1.f / DH);
-#pragma unroll
-    for (int cg = 0; cg < DHP / 8; ++cg) {
-      uint4 u = zero;
-      if (cg * 8 < DH) {
-        float o8[8], hg8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int d = cg * 8 + i;
-          o8[i] = rstd * (gg[d] - mean_g - xhat[d] * mean_gx);
-          hg8[i] = valid ? hg[d] : 0.f;
-        }
-        u = pack8_bf16(o8);
-        *reinterpret_cast<uint4*>(smem + L::HG + tile_off16(kTok, tid, head * (DH / 8) + cg)) = pack8_bf16(hg8);
-      }
-      *reinterpret_cast<uint4*>(smem + L::DHT + tile_off16(kTok, tid, head * (DHP / 8) + cg)) = u;
-    }
+  for (int d0 = 0; d0 < DH; d0 += (DH < 32 ? DH : 32)) {
+    warp_acc_vec<(DH < 32 ? DH : 32)>(par + L::P_ASK + head * DH + d0, r1 + d0);
+    warp_acc_vec<(DH < 32 ? DH : 32)>(par + L::P_AOW + head * DH + d0, r2 + d0);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -293,26 +287,26 @@ __global__ void __launch_bounds__(kTok) vil_post_bwd_kernel(const float* __restr
     umma_commit(&bar2);
     constexpr uint32_t HT = kTok * DHP * 2;
 #pragma unroll 1
-    for (int head = 0; head < 4; ++head) {
-      const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
-      bulk_s2g(dh_tiles + tile * HT, smem + L::DHT + head * HT, HT);
+    for (int hd = 0; hd < 4; ++hd) {
+      const size_t t2 = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
+      bulk_s2g(dh_tiles + t2 * HT, smem + L::DHT + hd * HT, HT);
     }
     bulk_commit();
   }
-  for (int e = tid; e < E; e += kTok) {
+  for (int e = tid; e < E; e += blockDim.x) {
     atomicAdd(gr.learnable_skip + e, par[L::P_ASK + e]);
     atomicAdd(gr.outnorm_weight + e, par[L::P_AOW + e]);
   }
   mbar_wait(&bar2, 0);
   tc_fence_after();
-  if (warp * 32 < E) {
-#pragma unroll
-    for (int c0 = 0; c0 < C; c0 += 16) {
+  if ((warp & 3) * 32 < E) {
+#pragma unroll 1
+    for (int c0 = head * 16; c0 < C; c0 += 64) {
       float v[16];
       tmem_ld16(tmem + lane_base + E + c0, v);
-      if (tid < E) {
+      if (tok < E) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(gr.proj_down_weight + static_cast<size_t>(c0 + i) * E + tid, v[i]);
+        for (int i = 0; i < 16; ++i) atomicAdd(gr.proj_down_weight + static_cast<size_t>(c0 + i) * E + tok, v[i]);
       }
     }
   }
@@ -329,7 +323,7 @@ static int launch_post_bwd(const float* dy, const void* h, const float* act, con
   cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_BWD, st);
-  vil_post_bwd_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g, (unsigned char*)dh, d_act, dz, *gr);
+  vil_post_bwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g, (unsigned char*)dh, d_act, dz, *gr);
   return (int)cudaGetLastError();
 }
 

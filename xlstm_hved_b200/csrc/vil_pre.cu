@@ -611,10 +611,12 @@ struct PreBwdBTC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kTok) vil_pre_bwd_b_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                                 xhved_vil_params p, VilGeom g, const float* __restrict__ dconv,
-                                                                 const float* __restrict__ dxmv, const float* __restrict__ dz,
-                                                                 float* __restrict__ dx, xhved_vil_grads gr) {
+__global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                     xhved_vil_params p, VilGeom g, const float* __restrict__ dconv,
+                                                                     const float* __restrict__ dxmv, const float* __restrict__ dz,
+                                                                     float* __restrict__ dx, xhved_vil_grads gr) {
+  // 512 threads: thread = (token, part); the four parts split the 2E columns of d[x_mlstm | z]; part 0 owns the
+  // LayerNorm backward of its token
   using L = PreBwdBTC<C>;
   constexpr int E = L::E;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -622,6 +624,7 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_tc_kernel(const float* __r
   __shared__ __align__(8) uint64_t bar1;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int tok = tid & (kTok - 1), part = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
   if (tid == 0) {
     mbar_init(&bar1, 1);
@@ -631,52 +634,60 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_tc_kernel(const float* __r
   if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
   stage(par + L::P_CW, p.conv_weight, E * 4);
   stage(par + L::P_NW, p.norm_weight, C);
-  for (int i = tid; i < C; i += kTok) par[L::P_ANW + i] = 0.f;
+  for (int i = tid; i < C; i += blockDim.x) par[L::P_ANW + i] = 0.f;
   stage_weight_tile(p.proj_up_weight, 2 * E, C, 2 * E, smem + L::WHI, smem + L::WLO);
-  const int tau = ch * kTok + tid;
+  const int tau = ch * kTok + tok;
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-  float xin[C];
+  float xin[C], xn[C], rstd = 0.f;
+  if (part == 0) {
 #pragma unroll
-  for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
+    for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
+  }
   __syncthreads();
-  float xn[C], rstd;
-  layernorm_token<C>(xin, par + L::P_NW, xn, &rstd);
+  if (part == 0) {
+    layernorm_token<C>(xin, par + L::P_NW, xn, &rstd);
 #pragma unroll
-  for (int cg = 0; cg < C / 8; ++cg) {
-    float v8[8];
+    for (int cg = 0; cg < C / 8; ++cg) {
+      float v8[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
-    *reinterpret_cast<uint4*>(smem + L::XNT + tile_off16(kTok, tid, cg)) = pack8_bf16(v8);
+      for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
+      *reinterpret_cast<uint4*>(smem + L::XNT + tile_off16(kTok, tok, cg)) = pack8_bf16(v8);
+    }
   }
   // d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
   const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
 #pragma unroll 1
-  for (int o8 = 0; o8 < 2 * E; o8 += 8) {
+  for (int o8 = part * 8; o8 < 2 * E; o8 += 32) {
     float d8[8];
+    if (o8 < E) {
+      float dc[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int o = o8 + i;
-      float d;
-      if (o8 < E) {
-        d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tid);
+      for (int k = 0; k < 4; ++k) {
+        const int tp = tau + k;
+        const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int tp = tau + k;
-          if (tp < g.S) {
-            const size_t off = (static_cast<size_t>(b) * g.nc + tp / kTok) * E * kTok + static_cast<size_t>(o) * kTok + (tp % kTok);
-            d += par[L::P_CW + o * 4 + 3 - k] * __ldg(dconv + off);
-          }
-        }
-      } else {
-        d = __ldg(dz + tm_chunk + static_cast<size_t>(o - E) * kTok + tid);
+        for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
       }
-      d8[i] = valid ? d : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = o8 + i;
+        float d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d += par[L::P_CW + o * 4 + 3 - k] * dc[k][i];
+        d8[i] = valid ? d : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
+        d8[i] = valid ? d : 0.f;
+      }
     }
     uint4 hi, lo;
     split8_hilo(d8, hi, lo);
-    *reinterpret_cast<uint4*>(smem + L::DINHI + tile_off16(kTok, tid, o8 / 8)) = hi;
-    *reinterpret_cast<uint4*>(smem + L::DINLO + tile_off16(kTok, tid, o8 / 8)) = lo;
+    *reinterpret_cast<uint4*>(smem + L::DINHI + tile_off16(kTok, tok, o8 / 8)) = hi;
+    *reinterpret_cast<uint4*>(smem + L::DINLO + tile_off16(kTok, tok, o8 / 8)) = lo;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -696,36 +707,40 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_tc_kernel(const float* __r
   }
   mbar_wait(&bar1, 0);
   tc_fence_after();
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  float dxn[C];
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  if (part == 0) {
+    float dxn[C], red[C];
 #pragma unroll
-  for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16(tmem + lane_base + c0, dxn + c0);
-  float mean_g = 0.f, mean_gx = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float w1 = 1.f + par[L::P_NW + c];
-    const float xhat = xn[c] / w1;
-    warp_acc(par + L::P_ANW + c, valid ? dxn[c] * xhat : 0.f);
-    dxn[c] *= w1;
-    xn[c] = xhat;
-    mean_g += dxn[c];
-    mean_gx += dxn[c] * xhat;
-  }
-  mean_g *= (1.f / C);
-  mean_gx *= (1.f / C);
-  if (valid) {
+    for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16(tmem + lane_base + c0, dxn + c0);
+    float mean_g = 0.f, mean_gx = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float v = rstd * (dxn[c] - mean_g - xn[c] * mean_gx);
-      dx[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) + v;
+      const float w1 = 1.f + par[L::P_NW + c];
+      const float xhat = xn[c] / w1;
+      red[c] = valid ? dxn[c] * xhat : 0.f;
+      dxn[c] *= w1;
+      xn[c] = xhat;
+      mean_g += dxn[c];
+      mean_gx += dxn[c] * xhat;
     }
+    mean_g *= (1.f / C);
+    mean_gx *= (1.f / C);
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float v = rstd * (dxn[c] - mean_g - xn[c] * mean_gx);
+        dx[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) + v;
+      }
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < C; c0 += (C < 32 ? C : 32)) warp_acc_vec<(C < 32 ? C : 32)>(par + L::P_ANW + c0, red + c0);
   }
-  // weight-gradient rows: thread o (and o + 128 for the second M tile)
+  // weight-gradient rows: lane = output row o (second M tile: o + 128); the parts split the C columns
 #pragma unroll
   for (int mt = 0; mt < L::MT; ++mt) {
-    const int o = mt * 128 + tid;
-#pragma unroll
-    for (int c0 = 0; c0 < C; c0 += 16) {
+    const int o = mt * 128 + tok;
+#pragma unroll 1
+    for (int c0 = part * 16; c0 < C; c0 += 64) {
       float v[16];
       tmem_ld16(tmem + lane_base + C + mt * C + c0, v);
       if (o < 2 * E) {
@@ -735,7 +750,7 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_b_tc_kernel(const float* __r
     }
   }
   __syncthreads();
-  for (int c = tid; c < C; c += kTok) atomicAdd(gr.norm_weight + c, par[L::P_ANW + c]);
+  for (int c = tid; c < C; c += blockDim.x) atomicAdd(gr.norm_weight + c, par[L::P_ANW + c]);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
@@ -760,14 +775,15 @@ struct PreBwdATC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
-                                                                 const unsigned char* __restrict__ q_tiles,
-                                                                 const unsigned char* __restrict__ k_tiles,
-                                                                 const unsigned char* __restrict__ v_tiles, const float* __restrict__ dq,
-                                                                 const float* __restrict__ dk, const float* __restrict__ dv,
-                                                                 const float* __restrict__ dig, const float* __restrict__ dfg,
-                                                                 const float* __restrict__ d_act, float* __restrict__ dconv_out,
-                                                                 float* __restrict__ dxmv_out, xhved_vil_grads gr) {
+__global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
+                                                                     const unsigned char* __restrict__ q_tiles,
+                                                                     const unsigned char* __restrict__ k_tiles,
+                                                                     const unsigned char* __restrict__ v_tiles, const float* __restrict__ dq,
+                                                                     const float* __restrict__ dk, const float* __restrict__ dv,
+                                                                     const float* __restrict__ dig, const float* __restrict__ dfg,
+                                                                     const float* __restrict__ d_act, float* __restrict__ dconv_out,
+                                                                     float* __restrict__ dxmv_out, xhved_vil_grads gr) {
+  // 512 threads: thread = (token, head); the four head groups of a token share the TMEM lane of that token
   using L = PreBwdATC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
   constexpr uint32_t HT = kTok * DHP * 2;
@@ -776,6 +792,7 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
   __shared__ __align__(8) uint64_t bar_load, bar1, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int tok = tid & (kTok - 1), head = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
   if (tid == 0) {
     mbar_init(&bar_load, 1);
@@ -789,11 +806,11 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
   if (tid == 0) {
     mbar_expect_tx(&bar_load, 12 * HT);
 #pragma unroll 1
-    for (int head = 0; head < 4; ++head) {
-      const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
-      bulk_g2s(smem + L::QKV + (0 * 4 + head) * HT, q_tiles + tile * HT, HT, &bar_load);
-      bulk_g2s(smem + L::QKV + (1 * 4 + head) * HT, k_tiles + tile * HT, HT, &bar_load);
-      bulk_g2s(smem + L::QKV + (2 * 4 + head) * HT, v_tiles + tile * HT, HT, &bar_load);
+    for (int hd = 0; hd < 4; ++hd) {
+      const size_t tile = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
+      bulk_g2s(smem + L::QKV + (0 * 4 + hd) * HT, q_tiles + tile * HT, HT, &bar_load);
+      bulk_g2s(smem + L::QKV + (1 * 4 + hd) * HT, k_tiles + tile * HT, HT, &bar_load);
+      bulk_g2s(smem + L::QKV + (2 * 4 + hd) * HT, v_tiles + tile * HT, HT, &bar_load);
     }
   }
   stage(par + L::P_CW, p.conv_weight, E * 4);
@@ -801,43 +818,44 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
   stage(par + L::P_WQ, p.q_weight, E * 4);
   stage(par + L::P_WK, p.k_weight, E * 4);
   stage(par + L::P_WV, p.v_weight, E * 4);
-  for (int i = tid; i < E * 4 + E + 8; i += kTok) par[L::A_CW + i] = 0.f;
-  for (int gi = tid; gi < 16 * (NQ / 8); gi += kTok) {
+  for (int i = tid; i < E * 4 + E + 8; i += blockDim.x) par[L::A_CW + i] = 0.f;
+  for (int gi = tid; gi < 16 * (NQ / 8); gi += blockDim.x) {
     const int hh = gi % 16, cg = gi / 16;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int j = cg * 8 + i, part = j / (4 * DHP), head = (j / DHP) % 4, d = j % DHP;
+      const int j = cg * 8 + i, part = j / (4 * DHP), hd = (j / DHP) % 4, d = j % DHP;
       const float* W = hh < 4 ? p.igate_weight + hh * 3 * E : p.fgate_weight + (hh - 4) * 3 * E;
-      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + head * DH + d) : 0.f;
+      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + hd * DH + d) : 0.f;
     }
     uint4 h, l;
     split8_hilo(v, h, l);
     *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
     *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
   }
-  const int tau = ch * kTok + tid;
+  const int tau = ch * kTok + tok;
   const bool valid = tau < g.S;
   float dg[8];
+  if (head == 0) {
 #pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tid;
-    dg[h] = valid ? __ldg(dig + o) : 0.f;
-    dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
-  }
-  {
+    for (int h = 0; h < 4; ++h) {
+      const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
+      dg[h] = valid ? __ldg(dig + o) : 0.f;
+      dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
+    }
     uint4 hi, lo;
     split8_hilo(dg, hi, lo);
-    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tid, 0)) = hi;
-    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tid, 0)) = lo;
-    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tid, 1)) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tid, 1)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 0)) = hi;
+    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 0)) = lo;
+    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   mbar_wait(&bar_load, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (head == 0) warp_acc_vec<8>(par + L::A_GB, dg);       // gate bias gradients (accumulators are zeroed by now)
   const uint32_t tmem = tmem_slot;
   if (tid == 0) {
     // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
@@ -852,12 +870,12 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
   }
   mbar_wait(&bar1, 0);
   tc_fence_after();
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
   float* acc = par;
 #pragma unroll 1
-  for (int e8 = 0; e8 < E; e8 += 8) {
-    const int head = e8 / DH, d0 = e8 % DH;
+  for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
+    const int d0 = e8 % DH;
     float a8[8], xm8[8], cv8[8], xr[4][8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k
@@ -869,6 +887,18 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
         xr[k][j] = (tp >= 0 && tp < g.S) ? __ldg(xm + off) : 0.f;
       }
     }
+    float gq[8], gk[8], gv[8], dsk[8];
+    const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tok) * DHP + d0;
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(dq + row)), c = __ldg(reinterpret_cast<const float4*>(dq + row + 4));
+      gq[0] = a.x, gq[1] = a.y, gq[2] = a.z, gq[3] = a.w, gq[4] = c.x, gq[5] = c.y, gq[6] = c.z, gq[7] = c.w;
+      const float4 a2 = __ldg(reinterpret_cast<const float4*>(dk + row)), c2 = __ldg(reinterpret_cast<const float4*>(dk + row + 4));
+      gk[0] = a2.x, gk[1] = a2.y, gk[2] = a2.z, gk[3] = a2.w, gk[4] = c2.x, gk[5] = c2.y, gk[6] = c2.z, gk[7] = c2.w;
+      const float4 a3 = __ldg(reinterpret_cast<const float4*>(dv + row)), c3 = __ldg(reinterpret_cast<const float4*>(dv + row + 4));
+      gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dsk[j] = __ldg(d_act + tm_base + static_cast<size_t>(e8 + j) * kTok);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = e8 + j;
@@ -877,18 +907,17 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
       a8[j] = silu(cv8[j]);
       xm8[j] = xr[3][j];
     }
-    // upstream gradients of q,k,v: cell gradients + gate path (TMEM)
-    float gq[8], gk[8], gv[8], t8[8];
-    const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tid) * DHP + d0;
+    // gate-path contribution (TMEM), zero for padding rows
+    float t8[8];
     tmem_ld8(tmem + lane_base + L::T_GQ + (0 * 4 + head) * DHP + d0, t8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gq[j] = valid ? __ldg(dq + row + j) + t8[j] : 0.f;
+    for (int j = 0; j < 8; ++j) gq[j] = valid ? gq[j] + t8[j] : 0.f;
     tmem_ld8(tmem + lane_base + L::T_GQ + (1 * 4 + head) * DHP + d0, t8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gk[j] = valid ? __ldg(dk + row + j) + t8[j] : 0.f;
+    for (int j = 0; j < 8; ++j) gk[j] = valid ? gk[j] + t8[j] : 0.f;
     tmem_ld8(tmem + lane_base + L::T_GQ + (2 * 4 + head) * DHP + d0, t8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gv[j] = valid ? __ldg(dv + row + j) + t8[j] : 0.f;
+    for (int j = 0; j < 8; ++j) gv[j] = valid ? gv[j] + t8[j] : 0.f;
     float da8[8], dxv8[8];
 #pragma unroll
     for (int blk = 0; blk < 2; ++blk) {
@@ -904,31 +933,29 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
         da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
       }
     }
-    float dc8[8];
+    float dc8[8], prod[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = e8 + j;
-      const float dact = da8[j] + (valid ? __ldg(d_act + tm_base + static_cast<size_t>(e) * kTok) : 0.f);
-      dc8[j] = valid ? dact * dsilu(cv8[j]) : 0.f;
+      dc8[j] = valid ? (da8[j] + dsk[j]) * dsilu(cv8[j]) : 0.f;
       dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc8[j];
       dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? dxv8[j] : 0.f;
-      warp_acc(acc + L::A_CB + e, dc8[j]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) warp_acc(acc + L::A_CW + e * 4 + k, dc8[j] * xr[k][j]);
+      for (int k = 0; k < 4; ++k) prod[j * 4 + k] = dc8[j] * xr[k][j];
     }
+    warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
+    warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
     // operands of the block-diagonal weight-gradient GEMMs (bf16)
     if (!valid) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
     }
-    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(gq);
-    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tid, (E + e8) / 8)) = pack8_bf16(gk);
-    *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(gv);
-    *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(a8);
-    *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tid, e8 / 8)) = pack8_bf16(xm8);
+    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gq);
+    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, (E + e8) / 8)) = pack8_bf16(gk);
+    *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gv);
+    *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(a8);
+    *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(xm8);
   }
-#pragma unroll
-  for (int h = 0; h < 8; ++h) warp_acc(acc + L::A_GB + h, dg[h]);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -941,64 +968,55 @@ __global__ void __launch_bounds__(kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params
               umma_idesc(128, E, true, true), kTok, false);
     umma_commit(&bar2);
   }
-  // gate-weight gradient rows hh = 0..7 live in the lanes of warp 0
-  if (warp == 0) {
+  // gate-weight gradient rows hh = 0..7 live in TMEM lanes 0..7: warps 0, 4, 8, 12 (quadrant 0) share the columns
+  if ((warp & 3) == 0) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < NQ; c0 += 16) {
+    for (int c0 = head * 16; c0 < NQ; c0 += 64) {
       float v[16];
       tmem_ld16(tmem + lane_base + L::T_DWG + c0, v);
-      if (tid < 8) {
-        float* W = tid < 4 ? gr.igate_weight + tid * 3 * E : gr.fgate_weight + (tid - 4) * 3 * E;
+      if (tok < 8) {
+        float* W = tok < 4 ? gr.igate_weight + tok * 3 * E : gr.fgate_weight + (tok - 4) * 3 * E;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int j = c0 + i, part = j / (4 * DHP), head = (j / DHP) % 4, d = j % DHP;
-          if (d < DH) atomicAdd(W + part * E + head * DH + d, v[i]);
+          const int j = c0 + i, part = j / (4 * DHP), hd = (j / DHP) % 4, d = j % DHP;
+          if (d < DH) atomicAdd(W + part * E + hd * DH + d, v[i]);
         }
       }
     }
   }
-  for (int i = tid; i < E * 4; i += kTok) atomicAdd(gr.conv_weight + i, acc[L::A_CW + i]);
-  for (int i = tid; i < E; i += kTok) atomicAdd(gr.conv_bias + i, acc[L::A_CB + i]);
+  for (int i = tid; i < E * 4; i += blockDim.x) atomicAdd(gr.conv_weight + i, acc[L::A_CW + i]);
+  for (int i = tid; i < E; i += blockDim.x) atomicAdd(gr.conv_bias + i, acc[L::A_CB + i]);
   if (tid < 4) atomicAdd(gr.igate_bias + tid, acc[L::A_GB + tid]);
   else if (tid < 8) atomicAdd(gr.fgate_bias + tid - 4, acc[L::A_GB + tid]);
   mbar_wait(&bar2, 0);
   tc_fence_after();
   {
-    // row r of the (2E x E) product: r < E -> q_proj row e_out = r, r >= E -> k_proj; its diagonal block = 4 columns
-    // (TMEM loads take a warp-uniform column address: walk all column groups and keep the one holding the block)
-    const int r = tid, e_out = r % E, blk = e_out / 4;
-    if (warp * 32 < 2 * E) {
-      float keep[4] = {0.f, 0.f, 0.f, 0.f};
+    // row r of the (2E x E) product: r < E -> q_proj row e_out = r, r >= E -> k_proj; its diagonal block = 4 columns.
+    // TMEM loads take a warp-uniform column address: every head group walks a quarter of the column groups.
+    const int r = tok, e_out = r % E, blk = e_out / 4;
+    const int want = (4 * blk) & ~7;
+    if ((warp & 3) * 32 < 2 * E) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < E; c0 += 8) {
+      for (int c0 = head * 8; c0 < E; c0 += 32) {
         float v[8];
         tmem_ld8(tmem + lane_base + L::T_DWQK + c0, v);
-        if (((4 * blk) & ~7) == c0) {
+        if (want == c0 && r < 2 * E) {
+          float* W = (r < E ? gr.q_weight : gr.k_weight) + blk * 16 + (e_out % 4) * 4;
 #pragma unroll
-          for (int d = 0; d < 4; ++d) keep[d] = ((4 * blk) & 7) ? v[4 + d] : v[d];
+          for (int d = 0; d < 4; ++d) atomicAdd(W + d, ((4 * blk) & 7) ? v[4 + d] : v[d]);
         }
-      }
-      if (r < 2 * E) {
-        float* W = (r < E ? gr.q_weight : gr.k_weight) + blk * 16 + (e_out % 4) * 4;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) atomicAdd(W + d, keep[d]);
       }
     }
-    if (warp * 32 < E) {
-      float keep[4] = {0.f, 0.f, 0.f, 0.f};
+    if ((warp & 3) * 32 < E) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < E; c0 += 8) {
+      for (int c0 = head * 8; c0 < E; c0 += 32) {
         float v[8];
         tmem_ld8(tmem + lane_base + L::T_DWV + c0, v);
-        if (((4 * blk) & ~7) == c0) {
+        if (want == c0 && r < E) {
+          float* W = gr.v_weight + blk * 16 + (e_out % 4) * 4;
 #pragma unroll
-          for (int d = 0; d < 4; ++d) keep[d] = ((4 * blk) & 7) ? v[4 + d] : v[d];
+          for (int d = 0; d < 4; ++d) atomicAdd(W + d, ((4 * blk) & 7) ? v[4 + d] : v[d]);
         }
-      }
-      if (r < E) {
-        float* W = gr.v_weight + blk * 16 + (e_out % 4) * 4;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) atomicAdd(W + d, keep[d]);
       }
     }
   }
@@ -1017,7 +1035,7 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_A, st);
-    vil_pre_bwd_a_tc_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(*p, g, xm, (const unsigned char*)q, (const unsigned char*)k,
+    vil_pre_bwd_a_tc_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(*p, g, xm, (const unsigned char*)q, (const unsigned char*)k,
                                                                (const unsigned char*)v, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv, *gr);
   } else {
     // dim 64: the CUDA-core kernel A (recomputes the forward from x); TMEM cannot hold its gate products in one pass
@@ -1032,7 +1050,7 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_b_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_B, st);
-    vil_pre_bwd_b_tc_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr);
+    vil_pre_bwd_b_tc_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr);
   }
   return (int)cudaGetLastError();
 }
