@@ -306,7 +306,8 @@ def run_gpu(args):
                    "collective": "1 flat-bucket NCCL all-reduce of the 28 ViL parameter gradients per step" if world > 1 else "none"},
         "e2e": {"value": round(vols / (ms_e2e * 1e-3), 2), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / K, 4)},
-        "gpu_launches": launches, "kernel_time_share": shares, "roofline": roof, "roofline_secondary": secondary,
+        "gpu_launches": launches, "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
+        "kernel_ms_per_step_total": round(sum(v[0] for v in kern.values()) / K, 4), "kernel_time_share": shares, "roofline": roof, "roofline_secondary": secondary,
         "clocks": clocks,
     }
     if cpu is not None:
