@@ -7,6 +7,7 @@
 // warp-shuffle + one atomic per block and subset.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "prof.cuh"
 #include "xhved.h"
@@ -268,9 +269,14 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restric
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static int grid_for(int64_t nvec) {
-  // grid sized in multiples of the SM count (148 SMs, up to 8 resident 256-thread CTAs each)
+  // grid sized in multiples of the SM count (148 SMs); XHVED_POE_WAVES (blocks per SM, default 8) is a tuning knob
+  static int per_sm = [] {
+    const char* e = getenv("XHVED_POE_WAVES");
+    const int v = e ? atoi(e) : 8;
+    return v > 0 ? v : 8;
+  }();
   const int64_t want = (nvec + 255) / 256;
-  const int64_t cap = 148 * 8;
+  const int64_t cap = 148LL * per_sm;
   return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
 }
 

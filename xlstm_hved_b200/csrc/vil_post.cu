@@ -67,9 +67,10 @@ __device__ __forceinline__ void gated_head(const unsigned char* h_tile, int tid,
 }
 
 template <int C>
-__global__ void __launch_bounds__(kTok) vil_post_fwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ h_tiles,
-                                                             const float* __restrict__ act, const float* __restrict__ z,
-                                                             xhved_vil_params p, VilGeom g, float* __restrict__ y) {
+__global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ h_tiles,
+                                                                 const float* __restrict__ act, const float* __restrict__ z,
+                                                                 xhved_vil_params p, VilGeom g, float* __restrict__ y) {
+  // 512 threads: thread = (token, head)
   using L = PostTC<C>;
   constexpr int E = L::E, DH = E / 4, DHP = DH < 16 ? 16 : DH;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(kTok) vil_post_fwd_kernel(const float* __restr
   __shared__ __align__(8) uint64_t bar1;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int tok = tid & (kTok - 1), head = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
   if (tid == 0) {
     mbar_init(&bar1, 1);
@@ -88,15 +90,14 @@ __global__ void __launch_bounds__(kTok) vil_post_fwd_kernel(const float* __restr
   stage(par + L::P_SK, p.learnable_skip, E);
   stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
   __syncthreads();
-  const int tau = ch * kTok + tid;
+  const int tau = ch * kTok + tok;
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
-#pragma unroll 1
-  for (int head = 0; head < 4; ++head) {
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
+  {
     const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
     float hg[DH];
-    gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tid, par + L::P_OW + head * DH, par + L::P_SK + head * DH,
+    gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tok, par + L::P_OW + head * DH, par + L::P_SK + head * DH,
                    act + tm_base + static_cast<size_t>(head * DH) * kTok, z + tm_base + static_cast<size_t>(head * DH) * kTok, kTok, hg,
                    nullptr, nullptr);
 #pragma unroll
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(kTok) vil_post_fwd_kernel(const float* __restr
       for (int i = 0; i < 8; ++i) v8[i] = valid ? hg[cg * 8 + i] : 0.f;
       uint4 hi, lo;
       split8_hilo(v8, hi, lo);
-      *reinterpret_cast<uint4*>(smem + L::HGHI + tile_off16(kTok, tid, head * (DH / 8) + cg)) = hi;
-      *reinterpret_cast<uint4*>(smem + L::HGLO + tile_off16(kTok, tid, head * (DH / 8) + cg)) = lo;
+      *reinterpret_cast<uint4*>(smem + L::HGHI + tile_off16(kTok, tok, head * (DH / 8) + cg)) = hi;
+      *reinterpret_cast<uint4*>(smem + L::HGLO + tile_off16(kTok, tok, head * (DH / 8) + cg)) = lo;
     }
   }
   fence_proxy_async();
@@ -123,14 +124,15 @@ __global__ void __launch_bounds__(kTok) vil_post_fwd_kernel(const float* __restr
   }
   mbar_wait(&bar1, 0);
   tc_fence_after();
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-#pragma unroll
-  for (int c0 = 0; c0 < C; c0 += 16) {
-    float o[16];
-    tmem_ld16(tmem + lane_base + c0, o);
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  // the four head groups split the C output channels of their token, 8 at a time
+#pragma unroll 1
+  for (int c0 = head * 8; c0 < C; c0 += 32) {
+    float o[8];
+    tmem_ld8(tmem + lane_base + c0, o);
     if (valid) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 8; ++i) {
         const int c = c0 + i;
         y[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) + o[i];
       }
@@ -148,7 +150,7 @@ static int launch_post_fwd(const float* x, const void* h, const float* act, cons
   cudaError_t e = cudaFuncSetAttribute(vil_post_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_FWD, st);
-  vil_post_fwd_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y);
+  vil_post_fwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y);
   return (int)cudaGetLastError();
 }
 

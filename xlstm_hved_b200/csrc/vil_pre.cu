@@ -84,11 +84,12 @@ struct PreTC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
-                                                            unsigned char* __restrict__ q_tiles, unsigned char* __restrict__ k_tiles,
-                                                            unsigned char* __restrict__ v_tiles, float* __restrict__ igp,
-                                                            float* __restrict__ fgp, float* __restrict__ act_out,
-                                                            float* __restrict__ z_out, float* __restrict__ xm_out) {
+__global__ void __launch_bounds__(4 * kTok) vil_pre_fwd_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
+                                                                unsigned char* __restrict__ q_tiles, unsigned char* __restrict__ k_tiles,
+                                                                unsigned char* __restrict__ v_tiles, float* __restrict__ igp,
+                                                                float* __restrict__ fgp, float* __restrict__ act_out,
+                                                                float* __restrict__ z_out, float* __restrict__ xm_out) {
+  // 512 threads: thread = (token, head); head group 0 additionally owns the LayerNorm and the gate read-out of its token
   using L = PreTC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restri
   __shared__ __align__(8) uint64_t bar1, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int tok = tid & (kTok - 1), head = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
 
   if (tid == 0) {
@@ -115,52 +117,55 @@ __global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restri
   stage(par + L::P_NW, p.norm_weight, C);
   stage_weight_tile(p.proj_up_weight, 2 * E, C, 2 * E, smem + L::WHI, smem + L::WLO);
   // gate weights as a [16][NQ] tile in the padded q|k|v column order: column (part*4 + head)*DHP + d
-  for (int gi = tid; gi < 16 * (NQ / 8); gi += kTok) {
+  for (int gi = tid; gi < 16 * (NQ / 8); gi += blockDim.x) {
     const int hh = gi % 16, cg = gi / 16;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int j = cg * 8 + i, part = j / (4 * DHP), head = (j / DHP) % 4, d = j % DHP;
+      const int j = cg * 8 + i, part = j / (4 * DHP), hd = (j / DHP) % 4, d = j % DHP;
       const float* W = hh < 4 ? p.igate_weight + hh * 3 * E : p.fgate_weight + (hh - 4) * 3 * E;
-      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + head * DH + d) : 0.f;
+      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + hd * DH + d) : 0.f;
     }
     uint4 h, l;
     split8_hilo(v, h, l);
     *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
     *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
   }
-  // ---- load the token, LayerNorm, stage it as a bf16 hi/lo row
-  const int tau = ch * kTok + tid;
+  // ---- load the token, LayerNorm, stage it as a bf16 hi/lo row (head group 0); conv halo tokens (first 3 threads of group 1)
+  const int tau = ch * kTok + tok;
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-  float xin[C], xn[C];
+  const bool is_halo = head == 1 && tok < 3;
+  const int htau = ch * kTok - 3 + tok;
+  const bool hvalid = is_halo && htau >= 0;
+  float xin[C];
+  if (head == 0) {
 #pragma unroll
-  for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
-  float hx[C];
-  const int htau = ch * kTok - 3 + tid;              // halo token of threads 0..2
-  const bool hvalid = tid < 3 && htau >= 0;
-  if (tid < 3) {
+    for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
+  } else if (is_halo) {
     const int hn_ = g.reverse ? g.S - 1 - htau : htau;
 #pragma unroll
-    for (int c = 0; c < C; ++c) hx[c] = hvalid ? __ldg(x + b * g.xsb + hn_ * g.xsn + c * g.xsc) : 0.f;
+    for (int c = 0; c < C; ++c) xin[c] = hvalid ? __ldg(x + b * g.xsb + hn_ * g.xsn + c * g.xsc) : 0.f;
   }
   __syncthreads();   // parameters (norm weight) staged
-  layernorm_token<C>(xin, par + L::P_NW, xn, nullptr);
+  if (head == 0) {
+    float xn[C];
+    layernorm_token<C>(xin, par + L::P_NW, xn, nullptr);
 #pragma unroll
-  for (int cg = 0; cg < C / 8; ++cg) {
-    float v8[8];
+    for (int cg = 0; cg < C / 8; ++cg) {
+      float v8[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
-    uint4 h, l;
-    split8_hilo(v8, h, l);
-    *reinterpret_cast<uint4*>(smem + L::XHI + tile_off16(kTok, tid, cg)) = h;
-    *reinterpret_cast<uint4*>(smem + L::XLO + tile_off16(kTok, tid, cg)) = l;
-  }
-  if (tid < 3) {
+      for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
+      uint4 h, l;
+      split8_hilo(v8, h, l);
+      *reinterpret_cast<uint4*>(smem + L::XHI + tile_off16(kTok, tok, cg)) = h;
+      *reinterpret_cast<uint4*>(smem + L::XLO + tile_off16(kTok, tok, cg)) = l;
+    }
+  } else if (is_halo) {
     float hn2[C];
-    layernorm_token<C>(hx, par + L::P_NW, hn2, nullptr);
+    layernorm_token<C>(xin, par + L::P_NW, hn2, nullptr);
 #pragma unroll
-    for (int c = 0; c < C; ++c) par[L::P_HX + tid * C + c] = hvalid ? hn2[c] : 0.f;
+    for (int c = 0; c < C; ++c) par[L::P_HX + tok * C + c] = hvalid ? hn2[c] : 0.f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restri
     umma_commit(&bar1);
   }
   // ---- conv halo (3 previous tokens): x_mlstm only, spread over the CTA while the MMA runs
-  for (int idx = tid; idx < 3 * E; idx += kTok) {
+  for (int idx = tid; idx < 3 * E; idx += blockDim.x) {
     const int row = idx / E, e = idx % E;
     const float* w = p.proj_up_weight + static_cast<size_t>(e) * C;
     float acc = 0.f;
@@ -188,29 +193,29 @@ __global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restri
   }
   mbar_wait(&bar1, 0);
   tc_fence_after();
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;   // token-minor (B, nc, E, 128)
-#pragma unroll 1
-  for (int c0 = 0; c0 < 2 * E; c0 += 32) {
-    float v[32];
-    tmem_ld32(tmem + lane_base + c0, v);
-    if (c0 < E) {
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;   // token-minor (B, nc, E, 128)
+  // this head's DH channels of x_mlstm (columns head*DH..) and of z (columns E + head*DH..)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        xm_s[(tid + 3) * L::XM_LD + c0 + i] = v[i];
-        xm_out[tm_base + static_cast<size_t>(c0 + i) * kTok] = v[i];
-      }
-    } else {
+  for (int c0 = 0; c0 < DH; c0 += 8) {
+    float v[8];
+    tmem_ld8(tmem + lane_base + head * DH + c0, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) z_out[tm_base + static_cast<size_t>(c0 - E + i) * kTok] = v[i];
+    for (int i = 0; i < 8; ++i) {
+      xm_s[(tok + 3) * L::XM_LD + head * DH + c0 + i] = v[i];
+      xm_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
     }
+    tmem_ld8(tmem + lane_base + E + head * DH + c0, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
   }
   tc_fence_before();
   __syncthreads();   // x_mlstm of all tokens visible; proj_up operands dead -> QKV tile may overwrite them
   // ---- conv + SiLU + block-diagonal q,k,v, 8 channels at a time
-  const float* xm0 = xm_s + tid * L::XM_LD;   // rows tid..tid+3 <-> tokens tau-3..tau
+  const float* xm0 = xm_s + tok * L::XM_LD;   // rows tok..tok+3 <-> tokens tau-3..tau
+  const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-  for (int e8 = 0; e8 < E; e8 += 8) {
+  for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
     float a8[8], xm8[8], q8[8], k8[8], v8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -237,16 +242,15 @@ __global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restri
         v8[blk * 4 + o] = wv.x * xv[0] + wv.y * xv[1] + wv.z * xv[2] + wv.w * xv[3];
       }
     }
-    const int head = e8 / DH, d0 = e8 % DH;
-    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const int d0 = e8 % DH;
     const uint4 uq = valid ? pack8_bf16(q8) : zero, uk = valid ? pack8_bf16(k8) : zero, uv = valid ? pack8_bf16(v8) : zero;
-    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((0 * 4 + head) * DHP + d0) / 8)) = uq;
-    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((1 * 4 + head) * DHP + d0) / 8)) = uk;
-    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((2 * 4 + head) * DHP + d0) / 8)) = uv;
+    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((0 * 4 + head) * DHP + d0) / 8)) = uq;
+    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((1 * 4 + head) * DHP + d0) / 8)) = uk;
+    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((2 * 4 + head) * DHP + d0) / 8)) = uv;
     if (DHP > DH) {   // DH = 8 padded to 16: zero the second column group of every head
 #pragma unroll
       for (int part = 0; part < 3; ++part)
-        *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tid, ((part * 4 + head) * DHP + 8) / 8)) = zero;
+        *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((part * 4 + head) * DHP + 8) / 8)) = zero;
     }
   }
   fence_proxy_async();
@@ -262,22 +266,22 @@ __global__ void __launch_bounds__(kTok) vil_pre_fwd_kernel(const float* __restri
     // q/k/v head tiles are contiguous column blocks of the staged tile: bulk-store them to the cell's operand tiles
     constexpr uint32_t HT = kTok * DHP * 2;
 #pragma unroll 1
-    for (int head = 0; head < 4; ++head) {
-      const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
-      bulk_s2g(q_tiles + tile * HT, smem + L::QKV + (0 * 4 + head) * HT, HT);
-      bulk_s2g(k_tiles + tile * HT, smem + L::QKV + (1 * 4 + head) * HT, HT);
-      bulk_s2g(v_tiles + tile * HT, smem + L::QKV + (2 * 4 + head) * HT, HT);
+    for (int hd = 0; hd < 4; ++hd) {
+      const size_t tile = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
+      bulk_s2g(q_tiles + tile * HT, smem + L::QKV + (0 * 4 + hd) * HT, HT);
+      bulk_s2g(k_tiles + tile * HT, smem + L::QKV + (1 * 4 + hd) * HT, HT);
+      bulk_s2g(v_tiles + tile * HT, smem + L::QKV + (2 * 4 + hd) * HT, HT);
     }
     bulk_commit();
   }
-  mbar_wait(&bar2, 0);
-  tc_fence_after();
-  {
+  if (head == 0) {
+    mbar_wait(&bar2, 0);
+    tc_fence_after();
     float gt[16];
     tmem_ld16(tmem + lane_base + 2 * E, gt);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-      const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tid;
+      const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
       igp[o] = valid ? gt[h] + __ldg(p.igate_bias + h) : -1e30f;
       fgp[o] = valid ? gt[4 + h] + __ldg(p.fgate_bias + h) : 1e30f;
     }
@@ -295,7 +299,7 @@ static int launch_pre_fwd(const float* x, const xhved_vil_params* p, const VilGe
   cudaError_t e = cudaFuncSetAttribute(vil_pre_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_PRE_FWD, st);
-  vil_pre_fwd_kernel<C><<<g.B * g.nc, kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z, xm);
+  vil_pre_fwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z, xm);
   return (int)cudaGetLastError();
 }
 
