@@ -69,26 +69,28 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
   for (int64_t iv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
        iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t i = iv * V;
-    float T[5][V], M[5][V];
-    uint32_t dropbits = 0;
+    float T[5][V], M[5][V], Lv[5][V];
+    uint32_t live = (ss.used << 1) | 1u;       // bit e = expert e must be read (the prior always)
     if (drop) {
       const uint8_t* d = drop + (i / per_sample) * 4;
-      dropbits = (d[0] ? 1u : 0u) | (d[1] ? 2u : 0u) | (d[2] ? 4u : 0u) | (d[3] ? 8u : 0u);
+      const uint32_t dropbits = (d[0] ? 1u : 0u) | (d[1] ? 2u : 0u) | (d[2] ? 4u : 0u) | (d[3] ? 8u : 0u);
+      live &= ~(dropbits << 1);
+    }
+    // all loads first (predicated, no control flow) so that every thread keeps ~10 x 16 B in flight
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) M[e][j] = 0.f, Lv[e][j] = 0.f;
+      if ((live >> e) & 1u) {
+        ld<V>(mu + e * stride + i, M[e]);
+        ld<V>(lv + e * stride + i, Lv[e]);
+      }
     }
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
-      const bool need = (e == 0) || ((ss.used >> (e - 1)) & 1u);
-      const bool dropped = (e > 0) && ((dropbits >> (e - 1)) & 1u);
-      if (need && !dropped) {
-        float l[V];
-        ld<V>(mu + e * stride + i, M[e]);
-        ld<V>(lv + e * stride + i, l);
+      const bool on = (live >> e) & 1u;
 #pragma unroll
-        for (int j = 0; j < V; ++j) T[e][j] = 1.0f / (__expf(l[j]) + eps);
-      } else {
-#pragma unroll
-        for (int j = 0; j < V; ++j) T[e][j] = 0.f, M[e][j] = 0.f;
-      }
+      for (int j = 0; j < V; ++j) T[e][j] = on ? __fdividef(1.0f, __expf(Lv[e][j]) + eps) : 0.f;
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
 #pragma unroll
           for (int e = 1; e < 5; ++e)
             if ((mask >> (e - 1)) & 1u) st_ += T[e][j], sm += M[e][j] * T[e][j];
-          om[j] = sm / st_;
+          om[j] = __fdividef(sm, st_);
           ol[j] = -__logf(st_);
         }
         st<V>(out_mu + s * n + i, om);
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
         }
         if (kld_out) {
 #pragma unroll
-          for (int j = 0; j < V; ++j) kld_acc[s] += -1.0f - ol[j] + (__expf(ol[j]) + om[j] * om[j]) / (1.0f + 1e-8f);
+          for (int j = 0; j < V; ++j) kld_acc[s] += -1.0f - ol[j] + (__expf(ol[j]) + om[j] * om[j]);   // / (1 + 1e-8) == 1 in fp32
         }
       }
     }
@@ -156,16 +158,19 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ 
       const uint8_t* d = drop + (i / per_sample) * 4;
       dropbits = (d[0] ? 1u : 0u) | (d[1] ? 2u : 0u) | (d[2] ? 4u : 0u) | (d[3] ? 8u : 0u);
     }
+    // all loads first, then the arithmetic
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      ld<V>(mu + e * stride + i, M[e]);
+      ld<V>(lv + e * stride + i, EL[e]);
+    }
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
       const bool dropped = (e > 0) && ((dropbits >> (e - 1)) & 1u);
-      float l[V];
-      ld<V>(mu + e * stride + i, M[e]);
-      ld<V>(lv + e * stride + i, l);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        EL[e][j] = __expf(l[j]);
-        T[e][j] = dropped ? 0.f : 1.0f / (EL[e][j] + eps);
+        EL[e][j] = __expf(EL[e][j]);
+        T[e][j] = dropped ? 0.f : __fdividef(1.0f, EL[e][j] + eps);
         if (dropped) M[e][j] = 0.f;
         dM[e][j] = 0.f, dT[e][j] = 0.f;
       }
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ 
 #pragma unroll
           for (int e = 0; e < 5; ++e)
             if ((mask >> e) & 1u) S += T[e][j], sm += M[e][j] * T[e][j];
-          const float rS = 1.0f / S;
+          const float rS = __fdividef(1.0f, S);
           const float mh = sm * rS;
           const float lh = -__logf(S);
           float a = gm[j], b = gl[j];
@@ -210,8 +215,8 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ 
           }
           if (use_kld) {
             const float ks = ss.kld_scale[s];
-            a += ks * 2.0f * mh / (1.0f + 1e-8f);
-            b += ks * (-1.0f + __expf(lh) / (1.0f + 1e-8f));
+            a += ks * 2.0f * mh;                       // / (1 + 1e-8) == 1 in fp32
+            b += ks * (-1.0f + __expf(lh));
           }
 #pragma unroll
           for (int e = 0; e < 5; ++e)
