@@ -91,10 +91,12 @@ def test_full_model_training_gradients_parity(model):
         assert abs(loss_ref - loss_new) < 1e-3 * abs(loss_ref)
         assert set(g_ref) == set(g_new)
         worst, checked, num, den = ("", 0.0), 0, 0.0, 0.0
+        gmax = max(g.norm().item() for g in g_ref.values())
         for n in g_ref:
             # gradients that are mathematically zero (conv biases in front of InstanceNorm ...) are pure rounding
             # noise even between two runs of the stock model: only parameters the reference reproduces are compared
-            if g_ref[n].norm() == 0 or rel_l2(g_ref2[n], g_ref[n]) > 1e-3:
+            # (conv biases in front of InstanceNorm have |g| ~ 1e-9 of the largest tensor: rounding residue, skipped)
+            if g_ref[n].norm().item() < 1e-5 * gmax or rel_l2(g_ref2[n], g_ref[n]) > 1e-3:
                 continue
             e = rel_l2(g_new[n], g_ref[n])
             if e > worst[1]:

@@ -66,6 +66,40 @@ __device__ __forceinline__ void gated_head(const unsigned char* h_tile, int tid,
   if (rstd_out) *rstd_out = rstd;
 }
 
+// Same computation with the global loads separated out so that kernels can issue them before their first barrier.
+template <int DH>
+struct HeadInputs {
+  uint4 h[DH / 8];
+  float a[DH], z[DH];
+  __device__ __forceinline__ void load(const unsigned char* h_tile, int r, const float* act, const float* zp, size_t stride) {
+#pragma unroll
+    for (int cg = 0; cg < DH / 8; ++cg) h[cg] = __ldg(reinterpret_cast<const uint4*>(h_tile + tile_off16(kTok, r, cg)));
+#pragma unroll
+    for (int d = 0; d < DH; ++d) a[d] = __ldg(act + d * stride), z[d] = __ldg(zp + d * stride);
+  }
+  // hg = (norm(h)*(1+ow) + sk*a) * silu(z); optionally xhat and rstd (vision_lstm.py:271-287, 437, 440)
+  __device__ __forceinline__ void gated(const float* ow, const float* sk, float* hg, float* xhat, float* rstd_out) const {
+    float hv[DH];
+#pragma unroll
+    for (int cg = 0; cg < DH / 8; ++cg) unpack8_bf16(h[cg], hv + cg * 8);
+    float mean = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) mean += hv[d];
+    mean *= (1.f / DH);
+    float var = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) var += (hv[d] - mean) * (hv[d] - mean);
+    const float rstd = rsqrtf(var * (1.f / DH) + 1e-5f);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      const float xh = (hv[d] - mean) * rstd;
+      hg[d] = (xh * (1.f + ow[d]) + sk[d] * a[d]) * silu(z[d]);
+      if (xhat) xhat[d] = xh;
+    }
+    if (rstd_out) *rstd_out = rstd;
+  }
+};
+
 template <int C>
 __global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ h_tiles,
                                                                  const float* __restrict__ act, const float* __restrict__ z,
@@ -80,6 +114,22 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __r
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tok = tid & (kTok - 1), head = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
+  const int tau = ch * kTok + tok;
+  const bool valid = tau < g.S;
+  const int n = g.reverse ? g.S - 1 - tau : tau;
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
+  // all per-token global loads first: their latency overlaps the parameter staging below
+  HeadInputs<DH> in;
+  in.load(h_tiles + ((static_cast<size_t>(b) * 4 + head) * g.nc + ch) * (kTok * DHP * 2), tok,
+          act + tm_base + static_cast<size_t>(head * DH) * kTok, z + tm_base + static_cast<size_t>(head * DH) * kTok, kTok);
+  float xres[8 * ((C + 31) / 32)];
+#pragma unroll
+  for (int it = 0; it < (C + 31) / 32; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = head * 8 + it * 32 + i;
+      xres[it * 8 + i] = (valid && c < C) ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
+    }
   if (tid == 0) {
     mbar_init(&bar1, 1);
     mbar_fence_init();
@@ -90,16 +140,9 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __r
   stage(par + L::P_SK, p.learnable_skip, E);
   stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
   __syncthreads();
-  const int tau = ch * kTok + tok;
-  const bool valid = tau < g.S;
-  const int n = g.reverse ? g.S - 1 - tau : tau;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
   {
-    const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
     float hg[DH];
-    gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tok, par + L::P_OW + head * DH, par + L::P_SK + head * DH,
-                   act + tm_base + static_cast<size_t>(head * DH) * kTok, z + tm_base + static_cast<size_t>(head * DH) * kTok, kTok, hg,
-                   nullptr, nullptr);
+    in.gated(par + L::P_OW + head * DH, par + L::P_SK + head * DH, hg, nullptr, nullptr);
 #pragma unroll
     for (int cg = 0; cg < DH / 8; ++cg) {
       float v8[8];
@@ -126,15 +169,15 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __r
   tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   // the four head groups split the C output channels of their token, 8 at a time
-#pragma unroll 1
-  for (int c0 = head * 8; c0 < C; c0 += 32) {
-    float o[8];
-    tmem_ld8(tmem + lane_base + c0, o);
-    if (valid) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        y[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) + o[i];
+  for (int it = 0; it < (C + 31) / 32; ++it) {
+    const int c0 = head * 8 + it * 32;
+    if (c0 < C) {
+      float o[8];
+      tmem_ld8(tmem + lane_base + c0, o);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[b * g.ysb + n * g.ysn + (c0 + i) * g.ysc] = xres[it * 8 + i] + o[i];
       }
     }
   }
@@ -184,6 +227,15 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tok = tid & (kTok - 1), head = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
+  const int tau = ch * kTok + tok;
+  const bool valid = tau < g.S;
+  const int n = g.reverse ? g.S - 1 - tau : tau;
+  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
+  const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
+  // all per-token global loads first: their latency overlaps the parameter staging below
+  HeadInputs<DH> in;
+  in.load(h_tiles + tile * (kTok * DHP * 2), tok, act + tm_base + static_cast<size_t>(head * DH) * kTok,
+          z + tm_base + static_cast<size_t>(head * DH) * kTok, kTok);
   if (tid == 0) {
     mbar_init(&bar1, 1);
     mbar_init(&bar2, 1);
@@ -195,9 +247,6 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
   stage(par + L::P_SK, p.learnable_skip, E);
   for (int i = tid; i < 2 * E; i += blockDim.x) par[L::P_ASK + i] = 0.f;
   stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
-  const int tau = ch * kTok + tok;
-  const bool valid = tau < g.S;
-  const int n = g.reverse ? g.S - 1 - tau : tau;
   for (int cg = head; cg < C / 8; cg += 4) {
     float v8[8];
 #pragma unroll
@@ -219,14 +268,10 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
     umma_commit(&bar1);
   }
   // recompute the gated activation of this (token, head) while the MMA runs
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
-  const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
   float hg[DH], xhat[DH], rstd;
   const float* ow = par + L::P_OW + head * DH;
   const float* sk = par + L::P_SK + head * DH;
-  const float* actp = act + tm_base + static_cast<size_t>(head * DH) * kTok;
-  const float* zp = z + tm_base + static_cast<size_t>(head * DH) * kTok;
-  gated_head<DH>(h_tiles + tile * (kTok * DHP * 2), tok, ow, sk, actp, zp, kTok, hg, xhat, &rstd);
+  in.gated(ow, sk, hg, xhat, &rstd);
   mbar_wait(&bar1, 0);
   tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -241,7 +286,7 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
 #pragma unroll
   for (int d = 0; d < DH; ++d) {
     const int e = head * DH + d;
-    const float a = __ldg(actp + d * kTok), zz = __ldg(zp + d * kTok);
+    const float a = in.a[d], zz = in.z[d];
     const float sz = silu(zz);
     const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
     const float dhs = valid ? dhg[d] * sz : 0.f;

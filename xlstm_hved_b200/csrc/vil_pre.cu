@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float*
   // d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
   const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
 #pragma unroll 1
-  for (int o8 = part * 8; o8 < 2 * E; o8 += 32) {
+  for (int o8 = (part - 1) * 8; part > 0 && o8 < 2 * E; o8 += 24) {      // part 0 is busy with the LayerNorm
     float d8[8];
     if (o8 < E) {
       float dc[4][8];
