@@ -609,7 +609,12 @@ struct PreBwdBTC {
   static constexpr uint32_t DIN_BYTES = kTok * 2 * E * 2, W_BYTES = 2 * E * C * 2, XN_BYTES = kTok * C * 2;
   static constexpr uint32_t DINHI = 0, DINLO = DIN_BYTES, WHI = 2 * DIN_BYTES, WLO = WHI + W_BYTES, XNT = WLO + W_BYTES, PAR = XNT + XN_BYTES;
   static constexpr int P_CW = 0, P_NW = E * 4, P_ANW = P_NW + C, P_N = P_ANW + C;
-  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  // token-minor input blocks (E x 128 fp32 each) staged by bulk async copies when they fit: dconv, dxmv, dz, + the
+  // first 3 tokens of the next chunk's dconv (E x 4 floats)
+  static constexpr bool STAGE_IN = C <= 32;
+  static constexpr uint32_t BLK = E * kTok * 4;
+  static constexpr uint32_t IN_DC = (PAR + P_N * 4 + 127) / 128 * 128, IN_DX = IN_DC + BLK, IN_DZ = IN_DX + BLK, IN_NX = IN_DZ + BLK;
+  static constexpr uint32_t TOTAL = STAGE_IN ? IN_NX + E * 4 * 4 : PAR + P_N * 4;
   static constexpr int MT = (2 * E + 127) / 128;                       // M tiles of the weight-gradient GEMM
   static constexpr uint32_t TMEM_COLS = next_pow2_tmem(C + MT * C);
 };
@@ -625,17 +630,34 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float*
   constexpr int E = L::E;
   extern __shared__ __align__(128) unsigned char smem[];
   float* par = reinterpret_cast<float*>(smem + L::PAR);
-  __shared__ __align__(8) uint64_t bar1;
+  __shared__ __align__(8) uint64_t bar1, bar_in;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tok = tid & (kTok - 1), part = tid >> 7;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
+  const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
   if (tid == 0) {
     mbar_init(&bar1, 1);
+    mbar_init(&bar_in, 1);
     mbar_fence_init();
+    if (L::STAGE_IN) {
+      mbar_expect_tx(&bar_in, 3 * L::BLK);
+      bulk_g2s(smem + L::IN_DC, dconv + tm_chunk, L::BLK, &bar_in);
+      bulk_g2s(smem + L::IN_DX, dxmv + tm_chunk, L::BLK, &bar_in);
+      bulk_g2s(smem + L::IN_DZ, dz + tm_chunk, L::BLK, &bar_in);
+    }
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
+  if (L::STAGE_IN) {
+    // dconv of the first 3 tokens of the next chunk (tokens tau0+128 .. +130), (E, 4) floats
+    float* nx = reinterpret_cast<float*>(smem + L::IN_NX);
+    for (int i = tid; i < E * 4; i += blockDim.x) {
+      const int e = i >> 2, k = i & 3;
+      const int tp = (ch + 1) * kTok + k;
+      nx[i] = (k < 3 && tp < g.S) ? __ldg(dconv + (static_cast<size_t>(b) * g.nc + ch + 1) * E * kTok + static_cast<size_t>(e) * kTok + k) : 0.f;
+    }
+  }
   stage(par + L::P_CW, p.conv_weight, E * 4);
   stage(par + L::P_NW, p.norm_weight, C);
   for (int i = tid; i < C; i += blockDim.x) par[L::P_ANW + i] = 0.f;
@@ -660,7 +682,11 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float*
     }
   }
   // d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
-  const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
+  if (L::STAGE_IN && part > 0) mbar_wait(&bar_in, 0);
+  const float* s_dc = reinterpret_cast<const float*>(smem + L::IN_DC);
+  const float* s_dx = reinterpret_cast<const float*>(smem + L::IN_DX);
+  const float* s_dz = reinterpret_cast<const float*>(smem + L::IN_DZ);
+  const float* s_nx = reinterpret_cast<const float*>(smem + L::IN_NX);
 #pragma unroll 1
   for (int o8 = (part - 1) * 8; part > 0 && o8 < 2 * E; o8 += 24) {      // part 0 is busy with the LayerNorm
     float d8[8];
@@ -669,14 +695,21 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float*
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int tp = tau + k;
-        const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
+        if (L::STAGE_IN) {
+          // dconv pads are written as zeros by kernel A, so only the chunk boundary needs care
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
+          for (int i = 0; i < 8; ++i)
+            dc[k][i] = (tok + k < kTok) ? s_dc[(o8 + i) * kTok + tok + k] : s_nx[(o8 + i) * 4 + (tok + k - kTok)];
+        } else {
+          const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int o = o8 + i;
-        float d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
+        float d = L::STAGE_IN ? s_dx[o * kTok + tok] : __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
 #pragma unroll
         for (int k = 0; k < 4; ++k) d += par[L::P_CW + o * 4 + 3 - k] * dc[k][i];
         d8[i] = valid ? d : 0.f;
@@ -684,7 +717,7 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float*
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float d = __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
+        const float d = L::STAGE_IN ? s_dz[(o8 - E + i) * kTok + tok] : __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
         d8[i] = valid ? d : 0.f;
       }
     }
@@ -768,12 +801,19 @@ struct PreBwdATC {
   static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
   static constexpr uint32_t DG_BYTES = kTok * 16 * 2, WG_BYTES = 16 * NQ * 2, QKV_BYTES = kTok * NQ * 2, T_BYTES = kTok * E * 2;
   static constexpr uint32_t DGHI = 0, DGLO = DG_BYTES, WGHI = 2 * DG_BYTES, WGLO = WGHI + WG_BYTES;   // inside a 32 KB window
-  static constexpr uint32_t QKV = 32768, GQK = QKV + QKV_BYTES;                                      // GQK: [128][2E], 32 KB window
-  static constexpr uint32_t GV = GQK + 32768, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;               // GV window covers ACT, XMT (+pad)
-  static constexpr uint32_t PAR = (XMT + T_BYTES) > (GV + 32768) ? (XMT + T_BYTES) : (GV + 32768);
+  // The q|k|v tile is dead once the first MMA group has completed; the weight-gradient operands written by the main loop
+  // reuse its space.  GQK: [128][2E] (32 KB window); GV: 32 KB window covering ACT, XMT.
+  static constexpr uint32_t QKV = 32768, GQK = QKV;
+  static constexpr uint32_t GV = GQK + 32768, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;
+  static constexpr uint32_t END1 = QKV + QKV_BYTES, END2 = XMT + T_BYTES, END3 = GV + 32768;
+  static constexpr uint32_t PAR = END1 > END2 ? (END1 > END3 ? END1 : END3) : (END2 > END3 ? END2 : END3);
   static constexpr int P_CW = 0, P_CB = E * 4, P_WQ = P_CB + E, P_WK = P_WQ + E * 4, P_WV = P_WK + E * 4, A_CW = P_WV + E * 4,
                        A_CB = A_CW + E * 4, A_GB = A_CB + E, P_N = A_GB + 8;
-  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  // token-minor input blocks staged by bulk async copies: x_mlstm, d_act (E x 128 fp32 each) + x_mlstm of the 3 tokens
+  // in front of the chunk (E x 4 floats)
+  static constexpr uint32_t BLK = E * kTok * 4;
+  static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + BLK, IN_HX = IN_DA + BLK;
+  static constexpr uint32_t TOTAL = IN_HX + E * 4 * 4;
   static constexpr uint32_t T_GQ = 0, T_DWG = NQ, T_DWQK = 2 * NQ, T_DWV = 2 * NQ + E;
   static_assert(2 * NQ + 2 * E <= 512 && WGLO + WG_BYTES <= 32768 && 2 * E <= 128, "tensor-core pre-backward A supports C <= 32");
 };
@@ -807,14 +847,25 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   __syncthreads();
+  const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
   if (tid == 0) {
-    mbar_expect_tx(&bar_load, 12 * HT);
+    mbar_expect_tx(&bar_load, 12 * HT + 2 * L::BLK);
 #pragma unroll 1
     for (int hd = 0; hd < 4; ++hd) {
       const size_t tile = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
       bulk_g2s(smem + L::QKV + (0 * 4 + hd) * HT, q_tiles + tile * HT, HT, &bar_load);
       bulk_g2s(smem + L::QKV + (1 * 4 + hd) * HT, k_tiles + tile * HT, HT, &bar_load);
       bulk_g2s(smem + L::QKV + (2 * 4 + hd) * HT, v_tiles + tile * HT, HT, &bar_load);
+    }
+    bulk_g2s(smem + L::IN_XM, xm + tm_chunk, L::BLK, &bar_load);
+    bulk_g2s(smem + L::IN_DA, d_act + tm_chunk, L::BLK, &bar_load);
+  }
+  {
+    // x_mlstm of the 3 tokens in front of this chunk (zeros in front of the sequence)
+    float* hx = reinterpret_cast<float*>(smem + L::IN_HX);
+    for (int i = tid; i < E * 4; i += blockDim.x) {
+      const int e = i >> 2, k = i & 3;
+      hx[i] = (k < 3 && ch > 0) ? __ldg(xm + (static_cast<size_t>(b) * g.nc + ch - 1) * E * kTok + static_cast<size_t>(e) * kTok + kTok - 3 + k) : 0.f;
     }
   }
   stage(par + L::P_CW, p.conv_weight, E * 4);
@@ -881,15 +932,14 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
   for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
     const int d0 = e8 % DH;
     float a8[8], xm8[8], cv8[8], xr[4][8];
+    const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM);
+    const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_HX);
+    const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k
-      const int tp = tau - 3 + k;
+    for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k (padding rows hold zeros)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const size_t off = (static_cast<size_t>(b) * g.nc + (tp >= 0 ? tp / kTok : 0)) * E * kTok + static_cast<size_t>(e8 + j) * kTok +
-                           (tp >= 0 ? tp % kTok : 0);
-        xr[k][j] = (tp >= 0 && tp < g.S) ? __ldg(xm + off) : 0.f;
-      }
+      for (int j = 0; j < 8; ++j)
+        xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
     }
     float gq[8], gk[8], gv[8], dsk[8];
     const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tok) * DHP + d0;
@@ -902,7 +952,7 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
       gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dsk[j] = __ldg(d_act + tm_base + static_cast<size_t>(e8 + j) * kTok);
+    for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int e = e8 + j;
