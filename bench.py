@@ -322,6 +322,20 @@ def run_gpu(args):
                  for k, _ in order[1:]}
     shares = {k: round(v[0] / sum(m for m, _ in kern.values()), 4) for k, v in order}
 
+    # "mLSTM kernel % of bf16 tensor peak" (second half of BASELINE.json's metric): the cell kernels alone, at the shipped
+    # head dim and at the scaled widths of SURVEY.md 8d (f_maps 16 / 32 -> DH 64 / 128)
+    cell = None
+    if world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_cell
+        cell = {}
+        for cfg in ((32, 4, 4096, 16), (16, 4, 4096, 64), (16, 4, 4096, 128)):
+            r = bench_cell.run(*cfg, iters=5)
+            ko = r["kernels"]["mlstm_chunk_out"]
+            cell[f"DH{cfg[3]}"] = {"shape_B_NH_S_DH": list(cfg), "chunk_out_ms": ko["ms"], "chunk_out_useful_tflops": ko["useful_tflops"],
+                                   "chunk_out_executed_tflops": ko["executed_tflops"],
+                                   "chunk_out_executed_frac_of_burst_peak": ko["executed_frac_of_bf16_burst_peak"],
+                                   "fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"]}
     cpu = cpu_reference_arm(steps=args.cpu_steps, warmup=1) if world == 1 and not args.no_cpu else None
     vols = world * B * K
     line = {
@@ -341,7 +355,7 @@ def run_gpu(args):
                         "step's compute) and reads the step's loss back; PCIe-bound"},
         "gpu_launches": launches, "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
         "kernel_ms_per_step_total": round(sum(v[0] for v in kern.values()) / K, 4), "kernel_time_share": shares, "roofline": roof, "roofline_secondary": secondary,
-        "clocks": clocks,
+        "clocks": clocks, "mlstm_cell_tensor_peak": cell,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

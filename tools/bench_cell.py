@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""mLSTM cell microbench: achieved tensor throughput of the chunkwise tcgen05 kernels at the reference head dim (16)
+and at the scaled widths SURVEY.md 8d asks for (DH = 32 / 64 / 128), forward and backward, B*NH*S large.
+Prints one JSON object per configuration; `useful` counts causal-half FLOP, `executed` counts the
+full 128x128 tiles the tensor pipe actually runs."""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from xlstm_hved_b200 import _lib, ops  # noqa: E402
+
+
+def run(B, NH, S, DH, iters=10):
+    lib = _lib.load_library()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    q, k, v = [0.3 * torch.randn(B, NH, S, DH, device=dev, generator=g) for _ in range(3)]
+    ig = torch.randn(B, NH, S, 1, device=dev, generator=g)
+    fg = 2.0 + torch.randn(B, NH, S, 1, device=dev, generator=g)
+    buf = ops.mlstm_pack_inputs(q, k, v, ig, fg)
+    dh_tiles = torch.randn_like(buf.h.float()).to(torch.bfloat16)
+    bwd = buf.dhp <= 64
+    for _ in range(2):
+        ops.mlstm_fwd_tiles(buf)
+        if bwd:
+            ops.mlstm_bwd_tiles(buf, dh_tiles)
+    nk = lib.xhved_profile_kernel_count()
+    names = [lib.xhved_profile_kernel_name(i).decode() for i in range(nk)]
+    ms, cnt = (ctypes.c_float * nk)(), (ctypes.c_int * nk)()
+    lib.xhved_profile_enable(1)
+    lib.xhved_profile_read(ms, cnt, nk)
+    for _ in range(iters):
+        ops.mlstm_fwd_tiles(buf)
+        if bwd:
+            ops.mlstm_bwd_tiles(buf, dh_tiles)
+    lib.xhved_profile_read(ms, cnt, nk)
+    lib.xhved_profile_enable(0)
+    t = {names[i]: ms[i] / cnt[i] for i in range(nk) if cnt[i]}
+    th = B * NH * S
+    L, D = 128, buf.dhp
+    useful = {"mlstm_chunk_out": th * (2 * L * DH + 2 * DH * DH), "mlstm_chunk_grad": th * (5 * L * DH + 6 * DH * DH),
+              "mlstm_chunk_state": th * 2 * DH * DH, "mlstm_chunk_rstate": th * 2 * DH * DH}
+    executed = {"mlstm_chunk_out": th * (4 * L * D + 2 * 2 * D * (D + 16)), "mlstm_chunk_grad": th * (2 * L * D + 2 * L * (D + 16) + 6 * L * D + 3 * 2 * 2 * D * (D + 16)),
+                "mlstm_chunk_state": th * 2 * 2 * 128 * (D + 16), "mlstm_chunk_rstate": th * 2 * 2 * 128 * (D + 16)}
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
+    out = {"B": B, "NH": NH, "S": S, "DH": DH, "dhp": D, "kernels": {}}
+    fwd_ms = sum(t.get(k_, 0) for k_ in ("mlstm_chunk_state", "mlstm_state_scan", "mlstm_chunk_out"))
+    bwd_ms = sum(t.get(k_, 0) for k_ in ("mlstm_chunk_rstate", "mlstm_chunk_grad", "mlstm_gate_finish")) + (t.get("mlstm_state_scan", 0) if bwd else 0)
+    for k_, v_ in t.items():
+        e = {"ms": round(v_, 4)}
+        if k_ in useful:
+            e["useful_tflops"] = round(useful[k_] / (v_ * 1e-3) / 1e12, 2)
+            e["executed_tflops"] = round(executed[k_] / (v_ * 1e-3) / 1e12, 2)
+            e["executed_frac_of_bf16_burst_peak"] = round(e["executed_tflops"] / peaks["bf16_tflops"], 4)
+        out["kernels"][k_] = e
+    out["fwd_ms"], out["bwd_ms"] = round(fwd_ms, 4), round(bwd_ms, 4) if bwd else None
+    out["fwd_useful_tflops"] = round((useful["mlstm_chunk_out"] + useful["mlstm_chunk_state"]) / (fwd_ms * 1e-3) / 1e12, 2)
+    return out
+
+
+if __name__ == "__main__":
+    for cfg in ((32, 4, 4096, 16), (8, 4, 32768, 16), (32, 4, 4096, 32), (16, 4, 4096, 64), (2, 4, 32768, 64), (16, 4, 4096, 128)):
+        print(json.dumps(run(*cfg)))
