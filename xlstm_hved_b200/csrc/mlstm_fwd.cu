@@ -106,46 +106,56 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
 // Writes, for every chunk c, the state ENTERING chunk c as a PAIR of bf16 tile-native tiles (hi, lo = residual)
 // [DHP rows (key dim d)][NE cols (value dim e | n | 0)] plus its log-scale m_prev[c].
 // `reverse` runs the same recurrence from the last chunk to the first (backward pass).
-template <int DHP, int PER_THREAD>
+template <int DHP>
 __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __restrict__ dstate, const float* __restrict__ g_in,
                                                                 const float* __restrict__ amax_in, int nc, int reverse,
                                                                 unsigned char* __restrict__ states, float* __restrict__ m_prev) {
+  // grid = (B*NH, ceil(DHP*NE / 512)): the state elements are independent, so they are spread over several CTAs; every
+  // CTA repeats the (scalar) log-scale recurrence.  The next chunk's contribution is prefetched one step ahead.
   constexpr int NE = ext_cols(DHP);
   constexpr int NEL = DHP * NE;
   const int bh = blockIdx.x, tid = threadIdx.x;
-  float acc[PER_THREAD];
-#pragma unroll
-  for (int k = 0; k < PER_THREAD; ++k) acc[k] = 0.f;
-  float m = -INFINITY;
+  const int i0 = blockIdx.y * 512 + tid, i1 = i0 + 256;
+  const bool on0 = i0 < NEL, on1 = i1 < NEL;
+  const uint32_t off0 = on0 ? tile_off16(DHP, i0 / NE, (i0 % NE) / 8) + ((i0 % NE) % 8) * 2 : 0;
+  const uint32_t off1 = on1 ? tile_off16(DHP, i1 / NE, (i1 % NE) / 8) + ((i1 % NE) % 8) * 2 : 0;
+  float acc0 = 0.f, acc1 = 0.f, m = -INFINITY;
+  const int c_first = reverse ? nc - 1 : 0;
+  const float* src = dstate + (static_cast<size_t>(bh) * nc + c_first) * NEL;
+  float nx0 = on0 ? src[i0] : 0.f, nx1 = on1 ? src[i1] : 0.f;
+  float gn = g_in[static_cast<size_t>(bh) * nc + c_first], an = amax_in[static_cast<size_t>(bh) * nc + c_first];
   for (int step = 0; step < nc; ++step) {
     const int c = reverse ? nc - 1 - step : step;
     const size_t tile = static_cast<size_t>(bh) * nc + c;
-    // emit the state entering this chunk
-    unsigned char* st = states + tile * (NEL * 4);      // [hi tile | lo tile]
-#pragma unroll
-    for (int k = 0; k < PER_THREAD; ++k) {
-      const int idx = tid + k * 256;
-      if (idx < NEL) {
-        const int d = idx / NE, e = idx % NE;
-        const __nv_bfloat16 hi = __float2bfloat16(acc[k]);
-        const __nv_bfloat16 lo = __float2bfloat16(acc[k] - __bfloat162float(hi));
-        const uint32_t off = tile_off16(DHP, d, e / 8) + (e % 8) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(st + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(st + NEL * 2 + off) = lo;
-      }
+    const float cur0 = nx0, cur1 = nx1, g = gn, amax = an;
+    if (step + 1 < nc) {      // prefetch the next chunk
+      const int cn = reverse ? c - 1 : c + 1;
+      const size_t tn = static_cast<size_t>(bh) * nc + cn;
+      const float* sn = dstate + tn * NEL;
+      nx0 = on0 ? sn[i0] : 0.f;
+      nx1 = on1 ? sn[i1] : 0.f;
+      gn = g_in[tn];
+      an = amax_in[tn];
     }
-    if (tid == 0) m_prev[tile] = m;
+    // emit the state entering this chunk as a bf16 hi/lo pair
+    unsigned char* st = states + tile * (NEL * 4);
+    if (on0) {
+      const __nv_bfloat16 hi = __float2bfloat16(acc0);
+      *reinterpret_cast<__nv_bfloat16*>(st + off0) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(st + NEL * 2 + off0) = __float2bfloat16(acc0 - __bfloat162float(hi));
+    }
+    if (on1) {
+      const __nv_bfloat16 hi = __float2bfloat16(acc1);
+      *reinterpret_cast<__nv_bfloat16*>(st + off1) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(st + NEL * 2 + off1) = __float2bfloat16(acc1 - __bfloat162float(hi));
+    }
+    if (tid == 0 && blockIdx.y == 0) m_prev[tile] = m;
     // fold this chunk in
-    const float g = g_in[tile], amax = amax_in[tile];
     const float m_new = fmaxf(g + m, amax);
     const float decay = __expf(g + m - m_new);   // exp(-inf) = 0 on the first step
     const float wnew = __expf(amax - m_new);
-    const float* src = dstate + tile * NEL;
-#pragma unroll
-    for (int k = 0; k < PER_THREAD; ++k) {
-      const int idx = tid + k * 256;
-      if (idx < NEL) acc[k] = decay * acc[k] + wnew * src[idx];
-    }
+    acc0 = decay * acc0 + wnew * cur0;
+    acc1 = decay * acc1 + wnew * cur1;
     m = m_new;
   }
 }
@@ -400,11 +410,13 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
 int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
                       float* m_prev, cudaStream_t st) {
   ProfScope ps(K_STATE_SCAN, st);
+  const int nel = dhp * (dhp + 16);
+  const dim3 grid(BH, (nel + 511) / 512);
   switch (dhp) {
-    case 16: mlstm_state_scan_kernel<16, (16 * 32 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 32: mlstm_state_scan_kernel<32, (32 * 48 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 64: mlstm_state_scan_kernel<64, (64 * 80 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 128: mlstm_state_scan_kernel<128, (128 * 144 + 255) / 256><<<BH, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 16: mlstm_state_scan_kernel<16><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 32: mlstm_state_scan_kernel<32><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 64: mlstm_state_scan_kernel<64><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 128: mlstm_state_scan_kernel<128><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
     default: return XHVED_ERR_UNSUPPORTED_DH;
   }
   return (int)cudaGetLastError();
