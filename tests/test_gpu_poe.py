@@ -86,3 +86,47 @@ def test_poe_full_backward_with_sampling_and_kld_vs_autograd():
     dmu, dlv = ops.poe_bwd(mu.detach().float().cuda(), lv.detach().float().cuda(), subsets, noise=noise.float().cuda(),
                            g_z=gz.float().cuda(), kld_scale=ks)
     assert rel_l2(dmu, rmu) < 1e-5 and rel_l2(dlv, rlv) < 1e-5
+
+
+def test_module_level_dropins_forward_and_gradients_vs_oracle():
+    """The drop-in callables of xlstm_hved_b200.modules (ProductOfExperts, ProductOfExperts2, reparametrize, compute_KLD)
+    with autograd, against autograd through the oracle restatement."""
+    import xlstm_hved_b200 as xh
+    g = torch.Generator().manual_seed(21)
+    shape = (3, 2, 4, 4, 4)
+    mu0 = torch.cat([torch.zeros(1, *shape), 1.3 * torch.randn(4, *shape, generator=g)])
+    lv0 = torch.cat([torch.zeros(1, *shape), 1.4 * torch.randn(4, *shape, generator=g)])
+    drop = torch.tensor([[False, True, False, False], [True, False, False, True], [False, False, False, False]])
+    w = torch.randn(shape, generator=g)
+
+    def loss_fn(poe, poe_drop, reparam, kld, mu, lv, noise):
+        a, b = poe(mu, lv, (0, 2))
+        c, d = poe_drop(mu.clone(), lv, drop.to(mu.device))
+        z = reparam(a, b, noise)
+        return (z * w.to(mu)).sum() + (c * d).sum() + 0.3 * kld(mu.transpose(1, 0), lv.transpose(1, 0), [14, 3])
+
+    # oracle (fp64, CPU)
+    mu64, lv64 = mu0.double().requires_grad_(), lv0.double().requires_grad_()
+    torch.manual_seed(5)
+    noise = torch.empty(shape).normal_()
+    ref = loss_fn(lambda m, l, s: restate.poe(m, l, s), lambda m, l, dr: restate.poe_drop(m, l, dr)[:2],
+                  lambda a, b, nz: restate.reparametrize(a, b, nz.double()), restate.compute_kld, mu64, lv64, noise)
+    rmu, rlv = torch.autograd.grad(ref, [mu64, lv64])
+    # kernels (reparametrize draws its own noise from the global CUDA generator: feed the same noise through the op)
+    muc, lvc = mu0.cuda().requires_grad_(), lv0.cuda().requires_grad_()
+    from xlstm_hved_b200.modules import _ReparamFunction
+    got = loss_fn(xh.ProductOfExperts(), xh.ProductOfExperts2(),
+                  lambda a, b, nz: _ReparamFunction.apply(a.contiguous(), b.contiguous(), nz.cuda()), xh.compute_KLD, muc, lvc, noise)
+    gmu, glv = torch.autograd.grad(got, [muc, lvc])
+    assert abs(got.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert rel_l2(gmu, rmu) < 1e-4 and rel_l2(glv, rlv) < 1e-4
+
+
+def test_product_of_experts2_mutates_mu_like_the_reference():
+    import xlstm_hved_b200 as xh
+    c = load_golden("poe.pt")
+    mu, lv = _mu5(c)
+    mu_c = mu.float().cuda()
+    a, b = xh.ProductOfExperts2()(mu_c, lv.float().cuda(), c["drop"].cuda())
+    assert rel_linf(a, c["drop_pd_mu"]) < TOL and rel_linf(b, c["drop_pd_logvar"]) < TOL
+    assert torch.equal(mu_c.cpu().double(), c["drop_mu_after"].float().double())      # buildingblocks.py:879-881
