@@ -374,9 +374,6 @@ __global__ void mlstm_unpack_kernel(const unsigned char* __restrict__ tiles, int
 }
 
 // ------------------------------------------------------------------ host launchers
-int launch_chunk_out_pipelined(int dhp, const void* q, const void* k, const void* v, const float* ig, const float* fg, const void* states,
-                               const float* m_prev, int ntiles, int nc, float scale, float eps, void* h, float* m, float* den,
-                               cudaStream_t st);
 int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
                       float* m_prev, cudaStream_t st);
 
@@ -398,14 +395,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
   }
   // phase 2
   if (int rc = launch_state_scan(DHP, ws_dstate, ws_g, ws_amax, BH, nc, 0, states, m_prev, st)) return rc;
-  // phase 3: persistent pipelined kernel (dhp <= 64; XHVED_CELL_PIPE=0 selects the one-tile-per-CTA kernel for A/B runs)
-  static const bool use_pipe = [] {
-    const char* e = getenv("XHVED_CELL_PIPE");
-    return !(e && e[0] == '0');
-  }();
-  int rc3 = -1000;
-  if (use_pipe) rc3 = launch_chunk_out_pipelined(DHP, q, k, v, ig, fg, states, m_prev, ntiles, nc, scale, eps, h, m, den, st);
-  if (rc3 != -1000) return rc3 ? rc3 : (int)cudaGetLastError();
+  // phase 3
   {
     const size_t smem = 3 * kL * DHP * 2 + kL * kL * 2 + 2 * DHP * NE * 2 + kL * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_out_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
