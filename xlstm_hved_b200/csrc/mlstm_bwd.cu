@@ -133,6 +133,25 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_rstate_kernel(const unsi
 }
 
 // ------------------------------------------------------------------ phase B3
+// 16 columns of one row: D'' = exp2(u_row + v_col); P = S o D'' and dS = dP o D'' written as bf16 (two 16-byte groups each)
+template <bool MASK>
+__device__ __forceinline__ void decay_pair(const float* sv, const float* dp, float urow, const float* vcol, int s0, int row,
+                                           unsigned char* dstP, unsigned char* dstS) {
+#pragma unroll
+  for (int j8 = 0; j8 < 2; ++j8) {
+    float p[8], ds[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = fast_exp2(urow + vcol[j8 * 8 + j]);
+      if (MASK) d = (s0 + j8 * 8 + j <= row) ? d : 0.f;
+      p[j] = sv[j8 * 8 + j] * d;
+      ds[j] = dp[j8 * 8 + j] * d;
+    }
+    *reinterpret_cast<uint4*>(dstP + j8 * (kL * 16)) = pack8_bf16(p);
+    *reinterpret_cast<uint4*>(dstS + j8 * (kL * 16)) = pack8_bf16(ds);
+  }
+}
+
 template <int DHP>
 struct BwdSmem {
   static constexpr int NE = ext_cols(DHP);
@@ -234,22 +253,12 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
         float sv[16], dp[16];
         tmem_ld16(tmem + lane_base + blk * 32 + half * 16, sv);
         tmem_ld16(tmem + lane_base + 128 + blk * 32 + half * 16, dp);
-#pragma unroll
-        for (int j8 = 0; j8 < 2; ++j8) {
-          float p[8], ds[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int s = blk * 32 + half * 16 + j8 * 8 + j;
-            const float d = (s <= tid) ? fast_exp2(urow + vcol[s]) : 0.f;
-            p[j] = sv[j8 * 8 + j] * d;
-            ds[j] = dp[j8 * 8 + j] * d;
-          }
-          const int cg = blk * 4 + half * 2 + j8;
-          *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, cg)) =
-              make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-          *reinterpret_cast<uint4*>(sdS + tile_off16(kL, tid, cg)) =
-              make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
-        }
+        const int s0 = blk * 32 + half * 16;
+        // only the diagonal block needs the causal mask
+        if (blk < warp)
+          decay_pair<false>(sv, dp, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8), sdS + tile_off16(kL, tid, s0 / 8));
+        else
+          decay_pair<true>(sv, dp, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8), sdS + tile_off16(kL, tid, s0 / 8));
       }
     } else {
 #pragma unroll

@@ -163,6 +163,25 @@ __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------ phase 3
+// One row of a 32-column block: p = S * exp2(u_row + v_col), bf16 P written to the row's four 16-byte groups (2 KB apart).
+template <bool MASK>
+__device__ __forceinline__ float decay_block(const float* sv, float urow, const float* vcol, int s0, int row, unsigned char* dst) {
+  float rowsum = 0.f;
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8) {
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = fast_exp2(urow + vcol[j8 * 8 + j]);
+      p[j] = sv[j8 * 8 + j] * d;
+      if (MASK) p[j] = (s0 + j8 * 8 + j <= row) ? p[j] : 0.f;
+      rowsum += p[j];
+    }
+    *reinterpret_cast<uint4*>(dst + j8 * (kL * 16)) = pack8_bf16(p);
+  }
+  return rowsum;
+}
+
 template <int DHP>
 __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
     const unsigned char* __restrict__ q_tiles, const unsigned char* __restrict__ k_tiles, const unsigned char* __restrict__ v_tiles,
@@ -240,23 +259,11 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
     if (blk <= warp) {
       float sv[32];
       tmem_ld32(tmem + lane_base + blk * 32, sv);
-#pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        float p[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int s = blk * 32 + j8 * 8 + j;
-          const float d = fast_exp2(urow + vcol[s]);
-          p[j] = (s <= tid) ? sv[j8 * 8 + j] * d : 0.f;
-          rowsum += p[j];
-        }
-        uint4 u;
-        u.x = pack_bf16x2(p[0], p[1]);
-        u.y = pack_bf16x2(p[2], p[3]);
-        u.z = pack_bf16x2(p[4], p[5]);
-        u.w = pack_bf16x2(p[6], p[7]);
-        *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, blk * 4 + j8)) = u;
-      }
+      // only the diagonal 32x32 block needs the causal mask; blocks left of it are fully visible
+      if (blk < warp)
+        rowsum += decay_block<false>(sv, urow, vcol + blk * 32, blk * 32, tid, sP + tile_off16(kL, tid, blk * 4));
+      else
+        rowsum += decay_block<true>(sv, urow, vcol + blk * 32, blk * 32, tid, sP + tile_off16(kL, tid, blk * 4));
     } else {
 #pragma unroll
       for (int j8 = 0; j8 < 4; ++j8) *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, blk * 4 + j8)) = make_uint4(0, 0, 0, 0);
