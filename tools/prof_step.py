@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0,'.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = torch.device('cuda',0)
