@@ -236,14 +236,17 @@ def product_of_experts(mu_list, logvar_list, mod_list, eps=1e-8):
 
 
 def product_of_experts_drop(mu, logvar, drop, eps=1e-8):
-    """ProductOfExperts2.forward (buildingblocks.py:875-886), including its in-place zeroing of ``mu``."""
-    mu5, lv5 = _stack5(mu), _stack5(logvar)
-    out = _PoEFunction.apply(mu5, lv5, (0, 1, 2, 3), drop.to(torch.uint8).contiguous(), eps)
+    """ProductOfExperts2.forward (buildingblocks.py:875-886), including its in-place zeroing of ``mu``.
+
+    The reference overwrites mu[m+1] with a copy whose dropped samples are zero (879-880).  The same side effect is
+    applied here BEFORE the fused op runs (so the tensor autograd saves is the final one); the kernel removes the dropped
+    experts through the mask itself and returns zero gradients for them, which is what ZeroLayerF's backward does."""
     if isinstance(mu, torch.Tensor):
-        with torch.no_grad():                              # the reference overwrites mu[m+1] (879-880)
+        with torch.no_grad():
             for m in range(drop.shape[1]):
                 mu[m + 1][drop[:, m].bool()] = 0
-    return out
+    mu5, lv5 = _stack5(mu), _stack5(logvar)
+    return _PoEFunction.apply(mu5, lv5, (0, 1, 2, 3), drop.to(torch.uint8).contiguous(), eps)
 
 
 class ProductOfExperts(nn.Module):
