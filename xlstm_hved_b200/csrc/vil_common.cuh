@@ -97,17 +97,4 @@ __device__ __forceinline__ void warp_acc_vec(float* slots, float* v) {
   if ((threadIdx.x & 31) < N) atomicAdd(slots + (threadIdx.x & 31), r);
 }
 
-// out[a][b] += sum_tok A[tok*lda + a] * Bm[tok*ldb + b]   (a < na, b < nb; ntok rows staged in shared memory)
-// Each thread owns outputs idx = tid, tid + nthreads, ...; consecutive threads take consecutive b.
-__device__ __forceinline__ void outer_accumulate(const float* sA, int lda, int na, const float* sB, int ldb, int nb, int ntok,
-                                                 float* __restrict__ gout) {
-  for (int idx = threadIdx.x; idx < na * nb; idx += blockDim.x) {
-    const int a = idx / nb, b = idx % nb;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int t = 0; t < ntok; ++t) acc += sA[t * lda + a] * sB[t * ldb + b];
-    atomicAdd(gout + idx, acc);
-  }
-}
-
 }  // namespace xhved

@@ -8,27 +8,6 @@
 
 namespace xhved {
 
-template <int C>
-struct PostSmem {
-  static constexpr int E = 2 * C;
-  static constexpr int WDT = 0;            // proj_down transposed: (E, C)
-  static constexpr int OW = WDT + E * C;   // outnorm weight (E)
-  static constexpr int SK = OW + E;        // learnable skip (E)
-  static constexpr int TOTAL = SK + E;
-};
-
-// load one head's row (DH values) of a tile-native bf16 tile
-template <int DH>
-__device__ __forceinline__ void load_h_row(const unsigned char* tile, int r, float* hv) {
-#pragma unroll
-  for (int cg = 0; cg < DH / 8; ++cg) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(tile + tile_off16(kTok, r, cg)));
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    hv[cg * 8 + 0] = a.x, hv[cg * 8 + 1] = a.y, hv[cg * 8 + 2] = b.x, hv[cg * 8 + 3] = b.y;
-    hv[cg * 8 + 4] = c.x, hv[cg * 8 + 5] = c.y, hv[cg * 8 + 6] = d.x, hv[cg * 8 + 7] = d.y;
-  }
-}
-
 // ------------------------------------------------------------------ forward (tcgen05 version)
 // Per token: per-head normalisation, skip, SiLU(z) gate on CUDA cores -> the gated row is staged as a bf16 hi/lo tile and
 // proj_down runs as a 3-product UMMA (tokens x C); the epilogue adds the residual and writes NCDHW.
@@ -42,31 +21,8 @@ struct PostTC {
   static constexpr uint32_t TMEM_COLS = next_pow2_tmem(C);
 };
 
-// the gated activation of one head for token `tid` (vision_lstm.py:271-287, 437, 440); also returns xhat and the statistics
-template <int DH>
-__device__ __forceinline__ void gated_head(const unsigned char* h_tile, int tid, const float* ow, const float* sk, const float* act,
-                                           const float* z, size_t tm_stride, float* hg, float* xhat, float* rstd_out) {
-  float hv[DH];
-  load_h_row<DH>(h_tile, tid, hv);
-  float mean = 0.f;
-#pragma unroll
-  for (int d = 0; d < DH; ++d) mean += hv[d];
-  mean *= (1.f / DH);
-  float var = 0.f;
-#pragma unroll
-  for (int d = 0; d < DH; ++d) var += (hv[d] - mean) * (hv[d] - mean);
-  const float rstd = rsqrtf(var * (1.f / DH) + 1e-5f);
-#pragma unroll
-  for (int d = 0; d < DH; ++d) {
-    const float xh = (hv[d] - mean) * rstd;
-    const float a = __ldg(act + d * tm_stride), zz = __ldg(z + d * tm_stride);
-    hg[d] = (xh * (1.f + ow[d]) + sk[d] * a) * silu(zz);
-    if (xhat) xhat[d] = xh;
-  }
-  if (rstd_out) *rstd_out = rstd;
-}
-
-// Same computation with the global loads separated out so that kernels can issue them before their first barrier.
+// Per-(token, head) inputs of the gated activation, with the global loads separated out so that kernels can issue
+// them before their first barrier.
 template <int DH>
 struct HeadInputs {
   uint4 h[DH / 8];

@@ -494,112 +494,6 @@ __global__ void __launch_bounds__(160) vil_pre_bwd_a_kernel(const float* __restr
   else if (tid < 8) atomicAdd(gr.fgate_bias + tid - 4, acc[LB::A_GB + tid]);
 }
 
-// ------------------------------------------------------------------ backward, kernel B
-// d x_mlstm = dxm_v + transposed causal conv of dconv (tokens tau..tau+3); [d x_mlstm | dz] -> proj_up^T -> LayerNorm
-// backward -> dx = dy + ...; accumulates proj_up and norm weight gradients.
-template <int C>
-struct PreBwdBSmem {
-  static constexpr int E = 2 * C;
-  static constexpr int W_UP = 0;                       // (2E, C)
-  static constexpr int CONV_W = W_UP + 2 * E * C;      // (E, 4)
-  static constexpr int NW = CONV_W + E * 4;
-  static constexpr int ACC_NW = NW + C;
-  static constexpr int DIN = ACC_NW + C;               // (128, E+1)   one half of d[x_mlstm | z] at a time
-  static constexpr int XN = DIN + kTok * (E + 1);      // (128, C+1)   normalised input
-  static constexpr int TOTAL = XN + kTok * (C + 1);
-};
-
-template <int C>
-__global__ void __launch_bounds__(kTok) vil_pre_bwd_b_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                              xhved_vil_params p, VilGeom g, const float* __restrict__ dconv,
-                                                              const float* __restrict__ dxmv, const float* __restrict__ dz,
-                                                              float* __restrict__ dx, xhved_vil_grads gr) {
-  using L = PreBwdBSmem<C>;
-  constexpr int E = L::E;
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
-  const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
-  stage(sm + L::W_UP, p.proj_up_weight, 2 * E * C);
-  stage(sm + L::CONV_W, p.conv_weight, E * 4);
-  stage(sm + L::NW, p.norm_weight, C);
-  for (int i = tid; i < C; i += kTok) sm[L::ACC_NW + i] = 0.f;
-  const int tau = ch * kTok + tid;
-  const bool valid = tau < g.S;
-  const int n = g.reverse ? g.S - 1 - tau : tau;
-  float xin[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
-  __syncthreads();
-  float xn[C], rstd;
-  layernorm_token<C>(xin, sm + L::NW, xn, &rstd);
-#pragma unroll
-  for (int c = 0; c < C; ++c) sm[L::XN + tid * (C + 1) + c] = valid ? xn[c] : 0.f;
-
-  float dxn[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) dxn[c] = 0.f;
-  const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
-  float* din = sm + L::DIN + tid * (E + 1);
-  // two halves of the proj_up output: o in [0,E) = d x_mlstm, o in [E,2E) = dz; the staging buffer is reused
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-#pragma unroll 1
-    for (int oo = 0; oo < E; ++oo) {
-      const int o = half * E + oo;
-      float d;
-      if (half == 0) {
-        // y_{t'} uses x_t with weight w[3 - (t' - t)], t' = t..t+3  (vision_lstm.py:213-221)
-        d = __ldg(dxmv + tm_chunk + static_cast<size_t>(oo) * kTok + tid);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int tp = tau + k;
-          if (tp < g.S) {
-            const size_t off = (static_cast<size_t>(b) * g.nc + tp / kTok) * E * kTok + static_cast<size_t>(oo) * kTok + (tp % kTok);
-            d += sm[L::CONV_W + oo * 4 + 3 - k] * __ldg(dconv + off);
-          }
-        }
-      } else {
-        d = __ldg(dz + tm_chunk + static_cast<size_t>(oo) * kTok + tid);
-      }
-      d = valid ? d : 0.f;
-      din[oo] = d;
-      const float* w = sm + L::W_UP + o * C;
-#pragma unroll
-      for (int c = 0; c < C; c += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(w + c);
-        dxn[c] += w4.x * d, dxn[c + 1] += w4.y * d, dxn[c + 2] += w4.z * d, dxn[c + 3] += w4.w * d;
-      }
-    }
-    __syncthreads();
-    // d proj_up[o][c] += sum_tok din[tok][o] * xn[tok][c]
-    outer_accumulate(sm + L::DIN, E + 1, E, sm + L::XN, C + 1, C, kTok, gr.proj_up_weight + half * E * C);
-    __syncthreads();
-  }
-  // LayerNorm backward (weight 1+w, no bias): xn = xhat*(1+w)
-  float mean_g = 0.f, mean_gx = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float w1 = 1.f + sm[L::NW + c];
-    const float xhat = xn[c] / w1;
-    warp_acc(sm + L::ACC_NW + c, valid ? dxn[c] * xhat : 0.f);
-    dxn[c] *= w1;
-    xn[c] = xhat;
-    mean_g += dxn[c];
-    mean_gx += dxn[c] * xhat;
-  }
-  mean_g *= (1.f / C);
-  mean_gx *= (1.f / C);
-  if (valid) {
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float v = rstd * (dxn[c] - mean_g - xn[c] * mean_gx);
-      dx[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) + v;
-    }
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += kTok) atomicAdd(gr.norm_weight + c, sm[L::ACC_NW + c]);
-}
-
 // ------------------------------------------------------------------ backward, tcgen05 versions
 // Kernel B (tensor-core): d[x_mlstm | z] rows are staged as bf16 hi/lo tiles; dxn = din W_up (3-product UMMA) and
 // d proj_up = din^T xn (UMMA over the CTA's tokens); LayerNorm backward and the residual add in the epilogue.
