@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
     const float* __restrict__ fg, const float* __restrict__ m_in, const float* __restrict__ den_in,
     const unsigned char* __restrict__ states, const float* __restrict__ m_prev, const unsigned char* __restrict__ rstates,
     const float* __restrict__ mu_next, int nc, float scale, float eps, float* __restrict__ dq, float* __restrict__ dk,
-    float* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out) {
+    float* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out, float* __restrict__ dc_tot) {
   using L = BwdSmem<DHP>;
   constexpr int NE = L::NE;
   constexpr uint32_t TILE = L::TILE, ST1 = L::ST, ST_BYTES = 2 * L::ST;   // hi + lo tiles
@@ -351,27 +351,35 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dv_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
   }
   dig[grow] = k_dk;
-  dc_out[grow] = q_dq - k_dk;
+  {
+    // d log f = reverse cumulative sum of dc over the whole sequence: the chunk-local suffix sum is taken here, the carry of
+    // the later chunks (sum of their totals) is added by mlstm_gate_finish_kernel
+    float tot;
+    const float suffix = block_rcumsum128(q_dq - k_dk, red, &tot);
+    dc_out[grow] = suffix;
+    if (tid == 0) dc_tot[tile] = tot;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ phase B4
-// dlf_u = sum_{t >= u} dc_t over the whole (padded) sequence; dfg = dlf * sigmoid(-fg)
-__global__ void __launch_bounds__(kThreads) mlstm_gate_finish_kernel(const float* __restrict__ dc, const float* __restrict__ fg, int nc,
-                                                                      float* __restrict__ dfg) {
-  __shared__ float red[8];
-  const int bh = blockIdx.x, tid = threadIdx.x;
-  float carry = 0.f;
-  for (int c = nc - 1; c >= 0; --c) {
-    const size_t o = (static_cast<size_t>(bh) * nc + c) * kL + tid;
-    float tot;
-    const float r = block_rcumsum128(dc[o], red, &tot) + carry;
-    const float f = fg[o];
-    dfg[o] = r * (1.f / (1.f + __expf(f)));
-    carry += tot;
-  }
+// dlf_u = (chunk-local suffix sum) + (totals of all later chunks); dfg = dlf * sigmoid(-fg).  One CTA per (b, head, chunk).
+__global__ void __launch_bounds__(kThreads) mlstm_gate_finish_kernel(const float* __restrict__ dc_suffix, const float* __restrict__ dc_tot,
+                                                                      const float* __restrict__ fg, int nc, float* __restrict__ dfg) {
+  __shared__ float red[4];
+  const int tile = blockIdx.x, tid = threadIdx.x;
+  const int bh = tile / nc, c = tile % nc;
+  float part = 0.f;
+  for (int cc = c + 1 + tid; cc < nc; cc += kThreads) part += dc_tot[static_cast<size_t>(bh) * nc + cc];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  const float carry = red[0] + red[1] + red[2] + red[3];
+  const size_t o = static_cast<size_t>(tile) * kL + tid;
+  dfg[o] = (dc_suffix[o] + carry) * (1.f / (1.f + __expf(fg[o])));
 }
 
 // fp32 (BH, nc*128, dhp) -> (BH, S, dh)
@@ -409,11 +417,12 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
     ProfScope ps(K_CHUNK_GRAD, st);
     mlstm_chunk_grad_kernel<DHP><<<ntiles, kThreads, smem, st>>>(
         (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, (const unsigned char*)h, (const unsigned char*)dh_t, ig, fg,
-        m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, scale, eps, dq, dk, dv, dig, ws_dc);
+        m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, scale, eps, dq, dk, dv, dig, ws_dc,
+        ws_lam /* free again after the reverse scan: receives the per-chunk totals of dc */);
   }
   {
     ProfScope ps(K_GATE_FINISH, st);
-    mlstm_gate_finish_kernel<<<BH, kThreads, 0, st>>>(ws_dc, fg, nc, dfg);
+    mlstm_gate_finish_kernel<<<ntiles, kThreads, 0, st>>>(ws_dc, ws_lam, fg, nc, dfg);
   }
   return (int)cudaGetLastError();
 }

@@ -316,7 +316,11 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float =
     dev = x_tok.device
     if dy_tok.dtype != torch.float32:
         dy_tok = dy_tok.float()
-    grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)      # one fill for all 14 tensors
+    grads, off = [], 0
+    for p in params:
+        grads.append(flat[off:off + p.numel()].view(p.shape))
+        off += p.numel()
     ps = _param_struct(params, _lib.VilParams)
     gs = _param_struct(grads, _lib.VilGrads)
     dx = torch.empty_strided(dy_tok.shape, dy_tok.stride(), device=dev, dtype=torch.float32)
