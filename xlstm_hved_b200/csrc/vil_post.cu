@@ -169,7 +169,7 @@ struct PostBwdTC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(4 * kTok, 2) vil_post_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
+__global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
                                                                  const float* __restrict__ act, const float* __restrict__ z,
                                                                  xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
                                                                  float* __restrict__ d_act, float* __restrict__ dz, xhved_vil_grads gr) {
