@@ -117,10 +117,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // a_addr/b_addr: smem byte addresses of tile-native tiles; *_lbo/_sbo as documented above.
 __device__ __forceinline__ void umma_gemm(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
                                           uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K, bool accumulate_first) {
+  // descriptors are built once; each K=16 slice only advances the 14-bit start-address field (2 core matrices along K)
+  uint64_t ad = umma_desc(a_addr, a_lbo, a_sbo);
+  uint64_t bd = umma_desc(b_addr, b_lbo, b_sbo);
+  const uint64_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
   for (int k = 0; k < K / 16; ++k) {
-    const uint64_t ad = umma_desc(a_addr + 2u * k * a_lbo, a_lbo, a_sbo);
-    const uint64_t bd = umma_desc(b_addr + 2u * k * b_lbo, b_lbo, b_sbo);
     umma_bf16(d_tmem, ad, bd, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+    ad += a_step;
+    bd += b_step;
   }
 }
 

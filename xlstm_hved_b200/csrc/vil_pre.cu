@@ -500,110 +500,98 @@ __global__ void __launch_bounds__(160) vil_pre_bwd_a_kernel(const float* __restr
 template <int C>
 struct PreBwdBTC {
   static constexpr int E = 2 * C;
+  static constexpr int CP = (C / 4) < 8 ? 8 : (C / 4);     // channels of one token handled by one thread
+  static constexpr int NPART = C / CP;                      // head groups that take part in the LayerNorm (C=16: 2, else 4)
   static constexpr uint32_t DIN_BYTES = kTok * 2 * E * 2, W_BYTES = 2 * E * C * 2, XN_BYTES = kTok * C * 2;
   static constexpr uint32_t DINHI = 0, DINLO = DIN_BYTES, WHI = 2 * DIN_BYTES, WLO = WHI + W_BYTES, XNT = WLO + W_BYTES, PAR = XNT + XN_BYTES;
-  static constexpr int P_CW = 0, P_NW = E * 4, P_ANW = P_NW + C, P_N = P_ANW + C;
-  // token-minor input blocks (E x 128 fp32 each) staged by bulk async copies when they fit: dconv, dxmv, dz, + the
-  // first 3 tokens of the next chunk's dconv (E x 4 floats)
-  static constexpr bool STAGE_IN = C <= 32;
-  static constexpr uint32_t BLK = E * kTok * 4;
-  static constexpr uint32_t IN_DC = (PAR + P_N * 4 + 127) / 128 * 128, IN_DX = IN_DC + BLK, IN_DZ = IN_DX + BLK, IN_NX = IN_DZ + BLK;
-  static constexpr uint32_t TOTAL = STAGE_IN ? IN_NX + E * 4 * 4 : PAR + P_N * 4;
+  static constexpr int P_CW = 0, P_NW = E * 4, P_ANW = P_NW + C, P_LN = P_ANW + C, P_N = P_LN + 2 * 4 * kTok;   // LN exchange: 2 x [4][128]
+  static constexpr uint32_t TOTAL = PAR + P_N * 4;
   static constexpr int MT = (2 * E + 127) / 128;                       // M tiles of the weight-gradient GEMM
   static constexpr uint32_t TMEM_COLS = next_pow2_tmem(C + MT * C);
 };
 
 template <int C>
-__global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                                     xhved_vil_params p, VilGeom g, const float* __restrict__ dconv,
-                                                                     const float* __restrict__ dxmv, const float* __restrict__ dz,
-                                                                     float* __restrict__ dx, xhved_vil_grads gr) {
-  // 512 threads: thread = (token, part); the four parts split the 2E columns of d[x_mlstm | z]; part 0 owns the
-  // LayerNorm backward of its token
+__global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                                        xhved_vil_params p, VilGeom g,
+                                                                                        const float* __restrict__ dconv,
+                                                                                        const float* __restrict__ dxmv,
+                                                                                        const float* __restrict__ dz, float* __restrict__ dx,
+                                                                                        xhved_vil_grads gr) {
+  // 512 threads: thread = (token, part).  Every part owns CP channels of its token for the LayerNorm (statistics are
+  // exchanged through shared memory) and a quarter of the 2E columns of d[x_mlstm | z].
   using L = PreBwdBTC<C>;
-  constexpr int E = L::E;
+  constexpr int E = L::E, CP = L::CP, NPART = L::NPART;
   extern __shared__ __align__(128) unsigned char smem[];
   float* par = reinterpret_cast<float*>(smem + L::PAR);
-  __shared__ __align__(8) uint64_t bar1, bar_in;
+  float* ln1 = par + L::P_LN;
+  float* ln2 = ln1 + 4 * kTok;
+  __shared__ __align__(8) uint64_t bar1;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tok = tid & (kTok - 1), part = tid >> 7;
+  const bool ln_on = part < NPART;
+  const int c0 = part * CP;
   const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
   const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
+  const int tau = ch * kTok + tok;
+  const bool valid = tau < g.S;
+  const int n = g.reverse ? g.S - 1 - tau : tau;
+  // this thread's channels of x (issued first: the latency overlaps the staging below)
+  float xin[CP];
+#pragma unroll
+  for (int i = 0; i < CP; ++i) xin[i] = (valid && ln_on) ? __ldg(x + b * g.xsb + n * g.xsn + (c0 + i) * g.xsc) : 0.f;
   if (tid == 0) {
     mbar_init(&bar1, 1);
-    mbar_init(&bar_in, 1);
     mbar_fence_init();
-    if (L::STAGE_IN) {
-      mbar_expect_tx(&bar_in, 3 * L::BLK);
-      bulk_g2s(smem + L::IN_DC, dconv + tm_chunk, L::BLK, &bar_in);
-      bulk_g2s(smem + L::IN_DX, dxmv + tm_chunk, L::BLK, &bar_in);
-      bulk_g2s(smem + L::IN_DZ, dz + tm_chunk, L::BLK, &bar_in);
-    }
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
-  if (L::STAGE_IN) {
-    // dconv of the first 3 tokens of the next chunk (tokens tau0+128 .. +130), (E, 4) floats
-    float* nx = reinterpret_cast<float*>(smem + L::IN_NX);
-    for (int i = tid; i < E * 4; i += blockDim.x) {
-      const int e = i >> 2, k = i & 3;
-      const int tp = (ch + 1) * kTok + k;
-      nx[i] = (k < 3 && tp < g.S) ? __ldg(dconv + (static_cast<size_t>(b) * g.nc + ch + 1) * E * kTok + static_cast<size_t>(e) * kTok + k) : 0.f;
-    }
-  }
   stage(par + L::P_CW, p.conv_weight, E * 4);
   stage(par + L::P_NW, p.norm_weight, C);
   for (int i = tid; i < C; i += blockDim.x) par[L::P_ANW + i] = 0.f;
   stage_weight_tile(p.proj_up_weight, 2 * E, C, 2 * E, smem + L::WHI, smem + L::WLO);
-  const int tau = ch * kTok + tok;
-  const bool valid = tau < g.S;
-  const int n = g.reverse ? g.S - 1 - tau : tau;
-  float xin[C], xn[C], rstd = 0.f;
-  if (part == 0) {
+  // ---- LayerNorm statistics, two passes through shared memory (mean, then centred second moment)
+  float s1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
-  }
+  for (int i = 0; i < CP; ++i) s1 += xin[i];
+  ln1[part * kTok + tok] = ln_on ? s1 : 0.f;
   __syncthreads();
-  if (part == 0) {
-    layernorm_token<C>(xin, par + L::P_NW, xn, &rstd);
+  const float mean = (ln1[tok] + ln1[kTok + tok] + ln1[2 * kTok + tok] + ln1[3 * kTok + tok]) * (1.f / C);
+  float s2 = 0.f;
 #pragma unroll
-    for (int cg = 0; cg < C / 8; ++cg) {
+  for (int i = 0; i < CP; ++i) s2 += (xin[i] - mean) * (xin[i] - mean);
+  ln2[part * kTok + tok] = ln_on ? s2 : 0.f;
+  __syncthreads();
+  const float rstd = rsqrtf((ln2[tok] + ln2[kTok + tok] + ln2[2 * kTok + tok] + ln2[3 * kTok + tok]) * (1.f / C) + 1e-5f);
+  float xhat[CP];
+#pragma unroll
+  for (int i = 0; i < CP; ++i) xhat[i] = (xin[i] - mean) * rstd;
+  if (ln_on) {
+#pragma unroll
+    for (int cg = 0; cg < CP / 8; ++cg) {
       float v8[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
-      *reinterpret_cast<uint4*>(smem + L::XNT + tile_off16(kTok, tok, cg)) = pack8_bf16(v8);
+      for (int i = 0; i < 8; ++i) v8[i] = valid ? xhat[cg * 8 + i] * (1.f + par[L::P_NW + c0 + cg * 8 + i]) : 0.f;
+      *reinterpret_cast<uint4*>(smem + L::XNT + tile_off16(kTok, tok, c0 / 8 + cg)) = pack8_bf16(v8);
     }
   }
-  // d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
-  if (L::STAGE_IN && part > 0) mbar_wait(&bar_in, 0);
-  const float* s_dc = reinterpret_cast<const float*>(smem + L::IN_DC);
-  const float* s_dx = reinterpret_cast<const float*>(smem + L::IN_DX);
-  const float* s_dz = reinterpret_cast<const float*>(smem + L::IN_DZ);
-  const float* s_nx = reinterpret_cast<const float*>(smem + L::IN_NX);
+  // ---- d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
 #pragma unroll 1
-  for (int o8 = (part - 1) * 8; part > 0 && o8 < 2 * E; o8 += 24) {      // part 0 is busy with the LayerNorm
+  for (int o8 = part * 8; o8 < 2 * E; o8 += 32) {
     float d8[8];
     if (o8 < E) {
       float dc[4][8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int tp = tau + k;
-        if (L::STAGE_IN) {
-          // dconv pads are written as zeros by kernel A, so only the chunk boundary needs care
+        const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dc[k][i] = (tok + k < kTok) ? s_dc[(o8 + i) * kTok + tok + k] : s_nx[(o8 + i) * 4 + (tok + k - kTok)];
-        } else {
-          const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
-        }
+        for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int o = o8 + i;
-        float d = L::STAGE_IN ? s_dx[o * kTok + tok] : __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
+        float d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
 #pragma unroll
         for (int k = 0; k < 4; ++k) d += par[L::P_CW + o * 4 + 3 - k] * dc[k][i];
         d8[i] = valid ? d : 0.f;
@@ -611,7 +599,7 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float*
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float d = L::STAGE_IN ? s_dz[(o8 - E + i) * kTok + tok] : __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
+        const float d = __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
         d8[i] = valid ? d : 0.f;
       }
     }
@@ -639,44 +627,46 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_b_tc_kernel(const float*
   mbar_wait(&bar1, 0);
   tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  if (part == 0) {
-    float dxn[C], red[C];
+  // ---- LayerNorm backward (weight 1+w, no bias), channels c0..c0+CP of this token
+  float dxn[CP], red[CP];
+  if (ln_on) {
 #pragma unroll
-    for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16(tmem + lane_base + c0, dxn + c0);
-    float mean_g = 0.f, mean_gx = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float w1 = 1.f + par[L::P_NW + c];
-      const float xhat = xn[c] / w1;
-      red[c] = valid ? dxn[c] * xhat : 0.f;
-      dxn[c] *= w1;
-      xn[c] = xhat;
-      mean_g += dxn[c];
-      mean_gx += dxn[c] * xhat;
-    }
-    mean_g *= (1.f / C);
-    mean_gx *= (1.f / C);
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float v = rstd * (dxn[c] - mean_g - xn[c] * mean_gx);
-        dx[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) + v;
-      }
-    }
-#pragma unroll
-    for (int c0 = 0; c0 < C; c0 += (C < 32 ? C : 32)) warp_acc_vec<(C < 32 ? C : 32)>(par + L::P_ANW + c0, red + c0);
+    for (int i = 0; i < CP; i += 8) tmem_ld8(tmem + lane_base + c0 + i, dxn + i);
   }
-  // weight-gradient rows: lane = output row o (second M tile: o + 128); the parts split the C columns
+  float pg = 0.f, pgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < CP; ++i) {
+    if (!ln_on) dxn[i] = 0.f;
+    red[i] = valid ? dxn[i] * xhat[i] : 0.f;
+    dxn[i] *= 1.f + par[L::P_NW + (ln_on ? c0 + i : 0)];
+    pg += dxn[i];
+    pgx += dxn[i] * xhat[i];
+  }
+  ln1[part * kTok + tok] = ln_on ? pg : 0.f;
+  ln2[part * kTok + tok] = ln_on ? pgx : 0.f;
+  __syncthreads();
+  const float mean_g = (ln1[tok] + ln1[kTok + tok] + ln1[2 * kTok + tok] + ln1[3 * kTok + tok]) * (1.f / C);
+  const float mean_gx = (ln2[tok] + ln2[kTok + tok] + ln2[2 * kTok + tok] + ln2[3 * kTok + tok]) * (1.f / C);
+  if (valid && ln_on) {
+#pragma unroll
+    for (int i = 0; i < CP; ++i) {
+      const float v = rstd * (dxn[i] - mean_g - xhat[i] * mean_gx);
+      const int c = c0 + i;
+      dx[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) + v;
+    }
+  }
+  if (ln_on) warp_acc_vec<CP>(par + L::P_ANW + c0, red);
+  // ---- weight-gradient rows: lane = output row o (second M tile: o + 128); the parts split the C columns
 #pragma unroll
   for (int mt = 0; mt < L::MT; ++mt) {
     const int o = mt * 128 + tok;
 #pragma unroll 1
-    for (int c0 = part * 16; c0 < C; c0 += 64) {
-      float v[16];
-      tmem_ld16(tmem + lane_base + C + mt * C + c0, v);
+    for (int cc = part * 8; cc < C; cc += 32) {
+      float v[8];
+      tmem_ld8(tmem + lane_base + C + mt * C + cc, v);
       if (o < 2 * E) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(gr.proj_up_weight + static_cast<size_t>(o) * C + c0 + i, v[i]);
+        for (int i = 0; i < 8; ++i) atomicAdd(gr.proj_up_weight + static_cast<size_t>(o) * C + cc + i, v[i]);
       }
     }
   }
@@ -810,18 +800,15 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
     // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
     umma_gemm_hilo(tmem + L::T_GQ, smem_u32(smem + L::DGHI), smem_u32(smem + L::DGLO), kTok * 16, 128, smem_u32(smem + L::WGHI),
                    smem_u32(smem + L::WGLO), 128, 16 * 16, umma_idesc(128, NQ, false, true), 16);
-    // d Wg[hh][j] = sum_tok [dig|dfg][tok][hh] qkv[tok][j]               (A: hi + lo, B: the bf16 q|k|v the cell consumed)
+    // d Wg[hh][j] = sum_tok [dig|dfg][tok][hh] qkv[tok][j]               (weight-gradient GEMM: plain bf16 operands)
     umma_gemm(tmem + L::T_DWG, smem_u32(smem + L::DGHI), 128, kTok * 16, smem_u32(smem + L::QKV), 128, kTok * 16,
               umma_idesc(128, NQ, true, true), kTok, false);
-    umma_gemm(tmem + L::T_DWG, smem_u32(smem + L::DGLO), 128, kTok * 16, smem_u32(smem + L::QKV), 128, kTok * 16,
-              umma_idesc(128, NQ, true, true), kTok, true);
     umma_commit(&bar1);
   }
-  mbar_wait(&bar1, 0);
-  tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
   float* acc = par;
+  bool mma1_pending = true;
 #pragma unroll 1
   for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
     const int d0 = e8 % DH;
@@ -855,7 +842,12 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
       a8[j] = silu(cv8[j]);
       xm8[j] = xr[3][j];
     }
-    // gate-path contribution (TMEM), zero for padding rows
+    // everything above is independent of the first MMA group and overlaps it; the gate-path contribution is read from TMEM
+    if (mma1_pending) {
+      mbar_wait(&bar1, 0);
+      tc_fence_after();
+      mma1_pending = false;
+    }
     float t8[8];
     tmem_ld8(tmem + lane_base + L::T_GQ + (0 * 4 + head) * DHP + d0, t8);
 #pragma unroll
