@@ -153,6 +153,12 @@ typedef struct xhved_vil_shape {
   int reverse;
   int64_t x_stride_b, x_stride_n, x_stride_c;
   int64_t y_stride_b, y_stride_n, y_stride_c;
+  /* Backward only: parameter gradients are accumulated with global atomics.  To spread that traffic over more L2
+   * slices the caller may provide grad_replicas (R >= 1) zero-filled copies of the whole gradient block, replica r
+   * starting grad_replica_stride elements after replica r-1 (the xhved_vil_grads pointers address replica 0); CTA i adds
+   * into replica i % R, and xhved_reduce_replicas sums them.  R <= 1 disables it. */
+  int grad_replicas;
+  int64_t grad_replica_stride;
 } xhved_vil_shape;
 
 /* K2: LayerNorm -> proj_up -> causal conv -> SiLU -> q,k,v (tiles) + gates (padded) + act, z, xm.
@@ -174,6 +180,9 @@ int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const vo
                       const float* dq, const float* dk, const float* dv, const float* dig, const float* dfg, const float* d_act,
                       const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx, const xhved_vil_grads* g,
                       float* ws_dconv, float* ws_dxmv, void* stream);
+
+/* dst[i] = sum_r src[r*stride + i], i < n  (reduction of the gradient replicas above). */
+int xhved_reduce_replicas(const float* src, int replicas, int64_t stride, int64_t n, float* dst, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,8 @@ class VilGrads(Structure):
 class VilShape(Structure):
     _fields_ = [("B", c_int), ("S", c_int), ("C", c_int), ("NH", c_int), ("QB", c_int), ("reverse", c_int),
                 ("x_stride_b", c_int64), ("x_stride_n", c_int64), ("x_stride_c", c_int64),
-                ("y_stride_b", c_int64), ("y_stride_n", c_int64), ("y_stride_c", c_int64)]
+                ("y_stride_b", c_int64), ("y_stride_n", c_int64), ("y_stride_c", c_int64),
+                ("grad_replicas", c_int), ("grad_replica_stride", c_int64)]
 
 
 # every symbol include/xhved.h declares -> argtypes (None = not yet bound with a signature)
@@ -54,6 +55,7 @@ SYMBOLS = {
     "xhved_profile_kernel_count": [],
     "xhved_profile_kernel_name": [c_int],
     "xhved_profile_read": [POINTER(c_float), POINTER(c_int), c_int],
+    "xhved_reduce_replicas": [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p],
     "xhved_umma_selftest": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_vil_pre_fwd": [c_void_p, POINTER(VilParams), POINTER(VilShape)] + [c_void_p] * 9,
     "xhved_vil_post_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p],

@@ -15,6 +15,8 @@ __host__ __device__ constexpr uint32_t next_pow2_tmem(int n) { return n <= 32 ? 
 struct VilGeom {
   int B, S, nc, Sp, NH, DH, DHP, reverse;
   int64_t xsb, xsn, xsc, ysb, ysn, ysc;
+  int grep;          // gradient replicas (>= 1)
+  int64_t gstride;   // elements between replicas
 };
 
 __host__ inline int vil_validate(const xhved_vil_shape* sh, VilGeom* g) {
@@ -26,7 +28,20 @@ __host__ inline int vil_validate(const xhved_vil_shape* sh, VilGeom* g) {
   g->NH = sh->NH, g->DH = E / sh->NH, g->DHP = g->DH <= 16 ? 16 : g->DH, g->reverse = sh->reverse;
   g->xsb = sh->x_stride_b, g->xsn = sh->x_stride_n, g->xsc = sh->x_stride_c;
   g->ysb = sh->y_stride_b, g->ysn = sh->y_stride_n, g->ysc = sh->y_stride_c;
+  g->grep = sh->grad_replicas > 1 ? sh->grad_replicas : 1;
+  g->gstride = sh->grad_replica_stride;
   return 0;
+}
+
+// the gradient block of the replica this CTA accumulates into (see xhved_vil_shape::grad_replicas)
+__device__ __forceinline__ xhved_vil_grads replica_of(xhved_vil_grads gr, const VilGeom& g) {
+  if (g.grep > 1) {
+    const int64_t off = static_cast<int64_t>(blockIdx.x % g.grep) * g.gstride;
+    gr.norm_weight += off, gr.proj_up_weight += off, gr.conv_weight += off, gr.conv_bias += off, gr.q_weight += off;
+    gr.k_weight += off, gr.v_weight += off, gr.igate_weight += off, gr.igate_bias += off, gr.fgate_weight += off;
+    gr.fgate_bias += off, gr.outnorm_weight += off, gr.learnable_skip += off, gr.proj_down_weight += off;
+  }
+  return gr;
 }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }

@@ -172,7 +172,8 @@ template <int C>
 __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
                                                                  const float* __restrict__ act, const float* __restrict__ z,
                                                                  xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
-                                                                 float* __restrict__ d_act, float* __restrict__ dz, xhved_vil_grads gr) {
+                                                                 float* __restrict__ d_act, float* __restrict__ dz, xhved_vil_grads gr_base) {
+  const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, head)
   using L = PostBwdTC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP;
@@ -361,4 +362,20 @@ extern "C" int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const fl
     case 64: return launch_post_bwd<64>(dy, h_tiles, act, z, p, geo, dh_tiles, d_act, dz, g, st);
     default: return XHVED_ERR_UNSUPPORTED_DIM;
   }
+}
+
+namespace xhved {
+__global__ void reduce_replicas_kernel(const float* __restrict__ src, int R, int64_t stride, int64_t n, float* __restrict__ dst) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) acc += src[r * stride + i];
+  dst[i] = acc;
+}
+}  // namespace xhved
+
+extern "C" int xhved_reduce_replicas(const float* src, int replicas, int64_t stride, int64_t n, float* dst, void* stream) {
+  if (!src || !dst || replicas < 1 || n <= 0 || stride < n) return XHVED_ERR_BAD_ARG;
+  xhved::reduce_replicas_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, replicas, stride, n, dst);
+  return (int)cudaGetLastError();
 }

@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(160) vil_pre_bwd_a_kernel(const float* __restr
                                                              const float* __restrict__ dv, const float* __restrict__ dig,
                                                              const float* __restrict__ dfg, const float* __restrict__ d_act,
                                                              float* __restrict__ dconv_out, float* __restrict__ dxmv_out,
-                                                             xhved_vil_grads gr) {
+                                                             xhved_vil_grads gr_base) {
+  const xhved_vil_grads gr = replica_of(gr_base, g);
   using L = PreSmem<C>;
   using LB = PreBwdASmem<C>;
   constexpr int E = L::E;
@@ -516,7 +517,8 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
                                                                                         const float* __restrict__ dconv,
                                                                                         const float* __restrict__ dxmv,
                                                                                         const float* __restrict__ dz, float* __restrict__ dx,
-                                                                                        xhved_vil_grads gr) {
+                                                                                        xhved_vil_grads gr_base) {
+  const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, part).  Every part owns CP channels of its token for the LayerNorm (statistics are
   // exchanged through shared memory) and a quarter of the 2E columns of d[x_mlstm | z].
   using L = PreBwdBTC<C>;
@@ -710,7 +712,8 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
                                                                      const float* __restrict__ dk, const float* __restrict__ dv,
                                                                      const float* __restrict__ dig, const float* __restrict__ dfg,
                                                                      const float* __restrict__ d_act, float* __restrict__ dconv_out,
-                                                                     float* __restrict__ dxmv_out, xhved_vil_grads gr) {
+                                                                     float* __restrict__ dxmv_out, xhved_vil_grads gr_base) {
+  const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, head); the four head groups of a token share the TMEM lane of that token
   using L = PreBwdATC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;

@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import check, ptr, stream
 
 CHUNK = 128
+GRAD_REPLICAS = 32      # copies of the parameter-gradient block the backward kernels scatter their atomics over
 
 # RA_HVED.py:733-738 -- subset index -> modalities present
 SUBSETS_MODALITIES = [(0,), (1,), (2,), (3,), (0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3),
@@ -316,7 +317,11 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float =
     dev = x_tok.device
     if dy_tok.dtype != torch.float32:
         dy_tok = dy_tok.float()
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)      # one fill for all 14 tensors
+    # parameter gradients are accumulated with global atomics into GRAD_REPLICAS zero-filled copies (CTA i -> copy i % R)
+    # to spread the traffic over L2 slices; xhved_reduce_replicas sums the copies at the end
+    P = sum(p.numel() for p in params)
+    stride = (P + 31) // 32 * 32
+    flat = torch.zeros(GRAD_REPLICAS * stride, device=dev, dtype=torch.float32)
     grads, off = [], 0
     for p in params:
         grads.append(flat[off:off + p.numel()].view(p.shape))
@@ -325,6 +330,7 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float =
     gs = _param_struct(grads, _lib.VilGrads)
     dx = torch.empty_strided(dy_tok.shape, dy_tok.stride(), device=dev, dtype=torch.float32)
     sh = _shape_struct(x_tok, dy_tok, reverse)          # y_* strides describe dy and dx
+    sh.grad_replicas, sh.grad_replica_stride = GRAD_REPLICAS, stride
     dh_tiles = torch.empty_like(c.h)
     d_act = torch.empty_like(ws.act)
     dz = torch.empty_like(ws.z)
@@ -336,6 +342,12 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float =
     check(lib.xhved_vil_pre_bwd(ptr(x_tok), ptr(dy_tok), ptr(ws.xm), ptr(c.q), ptr(c.k), ptr(c.v), ptr(gb.dq), ptr(gb.dk), ptr(gb.dv),
                                 ptr(gb.dig), ptr(gb.dfg), ptr(d_act), ptr(dz), ctypes.byref(ps), ctypes.byref(sh), ptr(dx), ctypes.byref(gs), ptr(ws_dconv), ptr(ws_dxmv),
                                 stream()), "xhved_vil_pre_bwd")
+    out = torch.empty(P, device=dev, dtype=torch.float32)
+    check(lib.xhved_reduce_replicas(ptr(flat), GRAD_REPLICAS, stride, P, ptr(out), stream()), "xhved_reduce_replicas")
+    grads, off = [], 0
+    for p in params:
+        grads.append(out[off:off + p.numel()].view(p.shape))
+        off += p.numel()
     return dx, grads
 
 
