@@ -6,6 +6,7 @@ sm_100a kernels of libxhved.so on the current CUDA stream.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_float, c_uint32
 
 import torch
@@ -14,7 +15,8 @@ from . import _lib
 from ._lib import check, ptr, stream
 
 CHUNK = 128
-GRAD_REPLICAS = 32      # copies of the parameter-gradient block the backward kernels scatter their atomics over
+# copies of the parameter-gradient block the backward kernels scatter their atomics over (XHVED_GRAD_REPLICAS to tune)
+GRAD_REPLICAS = max(1, int(os.environ.get("XHVED_GRAD_REPLICAS", "32")))
 
 # RA_HVED.py:733-738 -- subset index -> modalities present
 SUBSETS_MODALITIES = [(0,), (1,), (2,), (3,), (0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3),
