@@ -186,7 +186,9 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   unsigned char *sQ = smem + L::SQ, *sK = smem + L::SK, *sV = smem + L::SV, *sG = smem + L::SG, *sP = smem + L::SP,
                 *sdS = smem + L::SDS, *sC = smem + L::SC, *sR = smem + L::SR;
   float* vcol = reinterpret_cast<float*>(smem + L::VCOL);
-  __shared__ __align__(8) uint64_t bar_load, bar_mma1, bar_mma2;
+  // MMA groups are issued by lane 0 of three different warps (each tracks its own tcgen05.commit), so the descriptor
+  // arithmetic runs in parallel and the epilogue of dQ overlaps the dK / dV products
+  __shared__ __align__(8) uint64_t bar_load, bar_s, bar_p, bar_q, bar_k, bar_v;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8];
 
@@ -198,8 +200,11 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
 
   if (tid == 0) {
     mbar_init(&bar_load, 1);
-    mbar_init(&bar_mma1, 1);
-    mbar_init(&bar_mma2, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_p, 1);
+    mbar_init(&bar_q, 1);
+    mbar_init(&bar_k, 1);
+    mbar_init(&bar_v, 1);
     mbar_fence_init();
   }
   __syncwarp();
@@ -238,11 +243,14 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   if (tid == 0) {
     // S[t][s] = Q K^T            -> cols [0,128)
     umma_gemm(tmem, smem_u32(sQ), kL * 16, 128, smem_u32(sK), kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
+    umma_commit(&bar_s);
+  } else if (tid == 32) {
     // dP[t][s] = G Vext^T        -> cols [128,256)
     umma_gemm(tmem + 128, smem_u32(sG), kL * 16, 128, smem_u32(sV), kL * 16, 128, umma_idesc(128, kL, false, false), NE, false);
-    umma_commit(&bar_mma1);
+    umma_commit(&bar_p);
   }
-  mbar_wait(&bar_mma1, 0);
+  mbar_wait(&bar_s, 0);
+  mbar_wait(&bar_p, 0);
   tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 #pragma unroll 1
@@ -272,43 +280,49 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 0) {
+  {
     const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aG = smem_u32(sG), aP = smem_u32(sP), aS = smem_u32(sdS),
                    aC = smem_u32(sC), aR = smem_u32(sR);
-    // dQ_intra[t][d] = sum_s dS[t][s] K[s][d]
-    umma_gemm(tmem + 0 * DHP, aS, kL * 16, 128, aK, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
-    // dQ_inter[t][d] = sum_e' G[t][e'] Cn[d][e']
-    if (has_prev) {
-      umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
-      umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+    if (tid == 0) {
+      // dQ_intra[t][d] = sum_s dS[t][s] K[s][d]
+      umma_gemm(tmem + 0 * DHP, aS, kL * 16, 128, aK, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
+      // dQ_inter[t][d] = sum_e' G[t][e'] Cn[d][e']
+      if (has_prev) {
+        umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+        umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+      }
+      umma_commit(&bar_q);
+    } else if (tid == 32) {
+      // dK_intra[s][d] = sum_t dS[t][s] Q[t][d]
+      umma_gemm(tmem + 2 * DHP, aS, 128, kL * 16, aQ, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
+      // dK_inter[s][d] = sum_e' Vext[s][e'] R[d][e']
+      if (has_next) {
+        umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+        umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+      }
+      umma_commit(&bar_k);
+    } else if (tid == 64) {
+      // dV_intra[s][e] = sum_t P[t][s] G[t][e]
+      umma_gemm(tmem + 4 * DHP, aP, 128, kL * 16, aG, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
+      // dV_inter[s][e] = sum_d K[s][d] R[d][e]
+      if (has_next) {
+        umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
+        umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR + ST1, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, true);
+      }
+      umma_commit(&bar_v);
     }
-    // dK_intra[s][d] = sum_t dS[t][s] Q[t][d]
-    umma_gemm(tmem + 2 * DHP, aS, 128, kL * 16, aQ, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
-    // dK_inter[s][d] = sum_e' Vext[s][e'] R[d][e']
-    if (has_next) {
-      umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
-      umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
-    }
-    // dV_intra[s][e] = sum_t P[t][s] G[t][e]
-    umma_gemm(tmem + 4 * DHP, aP, 128, kL * 16, aG, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
-    // dV_inter[s][e] = sum_d K[s][d] R[d][e]
-    if (has_next) {
-      umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
-      umma_gemm(tmem + 5 * DHP, aK, kL * 16, 128, aR + ST1, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, true);
-    }
-    umma_commit(&bar_mma2);
+    __syncwarp();
   }
-  mbar_wait(&bar_mma2, 0);
-  tc_fence_after();
-  // ---- epilogue: combine intra/inter, write dq/dk/dv rows, gate-gradient dot products ----
+  // ---- epilogue: combine intra/inter, write dq/dk/dv rows, gate-gradient dot products; one pass per product ----
   float q_dq = 0.f, k_dk = 0.f;
   float* dq_row = dq + grow * DHP;
   float* dk_row = dk + grow * DHP;
   float* dv_row = dv + grow * DHP;
+  mbar_wait(&bar_q, 0);
+  tc_fence_after();
 #pragma unroll 1
   for (int c0 = 0; c0 < DHP; c0 += 16) {
     float a[16], bb[16];
-    // dQ
     tmem_ld16(tmem + lane_base + 0 * DHP + c0, a);
     if (has_prev) {
       tmem_ld16(tmem + lane_base + 1 * DHP + c0, bb);
@@ -317,14 +331,19 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const uint4 u = *reinterpret_cast<const uint4*>(sQ + tile_off16(kL, tid, c0 / 8 + half));
-      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      const float* x = a + half * 8;
-      q_dq += f0.x * x[0] + f0.y * x[1] + f1.x * x[2] + f1.y * x[3] + f2.x * x[4] + f2.y * x[5] + f3.x * x[6] + f3.y * x[7];
+      float f[8];
+      unpack8_bf16(*reinterpret_cast<const uint4*>(sQ + tile_off16(kL, tid, c0 / 8 + half)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q_dq += f[i] * a[half * 8 + i];
     }
 #pragma unroll
     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dq_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
-    // dK
+  }
+  mbar_wait(&bar_k, 0);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c0 = 0; c0 < DHP; c0 += 16) {
+    float a[16], bb[16];
     tmem_ld16(tmem + lane_base + 2 * DHP + c0, a);
     if (has_next) {
       tmem_ld16(tmem + lane_base + 3 * DHP + c0, bb);
@@ -333,14 +352,19 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const uint4 u = *reinterpret_cast<const uint4*>(sK + tile_off16(kL, tid, c0 / 8 + half));
-      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      const float* x = a + half * 8;
-      k_dk += f0.x * x[0] + f0.y * x[1] + f1.x * x[2] + f1.y * x[3] + f2.x * x[4] + f2.y * x[5] + f3.x * x[6] + f3.y * x[7];
+      float f[8];
+      unpack8_bf16(*reinterpret_cast<const uint4*>(sK + tile_off16(kL, tid, c0 / 8 + half)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k_dk += f[i] * a[half * 8 + i];
     }
 #pragma unroll
     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dk_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
-    // dV
+  }
+  mbar_wait(&bar_v, 0);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c0 = 0; c0 < DHP; c0 += 16) {
+    float a[16], bb[16];
     tmem_ld16(tmem + lane_base + 4 * DHP + c0, a);
     if (has_next) {
       tmem_ld16(tmem + lane_base + 5 * DHP + c0, bb);
