@@ -33,6 +33,13 @@ struct HeadInputs {
 #pragma unroll
     for (int d = 0; d < DH; ++d) a[d] = __ldg(act + d * stride), z[d] = __ldg(zp + d * stride);
   }
+  // the same inputs from a TMA-staged tile: [4 heads][kTok x DHP] h tiles, [E][kTok] act and z
+  __device__ __forceinline__ void load_smem(const unsigned char* h_tile, int r, const float* act, const float* zp) {
+#pragma unroll
+    for (int cg = 0; cg < DH / 8; ++cg) h[cg] = *reinterpret_cast<const uint4*>(h_tile + tile_off16(kTok, r, cg));
+#pragma unroll
+    for (int d = 0; d < DH; ++d) a[d] = act[d * kTok], z[d] = zp[d * kTok];
+  }
   // hg = (norm(h)*(1+ow) + sk*a) * silu(z); optionally xhat and rstd (vision_lstm.py:271-287, 437, 440)
   __device__ __forceinline__ void gated(const float* ow, const float* sk, float* hg, float* xhat, float* rstd_out) const {
     float hv[DH];
@@ -150,6 +157,165 @@ static int launch_post_fwd(const float* x, const void* h, const float* act, cons
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_FWD, st);
   vil_post_fwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y);
+  return (int)cudaGetLastError();
+}
+
+
+// Persistent variant (C <= 32): one CTA per SM walks the token tiles; a tile's h / act / z blocks are contiguous in HBM, so
+// the bulk-copy engine streams tile i+1 into the second smem stage while tile i is gated, multiplied and written back.
+// Parameters, the proj_down tile and the TMEM allocation are set up once per CTA.
+template <int C>
+struct PostPersist {
+  static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH;
+  static constexpr uint32_t ACT_BYTES = E * kTok * 4, H1_BYTES = kTok * DHP * 2, STAGE_BYTES = 2 * ACT_BYTES + 4 * H1_BYTES;
+  static constexpr uint32_t S_ACT = 0, S_Z = ACT_BYTES, S_H = 2 * ACT_BYTES;
+  static constexpr uint32_t HG_BYTES = kTok * E * 2, WD_BYTES = C * E * 2;
+  static constexpr uint32_t HGHI = 2 * STAGE_BYTES, HGLO = HGHI + HG_BYTES, WDHI = HGLO + HG_BYTES, WDLO = WDHI + WD_BYTES,
+                            PAR = WDLO + WD_BYTES;
+  static constexpr int P_OW = 0, P_SK = E, P_N = 2 * E;
+  static constexpr uint32_t TOTAL = PAR + P_N * 4;
+  static constexpr uint32_t TMEM_COLS = next_pow2_tmem(C);
+};
+
+template <int C>
+__global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const float* __restrict__ x, const unsigned char* __restrict__ h_tiles,
+                                                                            const float* __restrict__ act, const float* __restrict__ z,
+                                                                            xhved_vil_params p, VilGeom g, float* __restrict__ y, int ntiles) {
+  using L = PostPersist<C>;
+  constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NX = 8 * ((C + 31) / 32);
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* par = reinterpret_cast<float*>(smem + L::PAR);
+  __shared__ __align__(8) uint64_t bar_full[2], bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tok = tid & (kTok - 1), head = tid >> 7;
+
+  auto issue = [&](int tile, int s) {
+    unsigned char* st = smem + s * L::STAGE_BYTES;
+    mbar_expect_tx(&bar_full[s], L::STAGE_BYTES);
+    bulk_g2s(st + L::S_ACT, act + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
+    bulk_g2s(st + L::S_Z, z + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
+    const int b = tile / g.nc, ch = tile % g.nc;
+#pragma unroll
+    for (int hd = 0; hd < 4; ++hd)
+      bulk_g2s(st + L::S_H + hd * L::H1_BYTES, h_tiles + ((static_cast<size_t>(b) * 4 + hd) * g.nc + ch) * L::H1_BYTES, L::H1_BYTES,
+               &bar_full[s]);
+  };
+  auto load_x = [&](int tile, float* xr) {
+    const int b = tile / g.nc, ch = tile % g.nc;
+    const int tau = ch * kTok + tok;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
+#pragma unroll
+    for (int it = 0; it < (C + 31) / 32; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = head * 8 + it * 32 + i;
+        xr[it * 8 + i] = (tau < g.S && c < C) ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
+      }
+  };
+
+  if (tid == 0) {
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_mma, 1);
+    mbar_fence_init();
+    if (static_cast<int>(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
+  float xres[NX];
+  if (static_cast<int>(blockIdx.x) < ntiles) load_x(blockIdx.x, xres);
+  stage(par + L::P_OW, p.outnorm_weight, E);
+  stage(par + L::P_SK, p.learnable_skip, E);
+  stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int nxt = tile + gridDim.x;
+    if (tid == 0 && nxt < ntiles) issue(nxt, s ^ 1);
+    float xnext[NX];
+    if (nxt < ntiles) load_x(nxt, xnext);
+    const int b = tile / g.nc, ch = tile % g.nc;
+    const int tau = ch * kTok + tok;
+    const bool valid = tau < g.S;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
+    mbar_wait(&bar_full[s], (it >> 1) & 1);
+    {
+      const unsigned char* st = smem + s * L::STAGE_BYTES;
+      HeadInputs<DH> in;
+      in.load_smem(st + L::S_H + head * L::H1_BYTES, tok, reinterpret_cast<const float*>(st + L::S_ACT) + head * DH * kTok + tok,
+                   reinterpret_cast<const float*>(st + L::S_Z) + head * DH * kTok + tok);
+      float hg[DH];
+      in.gated(par + L::P_OW + head * DH, par + L::P_SK + head * DH, hg, nullptr, nullptr);
+#pragma unroll
+      for (int cg = 0; cg < DH / 8; ++cg) {
+        float v8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = valid ? hg[cg * 8 + i] : 0.f;
+        uint4 hi, lo;
+        split8_hilo(v8, hi, lo);
+        *reinterpret_cast<uint4*>(smem + L::HGHI + tile_off16(kTok, tok, head * (DH / 8) + cg)) = hi;
+        *reinterpret_cast<uint4*>(smem + L::HGLO + tile_off16(kTok, tok, head * (DH / 8) + cg)) = lo;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      umma_gemm_hilo(tmem, smem_u32(smem + L::HGHI), smem_u32(smem + L::HGLO), kTok * 16, 128, smem_u32(smem + L::WDHI),
+                     smem_u32(smem + L::WDLO), C * 16, 128, umma_idesc(128, C, false, false), E);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, it & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < (C + 31) / 32; ++k) {
+      const int c0 = head * 8 + k * 32;
+      if (c0 < C) {
+        float o[8];
+        tmem_ld8(tmem + lane_base + c0, o);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[b * g.ysb + n * g.ysn + (c0 + i) * g.ysc] = xres[k * 8 + i] + o[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xres[i] = xnext[i];
+    tc_fence_before();
+    __syncthreads();      // stage s, the gated tile and the accumulator are free again
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int C>
+static int launch_post_fwd_persist(const float* x, const void* h, const float* act, const float* z, const xhved_vil_params* p,
+                                   const VilGeom& g, float* y, cudaStream_t st) {
+  const size_t smem = PostPersist<C>::TOTAL;
+  cudaError_t e = cudaFuncSetAttribute(vil_post_fwd_persist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int ntiles = g.B * g.nc;
+  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  ProfScope ps(K_VIL_POST_FWD, st);
+  vil_post_fwd_persist_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y, ntiles);
   return (int)cudaGetLastError();
 }
 
@@ -342,8 +508,8 @@ extern "C" int xhved_vil_post_fwd(const float* x, const void* h_tiles, const flo
   if (!x || !h_tiles || !act || !z || !p || !y) return XHVED_ERR_BAD_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (sh->C) {
-    case 16: return launch_post_fwd<16>(x, h_tiles, act, z, p, g, y, st);
-    case 32: return launch_post_fwd<32>(x, h_tiles, act, z, p, g, y, st);
+    case 16: return launch_post_fwd_persist<16>(x, h_tiles, act, z, p, g, y, st);
+    case 32: return launch_post_fwd_persist<32>(x, h_tiles, act, z, p, g, y, st);
     case 64: return launch_post_fwd<64>(x, h_tiles, act, z, p, g, y, st);
     default: return XHVED_ERR_UNSUPPORTED_DIM;
   }
