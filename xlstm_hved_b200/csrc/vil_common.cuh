@@ -44,11 +44,20 @@ __device__ __forceinline__ xhved_vil_grads replica_of(xhved_vil_grads gr, const 
   return gr;
 }
 
-__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// sigmoid through the SFU (ex2 + rcp, ~2 ulp): an IEEE division costs ~15 issue slots and these kernels are issue-bound.
+// The exponent is clamped so that the denominator stays inside __fdividef's exact range (< 2^126).
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(fminf(-x, 80.f))); }
+__device__ __forceinline__ float silu(float x) { return x * fast_sigmoid(x); }
 // d/dx silu(x) = s + x s (1 - s), s = sigmoid(x)
 __device__ __forceinline__ float dsilu(float x) {
-  const float s = 1.f / (1.f + __expf(-x));
+  const float s = fast_sigmoid(x);
   return s * (1.f + x * (1.f - s));
+}
+// silu and its derivative from one sigmoid
+__device__ __forceinline__ void silu_both(float x, float& y, float& dy) {
+  const float s = fast_sigmoid(x);
+  y = x * s;
+  dy = s * (1.f + x * (1.f - s));
 }
 
 __device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int n) {

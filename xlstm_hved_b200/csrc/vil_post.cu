@@ -174,7 +174,7 @@ struct PostPersist {
                             PAR = WDLO + WD_BYTES;
   static constexpr int P_OW = 0, P_SK = E, P_N = 2 * E;
   static constexpr uint32_t TOTAL = PAR + P_N * 4;
-  static constexpr uint32_t TMEM_COLS = next_pow2_tmem(C);
+  static constexpr uint32_t ACC_COLS = next_pow2_tmem(C), TMEM_COLS = 2 * ACC_COLS;
 };
 
 template <int C>
@@ -234,17 +234,34 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
 
-  int it = 0;
+  // Software pipeline over the CTA's tiles: the UMMA of tile j runs while tile j-1's accumulator is drained and tile j+1's
+  // inputs are gated; one __syncthreads per tile.  Accumulators alternate between two TMEM column ranges.
+  auto epilogue = [&](int tile, uint32_t acc, const float* xr) {
+    const int b = tile / g.nc, ch = tile % g.nc;
+    const int tau = ch * kTok + tok;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
+#pragma unroll
+    for (int k = 0; k < (C + 31) / 32; ++k) {
+      const int c0 = head * 8 + k * 32;
+      if (c0 < C) {
+        float o[8];
+        tmem_ld8(acc + lane_base + c0, o);
+        if (tau < g.S) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[b * g.ysb + n * g.ysn + (c0 + i) * g.ysc] = xr[k * 8 + i] + o[i];
+        }
+      }
+    }
+  };
+  int it = 0, prev_tile = -1;
+  float xprev[NX];
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int s = it & 1;
     const int nxt = tile + gridDim.x;
     if (tid == 0 && nxt < ntiles) issue(nxt, s ^ 1);
     float xnext[NX];
     if (nxt < ntiles) load_x(nxt, xnext);
-    const int b = tile / g.nc, ch = tile % g.nc;
-    const int tau = ch * kTok + tok;
-    const bool valid = tau < g.S;
-    const int n = g.reverse ? g.S - 1 - tau : tau;
+    const bool valid = (tile % g.nc) * kTok + tok < g.S;
     mbar_wait(&bar_full[s], (it >> 1) & 1);
     {
       const unsigned char* st = smem + s * L::STAGE_BYTES;
@@ -253,6 +270,10 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
                    reinterpret_cast<const float*>(st + L::S_Z) + head * DH * kTok + tok);
       float hg[DH];
       in.gated(par + L::P_OW + head * DH, par + L::P_SK + head * DH, hg, nullptr, nullptr);
+      if (it > 0) {       // the previous product has read the gated tile and filled its accumulator
+        mbar_wait(&bar_mma, (it - 1) & 1);
+        tc_fence_after();
+      }
 #pragma unroll
       for (int cg = 0; cg < DH / 8; ++cg) {
         float v8[8];
@@ -269,30 +290,22 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
-      umma_gemm_hilo(tmem, smem_u32(smem + L::HGHI), smem_u32(smem + L::HGLO), kTok * 16, 128, smem_u32(smem + L::WDHI),
+      umma_gemm_hilo(tmem + s * L::ACC_COLS, smem_u32(smem + L::HGHI), smem_u32(smem + L::HGLO), kTok * 16, 128, smem_u32(smem + L::WDHI),
                      smem_u32(smem + L::WDLO), C * 16, 128, umma_idesc(128, C, false, false), E);
       umma_commit(&bar_mma);
     }
-    mbar_wait(&bar_mma, it & 1);
-    tc_fence_after();
+    if (it > 0) epilogue(prev_tile, tmem + (s ^ 1) * L::ACC_COLS, xprev);
 #pragma unroll
-    for (int k = 0; k < (C + 31) / 32; ++k) {
-      const int c0 = head * 8 + k * 32;
-      if (c0 < C) {
-        float o[8];
-        tmem_ld8(tmem + lane_base + c0, o);
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[b * g.ysb + n * g.ysn + (c0 + i) * g.ysc] = xres[k * 8 + i] + o[i];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xres[i] = xnext[i];
-    tc_fence_before();
-    __syncthreads();      // stage s, the gated tile and the accumulator are free again
-    tc_fence_after();
+    for (int i = 0; i < NX; ++i) xprev[i] = xres[i], xres[i] = xnext[i];
+    prev_tile = tile;
   }
+  if (it > 0) {
+    mbar_wait(&bar_mma, (it - 1) & 1);
+    tc_fence_after();
+    epilogue(prev_tile, tmem + ((it - 1) & 1) * L::ACC_COLS, xprev);
+  }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
@@ -410,10 +423,11 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
   for (int d = 0; d < DH; ++d) {
     const int e = head * DH + d;
     const float a = in.a[d], zz = in.z[d];
-    const float sz = silu(zz);
+    float sz, dsz;
+    silu_both(zz, sz, dsz);
     const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
     const float dhs = valid ? dhg[d] * sz : 0.f;
-    dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsilu(zz) : 0.f;
+    dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsz : 0.f;
     d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sk[d];
     r1[d] = dhs * a;
     r2[d] = dhs * xhat[d];
