@@ -150,6 +150,8 @@ class HotPath:
                 x=torch.zeros(B, DIM, *SPATIAL, device=device),
                 ready=torch.cuda.Event(), free=torch.cuda.Event()))
         self.copy_stream = torch.cuda.Stream(device=device)
+        self.kld = torch.zeros(4, device=device)                                 # per-level KL sums of a step
+        self.kld_w = torch.tensor([0.5 / (B * C * d ** 3) / 4 for C, d in LEVELS], device=device)
 
     def load(self, x, mus, lvs, slot=0):
         """Copy one batch into the device buffers of `slot` (H2D when the sources are pinned host tensors) on the copy
@@ -191,13 +193,13 @@ class HotPath:
         sl = self.slots[slot]
         mu5, lv5 = sl["mu5"], sl["lv5"]
         # ---- S-MVAE: fusion + sampling + KL in one launch per level, backward in one launch per level
-        kld_total = None
+        self.kld.zero_()
         for l in range(4):
             noise = torch.empty_like(self.gz[l]).normal_()                     # RA_HVED.py:743-744 semantics
             n = mu5[l][0].numel()
-            _, _, z, kld = ops.poe_fwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, want_kld=True)
+            ops.poe_fwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, kld_out=self.kld[l:l + 1])
             ops.poe_bwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, g_z=self.gz[l], kld_scale=[0.2 * 0.5 / n / 4])
-            kld_total = kld[0] * (0.5 / n / 4) if kld_total is None else kld_total + kld[0] * (0.5 / n / 4)
+        kld_total = torch.dot(self.kld, self.kld_w)                            # mean KL over the 4 levels (train.py:236-239)
         # ---- ViL block pair on the NCDHW feature (token view, no transposed copies), forward + backward
         x = sl["x"].detach().requires_grad_()
         tok = x.reshape(self.B, DIM, -1).transpose(-1, -2)

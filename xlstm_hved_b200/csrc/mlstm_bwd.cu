@@ -64,9 +64,11 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_rstate_kernel(const unsi
   constexpr uint32_t TILE = kL * DHP * 2;
   constexpr uint32_t TMEM_COLS = next_pow2_cols(NE);
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sQ = smem;                     // Q~ hi: 32 KB window (read as a 128-row MN-major A operand)
-  unsigned char* sQlo = smem + 32768;           // Q~ lo
-  unsigned char* sG = smem + 65536;             // [128][NE]
+  // Q~ hi / lo are read as 128-row MN-major A operands, i.e. through a 32 KB window each; rows >= DHP of the product are
+  // never read, so the windows simply run on over the lo tile, G, H (and each other) instead of owning 32 KB of padding
+  unsigned char* sQ = smem;
+  unsigned char* sQlo = smem + TILE;
+  unsigned char* sG = smem + 2 * TILE;          // [128][NE]
   unsigned char* sH = sG + kL * NE * 2;         // [128][DHP]
   __shared__ __align__(8) uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_slot;
@@ -426,7 +428,8 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   const int ntiles = BH * nc;
   {
-    const size_t smem = 65536 + kL * NE * 2 + kL * DHP * 2;
+    const size_t used = 3 * kL * DHP * 2 + kL * NE * 2, window = kL * DHP * 2 + 32768;
+    const size_t smem = used > window ? used : window;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_rstate_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_CHUNK_RSTATE, st);

@@ -28,11 +28,12 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
   constexpr int NE = ext_cols(DHP);
   constexpr uint32_t TILE = kL * DHP * 2;
   constexpr uint32_t TMEM_COLS = next_pow2_cols(NE);
-  // smem: [K~ hi | K~ lo, each read as a 128-row MN-major A operand => 32 KB window][Vext tile]
+  // smem: [K~ hi][K~ lo][Vext tile].  K~ hi / lo are read as 128-row MN-major A operands, i.e. through a 32 KB window each;
+  // rows >= DHP of the product are never read, so the windows run on over the following tiles instead of owning padding
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sK = smem;
-  unsigned char* sKlo = smem + 32768;
-  unsigned char* sV = smem + 65536;
+  unsigned char* sKlo = smem + TILE;
+  unsigned char* sV = smem + 2 * TILE;
   __shared__ __align__(8) uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8];
@@ -393,7 +394,8 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
   const int ntiles = BH * nc;
   // phase 1
   {
-    const size_t smem = 65536 + kL * NE * 2;
+    const size_t used = 2 * kL * DHP * 2 + kL * NE * 2, window = kL * DHP * 2 + 32768;
+    const size_t smem = used > window ? used : window;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_state_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_CHUNK_STATE, st);

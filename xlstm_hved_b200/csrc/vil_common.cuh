@@ -60,6 +60,21 @@ __device__ __forceinline__ void silu_both(float x, float& y, float& dy) {
   dy = s * (1.f + x * (1.f - s));
 }
 
+// SM count of the current device (persistent kernels launch one or two CTAs per SM)
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+inline int persistent_grid(int ntiles, int ctas_per_sm) {
+  const int cap = sm_count() * ctas_per_sm;
+  return ntiles < cap ? ntiles : cap;
+}
+
 __device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }

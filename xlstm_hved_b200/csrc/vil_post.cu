@@ -309,16 +309,6 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
-inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
 template <int C>
 static int launch_post_fwd_persist(const float* x, const void* h, const float* act, const float* z, const xhved_vil_params* p,
                                    const VilGeom& g, float* y, cudaStream_t st) {
@@ -326,7 +316,7 @@ static int launch_post_fwd_persist(const float* x, const void* h, const float* a
   cudaError_t e = cudaFuncSetAttribute(vil_post_fwd_persist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int ntiles = g.B * g.nc;
-  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  const int grid = persistent_grid(ntiles, 1);
   ProfScope ps(K_VIL_POST_FWD, st);
   vil_post_fwd_persist_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y, ntiles);
   return (int)cudaGetLastError();

@@ -517,10 +517,12 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
                                                                                         const float* __restrict__ dconv,
                                                                                         const float* __restrict__ dxmv,
                                                                                         const float* __restrict__ dz, float* __restrict__ dx,
-                                                                                        xhved_vil_grads gr_base) {
+                                                                                        xhved_vil_grads gr_base, int ntiles) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, part).  Every part owns CP channels of its token for the LayerNorm (statistics are
   // exchanged through shared memory) and a quarter of the 2E columns of d[x_mlstm | z].
+  // Persistent: the CTA walks tiles blockIdx.x, +gridDim.x, ...; parameters are staged once, and d proj_up / d norm.weight
+  // accumulate over all of the CTA's tiles (the UMMA keeps adding into the same TMEM columns) before ONE flush to global.
   using L = PreBwdBTC<C>;
   constexpr int E = L::E, CP = L::CP, NPART = L::NPART;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -533,15 +535,14 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
   const int tok = tid & (kTok - 1), part = tid >> 7;
   const bool ln_on = part < NPART;
   const int c0 = part * CP;
-  const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
-  const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
-  const int tau = ch * kTok + tok;
-  const bool valid = tau < g.S;
-  const int n = g.reverse ? g.S - 1 - tau : tau;
-  // this thread's channels of x (issued first: the latency overlaps the staging below)
-  float xin[CP];
+  auto load_x = [&](int tile, float* xin) {
+    const int b = tile / g.nc, tau = (tile % g.nc) * kTok + tok;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
 #pragma unroll
-  for (int i = 0; i < CP; ++i) xin[i] = (valid && ln_on) ? __ldg(x + b * g.xsb + n * g.xsn + (c0 + i) * g.xsc) : 0.f;
+    for (int i = 0; i < CP; ++i) xin[i] = (tau < g.S && ln_on) ? __ldg(x + b * g.xsb + n * g.xsn + (c0 + i) * g.xsc) : 0.f;
+  };
+  float xin[CP];
+  load_x(blockIdx.x, xin);
   if (tid == 0) {
     mbar_init(&bar1, 1);
     mbar_fence_init();
@@ -552,112 +553,132 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
   stage(par + L::P_NW, p.norm_weight, C);
   for (int i = tid; i < C; i += blockDim.x) par[L::P_ANW + i] = 0.f;
   stage_weight_tile(p.proj_up_weight, 2 * E, C, 2 * E, smem + L::WHI, smem + L::WLO);
-  // ---- LayerNorm statistics, two passes through shared memory (mean, then centred second moment)
-  float s1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < CP; ++i) s1 += xin[i];
-  ln1[part * kTok + tok] = ln_on ? s1 : 0.f;
-  __syncthreads();
-  const float mean = (ln1[tok] + ln1[kTok + tok] + ln1[2 * kTok + tok] + ln1[3 * kTok + tok]) * (1.f / C);
-  float s2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < CP; ++i) s2 += (xin[i] - mean) * (xin[i] - mean);
-  ln2[part * kTok + tok] = ln_on ? s2 : 0.f;
-  __syncthreads();
-  const float rstd = rsqrtf((ln2[tok] + ln2[kTok + tok] + ln2[2 * kTok + tok] + ln2[3 * kTok + tok]) * (1.f / C) + 1e-5f);
-  float xhat[CP];
-#pragma unroll
-  for (int i = 0; i < CP; ++i) xhat[i] = (xin[i] - mean) * rstd;
-  if (ln_on) {
-#pragma unroll
-    for (int cg = 0; cg < CP / 8; ++cg) {
-      float v8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v8[i] = valid ? xhat[cg * 8 + i] * (1.f + par[L::P_NW + c0 + cg * 8 + i]) : 0.f;
-      *reinterpret_cast<uint4*>(smem + L::XNT + tile_off16(kTok, tok, c0 / 8 + cg)) = pack8_bf16(v8);
-    }
-  }
-  // ---- d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
-#pragma unroll 1
-  for (int o8 = part * 8; o8 < 2 * E; o8 += 32) {
-    float d8[8];
-    if (o8 < E) {
-      float dc[4][8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int tp = tau + k;
-        const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int o = o8 + i;
-        float d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d += par[L::P_CW + o * 4 + 3 - k] * dc[k][i];
-        d8[i] = valid ? d : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
-        d8[i] = valid ? d : 0.f;
-      }
-    }
-    uint4 hi, lo;
-    split8_hilo(d8, hi, lo);
-    *reinterpret_cast<uint4*>(smem + L::DINHI + tile_off16(kTok, tok, o8 / 8)) = hi;
-    *reinterpret_cast<uint4*>(smem + L::DINLO + tile_off16(kTok, tok, o8 / 8)) = lo;
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
-    // dxn[tok][c] = sum_o din[tok][o] W_up[o][c]          (B = MN-major view of the [2E][C] weight tile)
-    umma_gemm_hilo(tmem, smem_u32(smem + L::DINHI), smem_u32(smem + L::DINLO), kTok * 16, 128, smem_u32(smem + L::WHI),
-                   smem_u32(smem + L::WLO), 128, 2 * E * 16, umma_idesc(128, C, false, true), 2 * E);
-    // d proj_up[o][c] = sum_tok din[tok][o] xn[tok][c]     (both operands MN-major views of token-row tiles)
-#pragma unroll
-    for (int mt = 0; mt < L::MT; ++mt)
-      umma_gemm(tmem + C + mt * C, smem_u32(smem + L::DINHI) + mt * 16 * kTok * 16, 128, kTok * 16, smem_u32(smem + L::XNT), 128, kTok * 16,
-                umma_idesc(128, C, true, true), kTok, false);
-    umma_commit(&bar1);
-  }
-  mbar_wait(&bar1, 0);
-  tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  // ---- LayerNorm backward (weight 1+w, no bias), channels c0..c0+CP of this token
-  float dxn[CP], red[CP];
-  if (ln_on) {
+
+  int it = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = tile / g.nc, ch = tile % g.nc;
+    const size_t tm_chunk = static_cast<size_t>(tile) * E * kTok;
+    const int tau = ch * kTok + tok;
+    const bool valid = tau < g.S;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
+    // ---- LayerNorm statistics, two passes through shared memory (mean, then centred second moment)
+    float s1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < CP; i += 8) tmem_ld8(tmem + lane_base + c0 + i, dxn + i);
-  }
-  float pg = 0.f, pgx = 0.f;
+    for (int i = 0; i < CP; ++i) s1 += xin[i];
+    ln1[part * kTok + tok] = ln_on ? s1 : 0.f;
+    __syncthreads();
+    const float mean = (ln1[tok] + ln1[kTok + tok] + ln1[2 * kTok + tok] + ln1[3 * kTok + tok]) * (1.f / C);
+    float s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < CP; ++i) {
-    if (!ln_on) dxn[i] = 0.f;
-    red[i] = valid ? dxn[i] * xhat[i] : 0.f;
-    dxn[i] *= 1.f + par[L::P_NW + (ln_on ? c0 + i : 0)];
-    pg += dxn[i];
-    pgx += dxn[i] * xhat[i];
-  }
-  ln1[part * kTok + tok] = ln_on ? pg : 0.f;
-  ln2[part * kTok + tok] = ln_on ? pgx : 0.f;
-  __syncthreads();
-  const float mean_g = (ln1[tok] + ln1[kTok + tok] + ln1[2 * kTok + tok] + ln1[3 * kTok + tok]) * (1.f / C);
-  const float mean_gx = (ln2[tok] + ln2[kTok + tok] + ln2[2 * kTok + tok] + ln2[3 * kTok + tok]) * (1.f / C);
-  if (valid && ln_on) {
+    for (int i = 0; i < CP; ++i) s2 += (xin[i] - mean) * (xin[i] - mean);
+    ln2[part * kTok + tok] = ln_on ? s2 : 0.f;
+    __syncthreads();
+    const float rstd = rsqrtf((ln2[tok] + ln2[kTok + tok] + ln2[2 * kTok + tok] + ln2[3 * kTok + tok]) * (1.f / C) + 1e-5f);
+    float xhat[CP];
+#pragma unroll
+    for (int i = 0; i < CP; ++i) xhat[i] = (xin[i] - mean) * rstd;
+    if (ln_on) {
+#pragma unroll
+      for (int cg = 0; cg < CP / 8; ++cg) {
+        float v8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = valid ? xhat[cg * 8 + i] * (1.f + par[L::P_NW + c0 + cg * 8 + i]) : 0.f;
+        *reinterpret_cast<uint4*>(smem + L::XNT + tile_off16(kTok, tok, c0 / 8 + cg)) = pack8_bf16(v8);
+      }
+    }
+    // ---- d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
+#pragma unroll 1
+    for (int o8 = part * 8; o8 < 2 * E; o8 += 32) {
+      float d8[8];
+      if (o8 < E) {
+        float dc[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int tp = tau + k;
+          const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int o = o8 + i;
+          float d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d += par[L::P_CW + o * 4 + 3 - k] * dc[k][i];
+          d8[i] = valid ? d : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
+          d8[i] = valid ? d : 0.f;
+        }
+      }
+      uint4 hi, lo;
+      split8_hilo(d8, hi, lo);
+      *reinterpret_cast<uint4*>(smem + L::DINHI + tile_off16(kTok, tok, o8 / 8)) = hi;
+      *reinterpret_cast<uint4*>(smem + L::DINLO + tile_off16(kTok, tok, o8 / 8)) = lo;
+    }
+    // loads whose latency hides behind the MMA: the residual path's upstream gradient and the next tile's tokens
+    float dyin[CP];
+#pragma unroll
+    for (int i = 0; i < CP; ++i) dyin[i] = (valid && ln_on) ? __ldg(dy + b * g.ysb + n * g.ysn + (c0 + i) * g.ysc) : 0.f;
+    if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x, xin);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      // dxn[tok][c] = sum_o din[tok][o] W_up[o][c]          (B = MN-major view of the [2E][C] weight tile)
+      umma_gemm_hilo(tmem, smem_u32(smem + L::DINHI), smem_u32(smem + L::DINLO), kTok * 16, 128, smem_u32(smem + L::WHI),
+                     smem_u32(smem + L::WLO), 128, 2 * E * 16, umma_idesc(128, C, false, true), 2 * E);
+      // d proj_up[o][c] += sum_tok din[tok][o] xn[tok][c]    (both operands MN-major views of token-row tiles)
+#pragma unroll
+      for (int mt = 0; mt < L::MT; ++mt)
+        umma_gemm(tmem + C + mt * C, smem_u32(smem + L::DINHI) + mt * 16 * kTok * 16, 128, kTok * 16, smem_u32(smem + L::XNT), 128, kTok * 16,
+                  umma_idesc(128, C, true, true), kTok, it > 0);
+      umma_commit(&bar1);
+    }
+    mbar_wait(&bar1, it & 1);
+    tc_fence_after();
+    // ---- LayerNorm backward (weight 1+w, no bias), channels c0..c0+CP of this token
+    float dxn[CP], red[CP];
+    if (ln_on) {
+#pragma unroll
+      for (int i = 0; i < CP; i += 8) tmem_ld8(tmem + lane_base + c0 + i, dxn + i);
+    }
+    float pg = 0.f, pgx = 0.f;
 #pragma unroll
     for (int i = 0; i < CP; ++i) {
-      const float v = rstd * (dxn[i] - mean_g - xhat[i] * mean_gx);
-      const int c = c0 + i;
-      dx[b * g.ysb + n * g.ysn + c * g.ysc] = __ldg(dy + b * g.ysb + n * g.ysn + c * g.ysc) + v;
+      if (!ln_on) dxn[i] = 0.f;
+      red[i] = valid ? dxn[i] * xhat[i] : 0.f;
+      dxn[i] *= 1.f + par[L::P_NW + (ln_on ? c0 + i : 0)];
+      pg += dxn[i];
+      pgx += dxn[i] * xhat[i];
     }
+    ln1[part * kTok + tok] = ln_on ? pg : 0.f;
+    ln2[part * kTok + tok] = ln_on ? pgx : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    const float mean_g = (ln1[tok] + ln1[kTok + tok] + ln1[2 * kTok + tok] + ln1[3 * kTok + tok]) * (1.f / C);
+    const float mean_gx = (ln2[tok] + ln2[kTok + tok] + ln2[2 * kTok + tok] + ln2[3 * kTok + tok]) * (1.f / C);
+    if (valid && ln_on) {
+#pragma unroll
+      for (int i = 0; i < CP; ++i) {
+        const float v = rstd * (dxn[i] - mean_g - xhat[i] * mean_gx);
+        dx[b * g.ysb + n * g.ysn + (c0 + i) * g.ysc] = dyin[i] + v;
+      }
+    }
+    if (ln_on) warp_acc_vec<CP>(par + L::P_ANW + c0, red);
+    __syncthreads();     // LayerNorm exchange buffers are rewritten by the next tile
   }
-  if (ln_on) warp_acc_vec<CP>(par + L::P_ANW + c0, red);
+  tc_fence_after();
   // ---- weight-gradient rows: lane = output row o (second M tile: o + 128); the parts split the C columns
 #pragma unroll
   for (int mt = 0; mt < L::MT; ++mt) {
@@ -672,7 +693,6 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
       }
     }
   }
-  __syncthreads();
   for (int c = tid; c < C; c += blockDim.x) atomicAdd(gr.norm_weight + c, par[L::P_ANW + c]);
   tc_fence_before();
   __syncthreads();
@@ -993,7 +1013,9 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_b_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_B, st);
-    vil_pre_bwd_b_tc_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr);
+    const int ntiles = g.B * g.nc;
+    vil_pre_bwd_b_tc_kernel<C><<<persistent_grid(ntiles, C <= 32 ? 2 : 1), 4 * kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr,
+                                                                                                ntiles);
   }
   return (int)cudaGetLastError();
 }

@@ -49,9 +49,12 @@ def _masks(subsets):
     return arr
 
 
-def poe_fwd(mu5: torch.Tensor, logvar5: torch.Tensor, subsets, drop=None, noise=None, want_kld=False, eps: float = 1e-8):
+def poe_fwd(mu5: torch.Tensor, logvar5: torch.Tensor, subsets, drop=None, noise=None, want_kld=False, eps: float = 1e-8,
+            kld_out=None):
     """All requested subsets in one launch.  mu5/logvar5: (5, ...) fp32 contiguous (prior first).
-    Returns (pd_mu, pd_logvar, z or None, kld_sums or None) each of shape (len(subsets), ...)."""
+    Returns (pd_mu, pd_logvar, z or None, kld_sums or None) each of shape (len(subsets), ...).
+    kld_out: optional pre-zeroed fp32 buffer of len(subsets) elements the KL sums are accumulated into (lets a caller
+    collect the sums of several latent levels in one tensor)."""
     lib = _lib.load_library()
     assert mu5.shape == logvar5.shape and mu5.shape[0] == 5
     mu5, logvar5 = _f32c(mu5), _f32c(logvar5)
@@ -60,7 +63,11 @@ def poe_fwd(mu5: torch.Tensor, logvar5: torch.Tensor, subsets, drop=None, noise=
     out_mu = torch.empty((ns, *mu5.shape[1:]), device=mu5.device, dtype=torch.float32)
     out_lv = torch.empty_like(out_mu)
     z = torch.empty_like(out_mu) if noise is not None else None
-    kld = torch.zeros(ns, device=mu5.device, dtype=torch.float32) if want_kld else None
+    if kld_out is not None:
+        assert kld_out.dtype == torch.float32 and kld_out.is_contiguous() and kld_out.numel() == ns and kld_out.device == mu5.device
+        kld = kld_out
+    else:
+        kld = torch.zeros(ns, device=mu5.device, dtype=torch.float32) if want_kld else None
     per_sample = 0
     if drop is not None:
         drop = drop.to(device=mu5.device, dtype=torch.uint8).contiguous()
