@@ -490,6 +490,228 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
+// Persistent variant (C <= 32): one CTA per SM walks the token tiles.  h / act / z tiles of tile i+1 stream into the second
+// smem stage (bulk copies) while tile i is processed; d proj_down accumulates in TMEM and d learnable_skip / d outnorm.weight
+// in shared memory over all of the CTA's tiles, and are flushed to global once.
+template <int C>
+struct PostBwdPersist {
+  static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH;
+  static constexpr uint32_t ACT_BYTES = E * kTok * 4, H1_BYTES = kTok * DHP * 2, STAGE_BYTES = 2 * ACT_BYTES + 4 * H1_BYTES;
+  static constexpr uint32_t S_ACT = 0, S_Z = ACT_BYTES, S_H = 2 * ACT_BYTES;
+  static constexpr uint32_t HG_BYTES = kTok * E * 2, DY_BYTES = kTok * C * 2, WD_BYTES = C * E * 2, DHT_BYTES = 4 * H1_BYTES;
+  // HG is read as a 128-row MN-major A operand through a 32 KB window that runs on over the tiles behind it
+  static constexpr uint32_t HG = 2 * STAGE_BYTES, DYHI = HG + HG_BYTES, DYLO = DYHI + DY_BYTES, WDHI = DYLO + DY_BYTES,
+                            WDLO = WDHI + WD_BYTES, DHT = WDLO + WD_BYTES, PAR = DHT + DHT_BYTES;
+  static constexpr int P_OW = 0, P_SK = E, P_ASK = 2 * E, P_AOW = 3 * E, P_N = 4 * E;
+  static constexpr uint32_t END = PAR + P_N * 4;
+  static constexpr uint32_t TOTAL = END > HG + 32768 ? END : HG + 32768;
+  static constexpr uint32_t TMEM_COLS = next_pow2_tmem(E + C);
+};
+
+template <int C>
+__global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
+                                                                            const float* __restrict__ act, const float* __restrict__ z,
+                                                                            xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
+                                                                            float* __restrict__ d_act, float* __restrict__ dz,
+                                                                            xhved_vil_grads gr_base, int ntiles) {
+  const xhved_vil_grads gr = replica_of(gr_base, g);
+  using L = PostBwdPersist<C>;
+  constexpr int E = L::E, DH = L::DH, DHP = L::DHP;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* par = reinterpret_cast<float*>(smem + L::PAR);
+  __shared__ __align__(8) uint64_t bar_full[2], bar1, bar2;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tok = tid & (kTok - 1), head = tid >> 7;
+
+  auto issue = [&](int tile, int s) {
+    unsigned char* st = smem + s * L::STAGE_BYTES;
+    mbar_expect_tx(&bar_full[s], L::STAGE_BYTES);
+    bulk_g2s(st + L::S_ACT, act + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
+    bulk_g2s(st + L::S_Z, z + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
+    const int b = tile / g.nc, ch = tile % g.nc;
+#pragma unroll
+    for (int hd = 0; hd < 4; ++hd)
+      bulk_g2s(st + L::S_H + hd * L::H1_BYTES, h_tiles + ((static_cast<size_t>(b) * 4 + hd) * g.nc + ch) * L::H1_BYTES, L::H1_BYTES,
+               &bar_full[s]);
+  };
+  // this thread's 8 channels of dy (column group `head` of the token; C <= 32 => at most one group per thread)
+  auto load_dy = [&](int tile, float* v8) {
+    const int b = tile / g.nc, tau = (tile % g.nc) * kTok + tok;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = (tau < g.S && head * 8 < C) ? __ldg(dy + b * g.ysb + n * g.ysn + (head * 8 + i) * g.ysc) : 0.f;
+  };
+
+  if (tid == 0) {
+    mbar_init(&bar_full[0], 1);
+    mbar_init(&bar_full[1], 1);
+    mbar_init(&bar1, 1);
+    mbar_init(&bar2, 1);
+    mbar_fence_init();
+    issue(blockIdx.x, 0);
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
+  float dy8[8];
+  load_dy(blockIdx.x, dy8);
+  stage(par + L::P_OW, p.outnorm_weight, E);
+  stage(par + L::P_SK, p.learnable_skip, E);
+  for (int i = tid; i < 2 * E; i += blockDim.x) par[L::P_ASK + i] = 0.f;
+  stage_weight_tile(p.proj_down_weight, C, E, C, smem + L::WDHI, smem + L::WDLO);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float* ow = par + L::P_OW + head * DH;
+  const float* sk = par + L::P_SK + head * DH;
+
+  int it = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int nxt = tile + gridDim.x;
+    if (tid == 0 && nxt < ntiles) issue(nxt, s ^ 1);
+    const int b = tile / g.nc, ch = tile % g.nc;
+    const bool valid = ch * kTok + tok < g.S;
+    const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;
+    if (it > 0) {     // the previous tile's weight-gradient product still reads the dy and gated tiles
+      mbar_wait(&bar2, (it - 1) & 1);
+      tc_fence_after();
+    }
+    if (head * 8 < C) {
+      uint4 hi, lo;
+      split8_hilo(dy8, hi, lo);
+      *reinterpret_cast<uint4*>(smem + L::DYHI + tile_off16(kTok, tok, head)) = hi;
+      *reinterpret_cast<uint4*>(smem + L::DYLO + tile_off16(kTok, tok, head)) = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      // dhg[tok][e] = sum_c dy[tok][c] W_down[c][e]     (B = MN-major view of the [C][E] weight tile)
+      umma_gemm_hilo(tmem, smem_u32(smem + L::DYHI), smem_u32(smem + L::DYLO), kTok * 16, 128, smem_u32(smem + L::WDHI),
+                     smem_u32(smem + L::WDLO), 128, C * 16, umma_idesc(128, E, false, true), C);
+      umma_commit(&bar1);
+    }
+    if (nxt < ntiles) load_dy(nxt, dy8);
+    // recompute the gated activation of this (token, head) while the MMA runs
+    mbar_wait(&bar_full[s], (it >> 1) & 1);
+    const unsigned char* st = smem + s * L::STAGE_BYTES;
+    HeadInputs<DH> in;
+    in.load_smem(st + L::S_H + head * L::H1_BYTES, tok, reinterpret_cast<const float*>(st + L::S_ACT) + head * DH * kTok + tok,
+                 reinterpret_cast<const float*>(st + L::S_Z) + head * DH * kTok + tok);
+    float hg[DH], xhat[DH], rstd;
+    in.gated(ow, sk, hg, xhat, &rstd);
+    mbar_wait(&bar1, it & 1);
+    tc_fence_after();
+    float dhg[DH];
+    if (DH >= 16) {
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 16) tmem_ld16(tmem + lane_base + head * DH + c0, dhg + c0);
+    } else {
+      tmem_ld8(tmem + lane_base + head * DH, dhg);
+    }
+    float gg[DH], r1[DH], r2[DH], mean_g = 0.f, mean_gx = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      const int e = head * DH + d;
+      const float a = in.a[d], zz = in.z[d];
+      float sz, dsz;
+      silu_both(zz, sz, dsz);
+      const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
+      const float dhs = valid ? dhg[d] * sz : 0.f;
+      dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsz : 0.f;
+      d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sk[d];
+      r1[d] = dhs * a;
+      r2[d] = dhs * xhat[d];
+      gg[d] = dhs * (1.f + ow[d]);
+      mean_g += gg[d];
+      mean_gx += gg[d] * xhat[d];
+    }
+    mean_g *= (1.f / DH);
+    mean_gx *= (1.f / DH);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int cg = 0; cg < DHP / 8; ++cg) {
+      uint4 u = zero;
+      if (cg * 8 < DH) {
+        float o8[8], hg8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int d = cg * 8 + i;
+          o8[i] = rstd * (gg[d] - mean_g - xhat[d] * mean_gx);
+          hg8[i] = valid ? hg[d] : 0.f;
+        }
+        u = pack8_bf16(o8);
+        *reinterpret_cast<uint4*>(smem + L::HG + tile_off16(kTok, tok, head * (DH / 8) + cg)) = pack8_bf16(hg8);
+      }
+      *reinterpret_cast<uint4*>(smem + L::DHT + tile_off16(kTok, tok, head * (DHP / 8) + cg)) = u;
+    }
+    // d learnable_skip / d outnorm.weight of this head's channels (accumulated over the CTA's tiles)
+#pragma unroll
+    for (int d0 = 0; d0 < DH; d0 += (DH < 32 ? DH : 32)) {
+      warp_acc_vec<(DH < 32 ? DH : 32)>(par + L::P_ASK + head * DH + d0, r1 + d0);
+      warp_acc_vec<(DH < 32 ? DH : 32)>(par + L::P_AOW + head * DH + d0, r2 + d0);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      // d proj_down^T[e][c] += sum_tok hg[tok][e] dy[tok][c]   (both operands MN-major views of token-row tiles)
+      umma_gemm(tmem + E, smem_u32(smem + L::HG), 128, kTok * 16, smem_u32(smem + L::DYHI), 128, kTok * 16, umma_idesc(128, C, true, true),
+                kTok, it > 0);
+      umma_commit(&bar2);
+#pragma unroll 1
+      for (int hd = 0; hd < 4; ++hd) {
+        const size_t t2 = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
+        bulk_s2g(dh_tiles + t2 * L::H1_BYTES, smem + L::DHT + hd * L::H1_BYTES, L::H1_BYTES);
+      }
+      bulk_commit();
+      bulk_wait_read();
+    }
+    __syncthreads();      // stage s and the dh tile are free again
+  }
+  if (it > 0) {
+    mbar_wait(&bar2, (it - 1) & 1);
+    tc_fence_after();
+  }
+  for (int e = tid; e < E; e += blockDim.x) {
+    atomicAdd(gr.learnable_skip + e, par[L::P_ASK + e]);
+    atomicAdd(gr.outnorm_weight + e, par[L::P_AOW + e]);
+  }
+  if ((warp & 3) * 32 < E) {
+#pragma unroll 1
+    for (int c0 = head * 16; c0 < C; c0 += 64) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + E + c0, v);
+      if (tok < E) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(gr.proj_down_weight + static_cast<size_t>(c0 + i) * E + tok, v[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
+}
+
+template <int C>
+static int launch_post_bwd_persist(const float* dy, const void* h, const float* act, const float* z, const xhved_vil_params* p,
+                                   const VilGeom& g, void* dh, float* d_act, float* dz, const xhved_vil_grads* gr, cudaStream_t st) {
+  const size_t smem = PostBwdPersist<C>::TOTAL;
+  cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_persist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int ntiles = g.B * g.nc;
+  ProfScope ps(K_VIL_POST_BWD, st);
+  vil_post_bwd_persist_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g,
+                                                                                    (unsigned char*)dh, d_act, dz, *gr, ntiles);
+  return (int)cudaGetLastError();
+}
+
 template <int C>
 static int launch_post_bwd(const float* dy, const void* h, const float* act, const float* z, const xhved_vil_params* p, const VilGeom& g,
                            void* dh, float* d_act, float* dz, const xhved_vil_grads* gr, cudaStream_t st) {
@@ -527,8 +749,8 @@ extern "C" int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const fl
   if (!dy || !h_tiles || !act || !z || !p || !dh_tiles || !d_act || !dz || !g) return XHVED_ERR_BAD_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (sh->C) {
-    case 16: return launch_post_bwd<16>(dy, h_tiles, act, z, p, geo, dh_tiles, d_act, dz, g, st);
-    case 32: return launch_post_bwd<32>(dy, h_tiles, act, z, p, geo, dh_tiles, d_act, dz, g, st);
+    case 16: return launch_post_bwd_persist<16>(dy, h_tiles, act, z, p, geo, dh_tiles, d_act, dz, g, st);
+    case 32: return launch_post_bwd_persist<32>(dy, h_tiles, act, z, p, geo, dh_tiles, d_act, dz, g, st);
     case 64: return launch_post_bwd<64>(dy, h_tiles, act, z, p, geo, dh_tiles, d_act, dz, g, st);
     default: return XHVED_ERR_UNSUPPORTED_DIM;
   }
