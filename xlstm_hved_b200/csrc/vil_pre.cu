@@ -68,27 +68,34 @@ __device__ __forceinline__ float dot_row(const float* xn, const float* wrow) {
 template <int C>
 struct PreTC {
   static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
+  // C <= 32: persistent CTAs (two per SM) keep the proj_up / gate weight tiles resident while they walk their token tiles.
+  // C = 64: one tile per CTA, and the q|k|v tile aliases ALL proj_up operands to fit into shared memory.
+  static constexpr bool PERSIST = C <= 32;
   static constexpr uint32_t X_BYTES = kTok * C * 2, W_BYTES = 2 * E * C * 2, QKV_BYTES = kTok * NQ * 2;
-  static constexpr uint32_t XHI = 0, XLO = X_BYTES, WHI = 2 * X_BYTES, WLO = 2 * X_BYTES + W_BYTES;
   static constexpr uint32_t OPER = (2 * X_BYTES + 2 * W_BYTES) > QKV_BYTES ? (2 * X_BYTES + 2 * W_BYTES) : QKV_BYTES;
-  static constexpr uint32_t QKV = 0;                              // aliases the proj_up operands once they are consumed
-  static constexpr uint32_t WG_BYTES = 16 * NQ * 2;
-  static constexpr uint32_t WGHI = OPER, WGLO = WGHI + WG_BYTES;
+  static constexpr uint32_t WHI = PERSIST ? 0 : 2 * X_BYTES, WLO = WHI + W_BYTES;
+  static constexpr uint32_t QKV = PERSIST ? 2 * W_BYTES : 0;      // the token tile's hi/lo rows alias the head of the q|k|v tile
+  static constexpr uint32_t XHI = QKV, XLO = QKV + X_BYTES;
+  // gate weights: [8 rows hh][NQ] bf16 tile read as a 16-row operand -- rows 8..15 of every column group fall onto the
+  // next group's rows 0..7 and only produce accumulator columns 8..15, which nobody reads
+  static constexpr uint32_t WG_BYTES = 8 * NQ * 2;
+  static constexpr uint32_t WGHI = PERSIST ? QKV + QKV_BYTES : OPER, WGLO = WGHI + WG_BYTES;
   static constexpr uint32_t XM = WGLO + WG_BYTES;                 // fp32 (131, E+1)
   static constexpr int XM_LD = E + 1;
   static constexpr uint32_t PAR = XM + ((kTok + 3) * XM_LD * 4 + 15) / 16 * 16;   // fp32 small parameters
   static constexpr int P_CW = 0, P_CB = E * 4, P_WQ = P_CB + E, P_WK = P_WQ + E * 4, P_WV = P_WK + E * 4, P_NW = P_WV + E * 4,
-                       P_HX = P_NW + C, P_N = P_HX + 3 * C;
+                       P_HX = P_NW + C, P_GB = P_HX + 3 * C, P_LN = P_GB + 8, P_N = P_LN + 2 * 4 * kTok;   // LN exchange: 2 x [4][128]
   static constexpr uint32_t TOTAL = PAR + P_N * 4;
   static constexpr uint32_t TMEM_COLS = next_pow2_tmem(2 * E + 16);
+  static_assert(2 * X_BYTES <= QKV_BYTES, "token rows must fit into the q|k|v tile they alias");
 };
 
 template <int C>
-__global__ void __launch_bounds__(4 * kTok) vil_pre_fwd_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
+__global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_fwd_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
                                                                 unsigned char* __restrict__ q_tiles, unsigned char* __restrict__ k_tiles,
                                                                 unsigned char* __restrict__ v_tiles, float* __restrict__ igp,
                                                                 float* __restrict__ fgp, float* __restrict__ act_out,
-                                                                float* __restrict__ z_out, float* __restrict__ xm_out) {
+                                                                float* __restrict__ z_out, float* __restrict__ xm_out, int ntiles) {
   // 512 threads: thread = (token, head); head group 0 additionally owns the LayerNorm and the gate read-out of its token
   using L = PreTC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
@@ -99,7 +106,6 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_fwd_kernel(const float* __re
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tok = tid & (kTok - 1), head = tid >> 7;
-  const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
 
   if (tid == 0) {
     mbar_init(&bar1, 1);
@@ -108,187 +114,231 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_fwd_kernel(const float* __re
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, L::TMEM_COLS);
-  // ---- stage parameters
+  // ---- stage parameters (once per CTA)
   stage(par + L::P_CW, p.conv_weight, E * 4);
   stage(par + L::P_CB, p.conv_bias, E);
   stage(par + L::P_WQ, p.q_weight, E * 4);
   stage(par + L::P_WK, p.k_weight, E * 4);
   stage(par + L::P_WV, p.v_weight, E * 4);
   stage(par + L::P_NW, p.norm_weight, C);
+  if (tid < 8) par[L::P_GB + tid] = tid < 4 ? __ldg(p.igate_bias + tid) : __ldg(p.fgate_bias + tid - 4);
   stage_weight_tile(p.proj_up_weight, 2 * E, C, 2 * E, smem + L::WHI, smem + L::WLO);
-  // gate weights as a [16][NQ] tile in the padded q|k|v column order: column (part*4 + head)*DHP + d
-  for (int gi = tid; gi < 16 * (NQ / 8); gi += blockDim.x) {
-    const int hh = gi % 16, cg = gi / 16;
+  // gate weights as an [8][NQ] tile in the padded q|k|v column order: column (part*4 + head)*DHP + d
+  for (int gi = tid; gi < 8 * (NQ / 8); gi += blockDim.x) {
+    const int hh = gi % 8, cg = gi / 8;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int j = cg * 8 + i, part = j / (4 * DHP), hd = (j / DHP) % 4, d = j % DHP;
       const float* W = hh < 4 ? p.igate_weight + hh * 3 * E : p.fgate_weight + (hh - 4) * 3 * E;
-      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + hd * DH + d) : 0.f;
+      v[i] = d < DH ? __ldg(W + part * E + hd * DH + d) : 0.f;
     }
     uint4 h, l;
     split8_hilo(v, h, l);
-    *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
-    *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
+    *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(8, hh, cg)) = h;
+    *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(8, hh, cg)) = l;
   }
-  // ---- load the token, LayerNorm, stage it as a bf16 hi/lo row (head group 0); conv halo tokens (first 3 threads of group 1)
-  const int tau = ch * kTok + tok;
-  const bool valid = tau < g.S;
-  const int n = g.reverse ? g.S - 1 - tau : tau;
-  const bool is_halo = head == 1 && tok < 3;
-  const int htau = ch * kTok - 3 + tok;
-  const bool hvalid = is_halo && htau >= 0;
-  float xin[C];
-  if (head == 0) {
-#pragma unroll
-    for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
-  } else if (is_halo) {
-    const int hn_ = g.reverse ? g.S - 1 - htau : htau;
-#pragma unroll
-    for (int c = 0; c < C; ++c) xin[c] = hvalid ? __ldg(x + b * g.xsb + hn_ * g.xsn + c * g.xsc) : 0.f;
-  }
-  __syncthreads();   // parameters (norm weight) staged
-  if (head == 0) {
-    float xn[C];
-    layernorm_token<C>(xin, par + L::P_NW, xn, nullptr);
-#pragma unroll
-    for (int cg = 0; cg < C / 8; ++cg) {
-      float v8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v8[i] = valid ? xn[cg * 8 + i] : 0.f;
-      uint4 h, l;
-      split8_hilo(v8, h, l);
-      *reinterpret_cast<uint4*>(smem + L::XHI + tile_off16(kTok, tok, cg)) = h;
-      *reinterpret_cast<uint4*>(smem + L::XLO + tile_off16(kTok, tok, cg)) = l;
-    }
-  } else if (is_halo) {
-    float hn2[C];
-    layernorm_token<C>(xin, par + L::P_NW, hn2, nullptr);
-#pragma unroll
-    for (int c = 0; c < C; ++c) par[L::P_HX + tok * C + c] = hvalid ? hn2[c] : 0.f;
-  }
-  fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();   // parameters staged, TMEM allocated
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
-    // D[tok][o] = sum_c xn[tok][c] W_up[o][c]
-    umma_gemm_hilo(tmem, smem_u32(smem + L::XHI), smem_u32(smem + L::XLO), kTok * 16, 128, smem_u32(smem + L::WHI),
-                   smem_u32(smem + L::WLO), 2 * E * 16, 128, umma_idesc(128, 2 * E, false, false), C);
-    umma_commit(&bar1);
-  }
-  // ---- conv halo (3 previous tokens): x_mlstm only, spread over the CTA while the MMA runs
-  for (int idx = tid; idx < 3 * E; idx += blockDim.x) {
-    const int row = idx / E, e = idx % E;
-    const float* w = p.proj_up_weight + static_cast<size_t>(e) * C;
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; c += 4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
-      const float* hxn = par + L::P_HX + row * C + c;
-      acc += hxn[0] * w4.x + hxn[1] * w4.y + hxn[2] * w4.z + hxn[3] * w4.w;
-    }
-    xm_s[row * L::XM_LD + e] = acc;
-  }
-  mbar_wait(&bar1, 0);
-  tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;   // token-minor (B, nc, E, 128)
-  // this head's DH channels of x_mlstm (columns head*DH..) and of z (columns E + head*DH..)
-#pragma unroll
-  for (int c0 = 0; c0 < DH; c0 += 8) {
-    float v[8];
-    tmem_ld8(tmem + lane_base + head * DH + c0, v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      xm_s[(tok + 3) * L::XM_LD + head * DH + c0 + i] = v[i];
-      xm_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
-    }
-    tmem_ld8(tmem + lane_base + E + head * DH + c0, v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) z_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
-  }
-  tc_fence_before();
-  __syncthreads();   // x_mlstm of all tokens visible; proj_up operands dead -> QKV tile may overwrite them
-  // ---- conv + SiLU + block-diagonal q,k,v, 8 channels at a time
-  const float* xm0 = xm_s + tok * L::XM_LD;   // rows tok..tok+3 <-> tokens tau-3..tau
   const uint4 zero = make_uint4(0, 0, 0, 0);
+  constexpr int CP = (C / 4) < 8 ? 8 : (C / 4), NPART = C / CP;   // channels per thread / head groups taking part in the LayerNorm
+  const bool ln_on = head < NPART;
+  const int c0 = head * CP;
+  float* ln1 = par + L::P_LN;
+  float* ln2 = ln1 + 4 * kTok;
+  auto load_x = [&](int tile, float* xin) {
+    const int b = tile / g.nc, tau = (tile % g.nc) * kTok + tok;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
+#pragma unroll
+    for (int i = 0; i < CP; ++i) xin[i] = (tau < g.S && ln_on) ? __ldg(x + b * g.xsb + n * g.xsn + (c0 + i) * g.xsc) : 0.f;
+  };
+  float xin[CP];
+  load_x(blockIdx.x, xin);
+
+  int it = 0;
 #pragma unroll 1
-  for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
-    float a8[8], xm8[8], q8[8], k8[8], v8[8];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = tile / g.nc, ch = tile % g.nc;
+    // ---- LayerNorm, token rows staged as bf16 hi/lo; conv halo tokens (first 3 threads of group 1)
+    const int tau = ch * kTok + tok;
+    const bool valid = tau < g.S;
+    const int n = g.reverse ? g.S - 1 - tau : tau;
+    {
+      // LayerNorm of the CTA's tokens: every head group owns CP channels of its token, statistics go through shared memory
+      // (mean first, then the centred second moment, as F.layer_norm does)
+      float s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = e8 + j;
-      const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
-      const float conv = par[L::P_CB + e] + w.x * xm0[e] + w.y * xm0[L::XM_LD + e] + w.z * xm0[2 * L::XM_LD + e] +
-                         w.w * xm0[3 * L::XM_LD + e];
-      a8[j] = silu(conv);
-      xm8[j] = xm0[3 * L::XM_LD + e];
-      act_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? a8[j] : 0.f;
+      for (int i = 0; i < CP; ++i) s1 += xin[i];
+      ln1[head * kTok + tok] = ln_on ? s1 : 0.f;
+      __syncthreads();
+      const float mean = (ln1[tok] + ln1[kTok + tok] + ln1[2 * kTok + tok] + ln1[3 * kTok + tok]) * (1.f / C);
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CP; ++i) s2 += (xin[i] - mean) * (xin[i] - mean);
+      ln2[head * kTok + tok] = ln_on ? s2 : 0.f;
+      __syncthreads();
+      const float rstd = rsqrtf((ln2[tok] + ln2[kTok + tok] + ln2[2 * kTok + tok] + ln2[3 * kTok + tok]) * (1.f / C) + 1e-5f);
+      if (ln_on) {
+#pragma unroll
+        for (int cg = 0; cg < CP / 8; ++cg) {
+          float v8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            v8[i] = valid ? (xin[cg * 8 + i] - mean) * rstd * (1.f + par[L::P_NW + c0 + cg * 8 + i]) : 0.f;
+          uint4 h, l;
+          split8_hilo(v8, h, l);
+          *reinterpret_cast<uint4*>(smem + L::XHI + tile_off16(kTok, tok, c0 / 8 + cg)) = h;
+          *reinterpret_cast<uint4*>(smem + L::XLO + tile_off16(kTok, tok, c0 / 8 + cg)) = l;
+        }
+      }
+      if (tile + static_cast<int>(gridDim.x) < ntiles) load_x(tile + gridDim.x, xin);   // next tile's tokens
     }
+    if (head == 2 && tok < 96) {
+      // conv halo: the 3 tokens in front of the chunk, one warp per token, lane = channel (LayerNorm through shuffles)
+      const int w = tok >> 5, lane = tok & 31;
+      const int htau = ch * kTok - 3 + w;
+      const int hn_ = g.reverse ? g.S - 1 - htau : htau;
+      float hv[(C + 31) / 32], sum = 0.f;
 #pragma unroll
-    for (int blk = 0; blk < 2; ++blk) {
-      const int wb = ((e8 >> 2) + blk) * 16;   // (block, out, in) 4x4
+      for (int i = 0; i < (C + 31) / 32; ++i) {
+        const int c = lane + 32 * i;
+        hv[i] = (htau >= 0 && c < C) ? __ldg(x + b * g.xsb + hn_ * g.xsn + c * g.xsc) : 0.f;
+        sum += hv[i];
+      }
+      const float mean = warp_sum_f(sum) * (1.f / C);
+      float sq = 0.f;
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const float4 wq = *reinterpret_cast<const float4*>(par + L::P_WQ + wb + o * 4);
-        const float4 wk = *reinterpret_cast<const float4*>(par + L::P_WK + wb + o * 4);
-        const float4 wv = *reinterpret_cast<const float4*>(par + L::P_WV + wb + o * 4);
-        const float* a = a8 + blk * 4;
-        const float* xv = xm8 + blk * 4;
-        q8[blk * 4 + o] = wq.x * a[0] + wq.y * a[1] + wq.z * a[2] + wq.w * a[3];
-        k8[blk * 4 + o] = wk.x * a[0] + wk.y * a[1] + wk.z * a[2] + wk.w * a[3];
-        v8[blk * 4 + o] = wv.x * xv[0] + wv.y * xv[1] + wv.z * xv[2] + wv.w * xv[3];
+      for (int i = 0; i < (C + 31) / 32; ++i) sq += (lane + 32 * i < C) ? (hv[i] - mean) * (hv[i] - mean) : 0.f;
+      const float rstd = rsqrtf(warp_sum_f(sq) * (1.f / C) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < (C + 31) / 32; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) par[L::P_HX + w * C + c] = htau >= 0 ? (hv[i] - mean) * rstd * (1.f + par[L::P_NW + c]) : 0.f;
       }
     }
-    const int d0 = e8 % DH;
-    const uint4 uq = valid ? pack8_bf16(q8) : zero, uk = valid ? pack8_bf16(k8) : zero, uv = valid ? pack8_bf16(v8) : zero;
-    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((0 * 4 + head) * DHP + d0) / 8)) = uq;
-    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((1 * 4 + head) * DHP + d0) / 8)) = uk;
-    *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((2 * 4 + head) * DHP + d0) / 8)) = uv;
-    if (DHP > DH) {   // DH = 8 padded to 16: zero the second column group of every head
-#pragma unroll
-      for (int part = 0; part < 3; ++part)
-        *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((part * 4 + head) * DHP + 8) / 8)) = zero;
-    }
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (tid == 0) {
-    // gates[tok][hh] = sum_j qkv[tok][j] Wg[hh][j]   (bf16 q,k,v exactly as the cell sees them; hi/lo weights)
-    const uint32_t aq = smem_u32(smem + L::QKV);
-    umma_gemm(tmem + 2 * E, aq, kTok * 16, 128, smem_u32(smem + L::WGHI), 16 * 16, 128, umma_idesc(128, 16, false, false), NQ, false);
-    umma_gemm(tmem + 2 * E, aq, kTok * 16, 128, smem_u32(smem + L::WGLO), 16 * 16, 128, umma_idesc(128, 16, false, false), NQ, true);
-    umma_commit(&bar2);
-    // q/k/v head tiles are contiguous column blocks of the staged tile: bulk-store them to the cell's operand tiles
-    constexpr uint32_t HT = kTok * DHP * 2;
-#pragma unroll 1
-    for (int hd = 0; hd < 4; ++hd) {
-      const size_t tile = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
-      bulk_s2g(q_tiles + tile * HT, smem + L::QKV + (0 * 4 + hd) * HT, HT);
-      bulk_s2g(k_tiles + tile * HT, smem + L::QKV + (1 * 4 + hd) * HT, HT);
-      bulk_s2g(v_tiles + tile * HT, smem + L::QKV + (2 * 4 + hd) * HT, HT);
-    }
-    bulk_commit();
-  }
-  if (head == 0) {
-    mbar_wait(&bar2, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
     tc_fence_after();
-    float gt[16];
-    tmem_ld16(tmem + lane_base + 2 * E, gt);
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
-      igp[o] = valid ? gt[h] + __ldg(p.igate_bias + h) : -1e30f;
-      fgp[o] = valid ? gt[4 + h] + __ldg(p.fgate_bias + h) : 1e30f;
+    if (tid == 0) {
+      // D[tok][o] = sum_c xn[tok][c] W_up[o][c]
+      umma_gemm_hilo(tmem, smem_u32(smem + L::XHI), smem_u32(smem + L::XLO), kTok * 16, 128, smem_u32(smem + L::WHI),
+                     smem_u32(smem + L::WLO), 2 * E * 16, 128, umma_idesc(128, 2 * E, false, false), C);
+      umma_commit(&bar1);
     }
+    // ---- conv halo (3 previous tokens): x_mlstm only, spread over the CTA while the MMA runs
+    for (int idx = tid; idx < 3 * E; idx += blockDim.x) {
+      const int row = idx / E, e = idx % E;
+      const float* w = p.proj_up_weight + static_cast<size_t>(e) * C;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; c += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+        const float* hxn = par + L::P_HX + row * C + c;
+        acc += hxn[0] * w4.x + hxn[1] * w4.y + hxn[2] * w4.z + hxn[3] * w4.w;
+      }
+      xm_s[row * L::XM_LD + e] = acc;
+    }
+    mbar_wait(&bar1, it & 1);
+    tc_fence_after();
+    const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;   // token-minor (B, nc, E, 128)
+    // this head's DH channels of x_mlstm (columns head*DH..) and of z (columns E + head*DH..)
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem + lane_base + head * DH + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xm_s[(tok + 3) * L::XM_LD + head * DH + c0 + i] = v[i];
+        xm_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
+      }
+      tmem_ld8(tmem + lane_base + E + head * DH + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();   // x_mlstm of all tokens visible; the token rows are dead -> the QKV tile may overwrite them
+    // ---- conv + SiLU + block-diagonal q,k,v, 8 channels at a time
+    const float* xm0 = xm_s + tok * L::XM_LD;   // rows tok..tok+3 <-> tokens tau-3..tau
+#pragma unroll 1
+    for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
+      float a8[8], xm8[8], q8[8], k8[8], v8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e8 + j;
+        const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
+        const float conv = par[L::P_CB + e] + w.x * xm0[e] + w.y * xm0[L::XM_LD + e] + w.z * xm0[2 * L::XM_LD + e] +
+                           w.w * xm0[3 * L::XM_LD + e];
+        a8[j] = silu(conv);
+        xm8[j] = xm0[3 * L::XM_LD + e];
+        act_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? a8[j] : 0.f;
+      }
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        const int wb = ((e8 >> 2) + blk) * 16;   // (block, out, in) 4x4
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float4 wq = *reinterpret_cast<const float4*>(par + L::P_WQ + wb + o * 4);
+          const float4 wk = *reinterpret_cast<const float4*>(par + L::P_WK + wb + o * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(par + L::P_WV + wb + o * 4);
+          const float* a = a8 + blk * 4;
+          const float* xv = xm8 + blk * 4;
+          q8[blk * 4 + o] = wq.x * a[0] + wq.y * a[1] + wq.z * a[2] + wq.w * a[3];
+          k8[blk * 4 + o] = wk.x * a[0] + wk.y * a[1] + wk.z * a[2] + wk.w * a[3];
+          v8[blk * 4 + o] = wv.x * xv[0] + wv.y * xv[1] + wv.z * xv[2] + wv.w * xv[3];
+        }
+      }
+      const int d0 = e8 % DH;
+      const uint4 uq = valid ? pack8_bf16(q8) : zero, uk = valid ? pack8_bf16(k8) : zero, uv = valid ? pack8_bf16(v8) : zero;
+      *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((0 * 4 + head) * DHP + d0) / 8)) = uq;
+      *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((1 * 4 + head) * DHP + d0) / 8)) = uk;
+      *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((2 * 4 + head) * DHP + d0) / 8)) = uv;
+      if (DHP > DH) {   // DH = 8 padded to 16: zero the second column group of every head
+#pragma unroll
+        for (int part = 0; part < 3; ++part)
+          *reinterpret_cast<uint4*>(smem + L::QKV + tile_off16(kTok, tok, ((part * 4 + head) * DHP + 8) / 8)) = zero;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      // gates[tok][hh] = sum_j qkv[tok][j] Wg[hh][j]   (bf16 q,k,v exactly as the cell sees them; hi/lo weights)
+      const uint32_t aq = smem_u32(smem + L::QKV);
+      umma_gemm(tmem + 2 * E, aq, kTok * 16, 128, smem_u32(smem + L::WGHI), 8 * 16, 128, umma_idesc(128, 16, false, false), NQ, false);
+      umma_gemm(tmem + 2 * E, aq, kTok * 16, 128, smem_u32(smem + L::WGLO), 8 * 16, 128, umma_idesc(128, 16, false, false), NQ, true);
+      umma_commit(&bar2);
+      // q/k/v head tiles are contiguous column blocks of the staged tile: bulk-store them to the cell's operand tiles
+      constexpr uint32_t HT = kTok * DHP * 2;
+#pragma unroll 1
+      for (int hd = 0; hd < 4; ++hd) {
+        const size_t t2 = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
+        bulk_s2g(q_tiles + t2 * HT, smem + L::QKV + (0 * 4 + hd) * HT, HT);
+        bulk_s2g(k_tiles + t2 * HT, smem + L::QKV + (1 * 4 + hd) * HT, HT);
+        bulk_s2g(v_tiles + t2 * HT, smem + L::QKV + (2 * 4 + hd) * HT, HT);
+      }
+      bulk_commit();
+    }
+    mbar_wait(&bar2, it & 1);     // everybody: the gate product reads the q|k|v tile that the next iteration overwrites
+    tc_fence_after();
+    if (head == 0) {
+      float gt[8];
+      tmem_ld8(tmem + lane_base + 2 * E, gt);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
+        igp[o] = valid ? gt[h] + par[L::P_GB + h] : -1e30f;
+        fgp[o] = valid ? gt[4 + h] + par[L::P_GB + 4 + h] : 1e30f;
+      }
+    }
+    if (tid == 0) bulk_wait_read();
+    tc_fence_before();
+    __syncthreads();
   }
-  if (tid == 0) bulk_wait_read();
-  tc_fence_before();
-  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
@@ -299,7 +349,10 @@ static int launch_pre_fwd(const float* x, const xhved_vil_params* p, const VilGe
   cudaError_t e = cudaFuncSetAttribute(vil_pre_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_PRE_FWD, st);
-  vil_pre_fwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z, xm);
+  const int ntiles = g.B * g.nc;
+  const int grid = PreTC<C>::PERSIST ? persistent_grid(ntiles, 2) : ntiles;
+  vil_pre_fwd_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z, xm,
+                                                      ntiles);
   return (int)cudaGetLastError();
 }
 
