@@ -759,13 +759,15 @@ template <int C>
 struct PreBwdATC {
   static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
   static constexpr uint32_t DG_BYTES = kTok * 16 * 2, WG_BYTES = 16 * NQ * 2, QKV_BYTES = kTok * NQ * 2, T_BYTES = kTok * E * 2;
-  static constexpr uint32_t DGHI = 0, DGLO = DG_BYTES, WGHI = 2 * DG_BYTES, WGLO = WGHI + WG_BYTES;   // inside a 32 KB window
-  // The q|k|v tile is dead once the first MMA group has completed; the weight-gradient operands written by the main loop
-  // reuse its space.  GQK: [128][2E] (32 KB window); GV: 32 KB window covering ACT, XMT.
-  static constexpr uint32_t QKV = 32768, GQK = QKV;
-  static constexpr uint32_t GV = GQK + 32768, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;
-  static constexpr uint32_t END1 = QKV + QKV_BYTES, END2 = XMT + T_BYTES, END3 = GV + 32768;
-  static constexpr uint32_t PAR = END1 > END2 ? (END1 > END3 ? END1 : END3) : (END2 > END3 ? END2 : END3);
+  // [dig|dfg] is read as a 128-row MN-major A operand (32 KB window that runs on over the tiles behind it; rows >= 16 of
+  // that product are never read)
+  static constexpr uint32_t DGHI = 0, DGLO = DG_BYTES, WGHI = 2 * DG_BYTES, WGLO = WGHI + WG_BYTES;
+  // The q|k|v tile has its own space so that the NEXT tile's q|k|v can stream in while the main loop of this tile runs.
+  // GQK: [128][2E]; GV: 32 KB window covering ACT, XMT.
+  static constexpr uint32_t QKV = WGLO + WG_BYTES, GQK = QKV + QKV_BYTES;
+  static constexpr uint32_t GV = GQK + kTok * 2 * E * 2, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;
+  static constexpr uint32_t END2 = XMT + T_BYTES, END3 = GV + 32768;
+  static constexpr uint32_t PAR = END2 > END3 ? END2 : END3;
   static constexpr int P_CW = 0, P_CB = E * 4, P_WQ = P_CB + E, P_WK = P_WQ + E * 4, P_WV = P_WK + E * 4, A_CW = P_WV + E * 4,
                        A_CB = A_CW + E * 4, A_GB = A_CB + E, P_N = A_GB + 8;
   // token-minor input blocks staged by bulk async copies: x_mlstm, d_act (E x 128 fp32 each) + x_mlstm of the 3 tokens
@@ -774,60 +776,61 @@ struct PreBwdATC {
   static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + BLK, IN_HX = IN_DA + BLK;
   static constexpr uint32_t TOTAL = IN_HX + E * 4 * 4;
   static constexpr uint32_t T_GQ = 0, T_DWG = NQ, T_DWQK = 2 * NQ, T_DWV = 2 * NQ + E;
-  static_assert(2 * NQ + 2 * E <= 512 && WGLO + WG_BYTES <= 32768 && 2 * E <= 128, "tensor-core pre-backward A supports C <= 32");
+  static_assert(2 * NQ + 2 * E <= 512 && 2 * E <= 128 && TOTAL <= 227 * 1024, "tensor-core pre-backward A supports C <= 32");
 };
 
 template <int C>
-__global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
-                                                                     const unsigned char* __restrict__ q_tiles,
-                                                                     const unsigned char* __restrict__ k_tiles,
-                                                                     const unsigned char* __restrict__ v_tiles, const float* __restrict__ dq,
-                                                                     const float* __restrict__ dk, const float* __restrict__ dv,
-                                                                     const float* __restrict__ dig, const float* __restrict__ dfg,
-                                                                     const float* __restrict__ d_act, float* __restrict__ dconv_out,
-                                                                     float* __restrict__ dxmv_out, xhved_vil_grads gr_base) {
+__global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
+                                                                        const unsigned char* __restrict__ q_tiles,
+                                                                        const unsigned char* __restrict__ k_tiles,
+                                                                        const unsigned char* __restrict__ v_tiles, const float* __restrict__ dq,
+                                                                        const float* __restrict__ dk, const float* __restrict__ dv,
+                                                                        const float* __restrict__ dig, const float* __restrict__ dfg,
+                                                                        const float* __restrict__ d_act, float* __restrict__ dconv_out,
+                                                                        float* __restrict__ dxmv_out, xhved_vil_grads gr_base, int ntiles) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
-  // 512 threads: thread = (token, head); the four head groups of a token share the TMEM lane of that token
+  // 512 threads: thread = (token, head); the four head groups of a token share the TMEM lane of that token.
+  // Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  All parameter gradients accumulate over the CTA's
+  // tiles -- the three weight-gradient UMMAs keep adding into their TMEM columns, conv / bias sums live in shared memory --
+  // and are flushed to global once.  The next tile's inputs stream in (bulk copies) as soon as their buffers are free.
   using L = PreBwdATC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
   constexpr uint32_t HT = kTok * DHP * 2;
   extern __shared__ __align__(128) unsigned char smem[];
   float* par = reinterpret_cast<float*>(smem + L::PAR);
-  __shared__ __align__(8) uint64_t bar_load, bar1, bar2;
+  __shared__ __align__(8) uint64_t bar_qkv, bar_in, bar1, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tok = tid & (kTok - 1), head = tid >> 7;
-  const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
+
+  auto issue_qkv = [&](int tile) {
+    const int b = tile / g.nc, ch = tile % g.nc;
+    mbar_expect_tx(&bar_qkv, 12 * HT);
+#pragma unroll 1
+    for (int hd = 0; hd < 4; ++hd) {
+      const size_t t2 = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
+      bulk_g2s(smem + L::QKV + (0 * 4 + hd) * HT, q_tiles + t2 * HT, HT, &bar_qkv);
+      bulk_g2s(smem + L::QKV + (1 * 4 + hd) * HT, k_tiles + t2 * HT, HT, &bar_qkv);
+      bulk_g2s(smem + L::QKV + (2 * 4 + hd) * HT, v_tiles + t2 * HT, HT, &bar_qkv);
+    }
+  };
+  auto issue_in = [&](int tile) {
+    mbar_expect_tx(&bar_in, 2 * L::BLK);
+    bulk_g2s(smem + L::IN_XM, xm + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_in);
+    bulk_g2s(smem + L::IN_DA, d_act + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_in);
+  };
+
   if (tid == 0) {
-    mbar_init(&bar_load, 1);
+    mbar_init(&bar_qkv, 1);
+    mbar_init(&bar_in, 1);
     mbar_init(&bar1, 1);
     mbar_init(&bar2, 1);
     mbar_fence_init();
+    issue_qkv(blockIdx.x);
+    issue_in(blockIdx.x);
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  __syncthreads();
-  const size_t tm_chunk = (static_cast<size_t>(b) * g.nc + ch) * E * kTok;
-  if (tid == 0) {
-    mbar_expect_tx(&bar_load, 12 * HT + 2 * L::BLK);
-#pragma unroll 1
-    for (int hd = 0; hd < 4; ++hd) {
-      const size_t tile = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
-      bulk_g2s(smem + L::QKV + (0 * 4 + hd) * HT, q_tiles + tile * HT, HT, &bar_load);
-      bulk_g2s(smem + L::QKV + (1 * 4 + hd) * HT, k_tiles + tile * HT, HT, &bar_load);
-      bulk_g2s(smem + L::QKV + (2 * 4 + hd) * HT, v_tiles + tile * HT, HT, &bar_load);
-    }
-    bulk_g2s(smem + L::IN_XM, xm + tm_chunk, L::BLK, &bar_load);
-    bulk_g2s(smem + L::IN_DA, d_act + tm_chunk, L::BLK, &bar_load);
-  }
-  {
-    // x_mlstm of the 3 tokens in front of this chunk (zeros in front of the sequence)
-    float* hx = reinterpret_cast<float*>(smem + L::IN_HX);
-    for (int i = tid; i < E * 4; i += blockDim.x) {
-      const int e = i >> 2, k = i & 3;
-      hx[i] = (k < 3 && ch > 0) ? __ldg(xm + (static_cast<size_t>(b) * g.nc + ch - 1) * E * kTok + static_cast<size_t>(e) * kTok + kTok - 3 + k) : 0.f;
-    }
-  }
   stage(par + L::P_CW, p.conv_weight, E * 4);
   stage(par + L::P_CB, p.conv_bias, E);
   stage(par + L::P_WQ, p.q_weight, E * 4);
@@ -848,142 +851,173 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
     *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
     *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
   }
-  const int tau = ch * kTok + tok;
-  const bool valid = tau < g.S;
-  float dg[8];
-  if (head == 0) {
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
-      dg[h] = valid ? __ldg(dig + o) : 0.f;
-      dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
-    }
-    uint4 hi, lo;
-    split8_hilo(dg, hi, lo);
-    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 0)) = hi;
-    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 0)) = lo;
-    *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
-  }
-  fence_proxy_async();
-  mbar_wait(&bar_load, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (head == 0) warp_acc_vec<8>(par + L::A_GB, dg);       // gate bias gradients (accumulators are zeroed by now)
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
-    // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
-    umma_gemm_hilo(tmem + L::T_GQ, smem_u32(smem + L::DGHI), smem_u32(smem + L::DGLO), kTok * 16, 128, smem_u32(smem + L::WGHI),
-                   smem_u32(smem + L::WGLO), 128, 16 * 16, umma_idesc(128, NQ, false, true), 16);
-    // d Wg[hh][j] = sum_tok [dig|dfg][tok][hh] qkv[tok][j]               (weight-gradient GEMM: plain bf16 operands)
-    umma_gemm(tmem + L::T_DWG, smem_u32(smem + L::DGHI), 128, kTok * 16, smem_u32(smem + L::QKV), 128, kTok * 16,
-              umma_idesc(128, NQ, true, true), kTok, false);
-    umma_commit(&bar1);
-  }
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
   float* acc = par;
-  bool mma1_pending = true;
+
+  int it = 0;
 #pragma unroll 1
-  for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
-    const int d0 = e8 % DH;
-    float a8[8], xm8[8], cv8[8], xr[4][8];
-    const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM);
-    const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_HX);
-    const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k (padding rows hold zeros)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
-    }
-    float gq[8], gk[8], gv[8], dsk[8];
-    const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tok) * DHP + d0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int b = tile / g.nc, ch = tile % g.nc;
+    const int nxt = tile + gridDim.x;
     {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(dq + row)), c = __ldg(reinterpret_cast<const float4*>(dq + row + 4));
-      gq[0] = a.x, gq[1] = a.y, gq[2] = a.z, gq[3] = a.w, gq[4] = c.x, gq[5] = c.y, gq[6] = c.z, gq[7] = c.w;
-      const float4 a2 = __ldg(reinterpret_cast<const float4*>(dk + row)), c2 = __ldg(reinterpret_cast<const float4*>(dk + row + 4));
-      gk[0] = a2.x, gk[1] = a2.y, gk[2] = a2.z, gk[3] = a2.w, gk[4] = c2.x, gk[5] = c2.y, gk[6] = c2.z, gk[7] = c2.w;
-      const float4 a3 = __ldg(reinterpret_cast<const float4*>(dv + row)), c3 = __ldg(reinterpret_cast<const float4*>(dv + row + 4));
-      gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = e8 + j;
-      const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
-      cv8[j] = par[L::P_CB + e] + w.x * xr[0][j] + w.y * xr[1][j] + w.z * xr[2][j] + w.w * xr[3][j];
-      a8[j] = silu(cv8[j]);
-      xm8[j] = xr[3][j];
-    }
-    // everything above is independent of the first MMA group and overlaps it; the gate-path contribution is read from TMEM
-    if (mma1_pending) {
-      mbar_wait(&bar1, 0);
-      tc_fence_after();
-      mma1_pending = false;
-    }
-    float t8[8];
-    tmem_ld8(tmem + lane_base + L::T_GQ + (0 * 4 + head) * DHP + d0, t8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gq[j] = valid ? gq[j] + t8[j] : 0.f;
-    tmem_ld8(tmem + lane_base + L::T_GQ + (1 * 4 + head) * DHP + d0, t8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gk[j] = valid ? gk[j] + t8[j] : 0.f;
-    tmem_ld8(tmem + lane_base + L::T_GQ + (2 * 4 + head) * DHP + d0, t8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gv[j] = valid ? gv[j] + t8[j] : 0.f;
-    float da8[8], dxv8[8];
-#pragma unroll
-    for (int blk = 0; blk < 2; ++blk) {
-      const int wb = ((e8 >> 2) + blk) * 16;
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        float sa = 0.f, sv = 0.f;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          sa += par[L::P_WQ + wb + o * 4 + d] * gq[blk * 4 + o] + par[L::P_WK + wb + o * 4 + d] * gk[blk * 4 + o];
-          sv += par[L::P_WV + wb + o * 4 + d] * gv[blk * 4 + o];
-        }
-        da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
+      // x_mlstm of the 3 tokens in front of this chunk (zeros in front of the sequence)
+      float* hx = reinterpret_cast<float*>(smem + L::IN_HX);
+      for (int i = tid; i < E * 4; i += blockDim.x) {
+        const int e = i >> 2, k = i & 3;
+        hx[i] = (k < 3 && ch > 0) ? __ldg(xm + static_cast<size_t>(tile - 1) * E * kTok + static_cast<size_t>(e) * kTok + kTok - 3 + k) : 0.f;
       }
     }
-    float dc8[8], prod[32];
+    const int tau = ch * kTok + tok;
+    const bool valid = tau < g.S;
+    float dg[8];
+    if (head == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = e8 + j;
-      dc8[j] = valid ? (da8[j] + dsk[j]) * dsilu(cv8[j]) : 0.f;
-      dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc8[j];
-      dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? dxv8[j] : 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) prod[j * 4 + k] = dc8[j] * xr[k][j];
+      for (int h = 0; h < 4; ++h) {
+        const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
+        dg[h] = valid ? __ldg(dig + o) : 0.f;
+        dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
+      }
+      uint4 hi, lo;
+      split8_hilo(dg, hi, lo);
+      *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 0)) = hi;
+      *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 0)) = lo;
+      *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
+      warp_acc_vec<8>(par + L::A_GB, dg);       // gate bias gradients
     }
-    warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
-    warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
-    // operands of the block-diagonal weight-gradient GEMMs (bf16)
-    if (!valid) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
+    fence_proxy_async();
+    mbar_wait(&bar_qkv, it & 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
+      umma_gemm_hilo(tmem + L::T_GQ, smem_u32(smem + L::DGHI), smem_u32(smem + L::DGLO), kTok * 16, 128, smem_u32(smem + L::WGHI),
+                     smem_u32(smem + L::WGLO), 128, 16 * 16, umma_idesc(128, NQ, false, true), 16);
+      // d Wg[hh][j] += sum_tok [dig|dfg][tok][hh] qkv[tok][j]              (weight-gradient GEMM: plain bf16 operands)
+      umma_gemm(tmem + L::T_DWG, smem_u32(smem + L::DGHI), 128, kTok * 16, smem_u32(smem + L::QKV), 128, kTok * 16,
+                umma_idesc(128, NQ, true, true), kTok, it > 0);
+      umma_commit(&bar1);
     }
-    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gq);
-    *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, (E + e8) / 8)) = pack8_bf16(gk);
-    *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gv);
-    *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(a8);
-    *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(xm8);
+    mbar_wait(&bar_in, it & 1);
+    if (it > 0) {      // the previous tile's weight-gradient products still read the operand tiles this loop rewrites
+      mbar_wait(&bar2, (it - 1) & 1);
+      tc_fence_after();
+    }
+    const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;
+    bool mma1_pending = true;
+#pragma unroll 1
+    for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
+      const int d0 = e8 % DH;
+      float a8[8], xm8[8], cv8[8], xr[4][8];
+      const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM);
+      const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_HX);
+      const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k (padding rows hold zeros)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
+      }
+      float gq[8], gk[8], gv[8], dsk[8];
+      const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tok) * DHP + d0;
+      {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(dq + row)), c = __ldg(reinterpret_cast<const float4*>(dq + row + 4));
+        gq[0] = a.x, gq[1] = a.y, gq[2] = a.z, gq[3] = a.w, gq[4] = c.x, gq[5] = c.y, gq[6] = c.z, gq[7] = c.w;
+        const float4 a2 = __ldg(reinterpret_cast<const float4*>(dk + row)), c2 = __ldg(reinterpret_cast<const float4*>(dk + row + 4));
+        gk[0] = a2.x, gk[1] = a2.y, gk[2] = a2.z, gk[3] = a2.w, gk[4] = c2.x, gk[5] = c2.y, gk[6] = c2.z, gk[7] = c2.w;
+        const float4 a3 = __ldg(reinterpret_cast<const float4*>(dv + row)), c3 = __ldg(reinterpret_cast<const float4*>(dv + row + 4));
+        gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e8 + j;
+        const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
+        cv8[j] = par[L::P_CB + e] + w.x * xr[0][j] + w.y * xr[1][j] + w.z * xr[2][j] + w.w * xr[3][j];
+        xm8[j] = xr[3][j];
+      }
+      // everything above is independent of the first MMA group and overlaps it; the gate-path contribution is read from TMEM
+      if (mma1_pending) {
+        mbar_wait(&bar1, it & 1);
+        tc_fence_after();
+        mma1_pending = false;
+        if (tid == 0 && nxt < ntiles) issue_qkv(nxt);     // the q|k|v tile has been consumed: stream in the next one
+      }
+      float t8[8];
+      tmem_ld8(tmem + lane_base + L::T_GQ + (0 * 4 + head) * DHP + d0, t8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gq[j] = valid ? gq[j] + t8[j] : 0.f;
+      tmem_ld8(tmem + lane_base + L::T_GQ + (1 * 4 + head) * DHP + d0, t8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gk[j] = valid ? gk[j] + t8[j] : 0.f;
+      tmem_ld8(tmem + lane_base + L::T_GQ + (2 * 4 + head) * DHP + d0, t8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = valid ? gv[j] + t8[j] : 0.f;
+      float da8[8], dxv8[8];
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        const int wb = ((e8 >> 2) + blk) * 16;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          float sa = 0.f, sv = 0.f;
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            sa += par[L::P_WQ + wb + o * 4 + d] * gq[blk * 4 + o] + par[L::P_WK + wb + o * 4 + d] * gk[blk * 4 + o];
+            sv += par[L::P_WV + wb + o * 4 + d] * gv[blk * 4 + o];
+          }
+          da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
+        }
+      }
+      float dc8[8], prod[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e8 + j;
+        float ds;
+        silu_both(cv8[j], a8[j], ds);
+        dc8[j] = valid ? (da8[j] + dsk[j]) * ds : 0.f;
+        dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc8[j];
+        dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? dxv8[j] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) prod[j * 4 + k] = dc8[j] * xr[k][j];
+      }
+      warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
+      warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
+      // operands of the block-diagonal weight-gradient GEMMs (bf16)
+      if (!valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gq);
+      *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, (E + e8) / 8)) = pack8_bf16(gk);
+      *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gv);
+      *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(a8);
+      *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(xm8);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      // d[q_proj|k_proj] as a dense (2E x E) product g_{q|k}^T act; only its 4x4 diagonal blocks are read back
+      umma_gemm(tmem + L::T_DWQK, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
+                umma_idesc(128, E, true, true), kTok, it > 0);
+      umma_gemm(tmem + L::T_DWV, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16,
+                umma_idesc(128, E, true, true), kTok, it > 0);
+      umma_commit(&bar2);
+      if (nxt < ntiles) issue_in(nxt);      // x_mlstm / d_act blocks are free: stream in the next tile's
+    }
   }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (tid == 0) {
-    // d[q_proj|k_proj] as a dense (2E x E) product g_{q|k}^T act; only its 4x4 diagonal blocks are read back
-    umma_gemm(tmem + L::T_DWQK, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
-              umma_idesc(128, E, true, true), kTok, false);
-    umma_gemm(tmem + L::T_DWV, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16,
-              umma_idesc(128, E, true, true), kTok, false);
-    umma_commit(&bar2);
+  if (it > 0) {
+    mbar_wait(&bar2, (it - 1) & 1);
+    tc_fence_after();
   }
+  // ---- flush the accumulated parameter gradients
   // gate-weight gradient rows hh = 0..7 live in TMEM lanes 0..7: warps 0, 4, 8, 12 (quadrant 0) share the columns
   if ((warp & 3) == 0) {
 #pragma unroll 1
@@ -1004,8 +1038,6 @@ __global__ void __launch_bounds__(4 * kTok) vil_pre_bwd_a_tc_kernel(xhved_vil_pa
   for (int i = tid; i < E; i += blockDim.x) atomicAdd(gr.conv_bias + i, acc[L::A_CB + i]);
   if (tid < 4) atomicAdd(gr.igate_bias + tid, acc[L::A_GB + tid]);
   else if (tid < 8) atomicAdd(gr.fgate_bias + tid - 4, acc[L::A_GB + tid]);
-  mbar_wait(&bar2, 0);
-  tc_fence_after();
   {
     // row r of the (2E x E) product: r < E -> q_proj row e_out = r, r >= E -> k_proj; its diagonal block = 4 columns.
     // TMEM loads take a warp-uniform column address: every head group walks a quarter of the column groups.
@@ -1051,8 +1083,10 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_A, st);
-    vil_pre_bwd_a_tc_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(*p, g, xm, (const unsigned char*)q, (const unsigned char*)k,
-                                                               (const unsigned char*)v, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv, *gr);
+    const int ntiles = g.B * g.nc;
+    vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, xm, (const unsigned char*)q, (const unsigned char*)k,
+                                                                                  (const unsigned char*)v, dq, dk, dv, dig, dfg, d_act,
+                                                                                  ws_dconv, ws_dxmv, *gr, ntiles);
   } else {
     // dim 64: the CUDA-core kernel A (recomputes the forward from x); TMEM cannot hold its gate products in one pass
     const size_t smem = PreBwdASmem<C>::TOTAL * sizeof(float);
