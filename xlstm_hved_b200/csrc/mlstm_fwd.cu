@@ -113,53 +113,78 @@ template <int DHP>
 __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __restrict__ dstate, const float* __restrict__ g_in,
                                                                 const float* __restrict__ amax_in, int nc, int reverse,
                                                                 unsigned char* __restrict__ states, float* __restrict__ m_prev) {
-  // grid = (B*NH, ceil(DHP*NE / 512)): the state elements are independent, so they are spread over several CTAs; every
-  // CTA repeats the (scalar) log-scale recurrence.  The next chunk's contribution is prefetched one step ahead.
+  // grid = (B*NH, ceil(DHP*NE / 512)): the state elements are independent, so they are spread over several CTAs.  The
+  // scalar log-scale recurrence is run once per CTA (one thread, coefficients into shared memory); after that every element
+  // follows acc <- decay_c * acc + w_c * dstate_c, with the chunk contributions loaded eight chunks at a time so that the
+  // serial chain sees ~nc/8 memory latencies instead of nc.
   constexpr int NE = ext_cols(DHP);
   constexpr int NEL = DHP * NE;
+  extern __shared__ float scan_smem[];
+  float* s_g = scan_smem;            // [nc] in scan order
+  float* s_a = s_g + nc;
+  float* s_dec = s_a + nc;
+  float* s_w = s_dec + nc;
+  float* s_m = s_w + nc;
   const int bh = blockIdx.x, tid = threadIdx.x;
   const int i0 = blockIdx.y * 512 + tid, i1 = i0 + 256;
   const bool on0 = i0 < NEL, on1 = i1 < NEL;
   const uint32_t off0 = on0 ? tile_off16(DHP, i0 / NE, (i0 % NE) / 8) + ((i0 % NE) % 8) * 2 : 0;
   const uint32_t off1 = on1 ? tile_off16(DHP, i1 / NE, (i1 % NE) / 8) + ((i1 % NE) % 8) * 2 : 0;
-  float acc0 = 0.f, acc1 = 0.f, m = -INFINITY;
-  const int c_first = reverse ? nc - 1 : 0;
-  const float* src = dstate + (static_cast<size_t>(bh) * nc + c_first) * NEL;
-  float nx0 = on0 ? src[i0] : 0.f, nx1 = on1 ? src[i1] : 0.f;
-  float gn = g_in[static_cast<size_t>(bh) * nc + c_first], an = amax_in[static_cast<size_t>(bh) * nc + c_first];
-  for (int step = 0; step < nc; ++step) {
-    const int c = reverse ? nc - 1 - step : step;
-    const size_t tile = static_cast<size_t>(bh) * nc + c;
-    const float cur0 = nx0, cur1 = nx1, g = gn, amax = an;
-    if (step + 1 < nc) {      // prefetch the next chunk
-      const int cn = reverse ? c - 1 : c + 1;
-      const size_t tn = static_cast<size_t>(bh) * nc + cn;
-      const float* sn = dstate + tn * NEL;
-      nx0 = on0 ? sn[i0] : 0.f;
-      nx1 = on1 ? sn[i1] : 0.f;
-      gn = g_in[tn];
-      an = amax_in[tn];
+  const size_t tile0 = static_cast<size_t>(bh) * nc;
+  for (int st = tid; st < nc; st += blockDim.x) {
+    const int c = reverse ? nc - 1 - st : st;
+    s_g[st] = g_in[tile0 + c];
+    s_a[st] = amax_in[tile0 + c];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float m = -INFINITY;
+    for (int st = 0; st < nc; ++st) {
+      const float m_new = fmaxf(s_g[st] + m, s_a[st]);
+      s_m[st] = m;                                   // log-scale of the state ENTERING the chunk
+      s_dec[st] = __expf(s_g[st] + m - m_new);       // exp(-inf) = 0 on the first step
+      s_w[st] = __expf(s_a[st] - m_new);
+      m = m_new;
     }
-    // emit the state entering this chunk as a bf16 hi/lo pair
-    unsigned char* st = states + tile * (NEL * 4);
-    if (on0) {
-      const __nv_bfloat16 hi = __float2bfloat16(acc0);
-      *reinterpret_cast<__nv_bfloat16*>(st + off0) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(st + NEL * 2 + off0) = __float2bfloat16(acc0 - __bfloat162float(hi));
+  }
+  __syncthreads();
+  if (blockIdx.y == 0) {
+    for (int st = tid; st < nc; st += blockDim.x) m_prev[tile0 + (reverse ? nc - 1 - st : st)] = s_m[st];
+  }
+  float acc0 = 0.f, acc1 = 0.f;
+  constexpr int PF = 8;
+  for (int s0 = 0; s0 < nc; s0 += PF) {
+    float cur0[PF], cur1[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int st = s0 + j;
+      const int c = reverse ? nc - 1 - st : st;
+      const float* sn = dstate + (tile0 + (st < nc ? c : 0)) * NEL;
+      cur0[j] = (on0 && st < nc) ? __ldg(sn + i0) : 0.f;
+      cur1[j] = (on1 && st < nc) ? __ldg(sn + i1) : 0.f;
     }
-    if (on1) {
-      const __nv_bfloat16 hi = __float2bfloat16(acc1);
-      *reinterpret_cast<__nv_bfloat16*>(st + off1) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(st + NEL * 2 + off1) = __float2bfloat16(acc1 - __bfloat162float(hi));
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int st = s0 + j;
+      if (st < nc) {
+        const int c = reverse ? nc - 1 - st : st;
+        // emit the state entering this chunk as a bf16 hi/lo pair
+        unsigned char* out = states + (tile0 + c) * (NEL * 4);
+        if (on0) {
+          const __nv_bfloat16 hi = __float2bfloat16(acc0);
+          *reinterpret_cast<__nv_bfloat16*>(out + off0) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(out + NEL * 2 + off0) = __float2bfloat16(acc0 - __bfloat162float(hi));
+        }
+        if (on1) {
+          const __nv_bfloat16 hi = __float2bfloat16(acc1);
+          *reinterpret_cast<__nv_bfloat16*>(out + off1) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(out + NEL * 2 + off1) = __float2bfloat16(acc1 - __bfloat162float(hi));
+        }
+        // fold this chunk in
+        acc0 = s_dec[st] * acc0 + s_w[st] * cur0[j];
+        acc1 = s_dec[st] * acc1 + s_w[st] * cur1[j];
+      }
     }
-    if (tid == 0 && blockIdx.y == 0) m_prev[tile] = m;
-    // fold this chunk in
-    const float m_new = fmaxf(g + m, amax);
-    const float decay = __expf(g + m - m_new);   // exp(-inf) = 0 on the first step
-    const float wnew = __expf(amax - m_new);
-    acc0 = decay * acc0 + wnew * cur0;
-    acc1 = decay * acc1 + wnew * cur1;
-    m = m_new;
   }
 }
 
@@ -423,11 +448,13 @@ int launch_state_scan(int dhp, const float* dstate, const float* g, const float*
   ProfScope ps(K_STATE_SCAN, st);
   const int nel = dhp * (dhp + 16);
   const dim3 grid(BH, (nel + 511) / 512);
+  const size_t smem = static_cast<size_t>(nc) * 5 * sizeof(float);
+  if (smem > 48 * 1024) return XHVED_ERR_BAD_SHAPE;
   switch (dhp) {
-    case 16: mlstm_state_scan_kernel<16><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 32: mlstm_state_scan_kernel<32><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 64: mlstm_state_scan_kernel<64><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 128: mlstm_state_scan_kernel<128><<<grid, 256, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 16: mlstm_state_scan_kernel<16><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 32: mlstm_state_scan_kernel<32><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 64: mlstm_state_scan_kernel<64><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 128: mlstm_state_scan_kernel<128><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
     default: return XHVED_ERR_UNSUPPORTED_DH;
   }
   return (int)cudaGetLastError();

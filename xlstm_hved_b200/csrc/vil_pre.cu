@@ -910,7 +910,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     }
     const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;
     bool mma1_pending = true;
-#pragma unroll 1
+#pragma unroll
     for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
       const int d0 = e8 % DH;
       float a8[8], xm8[8], cv8[8], xr[4][8];
