@@ -172,8 +172,11 @@ struct BwdSmem {
   static constexpr uint32_t TOTAL = VCOL + kL * 4;
 };
 
+// 256 threads: thread = (row, half).  Both halves know the gate quantities of their row; half 0 owns the row's operand
+// staging and the dQ / dK epilogue, half 1 the dV epilogue; the S / dP -> P / dS conversion of a row (the causal part, up to
+// 128 columns) is split between the two.
 template <int DHP>
-__global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
+__global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_grad_kernel(
     const unsigned char* __restrict__ q_tiles, const unsigned char* __restrict__ k_tiles, const unsigned char* __restrict__ v_tiles,
     const unsigned char* __restrict__ h_tiles, const unsigned char* __restrict__ dh_tiles, const float* __restrict__ ig,
     const float* __restrict__ fg, const float* __restrict__ m_in, const float* __restrict__ den_in,
@@ -194,13 +197,14 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x & (kL - 1), hsel = threadIdx.x >> 7, warp = tid >> 5;     // tid = row, warp = row group
+  const bool lead = threadIdx.x == 0;
   const int tile = blockIdx.x;
   const int c = tile % nc;
   const size_t grow = static_cast<size_t>(tile) * kL + tid;
   const bool has_prev = c > 0, has_next = c < nc - 1;
 
-  if (tid == 0) {
+  if (lead) {
     mbar_init(&bar_load, 1);
     mbar_init(&bar_s, 1);
     mbar_init(&bar_p, 1);
@@ -210,10 +214,10 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
     mbar_fence_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
-  write_ext_ones(sV, DHP, tid);
+  if (threadIdx.x < 32) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (hsel == 0) write_ext_ones(sV, DHP, tid);
   __syncthreads();
-  if (tid == 0) {
+  if (lead) {
     mbar_expect_tx(&bar_load, 5 * TILE + (has_prev ? ST_BYTES : 0) + (has_next ? ST_BYTES : 0));
     const size_t to = static_cast<size_t>(tile) * TILE;
     bulk_g2s(sQ, q_tiles + to, TILE, &bar_load);
@@ -236,17 +240,17 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   const float fac = has_next ? __expf(g - b + iv + mu_next[tile]) : 0.f;
 
   mbar_wait(&bar_load, 0);
-  build_G_row<DHP>(sG, sP, tid, m, den, eps);
+  if (hsel == 0) build_G_row<DHP>(sG, sP, tid, m, den, eps);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     // S[t][s] = Q K^T            -> cols [0,128)
     umma_gemm(tmem, smem_u32(sQ), kL * 16, 128, smem_u32(sK), kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
     umma_commit(&bar_s);
-  } else if (tid == 32) {
+  } else if (threadIdx.x == 32) {
     // dP[t][s] = G Vext^T        -> cols [128,256)
     umma_gemm(tmem + 128, smem_u32(sG), kL * 16, 128, smem_u32(sV), kL * 16, 128, umma_idesc(128, kL, false, false), NE, false);
     umma_commit(&bar_p);
@@ -255,28 +259,23 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   mbar_wait(&bar_p, 0);
   tc_fence_after();
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  // row group `warp` needs column blocks 0..warp (2 * (warp + 1) half-blocks of 16 columns): the two halves take warp + 1
+  // half-blocks each; the all-zero blocks behind the diagonal are cleared by half 0 (P) and half 1 (dS)
 #pragma unroll 1
-  for (int blk = 0; blk < 4; ++blk) {
-    if (blk <= warp) {
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float sv[16], dp[16];
-        tmem_ld16(tmem + lane_base + blk * 32 + half * 16, sv);
-        tmem_ld16(tmem + lane_base + 128 + blk * 32 + half * 16, dp);
-        const int s0 = blk * 32 + half * 16;
-        // only the diagonal block needs the causal mask
-        if (blk < warp)
-          decay_pair<false>(sv, dp, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8), sdS + tile_off16(kL, tid, s0 / 8));
-        else
-          decay_pair<true>(sv, dp, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8), sdS + tile_off16(kL, tid, s0 / 8));
-      }
-    } else {
-#pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, blk * 4 + j8)) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sdS + tile_off16(kL, tid, blk * 4 + j8)) = make_uint4(0, 0, 0, 0);
-      }
-    }
+  for (int hb = hsel * (warp + 1); hb < (hsel + 1) * (warp + 1); ++hb) {
+    const int blk = hb >> 1, s0 = hb * 16;
+    float sv[16], dp[16];
+    tmem_ld16(tmem + lane_base + s0, sv);
+    tmem_ld16(tmem + lane_base + 128 + s0, dp);
+    // only the diagonal block needs the causal mask
+    if (blk < warp)
+      decay_pair<false>(sv, dp, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8), sdS + tile_off16(kL, tid, s0 / 8));
+    else
+      decay_pair<true>(sv, dp, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8), sdS + tile_off16(kL, tid, s0 / 8));
+  }
+  {
+    unsigned char* zt = hsel == 0 ? sP : sdS;
+    for (int cg = (warp + 1) * 4; cg < 16; ++cg) *reinterpret_cast<uint4*>(zt + tile_off16(kL, tid, cg)) = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -285,7 +284,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   {
     const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aG = smem_u32(sG), aP = smem_u32(sP), aS = smem_u32(sdS),
                    aC = smem_u32(sC), aR = smem_u32(sR);
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
       // dQ_intra[t][d] = sum_s dS[t][s] K[s][d]
       umma_gemm(tmem + 0 * DHP, aS, kL * 16, 128, aK, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
       // dQ_inter[t][d] = sum_e' G[t][e'] Cn[d][e']
@@ -294,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
         umma_gemm(tmem + 1 * DHP, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
       }
       umma_commit(&bar_q);
-    } else if (tid == 32) {
+    } else if (threadIdx.x == 32) {
       // dK_intra[s][d] = sum_t dS[t][s] Q[t][d]
       umma_gemm(tmem + 2 * DHP, aS, 128, kL * 16, aQ, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
       // dK_inter[s][d] = sum_e' Vext[s][e'] R[d][e']
@@ -303,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
         umma_gemm(tmem + 3 * DHP, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
       }
       umma_commit(&bar_k);
-    } else if (tid == 64) {
+    } else if (threadIdx.x == 64) {
       // dV_intra[s][e] = sum_t P[t][s] G[t][e]
       umma_gemm(tmem + 4 * DHP, aP, 128, kL * 16, aG, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
       // dV_inter[s][e] = sum_d K[s][d] R[d][e]
@@ -320,6 +319,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
   float* dq_row = dq + grow * DHP;
   float* dk_row = dk + grow * DHP;
   float* dv_row = dv + grow * DHP;
+  if (hsel == 0) {
   mbar_wait(&bar_q, 0);
   tc_fence_after();
 #pragma unroll 1
@@ -362,6 +362,8 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
 #pragma unroll
     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dk_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
   }
+  dig[grow] = k_dk;
+  } else {
   mbar_wait(&bar_v, 0);
   tc_fence_after();
 #pragma unroll 1
@@ -376,18 +378,20 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_grad_kernel(
 #pragma unroll
     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dv_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
   }
-  dig[grow] = k_dk;
+  }
   {
     // d log f = reverse cumulative sum of dc over the whole sequence: the chunk-local suffix sum is taken here, the carry of
     // the later chunks (sum of their totals) is added by mlstm_gate_finish_kernel
     float tot;
-    const float suffix = block_rcumsum128(q_dq - k_dk, red, &tot);
-    dc_out[grow] = suffix;
-    if (tid == 0) dc_tot[tile] = tot;
+    const float suffix = block_rcumsum128(q_dq - k_dk, red, &tot);     // half 1 scans zeros
+    if (hsel == 0) {
+      dc_out[grow] = suffix;
+      if (tid == 0) dc_tot[tile] = tot;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+  if (threadIdx.x < 32) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ phase B4
@@ -442,7 +446,7 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_grad_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_CHUNK_GRAD, st);
-    mlstm_chunk_grad_kernel<DHP><<<ntiles, kThreads, smem, st>>>(
+    mlstm_chunk_grad_kernel<DHP><<<ntiles, 2 * kThreads, smem, st>>>(
         (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, (const unsigned char*)h, (const unsigned char*)dh_t, ig, fg,
         m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, scale, eps, dq, dk, dv, dig, ws_dc,
         ws_lam /* free again after the reverse scan: receives the per-chunk totals of dc */);

@@ -11,9 +11,11 @@ constexpr int kThreads = 128;  // one thread per chunk row
 __host__ __device__ constexpr int ext_cols(int dhp) { return dhp + 16; }
 __host__ __device__ constexpr uint32_t next_pow2_cols(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
-// ---- 128-wide block scans (4 warps).  `red` is 8 floats of shared scratch. ----
+// ---- 128-wide block scans (4 warps).  `red` is 8 floats of shared scratch.  A 256-thread CTA may call them too: its two
+// 128-thread halves then scan the same kind of 128 values independently (threads 128.. use red[4..7]). ----
 __device__ __forceinline__ float block_cumsum128(float x, float* red, float* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;
+  red += (threadIdx.x >> 7) << 2;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     float y = __shfl_up_sync(0xffffffffu, x, o);
@@ -33,7 +35,8 @@ __device__ __forceinline__ float block_cumsum128(float x, float* red, float* tot
   return x + off;
 }
 __device__ __forceinline__ float block_cummax128(float x, float* red, float* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;
+  red += (threadIdx.x >> 7) << 2;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     float y = __shfl_up_sync(0xffffffffu, x, o);
@@ -54,7 +57,8 @@ __device__ __forceinline__ float block_cummax128(float x, float* red, float* tot
 }
 // reverse (suffix) inclusive cumulative sum over the 128 threads
 __device__ __forceinline__ float block_rcumsum128(float x, float* red, float* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;
+  red += (threadIdx.x >> 7) << 2;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     float y = __shfl_down_sync(0xffffffffu, x, o);
