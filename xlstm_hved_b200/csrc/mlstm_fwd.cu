@@ -208,8 +208,29 @@ __device__ __forceinline__ float decay_block(const float* sv, float urow, const 
   return rowsum;
 }
 
+// 16 columns of one row (two 16-byte groups, 2 KB apart)
+template <bool MASK>
+__device__ __forceinline__ float decay_half(const float* sv, float urow, const float* vcol, int s0, int row, unsigned char* dst) {
+  float rowsum = 0.f;
+#pragma unroll
+  for (int j8 = 0; j8 < 2; ++j8) {
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = fast_exp2(urow + vcol[j8 * 8 + j]);
+      p[j] = sv[j8 * 8 + j] * d;
+      if (MASK) p[j] = (s0 + j8 * 8 + j <= row) ? p[j] : 0.f;
+      rowsum += p[j];
+    }
+    *reinterpret_cast<uint4*>(dst + j8 * (kL * 16)) = pack8_bf16(p);
+  }
+  return rowsum;
+}
+
+// 256 threads: thread = (row, half); the causal S -> P conversion of a row and (DHP >= 32) the output columns are split
+// between the two halves, both of which know the gate quantities of their row.
 template <int DHP>
-__global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
+__global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_out_kernel(
     const unsigned char* __restrict__ q_tiles, const unsigned char* __restrict__ k_tiles, const unsigned char* __restrict__ v_tiles,
     const float* __restrict__ ig, const float* __restrict__ fg, const unsigned char* __restrict__ states,
     const float* __restrict__ m_prev, int nc, float scale, float eps, unsigned char* __restrict__ h_tiles,
@@ -230,22 +251,24 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
   __shared__ __align__(8) uint64_t bar_load, bar_mma1, bar_mma2;
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8];
+  __shared__ float rs_part[2][kL];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x & (kL - 1), hsel = threadIdx.x >> 7, warp = tid >> 5;    // tid = row, warp = row group
+  const bool lead = threadIdx.x == 0;
   const int tile = blockIdx.x;
   const int c = tile % nc;
   const size_t grow = static_cast<size_t>(tile) * kL + tid;
   const bool has_state = c > 0;
 
-  if (tid == 0) {
+  if (lead) {
     mbar_init(&bar_load, 1);
     mbar_init(&bar_mma1, 1);
     mbar_init(&bar_mma2, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (threadIdx.x < 32) tmem_alloc(&tmem_slot, TMEM_COLS);
   __syncthreads();
-  if (tid == 0) {
+  if (lead) {
     mbar_expect_tx(&bar_load, 3 * TILE + (has_state ? ST_BYTES : 0));
     bulk_g2s(sQ, q_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
     bulk_g2s(sK, k_tiles + static_cast<size_t>(tile) * TILE, TILE, &bar_load);
@@ -270,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
   __syncthreads();   // vcol + tmem_slot visible
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (lead) {
     // S[t][s] = sum_d Q[t][d] K[s][d]
     umma_gemm(tmem, smem_u32(sQ), kL * 16, 128, smem_u32(sK), kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
     umma_commit(&bar_mma1);
@@ -280,26 +303,26 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
   // ---- P = S o D' (causal), row sums; P -> smem as the next A operand ----
   float rowsum = 0.f;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  // row group `warp` needs column blocks 0..warp, i.e. 2 * (warp + 1) half-blocks of 16 columns: warp + 1 per half
 #pragma unroll 1
-  for (int blk = 0; blk < 4; ++blk) {
-    if (blk <= warp) {
-      float sv[32];
-      tmem_ld32(tmem + lane_base + blk * 32, sv);
-      // only the diagonal 32x32 block needs the causal mask; blocks left of it are fully visible
-      if (blk < warp)
-        rowsum += decay_block<false>(sv, urow, vcol + blk * 32, blk * 32, tid, sP + tile_off16(kL, tid, blk * 4));
-      else
-        rowsum += decay_block<true>(sv, urow, vcol + blk * 32, blk * 32, tid, sP + tile_off16(kL, tid, blk * 4));
-    } else {
-#pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, blk * 4 + j8)) = make_uint4(0, 0, 0, 0);
-    }
+  for (int hb = hsel * (warp + 1); hb < (hsel + 1) * (warp + 1); ++hb) {
+    const int blk = hb >> 1, s0 = hb * 16;
+    float sv[16];
+    tmem_ld16(tmem + lane_base + s0, sv);
+    // only the diagonal 32x32 block needs the causal mask; blocks left of it are fully visible
+    if (blk < warp)
+      rowsum += decay_half<false>(sv, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8));
+    else
+      rowsum += decay_half<true>(sv, urow, vcol + s0, s0, tid, sP + tile_off16(kL, tid, s0 / 8));
   }
+  for (int cg = (warp + 1) * 4 + hsel; cg < 16; cg += 2) *reinterpret_cast<uint4*>(sP + tile_off16(kL, tid, cg)) = make_uint4(0, 0, 0, 0);
+  rs_part[hsel][tid] = rowsum;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 0) {
+  rowsum = rs_part[0][tid] + rs_part[1][tid];
+  if (lead) {
     // O_intra[t][e] = sum_s P[t][s] V[s][e]      (B = MN-major view of V)
     umma_gemm(tmem, smem_u32(sP), kL * 16, 128, smem_u32(sV), 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
     // O_inter[t][e'] = sum_d Q[t][d] [C|n][d][e'] (B = MN-major view of the state tile)
@@ -325,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
   const float rn = 1.f / nrm;
   unsigned char* hdst = h_tiles + static_cast<size_t>(tile) * TILE;
 #pragma unroll
-  for (int c0 = 0; c0 < DHP; c0 += 16) {
+  for (int c0 = hsel * 16; c0 < DHP; c0 += 32) {
     float o[16];
     tmem_ld16(tmem + lane_base + c0, o);
     if (has_state) {
@@ -348,11 +371,13 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_out_kernel(
     *reinterpret_cast<uint4*>(hdst + tile_off16(kL, tid, c0 / 8)) = u0;
     *reinterpret_cast<uint4*>(hdst + tile_off16(kL, tid, c0 / 8 + 1)) = u1;
   }
-  m_out[grow] = m;
-  den_out[grow] = den;
+  if (hsel == 0) {
+    m_out[grow] = m;
+    den_out[grow] = den;
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+  if (threadIdx.x < 32) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ pack / unpack (standalone cell API)
@@ -435,7 +460,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_out_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_CHUNK_OUT, st);
-    mlstm_chunk_out_kernel<DHP><<<ntiles, kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v,
+    mlstm_chunk_out_kernel<DHP><<<ntiles, 2 * kThreads, smem, st>>>((const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v,
                                                                 ig, fg, (const unsigned char*)states, m_prev, nc, scale, eps,
                                                                 (unsigned char*)h, m, den);
   }
