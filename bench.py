@@ -306,7 +306,10 @@ def run_gpu(args):
     tokens_heads = tokens * NH
     E = 2 * DIM
     L = 128
-    # ALGORITHMIC work per launch.  Cell kernels: useful causal-half FLOP; everything else: minimum HBM bytes.
+    # ALGORITHMIC work per launch: minimum HBM bytes for every kernel and, for the cell kernels, the
+    # useful (causal-half) tensor FLOP.  The roof that binds a kernel is the one with the larger bound time.
+    DHP, NE = max(DH, 16), max(DH, 16) + 16
+    st_tok = DHP * NE * 4 / L                         # one fp32 (or bf16 hi+lo) state per chunk, per token-head
     flops = {
         "mlstm_chunk_grad": tokens_heads * (5 * L * DH + 6 * DH * DH),      # S, dP, dQ, dK, dV causal halves + 3 inter products
         "mlstm_chunk_out": tokens_heads * (2 * L * DH + 2 * DH * DH),       # S, PV causal halves + q.[C|n]
@@ -321,34 +324,52 @@ def run_gpu(args):
         "vil_pre_bwd_a": E * 4 + 3 * E * 2 + 3 * E * 4 + 8 * 4 + E * 4 + 2 * E * 4,   # xm, q|k|v, dq,dk,dv, dgates, d_act in; dconv, dxmv out
         "vil_pre_bwd_b": 4 * DIM + 4 * DIM + 3 * E * 4 + 4 * DIM,                     # x, dy, dconv, dxmv, dz in; dx out
     }
+    per_tokenhead_bytes = {
+        "mlstm_chunk_state": 4 * DHP + 8 + st_tok,                                    # k,v tiles, i/f gates in; chunk state out
+        "mlstm_state_scan": 2 * st_tok,                                               # chunk states in; carried states (bf16 hi+lo) out
+        "mlstm_chunk_out": 6 * DHP + 8 + st_tok + 2 * DHP + 8,                        # q,k,v, gates, state in; h, m, den out
+        "mlstm_chunk_rstate": 6 * DHP + 12 + st_tok,                                  # q, dh, h tiles, f, m, den in; reverse chunk state out
+        "mlstm_chunk_grad": 10 * DHP + 16 + 2 * st_tok + 12 * DHP + 8,                # q,k,v,h,dh, gates, m, den, C, R in; dq,dk,dv, di, dc out
+        "mlstm_gate_finish": 12,
+    }
     bytes_per_launch = {k: v * tokens for k, v in per_token_bytes.items()}
+    bytes_per_launch.update({k: v * tokens_heads for k, v in per_tokenhead_bytes.items()})
     bytes_per_step = {"poe_fwd": n_lat * (40 + 4 + 12), "poe_bwd": n_lat * (40 + 4 + 4 + 40)}   # the 4 level launches of a step together
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
 
     def roofline_of(name):
         ms, cnt = kern[name]
-        if name in flops:
-            ach = flops[name] / (ms / cnt * 1e-3) / 1e12
-            return {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": peaks["tf"], "unit": "TFLOP/s",
-                    "frac": round(ach / peaks["tf"], 5), "traffic": traffic.get(name), "algorithmic_flop_per_launch": flops[name],
-                    "avg_launch_ms": round(ms / cnt, 5), "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside the step)"}
-        if name in bytes_per_launch:
-            ach = bytes_per_launch[name] / (ms / cnt * 1e-3) / 1e9
-            return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": round(ach / peaks["hbm"], 4), "traffic": traffic.get(name), "algorithmic_bytes_per_launch": bytes_per_launch[name],
-                    "avg_launch_ms": round(ms / cnt, 5), "peak_source": peaks["src"]}
         if name in bytes_per_step:
             ach = bytes_per_step[name] / (ms / K * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": round(ach / peaks["hbm"], 4), "traffic": traffic.get(name), "algorithmic_bytes_per_step": bytes_per_step[name],
                     "ms_per_step": round(ms / K, 5), "peak_source": peaks["src"], "note": "4 launches per step (one per latent level)"}
-        return {"kernel": name, "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
-                "avg_launch_ms": round(ms / cnt, 5)}
+        if name not in bytes_per_launch:
+            return {"kernel": name, "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                    "avg_launch_ms": round(ms / cnt, 5)}
+        sec = ms / cnt * 1e-3
+        nbytes, nflop = bytes_per_launch[name], flops.get(name, 0)
+        hbm = {"kernel": name, "bound": "hbm", "achieved": round(nbytes / sec / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+               "frac": round(nbytes / sec / 1e9 / peaks["hbm"], 4), "traffic": traffic.get(name), "algorithmic_bytes_per_launch": int(nbytes),
+               "avg_launch_ms": round(ms / cnt, 5), "peak_source": peaks["src"]}
+        if not nflop:
+            return hbm
+        tf = nflop / sec / 1e12
+        hbm["tensor_frac"] = round(tf / peaks["tf"], 5)
+        hbm["algorithmic_flop_per_launch"] = nflop
+        if nflop / (peaks["tf"] * 1e12) <= nbytes / (peaks["hbm"] * 1e9):
+            hbm["note"] = "arithmetic intensity %.0f FLOP/B is below the ridge (%.0f): HBM is the binding roof at this head dim" % (
+                nflop / nbytes, peaks["tf"] * 1e12 / (peaks["hbm"] * 1e9))
+            return hbm
+        return {"kernel": name, "bound": "tensor", "achieved": round(tf, 3), "peak": peaks["tf"], "unit": "TFLOP/s",
+                "frac": round(tf / peaks["tf"], 5), "traffic": traffic.get(name), "algorithmic_flop_per_launch": nflop,
+                "hbm_frac": hbm["frac"], "avg_launch_ms": round(ms / cnt, 5),
+                "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside the step)"}
 
     order = sorted(kern.items(), key=lambda kv: -kv[1][0])
     roof = roofline_of(order[0][0])
-    secondary = {k: {kk: vv for kk, vv in roofline_of(k).items() if kk in ("bound", "achieved", "unit", "frac", "avg_launch_ms", "ms_per_step")}
+    secondary = {k: {kk: vv for kk, vv in roofline_of(k).items() if kk in ("bound", "achieved", "unit", "frac", "tensor_frac", "avg_launch_ms", "ms_per_step")}
                  for k, _ in order[1:]}
     shares = {k: round(v[0] / sum(m for m, _ in kern.values()), 4) for k, v in order}
 
