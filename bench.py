@@ -321,7 +321,7 @@ def run_gpu(args):
         "vil_pre_fwd": 4 * DIM + 3 * E * 2 + 8 * 4 + 3 * E * 4,                       # x in; q,k,v tiles, gates, act, z, xm out
         "vil_post_fwd": E * 2 + 2 * E * 4 + 4 * DIM + 4 * DIM,                        # h, act, z, x in; y out
         "vil_post_bwd": 4 * DIM + E * 2 + 2 * E * 4 + E * 2 + 2 * E * 4,              # dy, h, act, z in; dh, d_act, dz out
-        "vil_pre_bwd_a": E * 4 + 3 * E * 2 + 3 * E * 4 + 8 * 4 + E * 4 + 2 * E * 4,   # xm, q|k|v, dq,dk,dv, dgates, d_act in; dconv, dxmv out
+        "vil_pre_bwd_a": E * 4 + 3 * E * 4 + 8 * 4 + E * 4 + 2 * E * 4,               # xm, dq,dk,dv, dgates, d_act in; dconv, dxmv out
         "vil_pre_bwd_b": 4 * DIM + 4 * DIM + 3 * E * 4 + 4 * DIM,                     # x, dy, dconv, dxmv, dz in; dx out
     }
     per_tokenhead_bytes = {

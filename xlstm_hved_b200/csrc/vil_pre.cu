@@ -752,85 +752,120 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
-// Kernel A (tensor-core, C <= 32): the forward's saved x_mlstm and bf16 q|k|v tiles are reloaded (no recompute of
-// proj_up); gate-path gradients (dig,dfg -> q,k,v), gate-weight and block-diagonal weight gradients run as UMMAs over the
-// CTA's tokens; conv / SiLU / 4x4 block backward on CUDA cores.
+// Kernel A (tensor-core, C <= 32).  Inputs per tile: the forward's saved x_mlstm (no recompute of proj_up), d_act, the
+// cell's dq/dk/dv and the gate gradients.  Gate-path gradients (dig,dfg -> q,k,v) and every parameter gradient that is a
+// token reduction run as UMMAs; conv / SiLU / 4x4 block backward on CUDA cores.
+// The gate-weight gradient  d Wg = [dig|dfg]^T [q|k|v]  is taken THROUGH the block-diagonal projections:
+//     [dig|dfg]^T q = ([dig|dfg]^T act) Wq^T   (k alike; v with x_mlstm and Wv)
+// so the kernel only reduces [dig|dfg]^T act and [dig|dfg]^T x_mlstm over tokens (operand tiles it stages anyway) and
+// applies the 4x4 blocks once per CTA at flush time -- the bf16 q|k|v tiles are not read at all.
 template <int C>
 struct PreBwdATC {
   static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
-  static constexpr uint32_t DG_BYTES = kTok * 16 * 2, WG_BYTES = 16 * NQ * 2, QKV_BYTES = kTok * NQ * 2, T_BYTES = kTok * E * 2;
-  // [dig|dfg] is read as a 128-row MN-major A operand (32 KB window that runs on over the tiles behind it; rows >= 16 of
-  // that product are never read)
-  static constexpr uint32_t DGHI = 0, DGLO = DG_BYTES, WGHI = 2 * DG_BYTES, WGLO = WGHI + WG_BYTES;
-  // The q|k|v tile has its own space so that the NEXT tile's q|k|v can stream in while the main loop of this tile runs.
-  // GQK: [128][2E]; GV: 32 KB window covering ACT, XMT.
-  static constexpr uint32_t QKV = WGLO + WG_BYTES, GQK = QKV + QKV_BYTES;
+  static constexpr uint32_t DG_BYTES = kTok * 16 * 2, WG_BYTES = 16 * NQ * 2, T_BYTES = kTok * E * 2;
+  // [dig|dfg] (double-buffered hi/lo pairs) is also read as a 128-row MN-major A operand: 32 KB window that runs on over
+  // the tiles behind it; rows >= 16 of those products are never read
+  static constexpr uint32_t DG0 = 0, DG_STRIDE = 2 * DG_BYTES, WGHI = 2 * DG_STRIDE, WGLO = WGHI + WG_BYTES;
+  // operands of the weight-gradient GEMMs.  GQK: [128][2E]; GV: 32 KB window covering ACT, XMT.
+  static constexpr uint32_t GQK = WGLO + WG_BYTES;
   static constexpr uint32_t GV = GQK + kTok * 2 * E * 2, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;
-  static constexpr uint32_t END2 = XMT + T_BYTES, END3 = GV + 32768;
-  static constexpr uint32_t PAR = END2 > END3 ? END2 : END3;
+  static constexpr uint32_t END2 = XMT + T_BYTES, END3 = GV + 32768, END4 = DG0 + DG_STRIDE + 32768;
+  static constexpr uint32_t PAR = END2 > END3 ? (END2 > END4 ? END2 : END4) : (END3 > END4 ? END3 : END4);
   static constexpr int P_CW = 0, P_CB = E * 4, P_WQ = P_CB + E, P_WK = P_WQ + E * 4, P_WV = P_WK + E * 4, A_CW = P_WV + E * 4,
                        A_CB = A_CW + E * 4, A_GB = A_CB + E, P_N = A_GB + 8;
-  // token-minor input blocks staged by bulk async copies: x_mlstm, d_act (E x 128 fp32 each) + x_mlstm of the 3 tokens
-  // in front of the chunk (E x 4 floats)
-  static constexpr uint32_t BLK = E * kTok * 4;
-  static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + BLK, IN_HX = IN_DA + BLK;
-  static constexpr uint32_t TOTAL = IN_HX + E * 4 * 4;
-  static constexpr uint32_t T_GQ = 0, T_DWG = NQ, T_DWQK = 2 * NQ, T_DWV = 2 * NQ + E;
-  static_assert(2 * NQ + 2 * E <= 512 && 2 * E <= 128 && TOTAL <= 227 * 1024, "tensor-core pre-backward A supports C <= 32");
+  // token-minor input blocks staged by bulk async copies: x_mlstm (two stages, each followed by the E x 4 floats of the
+  // 3 tokens in front of the chunk) and d_act (one stage), E x 128 fp32 each
+  static constexpr uint32_t BLK = E * kTok * 4, HX_BYTES = E * 4 * 4, XM_STRIDE = BLK + HX_BYTES;
+  static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + 2 * XM_STRIDE;
+  static constexpr uint32_t TOTAL = IN_DA + BLK;
+  static constexpr uint32_t T_GQ = 0, T_DWQK = NQ, T_DWV = NQ + E, T_DWGA = NQ + 2 * E, T_DWGX = NQ + 3 * E;
+  static_assert(NQ + 4 * E <= 512 && 2 * E <= 128 && TOTAL <= 227 * 1024, "tensor-core pre-backward A supports C <= 32");
 };
 
 template <int C>
 __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
-                                                                        const unsigned char* __restrict__ q_tiles,
-                                                                        const unsigned char* __restrict__ k_tiles,
-                                                                        const unsigned char* __restrict__ v_tiles, const float* __restrict__ dq,
-                                                                        const float* __restrict__ dk, const float* __restrict__ dv,
-                                                                        const float* __restrict__ dig, const float* __restrict__ dfg,
-                                                                        const float* __restrict__ d_act, float* __restrict__ dconv_out,
-                                                                        float* __restrict__ dxmv_out, xhved_vil_grads gr_base, int ntiles) {
+                                                                        const float* __restrict__ dq, const float* __restrict__ dk,
+                                                                        const float* __restrict__ dv, const float* __restrict__ dig,
+                                                                        const float* __restrict__ dfg, const float* __restrict__ d_act,
+                                                                        float* __restrict__ dconv_out, float* __restrict__ dxmv_out,
+                                                                        xhved_vil_grads gr_base, int ntiles) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, head); the four head groups of a token share the TMEM lane of that token.
   // Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  All parameter gradients accumulate over the CTA's
-  // tiles -- the three weight-gradient UMMAs keep adding into their TMEM columns, conv / bias sums live in shared memory --
-  // and are flushed to global once.  The next tile's inputs stream in (bulk copies) as soon as their buffers are free.
+  // tiles -- the weight-gradient UMMAs keep adding into their TMEM columns, conv / bias sums live in shared memory -- and
+  // are flushed to global once.  x_mlstm of the next tile streams into the other stage while this tile is processed, its
+  // gate gradients are fetched one tile ahead, and the gate-path UMMA of tile i+1 is issued right behind the weight-gradient
+  // UMMAs of tile i: one __syncthreads per tile.
   using L = PreBwdATC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
-  constexpr uint32_t HT = kTok * DHP * 2;
   extern __shared__ __align__(128) unsigned char smem[];
   float* par = reinterpret_cast<float*>(smem + L::PAR);
-  __shared__ __align__(8) uint64_t bar_qkv, bar_in, bar1, bar2;
+  __shared__ __align__(8) uint64_t bar_xm[2], bar_da, bar1, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tok = tid & (kTok - 1), head = tid >> 7;
 
-  auto issue_qkv = [&](int tile) {
-    const int b = tile / g.nc, ch = tile % g.nc;
-    mbar_expect_tx(&bar_qkv, 12 * HT);
-#pragma unroll 1
-    for (int hd = 0; hd < 4; ++hd) {
-      const size_t t2 = (static_cast<size_t>(b) * 4 + hd) * g.nc + ch;
-      bulk_g2s(smem + L::QKV + (0 * 4 + hd) * HT, q_tiles + t2 * HT, HT, &bar_qkv);
-      bulk_g2s(smem + L::QKV + (1 * 4 + hd) * HT, k_tiles + t2 * HT, HT, &bar_qkv);
-      bulk_g2s(smem + L::QKV + (2 * 4 + hd) * HT, v_tiles + t2 * HT, HT, &bar_qkv);
+  auto issue_xm = [&](int tile, int s) {
+    mbar_expect_tx(&bar_xm[s], L::BLK);
+    bulk_g2s(smem + L::IN_XM + s * L::XM_STRIDE, xm + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_xm[s]);
+  };
+  auto issue_da = [&](int tile) {
+    mbar_expect_tx(&bar_da, L::BLK);
+    bulk_g2s(smem + L::IN_DA, d_act + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_da);
+  };
+  // x_mlstm of the 3 tokens in front of chunk `tile` (zeros in front of the sequence) -> behind stage s
+  auto load_halo = [&](int tile, int s) {
+    float* hx = reinterpret_cast<float*>(smem + L::IN_XM + s * L::XM_STRIDE + L::BLK);
+    const int ch = tile % g.nc;
+    for (int i = tid; i < E * 4; i += blockDim.x) {
+      const int e = i >> 2, k = i & 3;
+      hx[i] = (k < 3 && ch > 0) ? __ldg(xm + static_cast<size_t>(tile - 1) * E * kTok + static_cast<size_t>(e) * kTok + kTok - 3 + k) : 0.f;
     }
   };
-  auto issue_in = [&](int tile) {
-    mbar_expect_tx(&bar_in, 2 * L::BLK);
-    bulk_g2s(smem + L::IN_XM, xm + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_in);
-    bulk_g2s(smem + L::IN_DA, d_act + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_in);
+  // [dig | dfg] of this token (head group 0 only)
+  auto load_dg = [&](int tile, float* dg) {
+    const int b = tile / g.nc, ch = tile % g.nc;
+    const bool valid = ch * kTok + tok < g.S;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
+      dg[h] = valid ? __ldg(dig + o) : 0.f;
+      dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
+    }
+  };
+  auto stage_dg = [&](float* dg, int s) {
+    unsigned char* d0 = smem + L::DG0 + s * L::DG_STRIDE;
+    uint4 hi, lo;
+    split8_hilo(dg, hi, lo);
+    *reinterpret_cast<uint4*>(d0 + tile_off16(kTok, tok, 0)) = hi;
+    *reinterpret_cast<uint4*>(d0 + L::DG_BYTES + tile_off16(kTok, tok, 0)) = lo;
+    *reinterpret_cast<uint4*>(d0 + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(d0 + L::DG_BYTES + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
+    warp_acc_vec<8>(par + L::A_GB, dg);       // gate bias gradients
+  };
+  // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
+  auto issue_mma1 = [&](uint32_t tmem, int s) {
+    const uint32_t d0 = smem_u32(smem + L::DG0 + s * L::DG_STRIDE);
+    umma_gemm_hilo(tmem + L::T_GQ, d0, d0 + L::DG_BYTES, kTok * 16, 128, smem_u32(smem + L::WGHI), smem_u32(smem + L::WGLO), 128, 16 * 16,
+                   umma_idesc(128, NQ, false, true), 16);
+    umma_commit(&bar1);
   };
 
   if (tid == 0) {
-    mbar_init(&bar_qkv, 1);
-    mbar_init(&bar_in, 1);
+    mbar_init(&bar_xm[0], 1);
+    mbar_init(&bar_xm[1], 1);
+    mbar_init(&bar_da, 1);
     mbar_init(&bar1, 1);
     mbar_init(&bar2, 1);
     mbar_fence_init();
-    issue_qkv(blockIdx.x);
-    issue_in(blockIdx.x);
+    issue_xm(blockIdx.x, 0);
+    issue_da(blockIdx.x);
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  float dgn[8];
+  if (head == 0) load_dg(blockIdx.x, dgn);
+  load_halo(blockIdx.x, 0);
   stage(par + L::P_CW, p.conv_weight, E * 4);
   stage(par + L::P_CB, p.conv_bias, E);
   stage(par + L::P_WQ, p.q_weight, E * 4);
@@ -851,72 +886,45 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
     *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
   }
+  __syncthreads();                    // gate-bias accumulators are zero
+  if (head == 0) stage_dg(dgn, 0);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   float* acc = par;
+  if (tid == 0) issue_mma1(tmem, 0);
 
   int it = 0;
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
     const int b = tile / g.nc, ch = tile % g.nc;
     const int nxt = tile + gridDim.x;
-    {
-      // x_mlstm of the 3 tokens in front of this chunk (zeros in front of the sequence)
-      float* hx = reinterpret_cast<float*>(smem + L::IN_HX);
-      for (int i = tid; i < E * 4; i += blockDim.x) {
-        const int e = i >> 2, k = i & 3;
-        hx[i] = (k < 3 && ch > 0) ? __ldg(xm + static_cast<size_t>(tile - 1) * E * kTok + static_cast<size_t>(e) * kTok + kTok - 3 + k) : 0.f;
-      }
+    const bool has_next = nxt < ntiles;
+    // one tile ahead: x_mlstm stage, halo and gate gradients of the next tile
+    if (has_next) {
+      if (tid == 0) issue_xm(nxt, s ^ 1);
+      load_halo(nxt, s ^ 1);
+      if (head == 0) load_dg(nxt, dgn);
     }
-    const int tau = ch * kTok + tok;
-    const bool valid = tau < g.S;
-    float dg[8];
-    if (head == 0) {
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const size_t o = (static_cast<size_t>(b) * 4 + h) * g.Sp + ch * kTok + tok;
-        dg[h] = valid ? __ldg(dig + o) : 0.f;
-        dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
-      }
-      uint4 hi, lo;
-      split8_hilo(dg, hi, lo);
-      *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 0)) = hi;
-      *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 0)) = lo;
-      *reinterpret_cast<uint4*>(smem + L::DGHI + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(smem + L::DGLO + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
-      warp_acc_vec<8>(par + L::A_GB, dg);       // gate bias gradients
-    }
-    fence_proxy_async();
-    mbar_wait(&bar_qkv, it & 1);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) {
-      // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
-      umma_gemm_hilo(tmem + L::T_GQ, smem_u32(smem + L::DGHI), smem_u32(smem + L::DGLO), kTok * 16, 128, smem_u32(smem + L::WGHI),
-                     smem_u32(smem + L::WGLO), 128, 16 * 16, umma_idesc(128, NQ, false, true), 16);
-      // d Wg[hh][j] += sum_tok [dig|dfg][tok][hh] qkv[tok][j]              (weight-gradient GEMM: plain bf16 operands)
-      umma_gemm(tmem + L::T_DWG, smem_u32(smem + L::DGHI), 128, kTok * 16, smem_u32(smem + L::QKV), 128, kTok * 16,
-                umma_idesc(128, NQ, true, true), kTok, it > 0);
-      umma_commit(&bar1);
-    }
-    mbar_wait(&bar_in, it & 1);
+    const bool valid = ch * kTok + tok < g.S;
+    mbar_wait(&bar_xm[s], (it >> 1) & 1);
     if (it > 0) {      // the previous tile's weight-gradient products still read the operand tiles this loop rewrites
       mbar_wait(&bar2, (it - 1) & 1);
       tc_fence_after();
     }
     const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;
-    bool mma1_pending = true;
+    const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE);
+    const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE + L::BLK);
+    const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
+    bool first = true;
 #pragma unroll
     for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
       const int d0 = e8 % DH;
       float a8[8], xm8[8], cv8[8], xr[4][8];
-      const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM);
-      const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_HX);
-      const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k (padding rows hold zeros)
 #pragma unroll
@@ -934,21 +942,21 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
-#pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int e = e8 + j;
         const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
         cv8[j] = par[L::P_CB + e] + w.x * xr[0][j] + w.y * xr[1][j] + w.z * xr[2][j] + w.w * xr[3][j];
         xm8[j] = xr[3][j];
       }
-      // everything above is independent of the first MMA group and overlaps it; the gate-path contribution is read from TMEM
-      if (mma1_pending) {
+      // everything above is independent of the gate-path UMMA and of d_act
+      if (first) {
         mbar_wait(&bar1, it & 1);
         tc_fence_after();
-        mma1_pending = false;
-        if (tid == 0 && nxt < ntiles) issue_qkv(nxt);     // the q|k|v tile has been consumed: stream in the next one
+        mbar_wait(&bar_da, it & 1);
+        first = false;
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
       float t8[8];
       tmem_ld8(tmem + lane_base + L::T_GQ + (0 * 4 + head) * DHP + d0, t8);
 #pragma unroll
@@ -988,7 +996,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
       }
       warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
       warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
-      // operands of the block-diagonal weight-gradient GEMMs (bf16)
+      // operands of the weight-gradient GEMMs (bf16)
       if (!valid) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
@@ -999,18 +1007,26 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
       *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(a8);
       *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(xm8);
     }
+    if (has_next && head == 0) stage_dg(dgn, s ^ 1);      // [dig|dfg] of the next tile (its buffer was last read two tiles ago)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
+      const uint32_t dgs = smem_u32(smem + L::DG0 + s * L::DG_STRIDE);
       // d[q_proj|k_proj] as a dense (2E x E) product g_{q|k}^T act; only its 4x4 diagonal blocks are read back
       umma_gemm(tmem + L::T_DWQK, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
                 umma_idesc(128, E, true, true), kTok, it > 0);
       umma_gemm(tmem + L::T_DWV, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16,
                 umma_idesc(128, E, true, true), kTok, it > 0);
+      // [dig|dfg]^T act and [dig|dfg]^T x_mlstm (rows hh = 0..7 of a 128-row window)
+      umma_gemm(tmem + L::T_DWGA, dgs, 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16, umma_idesc(128, E, true, true), kTok, it > 0);
+      umma_gemm(tmem + L::T_DWGX, dgs, 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16, umma_idesc(128, E, true, true), kTok, it > 0);
       umma_commit(&bar2);
-      if (nxt < ntiles) issue_in(nxt);      // x_mlstm / d_act blocks are free: stream in the next tile's
+      if (has_next) {
+        issue_mma1(tmem, s ^ 1);      // the gate-path accumulator has been drained by everybody (sync above)
+        issue_da(nxt);                // ... and so has the d_act block
+      }
     }
   }
   if (it > 0) {
@@ -1018,18 +1034,33 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     tc_fence_after();
   }
   // ---- flush the accumulated parameter gradients
-  // gate-weight gradient rows hh = 0..7 live in TMEM lanes 0..7: warps 0, 4, 8, 12 (quadrant 0) share the columns
+  // rows hh = 0..7 of the two gate reductions live in TMEM lanes 0..7: warps 0, 4, 8, 12 (quadrant 0) share the columns,
+  // 16 (= four 4x4 blocks) at a time; the block-diagonal projections are applied here
   if ((warp & 3) == 0) {
 #pragma unroll 1
-    for (int c0 = head * 16; c0 < NQ; c0 += 64) {
-      float v[16];
-      tmem_ld16(tmem + lane_base + L::T_DWG + c0, v);
+    for (int c0 = head * 16; c0 < E; c0 += 64) {
+      float ga[16], gx[16];
+      tmem_ld16(tmem + lane_base + L::T_DWGA + c0, ga);
+      tmem_ld16(tmem + lane_base + L::T_DWGX + c0, gx);
       if (tok < 8) {
         float* W = tok < 4 ? gr.igate_weight + tok * 3 * E : gr.fgate_weight + (tok - 4) * 3 * E;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int j = c0 + i, part = j / (4 * DHP), hd = (j / DHP) % 4, d = j % DHP;
-          if (d < DH) atomicAdd(W + part * E + hd * DH + d, v[i]);
+        for (int blk = 0; blk < 4; ++blk) {
+          const int wb = ((c0 >> 2) + blk) * 16;
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            float sq = 0.f, sk = 0.f, sv = 0.f;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              sq += par[L::P_WQ + wb + o * 4 + d] * ga[blk * 4 + d];
+              sk += par[L::P_WK + wb + o * 4 + d] * ga[blk * 4 + d];
+              sv += par[L::P_WV + wb + o * 4 + d] * gx[blk * 4 + d];
+            }
+            const int e_out = c0 + blk * 4 + o;
+            atomicAdd(W + 0 * E + e_out, sq);
+            atomicAdd(W + 1 * E + e_out, sk);
+            atomicAdd(W + 2 * E + e_out, sv);
+          }
         }
       }
     }
@@ -1084,9 +1115,8 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_A, st);
     const int ntiles = g.B * g.nc;
-    vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, xm, (const unsigned char*)q, (const unsigned char*)k,
-                                                                                  (const unsigned char*)v, dq, dk, dv, dig, dfg, d_act,
-                                                                                  ws_dconv, ws_dxmv, *gr, ntiles);
+    vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, xm, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv,
+                                                                                  *gr, ntiles);
   } else {
     // dim 64: the CUDA-core kernel A (recomputes the forward from x); TMEM cannot hold its gate products in one pass
     const size_t smem = PreBwdASmem<C>::TOTAL * sizeof(float);
