@@ -925,11 +925,18 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
       const int d0 = e8 % DH;
       float a8[8], xm8[8], cv8[8], xr[4][8];
+      // x_mlstm of tokens tau-3+k; only the first warp of a head group reaches into the halo in front of the chunk
+      if ((tok & ~31) != 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {       // x_mlstm of tokens tau-3+k (padding rows hold zeros)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
+          for (int j = 0; j < 8; ++j) xr[k][j] = s_xm[(e8 + j) * kTok + tok - 3 + k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
       }
       float gq[8], gk[8], gv[8], dsk[8];
       const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tok) * DHP + d0;
