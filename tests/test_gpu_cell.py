@@ -126,3 +126,19 @@ def test_cell_backward_long_multi_chunk_vs_oracle():
     for a, b, n in zip(got, emu, ("dq", "dk", "dv", "dig", "dfg")):
         print("adversarial", n, rel_l2(a, b))
         assert rel_l2(a, b) < 3e-2, n
+
+
+def test_cell_accepts_strided_head_views():
+    """The reference hands parallel_stabilized_simple transposed (B,S,NH,DH)->(B,NH,S,DH) views and (B,S,NH)->(B,NH,S,1)
+    gate views (vision_lstm.py:306-318): results must not depend on the memory layout of the arguments."""
+    from xlstm_hved_b200 import ops
+    torch.manual_seed(11)
+    B, S, NH, DH = 2, 300, 4, 16
+    q, k, v = (0.3 * torch.randn(B, S, NH * DH, device="cuda") for _ in range(3))
+    ig, fg = 0.2 * torch.randn(B, S, NH, device="cuda"), 4 + 0.3 * torch.randn(B, S, NH, device="cuda")
+    heads = lambda t: t.reshape(B, S, NH, DH).transpose(1, 2)
+    gate = lambda t: t.transpose(1, 2).unsqueeze(-1)
+    strided = ops.parallel_stabilized_simple(heads(q), heads(k), heads(v), gate(ig), gate(fg))
+    packed = ops.parallel_stabilized_simple(heads(q).contiguous(), heads(k).contiguous(), heads(v).contiguous(),
+                                            gate(ig).contiguous(), gate(fg).contiguous())
+    assert torch.equal(strided, packed)

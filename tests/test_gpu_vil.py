@@ -95,3 +95,63 @@ def test_vil_block_backward_bottleneck_vs_oracle():
     for a, b, k in zip(got[1:], ref[1:], keys):
         print(k, rel_l2(a, b))
         assert rel_l2(a, b) < 3e-2, k
+
+
+def _mirror_block_from_golden(name):
+    import xlstm_hved_b200 as xh
+    c = load_golden("vil_block.pt")[name]
+    dim = c["x"].shape[-1]
+    direction = xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT if c["reverse"] else xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT
+    blk = xh.ViLBlock(dim, direction)
+    blk.load_state_dict({k: v.float() for k, v in c["state_dict"].items()}, strict=True)
+    return blk.cuda(), c
+
+
+@pytest.mark.parametrize("name", ["dim32_s200_fwd", "dim32_s200_rev", "dim16_s150_fwd"])
+def test_inner_layer_standalone_matches_reference_block(name):
+    """SURVEY 8b entry point 3: the inner ViLLayer called on its own (vision_lstm.py:415-453).  x + layer(norm(x)) assembled
+    from the stand-alone sub-module forwards must reproduce the reference block output of the fixture."""
+    blk, c = _mirror_block_from_golden(name)
+    x = c["x"].float().cuda()
+    with torch.no_grad():
+        y = x + blk.layer(blk.norm(x))
+    br, br_ref = y.cpu().double() - c["x"], c["y"] - c["x"]
+    print(name, "stand-alone branch rel_l2", rel_l2(br, br_ref))
+    assert rel_l2(br, br_ref) < TOL_L2
+
+
+def test_matrix_lstm_cell_standalone_matches_oracle_and_backpropagates():
+    """SURVEY 8b entry point 4: MatrixLSTMCell.forward(q, k, v) (vision_lstm.py:302-339) against the oracle restatement."""
+    import xlstm_hved_b200 as xh
+    torch.manual_seed(3)
+    B, S, E, NH = 2, 300, 64, 4
+    cell = xh.modules.MatrixLSTMCell(E, NH)
+    with torch.no_grad():
+        cell.igate.weight.normal_(0, 0.05)
+        cell.fgate.weight.normal_(0, 0.05)
+        cell.outnorm.weight.normal_(0, 0.1)
+    q, k, v = (0.3 * torch.randn(B, S, E) for _ in range(3))
+    # oracle (fp64, CPU): gates -> parallel cell -> per-head norm
+    sd = {n: t.detach().double() for n, t in cell.state_dict().items()}
+    qkv = torch.cat([q, k, v], -1).double()
+    ig = (qkv @ sd["igate.weight"].T + sd["igate.bias"]).transpose(1, 2).unsqueeze(-1)
+    fg = (qkv @ sd["fgate.weight"].T + sd["fgate.bias"]).transpose(1, 2).unsqueeze(-1)
+    heads = lambda t: t.double().reshape(B, S, NH, E // NH).transpose(1, 2)
+    h_ref = restate.mlstm_parallel(heads(q), heads(k), heads(v), ig, fg)
+    ref = restate.multihead_layernorm(h_ref, sd["outnorm.weight"]).transpose(1, 2).reshape(B, S, E)
+    cell = cell.cuda()
+    qc, kc, vc = (t.cuda().requires_grad_() for t in (q, k, v))
+    out = cell(qc, kc, vc)
+    assert out.shape == (B, S, E)
+    print("cell stand-alone rel_l2", rel_l2(out, ref))
+    assert rel_l2(out, ref) < TOL_L2
+    out.square().sum().backward()
+    for t in (qc, kc, vc, cell.igate.weight, cell.fgate.bias, cell.outnorm.weight):
+        assert t.grad is not None and torch.isfinite(t.grad).all()
+
+
+def test_standalone_submodules_have_no_cpu_path():
+    import xlstm_hved_b200 as xh
+    lay = xh.modules.ViLLayer(32, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
+    with pytest.raises(RuntimeError):
+        lay(torch.zeros(1, 8, 32))

@@ -11,9 +11,14 @@ Reference classes mirrored (paths relative to the reference root):
   loss.py           : KL_divergence (29-40), compute_KLD (85-115)
 
 The containers below own the parameters exactly as the reference does, so ``load_state_dict(strict=True)``
-round-trips checkpoints of the reference modules.  Compute happens only at the fused entry points
-(ViLBlock / ViLLayer3D / parallel_stabilized_simple / ProductOfExperts(2) / reparametrize / compute_KLD); the
-small sub-modules are parameter holders and refuse to run stand-alone rather than fall back to PyTorch math.
+round-trips checkpoints of the reference modules.  The model path runs only through the fused entry points
+(ViLBlock / ViLLayer3D / parallel_stabilized_simple / ProductOfExperts(2) / reparametrize / compute_KLD).
+
+The sub-modules also keep the reference's stand-alone forwards (SURVEY 8b entry points 3 and 4: inner ``ViLLayer`` and
+``MatrixLSTMCell``): called on their own they run the S x S-shaped work -- the mLSTM cell -- through the same
+tcgen05 kernels (``xhved_mlstm_fwd/bwd``) and only the per-token glue around it (a (3E -> 4) gate Linear, the 4-tap conv,
+the 4x4 block projections, the norms) as device-side torch ops.  They need CUDA tensors and the built library like
+everything else here: there is no CPU path, and a fused ``ViLBlock`` never calls them.
 """
 from __future__ import annotations
 
@@ -23,7 +28,9 @@ from enum import Enum
 import torch
 from torch import nn
 
-from . import ops
+import torch.nn.functional as F
+
+from . import _lib, ops
 from .ops import SUBSETS_MODALITIES, parallel_stabilized_simple  # noqa: F401  (re-exported drop-in)
 
 
@@ -41,10 +48,16 @@ def _is_reverse(direction) -> bool:
     raise NotImplementedError(direction)       # vision_lstm.py:423-424
 
 
+def _require_device(*tensors):
+    """Stand-alone sub-module forwards are device-only, like the fused entry points."""
+    _lib.load_library()                                  # raises if libxhved.so has not been built
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("xlstm_hved_b200 has no CPU path")
+
+
 class _Holder(nn.Module):
-    def forward(self, *a, **k):
-        raise RuntimeError(f"{type(self).__name__} is a parameter holder of the fused ViL block; "
-                           "call ViLBlock / ViLLayer3D (there is no per-op PyTorch fallback)")
+    pass
 
 
 class LinearHeadwiseExpand(_Holder):
@@ -57,6 +70,13 @@ class LinearHeadwiseExpand(_Holder):
         self.bias = None
         nn.init.normal_(self.weight.data, mean=0.0, std=math.sqrt(2 / 5 / d))
 
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Block-diagonal linear (vision_lstm.py:159-165): every group of d channels is multiplied by its own d x d block."""
+        _require_device(x)
+        lead = x.shape[:-1]
+        xb = x.reshape(*lead, self.num_heads, self.dim // self.num_heads)
+        return torch.einsum("...hd,hod->...ho", xb, self.weight).reshape(*lead, self.dim)
+
 
 class CausalConv1d(_Holder):
     def __init__(self, dim, kernel_size=4, bias=True):
@@ -64,6 +84,12 @@ class CausalConv1d(_Holder):
         assert kernel_size == 4 and bias, "the fused kernel implements the reference's k=4, bias=True conv"
         self.dim, self.kernel_size, self.bias, self.pad = dim, kernel_size, bias, kernel_size - 1
         self.conv = nn.Conv1d(dim, dim, kernel_size=kernel_size, padding=self.pad, groups=dim, bias=bias)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Depthwise conv over the 3 previous tokens and the current one (vision_lstm.py:213-221); x: (B, S, dim)."""
+        _require_device(x)
+        xt = F.pad(x.transpose(1, 2), (self.pad, 0))              # left padding only == causal
+        return F.conv1d(xt, self.conv.weight, self.conv.bias, groups=self.dim).transpose(1, 2)
 
 
 class LayerNorm(_Holder):
@@ -74,9 +100,21 @@ class LayerNorm(_Holder):
         self.bias = None
         self.eps, self.residual_weight, self.ndim = eps, residual_weight, ndim
 
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """vision_lstm.py:258-268: layer norm over the last dim with weight 1 + w and no bias."""
+        _require_device(x)
+        return F.layer_norm(x, (self.ndim,), weight=1.0 + self.weight, bias=None, eps=self.eps)
+
 
 class MultiHeadLayerNorm(LayerNorm):
-    pass
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """vision_lstm.py:271-287: x (B, NH, S, DH) -> (B, S, NH*DH), every (token, head) normalised over DH."""
+        _require_device(x)
+        B, NH, S, DH = x.shape
+        xt = x.transpose(1, 2)                                      # (B, S, NH, DH)
+        xc = xt - xt.mean(dim=-1, keepdim=True)
+        xhat = xc * torch.rsqrt(xc.pow(2).mean(dim=-1, keepdim=True) + self.eps)
+        return (xhat * (1.0 + self.weight).view(NH, DH)).reshape(B, S, NH * DH)
 
 
 class MatrixLSTMCell(_Holder):
@@ -95,6 +133,19 @@ class MatrixLSTMCell(_Holder):
             self.fgate.bias.copy_(torch.linspace(3.0, 6.0, self.fgate.bias.shape[0]))
         nn.init.zeros_(self.igate.weight)
         nn.init.normal_(self.igate.bias, mean=0.0, std=0.1)
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+        """vision_lstm.py:302-339: gates from [q|k|v], heads split off the channel dim, stabilised cell, per-head norm.
+        The cell runs on the tcgen05 kernels (causal by construction: no S x S mask is built)."""
+        _require_device(q, k, v)
+        B, S, _ = q.shape
+        nh = self.num_heads
+        qkv = torch.cat([q, k, v], dim=-1)
+        ig = F.linear(qkv, self.igate.weight, self.igate.bias).transpose(1, 2).unsqueeze(-1)     # (B, NH, S, 1)
+        fg = F.linear(qkv, self.fgate.weight, self.fgate.bias).transpose(1, 2).unsqueeze(-1)
+        heads = lambda t: t.reshape(B, S, nh, -1).transpose(1, 2)                                 # (B, NH, S, DH)
+        h = ops.parallel_stabilized_simple(heads(q), heads(k), heads(v), ig, fg)
+        return self.outnorm(h)
 
 
 class ViLLayer(_Holder):
@@ -126,6 +177,19 @@ class ViLLayer(_Holder):
         for proj in (self.q_proj, self.k_proj, self.v_proj):
             nn.init.normal_(proj.weight, mean=0.0, std=math.sqrt(2 / (5 * self.dim)))
         self.mlstm_cell.reset_parameters()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Stand-alone inner layer (vision_lstm.py:415-453), x: (B, S, dim).  Inside a ViLBlock this is never called -- the
+        block runs the fused pre / cell / post kernels; here only the cell is a custom kernel."""
+        _require_device(x)
+        rev = _is_reverse(self.direction)
+        if rev:
+            x = x.flip(dims=[1])
+        x_mlstm, z = F.linear(x, self.proj_up.weight).chunk(2, dim=-1)
+        act = F.silu(self.conv1d(x_mlstm))
+        h = self.mlstm_cell(self.q_proj(act), self.k_proj(act), self.v_proj(x_mlstm))
+        y = F.linear((h + self.learnable_skip * act) * F.silu(z), self.proj_down.weight)
+        return y.flip(dims=[1]) if rev else y
 
 
 class DropPath(nn.Sequential):

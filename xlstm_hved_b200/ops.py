@@ -159,10 +159,13 @@ def mlstm_pack_inputs(q, k, v, ig, fg) -> CellBuffers:
     lib = _lib.load_library()
     B, NH, S, DH = q.shape
     buf = CellBuffers(B * NH, S, DH, q.device)
+    # contiguous copies of strided views (the reference hands over transposed head views) stay referenced until their
+    # kernel has been enqueued: a temporary freed earlier could be handed to the next allocation of this function
     for src, dst in ((q, buf.q), (k, buf.k), (v, buf.v)):
-        check(lib.xhved_mlstm_pack(ptr(_f32c(src)), buf.BH, S, DH, buf.dhp, ptr(dst), stream()), "xhved_mlstm_pack")
-    check(lib.xhved_mlstm_pack_gates(ptr(_f32c(ig)), ptr(_f32c(fg)), buf.BH, S, ptr(buf.ig), ptr(buf.fg), stream()),
-          "xhved_mlstm_pack_gates")
+        src_c = _f32c(src)
+        check(lib.xhved_mlstm_pack(ptr(src_c), buf.BH, S, DH, buf.dhp, ptr(dst), stream()), "xhved_mlstm_pack")
+    ig_c, fg_c = _f32c(ig), _f32c(fg)
+    check(lib.xhved_mlstm_pack_gates(ptr(ig_c), ptr(fg_c), buf.BH, S, ptr(buf.ig), ptr(buf.fg), stream()), "xhved_mlstm_pack_gates")
     return buf
 
 
@@ -237,7 +240,8 @@ class MLSTMCellFunction(torch.autograd.Function):
         buf = ctx.buf
         B, NH, S, DH = ctx.shape
         dh_tiles = torch.empty_like(buf.h)
-        check(lib.xhved_mlstm_pack(ptr(_f32c(dh)), buf.BH, S, DH, buf.dhp, ptr(dh_tiles), stream()), "xhved_mlstm_pack")
+        dh_c = _f32c(dh)
+        check(lib.xhved_mlstm_pack(ptr(dh_c), buf.BH, S, DH, buf.dhp, ptr(dh_tiles), stream()), "xhved_mlstm_pack")
         gb = mlstm_bwd_tiles(buf, dh_tiles, ctx.eps)
         dq = _unpad_rows(gb.dq, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
         dk = _unpad_rows(gb.dk, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
