@@ -197,8 +197,9 @@ class HotPath:
         for l in range(4):
             noise = torch.empty_like(self.gz[l]).normal_()                     # RA_HVED.py:743-744 semantics
             n = mu5[l][0].numel()
-            ops.poe_fwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, kld_out=self.kld[l:l + 1])
-            ops.poe_bwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, g_z=self.gz[l], kld_scale=[0.2 * 0.5 / n / 4])
+            # slab 0 is the model's constant prior (mu = 0, logvar = 0, RA_HVED.py:576-580): declared, not read
+            ops.poe_fwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, kld_out=self.kld[l:l + 1], standard_prior=True)
+            ops.poe_bwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, g_z=self.gz[l], kld_scale=[0.2 * 0.5 / n / 4], standard_prior=True)
         kld_total = torch.dot(self.kld, self.kld_w)                            # mean KL over the 4 levels (train.py:236-239)
         # ---- ViL block pair on the NCDHW feature (token view, no transposed copies), forward + backward
         x = sl["x"].detach().requires_grad_()
@@ -334,7 +335,9 @@ def run_gpu(args):
     }
     bytes_per_launch = {k: v * tokens for k, v in per_token_bytes.items()}
     bytes_per_launch.update({k: v * tokens_heads for k, v in per_tokenhead_bytes.items()})
-    bytes_per_step = {"poe_fwd": n_lat * (40 + 4 + 12), "poe_bwd": n_lat * (40 + 4 + 4 + 40)}   # the 4 level launches of a step together
+    # PoE per latent element: 4 x (mu, logvar) in (the constant prior is never read) + noise; mu^, logvar^, z out;
+    # backward: the same 32 B + noise + g_z in, 32 B of gradients out.  The 4 level launches of a step together.
+    bytes_per_step = {"poe_fwd": n_lat * (32 + 4 + 12), "poe_bwd": n_lat * (32 + 4 + 4 + 32)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
 

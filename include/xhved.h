@@ -50,17 +50,23 @@ int xhved_version(void);
  * noise/out_z (optional, (n_subsets, n)): z = out_mu + noise * exp(0.5 out_logvar) (RA_HVED.py:741-747).
  * kld_out (optional, device float[n_subsets], must be zeroed by the caller): accumulates
  *   sum over elements of (-1 - lv + (exp(lv) + mu^2)/(1+1e-8)); the caller scales by 0.5/n (loss.py:29-40).
- * subset_masks is a HOST array of n_subsets (<= 15) entries. */
+ * subset_masks is a HOST array of n_subsets (<= 15) entries.
+ * flags: XHVED_POE_STANDARD_PRIOR = the caller guarantees that expert 0 is the standard normal the model always passes
+ *   (mu = 0, logvar = 0, RA_HVED.py:576-580): its slabs are then never read (T_0 = 1/(1+eps)); mu / logvar still point
+ *   at the position slab 0 would have (expert e at base + e*expert_stride). */
+#define XHVED_POE_STANDARD_PRIOR 1
 int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
                   int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, float* out_mu, float* out_logvar,
-                  const float* noise, float* out_z, float* kld_out, void* stream);
+                  const float* noise, float* out_z, float* kld_out, int flags, void* stream);
 
 /* Backward of xhved_poe_fwd (optionally through z and the KL term): g_mu, g_logvar, g_z (each optional,
  * (n_subsets, n)); kld_scale[s] (host, optional) = dLoss/d(kld_out[s]).  Writes d_mu, d_logvar (5, n)
- * at stride expert_stride (summed over subsets; the prior slot receives its gradient too). */
+ * at stride expert_stride (summed over subsets; the prior slot receives its gradient too -- unless
+ * XHVED_POE_STANDARD_PRIOR is set: then slab 0 is neither read nor written). */
 int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
                   int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, const float* g_mu, const float* g_logvar,
-                  const float* noise, const float* g_z, const float* kld_scale, float* d_mu, float* d_logvar, void* stream);
+                  const float* noise, const float* g_z, const float* kld_scale, float* d_mu, float* d_logvar, int flags,
+                  void* stream);
 
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);

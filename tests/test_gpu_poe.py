@@ -130,3 +130,27 @@ def test_product_of_experts2_mutates_mu_like_the_reference():
     a, b = xh.ProductOfExperts2()(mu_c, lv.float().cuda(), c["drop"].cuda())
     assert rel_linf(a, c["drop_pd_mu"]) < TOL and rel_linf(b, c["drop_pd_logvar"]) < TOL
     assert torch.equal(mu_c.cpu().double(), c["drop_mu_after"].float().double())      # buildingblocks.py:879-881
+
+
+@pytest.mark.parametrize("n_extra", [0, 3])          # 128-bit and scalar code paths
+def test_poe_standard_prior_flag_equals_explicit_zero_prior(n_extra):
+    """XHVED_POE_STANDARD_PRIOR: the constant prior (mu = 0, logvar = 0, RA_HVED.py:576-580) is declared instead of read.
+    The slab is filled with NaN here to prove that it is not touched; results must equal the explicit-zero-prior call."""
+    from xlstm_hved_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n = 4 * 1000 + n_extra
+    mod_mu, mod_lv = 1.3 * torch.randn(4, n, generator=g), (1.4 * torch.randn(4, n, generator=g)).clamp(-50, 50)
+    zeros, nans = torch.zeros(1, n), torch.full((1, n), float("nan"))
+    subsets = [(0, 1, 2, 3), (1, 3), (2,)]
+    noise, gz = torch.randn(3, n, generator=g).cuda(), torch.randn(3, n, generator=g).cuda()
+    ks = [0.3, -0.2, 0.1]
+    ref_mu, ref_lv = torch.cat([zeros, mod_mu]).cuda(), torch.cat([zeros, mod_lv]).cuda()
+    nan_mu, nan_lv = torch.cat([nans, mod_mu]).cuda(), torch.cat([nans, mod_lv]).cuda()
+    a = ops.poe_fwd(ref_mu, ref_lv, subsets, noise=noise, want_kld=True)
+    b = ops.poe_fwd(nan_mu, nan_lv, subsets, noise=noise, want_kld=True, standard_prior=True)
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)
+    assert torch.allclose(a[3], b[3], rtol=1e-5)          # KL sums: block atomics, summation order is not fixed
+    dmu, dlv = ops.poe_bwd(ref_mu, ref_lv, subsets, noise=noise, g_z=gz, kld_scale=ks)
+    dmu4, dlv4 = ops.poe_bwd(nan_mu, nan_lv, subsets, noise=noise, g_z=gz, kld_scale=ks, standard_prior=True)
+    assert dmu4.shape == (4, n) and torch.equal(dmu[1:], dmu4) and torch.equal(dlv[1:], dlv4)

@@ -40,9 +40,9 @@ class VilShape(Structure):
 SYMBOLS = {
     "xhved_version": [],
     "xhved_poe_fwd": [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint32), c_int, c_void_p, c_int64, c_float, c_void_p,
-                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "xhved_poe_bwd": [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint32), c_int, c_void_p, c_int64, c_float, c_void_p,
-                      c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_void_p],
+                      c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int, c_void_p],
     "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,

@@ -56,7 +56,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int V, int NS>
+// SP: expert 0 is the constant standard-normal prior and is not read (XHVED_POE_STANDARD_PRIOR)
+template <int V, int NS, bool SP>
 __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t n,
                                                        int64_t stride, PoeSubsets ss, const uint8_t* __restrict__ drop,
                                                        int64_t per_sample, float eps, float* __restrict__ out_mu,
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
        iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t i = iv * V;
     float T[5][V], M[5][V], Lv[5][V];
-    uint32_t live = (ss.used << 1) | 1u;       // bit e = expert e must be read (the prior always)
+    uint32_t live = (ss.used << 1) | (SP ? 0u : 1u);       // bit e = expert e must be read
     if (drop) {
       const uint8_t* d = drop + (i / per_sample) * 4;
       const uint32_t dropbits = (d[0] ? 1u : 0u) | (d[1] ? 2u : 0u) | (d[2] ? 4u : 0u) | (d[3] ? 8u : 0u);
@@ -91,6 +92,10 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
       const bool on = (live >> e) & 1u;
 #pragma unroll
       for (int j = 0; j < V; ++j) T[e][j] = on ? __fdividef(1.0f, __expf(Lv[e][j]) + eps) : 0.f;
+    }
+    if (SP) {       // mu_0 = 0, logvar_0 = 0 without reading them
+#pragma unroll
+      for (int j = 0; j < V; ++j) T[0][j] = __fdividef(1.0f, 1.0f + eps);
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -141,8 +146,8 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
   }
 }
 
-template <int V, int NS>
-__global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t n,
+template <int V, int NS, bool SP>
+__global__ void __launch_bounds__(256, (NS <= 4 ? 2 : 1)) poe_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t n,
                                                        int64_t stride, PoeSubsets ss, const uint8_t* __restrict__ drop,
                                                        int64_t per_sample, float eps, const float* __restrict__ g_mu,
                                                        const float* __restrict__ g_lv, const float* __restrict__ noise,
@@ -161,8 +166,13 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ 
     // all loads first, then the arithmetic
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
-      ld<V>(mu + e * stride + i, M[e]);
-      ld<V>(lv + e * stride + i, EL[e]);
+      if (e == 0 && SP) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) M[0][j] = 0.f, EL[0][j] = 0.f;
+      } else {
+        ld<V>(mu + e * stride + i, M[e]);
+        ld<V>(lv + e * stride + i, EL[e]);
+      }
     }
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
@@ -229,6 +239,7 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const float* __restrict__ 
     }
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
+      if (e == 0 && SP) continue;
       float dl[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) dl[j] = -dT[e][j] * T[e][j] * T[e][j] * EL[e][j];
@@ -305,8 +316,9 @@ extern "C" int xhved_version(void) { return 100; }
 
 extern "C" int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
                              int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, float* out_mu, float* out_logvar,
-                             const float* noise, float* out_z, float* kld_out, void* stream) {
+                             const float* noise, float* out_z, float* kld_out, int flags, void* stream) {
   if (n <= 0 || expert_stride < n || !mu || !logvar || !out_mu || !out_logvar) return XHVED_ERR_BAD_ARG;
+  const int std_prior = (flags & XHVED_POE_STANDARD_PRIOR) ? 1 : 0;
   if ((out_z != nullptr) != (noise != nullptr)) return XHVED_ERR_BAD_ARG;
   if (drop && (per_sample <= 0 || n % per_sample)) return XHVED_ERR_BAD_SHAPE;
   PoeSubsets ss;
@@ -316,7 +328,14 @@ extern "C" int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, in
                   aligned16(out_mu) && aligned16(out_logvar) && (!noise || (aligned16(noise) && aligned16(out_z)));
   ProfScope ps(K_POE_FWD, st_);
 #define XHVED_POE_FWD(V, NS, GRID) \
-  poe_fwd_kernel<V, NS><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar, noise, out_z, kld_out)
+  do {                                                                                                                             \
+    if (std_prior)                                                                                                                 \
+      poe_fwd_kernel<V, NS, true><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar, \
+                                                         noise, out_z, kld_out);                                                  \
+    else                                                                                                                           \
+      poe_fwd_kernel<V, NS, false><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar, \
+                                                          noise, out_z, kld_out);                                                 \
+  } while (0)
   if (v4) {
     if (n_subsets == 1) XHVED_POE_FWD(4, 1, grid_for(n / 4));
     else if (n_subsets <= 4) XHVED_POE_FWD(4, 4, grid_for(n / 4));
@@ -331,8 +350,10 @@ extern "C" int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, in
 
 extern "C" int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
                              int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, const float* g_mu, const float* g_logvar,
-                             const float* noise, const float* g_z, const float* kld_scale, float* d_mu, float* d_logvar, void* stream) {
+                             const float* noise, const float* g_z, const float* kld_scale, float* d_mu, float* d_logvar, int flags,
+                             void* stream) {
   if (n <= 0 || expert_stride < n || !mu || !logvar || !d_mu || !d_logvar) return XHVED_ERR_BAD_ARG;
+  const int std_prior = (flags & XHVED_POE_STANDARD_PRIOR) ? 1 : 0;
   if (g_z && !noise) return XHVED_ERR_BAD_ARG;
   if (drop && (per_sample <= 0 || n % per_sample)) return XHVED_ERR_BAD_SHAPE;
   PoeSubsets ss;
@@ -343,8 +364,14 @@ extern "C" int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, in
                   (!g_z || (aligned16(g_z) && aligned16(noise)));
   ProfScope ps(K_POE_BWD, st_);
 #define XHVED_POE_BWD(V, NS, GRID)                                                                                                  \
-  poe_bwd_kernel<V, NS><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise, g_z, \
-                                               kld_scale != nullptr, d_mu, d_logvar)
+  do {                                                                                                                              \
+    if (std_prior)                                                                                                                  \
+      poe_bwd_kernel<V, NS, true><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise, \
+                                                         g_z, kld_scale != nullptr, d_mu, d_logvar);                                \
+    else                                                                                                                            \
+      poe_bwd_kernel<V, NS, false><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise, \
+                                                          g_z, kld_scale != nullptr, d_mu, d_logvar);                               \
+  } while (0)
   if (v4) {
     if (n_subsets == 1) XHVED_POE_BWD(4, 1, grid_for(n / 4));
     else if (n_subsets <= 4) XHVED_POE_BWD(4, 4, grid_for(n / 4));

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_float, c_uint32
+from ctypes import c_float, c_uint32, c_void_p
 
 import torch
 
@@ -49,12 +49,17 @@ def _masks(subsets):
     return arr
 
 
+POE_STANDARD_PRIOR = 1        # include/xhved.h: XHVED_POE_STANDARD_PRIOR
+
+
 def poe_fwd(mu5: torch.Tensor, logvar5: torch.Tensor, subsets, drop=None, noise=None, want_kld=False, eps: float = 1e-8,
-            kld_out=None):
+            kld_out=None, standard_prior: bool = False):
     """All requested subsets in one launch.  mu5/logvar5: (5, ...) fp32 contiguous (prior first).
     Returns (pd_mu, pd_logvar, z or None, kld_sums or None) each of shape (len(subsets), ...).
     kld_out: optional pre-zeroed fp32 buffer of len(subsets) elements the KL sums are accumulated into (lets a caller
-    collect the sums of several latent levels in one tensor)."""
+    collect the sums of several latent levels in one tensor).
+    standard_prior: the caller guarantees that slab 0 is the model's constant prior (mu = 0, logvar = 0,
+    RA_HVED.py:576-580); the kernel then does not read it (20 % fewer input bytes)."""
     lib = _lib.load_library()
     assert mu5.shape == logvar5.shape and mu5.shape[0] == 5
     mu5, logvar5 = _f32c(mu5), _f32c(logvar5)
@@ -76,11 +81,15 @@ def poe_fwd(mu5: torch.Tensor, logvar5: torch.Tensor, subsets, drop=None, noise=
         noise = _f32c(noise)
         assert noise.numel() == ns * n
     check(lib.xhved_poe_fwd(ptr(mu5), ptr(logvar5), n, n, _masks(subsets), ns, ptr(drop), per_sample, eps, ptr(out_mu),
-                            ptr(out_lv), ptr(noise), ptr(z), ptr(kld), stream()), "xhved_poe_fwd")
+                            ptr(out_lv), ptr(noise), ptr(z), ptr(kld), POE_STANDARD_PRIOR if standard_prior else 0, stream()),
+          "xhved_poe_fwd")
     return out_mu, out_lv, z, kld
 
 
-def poe_bwd(mu5, logvar5, subsets, g_mu=None, g_logvar=None, noise=None, g_z=None, kld_scale=None, drop=None, eps: float = 1e-8):
+def poe_bwd(mu5, logvar5, subsets, g_mu=None, g_logvar=None, noise=None, g_z=None, kld_scale=None, drop=None, eps: float = 1e-8,
+            standard_prior: bool = False):
+    """Gradients of poe_fwd w.r.t. the expert slabs.  Returns (d_mu, d_logvar) of shape (5, ...); with standard_prior=True
+    the constant prior slab is neither read nor given a gradient and the results have shape (4, ...) (modalities only)."""
     lib = _lib.load_library()
     mu5, logvar5 = _f32c(mu5), _f32c(logvar5)
     n = mu5[0].numel()
@@ -99,8 +108,10 @@ def poe_bwd(mu5, logvar5, subsets, g_mu=None, g_logvar=None, noise=None, g_z=Non
     g_z = _f32c(g_z) if g_z is not None else None
     noise = _f32c(noise) if noise is not None else None
     check(lib.xhved_poe_bwd(ptr(mu5), ptr(logvar5), n, n, _masks(subsets), ns, ptr(drop), per_sample, eps, ptr(g_mu), ptr(g_logvar),
-                            ptr(noise), ptr(g_z), ks, ptr(d_mu), ptr(d_lv), stream()), "xhved_poe_bwd")
-    return d_mu, d_lv
+                            ptr(noise), ptr(g_z), ks, ptr(d_mu), ptr(d_lv), POE_STANDARD_PRIOR if standard_prior else 0, stream()),
+          "xhved_poe_bwd")
+    # with a standard prior slab 0 is never written: hand back the modality slabs only
+    return (d_mu[1:], d_lv[1:]) if standard_prior else (d_mu, d_lv)
 
 
 def reparam_fwd(mu, logvar, noise):
