@@ -152,6 +152,7 @@ class HotPath:
         self.copy_stream = torch.cuda.Stream(device=device)
         self.kld = torch.zeros(4, device=device)                                 # per-level KL sums of a step
         self.kld_w = torch.tensor([0.5 / (B * C * d ** 3) / 4 for C, d in LEVELS], device=device)
+        self.kld_scales = [[0.2 * 0.5 / (B * C * d ** 3) / 4] for C, d in LEVELS]     # d loss / d kld_sum per level (weight 0.2)
 
     def load(self, x, mus, lvs, slot=0):
         """Copy one batch into the device buffers of `slot` (H2D when the sources are pinned host tensors) on the copy
@@ -194,12 +195,12 @@ class HotPath:
         mu5, lv5 = sl["mu5"], sl["lv5"]
         # ---- S-MVAE: fusion + sampling + KL in one launch per level, backward in one launch per level
         self.kld.zero_()
-        for l in range(4):
-            noise = torch.empty_like(self.gz[l]).normal_()                     # RA_HVED.py:743-744 semantics
-            n = mu5[l][0].numel()
-            # slab 0 is the model's constant prior (mu = 0, logvar = 0, RA_HVED.py:576-580): declared, not read
-            ops.poe_fwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, kld_out=self.kld[l:l + 1], standard_prior=True)
-            ops.poe_bwd(mu5[l], lv5[l], [SUBSET_FULL], noise=noise, g_z=self.gz[l], kld_scale=[0.2 * 0.5 / n / 4], standard_prior=True)
+        noises = [torch.empty_like(self.gz[l]).normal_() for l in range(4)]    # RA_HVED.py:743-744 semantics, one draw per level
+        levels = list(zip(mu5, lv5))
+        # the four latent levels ride in one launch; slab 0 is the model's constant prior (mu = 0, logvar = 0,
+        # RA_HVED.py:576-580): declared, not read
+        ops.poe_fwd_levels(levels, [SUBSET_FULL], noises=noises, kld_out=self.kld.view(4, 1), standard_prior=True)
+        ops.poe_bwd_levels(levels, [SUBSET_FULL], noises=noises, g_zs=self.gz, kld_scales=self.kld_scales, standard_prior=True)
         kld_total = torch.dot(self.kld, self.kld_w)                            # mean KL over the 4 levels (train.py:236-239)
         # ---- ViL block pair on the NCDHW feature (token view, no transposed copies), forward + backward
         x = sl["x"].detach().requires_grad_()
@@ -336,7 +337,7 @@ def run_gpu(args):
     bytes_per_launch = {k: v * tokens for k, v in per_token_bytes.items()}
     bytes_per_launch.update({k: v * tokens_heads for k, v in per_tokenhead_bytes.items()})
     # PoE per latent element: 4 x (mu, logvar) in (the constant prior is never read) + noise; mu^, logvar^, z out;
-    # backward: the same 32 B + noise + g_z in, 32 B of gradients out.  The 4 level launches of a step together.
+    # backward: the same 32 B + noise + g_z in, 32 B of gradients out.  One launch per step covers the 4 latent levels.
     bytes_per_step = {"poe_fwd": n_lat * (32 + 4 + 12), "poe_bwd": n_lat * (32 + 4 + 4 + 32)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
@@ -347,7 +348,7 @@ def run_gpu(args):
             ach = bytes_per_step[name] / (ms / K * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": round(ach / peaks["hbm"], 4), "traffic": traffic.get(name), "algorithmic_bytes_per_step": bytes_per_step[name],
-                    "ms_per_step": round(ms / K, 5), "peak_source": peaks["src"], "note": "4 launches per step (one per latent level)"}
+                    "ms_per_step": round(ms / K, 5), "peak_source": peaks["src"], "note": "one launch per step covers the four latent levels"}
         if name not in bytes_per_launch:
             return {"kernel": name, "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
                     "avg_launch_ms": round(ms / cnt, 5)}

@@ -68,6 +68,41 @@ int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, int64_t exper
                   const float* noise, const float* g_z, const float* kld_scale, float* d_mu, float* d_logvar, int flags,
                   void* stream);
 
+/* Several latent levels in ONE launch (the four latent resolutions of a volume, RA_HVED.py:567-605: the small levels are
+ * latency-bound on their own).  Every field has the meaning of the xhved_poe_fwd / xhved_poe_bwd argument of the same name;
+ * subsets, eps and flags are shared by the levels.  kld_scale is a HOST array of n_subsets floats per level (or NULL). */
+#define XHVED_POE_MAX_LEVELS 4
+typedef struct {
+  const float* mu;
+  const float* logvar;
+  int64_t n, expert_stride;
+  const uint8_t* drop;
+  int64_t per_sample;
+  float* out_mu;
+  float* out_logvar;
+  const float* noise;
+  float* out_z;
+  float* kld_out;
+} xhved_poe_level;
+typedef struct {
+  const float* mu;
+  const float* logvar;
+  int64_t n, expert_stride;
+  const uint8_t* drop;
+  int64_t per_sample;
+  const float* g_mu;
+  const float* g_logvar;
+  const float* noise;
+  const float* g_z;
+  const float* kld_scale;
+  float* d_mu;
+  float* d_logvar;
+} xhved_poe_level_grad;
+int xhved_poe_fwd_levels(const xhved_poe_level* levels, int n_levels, const uint32_t* subset_masks, int n_subsets, float eps,
+                         int flags, void* stream);
+int xhved_poe_bwd_levels(const xhved_poe_level_grad* levels, int n_levels, const uint32_t* subset_masks, int n_subsets, float eps,
+                         int flags, void* stream);
+
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
 int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);

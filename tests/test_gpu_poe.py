@@ -154,3 +154,30 @@ def test_poe_standard_prior_flag_equals_explicit_zero_prior(n_extra):
     dmu, dlv = ops.poe_bwd(ref_mu, ref_lv, subsets, noise=noise, g_z=gz, kld_scale=ks)
     dmu4, dlv4 = ops.poe_bwd(nan_mu, nan_lv, subsets, noise=noise, g_z=gz, kld_scale=ks, standard_prior=True)
     assert dmu4.shape == (4, n) and torch.equal(dmu[1:], dmu4) and torch.equal(dlv[1:], dlv4)
+
+
+def test_poe_levels_one_launch_equals_per_level_launches():
+    """xhved_poe_fwd_levels / _bwd_levels: the four latent levels of a volume in one launch (shapes of SURVEY appendix A,
+    plus a ragged level that forces the scalar path) must give exactly what four separate launches give."""
+    from xlstm_hved_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    subsets = [(0, 1, 2, 3), (0, 2)]
+    for shapes in ([(2, 1, 16, 16, 16), (2, 2, 8, 8, 8), (2, 4, 4, 4, 4), (2, 8, 2, 2, 2)], [(1, 3, 5, 7), (2, 4, 4, 4)]):
+        levels, noises, gzs, scales = [], [], [], []
+        for sh in shapes:
+            mu = torch.cat([torch.zeros(1, *sh), 1.3 * torch.randn(4, *sh, generator=g)]).cuda()
+            lv = torch.cat([torch.zeros(1, *sh), (1.4 * torch.randn(4, *sh, generator=g)).clamp(-50, 50)]).cuda()
+            levels.append((mu, lv))
+            noises.append(torch.randn(2, *sh, generator=g).cuda())
+            gzs.append(torch.randn(2, *sh, generator=g).cuda())
+            scales.append([0.3, -0.1])
+        for sp in (False, True):
+            kld = torch.zeros(len(shapes), 2, device="cuda")
+            outs = ops.poe_fwd_levels(levels, subsets, noises=noises, kld_out=kld, standard_prior=sp)
+            grads = ops.poe_bwd_levels(levels, subsets, noises=noises, g_zs=gzs, kld_scales=scales, standard_prior=sp)
+            for l, (mu, lv) in enumerate(levels):
+                pm, pl, z, k1 = ops.poe_fwd(mu, lv, subsets, noise=noises[l], want_kld=True, standard_prior=sp)
+                assert torch.equal(outs[l][0], pm) and torch.equal(outs[l][1], pl) and torch.equal(outs[l][2], z)
+                assert torch.allclose(kld[l], k1, rtol=1e-5)
+                dmu, dlv = ops.poe_bwd(mu, lv, subsets, noise=noises[l], g_z=gzs[l], kld_scale=scales[l], standard_prior=sp)
+                assert torch.equal(grads[l][0], dmu) and torch.equal(grads[l][1], dlv)

@@ -36,6 +36,18 @@ class VilShape(Structure):
                 ("grad_replicas", c_int), ("grad_replica_stride", c_int64)]
 
 
+class PoeLevel(Structure):            # xhved_poe_level
+    _fields_ = [("mu", c_void_p), ("logvar", c_void_p), ("n", c_int64), ("expert_stride", c_int64), ("drop", c_void_p),
+                ("per_sample", c_int64), ("out_mu", c_void_p), ("out_logvar", c_void_p), ("noise", c_void_p), ("out_z", c_void_p),
+                ("kld_out", c_void_p)]
+
+
+class PoeLevelGrad(Structure):        # xhved_poe_level_grad
+    _fields_ = [("mu", c_void_p), ("logvar", c_void_p), ("n", c_int64), ("expert_stride", c_int64), ("drop", c_void_p),
+                ("per_sample", c_int64), ("g_mu", c_void_p), ("g_logvar", c_void_p), ("noise", c_void_p), ("g_z", c_void_p),
+                ("kld_scale", POINTER(c_float)), ("d_mu", c_void_p), ("d_logvar", c_void_p)]
+
+
 # every symbol include/xhved.h declares -> argtypes (None = not yet bound with a signature)
 SYMBOLS = {
     "xhved_version": [],
@@ -43,6 +55,8 @@ SYMBOLS = {
                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "xhved_poe_bwd": [c_void_p, c_void_p, c_int64, c_int64, POINTER(c_uint32), c_int, c_void_p, c_int64, c_float, c_void_p,
                       c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int, c_void_p],
+    "xhved_poe_fwd_levels": [POINTER(PoeLevel), c_int, POINTER(c_uint32), c_int, c_float, c_int, c_void_p],
+    "xhved_poe_bwd_levels": [POINTER(PoeLevelGrad), c_int, POINTER(c_uint32), c_int, c_float, c_int, c_void_p],
     "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,

@@ -21,6 +21,62 @@ struct PoeSubsets {
   uint32_t used;  // union of masks: which modality slabs must be loaded
 };
 
+// One latent level of a launch.  A launch covers up to four levels (the four latent resolutions of a volume): the small
+// levels are latency-bound on their own, so they ride along with the big one.  blk_end[l] = first block of level l+1.
+struct PoeLevelF {
+  const float* mu;
+  const float* lv;
+  int64_t n, stride;
+  const uint8_t* drop;
+  int64_t per_sample;
+  float* out_mu;
+  float* out_lv;
+  const float* noise;
+  float* out_z;
+  float* kld_out;
+};
+struct PoeFwdArgs {
+  PoeLevelF lev[4];
+  int blk_end[4];
+  int nlev;
+};
+struct PoeLevelB {
+  const float* mu;
+  const float* lv;
+  int64_t n, stride;
+  const uint8_t* drop;
+  int64_t per_sample;
+  const float* g_mu;
+  const float* g_lv;
+  const float* noise;
+  const float* g_z;
+  float* d_mu;
+  float* d_lv;
+  int use_kld;
+  float kld_scale[15];
+};
+struct PoeBwdArgs {
+  PoeLevelB lev[4];
+  int blk_end[4];
+  int nlev;
+};
+// level of this block (selects instead of dynamic indexing into the parameter space)
+template <typename Args, typename Level>
+__device__ __forceinline__ void select_level(const Args& a, Level& L, int& blk0, int& nblk) {
+  L = a.lev[0];
+  blk0 = 0;
+  int end = a.blk_end[0];
+#pragma unroll
+  for (int l = 1; l < 4; ++l) {
+    if (l < a.nlev && static_cast<int>(blockIdx.x) >= a.blk_end[l - 1]) {
+      L = a.lev[l];
+      blk0 = a.blk_end[l - 1];
+      end = a.blk_end[l];
+    }
+  }
+  nblk = end - blk0;
+}
+
 template <int V>
 struct Vec;
 template <>
@@ -58,17 +114,25 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // SP: expert 0 is the constant standard-normal prior and is not read (XHVED_POE_STANDARD_PRIOR)
 template <int V, int NS, bool SP>
-__global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t n,
-                                                       int64_t stride, PoeSubsets ss, const uint8_t* __restrict__ drop,
-                                                       int64_t per_sample, float eps, float* __restrict__ out_mu,
-                                                       float* __restrict__ out_lv, const float* __restrict__ noise,
-                                                       float* __restrict__ out_z, float* __restrict__ kld_out) {
+__global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, const PoeSubsets ss, const float eps) {
+  PoeLevelF L;
+  int blk0, nblk;
+  select_level(args, L, blk0, nblk);
+  const float* __restrict__ mu = L.mu;
+  const float* __restrict__ lv = L.lv;
+  const int64_t n = L.n, stride = L.stride, per_sample = L.per_sample;
+  const uint8_t* __restrict__ drop = L.drop;
+  float* __restrict__ out_mu = L.out_mu;
+  float* __restrict__ out_lv = L.out_lv;
+  const float* __restrict__ noise = L.noise;
+  float* __restrict__ out_z = L.out_z;
+  float* __restrict__ kld_out = L.kld_out;
   float kld_acc[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) kld_acc[s] = 0.f;
   const int64_t nvec = n / V;
-  for (int64_t iv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
-       iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  for (int64_t iv = (blockIdx.x - blk0) * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
+       iv += static_cast<int64_t>(nblk) * blockDim.x) {
     const int64_t i = iv * V;
     float T[5][V], M[5][V], Lv[5][V];
     uint32_t live = (ss.used << 1) | (SP ? 0u : 1u);       // bit e = expert e must be read
@@ -147,15 +211,24 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const float* __restrict__ 
 }
 
 template <int V, int NS, bool SP>
-__global__ void __launch_bounds__(256, (NS <= 4 ? 2 : 1)) poe_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t n,
-                                                       int64_t stride, PoeSubsets ss, const uint8_t* __restrict__ drop,
-                                                       int64_t per_sample, float eps, const float* __restrict__ g_mu,
-                                                       const float* __restrict__ g_lv, const float* __restrict__ noise,
-                                                       const float* __restrict__ g_z, int use_kld, float* __restrict__ d_mu,
-                                                       float* __restrict__ d_lv) {
+__global__ void __launch_bounds__(256, (NS <= 4 ? 2 : 1)) poe_bwd_kernel(const PoeBwdArgs args, const PoeSubsets ss, const float eps) {
+  PoeLevelB L;
+  int blk0, nblk;
+  select_level(args, L, blk0, nblk);
+  const float* __restrict__ mu = L.mu;
+  const float* __restrict__ lv = L.lv;
+  const int64_t n = L.n, stride = L.stride, per_sample = L.per_sample;
+  const uint8_t* __restrict__ drop = L.drop;
+  const float* __restrict__ g_mu = L.g_mu;
+  const float* __restrict__ g_lv = L.g_lv;
+  const float* __restrict__ noise = L.noise;
+  const float* __restrict__ g_z = L.g_z;
+  float* __restrict__ d_mu = L.d_mu;
+  float* __restrict__ d_lv = L.d_lv;
+  const int use_kld = L.use_kld;
   const int64_t nvec = n / V;
-  for (int64_t iv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
-       iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  for (int64_t iv = (blockIdx.x - blk0) * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
+       iv += static_cast<int64_t>(nblk) * blockDim.x) {
     const int64_t i = iv * V;
     float T[5][V], M[5][V], EL[5][V], dM[5][V], dT[5][V];
     uint32_t dropbits = 0;
@@ -224,7 +297,7 @@ __global__ void __launch_bounds__(256, (NS <= 4 ? 2 : 1)) poe_bwd_kernel(const f
             b += gz[j] * nz[j] * 0.5f * __expf(0.5f * lh);
           }
           if (use_kld) {
-            const float ks = ss.kld_scale[s];
+            const float ks = L.kld_scale[s];
             a += ks * 2.0f * mh;                       // / (1 + 1e-8) == 1 in fp32
             b += ks * (-1.0f + __expf(lh));
           }
@@ -296,92 +369,166 @@ static int grid_for(int64_t nvec) {
   return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
-static int fill_subsets(PoeSubsets& ss, const uint32_t* masks, int n_subsets, const float* kld_scale) {
+static int fill_subsets(PoeSubsets& ss, const uint32_t* masks, int n_subsets) {
   if (n_subsets < 1 || n_subsets > 15 || !masks) return XHVED_ERR_BAD_ARG;
   ss.n = n_subsets;
   ss.used = 0;
   for (int s = 0; s < 15; ++s) {
     ss.mask[s] = s < n_subsets ? (masks[s] & 15u) : 0u;
-    ss.kld_scale[s] = (s < n_subsets && kld_scale) ? kld_scale[s] : 0.f;
+    ss.kld_scale[s] = 0.f;
     ss.used |= ss.mask[s];
   }
   return 0;
+}
+
+// blocks per level: the launch has 148 x XHVED_POE_WAVES blocks at most, shared out in proportion to the level sizes
+template <typename Args>
+static int assign_blocks(Args& a, int vec) {
+  int64_t want[4], total = 0;
+  for (int l = 0; l < a.nlev; ++l) {
+    want[l] = (a.lev[l].n / vec + 255) / 256;
+    if (want[l] < 1) want[l] = 1;
+    total += want[l];
+  }
+  const int64_t cap = grid_for(INT64_MAX / 2);
+  int end = 0;
+  for (int l = 0; l < a.nlev; ++l) {
+    int64_t blocks = total <= cap ? want[l] : (want[l] * cap + total - 1) / total;
+    if (blocks < 1) blocks = 1;
+    end += static_cast<int>(blocks);
+    a.blk_end[l] = end;
+  }
+  for (int l = a.nlev; l < 4; ++l) a.blk_end[l] = end;
+  return end;
+}
+
+static bool level_v4(const PoeLevelF& L) {
+  return (L.n % 4 == 0) && (L.stride % 4 == 0) && (!L.drop || L.per_sample % 4 == 0) && aligned16(L.mu) && aligned16(L.lv) &&
+         aligned16(L.out_mu) && aligned16(L.out_lv) && (!L.noise || (aligned16(L.noise) && aligned16(L.out_z)));
+}
+static bool level_v4(const PoeLevelB& L) {
+  return (L.n % 4 == 0) && (L.stride % 4 == 0) && (!L.drop || L.per_sample % 4 == 0) && aligned16(L.mu) && aligned16(L.lv) &&
+         aligned16(L.d_mu) && aligned16(L.d_lv) && (!L.g_mu || aligned16(L.g_mu)) && (!L.g_lv || aligned16(L.g_lv)) &&
+         (!L.g_z || (aligned16(L.g_z) && aligned16(L.noise)));
+}
+
+template <int V, int NS>
+static void launch_fwd(PoeFwdArgs& a, const PoeSubsets& ss, float eps, bool sp, cudaStream_t st) {
+  const int grid = assign_blocks(a, V);
+  if (sp) poe_fwd_kernel<V, NS, true><<<grid, 256, 0, st>>>(a, ss, eps);
+  else poe_fwd_kernel<V, NS, false><<<grid, 256, 0, st>>>(a, ss, eps);
+}
+template <int V, int NS>
+static void launch_bwd(PoeBwdArgs& a, const PoeSubsets& ss, float eps, bool sp, cudaStream_t st) {
+  const int grid = assign_blocks(a, V);
+  if (sp) poe_bwd_kernel<V, NS, true><<<grid, 256, 0, st>>>(a, ss, eps);
+  else poe_bwd_kernel<V, NS, false><<<grid, 256, 0, st>>>(a, ss, eps);
+}
+
+static int run_fwd(PoeFwdArgs& a, const uint32_t* subset_masks, int n_subsets, float eps, int flags, cudaStream_t st) {
+  PoeSubsets ss;
+  if (int rc = fill_subsets(ss, subset_masks, n_subsets)) return rc;
+  bool v4 = true;
+  for (int l = 0; l < a.nlev; ++l) {
+    const PoeLevelF& L = a.lev[l];
+    if (L.n <= 0 || L.stride < L.n || !L.mu || !L.lv || !L.out_mu || !L.out_lv) return XHVED_ERR_BAD_ARG;
+    if ((L.out_z != nullptr) != (L.noise != nullptr)) return XHVED_ERR_BAD_ARG;
+    if (L.drop && (L.per_sample <= 0 || L.n % L.per_sample)) return XHVED_ERR_BAD_SHAPE;
+    v4 = v4 && level_v4(L);
+  }
+  const bool sp = (flags & XHVED_POE_STANDARD_PRIOR) != 0;
+  ProfScope ps(K_POE_FWD, st);
+  if (v4) {
+    if (n_subsets == 1) launch_fwd<4, 1>(a, ss, eps, sp, st);
+    else if (n_subsets <= 4) launch_fwd<4, 4>(a, ss, eps, sp, st);
+    else launch_fwd<4, 15>(a, ss, eps, sp, st);
+  } else {
+    if (n_subsets == 1) launch_fwd<1, 1>(a, ss, eps, sp, st);
+    else launch_fwd<1, 15>(a, ss, eps, sp, st);
+  }
+  return (int)cudaGetLastError();
+}
+
+static int run_bwd(PoeBwdArgs& a, const uint32_t* subset_masks, int n_subsets, float eps, int flags, cudaStream_t st) {
+  PoeSubsets ss;
+  if (int rc = fill_subsets(ss, subset_masks, n_subsets)) return rc;
+  bool v4 = true;
+  for (int l = 0; l < a.nlev; ++l) {
+    const PoeLevelB& L = a.lev[l];
+    if (L.n <= 0 || L.stride < L.n || !L.mu || !L.lv || !L.d_mu || !L.d_lv) return XHVED_ERR_BAD_ARG;
+    if (L.g_z && !L.noise) return XHVED_ERR_BAD_ARG;
+    if (L.drop && (L.per_sample <= 0 || L.n % L.per_sample)) return XHVED_ERR_BAD_SHAPE;
+    v4 = v4 && level_v4(L);
+  }
+  const bool sp = (flags & XHVED_POE_STANDARD_PRIOR) != 0;
+  ProfScope ps(K_POE_BWD, st);
+  if (v4) {
+    if (n_subsets == 1) launch_bwd<4, 1>(a, ss, eps, sp, st);
+    else if (n_subsets <= 4) launch_bwd<4, 4>(a, ss, eps, sp, st);
+    else launch_bwd<4, 15>(a, ss, eps, sp, st);
+  } else {
+    if (n_subsets == 1) launch_bwd<1, 1>(a, ss, eps, sp, st);
+    else launch_bwd<1, 15>(a, ss, eps, sp, st);
+  }
+  return (int)cudaGetLastError();
 }
 
 }  // namespace xhved
 
 using namespace xhved;
 
-extern "C" int xhved_version(void) { return 100; }
+extern "C" int xhved_version(void) { return 101; }
 
 extern "C" int xhved_poe_fwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
                              int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, float* out_mu, float* out_logvar,
                              const float* noise, float* out_z, float* kld_out, int flags, void* stream) {
-  if (n <= 0 || expert_stride < n || !mu || !logvar || !out_mu || !out_logvar) return XHVED_ERR_BAD_ARG;
-  const int std_prior = (flags & XHVED_POE_STANDARD_PRIOR) ? 1 : 0;
-  if ((out_z != nullptr) != (noise != nullptr)) return XHVED_ERR_BAD_ARG;
-  if (drop && (per_sample <= 0 || n % per_sample)) return XHVED_ERR_BAD_SHAPE;
-  PoeSubsets ss;
-  if (int rc = fill_subsets(ss, subset_masks, n_subsets, nullptr)) return rc;
-  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
-  const bool v4 = (n % 4 == 0) && (expert_stride % 4 == 0) && (!drop || per_sample % 4 == 0) && aligned16(mu) && aligned16(logvar) &&
-                  aligned16(out_mu) && aligned16(out_logvar) && (!noise || (aligned16(noise) && aligned16(out_z)));
-  ProfScope ps(K_POE_FWD, st_);
-#define XHVED_POE_FWD(V, NS, GRID) \
-  do {                                                                                                                             \
-    if (std_prior)                                                                                                                 \
-      poe_fwd_kernel<V, NS, true><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar, \
-                                                         noise, out_z, kld_out);                                                  \
-    else                                                                                                                           \
-      poe_fwd_kernel<V, NS, false><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, out_mu, out_logvar, \
-                                                          noise, out_z, kld_out);                                                 \
-  } while (0)
-  if (v4) {
-    if (n_subsets == 1) XHVED_POE_FWD(4, 1, grid_for(n / 4));
-    else if (n_subsets <= 4) XHVED_POE_FWD(4, 4, grid_for(n / 4));
-    else XHVED_POE_FWD(4, 15, grid_for(n / 4));
-  } else {
-    if (n_subsets == 1) XHVED_POE_FWD(1, 1, grid_for(n));
-    else XHVED_POE_FWD(1, 15, grid_for(n));
-  }
-#undef XHVED_POE_FWD
-  return (int)cudaGetLastError();
+  PoeFwdArgs a = {};
+  a.nlev = 1;
+  a.lev[0] = PoeLevelF{mu, logvar, n, expert_stride, drop, per_sample, out_mu, out_logvar, noise, out_z, kld_out};
+  return run_fwd(a, subset_masks, n_subsets, eps, flags, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int xhved_poe_bwd(const float* mu, const float* logvar, int64_t n, int64_t expert_stride, const uint32_t* subset_masks,
                              int n_subsets, const uint8_t* drop, int64_t per_sample, float eps, const float* g_mu, const float* g_logvar,
                              const float* noise, const float* g_z, const float* kld_scale, float* d_mu, float* d_logvar, int flags,
                              void* stream) {
-  if (n <= 0 || expert_stride < n || !mu || !logvar || !d_mu || !d_logvar) return XHVED_ERR_BAD_ARG;
-  const int std_prior = (flags & XHVED_POE_STANDARD_PRIOR) ? 1 : 0;
-  if (g_z && !noise) return XHVED_ERR_BAD_ARG;
-  if (drop && (per_sample <= 0 || n % per_sample)) return XHVED_ERR_BAD_SHAPE;
-  PoeSubsets ss;
-  if (int rc = fill_subsets(ss, subset_masks, n_subsets, kld_scale)) return rc;
-  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
-  const bool v4 = (n % 4 == 0) && (expert_stride % 4 == 0) && (!drop || per_sample % 4 == 0) && aligned16(mu) && aligned16(logvar) &&
-                  aligned16(d_mu) && aligned16(d_logvar) && (!g_mu || aligned16(g_mu)) && (!g_logvar || aligned16(g_logvar)) &&
-                  (!g_z || (aligned16(g_z) && aligned16(noise)));
-  ProfScope ps(K_POE_BWD, st_);
-#define XHVED_POE_BWD(V, NS, GRID)                                                                                                  \
-  do {                                                                                                                              \
-    if (std_prior)                                                                                                                  \
-      poe_bwd_kernel<V, NS, true><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise, \
-                                                         g_z, kld_scale != nullptr, d_mu, d_logvar);                                \
-    else                                                                                                                            \
-      poe_bwd_kernel<V, NS, false><<<GRID, 256, 0, st_>>>(mu, logvar, n, expert_stride, ss, drop, per_sample, eps, g_mu, g_logvar, noise, \
-                                                          g_z, kld_scale != nullptr, d_mu, d_logvar);                               \
-  } while (0)
-  if (v4) {
-    if (n_subsets == 1) XHVED_POE_BWD(4, 1, grid_for(n / 4));
-    else if (n_subsets <= 4) XHVED_POE_BWD(4, 4, grid_for(n / 4));
-    else XHVED_POE_BWD(4, 15, grid_for(n / 4));
-  } else {
-    if (n_subsets == 1) XHVED_POE_BWD(1, 1, grid_for(n));
-    else XHVED_POE_BWD(1, 15, grid_for(n));
+  if (n_subsets < 1 || n_subsets > 15) return XHVED_ERR_BAD_ARG;
+  PoeBwdArgs a = {};
+  a.nlev = 1;
+  PoeLevelB& L = a.lev[0];
+  L.mu = mu, L.lv = logvar, L.n = n, L.stride = expert_stride, L.drop = drop, L.per_sample = per_sample;
+  L.g_mu = g_mu, L.g_lv = g_logvar, L.noise = noise, L.g_z = g_z, L.d_mu = d_mu, L.d_lv = d_logvar;
+  L.use_kld = kld_scale != nullptr;
+  for (int s = 0; s < n_subsets; ++s) L.kld_scale[s] = kld_scale ? kld_scale[s] : 0.f;
+  return run_bwd(a, subset_masks, n_subsets, eps, flags, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int xhved_poe_fwd_levels(const xhved_poe_level* levels, int n_levels, const uint32_t* subset_masks, int n_subsets, float eps,
+                                    int flags, void* stream) {
+  if (!levels || n_levels < 1 || n_levels > XHVED_POE_MAX_LEVELS) return XHVED_ERR_BAD_ARG;
+  PoeFwdArgs a = {};
+  a.nlev = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    const xhved_poe_level& s = levels[l];
+    a.lev[l] = PoeLevelF{s.mu, s.logvar, s.n, s.expert_stride, s.drop, s.per_sample, s.out_mu, s.out_logvar, s.noise, s.out_z, s.kld_out};
   }
-#undef XHVED_POE_BWD
-  return (int)cudaGetLastError();
+  return run_fwd(a, subset_masks, n_subsets, eps, flags, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int xhved_poe_bwd_levels(const xhved_poe_level_grad* levels, int n_levels, const uint32_t* subset_masks, int n_subsets,
+                                    float eps, int flags, void* stream) {
+  if (!levels || n_levels < 1 || n_levels > XHVED_POE_MAX_LEVELS || n_subsets < 1 || n_subsets > 15) return XHVED_ERR_BAD_ARG;
+  PoeBwdArgs a = {};
+  a.nlev = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    const xhved_poe_level_grad& s = levels[l];
+    PoeLevelB& L = a.lev[l];
+    L.mu = s.mu, L.lv = s.logvar, L.n = s.n, L.stride = s.expert_stride, L.drop = s.drop, L.per_sample = s.per_sample;
+    L.g_mu = s.g_mu, L.g_lv = s.g_logvar, L.noise = s.noise, L.g_z = s.g_z, L.d_mu = s.d_mu, L.d_lv = s.d_logvar;
+    L.use_kld = s.kld_scale != nullptr;
+    for (int k = 0; k < n_subsets; ++k) L.kld_scale[k] = s.kld_scale ? s.kld_scale[k] : 0.f;
+  }
+  return run_bwd(a, subset_masks, n_subsets, eps, flags, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream) {

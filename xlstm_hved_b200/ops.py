@@ -114,6 +114,69 @@ def poe_bwd(mu5, logvar5, subsets, g_mu=None, g_logvar=None, noise=None, g_z=Non
     return (d_mu[1:], d_lv[1:]) if standard_prior else (d_mu, d_lv)
 
 
+def _dp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def poe_fwd_levels(levels, subsets, noises=None, kld_out=None, eps: float = 1e-8, standard_prior: bool = False):
+    """poe_fwd for several latent levels in ONE launch (the four latent resolutions of a volume; the small ones are
+    latency-bound on their own).  levels: list of (mu5, logvar5) with shape (5, ...) each; noises: optional list of
+    (len(subsets), ...) tensors; kld_out: optional pre-zeroed fp32 (n_levels, len(subsets)) buffer.
+    Returns a list of (pd_mu, pd_logvar, z or None) per level."""
+    lib = _lib.load_library()
+    ns, nl = len(subsets), len(levels)
+    arr = (_lib.PoeLevel * nl)()
+    keep, outs = [], []
+    for l, (mu5, lv5) in enumerate(levels):
+        assert mu5.shape == lv5.shape and mu5.shape[0] == 5
+        mu5, lv5 = _f32c(mu5), _f32c(lv5)
+        n = mu5[0].numel()
+        out_mu = torch.empty((ns, *mu5.shape[1:]), device=mu5.device, dtype=torch.float32)
+        out_lv = torch.empty_like(out_mu)
+        noise = _f32c(noises[l]) if noises is not None else None
+        z = torch.empty_like(out_mu) if noise is not None else None
+        if noise is not None:
+            assert noise.numel() == ns * n
+        kl = kld_out[l] if kld_out is not None else None
+        if kl is not None:
+            assert kl.dtype == torch.float32 and kl.is_contiguous() and kl.numel() == ns
+        e = arr[l]
+        e.mu, e.logvar, e.n, e.expert_stride, e.drop, e.per_sample = mu5.data_ptr(), lv5.data_ptr(), n, n, None, 0
+        e.out_mu, e.out_logvar, e.noise, e.out_z, e.kld_out = out_mu.data_ptr(), out_lv.data_ptr(), _dp(noise), _dp(z), _dp(kl)
+        keep.append((mu5, lv5, noise))
+        outs.append((out_mu, out_lv, z))
+    check(lib.xhved_poe_fwd_levels(arr, nl, _masks(subsets), ns, eps, POE_STANDARD_PRIOR if standard_prior else 0, stream()),
+          "xhved_poe_fwd_levels")
+    return outs
+
+
+def poe_bwd_levels(levels, subsets, noises=None, g_zs=None, kld_scales=None, eps: float = 1e-8, standard_prior: bool = False):
+    """Backward of poe_fwd_levels through z and the KL term, one launch.  kld_scales: per level a list of len(subsets) floats.
+    Returns a list of (d_mu, d_logvar) per level ((4, ...) modality slabs with standard_prior, else (5, ...))."""
+    lib = _lib.load_library()
+    ns, nl = len(subsets), len(levels)
+    arr = (_lib.PoeLevelGrad * nl)()
+    keep, outs = [], []
+    for l, (mu5, lv5) in enumerate(levels):
+        mu5, lv5 = _f32c(mu5), _f32c(lv5)
+        n = mu5[0].numel()
+        d_mu, d_lv = torch.empty_like(mu5), torch.empty_like(mu5)
+        noise = _f32c(noises[l]) if noises is not None else None
+        g_z = _f32c(g_zs[l]) if g_zs is not None else None
+        ks = (c_float * ns)(*[float(v) for v in kld_scales[l]]) if kld_scales is not None else None
+        e = arr[l]
+        e.mu, e.logvar, e.n, e.expert_stride, e.drop, e.per_sample = mu5.data_ptr(), lv5.data_ptr(), n, n, None, 0
+        e.g_mu, e.g_logvar, e.noise, e.g_z = None, None, _dp(noise), _dp(g_z)
+        if ks is not None:
+            e.kld_scale = ks
+        e.d_mu, e.d_logvar = d_mu.data_ptr(), d_lv.data_ptr()
+        keep.append((mu5, lv5, noise, g_z, ks))
+        outs.append((d_mu[1:], d_lv[1:]) if standard_prior else (d_mu, d_lv))
+    check(lib.xhved_poe_bwd_levels(arr, nl, _masks(subsets), ns, eps, POE_STANDARD_PRIOR if standard_prior else 0, stream()),
+          "xhved_poe_bwd_levels")
+    return outs
+
+
 def reparam_fwd(mu, logvar, noise):
     lib = _lib.load_library()
     mu, logvar, noise = _f32c(mu), _f32c(logvar), _f32c(noise)
