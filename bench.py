@@ -150,6 +150,7 @@ class HotPath:
                 x=torch.zeros(B, DIM, *SPATIAL, device=device),
                 ready=torch.cuda.Event(), free=torch.cuda.Event()))
         self.copy_stream = torch.cuda.Stream(device=device)
+        self.n_lat = sum(t.numel() for t in self.gz)
         self.kld = torch.zeros(4, device=device)                                 # per-level KL sums of a step
         self.kld_w = torch.tensor([0.5 / (B * C * d ** 3) / 4 for C, d in LEVELS], device=device)
         self.kld_scales = [[0.2 * 0.5 / (B * C * d ** 3) / 4] for C, d in LEVELS]     # d loss / d kld_sum per level (weight 0.2)
@@ -195,7 +196,12 @@ class HotPath:
         mu5, lv5 = sl["mu5"], sl["lv5"]
         # ---- S-MVAE: fusion + sampling + KL in one launch per level, backward in one launch per level
         self.kld.zero_()
-        noises = [torch.empty_like(self.gz[l]).normal_() for l in range(4)]    # RA_HVED.py:743-744 semantics, one draw per level
+        # eps ~ N(0,1) for all four levels (RA_HVED.py:743-744) from torch's generator: one draw over a flat buffer, viewed per level
+        flat = torch.empty(self.n_lat, device=self.device).normal_()
+        noises, off = [], 0
+        for gzl in self.gz:
+            noises.append(flat[off:off + gzl.numel()].view(gzl.shape))
+            off += gzl.numel()
         levels = list(zip(mu5, lv5))
         # the four latent levels ride in one launch; slab 0 is the model's constant prior (mu = 0, logvar = 0,
         # RA_HVED.py:576-580): declared, not read
