@@ -181,3 +181,28 @@ def test_poe_levels_one_launch_equals_per_level_launches():
                 assert torch.allclose(kld[l], k1, rtol=1e-5)
                 dmu, dlv = ops.poe_bwd(mu, lv, subsets, noise=noises[l], g_z=gzs[l], kld_scale=scales[l], standard_prior=sp)
                 assert torch.equal(grads[l][0], dmu) and torch.equal(grads[l][1], dlv)
+
+
+def test_poe_full_bench_size_properties():
+    """Full bench size (B=32 volumes, 4 levels, 11.1 M latent elements): (1) the fused KL sum equals the KL recomputed from
+    the kernel's own outputs; (2) with one modality the product of that expert with the standard prior is reproduced in
+    closed form: T = 1/(e^lv + eps) + 1/(1 + eps), mu^ = mu T_m / T; (3) a dropped batch == the complementary subset."""
+    from xlstm_hved_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B = 32
+    for C, d in ((1, 64), (8, 8)):
+        sh = (B, C, d, d, d)
+        mu = torch.cat([torch.zeros(1, *sh, device="cuda"), 1.3 * torch.randn(4, *sh, device="cuda", generator=g)])
+        lv = torch.cat([torch.zeros(1, *sh, device="cuda"), (1.4 * torch.randn(4, *sh, device="cuda", generator=g)).clamp(-50, 50)])
+        pm, pl, _, kld = ops.poe_fwd(mu, lv, [(0, 1, 2, 3), (2,)], want_kld=True, standard_prior=True)
+        ref_kld = (-1.0 - pl.double() + (pl.double().exp() + pm.double() ** 2)).flatten(1).sum(1)
+        assert torch.allclose(kld.double(), ref_kld, rtol=2e-4)
+        T = 1.0 / (lv[3].double().exp() + 1e-8) + 1.0 / (1.0 + 1e-8)
+        assert rel_linf(pm[1], mu[3].double() / (lv[3].double().exp() + 1e-8) / T) < 1e-5
+        assert rel_linf(pl[1], -T.log()) < 1e-5
+        drop = torch.zeros(B, 4, dtype=torch.bool, device="cuda")
+        drop[:, 0] = True
+        drop[:, 3] = True
+        dm, dl, _, _ = ops.poe_fwd(mu, lv, [(0, 1, 2, 3)], drop=drop)
+        cm, cl, _, _ = ops.poe_fwd(mu, lv, [(1, 2)])
+        assert torch.equal(dm, cm) and torch.equal(dl, cl)
