@@ -261,9 +261,14 @@ def run_gpu(args):
     if graphed:
         hp.load(x, mus, lvs, slot=1)
         torch.cuda.synchronize()
-        hp.capture()
-        for _ in range(W):
-            hp.step(graphed=True)
+        try:
+            hp.capture()
+            for _ in range(W):
+                hp.step(graphed=True)
+        except Exception as e:      # a driver that refuses the capture must not cost the measurement: fall back to eager launches
+            print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graphed = False
+            torch.cuda.synchronize()
     run_step = (lambda: hp.step(graphed=True)) if graphed else hp.step
     sampler = ClockSampler(local)
     if rank == 0:
