@@ -7,59 +7,10 @@
 // (UxLSTMEnc_3d.py:59).  Outputs land in the cell's tile-native bf16 layout, so the cell kernels can bulk-copy
 // MMA-ready operand tiles.
 //
-// One CTA = 128 consecutive tokens (in traversal order) = one cell chunk for all heads; thread r owns token r.
+// One tile = 128 consecutive tokens (in traversal order) = one cell chunk for all heads; 512 threads = token x head group.
 #include "vil_common.cuh"
 
 namespace xhved {
-
-template <int C>
-struct PreSmem {
-  static constexpr int E = 2 * C;
-  static constexpr int XM_LD = E + 1;                 // odd row pitch: conflict-free column access
-  static constexpr int XM_ROWS = kTok + 3;
-  // float offsets
-  static constexpr int W_UP = 0;                      // (2E, C)
-  static constexpr int XM = W_UP + 2 * E * C;         // (131, E+1)
-  static constexpr int CONV_W = XM + (XM_ROWS * XM_LD + 3) / 4 * 4; // (E, 4), 16-byte aligned
-  static constexpr int CONV_B = CONV_W + E * 4;
-  static constexpr int WQ = CONV_B + E;               // (E/4, 4, 4) = E*4
-  static constexpr int WK = WQ + E * 4;
-  static constexpr int WV = WK + E * 4;
-  static constexpr int WI = WV + E * 4;               // (4, 3E)
-  static constexpr int WF = WI + 4 * 3 * E;
-  static constexpr int NW = WF + 4 * 3 * E;           // (C)
-  static constexpr int TOTAL = NW + C;
-};
-
-// LayerNorm of one token held in registers; returns xhat*(1+w) in xn, optionally xhat / rstd
-template <int C>
-__device__ __forceinline__ void layernorm_token(const float* xin, const float* nw, float* xn, float* rstd_out) {
-  float mean = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) mean += xin[c];
-  mean *= (1.f / C);
-  float var = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float d = xin[c] - mean;
-    var += d * d;
-  }
-  const float rstd = rsqrtf(var * (1.f / C) + 1e-5f);
-#pragma unroll
-  for (int c = 0; c < C; ++c) xn[c] = (xin[c] - mean) * rstd * (1.f + nw[c]);
-  if (rstd_out) *rstd_out = rstd;
-}
-
-template <int C>
-__device__ __forceinline__ float dot_row(const float* xn, const float* wrow) {
-  float acc = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; c += 4) {
-    const float4 w = *reinterpret_cast<const float4*>(wrow + c);
-    acc += xn[c] * w.x + xn[c + 1] * w.y + xn[c + 2] * w.z + xn[c + 3] * w.w;
-  }
-  return acc;
-}
 
 // ------------------------------------------------------------------ forward (tcgen05 version)
 // proj_up runs as a 3-product bf16 hi/lo UMMA (tokens x 2E, ~fp32 accuracy), the gate pre-activations as a UMMA over the
@@ -165,7 +116,6 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_fwd_kerne
     // ---- LayerNorm, token rows staged as bf16 hi/lo; conv halo tokens (first 3 threads of group 1)
     const int tau = ch * kTok + tok;
     const bool valid = tau < g.S;
-    const int n = g.reverse ? g.S - 1 - tau : tau;
     {
       // LayerNorm of the CTA's tokens: every head group owns CP channels of its token, statistics go through shared memory
       // (mean first, then the centred second moment, as F.layer_norm does)
@@ -354,198 +304,6 @@ static int launch_pre_fwd(const float* x, const xhved_vil_params* p, const VilGe
   vil_pre_fwd_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z, xm,
                                                       ntiles);
   return (int)cudaGetLastError();
-}
-
-// ------------------------------------------------------------------ backward, kernel A
-// Recomputes the forward up to q,k,v for 128 tokens (+3 halo), then pulls dq,dk,dv,dig,dfg and the skip-path
-// d_act back to (a) dconv = d(conv pre-activation) and (b) dxm_v = d(x_mlstm) through the v projection, both
-// written token-minor for kernel B; accumulates gate, q/k/v-projection and conv parameter gradients.
-template <int C>
-struct PreBwdASmem {
-  using F = PreSmem<C>;
-  static constexpr int E = 2 * C;
-  static constexpr int ACC = F::TOTAL;                 // per-CTA partial sums, see offsets below
-  static constexpr int A_WQ = 0, A_WK = E * 4, A_WV = 2 * E * 4, A_CW = 3 * E * 4, A_CB = 4 * E * 4, A_GB = 4 * E * 4 + E;
-  static constexpr int ACC_N = A_GB + 8;
-  static constexpr int DG = ACC + (ACC_N + 3) / 4 * 4;  // (128, 9): dig[4] | dfg[4] per token
-  // (128, E) staging of q / k / v per token, column-skewed by the row index (conflict-free).  When it fits
-  // (C >= 64) it ALIASES the proj_up weights, which are dead once x_mlstm has been recomputed.
-  static constexpr bool ALIAS = 2 * E * C >= kTok * E;
-  static constexpr int ST = ALIAS ? F::W_UP : DG + kTok * 9;
-  static constexpr int TOTAL = ALIAS ? DG + kTok * 9 : ST + kTok * E;
-};
-
-template <int C>
-__global__ void __launch_bounds__(160) vil_pre_bwd_a_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
-                                                             const float* __restrict__ dq, const float* __restrict__ dk,
-                                                             const float* __restrict__ dv, const float* __restrict__ dig,
-                                                             const float* __restrict__ dfg, const float* __restrict__ d_act,
-                                                             float* __restrict__ dconv_out, float* __restrict__ dxmv_out,
-                                                             xhved_vil_grads gr_base) {
-  const xhved_vil_grads gr = replica_of(gr_base, g);
-  using L = PreSmem<C>;
-  using LB = PreBwdASmem<C>;
-  constexpr int E = L::E;
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
-  const int b = blockIdx.x / g.nc, ch = blockIdx.x % g.nc;
-  stage(sm + L::W_UP, p.proj_up_weight, 2 * E * C);
-  stage(sm + L::CONV_W, p.conv_weight, E * 4);
-  stage(sm + L::CONV_B, p.conv_bias, E);
-  stage(sm + L::WQ, p.q_weight, E * 4);
-  stage(sm + L::WK, p.k_weight, E * 4);
-  stage(sm + L::WV, p.v_weight, E * 4);
-  stage(sm + L::WI, p.igate_weight, 4 * 3 * E);
-  stage(sm + L::WF, p.fgate_weight, 4 * 3 * E);
-  stage(sm + L::NW, p.norm_weight, C);
-  for (int i = tid; i < LB::ACC_N; i += blockDim.x) sm[LB::ACC + i] = 0.f;
-
-  const bool is_main = tid < kTok, is_halo = tid >= kTok && tid < kTok + 3;
-  const int tau = is_main ? ch * kTok + tid : ch * kTok - 3 + (tid - kTok);
-  const bool valid = (is_main || is_halo) && tau >= 0 && tau < g.S;
-  const int n = g.reverse ? g.S - 1 - tau : tau;
-  float xin[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) xin[c] = valid ? __ldg(x + b * g.xsb + n * g.xsn + c * g.xsc) : 0.f;
-  __syncthreads();
-  float xn[C];
-  layernorm_token<C>(xin, sm + L::NW, xn, nullptr);
-  const int xm_row = is_main ? tid + 3 : tid - kTok;
-  if (is_main || is_halo) {
-    float* xm = sm + L::XM + xm_row * L::XM_LD;
-#pragma unroll 1
-    for (int e = 0; e < E; ++e) xm[e] = valid ? dot_row<C>(xn, sm + L::W_UP + e * C) : 0.f;
-  }
-  float dgi[4], dgf[4];
-  const bool rowvalid = is_main && tau < g.S;
-  if (is_main) {
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const size_t o = (static_cast<size_t>(b) * g.NH + h) * g.Sp + ch * kTok + tid;
-      dgi[h] = rowvalid ? __ldg(dig + o) : 0.f;
-      dgf[h] = rowvalid ? __ldg(dfg + o) : 0.f;
-      sm[LB::DG + tid * 9 + h] = dgi[h];
-      sm[LB::DG + tid * 9 + 4 + h] = dgf[h];
-    }
-  }
-  __syncthreads();
-  float* acc = sm + LB::ACC;
-  float* stg = sm + LB::ST + (is_main ? tid : 0) * E;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tid;
-  const float* xm0 = sm + L::XM + (is_main ? tid : 0) * L::XM_LD;
-
-  // three passes over the channels: part 0 stages q, 1 stages k, 2 stages v (for the gate-weight outer products);
-  // pass 0 additionally does all the per-token backward work.
-#pragma unroll 1
-  for (int part = 0; part < 3; ++part) {
-    if (is_main) {
-#pragma unroll 1
-      for (int e8 = 0; e8 < E; e8 += 8) {
-        float a8[8], xm8[8], cv8[8], q8[8], k8[8], v8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int e = e8 + j;
-          const float4 w = *reinterpret_cast<const float4*>(sm + L::CONV_W + e * 4);
-          cv8[j] = sm[L::CONV_B + e] + w.x * xm0[e] + w.y * xm0[L::XM_LD + e] + w.z * xm0[2 * L::XM_LD + e] + w.w * xm0[3 * L::XM_LD + e];
-          a8[j] = silu(cv8[j]);
-          xm8[j] = xm0[3 * L::XM_LD + e];
-        }
-#pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
-          const int wb = ((e8 >> 2) + blk) * 16;
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            float aq = 0.f, ak = 0.f, av = 0.f;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-              aq += sm[L::WQ + wb + o * 4 + d] * a8[blk * 4 + d];
-              ak += sm[L::WK + wb + o * 4 + d] * a8[blk * 4 + d];
-              av += sm[L::WV + wb + o * 4 + d] * xm8[blk * 4 + d];
-            }
-            q8[blk * 4 + o] = aq, k8[blk * 4 + o] = ak, v8[blk * 4 + o] = av;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) stg[(e8 + j + tid) & (E - 1)] = rowvalid ? (part == 0 ? q8[j] : part == 1 ? k8[j] : v8[j]) : 0.f;
-        if (part == 0) {
-          // upstream gradients of q,k,v for these 8 channels (+ the gate paths, vision_lstm.py:305-318)
-          const int head = e8 / g.DH, d0 = e8 % g.DH;
-          const size_t row = ((static_cast<size_t>(b) * g.NH + head) * g.Sp + ch * kTok + tid) * g.DHP + d0;
-          float gq[8], gk[8], gv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int e = e8 + j;
-            gq[j] = rowvalid ? __ldg(dq + row + j) : 0.f;
-            gk[j] = rowvalid ? __ldg(dk + row + j) : 0.f;
-            gv[j] = rowvalid ? __ldg(dv + row + j) : 0.f;
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              gq[j] += dgi[h] * sm[L::WI + h * 3 * E + e] + dgf[h] * sm[L::WF + h * 3 * E + e];
-              gk[j] += dgi[h] * sm[L::WI + h * 3 * E + E + e] + dgf[h] * sm[L::WF + h * 3 * E + E + e];
-              gv[j] += dgi[h] * sm[L::WI + h * 3 * E + 2 * E + e] + dgf[h] * sm[L::WF + h * 3 * E + 2 * E + e];
-            }
-          }
-          float da8[8], dxv8[8];
-#pragma unroll
-          for (int blk = 0; blk < 2; ++blk) {
-            const int wb = ((e8 >> 2) + blk) * 16;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-              float sa = 0.f, sv = 0.f;
-#pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                sa += sm[L::WQ + wb + o * 4 + d] * gq[blk * 4 + o] + sm[L::WK + wb + o * 4 + d] * gk[blk * 4 + o];
-                sv += sm[L::WV + wb + o * 4 + d] * gv[blk * 4 + o];
-                // d q_proj[b][o][d] += gq[o] * act[d]  etc. (reduced over the CTA's tokens)
-                warp_acc(acc + LB::A_WQ + wb + o * 4 + d, gq[blk * 4 + o] * a8[blk * 4 + d]);
-                warp_acc(acc + LB::A_WK + wb + o * 4 + d, gk[blk * 4 + o] * a8[blk * 4 + d]);
-                warp_acc(acc + LB::A_WV + wb + o * 4 + d, gv[blk * 4 + o] * xm8[blk * 4 + d]);
-              }
-              da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int e = e8 + j;
-            const float dact = da8[j] + (rowvalid ? __ldg(d_act + tm_base + static_cast<size_t>(e) * kTok) : 0.f);
-            const float dc = rowvalid ? dact * dsilu(cv8[j]) : 0.f;
-            dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc;
-            dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = rowvalid ? dxv8[j] : 0.f;
-            warp_acc(acc + LB::A_CB + e, dc);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) warp_acc(acc + LB::A_CW + e * 4 + jj, dc * xm0[jj * L::XM_LD + e]);
-          }
-        }
-      }
-      if (part == 0) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          warp_acc(acc + LB::A_GB + h, dgi[h]);
-          warp_acc(acc + LB::A_GB + 4 + h, dgf[h]);
-        }
-      }
-    }
-    __syncthreads();
-    // d igate.weight[h][part*E + e] += sum_tok dig[tok][h] * qkv_part[tok][e]   (same for fgate)
-    for (int idx = tid; idx < 8 * E; idx += blockDim.x) {
-      const int hh = idx / E, e = idx % E;
-      float a = 0.f;
-#pragma unroll 4
-      for (int t = 0; t < kTok; ++t) a += sm[LB::DG + t * 9 + hh] * sm[LB::ST + t * E + ((e + t) & (E - 1))];
-      float* dst = (hh < 4 ? gr.igate_weight + hh * 3 * E : gr.fgate_weight + (hh - 4) * 3 * E) + part * E + e;
-      atomicAdd(dst, a);
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < E * 4; i += blockDim.x) {
-    atomicAdd(gr.q_weight + i, acc[LB::A_WQ + i]);
-    atomicAdd(gr.k_weight + i, acc[LB::A_WK + i]);
-    atomicAdd(gr.v_weight + i, acc[LB::A_WV + i]);
-    atomicAdd(gr.conv_weight + i, acc[LB::A_CW + i]);
-  }
-  for (int i = tid; i < E; i += blockDim.x) atomicAdd(gr.conv_bias + i, acc[LB::A_CB + i]);
-  if (tid < 4) atomicAdd(gr.igate_bias + tid, acc[LB::A_GB + tid]);
-  else if (tid < 8) atomicAdd(gr.fgate_bias + tid - 4, acc[LB::A_GB + tid]);
 }
 
 // ------------------------------------------------------------------ backward, tcgen05 versions
@@ -752,34 +510,43 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
   if (warp == 0) tmem_dealloc(tmem, L::TMEM_COLS);
 }
 
-// Kernel A (tensor-core, C <= 32).  Inputs per tile: the forward's saved x_mlstm (no recompute of proj_up), d_act, the
-// cell's dq/dk/dv and the gate gradients.  Gate-path gradients (dig,dfg -> q,k,v) and every parameter gradient that is a
-// token reduction run as UMMAs; conv / SiLU / 4x4 block backward on CUDA cores.
+// Kernel A (tensor-core).  Inputs per tile: the forward's saved x_mlstm (no recompute of proj_up), d_act, the cell's
+// dq/dk/dv and the gate gradients.  Gate-path gradients (dig,dfg -> q,k,v) and every parameter gradient that is a token
+// reduction run as UMMAs; conv / SiLU / 4x4 block backward on CUDA cores.
 // The gate-weight gradient  d Wg = [dig|dfg]^T [q|k|v]  is taken THROUGH the block-diagonal projections:
 //     [dig|dfg]^T q = ([dig|dfg]^T act) Wq^T   (k alike; v with x_mlstm and Wv)
 // so the kernel only reduces [dig|dfg]^T act and [dig|dfg]^T x_mlstm over tokens (operand tiles it stages anyway) and
 // applies the 4x4 blocks once per CTA at flush time -- the bf16 q|k|v tiles are not read at all.
+// Everything behind proj_up is separable over channels (conv and the 4x4 projections are block-diagonal), so the E inner
+// channels are processed in GROUPS of at most 64: dim 64 (E = 128) makes two sweeps over the CTA's tiles with the
+// shared-memory / TMEM budget of dim 32.
 template <int C>
 struct PreBwdATC {
-  static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
-  static constexpr uint32_t DG_BYTES = kTok * 16 * 2, WG_BYTES = 16 * NQ * 2, T_BYTES = kTok * E * 2;
+  static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH;
+  static constexpr int EG = E < 64 ? E : 64;          // channels per group
+  static constexpr int NG = E / EG;                   // sweeps
+  static constexpr int HG = EG / DH;                  // cell heads per group (4, or 2 for dim 64)
+  static constexpr int NQ = 3 * HG * DHP;             // padded q|k|v columns of a group
+  static constexpr int CPT = EG / 4;                  // channels per thread (thread = token x quarter of the group)
+  static constexpr uint32_t DG_BYTES = kTok * 16 * 2, WG_BYTES = 16 * NQ * 2, T_BYTES = kTok * EG * 2;
   // [dig|dfg] (double-buffered hi/lo pairs) is also read as a 128-row MN-major A operand: 32 KB window that runs on over
   // the tiles behind it; rows >= 16 of those products are never read
   static constexpr uint32_t DG0 = 0, DG_STRIDE = 2 * DG_BYTES, WGHI = 2 * DG_STRIDE, WGLO = WGHI + WG_BYTES;
-  // operands of the weight-gradient GEMMs.  GQK: [128][2E]; GV: 32 KB window covering ACT, XMT.
+  // operands of the weight-gradient GEMMs.  GQK: [128][2 EG]; GV: 32 KB window covering ACT, XMT.
   static constexpr uint32_t GQK = WGLO + WG_BYTES;
-  static constexpr uint32_t GV = GQK + kTok * 2 * E * 2, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;
+  static constexpr uint32_t GV = GQK + kTok * 2 * EG * 2, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;
   static constexpr uint32_t END2 = XMT + T_BYTES, END3 = GV + 32768, END4 = DG0 + DG_STRIDE + 32768;
   static constexpr uint32_t PAR = END2 > END3 ? (END2 > END4 ? END2 : END4) : (END3 > END4 ? END3 : END4);
-  static constexpr int P_CW = 0, P_CB = E * 4, P_WQ = P_CB + E, P_WK = P_WQ + E * 4, P_WV = P_WK + E * 4, A_CW = P_WV + E * 4,
-                       A_CB = A_CW + E * 4, A_GB = A_CB + E, P_N = A_GB + 8;
-  // token-minor input blocks staged by bulk async copies: x_mlstm (two stages, each followed by the E x 4 floats of the
-  // 3 tokens in front of the chunk) and d_act (one stage), E x 128 fp32 each
-  static constexpr uint32_t BLK = E * kTok * 4, HX_BYTES = E * 4 * 4, XM_STRIDE = BLK + HX_BYTES;
+  // per-group parameter slices and accumulators (restaged / flushed every sweep); the gate-bias sums once
+  static constexpr int P_CW = 0, P_CB = EG * 4, P_WQ = P_CB + EG, P_WK = P_WQ + EG * 4, P_WV = P_WK + EG * 4, A_CW = P_WV + EG * 4,
+                       A_CB = A_CW + EG * 4, A_GB = A_CB + EG, P_N = A_GB + 8;
+  // token-minor input blocks staged by bulk async copies: x_mlstm (two stages, each followed by the EG x 4 floats of the
+  // 3 tokens in front of the chunk) and d_act (one stage), EG x 128 fp32 each
+  static constexpr uint32_t BLK = EG * kTok * 4, HX_BYTES = EG * 4 * 4, XM_STRIDE = BLK + HX_BYTES;
   static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + 2 * XM_STRIDE;
   static constexpr uint32_t TOTAL = IN_DA + BLK;
-  static constexpr uint32_t T_GQ = 0, T_DWQK = NQ, T_DWV = NQ + E, T_DWGA = NQ + 2 * E, T_DWGX = NQ + 3 * E;
-  static_assert(NQ + 4 * E <= 512 && 2 * E <= 128 && TOTAL <= 227 * 1024, "tensor-core pre-backward A supports C <= 32");
+  static constexpr uint32_t T_GQ = 0, T_DWQK = NQ, T_DWV = NQ + EG, T_DWGA = NQ + 2 * EG, T_DWGX = NQ + 3 * EG;
+  static_assert(NQ + 4 * EG <= 512 && 2 * EG <= 128 && TOTAL <= 227 * 1024, "kernel A: a channel group must fit TMEM and shared memory");
 };
 
 template <int C>
@@ -790,39 +557,40 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
                                                                         float* __restrict__ dconv_out, float* __restrict__ dxmv_out,
                                                                         xhved_vil_grads gr_base, int ntiles) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
-  // 512 threads: thread = (token, head); the four head groups of a token share the TMEM lane of that token.
-  // Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  All parameter gradients accumulate over the CTA's
-  // tiles -- the weight-gradient UMMAs keep adding into their TMEM columns, conv / bias sums live in shared memory -- and
-  // are flushed to global once.  x_mlstm of the next tile streams into the other stage while this tile is processed, its
-  // gate gradients are fetched one tile ahead, and the gate-path UMMA of tile i+1 is issued right behind the weight-gradient
-  // UMMAs of tile i: one __syncthreads per tile.
+  // 512 threads: thread = (token, quarter of the channel group); the four quarters of a token share its TMEM lane.
+  // Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ... (once per channel group).  All parameter gradients
+  // accumulate over the CTA's tiles -- the weight-gradient UMMAs keep adding into their TMEM columns, conv / bias sums live
+  // in shared memory -- and are flushed to global once per sweep.  x_mlstm of the next tile streams into the other stage
+  // while this tile is processed, its gate gradients are fetched one tile ahead, and the gate-path UMMA of tile i+1 is
+  // issued right behind the weight-gradient UMMAs of tile i: one __syncthreads per tile.
   using L = PreBwdATC<C>;
-  constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
+  constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ, EG = L::EG, HG = L::HG, CPT = L::CPT;
   extern __shared__ __align__(128) unsigned char smem[];
   float* par = reinterpret_cast<float*>(smem + L::PAR);
   __shared__ __align__(8) uint64_t bar_xm[2], bar_da, bar1, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tok = tid & (kTok - 1), head = tid >> 7;
+  const int tok = tid & (kTok - 1), quarter = tid >> 7;
+  int ch0 = 0;                                         // first inner channel of the current group
 
   auto issue_xm = [&](int tile, int s) {
     mbar_expect_tx(&bar_xm[s], L::BLK);
-    bulk_g2s(smem + L::IN_XM + s * L::XM_STRIDE, xm + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_xm[s]);
+    bulk_g2s(smem + L::IN_XM + s * L::XM_STRIDE, xm + (static_cast<size_t>(tile) * E + ch0) * kTok, L::BLK, &bar_xm[s]);
   };
   auto issue_da = [&](int tile) {
     mbar_expect_tx(&bar_da, L::BLK);
-    bulk_g2s(smem + L::IN_DA, d_act + static_cast<size_t>(tile) * E * kTok, L::BLK, &bar_da);
+    bulk_g2s(smem + L::IN_DA, d_act + (static_cast<size_t>(tile) * E + ch0) * kTok, L::BLK, &bar_da);
   };
   // x_mlstm of the 3 tokens in front of chunk `tile` (zeros in front of the sequence) -> behind stage s
   auto load_halo = [&](int tile, int s) {
     float* hx = reinterpret_cast<float*>(smem + L::IN_XM + s * L::XM_STRIDE + L::BLK);
     const int ch = tile % g.nc;
-    for (int i = tid; i < E * 4; i += blockDim.x) {
+    for (int i = tid; i < EG * 4; i += blockDim.x) {
       const int e = i >> 2, k = i & 3;
-      hx[i] = (k < 3 && ch > 0) ? __ldg(xm + static_cast<size_t>(tile - 1) * E * kTok + static_cast<size_t>(e) * kTok + kTok - 3 + k) : 0.f;
+      hx[i] = (k < 3 && ch > 0) ? __ldg(xm + (static_cast<size_t>(tile - 1) * E + ch0 + e) * kTok + kTok - 3 + k) : 0.f;
     }
   };
-  // [dig | dfg] of this token (head group 0 only)
+  // [dig | dfg] of this token (quarter 0 only)
   auto load_dg = [&](int tile, float* dg) {
     const int b = tile / g.nc, ch = tile % g.nc;
     const bool valid = ch * kTok + tok < g.S;
@@ -833,7 +601,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
       dg[4 + h] = valid ? __ldg(dfg + o) : 0.f;
     }
   };
-  auto stage_dg = [&](float* dg, int s) {
+  auto stage_dg = [&](float* dg, int s, bool bias_sums) {
     unsigned char* d0 = smem + L::DG0 + s * L::DG_STRIDE;
     uint4 hi, lo;
     split8_hilo(dg, hi, lo);
@@ -841,7 +609,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     *reinterpret_cast<uint4*>(d0 + L::DG_BYTES + tile_off16(kTok, tok, 0)) = lo;
     *reinterpret_cast<uint4*>(d0 + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(d0 + L::DG_BYTES + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);
-    warp_acc_vec<8>(par + L::A_GB, dg);       // gate bias gradients
+    if (bias_sums) warp_acc_vec<8>(par + L::A_GB, dg);       // gate bias gradients (first sweep only)
   };
   // gate path: g_qkv[tok][j] = sum_hh [dig|dfg][tok][hh] Wg[hh][j]     (B = MN-major view of the [16][NQ] weight tile)
   auto issue_mma1 = [&](uint32_t tmem, int s) {
@@ -858,256 +626,270 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     mbar_init(&bar1, 1);
     mbar_init(&bar2, 1);
     mbar_fence_init();
-    issue_xm(blockIdx.x, 0);
-    issue_da(blockIdx.x);
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  float dgn[8];
-  if (head == 0) load_dg(blockIdx.x, dgn);
-  load_halo(blockIdx.x, 0);
-  stage(par + L::P_CW, p.conv_weight, E * 4);
-  stage(par + L::P_CB, p.conv_bias, E);
-  stage(par + L::P_WQ, p.q_weight, E * 4);
-  stage(par + L::P_WK, p.k_weight, E * 4);
-  stage(par + L::P_WV, p.v_weight, E * 4);
-  for (int i = tid; i < E * 4 + E + 8; i += blockDim.x) par[L::A_CW + i] = 0.f;
-  for (int gi = tid; gi < 16 * (NQ / 8); gi += blockDim.x) {
-    const int hh = gi % 16, cg = gi / 16;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = cg * 8 + i, part = j / (4 * DHP), hd = (j / DHP) % 4, d = j % DHP;
-      const float* W = hh < 4 ? p.igate_weight + hh * 3 * E : p.fgate_weight + (hh - 4) * 3 * E;
-      v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + hd * DH + d) : 0.f;
-    }
-    uint4 h, l;
-    split8_hilo(v, h, l);
-    *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
-    *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
-  }
-  __syncthreads();                    // gate-bias accumulators are zero
-  if (head == 0) stage_dg(dgn, 0);
-  fence_proxy_async();
+  if (tid < 8) par[L::A_GB + tid] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   float* acc = par;
-  if (tid == 0) issue_mma1(tmem, 0);
+  float dgn[8];
 
-  int it = 0;
+  int it = 0;                    // tiles processed so far, over all sweeps: stage / barrier phases follow its parity
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int s = it & 1;
-    const int b = tile / g.nc, ch = tile % g.nc;
-    const int nxt = tile + gridDim.x;
-    const bool has_next = nxt < ntiles;
-    // one tile ahead: x_mlstm stage, halo and gate gradients of the next tile
-    if (has_next) {
-      if (tid == 0) issue_xm(nxt, s ^ 1);
-      load_halo(nxt, s ^ 1);
-      if (head == 0) load_dg(nxt, dgn);
+  for (int grp = 0; grp < L::NG; ++grp) {
+    ch0 = grp * EG;
+    const int hd0 = ch0 / DH;    // first cell head of the group
+    // ---- per-sweep prologue: first tile's inputs, the group's parameter slices and gate-weight tile
+    if (tid == 0) {
+      issue_xm(blockIdx.x, it & 1);
+      issue_da(blockIdx.x);
     }
-    const bool valid = ch * kTok + tok < g.S;
-    mbar_wait(&bar_xm[s], (it >> 1) & 1);
-    if (it > 0) {      // the previous tile's weight-gradient products still read the operand tiles this loop rewrites
-      mbar_wait(&bar2, (it - 1) & 1);
-      tc_fence_after();
+    if (quarter == 0) load_dg(blockIdx.x, dgn);
+    load_halo(blockIdx.x, it & 1);
+    stage(par + L::P_CW, p.conv_weight + ch0 * 4, EG * 4);
+    stage(par + L::P_CB, p.conv_bias + ch0, EG);
+    stage(par + L::P_WQ, p.q_weight + ch0 * 4, EG * 4);
+    stage(par + L::P_WK, p.k_weight + ch0 * 4, EG * 4);
+    stage(par + L::P_WV, p.v_weight + ch0 * 4, EG * 4);
+    for (int i = tid; i < EG * 4 + EG; i += blockDim.x) par[L::A_CW + i] = 0.f;
+    for (int gi = tid; gi < 16 * (NQ / 8); gi += blockDim.x) {
+      const int hh = gi % 16, cg = gi / 16;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = cg * 8 + i, part = j / (HG * DHP), hd = (j / DHP) % HG, d = j % DHP;
+        const float* W = hh < 4 ? p.igate_weight + hh * 3 * E : p.fgate_weight + (hh - 4) * 3 * E;
+        v[i] = (hh < 8 && d < DH) ? __ldg(W + part * E + (hd0 + hd) * DH + d) : 0.f;
+      }
+      uint4 h, l;
+      split8_hilo(v, h, l);
+      *reinterpret_cast<uint4*>(smem + L::WGHI + tile_off16(16, hh, cg)) = h;
+      *reinterpret_cast<uint4*>(smem + L::WGLO + tile_off16(16, hh, cg)) = l;
     }
-    const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;
-    const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE);
-    const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE + L::BLK);
-    const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
-    bool first = true;
-#pragma unroll
-    for (int e8 = head * DH; e8 < (head + 1) * DH; e8 += 8) {
-      const int d0 = e8 % DH;
-      float a8[8], xm8[8], cv8[8], xr[4][8];
-      // x_mlstm of tokens tau-3+k; only the first warp of a head group reaches into the halo in front of the chunk
-      if ((tok & ~31) != 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xr[k][j] = s_xm[(e8 + j) * kTok + tok - 3 + k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
-      }
-      float gq[8], gk[8], gv[8], dsk[8];
-      const size_t row = ((static_cast<size_t>(b) * 4 + head) * g.Sp + ch * kTok + tok) * DHP + d0;
-      {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(dq + row)), c = __ldg(reinterpret_cast<const float4*>(dq + row + 4));
-        gq[0] = a.x, gq[1] = a.y, gq[2] = a.z, gq[3] = a.w, gq[4] = c.x, gq[5] = c.y, gq[6] = c.z, gq[7] = c.w;
-        const float4 a2 = __ldg(reinterpret_cast<const float4*>(dk + row)), c2 = __ldg(reinterpret_cast<const float4*>(dk + row + 4));
-        gk[0] = a2.x, gk[1] = a2.y, gk[2] = a2.z, gk[3] = a2.w, gk[4] = c2.x, gk[5] = c2.y, gk[6] = c2.z, gk[7] = c2.w;
-        const float4 a3 = __ldg(reinterpret_cast<const float4*>(dv + row)), c3 = __ldg(reinterpret_cast<const float4*>(dv + row + 4));
-        gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int e = e8 + j;
-        const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
-        cv8[j] = par[L::P_CB + e] + w.x * xr[0][j] + w.y * xr[1][j] + w.z * xr[2][j] + w.w * xr[3][j];
-        xm8[j] = xr[3][j];
-      }
-      // everything above is independent of the gate-path UMMA and of d_act
-      if (first) {
-        mbar_wait(&bar1, it & 1);
-        tc_fence_after();
-        mbar_wait(&bar_da, it & 1);
-        first = false;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
-      float t8[8];
-      tmem_ld8(tmem + lane_base + L::T_GQ + (0 * 4 + head) * DHP + d0, t8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gq[j] = valid ? gq[j] + t8[j] : 0.f;
-      tmem_ld8(tmem + lane_base + L::T_GQ + (1 * 4 + head) * DHP + d0, t8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gk[j] = valid ? gk[j] + t8[j] : 0.f;
-      tmem_ld8(tmem + lane_base + L::T_GQ + (2 * 4 + head) * DHP + d0, t8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gv[j] = valid ? gv[j] + t8[j] : 0.f;
-      float da8[8], dxv8[8];
-#pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        const int wb = ((e8 >> 2) + blk) * 16;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          float sa = 0.f, sv = 0.f;
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            sa += par[L::P_WQ + wb + o * 4 + d] * gq[blk * 4 + o] + par[L::P_WK + wb + o * 4 + d] * gk[blk * 4 + o];
-            sv += par[L::P_WV + wb + o * 4 + d] * gv[blk * 4 + o];
-          }
-          da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
-        }
-      }
-      float dc8[8], prod[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int e = e8 + j;
-        float ds;
-        silu_both(cv8[j], a8[j], ds);
-        dc8[j] = valid ? (da8[j] + dsk[j]) * ds : 0.f;
-        dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc8[j];
-        dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? dxv8[j] : 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) prod[j * 4 + k] = dc8[j] * xr[k][j];
-      }
-      warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
-      warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
-      // operands of the weight-gradient GEMMs (bf16)
-      if (!valid) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
-      }
-      *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gq);
-      *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, (E + e8) / 8)) = pack8_bf16(gk);
-      *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gv);
-      *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(a8);
-      *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(xm8);
-    }
-    if (has_next && head == 0) stage_dg(dgn, s ^ 1);      // [dig|dfg] of the next tile (its buffer was last read two tiles ago)
+    if (quarter == 0) stage_dg(dgn, it & 1, grp == 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid == 0) {
-      const uint32_t dgs = smem_u32(smem + L::DG0 + s * L::DG_STRIDE);
-      // d[q_proj|k_proj] as a dense (2E x E) product g_{q|k}^T act; only its 4x4 diagonal blocks are read back
-      umma_gemm(tmem + L::T_DWQK, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
-                umma_idesc(128, E, true, true), kTok, it > 0);
-      umma_gemm(tmem + L::T_DWV, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16,
-                umma_idesc(128, E, true, true), kTok, it > 0);
-      // [dig|dfg]^T act and [dig|dfg]^T x_mlstm (rows hh = 0..7 of a 128-row window)
-      umma_gemm(tmem + L::T_DWGA, dgs, 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16, umma_idesc(128, E, true, true), kTok, it > 0);
-      umma_gemm(tmem + L::T_DWGX, dgs, 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16, umma_idesc(128, E, true, true), kTok, it > 0);
-      umma_commit(&bar2);
+    if (tid == 0) issue_mma1(tmem, it & 1);
+
+    bool first_tile = true;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int b = tile / g.nc, ch = tile % g.nc;
+      const int nxt = tile + gridDim.x;
+      const bool has_next = nxt < ntiles;
+      // one tile ahead: x_mlstm stage, halo and gate gradients of the next tile
       if (has_next) {
-        issue_mma1(tmem, s ^ 1);      // the gate-path accumulator has been drained by everybody (sync above)
-        issue_da(nxt);                // ... and so has the d_act block
+        if (tid == 0) issue_xm(nxt, s ^ 1);
+        load_halo(nxt, s ^ 1);
+        if (quarter == 0) load_dg(nxt, dgn);
       }
+      const bool valid = ch * kTok + tok < g.S;
+      mbar_wait(&bar_xm[s], (it >> 1) & 1);
+      if (!first_tile) {      // the previous tile's weight-gradient products still read the operand tiles this loop rewrites
+        mbar_wait(&bar2, (it - 1) & 1);
+        tc_fence_after();
+      }
+      const size_t tm_base = (static_cast<size_t>(tile) * E + ch0) * kTok + tok;
+      const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE);
+      const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE + L::BLK);
+      const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
+      bool first = true;
+#pragma unroll
+      for (int e8 = quarter * CPT; e8 < (quarter + 1) * CPT; e8 += 8) {      // channel within the group
+        const int lh = e8 / DH, d0 = e8 % DH;                                 // cell head within the group, offset inside it
+        float a8[8], xm8[8], cv8[8], xr[4][8];
+        // x_mlstm of tokens tau-3+k; only the first warp of a quarter reaches into the halo in front of the chunk
+        if ((tok & ~31) != 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xr[k][j] = s_xm[(e8 + j) * kTok + tok - 3 + k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
+        }
+        float gq[8], gk[8], gv[8], dsk[8];
+        const size_t row = ((static_cast<size_t>(b) * 4 + hd0 + lh) * g.Sp + ch * kTok + tok) * DHP + d0;
+        {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(dq + row)), c = __ldg(reinterpret_cast<const float4*>(dq + row + 4));
+          gq[0] = a.x, gq[1] = a.y, gq[2] = a.z, gq[3] = a.w, gq[4] = c.x, gq[5] = c.y, gq[6] = c.z, gq[7] = c.w;
+          const float4 a2 = __ldg(reinterpret_cast<const float4*>(dk + row)), c2 = __ldg(reinterpret_cast<const float4*>(dk + row + 4));
+          gk[0] = a2.x, gk[1] = a2.y, gk[2] = a2.z, gk[3] = a2.w, gk[4] = c2.x, gk[5] = c2.y, gk[6] = c2.z, gk[7] = c2.w;
+          const float4 a3 = __ldg(reinterpret_cast<const float4*>(dv + row)), c3 = __ldg(reinterpret_cast<const float4*>(dv + row + 4));
+          gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = e8 + j;
+          const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + e * 4);
+          cv8[j] = par[L::P_CB + e] + w.x * xr[0][j] + w.y * xr[1][j] + w.z * xr[2][j] + w.w * xr[3][j];
+          xm8[j] = xr[3][j];
+        }
+        // everything above is independent of the gate-path UMMA and of d_act
+        if (first) {
+          mbar_wait(&bar1, it & 1);
+          tc_fence_after();
+          mbar_wait(&bar_da, it & 1);
+          first = false;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
+        float t8[8];
+        tmem_ld8(tmem + lane_base + L::T_GQ + (0 * HG + lh) * DHP + d0, t8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gq[j] = valid ? gq[j] + t8[j] : 0.f;
+        tmem_ld8(tmem + lane_base + L::T_GQ + (1 * HG + lh) * DHP + d0, t8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gk[j] = valid ? gk[j] + t8[j] : 0.f;
+        tmem_ld8(tmem + lane_base + L::T_GQ + (2 * HG + lh) * DHP + d0, t8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = valid ? gv[j] + t8[j] : 0.f;
+        float da8[8], dxv8[8];
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          const int wb = ((e8 >> 2) + blk) * 16;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            float sa = 0.f, sv = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              sa += par[L::P_WQ + wb + o * 4 + d] * gq[blk * 4 + o] + par[L::P_WK + wb + o * 4 + d] * gk[blk * 4 + o];
+              sv += par[L::P_WV + wb + o * 4 + d] * gv[blk * 4 + o];
+            }
+            da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
+          }
+        }
+        float dc8[8], prod[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = e8 + j;
+          float ds;
+          silu_both(cv8[j], a8[j], ds);
+          dc8[j] = valid ? (da8[j] + dsk[j]) * ds : 0.f;
+          dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc8[j];
+          dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? dxv8[j] : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) prod[j * 4 + k] = dc8[j] * xr[k][j];
+        }
+        warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
+        warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
+        // operands of the weight-gradient GEMMs (bf16)
+        if (!valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gq);
+        *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, (EG + e8) / 8)) = pack8_bf16(gk);
+        *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gv);
+        *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(a8);
+        *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(xm8);
+      }
+      if (has_next && quarter == 0) stage_dg(dgn, s ^ 1, grp == 0);      // [dig|dfg] of the next tile (its buffer was last read two tiles ago)
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (tid == 0) {
+        const uint32_t dgs = smem_u32(smem + L::DG0 + s * L::DG_STRIDE);
+        const uint32_t accu = first_tile ? 0u : 1u;
+        // d[q_proj|k_proj] as a dense (2 EG x EG) product g_{q|k}^T act; only its 4x4 diagonal blocks are read back
+        umma_gemm(tmem + L::T_DWQK, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
+                  umma_idesc(128, EG, true, true), kTok, accu);
+        umma_gemm(tmem + L::T_DWV, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16,
+                  umma_idesc(128, EG, true, true), kTok, accu);
+        // [dig|dfg]^T act and [dig|dfg]^T x_mlstm (rows hh = 0..7 of a 128-row window)
+        umma_gemm(tmem + L::T_DWGA, dgs, 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16, umma_idesc(128, EG, true, true), kTok, accu);
+        umma_gemm(tmem + L::T_DWGX, dgs, 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16, umma_idesc(128, EG, true, true), kTok, accu);
+        umma_commit(&bar2);
+        if (has_next) {
+          issue_mma1(tmem, s ^ 1);      // the gate-path accumulator has been drained by everybody (sync above)
+          issue_da(nxt);                // ... and so has the d_act block
+        }
+      }
+      first_tile = false;
     }
-  }
-  if (it > 0) {
     mbar_wait(&bar2, (it - 1) & 1);
     tc_fence_after();
-  }
-  // ---- flush the accumulated parameter gradients
-  // rows hh = 0..7 of the two gate reductions live in TMEM lanes 0..7: warps 0, 4, 8, 12 (quadrant 0) share the columns,
-  // 16 (= four 4x4 blocks) at a time; the block-diagonal projections are applied here
-  if ((warp & 3) == 0) {
+    // ---- flush the parameter gradients of this channel group
+    // rows hh = 0..7 of the two gate reductions live in TMEM lanes 0..7: warps 0, 4, 8, 12 (quadrant 0) share the columns,
+    // 16 (= four 4x4 blocks) at a time; the block-diagonal projections are applied here
+    if ((warp & 3) == 0) {
 #pragma unroll 1
-    for (int c0 = head * 16; c0 < E; c0 += 64) {
-      float ga[16], gx[16];
-      tmem_ld16(tmem + lane_base + L::T_DWGA + c0, ga);
-      tmem_ld16(tmem + lane_base + L::T_DWGX + c0, gx);
-      if (tok < 8) {
-        float* W = tok < 4 ? gr.igate_weight + tok * 3 * E : gr.fgate_weight + (tok - 4) * 3 * E;
+      for (int c0 = quarter * 16; c0 < EG; c0 += 64) {
+        float ga[16], gx[16];
+        tmem_ld16(tmem + lane_base + L::T_DWGA + c0, ga);
+        tmem_ld16(tmem + lane_base + L::T_DWGX + c0, gx);
+        if (tok < 8) {
+          float* W = tok < 4 ? gr.igate_weight + tok * 3 * E : gr.fgate_weight + (tok - 4) * 3 * E;
 #pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-          const int wb = ((c0 >> 2) + blk) * 16;
+          for (int blk = 0; blk < 4; ++blk) {
+            const int wb = ((c0 >> 2) + blk) * 16;
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            float sq = 0.f, sk = 0.f, sv = 0.f;
+            for (int o = 0; o < 4; ++o) {
+              float sq = 0.f, sk = 0.f, sv = 0.f;
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
-              sq += par[L::P_WQ + wb + o * 4 + d] * ga[blk * 4 + d];
-              sk += par[L::P_WK + wb + o * 4 + d] * ga[blk * 4 + d];
-              sv += par[L::P_WV + wb + o * 4 + d] * gx[blk * 4 + d];
+              for (int d = 0; d < 4; ++d) {
+                sq += par[L::P_WQ + wb + o * 4 + d] * ga[blk * 4 + d];
+                sk += par[L::P_WK + wb + o * 4 + d] * ga[blk * 4 + d];
+                sv += par[L::P_WV + wb + o * 4 + d] * gx[blk * 4 + d];
+              }
+              const int e_out = ch0 + c0 + blk * 4 + o;
+              atomicAdd(W + 0 * E + e_out, sq);
+              atomicAdd(W + 1 * E + e_out, sk);
+              atomicAdd(W + 2 * E + e_out, sv);
             }
-            const int e_out = c0 + blk * 4 + o;
-            atomicAdd(W + 0 * E + e_out, sq);
-            atomicAdd(W + 1 * E + e_out, sk);
-            atomicAdd(W + 2 * E + e_out, sv);
           }
         }
       }
     }
+    for (int i = tid; i < EG * 4; i += blockDim.x) atomicAdd(gr.conv_weight + ch0 * 4 + i, acc[L::A_CW + i]);
+    for (int i = tid; i < EG; i += blockDim.x) atomicAdd(gr.conv_bias + ch0 + i, acc[L::A_CB + i]);
+    {
+      // row r of the (2 EG x EG) product: r < EG -> q_proj row e_out = r, r >= EG -> k_proj; its diagonal block = 4 columns.
+      // TMEM loads take a warp-uniform column address: every quarter walks a quarter of the column groups.
+      const int r = tok, e_out = r % EG, blk = e_out / 4;
+      const int want = (4 * blk) & ~7;
+      if ((warp & 3) * 32 < 2 * EG) {
+#pragma unroll 1
+        for (int c0 = quarter * 8; c0 < EG; c0 += 32) {
+          float v[8];
+          tmem_ld8(tmem + lane_base + L::T_DWQK + c0, v);
+          if (want == c0 && r < 2 * EG) {
+            float* W = (r < EG ? gr.q_weight : gr.k_weight) + ch0 * 4 + blk * 16 + (e_out % 4) * 4;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) atomicAdd(W + d, ((4 * blk) & 7) ? v[4 + d] : v[d]);
+          }
+        }
+      }
+      if ((warp & 3) * 32 < EG) {
+#pragma unroll 1
+        for (int c0 = quarter * 8; c0 < EG; c0 += 32) {
+          float v[8];
+          tmem_ld8(tmem + lane_base + L::T_DWV + c0, v);
+          if (want == c0 && r < EG) {
+            float* W = gr.v_weight + ch0 * 4 + blk * 16 + (e_out % 4) * 4;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) atomicAdd(W + d, ((4 * blk) & 7) ? v[4 + d] : v[d]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();      // accumulators, parameter slices and stages are free for the next channel group
+    tc_fence_after();
   }
-  for (int i = tid; i < E * 4; i += blockDim.x) atomicAdd(gr.conv_weight + i, acc[L::A_CW + i]);
-  for (int i = tid; i < E; i += blockDim.x) atomicAdd(gr.conv_bias + i, acc[L::A_CB + i]);
   if (tid < 4) atomicAdd(gr.igate_bias + tid, acc[L::A_GB + tid]);
   else if (tid < 8) atomicAdd(gr.fgate_bias + tid - 4, acc[L::A_GB + tid]);
-  {
-    // row r of the (2E x E) product: r < E -> q_proj row e_out = r, r >= E -> k_proj; its diagonal block = 4 columns.
-    // TMEM loads take a warp-uniform column address: every head group walks a quarter of the column groups.
-    const int r = tok, e_out = r % E, blk = e_out / 4;
-    const int want = (4 * blk) & ~7;
-    if ((warp & 3) * 32 < 2 * E) {
-#pragma unroll 1
-      for (int c0 = head * 8; c0 < E; c0 += 32) {
-        float v[8];
-        tmem_ld8(tmem + lane_base + L::T_DWQK + c0, v);
-        if (want == c0 && r < 2 * E) {
-          float* W = (r < E ? gr.q_weight : gr.k_weight) + blk * 16 + (e_out % 4) * 4;
-#pragma unroll
-          for (int d = 0; d < 4; ++d) atomicAdd(W + d, ((4 * blk) & 7) ? v[4 + d] : v[d]);
-        }
-      }
-    }
-    if ((warp & 3) * 32 < E) {
-#pragma unroll 1
-      for (int c0 = head * 8; c0 < E; c0 += 32) {
-        float v[8];
-        tmem_ld8(tmem + lane_base + L::T_DWV + c0, v);
-        if (want == c0 && r < E) {
-          float* W = gr.v_weight + blk * 16 + (e_out % 4) * 4;
-#pragma unroll
-          for (int d = 0; d < 4; ++d) atomicAdd(W + d, ((4 * blk) & 7) ? v[4 + d] : v[d]);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -1116,7 +898,7 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
                           const float* dk, const float* dv, const float* dig, const float* dfg, const float* d_act, const float* dz,
                           const xhved_vil_params* p, const VilGeom& g, float* dx, const xhved_vil_grads* gr, float* ws_dconv,
                           float* ws_dxmv, cudaStream_t st) {
-  if constexpr (C <= 32) {
+  {
     const size_t smem = PreBwdATC<C>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1124,13 +906,6 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     const int ntiles = g.B * g.nc;
     vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, xm, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv,
                                                                                   *gr, ntiles);
-  } else {
-    // dim 64: the CUDA-core kernel A (recomputes the forward from x); TMEM cannot hold its gate products in one pass
-    const size_t smem = PreBwdASmem<C>::TOTAL * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    ProfScope ps(K_VIL_PRE_BWD_A, st);
-    vil_pre_bwd_a_kernel<C><<<g.B * g.nc, 160, smem, st>>>(x, *p, g, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv, *gr);
   }
   {
     const size_t smem = PreBwdBTC<C>::TOTAL;
