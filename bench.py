@@ -171,17 +171,13 @@ class HotPath:
         """Record the step of each slot (same public-API calls, static device buffers) into a CUDA graph: the ~30 launches
         of a step otherwise cost more host time than the kernels take on the device."""
         for slot, sl in enumerate(self.slots):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self._body(slot)
-            sl["graph"], sl["out"] = graph, out
+            sl["graph"] = self.xh.GraphedStep(lambda slot=slot: self._body(slot), warmup=1)
 
     def step(self, slot=0, graphed=False):
         sl = self.slots[slot]
         torch.cuda.current_stream().wait_event(sl["ready"])
         if graphed:
-            sl["graph"].replay()
-            out = sl["out"]
+            out = sl["graph"]()
         else:
             out = self._body(slot)
         if self.world > 1:
