@@ -136,6 +136,29 @@ int xhved_mlstm_unpack(const void* tiles, int BH, int S, int dh, int dhp, float*
 /* fp32 (BH, nc*128, dhp) row-major -> (BH, S, dh) contiguous (gradients of the stand-alone entry point) */
 int xhved_mlstm_unpad_rows(const float* src, int BH, int S, int dh, int dhp, float* dst, void* stream);
 
+/* Sizes of the caller-allocated buffers (host-only queries, no device needed).  The library never allocates: outputs, saved
+ * state and scratch are passed in, and these two functions are the single source of truth for how large they must be.
+ *   tile_bytes    each of q, k, v, h, dh tiles                 (BH * nc * 128 * dhp bf16)
+ *   row_bytes     each of ig, fg, m, den, dig, dfg, ws_dc       (BH * nc * 128 fp32)
+ *   dstate_bytes  ws_dstate                                     (BH * nc * dhp * (dhp+16) fp32)
+ *   chunk_bytes   each of ws_g, ws_amax, m_prev, mu_next        (BH * nc fp32)
+ *   states_bytes  each of states, rstates                       (BH * nc bf16 hi/lo pairs of dhp * (dhp+16))
+ *   grad_bytes    each of dq, dk, dv                            (BH * nc * 128 * dhp fp32) */
+typedef struct {
+  int nc, dhp;
+  int64_t tile_bytes, row_bytes, dstate_bytes, chunk_bytes, states_bytes, grad_bytes;
+} xhved_mlstm_workspace;
+int xhved_mlstm_workspace_query(int BH, int S, int dh, xhved_mlstm_workspace* out);
+/* ViL block of width C on B sequences of S tokens: its cell runs with BH = 4*B, dh = C/2;
+ *   token_minor_bytes   each of act, z, xm, d_act, dz, ws_dconv, ws_dxmv   (B * nc * 2C * 128 fp32)
+ *   grad_replica_stride floats per replica of the flat parameter-gradient buffer (sum of the 14 parameter sizes, padded) */
+typedef struct {
+  xhved_mlstm_workspace cell;
+  int64_t token_minor_bytes;
+  int64_t grad_replica_stride;
+} xhved_vil_workspace;
+int xhved_vil_workspace_query(int B, int S, int C, xhved_vil_workspace* out);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (off by default; used by bench.py to
  * attribute time to kernels).  xhved_profile_read synchronises the device, returns accumulated milliseconds
  * and launch counts per kernel id since the last read, and resets. */

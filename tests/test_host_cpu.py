@@ -60,3 +60,28 @@ def test_patch_and_unpatch_reference_model():
     with torch.no_grad():
         seg, _ = model.eval()(torch.rand(1, 4, 32, 32, 32), [14], valid=True)   # stock path still runs
     assert seg.shape == (1, 3, 32, 32, 32)
+
+
+def test_workspace_queries_match_the_host_layer():
+    """xhved_*_workspace_query (host-only) against the sizes the Python layer derives from shapes and parameters."""
+    import ctypes
+    import xlstm_hved_b200 as xh
+    from xlstm_hved_b200 import _lib
+    lib = _lib.load_library()
+    for dim, B, S in ((16, 1, 150), (32, 2, 4096), (64, 3, 6144)):
+        w = _lib.VilWorkspaceSizes()
+        assert lib.xhved_vil_workspace_query(B, S, dim, ctypes.byref(w)) == 0
+        E, nc = 2 * dim, (S + 127) // 128
+        dhp = max(E // 4, 16)
+        assert (w.cell.nc, w.cell.dhp) == (nc, dhp)
+        assert w.cell.tile_bytes == 4 * B * nc * 128 * dhp * 2
+        assert w.cell.row_bytes == 4 * B * nc * 128 * 4 and w.cell.chunk_bytes == 4 * B * nc * 4
+        assert w.cell.dstate_bytes == 4 * B * nc * dhp * (dhp + 16) * 4 == w.cell.states_bytes
+        assert w.cell.grad_bytes == 4 * B * nc * 128 * dhp * 4
+        assert w.token_minor_bytes == B * nc * E * 128 * 4
+        blk = xh.ViLBlock(dim, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
+        n_params = sum(p.numel() for p in xh.modules.vil_block_params(blk))
+        assert w.grad_replica_stride == (n_params + 31) // 32 * 32
+    bad = _lib.MlstmWorkspace()
+    assert lib.xhved_mlstm_workspace_query(4, 100, 200, ctypes.byref(bad)) == -2      # XHVED_ERR_UNSUPPORTED_DH
+    assert lib.xhved_vil_workspace_query(1, 100, 48, ctypes.byref(_lib.VilWorkspaceSizes())) == -4   # XHVED_ERR_UNSUPPORTED_DIM

@@ -199,12 +199,15 @@ class CellBuffers:
 
     def __init__(self, BH: int, S: int, dh: int, device):
         self.BH, self.S, self.dh = BH, S, dh
-        self.dhp = padded_dh(dh)
-        self.nc = (S + CHUNK - 1) // CHUNK
+        sizes = _lib.MlstmWorkspace()
+        check(_lib.load_library().xhved_mlstm_workspace_query(BH, S, dh, ctypes.byref(sizes)), "xhved_mlstm_workspace_query")
+        self.dhp, self.nc = sizes.dhp, sizes.nc
         self.Sp = self.nc * CHUNK
         ne = self.dhp + 16
         bf, f32 = torch.bfloat16, torch.float32
         nt = BH * self.nc
+        # the shapes below restate what the library reports (tests/test_host_cpu.py checks the two against each other)
+        assert sizes.tile_bytes == nt * CHUNK * self.dhp * 2 and sizes.dstate_bytes == nt * self.dhp * ne * 4
         e = lambda *s, dtype=f32: torch.empty(*s, device=device, dtype=dtype)
         self.q = e(nt, CHUNK * self.dhp, dtype=bf)
         self.k = e(nt, CHUNK * self.dhp, dtype=bf)
@@ -406,8 +409,11 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float =
         dy_tok = dy_tok.float()
     # parameter gradients are accumulated with global atomics into GRAD_REPLICAS zero-filled copies (CTA i -> copy i % R)
     # to spread the traffic over L2 slices; xhved_reduce_replicas sums the copies at the end
+    sizes = _lib.VilWorkspaceSizes()
+    check(lib.xhved_vil_workspace_query(x_tok.shape[0], x_tok.shape[1], x_tok.shape[2], ctypes.byref(sizes)), "xhved_vil_workspace_query")
+    stride = sizes.grad_replica_stride
     P = sum(p.numel() for p in params)
-    stride = (P + 31) // 32 * 32
+    assert stride >= P
     flat = torch.zeros(GRAD_REPLICAS * stride, device=dev, dtype=torch.float32)
     grads, off = [], 0
     for p in params:
