@@ -189,26 +189,7 @@ __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------ phase 3
-// One row of a 32-column block: p = S * exp2(u_row + v_col), bf16 P written to the row's four 16-byte groups (2 KB apart).
-template <bool MASK>
-__device__ __forceinline__ float decay_block(const float* sv, float urow, const float* vcol, int s0, int row, unsigned char* dst) {
-  float rowsum = 0.f;
-#pragma unroll
-  for (int j8 = 0; j8 < 4; ++j8) {
-    float p[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = fast_exp2(urow + vcol[j8 * 8 + j]);
-      p[j] = sv[j8 * 8 + j] * d;
-      if (MASK) p[j] = (s0 + j8 * 8 + j <= row) ? p[j] : 0.f;
-      rowsum += p[j];
-    }
-    *reinterpret_cast<uint4*>(dst + j8 * (kL * 16)) = pack8_bf16(p);
-  }
-  return rowsum;
-}
-
-// 16 columns of one row (two 16-byte groups, 2 KB apart)
+// p = S * exp2(u_row + v_col) for 16 columns of one row, bf16 P written to the row's two 16-byte groups (2 KB apart).
 template <bool MASK>
 __device__ __forceinline__ float decay_half(const float* sv, float urow, const float* vcol, int s0, int row, unsigned char* dst) {
   float rowsum = 0.f;

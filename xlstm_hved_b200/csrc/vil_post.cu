@@ -3,7 +3,7 @@
 // Restates, per token, vision_lstm.py:271-287 (MultiHeadLayerNorm: per-head normalisation over DH, weight
 // 1+w, eps 1e-5), :437 (learnable skip of the conv activation), :440 (SiLU(z) gate), :443 (proj_down),
 // :446-451 (un-flip, folded into the index map), vision_lstm_util.py:171-175 (residual add) and the token ->
-// NCDHW transpose of UxLSTMEnc_3d.py:61.  One CTA = 128 tokens; thread r owns token r.
+// NCDHW transpose of UxLSTMEnc_3d.py:61.  One tile = 128 tokens; 512 threads = token x head.
 #include "vil_common.cuh"
 
 namespace xhved {

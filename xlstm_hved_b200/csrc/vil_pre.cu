@@ -15,7 +15,7 @@ namespace xhved {
 // ------------------------------------------------------------------ forward (tcgen05 version)
 // proj_up runs as a 3-product bf16 hi/lo UMMA (tokens x 2E, ~fp32 accuracy), the gate pre-activations as a UMMA over the
 // bf16 q|k|v tile that is afterwards bulk-stored to the cell's operand tiles; conv / SiLU / the 4x4 block-diagonal
-// projections stay on CUDA cores.  128 threads, thread = token.
+// projections stay on CUDA cores.
 template <int C>
 struct PreTC {
   static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH, NQ = 12 * DHP;
