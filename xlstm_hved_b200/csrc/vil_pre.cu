@@ -404,37 +404,43 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
       }
     }
     // ---- d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
+    // the four taps read dconv of tokens tau..tau+3: this tile, or the first tokens of the next tile of the same sequence
+    const float* pk[4];
+    bool vk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = tok + k;
+      vk[k] = tau + k < g.S;
+      pk[k] = dconv + static_cast<size_t>(tile + (vk[k] ? (t >> 7) : 0)) * E * kTok + (t & (kTok - 1));
+    }
+    const float* px = dxmv + tm_chunk + tok;
+    const float* pz = dz + tm_chunk + tok;
+    // every pass handles 8 conv channels and 8 z channels of this token, with all of their loads issued together
 #pragma unroll 1
-    for (int o8 = part * 8; o8 < 2 * E; o8 += 32) {
+    for (int o8 = part * 8; o8 < E; o8 += 32) {
+      float dc[4][8], dzv[8], dxv[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dc[k][i] = vk[k] ? __ldg(pk[k] + (o8 + i) * kTok) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dxv[i] = __ldg(px + (o8 + i) * kTok), dzv[i] = __ldg(pz + (o8 + i) * kTok);
       float d8[8];
-      if (o8 < E) {
-        float dc[4][8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int tp = tau + k;
-          const size_t base = (static_cast<size_t>(b) * g.nc + (tp < g.S ? tp / kTok : 0)) * E * kTok + (tp < g.S ? tp % kTok : 0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dc[k][i] = tp < g.S ? __ldg(dconv + base + static_cast<size_t>(o8 + i) * kTok) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int o = o8 + i;
-          float d = __ldg(dxmv + tm_chunk + static_cast<size_t>(o) * kTok + tok);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) d += par[L::P_CW + o * 4 + 3 - k] * dc[k][i];
-          d8[i] = valid ? d : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float d = __ldg(dz + tm_chunk + static_cast<size_t>(o8 - E + i) * kTok + tok);
-          d8[i] = valid ? d : 0.f;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(par + L::P_CW + (o8 + i) * 4);      // taps of channel o8 + i
+        const float d = dxv[i] + w.w * dc[0][i] + w.z * dc[1][i] + w.y * dc[2][i] + w.x * dc[3][i];
+        d8[i] = valid ? d : 0.f;
       }
       uint4 hi, lo;
       split8_hilo(d8, hi, lo);
       *reinterpret_cast<uint4*>(smem + L::DINHI + tile_off16(kTok, tok, o8 / 8)) = hi;
       *reinterpret_cast<uint4*>(smem + L::DINLO + tile_off16(kTok, tok, o8 / 8)) = lo;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d8[i] = valid ? dzv[i] : 0.f;
+      split8_hilo(d8, hi, lo);
+      *reinterpret_cast<uint4*>(smem + L::DINHI + tile_off16(kTok, tok, (E + o8) / 8)) = hi;
+      *reinterpret_cast<uint4*>(smem + L::DINLO + tile_off16(kTok, tok, (E + o8) / 8)) = lo;
     }
     // loads whose latency hides behind the MMA: the residual path's upstream gradient and the next tile's tokens
     float dyin[CP];
