@@ -168,14 +168,18 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, con
     for (int s = 0; s < NS; ++s) {
       if (s < ss.n) {
         const uint32_t mask = ss.mask[s];
-        float om[V], ol[V];
+        // var^ = 1 / sum T: one reciprocal serves mu^ = (sum mu T) var^, exp(logvar^) = var^ (KL) and, through its square
+        // root, the standard deviation of the sample
+        float om[V], ol[V], var[V], sd[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
           float st_ = T[0][j], sm = M[0][j] * T[0][j];
 #pragma unroll
           for (int e = 1; e < 5; ++e)
             if ((mask >> (e - 1)) & 1u) st_ += T[e][j], sm += M[e][j] * T[e][j];
-          om[j] = __fdividef(sm, st_);
+          var[j] = __fdividef(1.0f, st_);
+          sd[j] = rsqrtf(st_);
+          om[j] = sm * var[j];
           ol[j] = -__logf(st_);
         }
         st<V>(out_mu + s * n + i, om);
@@ -184,12 +188,12 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, con
           float nz[V], z[V];
           ld<V>(noise + s * n + i, nz);
 #pragma unroll
-          for (int j = 0; j < V; ++j) z[j] = om[j] + nz[j] * __expf(0.5f * ol[j]);
+          for (int j = 0; j < V; ++j) z[j] = om[j] + nz[j] * sd[j];
           st<V>(out_z + s * n + i, z);
         }
         if (kld_out) {
 #pragma unroll
-          for (int j = 0; j < V; ++j) kld_acc[s] += -1.0f - ol[j] + (__expf(ol[j]) + om[j] * om[j]);   // / (1 + 1e-8) == 1 in fp32
+          for (int j = 0; j < V; ++j) kld_acc[s] += -1.0f - ol[j] + (var[j] + om[j] * om[j]);   // / (1 + 1e-8) == 1 in fp32
         }
       }
     }
