@@ -295,18 +295,17 @@ __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, 
 #pragma unroll
           for (int e = 0; e < 5; ++e)
             if ((mask >> e) & 1u) S += T[e][j], sm += M[e][j] * T[e][j];
-          const float rS = __fdividef(1.0f, S);
+          const float rS = __fdividef(1.0f, S);      // = exp(logvar^)
           const float mh = sm * rS;
-          const float lh = -__logf(S);
           float a = gm[j], b = gl[j];
           if (g_z) {
             a += gz[j];
-            b += gz[j] * nz[j] * 0.5f * __expf(0.5f * lh);
+            b += gz[j] * nz[j] * 0.5f * rsqrtf(S);   // d z / d logvar^ = 0.5 eps exp(0.5 logvar^)
           }
           if (use_kld) {
             const float ks = L.kld_scale[s];
             a += ks * 2.0f * mh;                       // / (1 + 1e-8) == 1 in fp32
-            b += ks * (-1.0f + __expf(lh));
+            b += ks * (-1.0f + rS);
           }
 #pragma unroll
           for (int e = 0; e < 5; ++e)
