@@ -237,9 +237,10 @@ int xhved_vil_post_fwd(const float* x, const void* h_tiles, const float* act, co
  * accumulates outnorm / skip / proj_down gradients. */
 int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
                        const xhved_vil_shape* sh, void* dh_tiles, float* d_act, float* dz, const xhved_vil_grads* g, void* stream);
-/* K2 backward: from the forward's saved xm and q/k/v tiles, dq, dk, dv (fp32 (BH, nc*128, dhp)), dig, dfg (padded),
- * d_act (skip path) and dz computes dx = dy + d(branch)/dx (dy and dx both use the y_* strides of sh) and accumulates
- * parameter gradients.  Scratch: ws_dconv, ws_dxmv fp32 (B, nc, E, 128) each. */
+/* K2 backward: from the forward's saved xm, dq, dk, dv (fp32 (BH, nc*128, dhp)), dig, dfg (padded), d_act (skip path) and
+ * dz computes dx = dy + d(branch)/dx (dy and dx both use the y_* strides of sh) and accumulates parameter gradients.
+ * q_tiles / k_tiles / v_tiles are accepted for ABI stability and not read: the gate-weight gradient is taken through the
+ * block-diagonal projections ([dig|dfg]^T q = ([dig|dfg]^T act) Wq^T).  Scratch: ws_dconv, ws_dxmv fp32 (B, nc, E, 128) each. */
 int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const void* q_tiles, const void* k_tiles, const void* v_tiles,
                       const float* dq, const float* dk, const float* dv, const float* dig, const float* dfg, const float* d_act,
                       const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx, const xhved_vil_grads* g,
