@@ -1,0 +1,68 @@
+"""Where the hot path sits inside the whole reference model ("the callers either side of the path").
+
+Times the UNMODIFIED reference XLSTM_HVED (f_maps=4, 128^3, B=1) on the GPU with its stock PyTorch ViL / PoE path and with
+xh.patch_model applied: inference forward (valid=True, subset 14) and a training-like forward+backward.  Also times the
+hot-path modules alone inside the stock model (forward hooks would perturb it, so the ViL wrapper is timed stand-alone on a
+tensor of the bottleneck shape).  Needs a reference tree (baseline/_ref or $XHVED_REFERENCE); test/dev tooling, not product.
+"""
+import contextlib, io, json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import xlstm_hved_b200 as xh            # noqa: E402
+from oracle import ref_loader           # noqa: E402
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    if ref_loader.find_reference() is None:
+        print(json.dumps({"unavailable": "no reference tree"}))
+        return
+    model = ref_loader.build_model(f_maps=4, seed=1).cuda()
+    x = torch.rand(1, 4, 128, 128, 128, device="cuda")
+    out = {}
+
+    def infer():
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            model(x, [14], valid=True)
+
+    def train_step():
+        model.zero_grad(set_to_none=True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            seg, (mu_list, logvar_list), recon = model(x, [14], recon=True, valid=False)
+        loss = seg.float().mean() + sum(r.float().mean() for r in recon) + sum(m.float().pow(2).mean() for m in mu_list)
+        loss.backward()
+
+    feat = torch.randn(1, 32, 16, 16, 16, device="cuda", requires_grad=True)
+
+    def vil_alone():
+        y = model.mViL(feat)
+        y.sum().backward()
+
+    for tag in ("stock", "patched"):
+        if tag == "patched":
+            xh.patch_model(model)
+        model.eval()
+        out[f"{tag}_infer_ms"] = round(timeit(infer), 2)
+        model.train()
+        out[f"{tag}_train_fwd_bwd_ms"] = round(timeit(train_step, iters=3, warm=1), 2)
+        out[f"{tag}_mViL_fwd_bwd_ms"] = round(timeit(vil_alone, iters=10), 3)
+    xh.unpatch_model(model)
+    out["note"] = "reference XLSTM_HVED f_maps=4, one 128^3 volume, fp32 eager on one B200; mViL = the bottleneck ViL wrapper alone"
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
