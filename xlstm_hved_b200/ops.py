@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_float, c_uint32, c_void_p
+from ctypes import c_float, c_uint32
 
 import torch
 
