@@ -491,30 +491,73 @@ def cpu_hot_path_one_volume(params_f, params_r, x, mus, lvs, gy, gzs):
     return float(loss)
 
 
+def reference_hot_path_one_volume(ns, blk_f, blk_r, x, mus, lvs, gy, gzs):
+    """The same hot path through the UNMODIFIED reference classes on the CPU: vision_lstm.ViLBlock (which builds the S x S
+    decay matrix, vision_lstm.py:48-130), buildingblocks.ProductOfExperts, RA_HVED.reparametrize / clip, loss.KL_divergence."""
+    x = x.clone().requires_grad_()
+    tok = x.reshape(1, DIM, -1).transpose(-1, -2)
+    y = blk_r(blk_f(tok))
+    loss = (y * gy.reshape(1, DIM, -1).transpose(-1, -2)).sum()
+    experts = ns.buildingblocks.ProductOfExperts()
+    for l in range(4):
+        mm = mus[l].clone().requires_grad_()
+        ll = lvs[l].clone().requires_grad_()
+        mu5 = torch.cat([torch.zeros_like(mm[:1]), mm], 0)                      # RA_HVED.py:576-580
+        lv5 = torch.cat([torch.zeros_like(ll[:1]), ns.RA_HVED.clip(ll)], 0)
+        a, b = experts(mu5, lv5, SUBSET_FULL)
+        z = ns.RA_HVED.reparametrize(a, b, False)
+        loss = loss + (z * gzs[l][0]).sum() + 0.2 * ns.loss.KL_divergence(a, b) / 4
+    loss.backward()
+    return float(loss)
+
+
 def cpu_reference_arm(steps, warmup):
+    """CPU timing of the path on the host cores: the reference's own classes when a reference tree travelled with the repo
+    (baseline/_ref, kind "reference"), else the oracle port of the same algorithm (kind "port")."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     import xlstm_hved_b200 as xh
     keys = xh.ops.VIL_PARAM_KEYS
-    blocks = []
-    for seed, direction in ((1, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT), (2, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)):
-        blk = xh.ViLBlock(DIM, direction)
-        randomise_params(blk, seed)
-        sd = blk.state_dict()
-        blocks.append({k: sd[k].clone().requires_grad_() for k in keys})
     x, mus, lvs = synth_inputs(1, 1000, None)
     g = torch.Generator().manual_seed(7)
     gy = torch.randn(1, DIM, *SPATIAL, generator=g)
     gzs = [torch.randn(1, 1, C, d, d, d, generator=g) for C, d in LEVELS]
+    mirrors = []
+    for seed, direction in ((1, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT), (2, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)):
+        blk = xh.ViLBlock(DIM, direction)
+        randomise_params(blk, seed)
+        mirrors.append(blk)
+    step, kind, what = None, "port", "oracle port of the reference's O(S^2) parallel cell + PoE"
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isfile(os.path.join(ref_dir, "RA_HVED.py")):
+        try:
+            os.environ["XHVED_REFERENCE"] = ref_dir
+            from oracle import ref_loader
+            ns = ref_loader.load_reference()
+            vl = ns.vision_lstm
+            real = []
+            for blk, direction in zip(mirrors, (vl.SequenceTraversal.ROWWISE_FROM_TOP_LEFT, vl.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)):
+                rb = vl.ViLBlock(dim=DIM, direction=direction)
+                rb.load_state_dict(blk.state_dict(), strict=True)
+                real.append(rb)
+            step = lambda: reference_hot_path_one_volume(ns, real[0], real[1], x, mus, lvs, gy, gzs)
+            step()                                                   # proves the reference tree is usable before it is timed
+            kind, what = "reference", "the reference's own vision_lstm.ViLBlock / ProductOfExperts / reparametrize / KL_divergence"
+        except Exception as e:
+            print(f"bench.py: reference tree unusable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+            step = None
+    if step is None:
+        blocks = [{k: blk.state_dict()[k].clone().requires_grad_() for k in keys} for blk in mirrors]
+        step = lambda: cpu_hot_path_one_volume(blocks[0], blocks[1], x, mus, lvs, gy, gzs)
     for _ in range(warmup):
-        cpu_hot_path_one_volume(blocks[0], blocks[1], x, mus, lvs, gy, gzs)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_hot_path_one_volume(blocks[0], blocks[1], x, mus, lvs, gy, gzs)
+        step()
     dt = time.perf_counter() - t0
-    return {"value": round(steps / dt, 4), "unit": "volumes/s", "cores": cores, "threads": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} volume(s), one per step, same hot path fwd+bwd (oracle port of the reference's O(S^2) parallel cell "
-                      f"+ PoE, fp32, torch CPU), {dt / steps:.2f} s/volume", "seconds_per_volume": round(dt / steps, 3)}
+    return {"value": round(steps / dt, 4), "unit": "volumes/s", "cores": cores, "threads": torch.get_num_threads(), "kind": kind,
+            "sample": f"{steps} volume(s), one per step, same hot path fwd+bwd ({what}, fp32, torch CPU), {dt / steps:.2f} s/volume",
+            "seconds_per_volume": round(dt / steps, 3)}
 
 
 def run_reference(args):
