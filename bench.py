@@ -14,8 +14,8 @@ plus the S-MVAE product-of-experts fusion / sampling / KL of the same volumes, w
 
 Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = same through the public API
 with host (pinned) inputs copied every step, roofline for the dominant kernel (CUDA-event timed, separate pass),
-cpu_baseline = the oracle port of the reference's algorithm on the host cores (bounded sample).
-`--impl reference` times that CPU port as its own arm.
+cpu_baseline = the reference's own classes (baseline/_ref, when it travelled with the repo) or else the oracle port of its
+algorithm, on the host cores (bounded sample).  `--impl reference` times that CPU path as its own arm.
 """
 from __future__ import annotations
 
