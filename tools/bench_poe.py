@@ -48,5 +48,26 @@ def main():
                                   "bwd_us": round(b_ms * 1e3, 1), "bwd_gbs": round(bb / b_ms / 1e6), "bwd_frac_of_hbm": round(bb / b_ms / 1e6 / peak, 3)}))
 
 
+def fused_levels():
+    """Config 3 as SURVEY 8d words it: ONE launch fusing all 4 latent levels x 15 subsets (inference: no sampling), B in {1, 8, 64};
+    bytes: 32 B in per latent element (constant prior declared, not read) + 8 B out per subset."""
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    for B in (1, 8, 64):
+        levels = []
+        for C, d in ((1, 64), (2, 32), (4, 16), (8, 8)):
+            mu = torch.randn(5, B, C, d, d, d, device="cuda")
+            lv = torch.randn(5, B, C, d, d, d, device="cuda")
+            mu[0].zero_(), lv[0].zero_()
+            levels.append((mu, lv))
+        n = sum(m[0].numel() for m, _ in levels)
+        ms = timeit(lambda: ops.poe_fwd_levels(levels, ALL15, standard_prior=True))
+        nbytes = n * (32 + 15 * 8)
+        print(json.dumps({"fused_levels": 4, "B": B, "subsets": 15, "elements": n, "fwd_us": round(ms * 1e3, 1),
+                          "fwd_gbs": round(nbytes / ms / 1e6), "fwd_frac_of_hbm": round(nbytes / ms / 1e6 / peak, 3)}))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "levels":
+        fused_levels()
+    else:
+        main()
