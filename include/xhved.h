@@ -48,8 +48,10 @@ int xhved_version(void);
  * drop (optional, device, (n/per_sample, 4) uint8): per-sample missing flags of ProductOfExperts2
  * (buildingblocks.py:875-886): expert m+1 of sample b is removed where drop[b][m] != 0.
  * noise/out_z (optional, (n_subsets, n)): z = out_mu + noise * exp(0.5 out_logvar) (RA_HVED.py:741-747).
- * kld_out (optional, device float[n_subsets], must be zeroed by the caller): accumulates
- *   sum over elements of (-1 - lv + (exp(lv) + mu^2)/(1+1e-8)); the caller scales by 0.5/n (loss.py:29-40).
+ * kld_out (optional, device float[n_subsets], must be zeroed by the caller): accumulates the sum over elements of
+ *   -1 + lv_0 - lv + (exp(lv) + (mu - mu_0)^2) / (exp(lv_0) + 1e-8)   with (mu_0, lv_0) = slab 0, the prior the
+ *   reference hands to KL_divergence (loss.py:95-97, 113, 29-40); the caller scales by 0.5/n.  With
+ *   XHVED_POE_STANDARD_PRIOR slab 0 is taken to be (0, 0) without being read.
  * subset_masks is a HOST array of n_subsets (<= 15) entries.
  * flags: XHVED_POE_STANDARD_PRIOR = the caller guarantees that expert 0 is the standard normal the model always passes
  *   (mu = 0, logvar = 0, RA_HVED.py:576-580): its slabs are then never read (T_0 = 1/(1+eps)); mu / logvar still point
@@ -102,6 +104,32 @@ int xhved_poe_fwd_levels(const xhved_poe_level* levels, int n_levels, const uint
                          int flags, void* stream);
 int xhved_poe_bwd_levels(const xhved_poe_level_grad* levels, int n_levels, const uint32_t* subset_masks, int n_subsets, float eps,
                          int flags, void* stream);
+
+/* The same two launches with the model's `clip` fused in (RA_HVED.py:580 applies clip = clamp(logvar, -50, 50),
+ * RA_HVED.py:749-753, to every modality's logvar while the experts are concatenated): with XHVED_POE_CLIP in flags the
+ * logvar slabs of experts 1..4 hold the RAW (unclipped) values, the kernel clamps them to [clip_lo, clip_hi] as it loads
+ * them, and the backward returns zero for d_logvar where the raw value lies outside the interval (torch.clamp's
+ * gradient).  The prior slab is never clipped (the reference does not clip it either). */
+#define XHVED_POE_CLIP 2
+typedef struct {
+  float eps;
+  int flags;              /* XHVED_POE_STANDARD_PRIOR | XHVED_POE_CLIP */
+  float clip_lo, clip_hi;
+} xhved_poe_opts;
+int xhved_poe_fwd_levels_opts(const xhved_poe_level* levels, int n_levels, const uint32_t* subset_masks, int n_subsets,
+                              const xhved_poe_opts* opts, void* stream);
+int xhved_poe_bwd_levels_opts(const xhved_poe_level_grad* levels, int n_levels, const uint32_t* subset_masks, int n_subsets,
+                              const xhved_poe_opts* opts, void* stream);
+
+/* clip on its own (RA_HVED.py:749-753): y = clamp(x, lo, hi) (NaN passes through, like torch.clamp); backward
+ * dx = g where lo <= x <= hi, else 0. */
+int xhved_clip_fwd(const float* x, int64_t n, float lo, float hi, float* y, void* stream);
+int xhved_clip_bwd(const float* x, const float* g, int64_t n, float lo, float hi, float* dx, void* stream);
+
+/* ZeroLayerF (buildingblocks.py:308-323; call sites RA_HVED.py:559, U_Hemis.py:42, buildingblocks.py:880-881):
+ * y[b, :] = mask[b] ? 0 : x[b, :] for a (rows, per_row) fp32 tensor and a per-row uint8 mask.  The backward of the
+ * reference is the same map applied to the incoming gradient, so one entry point serves both directions. */
+int xhved_zero_rows(const float* x, const uint8_t* mask, int64_t rows, int64_t per_row, float* y, void* stream);
 
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);

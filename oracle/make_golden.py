@@ -163,6 +163,43 @@ def gen_poe(ns):
     torch.save(out, os.path.join(OUT, "poe.pt"))
 
 
+def gen_smvae_extras(ns):
+    """Round-2 fixtures from the real reference: compute_KLD with a NON-standard prior in slab 0 (loss.py:95-97, 113) and its
+    gradients w.r.t. all five slabs, clip's gradient mask (RA_HVED.py:749-753) through the fusion, ZeroLayerF fwd + bwd
+    (buildingblocks.py:308-323)."""
+    RA, bb, loss = ns.RA_HVED, ns.buildingblocks, ns.loss
+    g = torch.Generator().manual_seed(77)
+    B, C, d = 2, 2, 6
+    out = {}
+    mu = (1.3 * torch.randn(B, 5, C, d, d, d, generator=g, dtype=torch.float64)).requires_grad_()
+    lv = (0.9 * torch.randn(B, 5, C, d, d, d, generator=g, dtype=torch.float64)).requires_grad_()
+    k = loss.compute_KLD(mu, lv, [14, 2, 9])
+    gm, gl = torch.autograd.grad(k, [mu, lv])
+    out["kld_prior"] = dict(mu=mu.detach(), logvar=lv.detach(), subsets=[14, 2, 9], kld=k.detach(), d_mu=gm, d_logvar=gl)
+    # clip + PoE: raw logvars with entries beyond +-50, gradient must vanish there (torch.clamp's autograd)
+    mm = 1.3 * torch.randn(4, B, C, d, d, d, generator=g, dtype=torch.float64)
+    raw = 30.0 * torch.randn(4, B, C, d, d, d, generator=g, dtype=torch.float64)
+    mm_r, raw_r = mm.clone().requires_grad_(), raw.clone().requires_grad_()
+    mu5 = torch.cat([torch.zeros(1, B, C, d, d, d, dtype=torch.float64), mm_r], 0)
+    lv5 = torch.cat([torch.zeros(1, B, C, d, d, d, dtype=torch.float64), RA.clip(raw_r)], 0)
+    res = {}
+    for idx in (14, 6):
+        a, b = bb.ProductOfExperts()(mu5, lv5, RA.SUBSETS_MODALITIES[idx])
+        ga = torch.randn(a.shape, generator=g, dtype=torch.float64)
+        gb = torch.randn(b.shape, generator=g, dtype=torch.float64)
+        dm, dl = torch.autograd.grad([a, b], [mm_r, raw_r], [ga, gb], retain_graph=True)
+        res[idx] = dict(pd_mu=a.detach(), pd_logvar=b.detach(), g_mu=ga, g_logvar=gb, d_mod_mu=dm, d_raw_logvar=dl)
+    out["clip_poe"] = dict(mod_mu=mm, raw_logvar=raw, clipped=RA.clip(raw), cases=res)
+    # ZeroLayerF
+    x = torch.randn(3, 4, 5, 5, 5, generator=g, dtype=torch.float64).requires_grad_()
+    alpha = torch.tensor([True, False, True])
+    y = bb.ZeroLayerF.apply(x, alpha)
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (dx,) = torch.autograd.grad(y, x, gy)
+    out["zero_layer"] = dict(x=x.detach(), alpha=alpha, y=y.detach(), gy=gy, dx=dx)
+    torch.save(out, os.path.join(OUT, "smvae_extras.pt"))
+
+
 def gen_model_boundary(ns):
     """Run the full XLSTM_HVED on a small seeded volume and record the tensors
     that cross the hot-path boundary (RA_HVED.py:588-597 and 623-626)."""
@@ -200,11 +237,12 @@ def main():
     ns = ref_loader.load_reference()
     assert ns is not None, "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
-    gen_cell(ns)
-    gen_block(ns)
-    gen_wrapper(ns)
-    gen_poe(ns)
-    gen_model_boundary(ns)
+    only = sys.argv[1:]            # e.g. `python oracle/make_golden.py smvae_extras` regenerates one file
+    gens = dict(cell=gen_cell, vil_block=gen_block, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras,
+                model_boundary=gen_model_boundary)
+    for name, fn in gens.items():
+        if not only or name in only:
+            fn(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -314,9 +314,15 @@ def kl_to_prior(mu1, logvar1):
     return 0.5 * torch.mean(-1.0 - logvar1 + (logvar1.exp() + mu1 * mu1) / (1.0 + 1e-8))
 
 
+def kl_divergence(mu1, logvar1, mu2, logvar2, eps: float = 1e-8):
+    """KL_divergence(mu1, logvar1, mu2, logvar2) -- loss.py:29-40 with an explicit second distribution (eps = 1e-8)."""
+    return 0.5 * torch.mean(-1.0 + logvar2 - logvar1 + (logvar1.exp() + (mu1 - mu2) ** 2) / (logvar2.exp() + eps))
+
+
 def compute_kld(mu_b5, logvar_b5, subset_index_list=(14,)):
     """compute_KLD -- loss.py:85-115.  Inputs are (B,5,...) as returned in the
-    model's mu_list/logvar_list (RA_HVED.py:582-583)."""
+    model's mu_list/logvar_list (RA_HVED.py:582-583).  The prior handed to KL_divergence is slab 0 of the inputs
+    (loss.py:95-97, 113) -- the standard normal for XLSTM_HVED, but whatever the caller put there in general."""
     mu = mu_b5.transpose(1, 0)
     lv = logvar_b5.transpose(1, 0)
     tot, cnt = 0.0, 0
@@ -324,8 +330,15 @@ def compute_kld(mu_b5, logvar_b5, subset_index_list=(14,)):
         if idx in subset_index_list:
             cnt += 1
             smu, slv = poe(mu, lv, subset)
-            tot = tot + kl_to_prior(smu, slv)
+            tot = tot + kl_divergence(smu, slv, mu[0], lv[0])
     return tot / cnt
+
+
+def zero_rows(x, alpha):
+    """ZeroLayerF.forward (and .backward applied to the gradient) -- buildingblocks.py:308-323."""
+    y = x.clone()
+    y[alpha] = 0
+    return y
 
 
 def poe_backward(mu, logvar, mod_list, g_mu, g_lv, eps: float = 1e-8):
@@ -353,11 +366,13 @@ def _bf16(x):
     return x.to(torch.bfloat16).to(x.dtype)
 
 
-def mlstm_forward_backward_bf16_operands(q, k, v, ig, fg, dh, eps: float = 1e-6):
+def mlstm_forward_backward_bf16_operands(q, k, v, ig, fg, dh, eps: float = 1e-6, den_from_rounded_p: bool = False):
     """vision_lstm.py:48-130 and its gradient with exactly the operands the sm_100a kernels feed to the
     tensor cores rounded to bf16 (q, k, v, P = S o D', h, dh/N, db, dS) and everything else exact.
     Used by the tests to separate kernel bugs (kernel != this) from the unavoidable cost of bf16
-    operands in ill-conditioned regimes (this != fp64 reference)."""
+    operands in ill-conditioned regimes (this != fp64 reference).
+    den_from_rounded_p: the warp-specialised forward (head dims >= 64) takes the normaliser input from the ones column of
+    the P [V|1] product, i.e. it sums the bf16-ROUNDED P -- consistent with the numerator -- instead of the fp32 values."""
     B, NH, S, DH = q.shape
     scale = 1.0 / math.sqrt(DH)
     q, k, v, dh = _bf16(q), _bf16(k), _bf16(v), _bf16(dh)
@@ -369,8 +384,8 @@ def mlstm_forward_backward_bf16_operands(q, k, v, ig, fg, dh, eps: float = 1e-6)
     m = logD.max(dim=-1, keepdim=True).values
     Dm = torch.exp(logD - m) * scale
     C = (q @ k.transpose(-2, -1)) * Dm
-    den = C.sum(-1, keepdim=True)
     Cb = _bf16(C)
+    den = (Cb if den_from_rounded_p else C).sum(-1, keepdim=True)
     floor = torch.exp(-m)
     N = torch.maximum(den.abs(), floor) + eps
     h = _bf16((Cb @ v) / N)

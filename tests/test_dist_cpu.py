@@ -22,15 +22,19 @@ def _worker(rank, world, port, out):
     blk = ViLBlock(32, SequenceTraversal.ROWWISE_FROM_TOP_LEFT)          # parameter container only (no CUDA compute here)
     params = list(blk.parameters())
     lo, hi = shard_range(5, rank, world)
-    # a fake per-volume gradient: volume v contributes (v+1) to every element; one tensor deliberately has no grad
+    # a fake per-volume gradient: volume v contributes (v+1) to every element.  Tensor 3 has no grad on any rank (it must
+    # stay None: the reference's Adam skips such parameters, train.py:177); tensor 5 has a grad on rank 1 only (every
+    # rank must end up with the sum)
     for i, p in enumerate(params):
-        if i == 3:
+        if i == 3 or (i == 5 and rank == 0):
             continue
         p.grad = torch.full_like(p, float(sum(v + 1 for v in range(lo, hi))))
     bucket = FlatGradBucket(params, average=False)
     flat = bucket.reduce()
     ok = bucket.numel == sum(p.numel() for p in params) == 8936
-    ok &= all(torch.all(p.grad == (0.0 if i == 3 else 15.0)).item() for i, p in enumerate(params))
+    ok &= params[3].grad is None
+    ok &= torch.all(params[5].grad == 9.0).item()                         # volumes 3, 4 live on rank 1: 4 + 5
+    ok &= all(torch.all(p.grad == 15.0).item() for i, p in enumerate(params) if i not in (3, 5))
     ok &= flat.numel() == 8936
     out[rank] = (bool(ok), (lo, hi))
     dist.destroy_process_group()

@@ -220,3 +220,65 @@ def test_vil_block_edge_lengths_forward_backward_vs_oracle(B, S, rev):
     else:
         for a, b, k in zip(got[1:], ref[1:], keys):
             assert torch.isfinite(a).all() and rel_l2(a, b) < 0.1, k
+
+
+def test_vil_block_expanded_gradient_sum_backward():
+    """Autograd hands ``y.sum().backward()`` an EXPANDED gradient (strides (0,0,0)): it must be materialised, not used as
+    the layout of dx (which would alias every element of dx to one address)."""
+    from xlstm_hved_b200 import ops
+    c = load_golden("vil_block.pt")["dim32_s200_fwd"]
+    params = _params(c["state_dict"])
+    x = c["x"].float().cuda().requires_grad_()
+    ops.vil_block(x, params, False).sum().backward()
+    x2 = c["x"].float().cuda().requires_grad_()
+    y2 = ops.vil_block(x2, params, False)
+    y2.backward(torch.ones_like(y2))
+    assert x.grad.shape == x2.grad.shape and x.grad.is_contiguous()
+    assert torch.equal(x.grad, x2.grad)
+    # an expanded INPUT view is materialised as well
+    xe = c["x"].float().cuda()[:1, :1].expand(2, 140, 32)
+    ye, _ = ops.vil_block_fwd(xe, params, False)
+    yc, _ = ops.vil_block_fwd(xe.contiguous(), params, False)
+    assert torch.equal(ye, yc)
+
+
+def test_dim16_block_at_32768_tokens_fwd_bwd_vs_oracle():
+    """BASELINE config 5 / SURVEY 8d: the reference's own 32^3 stage (DoubleConv_ViL, buildingblocks.py:509-555) sees
+    (B,16,32,32,32) = 32768 tokens of dim 16 (E = 32, DH = 8, zero-padded to 16 for the bf16 MMA K), 256 chunks.  Forward and
+    backward of the whole block through the NCDHW token view against the fp64 chunkwise oracle (the parallel form would need
+    17 GB per temporary)."""
+    import xlstm_hved_b200 as xh
+    from xlstm_hved_b200 import ops
+    torch.manual_seed(16)
+    blk = xh.ViLBlock(16, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if n.endswith(("igate.weight", "fgate.weight")):
+                p.copy_(0.3 * torch.randn_like(p))
+            elif n.endswith(("igate.bias", "fgate.bias")):
+                p.copy_(torch.randn_like(p))
+    sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    feat = torch.randn(1, 16, 32, 32, 32)
+    gy = torch.randn(1, 16, 32, 32, 32)
+    x = feat.cuda().requires_grad_()
+    params = [p.requires_grad_() for p in _params(sd)]
+    tok = x.reshape(1, 16, -1).transpose(-1, -2)
+    y = ops.vil_block(tok, params, False)
+    assert y.stride() == tok.stride()                               # NCDHW-backed token view in, NCDHW-backed out
+    grads = torch.autograd.grad(y, [x] + params, gy.cuda().reshape(1, 16, -1).transpose(-1, -2))
+    p64 = {k: v.double().requires_grad_() for k, v in sd.items()}
+    x64 = feat.double().requires_grad_()
+    tok64 = x64.reshape(1, 16, -1).transpose(-1, -2)
+    ref = restate.vil_block(tok64, p64, reverse=False, cell=lambda *a: restate.mlstm_chunkwise(*a, chunk=512))
+    keys = list(ops.VIL_PARAM_KEYS)
+    ref_grads = torch.autograd.grad(ref, [x64] + [p64[k] for k in keys], gy.double().reshape(1, 16, -1).transpose(-1, -2))
+    br, br_ref = y.detach().cpu().double() - tok64.detach(), ref.detach() - tok64.detach()
+    print("S=32768 dim16 branch rel_l2", rel_l2(br, br_ref))
+    assert rel_l2(br, br_ref) < TOL_L2
+    dbr = grads[0].cpu().double() - gy.double()
+    dbr_ref = ref_grads[0] - gy.double()
+    print("dx(branch) rel_l2", rel_l2(dbr, dbr_ref))
+    assert rel_l2(dbr, dbr_ref) < 3e-2
+    for g, rg, key in zip(grads[1:], ref_grads[1:], keys):
+        print(key, rel_l2(g, rg))
+        assert rel_l2(g, rg) < 3e-2, key

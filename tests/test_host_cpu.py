@@ -47,19 +47,96 @@ def test_patch_and_unpatch_reference_model():
     from oracle import ref_loader
     if ref_loader.find_reference() is None:
         pytest.skip("reference tree not present on this machine")
+    import io
+    import sys
+    import types
     import xlstm_hved_b200 as xh
     model = ref_loader.build_model()
-    counts = xh.patch_model(model)
-    assert counts["ViLBlock"] == 1 and counts["ProductOfExperts"] == 1 and counts["ProductOfExperts2"] == 1
-    assert "forward" in model.mViL.vil.__dict__
-    keys = set(model.state_dict().keys())
-    xh.unpatch_model(model)
-    assert "forward" not in model.mViL.vil.__dict__ and set(model.state_dict().keys()) == keys
     ns = ref_loader.load_reference()
-    assert ns.RA_HVED.reparametrize.__module__ == "RA_HVED"
+    # train.py:23 / Pretrain.py:23 bind the loss function by name at import time: the patch must reach such bindings too
+    fake_train = types.ModuleType("xhved_fake_train")
+    fake_train.compute_KLD = ns.loss.compute_KLD
+    sys.modules["xhved_fake_train"] = fake_train
+    try:
+        stock_cls = type(model.mViL.vil)
+        counts = xh.patch_model(model)
+        assert counts["ViLBlock"] == 1 and counts["ProductOfExperts"] == 1 and counts["ProductOfExperts2"] == 1
+        assert "xhved_fake_train.compute_KLD" in counts["rebound"] and "loss.compute_KLD" in counts["rebound"]
+        assert "RA_HVED.reparametrize" in counts["rebound"] and "RA_HVED.clip" in counts["rebound"]
+        assert "buildingblocks.ZeroLayerF" in counts["rebound"] and "RA_HVED.ZeroLayerF" in counts["rebound"]
+        assert fake_train.compute_KLD is xh.compute_KLD and ns.RA_HVED.ZeroLayerF is xh.modules.ZeroLayerF
+        # no instance-level state: the override lives on a subclass, so DataParallel replicas (which copy __dict__,
+        # train.py:148-151) resolve `self` to the replica
+        vil = model.mViL.vil
+        assert "forward" not in vil.__dict__ and type(vil) is not stock_cls and isinstance(vil, stock_cls)
+        replica = vil._replicate_for_data_parallel()
+        assert type(replica) is type(vil) and replica.forward.__self__ is replica
+        # train.py:370-397 pickles the whole model: a patched model must save, and load back as the stock classes
+        buf = io.BytesIO()
+        torch.save({"model": model}, buf)
+        buf.seek(0)
+        back = torch.load(buf, weights_only=False)["model"]
+        assert type(back.mViL.vil) is stock_cls and type(back.experts).__name__ == "ProductOfExperts"
+        assert not hasattr(type(back.experts), "_xhved_base")
+        keys = set(model.state_dict().keys())
+        assert set(back.state_dict().keys()) == keys
+        xh.unpatch_model(model)
+        assert type(model.mViL.vil) is stock_cls and set(model.state_dict().keys()) == keys
+        assert ns.RA_HVED.reparametrize.__module__ == "RA_HVED" and ns.RA_HVED.clip.__module__ == "RA_HVED"
+        assert fake_train.compute_KLD is ns.loss.compute_KLD and fake_train.compute_KLD.__module__ == "loss"
+        assert ns.RA_HVED.ZeroLayerF is ns.buildingblocks.ZeroLayerF and ns.RA_HVED.ZeroLayerF.__module__ == "buildingblocks"
+    finally:
+        del sys.modules["xhved_fake_train"]
     with torch.no_grad():
         seg, _ = model.eval()(torch.rand(1, 4, 32, 32, 32), [14], valid=True)   # stock path still runs
     assert seg.shape == (1, 3, 32, 32, 32)
+
+
+def test_patched_classes_without_a_reference_tree():
+    """The same mechanics on a stand-in class (the GPU box has no reference tree): class swap, replica binding, pickling
+    as the original class."""
+    import io
+    import xlstm_hved_b200 as xh
+    from xlstm_hved_b200 import patch
+
+    blk = _StandInViLBlock()
+    model = torch.nn.Sequential(blk)
+    counts = xh.patch_model(model, patch_globals=False)
+    assert counts["ViLBlock"] == 1 and type(blk) is not _StandInViLBlock and isinstance(blk, _StandInViLBlock)
+    assert xh.patch_model(model, patch_globals=False)["ViLBlock"] == 0          # idempotent
+    assert type(blk).forward is patch._vil_forward
+    rep = blk._replicate_for_data_parallel()
+    assert rep.forward.__self__ is rep
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert type(back[0]) is _StandInViLBlock
+    xh.unpatch_model(model)
+    assert type(blk) is _StandInViLBlock
+
+
+class _Cell(torch.nn.Module):
+    pass
+
+
+class _Layer(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.mlstm_cell = _Cell()
+
+
+class ViLBlock(torch.nn.Module):                    # stand-in: patch_model recognises the reference class by name + structure
+    def __init__(self):
+        super().__init__()
+        self.layer = _Layer()
+        self.w = torch.nn.Parameter(torch.zeros(3))
+
+    def forward(self, x):
+        return x
+
+
+_StandInViLBlock = ViLBlock
 
 
 def test_workspace_queries_match_the_host_layer():

@@ -113,3 +113,28 @@ def test_model_boundary_fixture_is_consistent():
     p = {k: v.double() for k, v in c["vil_state_dict"].items()}
     y = restate.vil_wrapper(c["vil"]["x"].double(), p)
     assert rel_linf(y, c["vil"]["y"]) < 1e-4     # the fixture is the reference's fp32 run
+
+
+def test_smvae_extras_general_prior_clip_zero_layer_match_reference():
+    """Round-2 fixtures: compute_KLD with a non-standard prior in slab 0 (loss.py:95-97, 113) and its gradients, clip's
+    gradient mask through the fusion (RA_HVED.py:580, 749-753), ZeroLayerF forward and backward (buildingblocks.py:308-323)."""
+    c = load_golden("smvae_extras.pt")
+    k = c["kld_prior"]
+    mu, lv = k["mu"].clone().requires_grad_(), k["logvar"].clone().requires_grad_()
+    val = restate.compute_kld(mu, lv, k["subsets"])
+    gm, gl = torch.autograd.grad(val, [mu, lv])
+    assert abs(val.item() - k["kld"].item()) < 1e-12 * abs(k["kld"].item())
+    assert rel_linf(gm, k["d_mu"]) < 1e-12 and rel_linf(gl, k["d_logvar"]) < 1e-12
+    cp = c["clip_poe"]
+    assert torch.equal(restate.clip_logvar(cp["raw_logvar"]), cp["clipped"]) and (cp["raw_logvar"].abs() > 50).sum() > 10
+    z = torch.zeros(1, *cp["mod_mu"].shape[1:], dtype=torch.float64)
+    mu5, lv5 = torch.cat([z, cp["mod_mu"]]), torch.cat([z, cp["clipped"]])
+    for idx, r in cp["cases"].items():
+        subset = restate.SUBSETS_MODALITIES[idx]
+        a, b = restate.poe(mu5, lv5, subset)
+        assert rel_linf(a, r["pd_mu"]) < 1e-13 and rel_linf(b, r["pd_logvar"]) < 1e-13
+        dmu, dlv = restate.poe_backward(mu5, lv5, subset, r["g_mu"], r["g_logvar"])
+        dlv = dlv * (cp["raw_logvar"].abs() <= 50)
+        assert rel_linf(dmu, r["d_mod_mu"]) < 1e-12 and rel_linf(dlv, r["d_raw_logvar"]) < 1e-12
+    zl = c["zero_layer"]
+    assert torch.equal(restate.zero_rows(zl["x"], zl["alpha"]), zl["y"]) and torch.equal(restate.zero_rows(zl["gy"], zl["alpha"]), zl["dx"])

@@ -48,6 +48,10 @@ class PoeLevelGrad(Structure):        # xhved_poe_level_grad
                 ("kld_scale", POINTER(c_float)), ("d_mu", c_void_p), ("d_logvar", c_void_p)]
 
 
+class PoeOpts(Structure):             # xhved_poe_opts
+    _fields_ = [("eps", c_float), ("flags", c_int), ("clip_lo", c_float), ("clip_hi", c_float)]
+
+
 class MlstmWorkspace(Structure):      # xhved_mlstm_workspace
     _fields_ = [("nc", c_int), ("dhp", c_int), ("tile_bytes", c_int64), ("row_bytes", c_int64), ("dstate_bytes", c_int64),
                 ("chunk_bytes", c_int64), ("states_bytes", c_int64), ("grad_bytes", c_int64)]
@@ -66,6 +70,11 @@ SYMBOLS = {
                       c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int, c_void_p],
     "xhved_poe_fwd_levels": [POINTER(PoeLevel), c_int, POINTER(c_uint32), c_int, c_float, c_int, c_void_p],
     "xhved_poe_bwd_levels": [POINTER(PoeLevelGrad), c_int, POINTER(c_uint32), c_int, c_float, c_int, c_void_p],
+    "xhved_poe_fwd_levels_opts": [POINTER(PoeLevel), c_int, POINTER(c_uint32), c_int, POINTER(PoeOpts), c_void_p],
+    "xhved_poe_bwd_levels_opts": [POINTER(PoeLevelGrad), c_int, POINTER(c_uint32), c_int, POINTER(PoeOpts), c_void_p],
+    "xhved_clip_fwd": [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p],
+    "xhved_clip_bwd": [c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p],
+    "xhved_zero_rows": [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
     "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,
@@ -135,3 +144,19 @@ def ptr(t):
 
 def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device(fn):
+    """Run an autograd.Function forward / backward with the CUDA device of its first CUDA tensor argument current.
+    The kernels launch on the calling thread's current device and stream; under nn.DataParallel (train.py:148-151) every
+    replica runs in its own thread, and autograd's backward threads do not inherit a ``torch.cuda.device`` context."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped

@@ -415,6 +415,20 @@ __global__ void mlstm_unpack_kernel(const unsigned char* __restrict__ tiles, int
 // ------------------------------------------------------------------ host launchers
 int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
                       float* m_prev, cudaStream_t st);
+int launch_chunk_out_ws(int dhp, const void* q, const void* k, const void* v, const float* ig, const float* fg, const void* states,
+                        const float* m_prev, int BH, int nc, float scale, float eps, void* h, float* m, float* den,
+                        cudaStream_t st);
+
+// Which chunk_out kernel runs: the persistent warp-specialised one with P kept in tensor memory (mlstm_fwd_ws.cu) where it
+// is the faster of the two on B200 (measured, profiles/r02_cell_scaling.jsonl: dhp >= 64), the one-tile-per-CTA kernel
+// above for the narrow heads.  XHVED_CELL_WS=0 / 1 forces one of them for A/B measurements.  Read once.
+bool cell_ws_enabled(int dhp) {
+  static const int mode = [] {
+    const char* e = getenv("XHVED_CELL_WS");
+    return !e ? -1 : (e[0] == '0' ? 0 : 1);
+  }();
+  return mode < 0 ? dhp >= 64 : mode != 0;
+}
 
 template <int DHP>
 static int launch_fwd(const void* q, const void* k, const void* v, const float* ig, const float* fg, int BH, int nc, int dh,
@@ -436,6 +450,7 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
   // phase 2
   if (int rc = launch_state_scan(DHP, ws_dstate, ws_g, ws_amax, BH, nc, 0, states, m_prev, st)) return rc;
   // phase 3
+  if (cell_ws_enabled(DHP)) return launch_chunk_out_ws(DHP, q, k, v, ig, fg, states, m_prev, BH, nc, scale, eps, h, m, den, st);
   {
     const size_t smem = 3 * kL * DHP * 2 + kL * kL * 2 + 2 * DHP * NE * 2 + kL * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_out_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

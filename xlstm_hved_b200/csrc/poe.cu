@@ -19,7 +19,12 @@ struct PoeSubsets {
   float kld_scale[15];
   int n;
   uint32_t used;  // union of masks: which modality slabs must be loaded
+  // fused clip (RA_HVED.py:580, 749-753): the logvar slabs of the four modality experts are clamped to [clip_lo, clip_hi]
+  // as they are loaded; the backward zeroes their gradient outside the interval (what torch.clamp's autograd does)
+  int clip;
+  float clip_lo, clip_hi;
 };
+constexpr float kKlEps = 1e-8f;   // KL_divergence's own eps (loss.py:29), independent of the fusion's
 
 // One latent level of a launch.  A launch covers up to four levels (the four latent resolutions of a volume): the small
 // levels are latency-bound on their own, so they ride along with the big one.  blk_end[l] = first block of level l+1.
@@ -154,6 +159,12 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, con
         ld<V>(lv + e * stride + i, Lv[e]);
       }
     }
+    if (ss.clip) {
+#pragma unroll
+      for (int e = 1; e < 5; ++e)
+#pragma unroll
+        for (int j = 0; j < V; ++j) Lv[e][j] = fminf(fmaxf(Lv[e][j], ss.clip_lo), ss.clip_hi);
+    }
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
       const bool on = (live >> e) & 1u;
@@ -192,8 +203,16 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, con
           st<V>(out_z + s * n + i, z);
         }
         if (kld_out) {
+          // KL_divergence(sub_mu, sub_logvar, mu_prior, logvar_prior) (loss.py:29-40, 113): the prior is slab 0
 #pragma unroll
-          for (int j = 0; j < V; ++j) kld_acc[s] += -1.0f - ol[j] + (var[j] + om[j] * om[j]);   // / (1 + 1e-8) == 1 in fp32
+          for (int j = 0; j < V; ++j) {
+            if (SP) {
+              kld_acc[s] += -1.0f - ol[j] + (var[j] + om[j] * om[j]);   // / (1 + 1e-8) == 1 in fp32
+            } else {
+              const float dm = om[j] - M[0][j];
+              kld_acc[s] += -1.0f + Lv[0][j] - ol[j] + (var[j] + dm * dm) * __frcp_rn(__expf(Lv[0][j]) + kKlEps);
+            }
+          }
         }
       }
     }
@@ -238,6 +257,8 @@ __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, 
        iv += static_cast<int64_t>(nblk) * blockDim.x) {
     const int64_t i = iv * V;
     float T[5][V], M[5][V], EL[5][V], dM[5][V], dT[5][V];
+    float dL0[V];                 // direct KL gradient w.r.t. the prior logvar (general prior only)
+    uint32_t pass = 0xFFFFFFFFu;  // bit e*4+j: gradient of logvar[e][j] passes the fused clip
     uint32_t dropbits = 0;
     if (drop) {
       const uint8_t* d = drop + (i / per_sample) * 4;
@@ -254,6 +275,17 @@ __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, 
         ld<V>(lv + e * stride + i, EL[e]);
       }
     }
+    if (ss.clip) {
+#pragma unroll
+      for (int e = 1; e < 5; ++e)
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          if (EL[e][j] < ss.clip_lo || EL[e][j] > ss.clip_hi) pass &= ~(1u << (e * 4 + j));
+          EL[e][j] = fminf(fmaxf(EL[e][j], ss.clip_lo), ss.clip_hi);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) dL0[j] = 0.f;
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
       const bool dropped = (e > 0) && ((dropbits >> (e - 1)) & 1u);
@@ -304,8 +336,19 @@ __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, 
           }
           if (use_kld) {
             const float ks = L.kld_scale[s];
-            a += ks * 2.0f * mh;                       // / (1 + 1e-8) == 1 in fp32
-            b += ks * (-1.0f + rS);
+            if (SP) {
+              a += ks * 2.0f * mh;                       // / (1 + 1e-8) == 1 in fp32
+              b += ks * (-1.0f + rS);
+            } else {
+              // d/d(mu^, logvar^) of -1 + lv0 - lv^ + (exp(lv^) + (mu^ - mu0)^2) / (exp(lv0) + 1e-8), and the direct
+              // terms w.r.t. the prior slab itself (on top of its gradient as expert 0 of the fusion)
+              const float rv2 = __frcp_rn(EL[0][j] + kKlEps);   // exactly 1 for the standard prior
+              const float dm = mh - M[0][j];
+              a += ks * 2.0f * dm * rv2;
+              b += ks * (-1.0f + rS * rv2);
+              dM[0][j] -= ks * 2.0f * dm * rv2;
+              dL0[j] += ks * (1.0f - (rS + dm * dm) * EL[0][j] * rv2 * rv2);
+            }
           }
 #pragma unroll
           for (int e = 0; e < 5; ++e)
@@ -321,7 +364,11 @@ __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, 
       if (e == 0 && SP) continue;
       float dl[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) dl[j] = -dT[e][j] * T[e][j] * T[e][j] * EL[e][j];
+      for (int j = 0; j < V; ++j) {
+        dl[j] = -dT[e][j] * T[e][j] * T[e][j] * EL[e][j];
+        if (e == 0) dl[j] += dL0[j];
+        else if (!((pass >> (e * 4 + j)) & 1u)) dl[j] = 0.f;
+      }
       st<V, true>(d_mu + e * stride + i, dM[e]);
       st<V, true>(d_lv + e * stride + i, dl);
     }
@@ -376,8 +423,12 @@ static int grid_for(int64_t nvec) {
   return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
-static int fill_subsets(PoeSubsets& ss, const uint32_t* masks, int n_subsets) {
+static int fill_subsets(PoeSubsets& ss, const uint32_t* masks, int n_subsets, const xhved_poe_opts* o) {
   if (n_subsets < 1 || n_subsets > 15 || !masks) return XHVED_ERR_BAD_ARG;
+  ss.clip = (o && (o->flags & XHVED_POE_CLIP)) ? 1 : 0;
+  ss.clip_lo = o ? o->clip_lo : 0.f;
+  ss.clip_hi = o ? o->clip_hi : 0.f;
+  if (ss.clip && !(ss.clip_lo <= ss.clip_hi)) return XHVED_ERR_BAD_ARG;
   ss.n = n_subsets;
   ss.used = 0;
   for (int s = 0; s < 15; ++s) {
@@ -432,9 +483,10 @@ static void launch_bwd(PoeBwdArgs& a, const PoeSubsets& ss, float eps, bool sp, 
   else poe_bwd_kernel<V, NS, false><<<grid, 256, 0, st>>>(a, ss, eps);
 }
 
-static int run_fwd(PoeFwdArgs& a, const uint32_t* subset_masks, int n_subsets, float eps, int flags, cudaStream_t st) {
+static int run_fwd(PoeFwdArgs& a, const uint32_t* subset_masks, int n_subsets, float eps, int flags, cudaStream_t st,
+                   const xhved_poe_opts* opts = nullptr) {
   PoeSubsets ss;
-  if (int rc = fill_subsets(ss, subset_masks, n_subsets)) return rc;
+  if (int rc = fill_subsets(ss, subset_masks, n_subsets, opts)) return rc;
   bool v4 = true;
   for (int l = 0; l < a.nlev; ++l) {
     const PoeLevelF& L = a.lev[l];
@@ -456,9 +508,10 @@ static int run_fwd(PoeFwdArgs& a, const uint32_t* subset_masks, int n_subsets, f
   return (int)cudaGetLastError();
 }
 
-static int run_bwd(PoeBwdArgs& a, const uint32_t* subset_masks, int n_subsets, float eps, int flags, cudaStream_t st) {
+static int run_bwd(PoeBwdArgs& a, const uint32_t* subset_masks, int n_subsets, float eps, int flags, cudaStream_t st,
+                   const xhved_poe_opts* opts = nullptr) {
   PoeSubsets ss;
-  if (int rc = fill_subsets(ss, subset_masks, n_subsets)) return rc;
+  if (int rc = fill_subsets(ss, subset_masks, n_subsets, opts)) return rc;
   bool v4 = true;
   for (int l = 0; l < a.nlev; ++l) {
     const PoeLevelB& L = a.lev[l];
@@ -536,6 +589,109 @@ extern "C" int xhved_poe_bwd_levels(const xhved_poe_level_grad* levels, int n_le
     for (int k = 0; k < n_subsets; ++k) L.kld_scale[k] = s.kld_scale ? s.kld_scale[k] : 0.f;
   }
   return run_bwd(a, subset_masks, n_subsets, eps, flags, static_cast<cudaStream_t>(stream));
+}
+
+static void fill_fwd_levels(PoeFwdArgs& a, const xhved_poe_level* levels, int n_levels) {
+  a.nlev = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    const xhved_poe_level& s = levels[l];
+    a.lev[l] = PoeLevelF{s.mu, s.logvar, s.n, s.expert_stride, s.drop, s.per_sample, s.out_mu, s.out_logvar, s.noise, s.out_z, s.kld_out};
+  }
+}
+static void fill_bwd_levels(PoeBwdArgs& a, const xhved_poe_level_grad* levels, int n_levels, int n_subsets) {
+  a.nlev = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    const xhved_poe_level_grad& s = levels[l];
+    PoeLevelB& L = a.lev[l];
+    L.mu = s.mu, L.lv = s.logvar, L.n = s.n, L.stride = s.expert_stride, L.drop = s.drop, L.per_sample = s.per_sample;
+    L.g_mu = s.g_mu, L.g_lv = s.g_logvar, L.noise = s.noise, L.g_z = s.g_z, L.d_mu = s.d_mu, L.d_lv = s.d_logvar;
+    L.use_kld = s.kld_scale != nullptr;
+    for (int k = 0; k < n_subsets; ++k) L.kld_scale[k] = s.kld_scale ? s.kld_scale[k] : 0.f;
+  }
+}
+
+extern "C" int xhved_poe_fwd_levels_opts(const xhved_poe_level* levels, int n_levels, const uint32_t* subset_masks, int n_subsets,
+                                         const xhved_poe_opts* opts, void* stream) {
+  if (!levels || !opts || n_levels < 1 || n_levels > XHVED_POE_MAX_LEVELS) return XHVED_ERR_BAD_ARG;
+  PoeFwdArgs a = {};
+  fill_fwd_levels(a, levels, n_levels);
+  return run_fwd(a, subset_masks, n_subsets, opts->eps, opts->flags, static_cast<cudaStream_t>(stream), opts);
+}
+extern "C" int xhved_poe_bwd_levels_opts(const xhved_poe_level_grad* levels, int n_levels, const uint32_t* subset_masks, int n_subsets,
+                                         const xhved_poe_opts* opts, void* stream) {
+  if (!levels || !opts || n_levels < 1 || n_levels > XHVED_POE_MAX_LEVELS || n_subsets < 1 || n_subsets > 15) return XHVED_ERR_BAD_ARG;
+  PoeBwdArgs a = {};
+  fill_bwd_levels(a, levels, n_levels, n_subsets);
+  return run_bwd(a, subset_masks, n_subsets, opts->eps, opts->flags, static_cast<cudaStream_t>(stream), opts);
+}
+
+// ---------------------------------------------------------------- stand-alone clip and ZeroLayerF
+template <int V>
+__global__ void __launch_bounds__(256) clip_fwd_kernel(const float* __restrict__ x, int64_t n, float lo, float hi, float* __restrict__ y) {
+  const int64_t nvec = n / V;
+  for (int64_t iv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
+       iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[V];
+    ld<V>(x + iv * V, a);
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] = (a[j] != a[j]) ? a[j] : fminf(fmaxf(a[j], lo), hi);   // NaN passes, like torch.clamp
+    st<V>(y + iv * V, a);
+  }
+}
+template <int V>
+__global__ void __launch_bounds__(256) clip_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, int64_t n, float lo,
+                                                        float hi, float* __restrict__ dx) {
+  const int64_t nvec = n / V;
+  for (int64_t iv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
+       iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[V], b[V];
+    ld<V>(x + iv * V, a);
+    ld<V>(g + iv * V, b);
+#pragma unroll
+    for (int j = 0; j < V; ++j) b[j] = (a[j] < lo || a[j] > hi) ? 0.f : b[j];
+    st<V>(dx + iv * V, b);
+  }
+}
+// y[b, :] = mask[b] ? 0 : x[b, :]   (ZeroLayerF forward AND backward, buildingblocks.py:308-323)
+template <int V>
+__global__ void __launch_bounds__(256) zero_rows_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t n,
+                                                         int64_t per_row, float* __restrict__ y) {
+  const int64_t nvec = n / V;
+  for (int64_t iv = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; iv < nvec;
+       iv += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[V];
+    const bool dead = mask[(iv * V) / per_row] != 0;
+    if (!dead) {
+      ld<V>(x + iv * V, a);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) a[j] = 0.f;
+    }
+    st<V>(y + iv * V, a);
+  }
+}
+
+extern "C" int xhved_clip_fwd(const float* x, int64_t n, float lo, float hi, float* y, void* stream) {
+  if (n <= 0 || !x || !y || !(lo <= hi)) return XHVED_ERR_BAD_ARG;
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  if (n % 4 == 0 && aligned16(x) && aligned16(y)) clip_fwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(x, n, lo, hi, y);
+  else clip_fwd_kernel<1><<<grid_for(n), 256, 0, st_>>>(x, n, lo, hi, y);
+  return (int)cudaGetLastError();
+}
+extern "C" int xhved_clip_bwd(const float* x, const float* g, int64_t n, float lo, float hi, float* dx, void* stream) {
+  if (n <= 0 || !x || !g || !dx || !(lo <= hi)) return XHVED_ERR_BAD_ARG;
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  if (n % 4 == 0 && aligned16(x) && aligned16(g) && aligned16(dx)) clip_bwd_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(x, g, n, lo, hi, dx);
+  else clip_bwd_kernel<1><<<grid_for(n), 256, 0, st_>>>(x, g, n, lo, hi, dx);
+  return (int)cudaGetLastError();
+}
+extern "C" int xhved_zero_rows(const float* x, const uint8_t* mask, int64_t rows, int64_t per_row, float* y, void* stream) {
+  if (rows <= 0 || per_row <= 0 || !x || !mask || !y) return XHVED_ERR_BAD_ARG;
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  const int64_t n = rows * per_row;
+  if (per_row % 4 == 0 && aligned16(x) && aligned16(y)) zero_rows_kernel<4><<<grid_for(n / 4), 256, 0, st_>>>(x, mask, n, per_row, y);
+  else zero_rows_kernel<1><<<grid_for(n), 256, 0, st_>>>(x, mask, n, per_row, y);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream) {

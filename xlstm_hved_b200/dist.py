@@ -17,32 +17,45 @@ def shard_range(n_items: int, rank: int, world: int):
 
 class FlatGradBucket:
     """Sum (or average) the gradients of ``params`` across ranks with a single collective on one contiguous buffer.
-    Parameters without a gradient contribute zeros (the reference model leaves ~50 tensors without one)."""
+
+    The reference model leaves ~50 parameter tensors without a gradient, and its optimizer (Adam with weight decay,
+    train.py:177) skips parameters whose ``grad`` is None.  To keep that behaviour the bucket carries one has-gradient flag
+    per parameter behind the gradient data (same buffer, same collective): a parameter that received a gradient on no rank
+    keeps ``grad = None``; one that received a gradient on some ranks gets the reduced value everywhere."""
 
     def __init__(self, params, average: bool = True):
         self.params = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
         p0 = self.params[0]
-        self.flat = torch.zeros(self.numel, device=p0.device, dtype=torch.float32)
+        self.flat = torch.zeros(self.numel + len(self.params), device=p0.device, dtype=torch.float32)
+        self.grads = self.flat[:self.numel]
+        self.flags = self.flat[self.numel:]
         self.average = average
         self.views, off = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            self.views.append(self.grads[off:off + p.numel()].view_as(p))
             off += p.numel()
 
     def reduce(self, group=None):
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-            else:
+        """Gather p.grad into the bucket, all-reduce it, write the result back into p.grad.  Returns the gradient part."""
+        has = [p.grad is not None for p in self.params]
+        self.flags.copy_(torch.tensor(has, dtype=torch.float32), non_blocking=True)
+        for p, v, h in zip(self.params, self.views, has):
+            if h:
                 v.copy_(p.grad)
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            else:
+                v.zero_()
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
             dist.all_reduce(self.flat, group=group)
             if self.average:
-                self.flat.div_(dist.get_world_size(group))
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
+                self.grads.div_(world)
+            anyone = (self.flags > 0).tolist() if not all(has) else has       # one small D2H only when some grad is missing
+        else:
+            anyone = has
+        for p, v, h, a in zip(self.params, self.views, has, anyone):
+            if h:
                 p.grad.copy_(v)
-        return self.flat
+            elif a:
+                p.grad = v.clone()
+        return self.grads

@@ -272,6 +272,7 @@ class ViLLayer3D(nn.Module):
 # --------------------------------------------------------------------------------------------- S-MVAE
 class _PoEFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, mu5, logvar5, subset, drop, eps):
         pm, pl, _, _ = ops.poe_fwd(mu5, logvar5, [subset], drop=drop, eps=eps)
         ctx.save_for_backward(mu5, logvar5)
@@ -279,6 +280,7 @@ class _PoEFunction(torch.autograd.Function):
         return pm[0], pl[0]
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, g_mu, g_lv):
         mu5, logvar5 = ctx.saved_tensors
         d_mu, d_lv = ops.poe_bwd(mu5, logvar5, [ctx.subset], g_mu=g_mu.contiguous()[None], g_logvar=g_lv.contiguous()[None],
@@ -325,11 +327,13 @@ class ProductOfExperts2(nn.Module):
 
 class _ReparamFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, mu, logvar, noise):
         ctx.save_for_backward(logvar, noise)
         return ops.reparam_fwd(mu, logvar, noise)
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, g):
         logvar, noise = ctx.saved_tensors
         d_mu, d_lv = ops.reparam_bwd(logvar, noise, g.contiguous())
@@ -345,13 +349,52 @@ def reparametrize(mu, logvar, valid=False):
     return _ReparamFunction.apply(mu.float().contiguous(), logvar.float().contiguous(), noise)
 
 
+class _ClipFunction(torch.autograd.Function):
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, lo, hi):
+        ctx.save_for_backward(x)
+        ctx.lo, ctx.hi = lo, hi
+        return ops.clip_fwd(x, lo, hi)
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.clip_bwd(x, g, ctx.lo, ctx.hi), None, None
+
+
 def clip(input):
-    """RA_HVED.py:749-753 (stays a plain clamp: it is applied while the experts are concatenated)."""
-    return torch.clamp(input, min=-50.0, max=50.0)
+    """RA_HVED.py:749-753: clamp(input, -50, 50), applied to every modality's logvar while the experts are concatenated
+    (RA_HVED.py:580).  Stand-alone kernel with torch.clamp's gradient mask; ``ops.poe_fwd_levels(..., clip=(-50, 50))``
+    is the fused form (the clamp happens as the PoE kernel loads the slabs)."""
+    _require_device(input)
+    out = _ClipFunction.apply(input.float().contiguous(), -50.0, 50.0)
+    return out.to(input.dtype)
+
+
+class ZeroLayerF(torch.autograd.Function):
+    """buildingblocks.py:308-323 (call sites RA_HVED.py:559, U_Hemis.py:42, buildingblocks.py:879-881):
+    ``ZeroLayerF.apply(x, alpha)`` returns a copy of x with the rows selected by the (B,) boolean ``alpha`` zeroed; the
+    backward zeroes the same rows of the gradient."""
+
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, alpha):
+        _require_device(x)
+        ctx.alpha = alpha
+        ctx.dtype = x.dtype
+        return ops.zero_rows(x, alpha).to(x.dtype)
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, grad_output):
+        return ops.zero_rows(grad_output, ctx.alpha).to(ctx.dtype), None
 
 
 class _KLDFunction(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, mu5, logvar5, subsets):
         _, _, _, kld = ops.poe_fwd(mu5, logvar5, subsets, want_kld=True)
         n = mu5[0].numel()
@@ -360,6 +403,7 @@ class _KLDFunction(torch.autograd.Function):
         return kld.sum() * ctx.scale
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, g):
         mu5, logvar5 = ctx.saved_tensors
         d_mu, d_lv = ops.poe_bwd(mu5, logvar5, ctx.subsets, kld_scale=[ctx.scale] * len(ctx.subsets))

@@ -118,10 +118,25 @@ def _dp(t):
     return t.data_ptr() if t is not None else None
 
 
-def poe_fwd_levels(levels, subsets, noises=None, kld_out=None, eps: float = 1e-8, standard_prior: bool = False):
+POE_CLIP = 2                  # include/xhved.h: XHVED_POE_CLIP
+
+
+def _poe_opts(eps, standard_prior, clip):
+    """xhved_poe_opts: clip = None or (lo, hi) -- the model's clamp of the modality logvars (RA_HVED.py:580, 749-753) fused
+    into the launch (the slabs then hold RAW logvars; the backward zeroes d_logvar outside the interval)."""
+    o = _lib.PoeOpts()
+    o.eps = eps
+    o.flags = (POE_STANDARD_PRIOR if standard_prior else 0) | (POE_CLIP if clip is not None else 0)
+    o.clip_lo, o.clip_hi = (float(clip[0]), float(clip[1])) if clip is not None else (0.0, 0.0)
+    return o
+
+
+def poe_fwd_levels(levels, subsets, noises=None, kld_out=None, eps: float = 1e-8, standard_prior: bool = False, clip=None,
+                   drops=None):
     """poe_fwd for several latent levels in ONE launch (the four latent resolutions of a volume; the small ones are
     latency-bound on their own).  levels: list of (mu5, logvar5) with shape (5, ...) each; noises: optional list of
-    (len(subsets), ...) tensors; kld_out: optional pre-zeroed fp32 (n_levels, len(subsets)) buffer.
+    (len(subsets), ...) tensors; kld_out: optional pre-zeroed fp32 (n_levels, len(subsets)) buffer; clip: None or
+    (lo, hi), see _poe_opts; drops: optional per-level (B, 4) uint8 missing flags (ProductOfExperts2).
     Returns a list of (pd_mu, pd_logvar, z or None) per level."""
     lib = _lib.load_library()
     ns, nl = len(subsets), len(levels)
@@ -140,19 +155,24 @@ def poe_fwd_levels(levels, subsets, noises=None, kld_out=None, eps: float = 1e-8
         kl = kld_out[l] if kld_out is not None else None
         if kl is not None:
             assert kl.dtype == torch.float32 and kl.is_contiguous() and kl.numel() == ns
+        drop = drops[l].to(device=mu5.device, dtype=torch.uint8).contiguous() if drops is not None and drops[l] is not None else None
         e = arr[l]
-        e.mu, e.logvar, e.n, e.expert_stride, e.drop, e.per_sample = mu5.data_ptr(), lv5.data_ptr(), n, n, None, 0
+        e.mu, e.logvar, e.n, e.expert_stride = mu5.data_ptr(), lv5.data_ptr(), n, n
+        e.drop, e.per_sample = _dp(drop), (n // drop.shape[0] if drop is not None else 0)
         e.out_mu, e.out_logvar, e.noise, e.out_z, e.kld_out = out_mu.data_ptr(), out_lv.data_ptr(), _dp(noise), _dp(z), _dp(kl)
-        keep.append((mu5, lv5, noise))
+        keep.append((mu5, lv5, noise, drop))
         outs.append((out_mu, out_lv, z))
-    check(lib.xhved_poe_fwd_levels(arr, nl, _masks(subsets), ns, eps, POE_STANDARD_PRIOR if standard_prior else 0, stream()),
-          "xhved_poe_fwd_levels")
+    opts = _poe_opts(eps, standard_prior, clip)
+    check(lib.xhved_poe_fwd_levels_opts(arr, nl, _masks(subsets), ns, ctypes.byref(opts), stream()), "xhved_poe_fwd_levels_opts")
     return outs
 
 
-def poe_bwd_levels(levels, subsets, noises=None, g_zs=None, kld_scales=None, eps: float = 1e-8, standard_prior: bool = False):
-    """Backward of poe_fwd_levels through z and the KL term, one launch.  kld_scales: per level a list of len(subsets) floats.
-    Returns a list of (d_mu, d_logvar) per level ((4, ...) modality slabs with standard_prior, else (5, ...))."""
+def poe_bwd_levels(levels, subsets, noises=None, g_zs=None, kld_scales=None, eps: float = 1e-8, standard_prior: bool = False,
+                   clip=None, g_mus=None, g_logvars=None, drops=None):
+    """Backward of poe_fwd_levels through z, the KL term and (optionally) the fused outputs themselves, one launch.
+    kld_scales: per level a list of len(subsets) floats; g_mus / g_logvars: optional per-level (len(subsets), ...) upstream
+    gradients of pd_mu / pd_logvar.  Returns a list of (d_mu, d_logvar) per level ((4, ...) modality slabs with
+    standard_prior, else (5, ...))."""
     lib = _lib.load_library()
     ns, nl = len(subsets), len(levels)
     arr = (_lib.PoeLevelGrad * nl)()
@@ -164,17 +184,54 @@ def poe_bwd_levels(levels, subsets, noises=None, g_zs=None, kld_scales=None, eps
         noise = _f32c(noises[l]) if noises is not None else None
         g_z = _f32c(g_zs[l]) if g_zs is not None else None
         ks = (c_float * ns)(*[float(v) for v in kld_scales[l]]) if kld_scales is not None else None
+        g_mu = _f32c(g_mus[l]) if g_mus is not None and g_mus[l] is not None else None
+        g_lv = _f32c(g_logvars[l]) if g_logvars is not None and g_logvars[l] is not None else None
+        drop = drops[l].to(device=mu5.device, dtype=torch.uint8).contiguous() if drops is not None and drops[l] is not None else None
         e = arr[l]
-        e.mu, e.logvar, e.n, e.expert_stride, e.drop, e.per_sample = mu5.data_ptr(), lv5.data_ptr(), n, n, None, 0
-        e.g_mu, e.g_logvar, e.noise, e.g_z = None, None, _dp(noise), _dp(g_z)
+        e.mu, e.logvar, e.n, e.expert_stride = mu5.data_ptr(), lv5.data_ptr(), n, n
+        e.drop, e.per_sample = _dp(drop), (n // drop.shape[0] if drop is not None else 0)
+        e.g_mu, e.g_logvar, e.noise, e.g_z = _dp(g_mu), _dp(g_lv), _dp(noise), _dp(g_z)
         if ks is not None:
             e.kld_scale = ks
         e.d_mu, e.d_logvar = d_mu.data_ptr(), d_lv.data_ptr()
-        keep.append((mu5, lv5, noise, g_z, ks))
+        keep.append((mu5, lv5, noise, g_z, ks, g_mu, g_lv, drop))
         outs.append((d_mu[1:], d_lv[1:]) if standard_prior else (d_mu, d_lv))
-    check(lib.xhved_poe_bwd_levels(arr, nl, _masks(subsets), ns, eps, POE_STANDARD_PRIOR if standard_prior else 0, stream()),
-          "xhved_poe_bwd_levels")
+    opts = _poe_opts(eps, standard_prior, clip)
+    check(lib.xhved_poe_bwd_levels_opts(arr, nl, _masks(subsets), ns, ctypes.byref(opts), stream()), "xhved_poe_bwd_levels_opts")
     return outs
+
+
+def clip_fwd(x, lo: float = -50.0, hi: float = 50.0):
+    """clip (RA_HVED.py:749-753): clamp(x, lo, hi) on the device."""
+    lib = _lib.load_library()
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    if x.numel():
+        check(lib.xhved_clip_fwd(ptr(x), x.numel(), lo, hi, ptr(y), stream()), "xhved_clip_fwd")
+    return y
+
+
+def clip_bwd(x, g, lo: float = -50.0, hi: float = 50.0):
+    lib = _lib.load_library()
+    x, g = _f32c(x), _f32c(g)
+    dx = torch.empty_like(x)
+    if x.numel():
+        check(lib.xhved_clip_bwd(ptr(x), ptr(g), x.numel(), lo, hi, ptr(dx), stream()), "xhved_clip_bwd")
+    return dx
+
+
+def zero_rows(x, mask):
+    """ZeroLayerF (buildingblocks.py:308-323): a copy of x whose rows x[b] with mask[b] set are zero.  The reference's
+    backward is the same map applied to the gradient."""
+    lib = _lib.load_library()
+    x = _f32c(x)
+    mask = mask.to(device=x.device, dtype=torch.uint8).contiguous()
+    if mask.dim() != 1 or mask.shape[0] != x.shape[0]:
+        raise ValueError("zero_rows: mask must be a (B,) boolean vector over the leading dimension of x")
+    y = torch.empty_like(x)
+    if x.numel():
+        check(lib.xhved_zero_rows(ptr(x), ptr(mask), x.shape[0], x.numel() // x.shape[0], ptr(y), stream()), "xhved_zero_rows")
+    return y
 
 
 def reparam_fwd(mu, logvar, noise):
@@ -304,6 +361,7 @@ class MLSTMCellFunction(torch.autograd.Function):
     """parallel_stabilized_simple (vision_lstm.py:48-130) on the chunkwise tcgen05 kernels."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, q, k, v, ig, fg, eps):
         B, NH, S, DH = q.shape
         buf = mlstm_pack_inputs(q, k, v, ig, fg)
@@ -312,6 +370,7 @@ class MLSTMCellFunction(torch.autograd.Function):
         return mlstm_unpack_h(buf, B, NH)
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dh):
         lib = _lib.load_library()
         buf = ctx.buf
@@ -361,6 +420,21 @@ def _token_strides(x_tok: torch.Tensor):
     return x_tok.stride(0), x_tok.stride(1), x_tok.stride(2)
 
 
+def _dense_view(t: torch.Tensor) -> torch.Tensor:
+    """The kernels address (B,S,C) views through their strides and allocate outputs with the same strides, which is only
+    sound when distinct indices map to distinct addresses.  Autograd hands over EXPANDED gradients (``y.sum().backward()``
+    arrives with strides (0,0,0)) and callers may pass overlapping views: those are materialised here; non-overlapping views
+    of any memory format (e.g. the transpose of an NCDHW feature, slices) pass through untouched."""
+    if t.numel() <= 1 or t.is_contiguous():
+        return t
+    extent = 1                                       # elements spanned by the dimensions with smaller strides
+    for st, sz in sorted((st, sz) for sz, st in zip(t.shape, t.stride()) if sz > 1):
+        if st < extent:                              # stride 0 (expanded) or overlapping windows
+            return t.contiguous()
+        extent = st * (sz - 1) + extent
+    return t
+
+
 class VilWorkspace:
     """Per-call device buffers of the fused ViL block."""
 
@@ -385,6 +459,7 @@ def _shape_struct(x_tok, y_tok, reverse):
 def vil_block_fwd(x_tok: torch.Tensor, params, reverse: bool, eps: float = 1e-6):
     """x_tok: (B,S,C) fp32 view; params: the 14 tensors in VIL_PARAM_KEYS order.  Returns (y_tok, workspace)."""
     lib = _lib.load_library()
+    x_tok = _dense_view(x_tok)
     B, S, C = x_tok.shape
     ws = VilWorkspace(B, S, C, x_tok.device)
     # output takes the memory format of the input (NCDHW-backed token view stays NCDHW-backed)
@@ -407,6 +482,7 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float =
     dev = x_tok.device
     if dy_tok.dtype != torch.float32:
         dy_tok = dy_tok.float()
+    dy_tok = _dense_view(dy_tok)
     # parameter gradients are accumulated with global atomics into GRAD_REPLICAS zero-filled copies (CTA i -> copy i % R)
     # to spread the traffic over L2 slices; xhved_reduce_replicas sums the copies at the end
     sizes = _lib.VilWorkspaceSizes()
@@ -448,14 +524,17 @@ class VilBlockFunction(torch.autograd.Function):
     """ViLBlock.forward (vision_lstm.py:494-502) as three fused launches + the chunkwise cell, with backward."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x_tok, reverse, eps, *params):
         params = [p.detach() if p.dtype == torch.float32 and p.is_contiguous() else p.detach().float().contiguous() for p in params]
+        x_tok = _dense_view(x_tok)
         y, ws = vil_block_fwd(x_tok, params, reverse, eps)
         ctx.reverse, ctx.eps, ctx.ws = reverse, eps, ws
         ctx.save_for_backward(x_tok, *params)
         return y
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, dy):
         x_tok, *params = ctx.saved_tensors
         dx, grads = vil_block_bwd(x_tok, dy, params, ctx.reverse, ctx.ws, ctx.eps)

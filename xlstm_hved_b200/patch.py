@@ -1,71 +1,115 @@
 """Drop-in patching of a live reference model (Quanato607/XLSTM-HVED) onto the sm_100a kernels.
 
-``patch_model(model)`` rebinds ``forward`` of every reference ``ViLBlock`` and ``ProductOfExperts(2)`` instance
-found in ``model`` and, when the reference's ``RA_HVED`` / ``loss`` modules are importable, the module-level
-``reparametrize`` and ``compute_KLD`` they look up at call time (RA_HVED.py:597, train.py:236-239).  Classes,
-parameters and state_dict keys are untouched (checkpoints pickle the whole module, train.py:374), so
-``unpatch_model`` restores the stock PyTorch path exactly.
+``patch_model(model)`` moves every reference ``ViLBlock`` and ``ProductOfExperts(2)`` instance found in ``model`` onto
+a patched SUBCLASS of its own class (``instance.__class__`` is swapped; the subclass only overrides ``forward``) and
+rebinds the module-level functions of the path -- ``reparametrize`` / ``clip`` (RA_HVED.py:741-753, looked up at
+RA_HVED.py:597, 580), ``compute_KLD`` (loss.py:85) and the ``ZeroLayerF`` autograd function
+(buildingblocks.py:308-323) -- in EVERY loaded module that holds a reference to the original object (``train.py:23``
+and ``Pretrain.py:23`` do ``from loss import compute_KLD``, so rebinding ``loss.compute_KLD`` alone would not reach the
+training loop).
+
+Why a subclass and not an instance attribute:
+  * ``nn.DataParallel`` (train.py:148-151) replicates modules with ``replica.__dict__ = module.__dict__.copy()``: a bound
+    method stored on the instance would keep pointing at the device-0 module; a class-level ``forward`` resolves ``self``
+    to the replica and therefore to the replica's parameters and device.
+  * ``torch.save({'model': model})`` (train.py:370-397) pickles whole modules: the patched subclasses reduce themselves
+    as their ORIGINAL class, so a checkpoint written from a patched model is byte-compatible with the reference (it
+    loads without this package and comes back unpatched).
+Parameters and state_dict keys are untouched; ``unpatch_model`` restores classes and globals exactly.
 """
 from __future__ import annotations
 
+import copyreg
 import sys
-import types
 
 from . import modules
 
-_ORIG = "_xhved_original_forward"
+_PATCHED = {}          # (original class, kind) -> patched subclass
+_GLOBALS = []          # (module, attribute name, original object) of every rebound global
 
 
-def _bind(mod, fn):
-    if not hasattr(mod, _ORIG):
-        setattr(mod, _ORIG, mod.__dict__.get("forward", None))   # instance-level override, if any
-    mod.forward = types.MethodType(fn, mod)
+def _reduce_as_base(self, protocol):
+    """Pickle a patched module as an instance of the reference's own class (stdlib reconstructor + the instance state:
+    nothing of this package is needed to load the checkpoint)."""
+    state = object.__reduce_ex__(self, 2)[2]
+    return (copyreg._reconstructor, (type(self)._xhved_base, object, None), state)
+
+
+def _vil_forward(self, x):
+    return modules.vil_block_forward(self, x)
+
+
+def _poe_forward(self, mu_list, logvar_list, mod_list, eps=1e-8):
+    return modules.product_of_experts(mu_list, logvar_list, mod_list, eps)
+
+
+def _poe2_forward(self, mu, logvar, drop, eps=1e-8):
+    return modules.product_of_experts_drop(mu, logvar, drop, eps)
+
+
+_FORWARDS = {"ViLBlock": _vil_forward, "ProductOfExperts": _poe_forward, "ProductOfExperts2": _poe2_forward}
+
+
+def _patched_class(cls, kind):
+    key = (cls, kind)
+    if key not in _PATCHED:
+        _PATCHED[key] = type(cls.__name__, (cls,), {"forward": _FORWARDS[kind], "_xhved_base": cls, "__reduce_ex__": _reduce_as_base,
+                                                    "__module__": cls.__module__, "__qualname__": cls.__qualname__})
+    return _PATCHED[key]
+
+
+def _kind_of(m):
+    if hasattr(type(m), "_xhved_base"):
+        return None                                   # already patched
+    name = type(m).__name__
+    if name == "ViLBlock" and hasattr(m, "layer") and hasattr(m.layer, "mlstm_cell"):
+        return "ViLBlock"
+    if name in ("ProductOfExperts", "ProductOfExperts2") and type(m).__module__ != modules.__name__:
+        return name
+    return None
+
+
+def _rebind_everywhere(original, replacement, attr):
+    """Replace ``attr`` in every loaded module where it IS ``original`` (from-imports included).  Returns the count."""
+    n = 0
+    for mod in list(sys.modules.values()):
+        d = getattr(mod, "__dict__", None)
+        if d is None or d.get(attr) is not original:
+            continue
+        _GLOBALS.append((mod, attr, original))
+        setattr(mod, attr, replacement)
+        n += 1
+    return n
 
 
 def patch_model(model, patch_globals: bool = True):
-    """Returns a dict with the number of patched objects per kind."""
-    counts = {"ViLBlock": 0, "ProductOfExperts": 0, "ProductOfExperts2": 0, "globals": 0}
+    """Returns a dict with the number of patched objects per kind; ``globals`` counts (module, name) bindings rebound and
+    ``rebound`` lists them as "module.name"."""
+    counts = {"ViLBlock": 0, "ProductOfExperts": 0, "ProductOfExperts2": 0, "globals": 0, "rebound": []}
     for m in model.modules():
-        name = type(m).__name__
-        if name == "ViLBlock" and hasattr(m, "layer") and hasattr(m.layer, "mlstm_cell"):
-            _bind(m, lambda self, x: modules.vil_block_forward(self, x))
-            counts["ViLBlock"] += 1
-        elif name == "ProductOfExperts":
-            _bind(m, lambda self, mu_list, logvar_list, mod_list, eps=1e-8: modules.product_of_experts(mu_list, logvar_list, mod_list, eps))
-            counts["ProductOfExperts"] += 1
-        elif name == "ProductOfExperts2":
-            _bind(m, lambda self, mu, logvar, drop, eps=1e-8: modules.product_of_experts_drop(mu, logvar, drop, eps))
-            counts["ProductOfExperts2"] += 1
+        kind = _kind_of(m)
+        if kind is not None:
+            m.__class__ = _patched_class(type(m), kind)
+            counts[kind] += 1
     if patch_globals:
-        ra = sys.modules.get("RA_HVED")
-        if ra is not None and hasattr(ra, "reparametrize"):
-            if not hasattr(ra, "_xhved_reparametrize"):
-                ra._xhved_reparametrize = ra.reparametrize
-            ra.reparametrize = modules.reparametrize
-            counts["globals"] += 1
-        ls = sys.modules.get("loss")
-        if ls is not None and hasattr(ls, "compute_KLD"):
-            if not hasattr(ls, "_xhved_compute_KLD"):
-                ls._xhved_compute_KLD = ls.compute_KLD
-            ls.compute_KLD = modules.compute_KLD
-            counts["globals"] += 1
+        before = len(_GLOBALS)
+        ra, ls, bb = sys.modules.get("RA_HVED"), sys.modules.get("loss"), sys.modules.get("buildingblocks")
+        for owner, attr, repl in ((ra, "reparametrize", modules.reparametrize), (ra, "clip", modules.clip),
+                                  (ls, "compute_KLD", modules.compute_KLD), (bb, "ZeroLayerF", modules.ZeroLayerF)):
+            orig = getattr(owner, attr, None) if owner is not None else None
+            if orig is None or orig is repl:
+                continue
+            _rebind_everywhere(orig, repl, attr)
+        counts["globals"] = len(_GLOBALS) - before
+        counts["rebound"] = [f"{mod.__name__}.{attr}" for mod, attr, _ in _GLOBALS[before:]]
     return counts
 
 
 def unpatch_model(model):
     for m in model.modules():
-        if hasattr(m, _ORIG):
-            orig = getattr(m, _ORIG)
-            if orig is None:
-                m.__dict__.pop("forward", None)
-            else:
-                m.forward = orig
-            delattr(m, _ORIG)
-    ra = sys.modules.get("RA_HVED")
-    if ra is not None and hasattr(ra, "_xhved_reparametrize"):
-        ra.reparametrize = ra._xhved_reparametrize
-        del ra._xhved_reparametrize
-    ls = sys.modules.get("loss")
-    if ls is not None and hasattr(ls, "_xhved_compute_KLD"):
-        ls.compute_KLD = ls._xhved_compute_KLD
-        del ls._xhved_compute_KLD
+        base = getattr(type(m), "_xhved_base", None)
+        if base is not None:
+            m.__class__ = base
+    while _GLOBALS:
+        mod, attr, orig = _GLOBALS.pop()
+        setattr(mod, attr, orig)
