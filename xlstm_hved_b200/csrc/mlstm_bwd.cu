@@ -14,6 +14,8 @@
 //   phase B4  gate_finish   per (b,head): reverse cumsum over the whole sequence
 //
 // The gradient through the row-max stabiliser m_t is dropped (relative effect ~1e-6, see tests).
+#include <stdlib.h>
+
 #include "mlstm_common.cuh"
 #include "prof.cuh"
 #include "xhved.h"
@@ -22,6 +24,21 @@ namespace xhved {
 
 int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
                       float* m_prev, cudaStream_t st);
+int launch_chunk_grad_ws(int dhp, const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig,
+                         const float* fg, const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
+                         const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
+                         float* dc, float* dc_tot, cudaStream_t st);
+
+// Which chunk_grad kernel runs: the persistent kernel with balanced roles and P^T in tensor memory (mlstm_bwd_ws.cu) where it
+// is the faster of the two on B200 (measured, profiles/r02_cell_scaling.jsonl: dhp <= 32, two CTAs per SM), the
+// one-tile-per-CTA kernel below for dhp = 64.  XHVED_GRAD_WS=0 / 1 forces one of them for A/B measurements.  Read once.
+static bool grad_ws_enabled(int dhp) {
+  static const int mode = [] {
+    const char* e = getenv("XHVED_GRAD_WS");
+    return !e ? -1 : (e[0] == '0' ? 0 : 1);
+  }();
+  return mode < 0 ? dhp <= 32 : mode != 0;
+}
 
 // Build the row-extended gradient G_t in place over the dH tile (sG: [128][NE] tile-native) using the H tile.
 template <int DHP>
@@ -441,7 +458,11 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
                                                                    fg, m, den, scale, eps, ws_dstate, ws_g, ws_lam);
   }
   if (int rc = launch_state_scan(DHP, ws_dstate, ws_g, ws_lam, BH, nc, 1, rstates, mu_next, st)) return rc;
-  {
+  if (grad_ws_enabled(DHP)) {
+    if (int rc = launch_chunk_grad_ws(DHP, q, k, v, h, dh_t, ig, fg, m, den, states, m_prev, rstates, mu_next, BH, nc, scale, eps, dq, dk,
+                                      dv, dig, ws_dc, ws_lam, st))
+      return rc;
+  } else {
     const size_t smem = BwdSmem<DHP>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_grad_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

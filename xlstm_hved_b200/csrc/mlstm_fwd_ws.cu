@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-static int sm_count() {
+int sm_count_cached() {
   static int cached[16] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -321,7 +321,7 @@ static int launch_out_ws(const void* q, const void* k, const void* v, const floa
   const int ntiles = BH * nc;
   cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_out_ws_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) return (int)e;
-  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  const int grid = ntiles < sm_count_cached() ? ntiles : sm_count_cached();
   ProfScope ps(K_CHUNK_OUT, st);
   mlstm_chunk_out_ws_kernel<DHP><<<grid, C::NTHREADS, C::SMEM, st>>>(
       (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, ig, fg, (const unsigned char*)states, m_prev, nc,

@@ -46,13 +46,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware (up to `ns`) instead of spinning through issue slots
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a producer that never arrives traps the kernel (reported as a
-// launch failure through the C ABI) instead of hanging the device.
+// launch failure through the C ABI) instead of hanging the device.  The clock is
+// read once per 64 polls only: the poll loop itself stays three instructions.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+  long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+    if ((it & 63u) == 0u) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000LL) __trap();
+    }
   }
 }
 
