@@ -197,6 +197,10 @@ int xhved_profile_read(float* ms, int* launches, int n);
 
 /* Diagnostic: D[128][N] = A * B^T through tcgen05 with tile-native operands (see mlstm_fwd.cu). */
 int xhved_umma_selftest(const void* a_tile, const void* b_tile, int N, int K, int a_mn, int b_mn, float* d, void* stream);
+/* Diagnostic: clock64 cycles one thread needs to ISSUE `reps` tcgen05.mma (M = 128, bf16, K = 16 each, spread round-robin over
+ * n_acc independent accumulators; A in shared or tensor memory; K- or MN-major operands) and until they have COMPLETED.
+ * out2: device int64[2] = {issue cycles, issue + completion cycles}. */
+int xhved_umma_issue_bench(int N, int reps, int n_acc, int a_in_tmem, int mn_major, long long* out2, void* stream);
 
 /* ---------------------------------------------------------------- ViL block around the cell (K2, K3)
  * Parameter block: pointers to the reference's parameters (fp32, contiguous), named by state_dict key

@@ -90,6 +90,7 @@ SYMBOLS = {
     "xhved_profile_kernel_name": [c_int],
     "xhved_profile_read": [POINTER(c_float), POINTER(c_int), c_int],
     "xhved_reduce_replicas": [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p],
+    "xhved_umma_issue_bench": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_umma_selftest": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_vil_pre_fwd": [c_void_p, POINTER(VilParams), POINTER(VilShape)] + [c_void_p] * 9,
     "xhved_vil_post_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p],

@@ -122,26 +122,17 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_rstate_kernel(const unsi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  // dR[d][e'] = sum_t Q~[t][d] * G[t][e'].  As in chunk_state the lo tile sits inside the hi operand's 128-row window: one
+  // pass yields hi^T G in rows [0, DHP) and lo^T G in rows [DHP, 2 DHP); the epilogue adds them (DHP <= 64).
+  constexpr bool ONE_PASS = DHP <= 64;
   if (tid == 0) {
-    // dR[d][e'] = sum_t Q~[t][d] * G[t][e']
     umma_gemm(tmem, smem_u32(sQ), 128, kL * 16, smem_u32(sG), 128, kL * 16, umma_idesc(128, NE, true, true), kL, false);
-    umma_gemm(tmem, smem_u32(sQlo), 128, kL * 16, smem_u32(sG), 128, kL * 16, umma_idesc(128, NE, true, true), kL, true);
+    if (!ONE_PASS) umma_gemm(tmem, smem_u32(sQlo), 128, kL * 16, smem_u32(sG), 128, kL * 16, umma_idesc(128, NE, true, true), kL, true);
     umma_commit(&bar_mma);
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after();
-  if (warp * 32 < DHP) {
-    float* out = dstate + (static_cast<size_t>(tile) * DHP + tid) * NE;
-#pragma unroll
-    for (int c0 = 0; c0 < NE; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
-      if (tid < DHP) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      }
-    }
-  }
+  store_state_rows<DHP, ONE_PASS>(tmem, dstate + static_cast<size_t>(tile) * DHP * NE, reinterpret_cast<float*>(smem));
   if (tid == 0) {
     g_out[tile] = g;
     lam_out[tile] = lam;

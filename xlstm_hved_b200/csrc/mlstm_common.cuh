@@ -107,4 +107,49 @@ __device__ __forceinline__ void scale_row_hilo(unsigned char* hi, unsigned char*
   }
 }
 
+// Epilogue of chunk_state / chunk_rstate: rows d < DHP of the accumulator (plus, with ONE_PASS, rows d + DHP: the lo half of
+// the hi/lo operand, see the callers) -> out[d][0 .. NE) fp32.  DHP = 16: both row groups live in warp 0 (lanes d, d + 16);
+// DHP = 32 / 64: the lo rows belong to other warps and travel through `scratch` (>= DHP * NE floats of shared memory that
+// the finished MMAs no longer read).
+template <int DHP, bool ONE_PASS>
+__device__ __forceinline__ void store_state_rows(uint32_t tmem, float* __restrict__ out, float* scratch) {
+  constexpr int NE = ext_cols(DHP);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const int rows = ONE_PASS ? 2 * DHP : DHP;
+  if (ONE_PASS && DHP >= 32) {
+    if (tid >= DHP && tid < 2 * DHP) {
+#pragma unroll
+      for (int c0 = 0; c0 < NE; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + lane_base + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) scratch[(c0 + i) * DHP + (tid - DHP)] = v[i];
+      }
+    }
+    __syncthreads();
+  }
+  if (warp * 32 < (DHP >= 32 ? DHP : rows)) {
+#pragma unroll
+    for (int c0 = 0; c0 < NE; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + c0, v);
+      if (ONE_PASS && DHP == 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += __shfl_down_sync(0xffffffffu, v[i], 16);
+      } else if (ONE_PASS) {
+        if (tid < DHP) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += scratch[(c0 + i) * DHP + tid];
+        }
+      }
+      if (tid < DHP) {
+        float* o = out + static_cast<size_t>(tid) * NE + c0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+}
+
 }  // namespace xhved

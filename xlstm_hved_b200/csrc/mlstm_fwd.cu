@@ -74,27 +74,21 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  // D[d][e'] = sum_j K~[j][d] * Vext[j][e']   (A, B both MN-major views of row-j tiles).  The lo tile lies directly behind the
+  // hi tile, i.e. inside the 128-row MN window of the hi operand: rows [DHP, 2 DHP) of the SAME product are lo^T Vext, so
+  // for DHP <= 64 one pass of K = 128 yields both halves (a tcgen05.mma costs ~80 cycles whatever its size, measured with
+  // tools/bench_umma_issue.py: the instruction count is what bounds this kernel) and the epilogue adds the two row groups.
+  constexpr bool ONE_PASS = DHP <= 64;
   if (tid == 0) {
-    // D[d][e'] = sum_j K~[j][d] * Vext[j][e']   (A, B both MN-major views of row-j tiles)
     umma_gemm(tmem, smem_u32(sK), /*lbo*/ 128, /*sbo*/ kL * 16, smem_u32(sV), 128, kL * 16,
               umma_idesc(128, NE, true, true), kL, false);
-    umma_gemm(tmem, smem_u32(sKlo), 128, kL * 16, smem_u32(sV), 128, kL * 16, umma_idesc(128, NE, true, true), kL, true);
+    if (!ONE_PASS)
+      umma_gemm(tmem, smem_u32(sKlo), 128, kL * 16, smem_u32(sV), 128, kL * 16, umma_idesc(128, NE, true, true), kL, true);
     umma_commit(&bar_mma);
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after();
-  if (warp * 32 < DHP) {
-    float* out = dstate + (static_cast<size_t>(tile) * DHP + tid) * NE;
-#pragma unroll
-    for (int c0 = 0; c0 < NE; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
-      if (tid < DHP) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      }
-    }
-  }
+  store_state_rows<DHP, ONE_PASS>(tmem, dstate + static_cast<size_t>(tile) * DHP * NE, reinterpret_cast<float*>(smem));
   if (tid == 0) {
     g_out[tile] = g;
     amax_out[tile] = amax;

@@ -35,6 +35,18 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// ---- "leader" forms.  tcgen05.mma / tcgen05.commit / cp.async.bulk take their operands from UNIFORM registers.  Issued from
+// inside a divergent `if (lane == 0)` region every operand goes through R2UR (~100 cycles per instruction, measured); the
+// forms below are meant to be executed by a WHOLE warp in uniform control flow with identical operands, only the
+// instruction itself being predicated on `leader` (one lane), so the operands can live in uniform registers.
+__device__ __forceinline__ void mbar_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -79,6 +91,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_p(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "r"(leader)
       : "memory");
 }
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
@@ -126,6 +146,52 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_p(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// "elect" forms: executed by a whole CONVERGED warp with warp-uniform operands; one lane is elected inside the asm.  With
+// operands the compiler can prove uniform (kernel parameters, blockIdx, loop counters, __shfl_sync(.., 0) results) the
+// tcgen05 / bulk-copy instruction is emitted straight from uniform registers -- no per-lane "waterfall" loop around it.
+__device__ __forceinline__ void umma_bf16_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread are done
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -141,6 +207,68 @@ __device__ __forceinline__ void umma_gemm(uint32_t d_tmem, uint32_t a_addr, uint
   const uint64_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
   for (int k = 0; k < K / 16; ++k) {
     umma_bf16(d_tmem, ad, bd, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+    ad += a_step;
+    bd += b_step;
+  }
+}
+
+// One accumulation chain: D[128 x N] (+)= sum over K slices of A_k B_k^T.  The K = 16 slices of ONE chain are dependent
+// (each reads the accumulator the previous one wrote): with small N they do not cover the tensor pipe's latency, so several
+// independent chains are issued round-robin (umma_issue_interleaved) instead of one after the other.
+struct UmmaChain {
+  uint32_t d_tmem;      // accumulator
+  uint64_t ad, bd;      // running descriptors (A unused when a_in_tmem)
+  uint32_t a_tmem;      // A operand in tensor memory (packed bf16, 8 columns per slice) when a_in_tmem
+  uint32_t a_step, b_step, idesc;
+  int nk;               // remaining slices
+  uint32_t acc;         // accumulate flag of the next slice
+  bool a_in_tmem;
+};
+__device__ __forceinline__ UmmaChain umma_chain(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
+                                                uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K, bool accumulate_first) {
+  UmmaChain c;
+  c.d_tmem = d_tmem, c.ad = umma_desc(a_addr, a_lbo, a_sbo), c.bd = umma_desc(b_addr, b_lbo, b_sbo), c.a_tmem = 0;
+  c.a_step = (2u * a_lbo) >> 4, c.b_step = (2u * b_lbo) >> 4, c.idesc = idesc, c.nk = K / 16, c.acc = accumulate_first ? 1u : 0u;
+  c.a_in_tmem = false;
+  return c;
+}
+__device__ __forceinline__ UmmaChain umma_chain_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo,
+                                                   uint32_t idesc, int K, bool accumulate_first) {
+  UmmaChain c;
+  c.d_tmem = d_tmem, c.ad = 0, c.bd = umma_desc(b_addr, b_lbo, b_sbo), c.a_tmem = a_tmem;
+  c.a_step = 8u, c.b_step = (2u * b_lbo) >> 4, c.idesc = idesc, c.nk = K / 16, c.acc = accumulate_first ? 1u : 0u;
+  c.a_in_tmem = true;
+  return c;
+}
+// continue a chain with a second operand pair into the same accumulator (e.g. the lo half of a hi/lo split)
+__device__ __forceinline__ void umma_chain_rebase(UmmaChain& c, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
+                                                  uint32_t b_lbo, uint32_t b_sbo, int K) {
+  c.ad = umma_desc(a_addr, a_lbo, a_sbo), c.bd = umma_desc(b_addr, b_lbo, b_sbo);
+  c.a_step = (2u * a_lbo) >> 4, c.b_step = (2u * b_lbo) >> 4, c.nk = K / 16;
+}
+__device__ __forceinline__ void umma_chain_step(UmmaChain& c, uint32_t leader = 1u);
+template <int N>
+__device__ __forceinline__ void umma_issue_interleaved(UmmaChain (&c)[N], uint32_t leader = 1u) {
+  bool any = true;
+  while (any) {
+    any = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (c[i].nk > 0) {
+        umma_chain_step(c[i], leader);
+        any = true;
+      }
+  }
+}
+
+// whole-warp form of umma_gemm (see the "leader" forms above)
+__device__ __forceinline__ void umma_gemm_p(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
+                                            uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K, bool accumulate_first, uint32_t leader) {
+  uint64_t ad = umma_desc(a_addr, a_lbo, a_sbo);
+  uint64_t bd = umma_desc(b_addr, b_lbo, b_sbo);
+  const uint64_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
+  for (int k = 0; k < K / 16; ++k) {
+    umma_bf16_p(d_tmem, ad, bd, idesc, (k > 0 || accumulate_first) ? 1u : 0u, leader);
     ad += a_step;
     bd += b_step;
   }
@@ -197,6 +325,16 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
 // D[128 x N] (+)= A[128 x K] (TMEM, K-major packed bf16) * B[N x K]^T (smem tile-native view), K multiple of 16
 __device__ __forceinline__ void umma_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo,
                                              uint32_t idesc, int K, bool accumulate_first) {
@@ -206,6 +344,18 @@ __device__ __forceinline__ void umma_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, u
     umma_bf16_ts(d_tmem, a_tmem + 8u * k, bd, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
     bd += b_step;
   }
+}
+__device__ __forceinline__ void umma_chain_step(UmmaChain& c, uint32_t leader) {
+  if (c.a_in_tmem) {
+    umma_bf16_ts_p(c.d_tmem, c.a_tmem, c.bd, c.idesc, c.acc, leader);
+    c.a_tmem += c.a_step;
+  } else {
+    umma_bf16_p(c.d_tmem, c.ad, c.bd, c.idesc, c.acc, leader);
+    c.ad += c.a_step;
+  }
+  c.bd += c.b_step;
+  c.acc = 1u;
+  --c.nk;
 }
 // registers -> TMEM: this thread's lane, 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
