@@ -13,7 +13,10 @@ plus the S-MVAE product-of-experts fusion / sampling / KL of the same volumes, w
                are summed with one flat-bucket NCCL all-reduce per step.
 
 Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = same through the public API
-with host (pinned) inputs copied every step, roofline for the dominant kernel (CUDA-event timed, separate pass),
+with host (pinned) inputs copied every step and the step's outputs (y, dx, z, KL) copied back, roofline for the dominant
+kernel (CUDA-event timed, separate pass; HBM roof on MINIMUM bytes and tensor roof side by side for the cell kernels),
+sustained = the same step looped for >= 2 s, config3 = BASELINE configs[2]'s fusion (4 levels x 15 missing-modality subsets
+in one launch), gpu_eager_reference = the reference's own PyTorch classes on the same GPU (the competitor a user has today),
 cpu_baseline = the reference's own classes (baseline/_ref, when it travelled with the repo) or else the oracle port of its
 algorithm, on the host cores (bounded sample).  `--impl reference` times that CPU path as its own arm.
 """
@@ -135,6 +138,46 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def bind_to_gpu_numa_node(local_rank, world):
+    """Pin this rank (and therefore the pinned host buffers it allocates afterwards: first-touch) to the NUMA node of its GPU.
+    The node comes from /sys/bus/pci/devices/<bdf>/numa_node when the platform reports it, else from the usual HGX layout
+    (GPUs split evenly over the nodes in index order).  Returns a description for the JSON line."""
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    except OSError:
+        nodes = []
+    if len(nodes) < 2:
+        return {"numa_nodes": len(nodes), "bound": False}
+    node, how = None, "index"
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        v = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if v >= 0:
+            node, how = v, "pci"
+    except Exception:
+        pass
+    if node is None:
+        n_gpu = max(torch.cuda.device_count(), world)
+        node = nodes[min(len(nodes) - 1, local_rank * len(nodes) // n_gpu)]
+    cpus = set()
+    try:
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        # prefer this node for every later allocation of the process (set_mempolicy(MPOL_PREFERRED)); pinned buffers are
+        # allocated after this call
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))      # x86-64 set_mempolicy, MPOL_PREFERRED
+        return {"numa_nodes": len(nodes), "bound": True, "node": node, "cpus": len(use), "via": how}
+    except Exception as e:
+        return {"numa_nodes": len(nodes), "bound": False, "error": f"{type(e).__name__}: {e}"}
+
+
 def randomise_params(block, seed):
     """utils.init_weights semantics (utils.py:191-215): xavier-normal Linear weights, N(0,1) biases."""
     g = torch.Generator().manual_seed(seed)
@@ -177,7 +220,8 @@ class HotPath:
         self.blk_f.to(device)
         self.blk_r.to(device)
         self.params = list(self.blk_f.parameters()) + list(self.blk_r.parameters())
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=device)
+        # N > 1: ONE flat-bucket all-reduce of the parameter gradients per step (xlstm_hved_b200.dist.FlatGradBucket)
+        self.bucket = xh.dist.FlatGradBucket(self.params, average=True) if world > 1 else None
         g = torch.Generator().manual_seed(7)
         self.gy = torch.randn(B, DIM, *SPATIAL, generator=g).to(device)          # upstream gradient of the block output
         self.gz = [torch.randn(1, B, C, d, d, d, generator=g).to(device) for C, d in LEVELS]
@@ -222,8 +266,7 @@ class HotPath:
         else:
             out = self._body(slot)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat)
+            self.bucket.reduce()             # gather -> one NCCL all-reduce -> averaged gradients written back into p.grad
         sl["free"].record()
         return out
 
@@ -242,7 +285,7 @@ class HotPath:
         levels = list(zip(mu5, lv5))
         # the four latent levels ride in one launch; slab 0 is the model's constant prior (mu = 0, logvar = 0,
         # RA_HVED.py:576-580): declared, not read
-        ops.poe_fwd_levels(levels, [SUBSET_FULL], noises=noises, kld_out=self.kld.view(4, 1), standard_prior=True)
+        fused = ops.poe_fwd_levels(levels, [SUBSET_FULL], noises=noises, kld_out=self.kld.view(4, 1), standard_prior=True)
         ops.poe_bwd_levels(levels, [SUBSET_FULL], noises=noises, g_zs=self.gz, kld_scales=self.kld_scales, standard_prior=True)
         kld_total = torch.dot(self.kld, self.kld_w)                            # mean KL over the 4 levels (train.py:236-239)
         # ---- ViL block pair on the NCDHW feature (token view, no transposed copies), forward + backward
@@ -252,9 +295,10 @@ class HotPath:
         for p in self.params:
             p.grad = None
         y.backward(self.gy.reshape(self.B, DIM, -1).transpose(-1, -2))
-        if self.world > 1:
-            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat)
-        return kld_total + y.detach()[0, 0, 0]
+        # what the model consumes downstream / upstream of the path: y (-> decoder), z per level (-> decoder), dx (-> encoder
+        # backward) and the KL term of the loss
+        sl["outs"] = dict(y=y.detach(), dx=x.grad, z=[f[2] for f in fused], loss=kld_total + y.detach()[0, 0, 0])
+        return sl["outs"]["loss"]
 
 
 def run_gpu(args):
@@ -264,6 +308,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local, world)          # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from xlstm_hved_b200 import _lib
@@ -316,7 +361,12 @@ def run_gpu(args):
     # ---- e2e: host (pinned) inputs copied in every step, result read back every step
     hx, hmus, hlvs = synth_inputs(B, 2000 + rank, None, pin=True)
     h2d = hx.numel() * 4 + sum(m.numel() * 4 for m in hmus) + sum(l.numel() * 4 for l in hlvs)
-    out_host = torch.empty(1).pin_memory()
+    # outputs read back every step: y (-> decoder), z of the four levels (-> decoder), dx (-> encoder backward), the loss term
+    out_host = dict(y=torch.empty(B, DIM, *SPATIAL).pin_memory(), dx=torch.empty(B, DIM, *SPATIAL).pin_memory(),
+                    z=[torch.empty(1, B, C, d, d, d).pin_memory() for C, d in LEVELS], loss=torch.empty(1).pin_memory())
+    d2h = sum(t.numel() * 4 for t in (out_host["y"], out_host["dx"], out_host["loss"], *out_host["z"]))
+    d2h_stream = torch.cuda.Stream(device=device)
+    done = [torch.cuda.Event(), torch.cuda.Event()]
 
     state = {"k": 0}
     hp.load(hx, hmus, hlvs, slot=0)
@@ -324,7 +374,22 @@ def run_gpu(args):
     def e2e_step():
         k = state["k"]
         hp.load(hx, hmus, hlvs, slot=(k + 1) & 1)          # next step's inputs stream in while this step computes
-        out_host.copy_(hp.step(slot=k & 1, graphed=graphed).reshape(1), non_blocking=False)
+        if k >= 2:
+            torch.cuda.current_stream().wait_event(done[k & 1])     # step k-2 (same slot) has handed its results over
+        hp.step(slot=k & 1, graphed=graphed)
+        outs = hp.slots[k & 1]["outs"]
+        # results leave on their own stream (full duplex with the next step's H2D); the step is complete for the host when
+        # its results have landed
+        d2h_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(d2h_stream):
+            out_host["y"].copy_(outs["y"].transpose(-1, -2).reshape(B, DIM, *SPATIAL), non_blocking=True)
+            out_host["dx"].copy_(outs["dx"], non_blocking=True)
+            for hz, dz in zip(out_host["z"], outs["z"]):
+                hz.copy_(dz, non_blocking=True)
+            out_host["loss"].copy_(outs["loss"].reshape(1), non_blocking=True)
+            done[k & 1].record(d2h_stream)
+        if k > 0:
+            done[(k - 1) & 1].synchronize()                # the previous step's results are on the host
         state["k"] = k + 1
 
     for _ in range(2):
@@ -333,6 +398,38 @@ def run_gpu(args):
     torch.cuda.synchronize()
     hp.load(x, mus, lvs, slot=0)
     torch.cuda.synchronize()
+
+    # ---- sustained: the same device-resident step looped for >= 2 s (the 20-step figure above is a burst of ~25 ms)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(K, int(math.ceil(2000.0 / (ms_total / K))))
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        ms_sus = timed(run_step, n_sus)
+        c2 = sampler2.stop() if rank == 0 else None
+        sustained = {"value": round(world * B * n_sus / (ms_sus * 1e-3), 2), "unit": "volumes/s", "steps": n_sus,
+                     "seconds": round(ms_sus * 1e-3, 3), "ms_per_step": round(ms_sus / n_sus, 4), "clocks": c2}
+
+    # ---- config3 (BASELINE configs[2]): the S-MVAE fusion of all 15 missing-modality subsets, 4 latent levels, ONE launch,
+    # inference (no sampling), for this rank's B volumes; posteriors larger than L2
+    config3 = None
+    if True:
+        from xlstm_hved_b200 import ops as xops
+        sl0 = hp.slots[0]
+        levels3 = list(zip(sl0["mu5"], sl0["lv5"]))
+        for _ in range(W):
+            xops.poe_fwd_levels(levels3, xops.SUBSETS_MODALITIES, standard_prior=True)
+        ms_c3 = timed(lambda: xops.poe_fwd_levels(levels3, xops.SUBSETS_MODALITIES, standard_prior=True), K)
+        n_lat_rank = sum(C * d ** 3 for C, d in LEVELS) * B
+        bytes_c3 = n_lat_rank * (32 + 15 * 8)
+        gbs = bytes_c3 / (ms_c3 / K * 1e-3) / 1e9
+        peaks0 = load_peaks()
+        config3 = {"workload": "configs[2]: PoE fusion under all 15 missing-modality subsets x 4 latent levels, one launch, inference",
+                   "value": round(world * B * K / (ms_c3 * 1e-3), 1), "unit": "volumes/s (x 15 subsets each)", "ms_per_launch": round(ms_c3 / K, 4),
+                   "roofline": {"kernel": "poe_fwd<15 subsets>", "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks0["hbm"], "unit": "GB/s",
+                                "frac": round(gbs / peaks0["hbm"], 4), "algorithmic_bytes_per_launch": bytes_c3,
+                                "note": "32 B in (4 modality posteriors; the constant prior is declared, not read) + 15 x 8 B out per latent element"}}
 
     # ---- per-kernel attribution (separate pass, CUDA events on the launching stream)
     nk = lib.xhved_profile_kernel_count()
@@ -374,20 +471,32 @@ def run_gpu(args):
         "vil_pre_bwd_a": E * 4 + 3 * E * 4 + 8 * 4 + E * 4 + 2 * E * 4,               # xm, dq,dk,dv, dgates, d_act in; dconv, dxmv out
         "vil_pre_bwd_b": 4 * DIM + 4 * DIM + 3 * E * 4 + 4 * DIM,                     # x, dy, dconv, dxmv, dz in; dx out
     }
+    # cell kernels, per token-head: MINIMUM bytes in the sense of SURVEY 8d -- bf16 q,k,v (dh) in, bf16 h (dq,dk,dv) out, fp32
+    # gates / stabiliser / normaliser; carried states, hi/lo pairs and fp32 gradient rows are implementation traffic and do
+    # NOT count (impl_bytes below keeps them for reference)
     per_tokenhead_bytes = {
-        "mlstm_chunk_state": 4 * DHP + 8 + st_tok,                                    # k,v tiles, i/f gates in; chunk state out
-        "mlstm_state_scan": 2 * st_tok,                                               # chunk states in; carried states (bf16 hi+lo) out
-        "mlstm_chunk_out": 6 * DHP + 8 + st_tok + 2 * DHP + 8,                        # q,k,v, gates, state in; h, m, den out
-        "mlstm_chunk_rstate": 6 * DHP + 12 + st_tok,                                  # q, dh, h tiles, f, m, den in; reverse chunk state out
-        "mlstm_chunk_grad": 10 * DHP + 16 + 2 * st_tok + 12 * DHP + 8,                # q,k,v,h,dh, gates, m, den, C, R in; dq,dk,dv, di, dc out
+        "mlstm_chunk_state": 4 * DHP + 8,                                             # k, v tiles, i/f gates in (the chunk state is an intermediate)
+        "mlstm_chunk_out": 6 * DHP + 8 + 2 * DHP + 8,                                 # q,k,v, gates in; h, m, den out
+        "mlstm_chunk_rstate": 6 * DHP + 12,                                           # q, dh, h tiles, f, m, den in
+        "mlstm_chunk_grad": 10 * DHP + 16 + 6 * DHP + 8,                              # q,k,v,h,dh, gates, m, den in; bf16 dq,dk,dv, di, dc out = 280 B at dhp 16
+    }
+    impl_tokenhead_bytes = {
+        "mlstm_chunk_state": 4 * DHP + 8 + st_tok,
+        "mlstm_state_scan": 2 * st_tok,
+        "mlstm_chunk_out": 6 * DHP + 8 + st_tok + 2 * DHP + 8,
+        "mlstm_chunk_rstate": 6 * DHP + 12 + st_tok,
+        "mlstm_chunk_grad": 10 * DHP + 16 + 2 * st_tok + 12 * DHP + 8,                # fp32 dq,dk,dv rows, hi/lo states C and R
         "mlstm_gate_finish": 12,
     }
     bytes_per_launch = {k: v * tokens for k, v in per_token_bytes.items()}
     bytes_per_launch.update({k: v * tokens_heads for k, v in per_tokenhead_bytes.items()})
+    impl_bytes_per_launch = {k: v * tokens_heads for k, v in impl_tokenhead_bytes.items()}
     # PoE per latent element: 4 x (mu, logvar) in (the constant prior is never read) + noise; mu^, logvar^, z out;
     # backward: the same 32 B + noise + g_z in, 32 B of gradients out.  One launch per step covers the 4 latent levels.
     bytes_per_step = {"poe_fwd": n_lat * (32 + 4 + 12), "poe_bwd": n_lat * (32 + 4 + 4 + 32)}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if not os.path.exists(traffic_file):
+        traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
 
     def roofline_of(name):
@@ -399,25 +508,31 @@ def run_gpu(args):
                     "ms_per_step": round(ms / K, 5), "peak_source": peaks["src"], "note": "one launch per step covers the four latent levels"}
         if name not in bytes_per_launch:
             return {"kernel": name, "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
-                    "avg_launch_ms": round(ms / cnt, 5)}
+                    "avg_launch_ms": round(ms / cnt, 5),
+                    "note": "moves intermediates only (no algorithmic bytes of its own): pure latency"}
         sec = ms / cnt * 1e-3
         nbytes, nflop = bytes_per_launch[name], flops.get(name, 0)
         hbm = {"kernel": name, "bound": "hbm", "achieved": round(nbytes / sec / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
                "frac": round(nbytes / sec / 1e9 / peaks["hbm"], 4), "traffic": traffic.get(name), "algorithmic_bytes_per_launch": int(nbytes),
                "avg_launch_ms": round(ms / cnt, 5), "peak_source": peaks["src"]}
+        if name in impl_bytes_per_launch:
+            hbm["implementation_bytes_per_launch"] = int(impl_bytes_per_launch[name])
+            hbm["note_bytes"] = "algorithmic = minimum bytes (bf16 operands / results, fp32 gates); implementation bytes add carried states and fp32 gradient rows"
         if not nflop:
             return hbm
+        # cell kernels: both roofs side by side -- HBM on minimum bytes (frac) and bf16 tensor peak on useful FLOP (tensor_frac)
         tf = nflop / sec / 1e12
         hbm["tensor_frac"] = round(tf / peaks["tf"], 5)
+        hbm["tensor_achieved_tflops"] = round(tf, 2)
+        hbm["tensor_peak_tflops"] = peaks["tf"]
         hbm["algorithmic_flop_per_launch"] = nflop
-        if nflop / (peaks["tf"] * 1e12) <= nbytes / (peaks["hbm"] * 1e9):
-            hbm["note"] = "arithmetic intensity %.0f FLOP/B is below the ridge (%.0f): HBM is the binding roof at this head dim" % (
-                nflop / nbytes, peaks["tf"] * 1e12 / (peaks["hbm"] * 1e9))
-            return hbm
-        return {"kernel": name, "bound": "tensor", "achieved": round(tf, 3), "peak": peaks["tf"], "unit": "TFLOP/s",
-                "frac": round(tf / peaks["tf"], 5), "traffic": traffic.get(name), "algorithmic_flop_per_launch": nflop,
-                "hbm_frac": hbm["frac"], "avg_launch_ms": round(ms / cnt, 5),
-                "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside the step)"}
+        binding = "hbm" if nflop / (peaks["tf"] * 1e12) <= nbytes / (peaks["hbm"] * 1e9) else "tensor"
+        hbm["note"] = "arithmetic intensity %.0f FLOP/B vs ridge %.0f: the binding roof is %s; both fractions are reported" % (
+            nflop / nbytes, peaks["tf"] * 1e12 / (peaks["hbm"] * 1e9), binding)
+        if binding == "tensor":
+            hbm.update({"bound": "tensor", "achieved": round(tf, 3), "peak": peaks["tf"], "unit": "TFLOP/s", "hbm_frac": hbm["frac"],
+                        "frac": round(tf / peaks["tf"], 5)})
+        return hbm
 
     order = sorted(kern.items(), key=lambda kv: -kv[1][0])
     roof = roofline_of(order[0][0])
@@ -439,6 +554,13 @@ def run_gpu(args):
                                    "chunk_out_executed_tflops": ko["executed_tflops"],
                                    "chunk_out_executed_frac_of_burst_peak": ko["executed_frac_of_bf16_burst_peak"],
                                    "fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"]}
+            kg = r["kernels"].get("mlstm_chunk_grad")
+            if kg:
+                cell[f"DH{cfg[3]}"].update({"chunk_grad_ms": kg["ms"], "chunk_grad_useful_tflops": kg["useful_tflops"],
+                                            "chunk_grad_executed_tflops": kg["executed_tflops"],
+                                            "chunk_grad_executed_frac_of_burst_peak": kg["executed_frac_of_bf16_burst_peak"]})
+    eager_ref = gpu_eager_reference(device) if world == 1 and not args.no_eager_ref else None
+    torch.cuda.empty_cache()
     cpu = cpu_reference_arm(steps=args.cpu_steps, warmup=1) if world == 1 and not args.no_cpu else None
     vols = world * B * K
     line = {
@@ -453,11 +575,16 @@ def run_gpu(args):
                    "l2_policy": f"inputs larger than L2 (PoE posteriors {h2d / 2**20:.0f} MiB per step > 126 MiB)",
                    "launch": "CUDA graph replay of the step captured through the public API" if graphed else "eager (one Python call per op)",
                    "eager_ms_per_step": round(ms_eager / K, 4),
-                   "collective": "1 flat-bucket NCCL all-reduce of the 28 ViL parameter gradients per step" if world > 1 else "none"},
-        "e2e": {"value": round(vols / (ms_e2e * 1e-3), 2), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / K, 4),
+                   "collective": "1 flat-bucket NCCL all-reduce (xlstm_hved_b200.dist.FlatGradBucket: gather, all-reduce, average, write "
+                                 "back) of the 28 ViL parameter gradients per step" if world > 1 else "none"},
+        "e2e": {"value": round(vols / (ms_e2e * 1e-3), 2), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(ms_e2e / K, 4), "numa": numa,
                 "note": "every step copies its inputs from pinned host memory (copy stream, double-buffered against the previous "
-                        "step's compute) and reads the step's loss back; PCIe-bound"},
+                        "step's compute) and copies back what the model consumes around the path: y and dx (B,32,16,16,16), z of the four "
+                        "latent levels and the loss term (own stream, full duplex with the next step's inputs).  The gradients w.r.t. the "
+                        "posteriors (d_mu, d_logvar: 8 x the z bytes) and the 28 parameter gradients stay on the device, where the encoder "
+                        "backward / the optimizer consume them.  PCIe-bound"},
+        "sustained": sustained, "config3": config3, "gpu_eager_reference": eager_ref,
         "gpu_launches": launches, "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
         "kernel_ms_per_step_total": round(sum(v[0] for v in kern.values()) / K, 4), "kernel_time_share": shares, "roofline": roof, "roofline_secondary": secondary,
         "clocks": clocks, "mlstm_cell_tensor_peak": cell,
@@ -509,6 +636,50 @@ def reference_hot_path_one_volume(ns, blk_f, blk_r, x, mus, lvs, gy, gzs):
         loss = loss + (z * gzs[l][0]).sum() + 0.2 * ns.loss.KL_divergence(a, b) / 4
     loss.backward()
     return float(loss)
+
+
+def gpu_eager_reference(device, iters=3):
+    """The competitor a user of the reference has on the same GPU: the reference's OWN classes (baseline/_ref, unmodified) in
+    PyTorch eager on the B200 -- vision_lstm.ViLBlock pair (O(S^2) parallel cell), buildingblocks.ProductOfExperts,
+    RA_HVED.reparametrize / clip, loss.KL_divergence -- fwd + bwd, one volume per step as the reference trains (train.py:50).
+    A baseline leg: nothing of it is on the product path."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "RA_HVED.py")):
+        return {"unavailable": "no reference tree travelled with the repo (baseline/_ref)"}
+    try:
+        os.environ["XHVED_REFERENCE"] = ref_dir
+        from oracle import ref_loader
+        import xlstm_hved_b200 as xh
+        ns = ref_loader.load_reference()
+        vl = ns.vision_lstm
+        blocks = []
+        for seed, md, rd in ((1, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT, vl.SequenceTraversal.ROWWISE_FROM_TOP_LEFT),
+                             (2, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT, vl.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)):
+            mirror = xh.ViLBlock(DIM, md)
+            randomise_params(mirror, seed)
+            rb = vl.ViLBlock(dim=DIM, direction=rd)
+            rb.load_state_dict(mirror.state_dict(), strict=True)
+            blocks.append(rb.to(device))
+        x, mus, lvs = synth_inputs(1, 1000, device)
+        g = torch.Generator().manual_seed(7)
+        gy = torch.randn(1, DIM, *SPATIAL, generator=g).to(device)
+        gzs = [torch.randn(1, 1, C, d, d, d, generator=g).to(device) for C, d in LEVELS]
+        step = lambda: reference_hot_path_one_volume(ns, blocks[0], blocks[1], x, mus, lvs, gy, gzs)
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return {"value": round(1e3 / ms, 2), "unit": "volumes/s", "ms_per_volume": round(ms, 3), "volumes_per_step": 1, "iters": iters,
+                "what": "reference's own vision_lstm.ViLBlock pair + ProductOfExperts / reparametrize / clip / KL_divergence, fp32 eager, "
+                        "fwd+bwd through autograd, on this GPU (includes the loss read-back the helper does per volume)",
+                "peak_mem_gb": round(torch.cuda.max_memory_allocated(device) / 2 ** 30, 2)}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def cpu_reference_arm(steps, warmup):
@@ -593,6 +764,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="volumes per GPU per step")
     ap.add_argument("--cpu-steps", type=int, default=2, help="volumes timed for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained loop")
+    ap.add_argument("--no-eager-ref", action="store_true", help="skip timing the reference's PyTorch classes on the GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured step")
     args = ap.parse_args()
     if args.impl == "reference":

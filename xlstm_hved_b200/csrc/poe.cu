@@ -121,7 +121,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // SP: expert 0 is the constant standard-normal prior and is not read (XHVED_POE_STANDARD_PRIOR)
-template <int V, int NS, bool SP>
+template <int V, int NS, bool SP, bool CLIP>
 __global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, const PoeSubsets ss, const float eps) {
   PoeLevelF L;
   int blk0, nblk;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, con
         ld<V>(lv + e * stride + i, Lv[e]);
       }
     }
-    if (ss.clip) {
+    if (CLIP) {
 #pragma unroll
       for (int e = 1; e < 5; ++e)
 #pragma unroll
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const PoeFwdArgs args, con
   }
 }
 
-template <int V, int NS, bool SP>
+template <int V, int NS, bool SP, bool CLIP>
 __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, const PoeSubsets ss, const float eps) {
   PoeLevelB L;
   int blk0, nblk;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, 
         ld<V>(lv + e * stride + i, EL[e]);
       }
     }
-    if (ss.clip) {
+    if (CLIP) {
 #pragma unroll
       for (int e = 1; e < 5; ++e)
 #pragma unroll
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256, 2) poe_bwd_kernel(const PoeBwdArgs args, 
       for (int j = 0; j < V; ++j) {
         dl[j] = -dT[e][j] * T[e][j] * T[e][j] * EL[e][j];
         if (e == 0) dl[j] += dL0[j];
-        else if (!((pass >> (e * 4 + j)) & 1u)) dl[j] = 0.f;
+        else if (CLIP && !((pass >> (e * 4 + j)) & 1u)) dl[j] = 0.f;
       }
       st<V, true>(d_mu + e * stride + i, dM[e]);
       st<V, true>(d_lv + e * stride + i, dl);
@@ -473,14 +473,25 @@ static bool level_v4(const PoeLevelB& L) {
 template <int V, int NS>
 static void launch_fwd(PoeFwdArgs& a, const PoeSubsets& ss, float eps, bool sp, cudaStream_t st) {
   const int grid = assign_blocks(a, V);
-  if (sp) poe_fwd_kernel<V, NS, true><<<grid, 256, 0, st>>>(a, ss, eps);
-  else poe_fwd_kernel<V, NS, false><<<grid, 256, 0, st>>>(a, ss, eps);
+  if (ss.clip) {
+    if (sp) poe_fwd_kernel<V, NS, true, true><<<grid, 256, 0, st>>>(a, ss, eps);
+    else poe_fwd_kernel<V, NS, false, true><<<grid, 256, 0, st>>>(a, ss, eps);
+  } else {
+    if (sp) poe_fwd_kernel<V, NS, true, false><<<grid, 256, 0, st>>>(a, ss, eps);
+    else poe_fwd_kernel<V, NS, false, false><<<grid, 256, 0, st>>>(a, ss, eps);
+  }
 }
 template <int V, int NS>
 static void launch_bwd(PoeBwdArgs& a, const PoeSubsets& ss, float eps, bool sp, cudaStream_t st) {
   const int grid = assign_blocks(a, V);
-  if (sp) poe_bwd_kernel<V, NS, true><<<grid, 256, 0, st>>>(a, ss, eps);
-  else poe_bwd_kernel<V, NS, false><<<grid, 256, 0, st>>>(a, ss, eps);
+  // the fused clip is a compile-time variant: the un-clipped kernels keep the register budget they were tuned with
+  if (ss.clip) {
+    if (sp) poe_bwd_kernel<V, NS, true, true><<<grid, 256, 0, st>>>(a, ss, eps);
+    else poe_bwd_kernel<V, NS, false, true><<<grid, 256, 0, st>>>(a, ss, eps);
+  } else {
+    if (sp) poe_bwd_kernel<V, NS, true, false><<<grid, 256, 0, st>>>(a, ss, eps);
+    else poe_bwd_kernel<V, NS, false, false><<<grid, 256, 0, st>>>(a, ss, eps);
+  }
 }
 
 static int run_fwd(PoeFwdArgs& a, const uint32_t* subset_masks, int n_subsets, float eps, int flags, cudaStream_t st,

@@ -31,31 +31,37 @@ class FlatGradBucket:
         self.grads = self.flat[:self.numel]
         self.flags = self.flat[self.numel:]
         self.average = average
+        self._has = None
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.grads[off:off + p.numel()].view_as(p))
             off += p.numel()
 
     def reduce(self, group=None):
-        """Gather p.grad into the bucket, all-reduce it, write the result back into p.grad.  Returns the gradient part."""
-        has = [p.grad is not None for p in self.params]
-        self.flags.copy_(torch.tensor(has, dtype=torch.float32), non_blocking=True)
-        for p, v, h in zip(self.params, self.views, has):
-            if h:
-                v.copy_(p.grad)
-            else:
-                v.zero_()
+        """Gather p.grad into the bucket, all-reduce it, write the result back into p.grad.  Returns the gradient part.
+        Two multi-tensor copies and one collective per call, whatever the number of parameters."""
+        has = tuple(p.grad is not None for p in self.params)
+        if has != self._has:                      # upload the flags only when the pattern changes (normally once)
+            self.flags.copy_(torch.tensor(has, dtype=torch.float32))
+            self._has = has
+        with_grad = [(p.grad, v) for p, v in zip(self.params, self.views) if p.grad is not None]
+        without = [v for p, v in zip(self.params, self.views) if p.grad is None]
+        if with_grad:
+            torch._foreach_copy_([v for _, v in with_grad], [g for g, _ in with_grad])
+        if without:
+            torch._foreach_zero_(without)
         world = dist.get_world_size(group) if dist.is_initialized() else 1
+        anyone = has
         if world > 1:
             dist.all_reduce(self.flat, group=group)
             if self.average:
                 self.grads.div_(world)
-            anyone = (self.flags > 0).tolist() if not all(has) else has       # one small D2H only when some grad is missing
-        else:
-            anyone = has
+            if not all(has):                      # one small D2H only when some gradient is missing on this rank
+                anyone = tuple(f > 0 for f in self.flags.tolist())
+                self._has = None                  # the flags now hold counts: re-upload next time
+        if with_grad:
+            torch._foreach_copy_([g for g, _ in with_grad], [v for _, v in with_grad])
         for p, v, h, a in zip(self.params, self.views, has, anyone):
-            if h:
-                p.grad.copy_(v)
-            elif a:
+            if not h and a:
                 p.grad = v.clone()
         return self.grads
