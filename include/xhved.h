@@ -278,6 +278,19 @@ int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const vo
                       const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx, const xhved_vil_grads* g,
                       float* ws_dconv, float* ws_dxmv, void* stream);
 
+/* One whole ViL block per call (ViLBlock.forward, vision_lstm.py:494-502, and its backward): K2 -> cell -> K3 enqueued on
+ * `stream` into caller-allocated blobs.  xhved_vil_block_workspace reports the blob sizes: `saved` is written by the forward
+ * and read by the backward of the same call (it must stay untouched in between: one blob per live forward), `scratch` is
+ * the backward's own; n_param_grads = the number of floats of `param_grads`, which receives the 14 parameter gradients
+ * back to back in xhved_vil_params order.  sh->grad_replicas / grad_replica_stride as for xhved_vil_pre_bwd (the replicas
+ * live inside `scratch`, zero-filled by the call).  Nothing is allocated and no state is kept between calls. */
+int xhved_vil_block_workspace(int B, int S, int C, int grad_replicas, int64_t* saved_bytes, int64_t* scratch_bytes,
+                              int64_t* n_param_grads);
+int xhved_vil_block_fwd(const float* x, const xhved_vil_params* p, const xhved_vil_shape* sh, float eps, void* saved, float* y,
+                        void* stream);
+int xhved_vil_block_bwd(const float* x, const float* dy, const xhved_vil_params* p, const xhved_vil_shape* sh, float eps, void* saved,
+                        void* scratch, float* dx, float* param_grads, void* stream);
+
 /* dst[i] = sum_r src[r*stride + i], i < n  (reduction of the gradient replicas above). */
 int xhved_reduce_replicas(const float* src, int replicas, int64_t stride, int64_t n, float* dst, void* stream);
 

@@ -282,3 +282,44 @@ def test_dim16_block_at_32768_tokens_fwd_bwd_vs_oracle():
     for g, rg, key in zip(grads[1:], ref_grads[1:], keys):
         print(key, rel_l2(g, rg))
         assert rel_l2(g, rg) < 3e-2, key
+
+
+def test_vil_block_reentrant_on_two_streams_from_two_threads():
+    """The library keeps no state between calls and launches on the caller's stream (the reference runs replicas from several
+    Python threads, train.py:148-151): two threads, each on its own CUDA stream, running forward + backward on different
+    inputs at the same time give exactly what the same calls give one after the other."""
+    import threading
+    from xlstm_hved_b200 import ops
+    c = load_golden("vil_block.pt")["dim32_s200_fwd"]
+    params = _params(c["state_dict"])
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.randn(2, 900, 32, generator=g).cuda() for _ in range(2)]
+    dys = [torch.randn(2, 900, 32, generator=g).cuda() for _ in range(2)]
+
+    def run(i, out):
+        y, ws = ops.vil_block_fwd(xs[i], params, bool(i))
+        dx, grads = ops.vil_block_bwd(xs[i], dys[i], params, bool(i), ws)
+        out[i] = (y, dx, grads)
+
+    seq = {}
+    for i in range(2):
+        run(i, seq)
+    torch.cuda.synchronize()
+    par = {}
+    streams = [torch.cuda.Stream() for _ in range(2)]
+
+    def worker(i):
+        with torch.cuda.stream(streams[i]):
+            for _ in range(5):
+                run(i, par)
+            streams[i].synchronize()
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(2):
+        assert torch.equal(seq[i][0], par[i][0]) and torch.equal(seq[i][1], par[i][1])
+        for a, b in zip(seq[i][2], par[i][2]):           # parameter gradients: atomics, summation order is not fixed
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)

@@ -159,6 +159,12 @@ def test_workspace_queries_match_the_host_layer():
         blk = xh.ViLBlock(dim, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
         n_params = sum(p.numel() for p in xh.modules.vil_block_params(blk))
         assert w.grad_replica_stride == (n_params + 31) // 32 * 32
+        # the one-call block entry points carve their buffers out of two blobs: at least the sum of the parts
+        sv, sc, npg = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        assert lib.xhved_vil_block_workspace(B, S, dim, 32, ctypes.byref(sv), ctypes.byref(sc), ctypes.byref(npg)) == 0
+        assert npg.value == n_params
+        assert sv.value >= 4 * w.cell.tile_bytes + w.cell.states_bytes + 4 * w.cell.row_bytes + w.cell.dstate_bytes + 3 * w.token_minor_bytes
+        assert sc.value >= 32 * w.grad_replica_stride * 4 + w.cell.tile_bytes + w.cell.states_bytes + 3 * w.cell.grad_bytes + 4 * w.token_minor_bytes
     bad = _lib.MlstmWorkspace()
     assert lib.xhved_mlstm_workspace_query(4, 100, 200, ctypes.byref(bad)) == -2      # XHVED_ERR_UNSUPPORTED_DH
     assert lib.xhved_vil_workspace_query(1, 100, 48, ctypes.byref(_lib.VilWorkspaceSizes())) == -4   # XHVED_ERR_UNSUPPORTED_DIM

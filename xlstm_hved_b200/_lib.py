@@ -92,6 +92,10 @@ SYMBOLS = {
     "xhved_reduce_replicas": [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p],
     "xhved_umma_issue_bench": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_umma_selftest": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "xhved_vil_block_workspace": [c_int, c_int, c_int, c_int, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)],
+    "xhved_vil_block_fwd": [c_void_p, POINTER(VilParams), POINTER(VilShape), c_float, c_void_p, c_void_p, c_void_p],
+    "xhved_vil_block_bwd": [c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p],
     "xhved_vil_pre_fwd": [c_void_p, POINTER(VilParams), POINTER(VilShape)] + [c_void_p] * 9,
     "xhved_vil_post_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p],
     "xhved_vil_post_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_void_p, c_void_p,

@@ -435,16 +435,29 @@ def _dense_view(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-class VilWorkspace:
-    """Per-call device buffers of the fused ViL block."""
+class VilSaved:
+    """What one forward of the fused ViL block leaves for its backward: ONE device blob (tiles, gates, stabiliser, carried
+    states, act / z / xm; carved up inside xhved_vil_block_fwd / _bwd) and the sizes the library reported for this shape."""
+    __slots__ = ("blob", "scratch_bytes", "n_param_grads", "stride")
 
-    def __init__(self, B, S, C, device):
-        E = 2 * C
-        self.cell = CellBuffers(B * 4, S, E // 4, device)
-        nc = self.cell.nc
-        self.act = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
-        self.z = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
-        self.xm = torch.empty(B, nc, E, CHUNK, device=device, dtype=torch.float32)
+    def __init__(self, blob, scratch_bytes, n_param_grads, stride):
+        self.blob, self.scratch_bytes, self.n_param_grads, self.stride = blob, scratch_bytes, n_param_grads, stride
+
+
+_BLOCK_SIZES = {}        # (B, S, C, replicas) -> (saved_bytes, scratch_bytes, n_param_grads, stride): host-only queries, cached
+
+
+def _block_sizes(B, S, C):
+    key = (B, S, C, GRAD_REPLICAS)
+    if key not in _BLOCK_SIZES:
+        lib = _lib.load_library()
+        sv, sc, npg = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib.xhved_vil_block_workspace(B, S, C, GRAD_REPLICAS, ctypes.byref(sv), ctypes.byref(sc), ctypes.byref(npg)),
+              "xhved_vil_block_workspace")
+        sizes = _lib.VilWorkspaceSizes()
+        check(lib.xhved_vil_workspace_query(B, S, C, ctypes.byref(sizes)), "xhved_vil_workspace_query")
+        _BLOCK_SIZES[key] = (sv.value, sc.value, npg.value, sizes.grad_replica_stride)
+    return _BLOCK_SIZES[key]
 
 
 def _shape_struct(x_tok, y_tok, reverse):
@@ -457,62 +470,40 @@ def _shape_struct(x_tok, y_tok, reverse):
 
 
 def vil_block_fwd(x_tok: torch.Tensor, params, reverse: bool, eps: float = 1e-6):
-    """x_tok: (B,S,C) fp32 view; params: the 14 tensors in VIL_PARAM_KEYS order.  Returns (y_tok, workspace)."""
+    """x_tok: (B,S,C) fp32 view; params: the 14 tensors in VIL_PARAM_KEYS order.  Returns (y_tok, saved).
+    ONE call into the library (xhved_vil_block_fwd: K2 -> cell -> K3) and two allocations (y, the saved blob)."""
     lib = _lib.load_library()
     x_tok = _dense_view(x_tok)
     B, S, C = x_tok.shape
-    ws = VilWorkspace(B, S, C, x_tok.device)
+    saved_bytes, scratch_bytes, npg, stride = _block_sizes(B, S, C)
+    blob = torch.empty(saved_bytes, device=x_tok.device, dtype=torch.uint8)
     # output takes the memory format of the input (NCDHW-backed token view stays NCDHW-backed)
     y = torch.empty_strided(x_tok.shape, x_tok.stride(), device=x_tok.device, dtype=torch.float32)
     ps = _param_struct(params, _lib.VilParams)
     sh = _shape_struct(x_tok, y, reverse)
-    c = ws.cell
-    check(lib.xhved_vil_pre_fwd(ptr(x_tok), ctypes.byref(ps), ctypes.byref(sh), ptr(c.q), ptr(c.k), ptr(c.v), ptr(c.ig), ptr(c.fg),
-                                ptr(ws.act), ptr(ws.z), ptr(ws.xm), stream()), "xhved_vil_pre_fwd")
-    mlstm_fwd_tiles(c, eps)
-    check(lib.xhved_vil_post_fwd(ptr(x_tok), ptr(c.h), ptr(ws.act), ptr(ws.z), ctypes.byref(ps), ctypes.byref(sh), ptr(y), stream()),
-          "xhved_vil_post_fwd")
-    return y, ws
+    check(lib.xhved_vil_block_fwd(ptr(x_tok), ctypes.byref(ps), ctypes.byref(sh), eps, ptr(blob), ptr(y), stream()), "xhved_vil_block_fwd")
+    return y, VilSaved(blob, scratch_bytes, npg, stride)
 
 
-def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilWorkspace, eps: float = 1e-6):
-    """Backward of vil_block_fwd.  Returns (dx_tok, [14 parameter gradients in VIL_PARAM_KEYS order])."""
+def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilSaved, eps: float = 1e-6):
+    """Backward of vil_block_fwd.  Returns (dx_tok, [14 parameter gradients in VIL_PARAM_KEYS order]).
+    ONE call into the library (xhved_vil_block_bwd) and three allocations (scratch blob, dx, the flat parameter gradients)."""
     lib = _lib.load_library()
-    c = ws.cell
     dev = x_tok.device
     if dy_tok.dtype != torch.float32:
         dy_tok = dy_tok.float()
     dy_tok = _dense_view(dy_tok)
-    # parameter gradients are accumulated with global atomics into GRAD_REPLICAS zero-filled copies (CTA i -> copy i % R)
-    # to spread the traffic over L2 slices; xhved_reduce_replicas sums the copies at the end
-    sizes = _lib.VilWorkspaceSizes()
-    check(lib.xhved_vil_workspace_query(x_tok.shape[0], x_tok.shape[1], x_tok.shape[2], ctypes.byref(sizes)), "xhved_vil_workspace_query")
-    stride = sizes.grad_replica_stride
-    P = sum(p.numel() for p in params)
-    assert stride >= P
-    flat = torch.zeros(GRAD_REPLICAS * stride, device=dev, dtype=torch.float32)
-    grads, off = [], 0
-    for p in params:
-        grads.append(flat[off:off + p.numel()].view(p.shape))
-        off += p.numel()
-    ps = _param_struct(params, _lib.VilParams)
-    gs = _param_struct(grads, _lib.VilGrads)
+    assert sum(p.numel() for p in params) == ws.n_param_grads
+    scratch = torch.empty(ws.scratch_bytes, device=dev, dtype=torch.uint8)
+    out = torch.empty(ws.n_param_grads, device=dev, dtype=torch.float32)
     dx = torch.empty_strided(dy_tok.shape, dy_tok.stride(), device=dev, dtype=torch.float32)
+    ps = _param_struct(params, _lib.VilParams)
     sh = _shape_struct(x_tok, dy_tok, reverse)          # y_* strides describe dy and dx
-    sh.grad_replicas, sh.grad_replica_stride = GRAD_REPLICAS, stride
-    dh_tiles = torch.empty_like(c.h)
-    d_act = torch.empty_like(ws.act)
-    dz = torch.empty_like(ws.z)
-    check(lib.xhved_vil_post_bwd(ptr(dy_tok), ptr(c.h), ptr(ws.act), ptr(ws.z), ctypes.byref(ps), ctypes.byref(sh), ptr(dh_tiles),
-                                 ptr(d_act), ptr(dz), ctypes.byref(gs), stream()), "xhved_vil_post_bwd")
-    gb = mlstm_bwd_tiles(c, dh_tiles, eps)
-    ws_dconv = torch.empty_like(ws.act)
-    ws_dxmv = torch.empty_like(ws.act)
-    check(lib.xhved_vil_pre_bwd(ptr(x_tok), ptr(dy_tok), ptr(ws.xm), ptr(c.q), ptr(c.k), ptr(c.v), ptr(gb.dq), ptr(gb.dk), ptr(gb.dv),
-                                ptr(gb.dig), ptr(gb.dfg), ptr(d_act), ptr(dz), ctypes.byref(ps), ctypes.byref(sh), ptr(dx), ctypes.byref(gs), ptr(ws_dconv), ptr(ws_dxmv),
-                                stream()), "xhved_vil_pre_bwd")
-    out = torch.empty(P, device=dev, dtype=torch.float32)
-    check(lib.xhved_reduce_replicas(ptr(flat), GRAD_REPLICAS, stride, P, ptr(out), stream()), "xhved_reduce_replicas")
+    # parameter gradients are accumulated with global atomics into GRAD_REPLICAS zero-filled copies (CTA i -> copy i % R) to
+    # spread the traffic over L2 slices; the call sums the copies at the end
+    sh.grad_replicas, sh.grad_replica_stride = GRAD_REPLICAS, ws.stride
+    check(lib.xhved_vil_block_bwd(ptr(x_tok), ptr(dy_tok), ctypes.byref(ps), ctypes.byref(sh), eps, ptr(ws.blob), ptr(scratch), ptr(dx),
+                                  ptr(out), stream()), "xhved_vil_block_bwd")
     grads, off = [], 0
     for p in params:
         grads.append(out[off:off + p.numel()].view(p.shape))
