@@ -553,12 +553,22 @@ def run_gpu(args):
             cell[f"DH{cfg[3]}"] = {"shape_B_NH_S_DH": list(cfg), "chunk_out_ms": ko["ms"], "chunk_out_useful_tflops": ko["useful_tflops"],
                                    "chunk_out_executed_tflops": ko["executed_tflops"],
                                    "chunk_out_executed_frac_of_burst_peak": ko["executed_frac_of_bf16_burst_peak"],
-                                   "fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"]}
+                                   "fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"],
+                                   "chunk_out_flop_per_byte": ko["flop_per_byte"], "ridge_flop_per_byte": r["ridge_flop_per_byte"],
+                                   "chunk_out_hbm_frac_on_required_bytes": ko["hbm_frac_on_required_bytes"],
+                                   "reference_form_equiv_tflops_fwd": r["reference_form_equiv_tflops_fwd"],
+                                   "reference_form_equiv_frac_of_bf16_burst_peak_fwd": r["reference_form_equiv_frac_of_bf16_burst_peak_fwd"],
+                                   "reference_form_equiv_frac_of_bf16_burst_peak_fwd_bwd": r.get("reference_form_equiv_frac_of_bf16_burst_peak_fwd_bwd")}
             kg = r["kernels"].get("mlstm_chunk_grad")
             if kg:
                 cell[f"DH{cfg[3]}"].update({"chunk_grad_ms": kg["ms"], "chunk_grad_useful_tflops": kg["useful_tflops"],
                                             "chunk_grad_executed_tflops": kg["executed_tflops"],
-                                            "chunk_grad_executed_frac_of_burst_peak": kg["executed_frac_of_bf16_burst_peak"]})
+                                            "chunk_grad_executed_frac_of_burst_peak": kg["executed_frac_of_bf16_burst_peak"],
+                                            "chunk_grad_hbm_frac_on_required_bytes": kg["hbm_frac_on_required_bytes"]})
+        cell["note"] = ("useful = causal-half FLOP of the chunkwise algorithm, executed = full 128x128 tiles on the tensor pipe; the chunkwise "
+                        "form (L = 128) has 20-90 executed FLOP per byte it must move, below the ridge of the measured peaks, so HBM is the "
+                        "binding roof at every head dim (hbm_frac_on_required_bytes); reference_form_equiv = the FLOP the reference's O(S^2) "
+                        "parallel form needs for the same problem / our time")
     eager_ref = gpu_eager_reference(device) if world == 1 and not args.no_eager_ref else None
     torch.cuda.empty_cache()
     cpu = cpu_reference_arm(steps=args.cpu_steps, warmup=1) if world == 1 and not args.no_cpu else None

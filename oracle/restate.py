@@ -371,8 +371,8 @@ def mlstm_forward_backward_bf16_operands(q, k, v, ig, fg, dh, eps: float = 1e-6,
     tensor cores rounded to bf16 (q, k, v, P = S o D', h, dh/N, db, dS) and everything else exact.
     Used by the tests to separate kernel bugs (kernel != this) from the unavoidable cost of bf16
     operands in ill-conditioned regimes (this != fp64 reference).
-    den_from_rounded_p: the warp-specialised forward (head dims >= 64) takes the normaliser input from the ones column of
-    the P [V|1] product, i.e. it sums the bf16-ROUNDED P -- consistent with the numerator -- instead of the fp32 values."""
+    den_from_rounded_p: the warp-specialised forward takes the normaliser input from the ones column of the P [V|1]
+    product, i.e. it sums the bf16-ROUNDED P -- consistent with the numerator -- instead of the fp32 values."""
     B, NH, S, DH = q.shape
     scale = 1.0 / math.sqrt(DH)
     q, k, v, dh = _bf16(q), _bf16(k), _bf16(v), _bf16(dh)

@@ -94,9 +94,7 @@ def test_cell_backward_matches_reference_autograd_golden(name):
     leaves = [c[n].float().cuda().requires_grad_() for n in ("q", "k", "v", "ig", "fg")]
     h = ops.parallel_stabilized_simple(*leaves)
     grads = torch.autograd.grad(h, leaves, c["dh"].float().cuda())
-    # head dims >= 64 run the warp-specialised forward, whose normaliser sums the bf16-rounded P (ones column of P [V|1])
-    _, emu = restate.mlstm_forward_backward_bf16_operands(*[c[n].double() for n in ("q", "k", "v", "ig", "fg", "dh")],
-                                                           den_from_rounded_p=c["q"].shape[-1] > 32)
+    _, emu = restate.mlstm_forward_backward_bf16_operands(*[c[n].double() for n in ("q", "k", "v", "ig", "fg", "dh")])
     for g, e, n in zip(grads, emu, ("dq", "dk", "dv", "dig", "dfg")):
         err, err_emu = rel_l2(g, c[n]), rel_l2(g, e)
         print(name, n, "vs fp64 reference", err, "vs bf16-operand emulation", err_emu, "emulation vs reference", rel_l2(e, c[n]))

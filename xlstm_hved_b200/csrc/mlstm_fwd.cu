@@ -413,15 +413,15 @@ int launch_chunk_out_ws(int dhp, const void* q, const void* k, const void* v, co
                         const float* m_prev, int BH, int nc, float scale, float eps, void* h, float* m, float* den,
                         cudaStream_t st);
 
-// Which chunk_out kernel runs: the persistent warp-specialised one with P kept in tensor memory (mlstm_fwd_ws.cu) where it
-// is the faster of the two on B200 (measured, profiles/r02_cell_scaling.jsonl: dhp >= 64), the one-tile-per-CTA kernel
-// above for the narrow heads.  XHVED_CELL_WS=0 / 1 forces one of them for A/B measurements.  Read once.
-bool cell_ws_enabled(int dhp) {
-  static const int mode = [] {
+// Which chunk_out kernel runs: the persistent warp-specialised one with P kept in tensor memory (mlstm_fwd_ws.cu) -- the
+// faster of the two at every head dim on B200 (profiles/r02_cell_scaling.jsonl).  XHVED_CELL_WS=0 selects the
+// one-tile-per-CTA kernel above for A/B measurements.  Read once.
+bool cell_ws_enabled(int) {
+  static const int on = [] {
     const char* e = getenv("XHVED_CELL_WS");
-    return !e ? -1 : (e[0] == '0' ? 0 : 1);
+    return (e && e[0] == '0') ? 0 : 1;
   }();
-  return mode < 0 ? dhp >= 64 : mode != 0;
+  return on != 0;
 }
 
 template <int DHP>

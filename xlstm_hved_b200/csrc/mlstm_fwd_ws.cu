@@ -3,15 +3,18 @@
 // Same mathematics as mlstm_chunk_out_kernel (mlstm_fwd.cu; reference: vision_lstm.py:99-128 in the chunkwise form of
 // SURVEY.md 8a-note), different machine mapping:
 //
-//   * one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...; NSLOT tiles are in flight at any time, each with its own
-//     shared-memory stage (Q, K, [V|1], state hi/lo) and its own TMEM columns (S 128 + O dhp+16);
+//   * one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...; NSLOT tiles are in flight in tensor memory at any time (S 128
+//     + O dhp+16 columns each), and the producer runs NSTAGE >= NSLOT shared-memory stages (Q, K, [V|1], state hi/lo) ahead,
+//     so that a tile's operands have landed long before its TMEM slot frees up;
 //   * warp roles: NSLOT consumer warpgroups (128 threads = the 128 rows / TMEM lanes of a tile), one producer warp
 //     (cp.async.bulk into the stage ring, full/empty mbarriers), one MMA warp (a single thread issues every tcgen05.mma);
 //   * P = S o D' never touches shared memory: the consumer converts its row in registers and stores bf16 P back into the
 //     S columns with tcgen05.st; the second product O += P [V|1] takes its A operand from TENSOR MEMORY;
 //   * the inter-chunk part w_t * (q_t [C|n]) is folded into the same accumulator: Q [C|n] is issued together with S, the
-//     consumer scales its row by w_t in TMEM (tcgen05.ld / st) and P [V|1] accumulates on top -- the ones column of
-//     [V|1] makes column dhp of O the normaliser input den_t = sum_s P_ts + w_t q_t.n directly;
+//     consumer scales its row by w_t in TMEM (tcgen05.ld / st) and P [V|1] accumulates on top.  The normaliser input
+//     den_t = sum_s P_ts + w_t q_t.n is taken from the fp32 weights BEFORE they are rounded to bf16 (plus column dhp of the
+//     scaled inter-chunk product): summing the rounded P instead costs up to 4x in gradient accuracy where |den| sits near
+//     its floor (tests/test_gpu_cell.py, oracle emulation);
 //   * decay weights without one ex2 per (t,s): left of the diagonal block D'_ts = exp2(u_t + vmax_j) * exp2(v_s - vmax_j)
 //     with vmax_j the maximum over the 32-column block j (second factor once per column, first once per row and block;
 //     u_t + vmax_j <= 0 there because m_t is the row maximum, so nothing overflows and an underflowing second factor
@@ -27,7 +30,8 @@ namespace xhved {
 template <int DHP>
 struct FwdWs {
   static constexpr int NE = ext_cols(DHP);
-  static constexpr int NSLOT = DHP <= 16 ? 3 : (DHP <= 64 ? 2 : 1);
+  static constexpr int NSLOT = DHP <= 16 ? 3 : (DHP <= 64 ? 2 : 1);    // tiles in flight in tensor memory (one consumer warpgroup each)
+  static constexpr int NSTAGE = DHP <= 16 ? 6 : (DHP <= 32 ? 4 : (DHP <= 64 ? 2 : 1));   // operand stages the producer runs ahead by
   static constexpr uint32_t TILE = kL * DHP * 2;
   static constexpr uint32_t VEXT = kL * NE * 2;
   static constexpr uint32_t ST1 = DHP * NE * 2;            // one state tile (hi or lo)
@@ -37,7 +41,7 @@ struct FwdWs {
   static constexpr int NTHREADS = (4 * NSLOT + 2) * 32;
   // per-slot fp32 arrays behind the stages: vcol[128], ev[128], vmax[4], red_sum[4], red_max[4]
   static constexpr uint32_t AUX = (128 + 128 + 4 + 4 + 4) * 4;
-  static constexpr uint32_t SMEM_USED = NSLOT * (STAGE + AUX);
+  static constexpr uint32_t SMEM_USED = NSTAGE * STAGE + NSLOT * AUX;
   static constexpr uint32_t SMEM = SMEM_USED > 120 * 1024 ? SMEM_USED : 120 * 1024;   // > half an SM: one CTA per SM
 };
 
@@ -48,20 +52,22 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
     const float* __restrict__ m_prev, int nc, int ntiles, float scale, float eps, unsigned char* __restrict__ h_tiles,
     float* __restrict__ m_out, float* __restrict__ den_out) {
   using C = FwdWs<DHP>;
-  constexpr int NE = C::NE, NSLOT = C::NSLOT;
+  constexpr int NE = C::NE, NSLOT = C::NSLOT, NSTAGE = C::NSTAGE;
   constexpr uint32_t TILE = C::TILE, ST1 = C::ST1;
   extern __shared__ __align__(128) unsigned char smem[];
-  float* aux = reinterpret_cast<float*>(smem + NSLOT * C::STAGE);
-  __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_empty[NSLOT], bar_s[NSLOT], bar_p[NSLOT], bar_o[NSLOT], bar_free[NSLOT];
+  float* aux = reinterpret_cast<float*>(smem + NSTAGE * C::STAGE);
+  __shared__ __align__(8) uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_s[NSLOT], bar_p[NSLOT], bar_o[NSLOT], bar_free[NSLOT];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSLOT; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
+    }
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&bar_s[s], 1);
       mbar_init(&bar_p[s], kL);
       mbar_init(&bar_o[s], 1);
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   // constant ext columns [1 | 0] of every stage's V buffer (bulk loads only ever overwrite the first DHP columns)
-  for (int i = threadIdx.x; i < NSLOT * kL; i += blockDim.x) write_ext_ones(smem + (i / kL) * C::STAGE + C::OFF_V, DHP, i % kL);
+  for (int i = threadIdx.x; i < NSTAGE * kL; i += blockDim.x) write_ext_ones(smem + (i / kL) * C::STAGE + C::OFF_V, DHP, i % kL);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
     // ===================================================================== producer
     if (lane == 0) {
       for (int it = 0; it < n_my; ++it) {
-        const int s = it % NSLOT, use = it / NSLOT;
+        const int s = it % NSTAGE, use = it / NSTAGE;
         const int tile = blockIdx.x + it * gridDim.x;
         const bool has_state = (tile % nc) > 0;
         unsigned char* st = smem + s * C::STAGE;
@@ -101,13 +107,13 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
       constexpr int LA = NSLOT - 1;   // S of tile it+LA is issued before P V of tile it
       for (int step = 0; step < n_my + LA; ++step) {
         if (step < n_my) {
-          const int it = step, s = it % NSLOT, use = it / NSLOT;
+          const int it = step, s = it % NSLOT, use = it / NSLOT, sg = it % NSTAGE, use_sg = it / NSTAGE;
           const int tile = blockIdx.x + it * gridDim.x;
           const bool has_state = (tile % nc) > 0;
-          const uint32_t st = smem_u32(smem + s * C::STAGE);
+          const uint32_t st = smem_u32(smem + sg * C::STAGE);
           const uint32_t tS = tmem + s * C::TM_SLOT, tO = tS + 128;
           mbar_wait(&bar_free[s], (use & 1) ^ 1);     // epilogue of the previous tile in this slot has drained TMEM
-          mbar_wait(&bar_full[s], use & 1);
+          mbar_wait(&bar_full[sg], use_sg & 1);
           tc_fence_after();
           // S[t][s'] = sum_d Q[t][d] K[s'][d]
           umma_gemm(tS, st + C::OFF_Q, kL * 16, 128, st + C::OFF_K, kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
@@ -119,17 +125,17 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
           umma_commit(&bar_s[s]);
         }
         if (step >= LA) {
-          const int it = step - LA, s = it % NSLOT, use = it / NSLOT;
+          const int it = step - LA, s = it % NSLOT, use = it / NSLOT, sg = it % NSTAGE;
           const int tile = blockIdx.x + it * gridDim.x;
           const bool has_state = (tile % nc) > 0;
-          const uint32_t st = smem_u32(smem + s * C::STAGE);
+          const uint32_t st = smem_u32(smem + sg * C::STAGE);
           const uint32_t tS = tmem + s * C::TM_SLOT, tO = tS + 128;
           mbar_wait(&bar_p[s], use & 1);
           tc_fence_after();
           // O[t][e'] += sum_s' P[t][s'] [V|1][s'][e']   (A = bf16 P in TMEM, B = MN-major view of the V stage)
           umma_gemm_ts(tO, tS, st + C::OFF_V, 128, kL * 16, umma_idesc(128, NE, false, true), kL, has_state);
           umma_commit(&bar_o[s]);
-          umma_commit(&bar_empty[s]);                 // every MMA reading this stage has completed
+          umma_commit(&bar_empty[sg]);                // every MMA reading this stage has completed
         }
       }
     }
@@ -206,7 +212,8 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
       const uint32_t tS = tmem + wg * C::TM_SLOT + lane_base, tO = tS + 128;
       mbar_wait(&bar_s[wg], use & 1);
       tc_fence_after();
-      // ---- inter-chunk part: O <- w_t * (Q [C|n]) in place ----
+      // ---- inter-chunk part: O <- w_t * (Q [C|n]) in place; column dhp of it is w_t q_t.n, the inter-chunk part of den ----
+      float den = 0.f;
       if (has_state) {
 #pragma unroll
         for (int c0 = 0; c0 < NE; c0 += 16) {
@@ -215,61 +222,65 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
           tmem_wait_ld16(o);
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * wgt);
+          if (c0 == DHP) den = __uint_as_float(o[0]);
           tmem_st16(tO + c0, o);
         }
       }
       // ---- P = S o D' (causal), bf16, back into the S columns (block j -> columns [16j, 16j+16)) ----
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      {
         uint32_t pk[16];
-        if (j <= w) {
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < w; ++j) {          // blocks left of the diagonal: separable weights
           uint32_t sv[32];
           tmem_ld32_nowait(tS + 32 * j, sv);
+          const float eu = fast_exp2(urow + vmax[j]);
           tmem_wait_ld32(sv);
-          if (j < w) {
-            const float eu = fast_exp2(urow + vmax[j]);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 e4 = *reinterpret_cast<const float4*>(ev + 32 * j + i);
-              const float p0 = __uint_as_float(sv[i]) * e4.x * eu, p1 = __uint_as_float(sv[i + 1]) * e4.y * eu;
-              const float p2 = __uint_as_float(sv[i + 2]) * e4.z * eu, p3 = __uint_as_float(sv[i + 3]) * e4.w * eu;
-              pk[i / 2] = pack_bf16x2(p0, p1);
-              pk[i / 2 + 1] = pack_bf16x2(p2, p3);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 v4 = *reinterpret_cast<const float4*>(vcol + 32 * j + i);
-              float p0 = __uint_as_float(sv[i]) * fast_exp2(urow + v4.x), p1 = __uint_as_float(sv[i + 1]) * fast_exp2(urow + v4.y);
-              float p2 = __uint_as_float(sv[i + 2]) * fast_exp2(urow + v4.z), p3 = __uint_as_float(sv[i + 3]) * fast_exp2(urow + v4.w);
-              p0 = (i <= lane) ? p0 : 0.f;
-              p1 = (i + 1 <= lane) ? p1 : 0.f;
-              p2 = (i + 2 <= lane) ? p2 : 0.f;
-              p3 = (i + 3 <= lane) ? p3 : 0.f;
-              pk[i / 2] = pack_bf16x2(p0, p1);
-              pk[i / 2 + 1] = pack_bf16x2(p2, p3);
-            }
+          for (int i = 0; i < 32; i += 4) {
+            const float4 e4 = *reinterpret_cast<const float4*>(ev + 32 * j + i);
+            const float p0 = __uint_as_float(sv[i]) * (e4.x * eu), p1 = __uint_as_float(sv[i + 1]) * (e4.y * eu);
+            const float p2 = __uint_as_float(sv[i + 2]) * (e4.z * eu), p3 = __uint_as_float(sv[i + 3]) * (e4.w * eu);
+            rs0 += p0 + p1;
+            rs1 += p2 + p3;
+            pk[i / 2] = pack_bf16x2(p0, p1);
+            pk[i / 2 + 1] = pack_bf16x2(p2, p3);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          tmem_st16(tS + 16 * j, pk);
         }
-        tmem_st16(tS + 16 * j, pk);
+        {                                       // the diagonal block: direct weights, causal mask
+          uint32_t sv[32];
+          tmem_ld32_nowait(tS + 32 * w, sv);
+          tmem_wait_ld32(sv);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(vcol + 32 * w + i);
+            float p0 = __uint_as_float(sv[i]) * fast_exp2(urow + v4.x), p1 = __uint_as_float(sv[i + 1]) * fast_exp2(urow + v4.y);
+            float p2 = __uint_as_float(sv[i + 2]) * fast_exp2(urow + v4.z), p3 = __uint_as_float(sv[i + 3]) * fast_exp2(urow + v4.w);
+            p0 = (i <= lane) ? p0 : 0.f;
+            p1 = (i + 1 <= lane) ? p1 : 0.f;
+            p2 = (i + 2 <= lane) ? p2 : 0.f;
+            p3 = (i + 3 <= lane) ? p3 : 0.f;
+            rs0 += p0 + p1;
+            rs1 += p2 + p3;
+            pk[i / 2] = pack_bf16x2(p0, p1);
+            pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st16(tS + 16 * w, pk);
+        }
+        den += rs0 + rs1;                       // normaliser input: fp32 sum of the UNROUNDED weights (vision_lstm.py:123)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+#pragma unroll 1
+        for (int j = w + 1; j < 4; ++j) tmem_st16(tS + 16 * j, pk);      // behind the diagonal: zero
       }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bar_p[wg]);
 
-      // ---- epilogue: h = O / (max(|den|, exp(-m)) + eps), den = column dhp of O   (vision_lstm.py:123-128) ----
+      // ---- epilogue: h = O / (max(|den|, exp(-m)) + eps)   (vision_lstm.py:123-128) ----
       mbar_wait(&bar_o[wg], use & 1);
       tc_fence_after();
-      float den;
-      {
-        uint32_t d16[16];
-        tmem_ld16_nowait(tO + DHP, d16);
-        tmem_wait_ld16(d16);
-        den = __uint_as_float(d16[0]);
-      }
       const float rn = 1.f / (fmaxf(fabsf(den), __expf(-m)) + eps);
       unsigned char* hdst = h_tiles + static_cast<size_t>(tile) * TILE;
 #pragma unroll
