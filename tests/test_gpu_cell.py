@@ -164,3 +164,31 @@ def test_cell_backward_long_sequence_32768_vs_oracle():
     # the sum over the sequence of d f~ is where a drifting telescoping sum would show (31 % with plain bf16 states at S=1024)
     tot, tot_ref = got[4].double().sum(2).cpu(), ref[4].sum(2)
     assert ((tot - tot_ref).abs() / tot_ref.abs().clamp_min(1e-12)).max() < 5e-2
+
+
+@pytest.mark.parametrize("B,NH,S,DH", [(1, 2, 384, 128), (1, 1, 700, 128), (1, 2, 300, 96)])
+def test_cell_backward_widest_head_vs_oracle(B, NH, S, DH):
+    """dhp = 128 (f_maps = 32: dim 256, DH = 128): the backward runs as three part-kernels
+    (mlstm_bwd_wide.cu).  Bottleneck statistics against the fp64 oracle, unit-variance inputs against the bf16-operand
+    emulation of the kernels."""
+    from xlstm_hved_b200 import ops
+    g = torch.Generator().manual_seed(S + DH)
+    q, k, v = [0.06 * torch.randn(B, NH, S, DH, generator=g), 0.06 * torch.randn(B, NH, S, DH, generator=g),
+               0.12 * torch.randn(B, NH, S, DH, generator=g)]
+    ig, fg = -0.67 + 0.48 * torch.randn(B, NH, S, 1, generator=g), 0.41 + 1.03 * torch.randn(B, NH, S, 1, generator=g)
+    dh = torch.randn(B, NH, S, DH, generator=g)
+    leaves = [t.double().requires_grad_() for t in (q, k, v, ig, fg)]
+    ref = torch.autograd.grad(restate.mlstm_chunkwise(*leaves, chunk=128), leaves, dh.double())
+    cl = [t.cuda().requires_grad_() for t in (q, k, v, ig, fg)]
+    got = torch.autograd.grad(ops.parallel_stabilized_simple(*cl), cl, dh.cuda())
+    for a, b, n in zip(got, ref, ("dq", "dk", "dv", "dig", "dfg")):
+        print((B, NH, S, DH), n, rel_l2(a, b), rel_linf(a, b))
+        assert rel_l2(a, b) < 2e-2, n
+    q, k, v = [torch.randn(B, NH, S, DH, generator=g) for _ in range(3)]
+    ig, fg = torch.randn(B, NH, S, 1, generator=g), 2.0 + torch.randn(B, NH, S, 1, generator=g)
+    cl = [t.cuda().requires_grad_() for t in (q, k, v, ig, fg)]
+    got = torch.autograd.grad(ops.parallel_stabilized_simple(*cl), cl, dh.cuda())
+    _, emu = restate.mlstm_forward_backward_bf16_operands(*[t.double() for t in (q, k, v, ig, fg, dh)])
+    for a, b, n in zip(got, emu, ("dq", "dk", "dv", "dig", "dfg")):
+        print("unit variance", n, rel_l2(a, b))
+        assert rel_l2(a, b) < 3e-2, n

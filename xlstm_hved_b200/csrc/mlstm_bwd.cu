@@ -29,6 +29,11 @@ int launch_chunk_grad_ws(int dhp, const void* q, const void* k, const void* v, c
                          const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
                          float* dc, float* dc_tot, cudaStream_t st);
 
+int launch_chunk_grad_wide(const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig, const float* fg,
+                           const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
+                           const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
+                           float* dc, float* dc_tot, cudaStream_t st);
+
 // Which chunk_grad kernel runs: the persistent kernel with balanced roles and P^T in tensor memory (mlstm_bwd_ws.cu) where it
 // is the faster of the two on B200 (measured, profiles/r02_cell_scaling.jsonl: dhp <= 32, two CTAs per SM), the
 // one-tile-per-CTA kernel below for dhp = 64.  XHVED_GRAD_WS=0 / 1 forces one of them for A/B measurements.  Read once.
@@ -449,7 +454,12 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
                                                                    fg, m, den, scale, eps, ws_dstate, ws_g, ws_lam);
   }
   if (int rc = launch_state_scan(DHP, ws_dstate, ws_g, ws_lam, BH, nc, 1, rstates, mu_next, st)) return rc;
-  if (grad_ws_enabled(DHP)) {
+  if constexpr (DHP == 128) {
+    // the widest head does not fit one fused kernel (346 KB of shared memory, 1024 TMEM columns): three part-kernels
+    if (int rc = launch_chunk_grad_wide(q, k, v, h, dh_t, ig, fg, m, den, states, m_prev, rstates, mu_next, BH, nc, scale, eps, dq, dk, dv,
+                                        dig, ws_dc, ws_lam, st))
+      return rc;
+  } else if (grad_ws_enabled(DHP)) {
     if (int rc = launch_chunk_grad_ws(DHP, q, k, v, h, dh_t, ig, fg, m, den, states, m_prev, rstates, mu_next, BH, nc, scale, eps, dq, dk,
                                       dv, dig, ws_dc, ws_lam, st))
       return rc;
@@ -485,7 +495,8 @@ extern "C" int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const v
     case 16: return launch_bwd<16>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
     case 32: return launch_bwd<32>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
     case 64: return launch_bwd<64>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
-    default: return XHVED_ERR_UNSUPPORTED_DH;   // dhp = 128 backward: not built yet (shared-memory budget)
+    case 128: return launch_bwd<128>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
+    default: return XHVED_ERR_UNSUPPORTED_DH;
   }
 }
 
