@@ -323,3 +323,66 @@ def test_vil_block_reentrant_on_two_streams_from_two_threads():
         assert torch.equal(seq[i][0], par[i][0]) and torch.equal(seq[i][1], par[i][1])
         for a, b in zip(seq[i][2], par[i][2]):           # parameter gradients: atomics, summation order is not fixed
             assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dim,S", [(128, 300), (256, 200)])
+def test_wide_block_cell_on_kernels_vs_oracle(dim, S):
+    """blocks of f_maps 16 / 32 (dim 128 / 256, head dim 64 / 128).  K2 / K3 are not fused at these
+    widths: the cell (forward AND backward, dhp = 64 / 128) runs on the tcgen05 kernels, the per-token glue as torch ops.
+    Forward and all gradients against the fp64 oracle of the whole block."""
+    import xlstm_hved_b200 as xh
+    from xlstm_hved_b200 import ops
+    torch.manual_seed(dim)
+    blk = xh.ViLBlock(dim, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT).cuda()
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if n.endswith(("igate.weight", "fgate.weight")):
+                p.copy_(0.1 * torch.randn_like(p))
+            elif n.endswith(("igate.bias", "fgate.bias")):
+                p.copy_(torch.randn_like(p))
+    sd = {k: v.detach().cpu().clone() for k, v in blk.state_dict().items()}
+    x = torch.randn(2, S, dim)
+    gy = torch.randn(2, S, dim)
+    xc = x.cuda().requires_grad_()
+    y = blk(xc)
+    keys = list(ops.VIL_PARAM_KEYS)
+    named = dict(blk.named_parameters())
+    grads = torch.autograd.grad(y, [xc] + [named[k] for k in keys], gy.cuda())
+    p64 = {k: v.double().requires_grad_() for k, v in sd.items()}
+    x64 = x.double().requires_grad_()
+    ref = restate.vil_block(x64, p64, reverse=True, cell=lambda *a: restate.mlstm_chunkwise(*a, chunk=128))
+    ref_grads = torch.autograd.grad(ref, [x64] + [p64[k] for k in keys], gy.double())
+    br, br_ref = y.detach().cpu().double() - x.double(), ref.detach() - x.double()
+    print(dim, "branch rel_l2", rel_l2(br, br_ref))
+    assert rel_l2(br, br_ref) < TOL_L2
+    assert rel_l2(grads[0].cpu().double() - gy.double(), ref_grads[0] - gy.double()) < 3e-2
+    for g, rg, key in zip(grads[1:], ref_grads[1:], keys):
+        print(dim, key, rel_l2(g, rg))
+        assert rel_l2(g, rg) < 3e-2, key
+
+
+def test_patched_reference_block_wider_than_the_fused_kernels():
+    """A reference ViLBlock of dim 128 after patch_model: its own glue, the cell on the kernels (vision_lstm's
+    parallel_stabilized_simple is rebound), same result as the stock O(S^2) path within the bf16-operand budget."""
+    from oracle import ref_loader
+    if ref_loader.find_reference() is None:
+        pytest.skip("no reference tree on this machine (baseline/_ref absent)")
+    import xlstm_hved_b200 as xh
+    ns = ref_loader.load_reference()
+    vl = ns.vision_lstm
+    torch.manual_seed(4)
+    blk = vl.ViLBlock(dim=128, direction=vl.SequenceTraversal.ROWWISE_FROM_TOP_LEFT).cuda()
+    x = torch.randn(1, 260, 128, device="cuda", requires_grad=True)
+    gy = torch.randn(1, 260, 128, device="cuda")
+    y0 = blk(x)
+    (dx0,) = torch.autograd.grad(y0, x, gy)
+    model = torch.nn.Sequential(blk)
+    counts = xh.patch_model(model)
+    try:
+        assert counts["ViLBlock"] == 1 and any(r.endswith("vision_lstm.parallel_stabilized_simple") for r in counts["rebound"])
+        y1 = blk(x)
+        (dx1,) = torch.autograd.grad(y1, x, gy)
+    finally:
+        xh.unpatch_model(model)
+    assert vl.parallel_stabilized_simple.__module__.endswith("vision_lstm")
+    assert rel_l2(y1 - x, y0 - x) < TOL_L2 and rel_l2(dx1 - gy, dx0 - gy) < 3e-2

@@ -1,5 +1,6 @@
-"""ViLBlock pair (TOP_LEFT + BOT_RIGHT) forward+backward at the model widths the kernels cover (dim 16 / 32 / 64 = f_maps 2 / 4 / 8),
-per-kernel times from the library's CUDA-event profiler.  Prints one JSON line per width."""
+"""ViLBlock pair (TOP_LEFT + BOT_RIGHT) forward+backward at the model widths dim 16 / 32 / 64 (f_maps 2 / 4 / 8: fused K2 / K3
+kernels) and dim 128 / 256 (f_maps 16 / 32: the cell on the tcgen05 kernels at head dim 64 / 128, the per-token glue as torch
+ops), per-kernel times from the library's CUDA-event profiler.  Prints one JSON line per width."""
 import ctypes, json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -40,10 +41,13 @@ def run(dim, B=32, S=4096, iters=10):
     lib.xhved_profile_read(ms, cnt, nk)
     lib.xhved_profile_enable(0)
     kern = {names[i]: round(ms[i] / iters, 4) for i in range(nk) if cnt[i]}
-    return {"dim": dim, "B": B, "S": S, "eager_ms_per_pair_fwd_bwd": round(e0.elapsed_time(e1) / iters, 4),
+    return {"dim": dim, "B": B, "S": S, "path": "fused K2 / cell / K3" if dim in xh.modules.FUSED_DIMS else "cell kernels + torch glue",
+            "eager_ms_per_pair_fwd_bwd": round(e0.elapsed_time(e1) / iters, 4),
             "kernel_ms": dict(sorted(kern.items(), key=lambda kv: -kv[1])), "kernel_ms_total": round(sum(kern.values()), 4)}
 
 
 if __name__ == "__main__":
     for dim in (16, 32, 64):
         print(json.dumps(run(dim)))
+    for dim in (128, 256):                      # roofline shapes B = 16, S = 4096
+        print(json.dumps(run(dim, B=16)))

@@ -214,14 +214,29 @@ def vil_block_params(block):
             cell.outnorm.weight, lay.learnable_skip, lay.proj_down.weight]
 
 
+FUSED_DIMS = (16, 32, 64)        # model dims the fused K2 / K3 kernels are built for (f_maps 2 / 4 / 8: vil_pre.cu, vil_post.cu)
+
+
 def vil_block_forward(block, x: torch.Tensor) -> torch.Tensor:
-    """ViLBlock.forward (vision_lstm.py:499-502): x + layer(norm(x)) for a (B,S,C) token tensor or view."""
+    """ViLBlock.forward (vision_lstm.py:499-502): x + layer(norm(x)) for a (B,S,C) token tensor or view.
+
+    dims 16 / 32 / 64: the fused pre / cell / post kernels.  Wider blocks (f_maps 16 / 32: dim 128 / 256, head dim 64 / 128,
+    SURVEY 8d config 2 (iii)) are not fused yet: their S x S-shaped work -- the mLSTM cell, forward and backward -- runs on
+    the same tcgen05 kernels, the per-token glue around it (norm, projections, 4-tap conv, gate Linear) as device-side torch
+    ops: the mirror modules' own forwards, or, for a patched reference block, the reference's own ``forward`` with
+    ``parallel_stabilized_simple`` rebound to the kernels (patch.py)."""
+    _require_device(x)
     dp = getattr(block.drop_path, "drop_prob", 0.0)
     if dp != 0.0 and block.training:
         raise NotImplementedError("stochastic depth (drop_path > 0 in training) is never used by XLSTM-HVED")
     if block.layer.qkv_block_size != 4 or getattr(block.norm, "bias", None) is not None:
         raise NotImplementedError("fused ViL block: qkv_block_size must be 4 and the norm bias-free (reference defaults)")
-    return ops.vil_block(x, vil_block_params(block), reverse=_is_reverse(block.direction))
+    if x.shape[-1] in FUSED_DIMS:
+        return ops.vil_block(x, vil_block_params(block), reverse=_is_reverse(block.direction))
+    stock = getattr(type(block), "_xhved_base", None)
+    if stock is not None:                               # a patched reference block: its own glue, our cell
+        return stock.forward(block, x)
+    return x + block.layer(block.norm(x))
 
 
 class ViLBlock(nn.Module):

@@ -94,8 +94,12 @@ def patch_model(model, patch_globals: bool = True):
     if patch_globals:
         before = len(_GLOBALS)
         ra, ls, bb = sys.modules.get("RA_HVED"), sys.modules.get("loss"), sys.modules.get("buildingblocks")
+        vl = next((m for n, m in sys.modules.items() if n.endswith("nets.vision_lstm") and hasattr(m, "parallel_stabilized_simple")), None)
         for owner, attr, repl in ((ra, "reparametrize", modules.reparametrize), (ra, "clip", modules.clip),
-                                  (ls, "compute_KLD", modules.compute_KLD), (bb, "ZeroLayerF", modules.ZeroLayerF)):
+                                  (ls, "compute_KLD", modules.compute_KLD), (bb, "ZeroLayerF", modules.ZeroLayerF),
+                                  # the cell itself (vision_lstm.py:48-130, called at 327): reached by blocks wider than the
+                                  # fused kernels cover and by any stand-alone MatrixLSTMCell of the reference
+                                  (vl, "parallel_stabilized_simple", modules.parallel_stabilized_simple)):
             orig = getattr(owner, attr, None) if owner is not None else None
             if orig is None or orig is repl:
                 continue
