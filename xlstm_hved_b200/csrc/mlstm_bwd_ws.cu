@@ -147,22 +147,27 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
 
   if (warp == 8) {
     // ===================================================================== control: bulk loads + every tcgen05.mma
-    if (lane == 0) {
+    // The WHOLE warp runs this loop in uniform control flow with warp-uniform operands (kernel parameters, blockIdx, loop
+    // counters, the tensor-memory base through a shuffle); one lane is elected inside every issuing instruction (umma.cuh,
+    // "elect" forms), so the tcgen05 / bulk-copy operands stay in uniform registers instead of going through a per-lane
+    // waterfall of R2UR moves.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    {
       auto issue_load = [&](int it) {
         const int s = it % NSTAGE;
         const int tile = blockIdx.x + it * gridDim.x;
         const int c = tile % nc;
         const bool has_prev = c > 0, has_next = c < nc - 1;
         unsigned char* st = smem + s * C::STAGE;
-        mbar_expect_tx(&bar_full[s], 5 * TILE + (has_prev ? 2 * ST1 : 0) + (has_next ? 2 * ST1 : 0));
+        mbar_expect_tx_e(&bar_full[s], 5 * TILE + (has_prev ? 2 * ST1 : 0) + (has_next ? 2 * ST1 : 0));
         const size_t to = static_cast<size_t>(tile) * TILE;
-        bulk_g2s(st + C::OFF_Q, q_tiles + to, TILE, &bar_full[s]);
-        bulk_g2s(st + C::OFF_K, k_tiles + to, TILE, &bar_full[s]);
-        bulk_g2s(st + C::OFF_G, dh_tiles + to, TILE, &bar_full[s]);
-        bulk_g2s(st + C::OFF_H, h_tiles + to, TILE, &bar_full[s]);
-        bulk_g2s(st + C::OFF_V, v_tiles + to, TILE, &bar_full[s]);
-        if (has_prev) bulk_g2s(st + C::OFF_C, states + static_cast<size_t>(tile) * (2 * ST1), 2 * ST1, &bar_full[s]);
-        if (has_next) bulk_g2s(st + C::OFF_R, rstates + static_cast<size_t>(tile) * (2 * ST1), 2 * ST1, &bar_full[s]);
+        bulk_g2s_e(st + C::OFF_Q, q_tiles + to, TILE, &bar_full[s]);
+        bulk_g2s_e(st + C::OFF_K, k_tiles + to, TILE, &bar_full[s]);
+        bulk_g2s_e(st + C::OFF_G, dh_tiles + to, TILE, &bar_full[s]);
+        bulk_g2s_e(st + C::OFF_H, h_tiles + to, TILE, &bar_full[s]);
+        bulk_g2s_e(st + C::OFF_V, v_tiles + to, TILE, &bar_full[s]);
+        if (has_prev) bulk_g2s_e(st + C::OFF_C, states + static_cast<size_t>(tile) * (2 * ST1), 2 * ST1, &bar_full[s]);
+        if (has_next) bulk_g2s_e(st + C::OFF_R, rstates + static_cast<size_t>(tile) * (2 * ST1), 2 * ST1, &bar_full[s]);
       };
       if (PIPE) issue_load(0);
       for (int it = 0; it < n_my; ++it) {
@@ -178,8 +183,8 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
         if (!PIPE) issue_load(it);
         mbar_wait(&bar_full[s], (it / NSTAGE) & 1);
         tc_fence_after();
-        umma_gemm(tmem + C::T_ST, aK, kL * 16, 128, aQ, kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
-        umma_commit(&bar_s);
+        umma_gemm_e(tmem_u + C::T_ST, aK, kL * 16, 128, aQ, kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
+        umma_commit_e(&bar_s);
         // ---- dP[t][s] = sum_e' G[t][e'] Vext[s][e'] -> cols [128,256): needs G and the previous tile's outputs read
         if (PIPE) {
           if (it > 0) mbar_wait(&bar_tfree, (it - 1) & 1);
@@ -187,49 +192,49 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
         }
         mbar_wait(&bar_prep, it & 1);
         tc_fence_after();
-        umma_gemm(tmem + C::T_DP, aG, kL * 16, 128, aV, kL * 16, 128, umma_idesc(128, kL, false, false), NE, false);
+        umma_gemm_e(tmem_u + C::T_DP, aG, kL * 16, 128, aV, kL * 16, 128, umma_idesc(128, kL, false, false), NE, false);
         if (DHP > 32) {
           // wide heads: the inter-chunk products have their own columns and do not wait for the conversions
           if (has_prev) {
-            umma_gemm(tmem + C::T_DQX, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
-            umma_gemm(tmem + C::T_DQX, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+            umma_gemm_e(tmem_u + C::T_DQX, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+            umma_gemm_e(tmem_u + C::T_DQX, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
           }
           if (has_next) {
-            umma_gemm(tmem + C::T_DKX, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
-            umma_gemm(tmem + C::T_DKX, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
-            umma_gemm(tmem + C::T_DVX, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
-            umma_gemm(tmem + C::T_DVX, aK, kL * 16, 128, aR + ST1, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, true);
+            umma_gemm_e(tmem_u + C::T_DKX, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+            umma_gemm_e(tmem_u + C::T_DKX, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+            umma_gemm_e(tmem_u + C::T_DVX, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
+            umma_gemm_e(tmem_u + C::T_DVX, aK, kL * 16, 128, aR + ST1, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, true);
           }
         }
-        umma_commit(&bar_p);
+        umma_commit_e(&bar_p);
         // ---- dS written: dQ_intra[t][d] = sum_s dS[t][s] K[s][d],  dK_intra[s][d] = sum_t dS[t][s] Q[t][d] (MN-major A view)
         mbar_wait(&bar_c0, it & 1);
         tc_fence_after();
-        umma_gemm(tmem + C::T_DQI, aS, kL * 16, 128, aK, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
-        umma_gemm(tmem + C::T_DKI, aS, 128, kL * 16, aQ, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
+        umma_gemm_e(tmem_u + C::T_DQI, aS, kL * 16, 128, aK, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
+        umma_gemm_e(tmem_u + C::T_DKI, aS, 128, kL * 16, aQ, 128, kL * 16, umma_idesc(128, DHP, true, true), kL, false);
         if (DHP <= 32) {
           if (has_prev) {
             // dQ_inter[t][d] = sum_e' G[t][e'] Cn[d][e']
-            umma_gemm(tmem + C::T_DQX, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
-            umma_gemm(tmem + C::T_DQX, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+            umma_gemm_e(tmem_u + C::T_DQX, aG, kL * 16, 128, aC, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+            umma_gemm_e(tmem_u + C::T_DQX, aG, kL * 16, 128, aC + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
           }
           if (has_next) {
             // dK_inter[s][d] = sum_e' Vext[s][e'] R[d][e']
-            umma_gemm(tmem + C::T_DKX, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
-            umma_gemm(tmem + C::T_DKX, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
+            umma_gemm_e(tmem_u + C::T_DKX, aV, kL * 16, 128, aR, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, false);
+            umma_gemm_e(tmem_u + C::T_DKX, aV, kL * 16, 128, aR + ST1, DHP * 16, 128, umma_idesc(128, DHP, false, false), NE, true);
           }
         }
-        umma_commit(&bar_ma);
+        umma_commit_e(&bar_ma);
         // ---- P^T written: dV_intra[s][e] = sum_t P^T[s][t] G[t][e]  (A = bf16 P^T in tensor memory)
         mbar_wait(&bar_c1, it & 1);
         tc_fence_after();
-        umma_gemm_ts(tmem + C::T_DVI, tmem + C::T_ST, aG, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
+        umma_gemm_ts_e(tmem_u + C::T_DVI, tmem_u + C::T_ST, aG, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
         if (DHP <= 32 && has_next) {
           // dV_inter[s][e] = sum_d K[s][d] R[d][e]
-          umma_gemm(tmem + C::T_DVX, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
-          umma_gemm(tmem + C::T_DVX, aK, kL * 16, 128, aR + ST1, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, true);
+          umma_gemm_e(tmem_u + C::T_DVX, aK, kL * 16, 128, aR, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, false);
+          umma_gemm_e(tmem_u + C::T_DVX, aK, kL * 16, 128, aR + ST1, 128, DHP * 16, umma_idesc(128, DHP, false, true), DHP, true);
         }
-        umma_commit(&bar_mb);
+        umma_commit_e(&bar_mb);
       }
     }
   } else if (warp < 4) {

@@ -184,6 +184,43 @@ __device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_e(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// whole-warp forms of umma_gemm / umma_gemm_ts (uniform operands, see above)
+__device__ __forceinline__ void umma_gemm_e(uint32_t d_tmem, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_addr,
+                                            uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, int K, bool accumulate_first) {
+  uint64_t ad = umma_desc(a_addr, a_lbo, a_sbo);
+  uint64_t bd = umma_desc(b_addr, b_lbo, b_sbo);
+  const uint64_t a_step = (2u * a_lbo) >> 4, b_step = (2u * b_lbo) >> 4;
+  for (int k = 0; k < K / 16; ++k) {
+    umma_bf16_e(d_tmem, ad, bd, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+    ad += a_step;
+    bd += b_step;
+  }
+}
+__device__ __forceinline__ void umma_gemm_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo,
+                                               uint32_t idesc, int K, bool accumulate_first) {
+  uint64_t bd = umma_desc(b_addr, b_lbo, b_sbo);
+  const uint64_t b_step = (2u * b_lbo) >> 4;
+  for (int k = 0; k < K / 16; ++k) {
+    umma_bf16_ts_e(d_tmem, a_tmem + 8u * k, bd, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+    bd += b_step;
+  }
+}
 __device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
