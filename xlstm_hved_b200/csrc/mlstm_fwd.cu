@@ -356,27 +356,37 @@ __global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_out_kernel(
 }
 
 // ------------------------------------------------------------------ pack / unpack (standalone cell API)
-// fp32 (BH, S, DH) row-major -> bf16 tile-native tiles (BH*nc tiles of 128 x DHP), zero padded.
-__global__ void mlstm_pack_kernel(const float* __restrict__ src, int S, int DH, int DHP, int nc, unsigned char* __restrict__ tiles) {
-  const int tile = blockIdx.x, r = threadIdx.x;
+// fp32 (BH, S, DH) row-major -> bf16 tile-native tiles (BH*nc tiles of 128 x DHP), zero padded.  The 128 x DH block of a tile
+// is contiguous in the source and the tile is contiguous in the destination: both sides are moved with coalesced 16-byte
+// accesses, the layout change happens in shared memory.
+__global__ void __launch_bounds__(256) mlstm_pack_kernel(const float* __restrict__ src, int S, int DH, int DHP, int nc,
+                                                         unsigned char* __restrict__ tiles) {
+  extern __shared__ __align__(16) unsigned char pk_smem[];          // one tile: 128 * DHP * 2 bytes
+  const int tile = blockIdx.x, tid = threadIdx.x;
   const int bh = tile / nc, c = tile % nc;
-  const int t = c * kL + r;
-  unsigned char* dst = tiles + static_cast<size_t>(tile) * (kL * DHP * 2);
-  const float* row = src + (static_cast<size_t>(bh) * S + t) * DH;
-  for (int cg = 0; cg < DHP / 8; ++cg) {
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int d = cg * 8 + j;
-      f[j] = (t < S && d < DH) ? row[d] : 0.f;
+  const int t0 = c * kL, rows = min(kL, S - t0);
+  const uint32_t tile_bytes = kL * DHP * 2;
+  for (uint32_t i = tid; i < tile_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(pk_smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const float* blk = src + (static_cast<size_t>(bh) * S + t0) * DH;
+  const int n = rows * DH;
+  if ((DH & 3) == 0 && (reinterpret_cast<uintptr_t>(blk) & 15) == 0) {
+    for (int i = tid * 4; i < n; i += blockDim.x * 4) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(blk + i));
+      const int r = i / DH, d = i % DH;                              // DH % 4 == 0: the four values share a row
+      unsigned char* dst = pk_smem + tile_off16(kL, r, d / 8) + (d % 8) * 2;
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(f.x, f.y);
+      *reinterpret_cast<uint32_t*>(dst + 4) = pack_bf16x2(f.z, f.w);
     }
-    uint4 u;
-    u.x = pack_bf16x2(f[0], f[1]);
-    u.y = pack_bf16x2(f[2], f[3]);
-    u.z = pack_bf16x2(f[4], f[5]);
-    u.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(dst + tile_off16(kL, r, cg)) = u;
+  } else {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int r = i / DH, d = i % DH;
+      *reinterpret_cast<__nv_bfloat16*>(pk_smem + tile_off16(kL, r, d / 8) + (d % 8) * 2) = __float2bfloat16(__ldg(blk + i));
+    }
   }
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(tiles + static_cast<size_t>(tile) * tile_bytes);
+  for (uint32_t i = tid; i < tile_bytes / 16; i += blockDim.x) out[i] = reinterpret_cast<const uint4*>(pk_smem)[i];
 }
 // gates (BH, S) -> (BH, nc*128); padding rows get i = -1e30 (no weight), f = +1e30 (log sigmoid = 0)
 __global__ void mlstm_pack_gates_kernel(const float* __restrict__ ig, const float* __restrict__ fg, int S, int nc,
@@ -388,21 +398,31 @@ __global__ void mlstm_pack_gates_kernel(const float* __restrict__ ig, const floa
   igp[o] = t < S ? ig[static_cast<size_t>(bh) * S + t] : -1e30f;
   fgp[o] = t < S ? fg[static_cast<size_t>(bh) * S + t] : 1e30f;
 }
-// bf16 tiles -> fp32 (BH, S, DH)
-__global__ void mlstm_unpack_kernel(const unsigned char* __restrict__ tiles, int S, int DH, int DHP, int nc, float* __restrict__ dst) {
-  const int tile = blockIdx.x, r = threadIdx.x;
+// bf16 tiles -> fp32 (BH, S, DH): the same movement in the other direction
+__global__ void __launch_bounds__(256) mlstm_unpack_kernel(const unsigned char* __restrict__ tiles, int S, int DH, int DHP, int nc,
+                                                           float* __restrict__ dst) {
+  extern __shared__ __align__(16) unsigned char pk_smem[];
+  const int tile = blockIdx.x, tid = threadIdx.x;
   const int bh = tile / nc, c = tile % nc;
-  const int t = c * kL + r;
-  if (t >= S) return;
-  const unsigned char* src = tiles + static_cast<size_t>(tile) * (kL * DHP * 2);
-  float* row = dst + (static_cast<size_t>(bh) * S + t) * DH;
-  for (int cg = 0; cg < DHP / 8; ++cg) {
-    const uint4 u = *reinterpret_cast<const uint4*>(src + tile_off16(kL, r, cg));
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    const float f[8] = {a.x, a.y, b.x, b.y, cc.x, cc.y, d.x, d.y};
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (cg * 8 + j < DH) row[cg * 8 + j] = f[j];
+  const int t0 = c * kL, rows = min(kL, S - t0);
+  const uint32_t tile_bytes = kL * DHP * 2;
+  const uint4* in = reinterpret_cast<const uint4*>(tiles + static_cast<size_t>(tile) * tile_bytes);
+  for (uint32_t i = tid; i < tile_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(pk_smem)[i] = __ldg(in + i);
+  __syncthreads();
+  float* blk = dst + (static_cast<size_t>(bh) * S + t0) * DH;
+  const int n = rows * DH;
+  if ((DH & 3) == 0 && (reinterpret_cast<uintptr_t>(blk) & 15) == 0) {
+    for (int i = tid * 4; i < n; i += blockDim.x * 4) {
+      const int r = i / DH, d = i % DH;
+      const unsigned char* sp = pk_smem + tile_off16(kL, r, d / 8) + (d % 8) * 2;
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sp)), b2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sp + 4));
+      *reinterpret_cast<float4*>(blk + i) = make_float4(a.x, a.y, b2.x, b2.y);
+    }
+  } else {
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int r = i / DH, d = i % DH;
+      blk[i] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(pk_smem + tile_off16(kL, r, d / 8) + (d % 8) * 2));
+    }
   }
 }
 
@@ -497,7 +517,7 @@ extern "C" int xhved_mlstm_pack(const float* src, int BH, int S, int dh, int dhp
   if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp || dhp % 16) return XHVED_ERR_BAD_SHAPE;
   const int nc = (S + kL - 1) / kL;
   ProfScope ps(K_PACK, static_cast<cudaStream_t>(stream));
-  mlstm_pack_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>(src, S, dh, dhp, nc, (unsigned char*)tiles);
+  mlstm_pack_kernel<<<BH * nc, 256, kL * dhp * 2, static_cast<cudaStream_t>(stream)>>>(src, S, dh, dhp, nc, (unsigned char*)tiles);
   return (int)cudaGetLastError();
 }
 extern "C" int xhved_mlstm_pack_gates(const float* ig, const float* fg, int BH, int S, float* ig_padded, float* fg_padded, void* stream) {
@@ -511,7 +531,7 @@ extern "C" int xhved_mlstm_unpack(const void* tiles, int BH, int S, int dh, int 
   if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp || dhp % 16) return XHVED_ERR_BAD_SHAPE;
   const int nc = (S + kL - 1) / kL;
   ProfScope ps(K_UNPACK, static_cast<cudaStream_t>(stream));
-  mlstm_unpack_kernel<<<BH * nc, kL, 0, static_cast<cudaStream_t>(stream)>>>((const unsigned char*)tiles, S, dh, dhp, nc, dst);
+  mlstm_unpack_kernel<<<BH * nc, 256, kL * dhp * 2, static_cast<cudaStream_t>(stream)>>>((const unsigned char*)tiles, S, dh, dhp, nc, dst);
   return (int)cudaGetLastError();
 }
 
