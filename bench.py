@@ -210,9 +210,11 @@ def synth_inputs(B, seed, device, pin=False):
 class HotPath:
     """The hot path of B volumes on one GPU, through the package's public API."""
 
-    def __init__(self, B, device, world):
+    def __init__(self, B, device, world, two_streams=False):
         import xlstm_hved_b200 as xh
         self.xh, self.B, self.device, self.world = xh, B, device, world
+        self.two_streams = two_streams
+        self.side = torch.cuda.Stream(device=device) if two_streams else None
         self.blk_f = xh.ViLBlock(DIM, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
         self.blk_r = xh.ViLBlock(DIM, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT)
         randomise_params(self.blk_f, 1)
@@ -271,6 +273,29 @@ class HotPath:
         return out
 
     def _body(self, slot):
+        """One step.  The two halves of the path are independent (the S-MVAE fusion works on the latent posteriors, the ViL
+        pair on the bottleneck feature): with two_streams the fusion is enqueued on a side stream, forked from and joined
+        back into the main stream, so that its bandwidth-bound kernels can fill SMs the cell kernels leave partly empty
+        (captured as a fork / join inside the CUDA graph)."""
+        main = torch.cuda.current_stream()
+        if self.two_streams:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                fused, kld_total = self._smvae(slot)
+        else:
+            fused, kld_total = self._smvae(slot)
+        y, x = self._vil(slot)
+        if self.two_streams:
+            main.wait_stream(self.side)
+            for t in [kld_total] + [f[2] for f in fused]:
+                t.record_stream(main)
+        # what the model consumes downstream / upstream of the path: y (-> decoder), z per level (-> decoder), dx (-> encoder
+        # backward) and the KL term of the loss
+        sl = self.slots[slot]
+        sl["outs"] = dict(y=y.detach(), dx=x.grad, z=[f[2] for f in fused], loss=kld_total + y.detach()[0, 0, 0])
+        return sl["outs"]["loss"]
+
+    def _smvae(self, slot):
         ops = self.xh.ops
         sl = self.slots[slot]
         mu5, lv5 = sl["mu5"], sl["lv5"]
@@ -288,6 +313,10 @@ class HotPath:
         fused = ops.poe_fwd_levels(levels, [SUBSET_FULL], noises=noises, kld_out=self.kld.view(4, 1), standard_prior=True)
         ops.poe_bwd_levels(levels, [SUBSET_FULL], noises=noises, g_zs=self.gz, kld_scales=self.kld_scales, standard_prior=True)
         kld_total = torch.dot(self.kld, self.kld_w)                            # mean KL over the 4 levels (train.py:236-239)
+        return fused, kld_total
+
+    def _vil(self, slot):
+        sl = self.slots[slot]
         # ---- ViL block pair on the NCDHW feature (token view, no transposed copies), forward + backward
         x = sl["x"].detach().requires_grad_()
         tok = x.reshape(self.B, DIM, -1).transpose(-1, -2)
@@ -295,10 +324,7 @@ class HotPath:
         for p in self.params:
             p.grad = None
         y.backward(self.gy.reshape(self.B, DIM, -1).transpose(-1, -2))
-        # what the model consumes downstream / upstream of the path: y (-> decoder), z per level (-> decoder), dx (-> encoder
-        # backward) and the KL term of the loss
-        sl["outs"] = dict(y=y.detach(), dx=x.grad, z=[f[2] for f in fused], loss=kld_total + y.detach()[0, 0, 0])
-        return sl["outs"]["loss"]
+        return y, x
 
 
 def run_gpu(args):
@@ -314,7 +340,7 @@ def run_gpu(args):
     from xlstm_hved_b200 import _lib
     lib = _lib.load_library()
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    hp = HotPath(B, device, world)
+    hp = HotPath(B, device, world, two_streams=args.streams == 2)
     x, mus, lvs = synth_inputs(B, 1000 + rank, device)
     hp.load(x, mus, lvs)
 
@@ -584,6 +610,7 @@ def run_gpu(args):
                    "latent_elements_per_volume": sum(C * d ** 3 for C, d in LEVELS),
                    "l2_policy": f"inputs larger than L2 (PoE posteriors {h2d / 2**20:.0f} MiB per step > 126 MiB)",
                    "launch": "CUDA graph replay of the step captured through the public API" if graphed else "eager (one Python call per op)",
+                   "streams": args.streams,
                    "eager_ms_per_step": round(ms_eager / K, 4),
                    "collective": "1 flat-bucket NCCL all-reduce (xlstm_hved_b200.dist.FlatGradBucket: gather, all-reduce, average, write "
                                  "back) of the 28 ViL parameter gradients per step" if world > 1 else "none"},
@@ -775,6 +802,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=2, help="volumes timed for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained loop")
+    ap.add_argument("--streams", type=int, default=1, choices=[1, 2], help="2: S-MVAE fusion on a side stream next to the ViL pair")
     ap.add_argument("--no-eager-ref", action="store_true", help="skip timing the reference's PyTorch classes on the GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured step")
     args = ap.parse_args()

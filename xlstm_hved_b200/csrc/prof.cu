@@ -16,7 +16,6 @@ struct Rec {
 };
 static std::vector<Rec> g_recs;
 static std::vector<cudaEvent_t> g_pool;
-static cudaEvent_t g_pending[K_COUNT];
 
 static cudaEvent_t get_event() {
   if (!g_pool.empty()) {
@@ -31,17 +30,17 @@ static cudaEvent_t get_event() {
 
 bool prof_enabled() { return g_on.load(std::memory_order_relaxed); }
 
-void prof_begin(int id, cudaStream_t st) {
+cudaEvent_t prof_begin(cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_mu);
   cudaEvent_t e = get_event();
   cudaEventRecord(e, st);
-  g_pending[id] = e;
+  return e;
 }
-void prof_end(int id, cudaStream_t st) {
+void prof_end(int id, cudaEvent_t begin, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_mu);
   cudaEvent_t e = get_event();
   cudaEventRecord(e, st);
-  g_recs.push_back({id, g_pending[id], e});
+  g_recs.push_back({id, begin, e});
 }
 
 static const char* kNames[K_COUNT] = {

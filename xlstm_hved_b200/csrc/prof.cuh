@@ -13,18 +13,21 @@ enum KernelId {
 };
 
 bool prof_enabled();
-void prof_begin(int id, cudaStream_t st);
-void prof_end(int id, cudaStream_t st);
+cudaEvent_t prof_begin(cudaStream_t st);
+void prof_end(int id, cudaEvent_t begin, cudaStream_t st);
 
+// The begin event lives in the scope object (not in a per-kernel-id global), so scopes opened concurrently from several
+// host threads -- the reference runs replicas from several threads, train.py:148-151 -- cannot overwrite each other's.
 struct ProfScope {
   int id;
   cudaStream_t st;
   bool on;
-  ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), on(prof_enabled()) {
-    if (on) prof_begin(id, st);
+  cudaEvent_t begin;
+  ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), on(prof_enabled()), begin(nullptr) {
+    if (on) begin = prof_begin(st);
   }
   ~ProfScope() {
-    if (on) prof_end(id, st);
+    if (on) prof_end(id, begin, st);
   }
 };
 
