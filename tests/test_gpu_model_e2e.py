@@ -143,3 +143,34 @@ def test_graphed_step_replays_forward_and_backward():
         y_e, dx_e, dw_e = step()
         assert torch.equal(y_g, y_e) and torch.equal(dx_g, dx_e)
         assert rel_l2(dw_g, dw_e) < 1e-5          # parameter gradients: atomics, order not fixed
+
+
+def test_all_subsets_in_one_batch_matches_15_forwards(model):
+    """xh.all_subsets_forward: the 15 masked copies of a volume as ONE batch through the patched model (per-sample drop mask,
+    ProductOfExperts2 path) against the reference's own evaluation loop on the STOCK model (15 forwards, test.py:78-102)."""
+    import xlstm_hved_b200 as xh
+    ns = ref_loader.load_reference()
+    torch.manual_seed(9)
+    x = torch.rand(1, 4, 64, 64, 64, device="cuda")
+    ref = []
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        for idx, present in enumerate(ns.RA_HVED.SUBSETS_MODALITIES):
+            xm = x.clone()
+            for m in range(4):
+                if m not in present:
+                    xm[:, m] = 0
+            seg, _ = model(xm, [idx], valid=True)
+            ref.append(seg)
+    ref = torch.stack(ref)
+    xh.patch_model(model)
+    try:
+        got = xh.all_subsets_forward(model, x)
+        got8 = xh.all_subsets_forward(model, x, max_batch=8)
+    finally:
+        xh.unpatch_model(model)
+    assert got.shape == ref.shape == (15, 1, 3, 64, 64, 64)
+    same_mask = ((ref > 0.5) == (got > 0.5)).float().mean().item()
+    same_arg = (ref.argmax(2) == got.argmax(2)).float().mean().item()
+    print("all subsets in one batch: same (p>0.5)", same_mask, "same argmax", same_arg, "max abs diff", (ref - got).abs().max().item())
+    assert same_mask >= 0.999 and same_arg >= 0.999
+    assert ((got8 > 0.5) == (got > 0.5)).float().mean().item() >= 0.999          # (cuDNN picks algorithms per batch size)

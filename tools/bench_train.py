@@ -175,6 +175,15 @@ def main():
             print(json.dumps({"mode": "infer", **common, "steps": args.steps, "ms_per_volume_all_15_subsets": round(ms / args.steps / B, 2),
                               "volumes_per_s": round(world * B * args.steps / (ms * 1e-3), 3),
                               "forwards_per_s": round(15 * world * B * args.steps / (ms * 1e-3), 2)}))
+        # the same evaluation as ONE batch of 15 masked copies per volume (xlstm_hved_b200.driver)
+        batched = lambda: xh.all_subsets_forward(model, x)
+        batched()
+        torch.cuda.reset_peak_memory_stats(dev)
+        ms_b = timed(batched, args.steps)
+        if rank == 0:
+            print(json.dumps({"mode": "infer_batched", **common, "steps": args.steps, "ms_per_volume_all_15_subsets": round(ms_b / args.steps / B, 2),
+                              "volumes_per_s": round(world * B * args.steps / (ms_b * 1e-3), 3), "speedup_vs_15_forwards": round(ms / ms_b, 3),
+                              "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -3,7 +3,8 @@
 CUDA only: importing is cheap, but every op needs libxhved.so (python -m xlstm_hved_b200.build)
 and a CUDA device; there is no CPU / PyTorch-eager fallback.
 """
-from . import dist, modules, ops  # noqa: F401
+from . import dist, driver, modules, ops  # noqa: F401
+from .driver import all_subsets_forward  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
 from .modules import (ProductOfExperts, ProductOfExperts2, SequenceTraversal, ViLBlock, ViLLayer, ViLLayer3D,  # noqa: F401
                       clip, compute_KLD, parallel_stabilized_simple, reparametrize)
