@@ -7,7 +7,8 @@
 //     + O dhp+16 columns each), and the producer runs NSTAGE >= NSLOT shared-memory stages (Q, K, [V|1], state hi/lo) ahead,
 //     so that a tile's operands have landed long before its TMEM slot frees up;
 //   * warp roles: NSLOT consumer warpgroups (128 threads = the 128 rows / TMEM lanes of a tile), one producer warp
-//     (cp.async.bulk into the stage ring, full/empty mbarriers), one MMA warp (a single thread issues every tcgen05.mma);
+//     (cp.async.bulk into the stage ring, full/empty mbarriers), TWO MMA warps (S = Q K^T / O = P V; each runs in uniform
+//     control flow and elects a lane inside every tcgen05 instruction);
 //   * P = S o D' never touches shared memory: the consumer converts its row in registers and stores bf16 P back into the
 //     S columns with tcgen05.st; the second product O += P [V|1] takes its A operand from TENSOR MEMORY;
 //   * the inter-chunk part w_t * (q_t [C|n]) is folded into the same accumulator: Q [C|n] is issued together with S, the
@@ -30,15 +31,20 @@ namespace xhved {
 template <int DHP>
 struct FwdWs {
   static constexpr int NE = ext_cols(DHP);
-  static constexpr int NSLOT = DHP <= 16 ? 3 : (DHP <= 64 ? 2 : 1);    // tiles in flight in tensor memory (one consumer warpgroup each)
-  static constexpr int NSTAGE = DHP <= 16 ? 6 : (DHP <= 32 ? 4 : (DHP <= 64 ? 2 : 1));   // operand stages the producer runs ahead by
+  // dhp = 16: a slot is 128 columns -- the accumulators live in the half of the S columns that the bf16 P leaves free
+  // (O_intra = P V at [64, 80), O_inter = Q [C|n] at [80, 112), both issued once P is written) -- so FOUR tiles are in flight
+  static constexpr bool COMPACT = DHP <= 16;
+  static constexpr int NSLOT = DHP <= 16 ? 4 : (DHP <= 64 ? 2 : 1);    // tiles in flight in tensor memory (one consumer warpgroup each)
+  static constexpr int NSTAGE = DHP <= 16 ? 8 : (DHP <= 32 ? 4 : (DHP <= 64 ? 2 : 1));   // operand stages the producer runs ahead by
   static constexpr uint32_t TILE = kL * DHP * 2;
   static constexpr uint32_t VEXT = kL * NE * 2;
   static constexpr uint32_t ST1 = DHP * NE * 2;            // one state tile (hi or lo)
   static constexpr uint32_t OFF_Q = 0, OFF_K = TILE, OFF_V = 2 * TILE, OFF_S = 2 * TILE + VEXT;
   static constexpr uint32_t STAGE = 2 * TILE + VEXT + 2 * ST1;
-  static constexpr uint32_t TM_SLOT = 128 + NE;            // TMEM columns per slot: S | O
-  static constexpr int NTHREADS = (4 * NSLOT + 2) * 32;
+  static constexpr uint32_t TM_SLOT = COMPACT ? 128 : 128 + NE;   // TMEM columns per slot: S | O (COMPACT: O inside the S columns)
+  static constexpr uint32_t T_OI = COMPACT ? 64 : 128;            // O (intra; COMPACT: intra only) relative to the slot
+  static constexpr uint32_t T_OX = 80;                            // COMPACT: Q [C|n], NE columns
+  static constexpr int NTHREADS = (4 * NSLOT + 3) * 32;      // consumers | producer | S issuer | PV issuer
   // per-slot fp32 arrays behind the stages: vcol[128], ev[128], vmax[4], red_sum[4], red_max[4]
   static constexpr uint32_t AUX = (128 + 128 + 4 + 4 + 4) * 4;
   static constexpr uint32_t SMEM_USED = NSTAGE * STAGE + NSLOT * AUX;
@@ -102,42 +108,52 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
       }
     }
   } else if (warp == 4 * NSLOT + 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr int LA = NSLOT - 1;   // S of tile it+LA is issued before P V of tile it
-      for (int step = 0; step < n_my + LA; ++step) {
-        if (step < n_my) {
-          const int it = step, s = it % NSLOT, use = it / NSLOT, sg = it % NSTAGE, use_sg = it / NSTAGE;
-          const int tile = blockIdx.x + it * gridDim.x;
-          const bool has_state = (tile % nc) > 0;
-          const uint32_t st = smem_u32(smem + sg * C::STAGE);
-          const uint32_t tS = tmem + s * C::TM_SLOT, tO = tS + 128;
-          mbar_wait(&bar_free[s], (use & 1) ^ 1);     // epilogue of the previous tile in this slot has drained TMEM
-          mbar_wait(&bar_full[sg], use_sg & 1);
-          tc_fence_after();
-          // S[t][s'] = sum_d Q[t][d] K[s'][d]
-          umma_gemm(tS, st + C::OFF_Q, kL * 16, 128, st + C::OFF_K, kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
-          // O[t][e'] = sum_d Q[t][d] [C|n][d][e']   (hi + lo state tiles; B = MN-major view)
-          if (has_state) {
-            umma_gemm(tO, st + C::OFF_Q, kL * 16, 128, st + C::OFF_S, 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, false);
-            umma_gemm(tO, st + C::OFF_Q, kL * 16, 128, st + C::OFF_S + ST1, 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, true);
-          }
-          umma_commit(&bar_s[s]);
-        }
-        if (step >= LA) {
-          const int it = step - LA, s = it % NSLOT, use = it / NSLOT, sg = it % NSTAGE;
-          const int tile = blockIdx.x + it * gridDim.x;
-          const bool has_state = (tile % nc) > 0;
-          const uint32_t st = smem_u32(smem + sg * C::STAGE);
-          const uint32_t tS = tmem + s * C::TM_SLOT, tO = tS + 128;
-          mbar_wait(&bar_p[s], use & 1);
-          tc_fence_after();
-          // O[t][e'] += sum_s' P[t][s'] [V|1][s'][e']   (A = bf16 P in TMEM, B = MN-major view of the V stage)
-          umma_gemm_ts(tO, tS, st + C::OFF_V, 128, kL * 16, umma_idesc(128, NE, false, true), kL, has_state);
-          umma_commit(&bar_o[s]);
-          umma_commit(&bar_empty[sg]);                // every MMA reading this stage has completed
-        }
+    // ===================================================================== MMA issuer 1: S = Q K^T (and, outside COMPACT, Q [C|n])
+    // Two issuing warps: a single thread that waits for three barriers and issues ~13 tcgen05 instructions per tile (~100
+    // cycles each) is itself the bottleneck of the kernel (2,700 cycles per tile measured, whatever the number of slots).
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % NSLOT, use = it / NSLOT, sg = it % NSTAGE, use_sg = it / NSTAGE;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const bool has_state = (tile % nc) > 0;
+      const uint32_t st = smem_u32(smem + sg * C::STAGE);
+      const uint32_t tS = tm + s * C::TM_SLOT, tO = tS + 128;
+      mbar_wait(&bar_free[s], (use & 1) ^ 1);     // epilogue of the previous tile in this slot has drained TMEM
+      mbar_wait(&bar_full[sg], use_sg & 1);
+      tc_fence_after();
+      // S[t][s'] = sum_d Q[t][d] K[s'][d]
+      umma_gemm_e(tS, st + C::OFF_Q, kL * 16, 128, st + C::OFF_K, kL * 16, 128, umma_idesc(128, kL, false, false), DHP, false);
+      // O[t][e'] = sum_d Q[t][d] [C|n][d][e']   (hi + lo state tiles; B = MN-major view)
+      if (has_state && !C::COMPACT) {
+        umma_gemm_e(tO, st + C::OFF_Q, kL * 16, 128, st + C::OFF_S, 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, false);
+        umma_gemm_e(tO, st + C::OFF_Q, kL * 16, 128, st + C::OFF_S + ST1, 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, true);
       }
+      umma_commit_e(&bar_s[s]);
+    }
+  } else if (warp == 4 * NSLOT + 2) {
+    // ===================================================================== MMA issuer 2: O (+)= P [V|1] once P is written
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % NSLOT, use = it / NSLOT, sg = it % NSTAGE;
+      const int tile = blockIdx.x + it * gridDim.x;
+      const bool has_state = (tile % nc) > 0;
+      const uint32_t st = smem_u32(smem + sg * C::STAGE);
+      const uint32_t tS = tm + s * C::TM_SLOT, tO = tS + 128;
+      mbar_wait(&bar_p[s], use & 1);
+      tc_fence_after();
+      if (C::COMPACT) {
+        // O_intra[t][e] = sum_s' P[t][s'] V[s'][e] and O_inter[t][e'] = sum_d Q[t][d] [C|n][d][e'] into the S columns P left free
+        umma_gemm_ts_e(tS + C::T_OI, tS, st + C::OFF_V, 128, kL * 16, umma_idesc(128, DHP, false, true), kL, false);
+        if (has_state) {
+          umma_gemm_e(tS + C::T_OX, st + C::OFF_Q, kL * 16, 128, st + C::OFF_S, 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, false);
+          umma_gemm_e(tS + C::T_OX, st + C::OFF_Q, kL * 16, 128, st + C::OFF_S + ST1, 128, DHP * 16, umma_idesc(128, NE, false, true), DHP, true);
+        }
+      } else {
+        // O[t][e'] += sum_s' P[t][s'] [V|1][s'][e']   (A = bf16 P in TMEM, B = MN-major view of the V stage)
+        umma_gemm_ts_e(tO, tS, st + C::OFF_V, 128, kL * 16, umma_idesc(128, NE, false, true), kL, has_state);
+      }
+      umma_commit_e(&bar_o[s]);
+      umma_commit_e(&bar_empty[sg]);                // every MMA reading this stage has completed
     }
   } else {
     // ===================================================================== consumers: warpgroup wg owns slot wg
@@ -209,12 +225,12 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
       if (lane == 0) vmax[w] = bm;
       named_bar_sync(1 + wg, kL);
 
-      const uint32_t tS = tmem + wg * C::TM_SLOT + lane_base, tO = tS + 128;
+      const uint32_t tS = tmem + wg * C::TM_SLOT + lane_base, tO = tS + C::T_OI;
       mbar_wait(&bar_s[wg], use & 1);
       tc_fence_after();
       // ---- inter-chunk part: O <- w_t * (Q [C|n]) in place; column dhp of it is w_t q_t.n, the inter-chunk part of den ----
       float den = 0.f;
-      if (has_state) {
+      if (has_state && !C::COMPACT) {
 #pragma unroll
         for (int c0 = 0; c0 < NE; c0 += 16) {
           uint32_t o[16];
@@ -281,6 +297,21 @@ __global__ void __launch_bounds__(FwdWs<DHP>::NTHREADS, 1) mlstm_chunk_out_ws_ke
       // ---- epilogue: h = O / (max(|den|, exp(-m)) + eps)   (vision_lstm.py:123-128) ----
       mbar_wait(&bar_o[wg], use & 1);
       tc_fence_after();
+      if (C::COMPACT && has_state) {               // the inter-chunk accumulator was not pre-scaled: fold it in here
+        uint32_t ox[16], on[16];
+        uint32_t o0[16];
+        tmem_ld16_nowait(tS + C::T_OX, ox);
+        tmem_ld16_nowait(tS + C::T_OX + 16, on);
+        tmem_ld16_nowait(tO, o0);
+        tmem_wait_ld16(ox);
+        tmem_wait_ld16(on);
+        tmem_wait_ld16(o0);
+        den += wgt * __uint_as_float(on[0]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) + wgt * __uint_as_float(ox[i]));
+        tmem_st16(tO, o0);                          // (this lane's own columns: read back below)
+        tmem_wait_st();
+      }
       const float rn = 1.f / (fmaxf(fabsf(den), __expf(-m)) + eps);
       unsigned char* hdst = h_tiles + static_cast<size_t>(tile) * TILE;
 #pragma unroll
