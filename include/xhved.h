@@ -131,6 +131,14 @@ int xhved_clip_bwd(const float* x, const float* g, int64_t n, float lo, float hi
  * reference is the same map applied to the incoming gradient, so one entry point serves both directions. */
 int xhved_zero_rows(const float* x, const uint8_t* mask, int64_t rows, int64_t per_row, float* y, void* stream);
 
+/* Per-channel Dice coefficient of the training loss (compute_per_channel_dice, loss.py:257-285, called from DiceLoss.forward,
+ * loss.py:201-209): p, t fp32 (N, C, spatial) contiguous.  xhved_dice_sums accumulates into sums[3 C] (zeroed by the caller)
+ * {sum p t, sum p^2, sum t^2} per channel in one pass; dice_c = 2 sums[3c] / max(sums[3c+1] + sums[3c+2], eps) is left to the
+ * caller (C numbers).  xhved_dice_bwd: dp = g_dice[c] * d dice_c / d p (zero where the clamp is active). */
+int xhved_dice_sums(const float* p, const float* t, int N, int C, int64_t spatial, float* sums, void* stream);
+int xhved_dice_bwd(const float* p, const float* t, const float* sums, const float* g_dice, int N, int C, int64_t spatial, float eps,
+                   float* dp, void* stream);
+
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
 int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);

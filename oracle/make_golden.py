@@ -200,6 +200,25 @@ def gen_smvae_extras(ns):
     torch.save(out, os.path.join(OUT, "smvae_extras.pt"))
 
 
+def gen_losses(ns):
+    """DiceLoss (loss.py:188-209, 257-301) of the real reference on sigmoid-like probabilities and a binary mask: value,
+    per-channel coefficients and the gradient w.r.t. the probabilities; one channel is empty on both sides (clamp active)."""
+    import contextlib
+    import io
+    loss = ns.loss
+    g = torch.Generator().manual_seed(5)
+    p = torch.rand(2, 4, 6, 7, 5, generator=g, dtype=torch.float64)
+    t = (torch.rand(2, 4, 6, 7, 5, generator=g) > 0.5).double()
+    p[:, 3] = 0
+    t[:, 3] = 0
+    pr = p.clone().requires_grad_()
+    with contextlib.redirect_stdout(io.StringIO()):
+        val = loss.DiceLoss()(pr, t)
+        per = loss.compute_per_channel_dice(p, t)
+    (dp,) = torch.autograd.grad(val, pr)
+    torch.save(dict(p=p, t=t, loss=val.detach(), per_channel=per, dp=dp), os.path.join(OUT, "losses.pt"))
+
+
 def gen_model_boundary(ns):
     """Run the full XLSTM_HVED on a small seeded volume and record the tensors
     that cross the hot-path boundary (RA_HVED.py:588-597 and 623-626)."""
@@ -238,7 +257,7 @@ def main():
     assert ns is not None, "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]            # e.g. `python oracle/make_golden.py smvae_extras` regenerates one file
-    gens = dict(cell=gen_cell, vil_block=gen_block, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras,
+    gens = dict(cell=gen_cell, vil_block=gen_block, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras, losses=gen_losses,
                 model_boundary=gen_model_boundary)
     for name, fn in gens.items():
         if not only or name in only:

@@ -334,6 +334,23 @@ def compute_kld(mu_b5, logvar_b5, subset_index_list=(14,)):
     return tot / cnt
 
 
+def dice_per_channel(inp, target, epsilon: float = 1e-6, weight=None):
+    """compute_per_channel_dice -- loss.py:257-285 (flatten: 287-301): per channel over batch and voxels,
+    2 sum(p t) / clamp(sum p^2 + sum t^2, eps), the optional weight on the intersection."""
+    C = inp.shape[1]
+    p = inp.transpose(0, 1).reshape(C, -1)
+    t = target.transpose(0, 1).reshape(C, -1).to(p.dtype)
+    inter = (p * t).sum(-1)
+    if weight is not None:
+        inter = weight * inter
+    return 2 * (inter / ((p * p).sum(-1) + (t * t).sum(-1)).clamp(min=epsilon))
+
+
+def dice_loss(inp, target, weight=None):
+    """DiceLoss.forward -- loss.py:201-209: 1 - mean over channels (the input is NOT normalised: line 203 is commented out)."""
+    return 1.0 - torch.mean(dice_per_channel(inp, target, weight=weight))
+
+
 def zero_rows(x, alpha):
     """ZeroLayerF.forward (and .backward applied to the gradient) -- buildingblocks.py:308-323."""
     y = x.clone()

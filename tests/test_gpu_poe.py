@@ -283,3 +283,31 @@ def test_zero_layer_golden_and_patch_target():
     x2 = torch.randn(4, 7, device="cuda")
     m2 = torch.tensor([False, True, True, False])
     assert torch.equal(xh.modules.ZeroLayerF.apply(x2, m2), restate.zero_rows(x2.cpu(), m2).cuda())
+
+
+def test_dice_loss_fused_golden_and_large():
+    """compute_per_channel_dice / DiceLoss (loss.py:188-209, 257-301) as one fused pass: the reference fixture (value, per-channel
+    coefficients, gradient, a channel with the clamp active), fp16 inputs as under the reference's autocast, and a full-size
+    segmentation output against the oracle."""
+    import xlstm_hved_b200 as xh
+    c = load_golden("losses.pt")
+    p = c["p"].float().cuda().requires_grad_()
+    t = c["t"].float().cuda()
+    val = xh.DiceLoss()(p, t)
+    (dp,) = torch.autograd.grad(val, p)
+    assert abs(val.item() - c["loss"].item()) < 1e-5
+    assert rel_linf(xh.modules.compute_per_channel_dice(p.detach(), t), c["per_channel"]) < 1e-5 and rel_l2(dp, c["dp"]) < 1e-5
+    assert dp[:, 3].abs().max().item() == 0.0
+    w = torch.tensor([0.5, 1.0, 2.0, 1.0], device="cuda")
+    assert rel_linf(xh.modules.compute_per_channel_dice(p.detach(), t, weight=w), restate.dice_per_channel(c["p"], c["t"], weight=w.cpu().double())) < 1e-5
+    h = xh.modules.compute_per_channel_dice(p.detach().half(), t.half())
+    assert h.dtype == torch.float16 and rel_linf(h.float(), c["per_channel"]) < 2e-3
+    g = torch.Generator(device="cuda").manual_seed(2)
+    P = torch.rand(2, 3, 128, 128, 128, device="cuda", generator=g).requires_grad_()
+    T = (torch.rand(2, 3, 128, 128, 128, device="cuda", generator=g) > 0.5).float()
+    v = xh.DiceLoss()(P, T)
+    (dP,) = torch.autograd.grad(v, P)
+    P64 = P.detach().double().requires_grad_()
+    v64 = restate.dice_loss(P64, T.double())
+    (dP64,) = torch.autograd.grad(v64, P64)
+    assert abs(v.item() - v64.item()) < 1e-5 and rel_l2(dP, dP64) < 1e-5

@@ -138,3 +138,14 @@ def test_smvae_extras_general_prior_clip_zero_layer_match_reference():
         assert rel_linf(dmu, r["d_mod_mu"]) < 1e-12 and rel_linf(dlv, r["d_raw_logvar"]) < 1e-12
     zl = c["zero_layer"]
     assert torch.equal(restate.zero_rows(zl["x"], zl["alpha"]), zl["y"]) and torch.equal(restate.zero_rows(zl["gy"], zl["alpha"]), zl["dx"])
+
+
+def test_dice_loss_matches_reference():
+    """DiceLoss / compute_per_channel_dice (loss.py:188-209, 257-301), value and gradient, incl. a channel where the clamp is active."""
+    c = load_golden("losses.pt")
+    p = c["p"].clone().requires_grad_()
+    val = restate.dice_loss(p, c["t"])
+    (dp,) = torch.autograd.grad(val, p)
+    assert abs(val.item() - c["loss"].item()) < 1e-14
+    assert rel_linf(restate.dice_per_channel(c["p"], c["t"]), c["per_channel"]) < 1e-14 and rel_linf(dp, c["dp"]) < 1e-13
+    assert c["per_channel"][3].item() == 0.0 and c["dp"][:, 3].abs().max().item() == 0.0

@@ -75,6 +75,8 @@ SYMBOLS = {
     "xhved_clip_fwd": [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p],
     "xhved_clip_bwd": [c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p],
     "xhved_zero_rows": [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
+    "xhved_dice_sums": [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p],
+    "xhved_dice_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p, c_void_p],
     "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,

@@ -416,6 +416,46 @@ class ZeroLayerF(torch.autograd.Function):
         return ops.zero_rows(grad_output, ctx.alpha).to(ctx.dtype), None
 
 
+class _DiceFunction(torch.autograd.Function):
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, p, t, eps):
+        sums = ops.dice_sums(p, t)
+        ctx.save_for_backward(p, t, sums)
+        ctx.eps = eps
+        return 2.0 * sums[:, 0] / (sums[:, 1] + sums[:, 2]).clamp(min=eps)
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, g):
+        p, t, sums = ctx.saved_tensors
+        return ops.dice_bwd(p, t, sums, g.contiguous(), ctx.eps), None, None
+
+
+def compute_per_channel_dice(input, target, epsilon=1e-6, weight=None):
+    """loss.py:257-285: Dice coefficient per channel of (N, C, *spatial) probabilities and targets,
+    2 sum(p t) / clamp(sum p^2 + sum t^2, eps), with the optional per-channel weight on the intersection.  One fused pass
+    (and one for the gradient w.r.t. ``input``; the target is a label map and receives none)."""
+    assert input.size() == target.size(), "'input' and 'target' must have the same shape"
+    _require_device(input)
+    dice = _DiceFunction.apply(input.float().contiguous(), target.float().contiguous(), float(epsilon))
+    if weight is not None:
+        dice = dice * weight.reshape(-1).to(dice)
+    return dice.to(input.dtype) if input.dtype in (torch.float16, torch.bfloat16) else dice
+
+
+class DiceLoss(nn.Module):
+    """Mirror of loss.DiceLoss (loss.py:188-209): 1 - mean over channels of the Dice coefficient (no normalisation of the
+    input: the model ends in a sigmoid, RA_HVED.py:483-484)."""
+
+    def __init__(self, weight=None):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, input, target):
+        return 1.0 - torch.mean(compute_per_channel_dice(input, target, weight=self.weight))
+
+
 class _KLDFunction(torch.autograd.Function):
     @staticmethod
     @_lib.on_device

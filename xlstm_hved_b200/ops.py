@@ -234,6 +234,26 @@ def zero_rows(x, mask):
     return y
 
 
+def dice_sums(p, t):
+    """{sum p t, sum p^2, sum t^2} per channel of (N, C, *spatial) fp32 tensors, one pass.  Returns a (C, 3) tensor."""
+    lib = _lib.load_library()
+    p, t = _f32c(p), _f32c(t)
+    N, C = p.shape[:2]
+    spatial = p[0, 0].numel()
+    sums = torch.zeros(C, 3, device=p.device, dtype=torch.float32)
+    check(lib.xhved_dice_sums(ptr(p), ptr(t), N, C, spatial, ptr(sums), stream()), "xhved_dice_sums")
+    return sums
+
+
+def dice_bwd(p, t, sums, g_dice, eps: float = 1e-6):
+    lib = _lib.load_library()
+    p, t = _f32c(p), _f32c(t)
+    N, C = p.shape[:2]
+    dp = torch.empty_like(p)
+    check(lib.xhved_dice_bwd(ptr(p), ptr(t), ptr(sums), ptr(_f32c(g_dice)), N, C, p[0, 0].numel(), eps, ptr(dp), stream()), "xhved_dice_bwd")
+    return dp
+
+
 def reparam_fwd(mu, logvar, noise):
     lib = _lib.load_library()
     mu, logvar, noise = _f32c(mu), _f32c(logvar), _f32c(noise)

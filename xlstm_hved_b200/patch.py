@@ -97,6 +97,8 @@ def patch_model(model, patch_globals: bool = True):
         vl = next((m for n, m in sys.modules.items() if n.endswith("nets.vision_lstm") and hasattr(m, "parallel_stabilized_simple")), None)
         for owner, attr, repl in ((ra, "reparametrize", modules.reparametrize), (ra, "clip", modules.clip),
                                   (ls, "compute_KLD", modules.compute_KLD), (bb, "ZeroLayerF", modules.ZeroLayerF),
+                                  # DiceLoss.forward calls this through the loss module's globals (loss.py:198-199)
+                                  (ls, "compute_per_channel_dice", modules.compute_per_channel_dice),
                                   # the cell itself (vision_lstm.py:48-130, called at 327): reached by blocks wider than the
                                   # fused kernels cover and by any stand-alone MatrixLSTMCell of the reference
                                   (vl, "parallel_stabilized_simple", modules.parallel_stabilized_simple)):
