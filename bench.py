@@ -490,12 +490,22 @@ def run_gpu(args):
         "mlstm_chunk_rstate": tokens_heads * (2 * DH * DH),
     }
     n_lat = sum(C * d ** 3 for C, d in LEVELS) * B
+    # ViL kernels, per token: MINIMUM bytes in the sense of SURVEY 8d (fp32 x / y / dy / dx, bf16 for every intermediate:
+    # K2 + K3 forward = 12 C + 16 E + 8 NH = 1440 B at C = 32); impl_token_bytes = what the kernels move today
     per_token_bytes = {
-        "vil_pre_fwd": 4 * DIM + 3 * E * 2 + 8 * 4 + 3 * E * 4,                       # x in; q,k,v tiles, gates, act, z, xm out
-        "vil_post_fwd": E * 2 + 2 * E * 4 + 4 * DIM + 4 * DIM,                        # h, act, z, x in; y out
-        "vil_post_bwd": 4 * DIM + E * 2 + 2 * E * 4 + E * 2 + 2 * E * 4,              # dy, h, act, z in; dh, d_act, dz out
-        "vil_pre_bwd_a": E * 4 + 3 * E * 4 + 8 * 4 + E * 4 + 2 * E * 4,               # xm, dq,dk,dv, dgates, d_act in; dconv, dxmv out
-        "vil_pre_bwd_b": 4 * DIM + 4 * DIM + 3 * E * 4 + 4 * DIM,                     # x, dy, dconv, dxmv, dz in; dx out
+        "vil_pre_fwd": 4 * DIM + 3 * E * 2 + 8 * 4 + 2 * E * 2,                       # x in; q,k,v tiles, gates, act, z out
+        "vil_post_fwd": E * 2 + 2 * E * 2 + 4 * DIM + 4 * DIM,                        # h, act, z, x in; y out
+        "vil_post_bwd": 4 * DIM + E * 2 + 2 * E * 2 + E * 2 + 2 * E * 2,              # dy, h, act, z in; dh, d_act, dz out
+        "vil_pre_bwd_a": E * 2 + 3 * E * 2 + 8 * 4 + E * 2 + 2 * E * 2,               # xm, dq,dk,dv, dgates, d_act in; dconv, dxmv out
+        "vil_pre_bwd_b": 4 * DIM + 4 * DIM + 3 * E * 2 + 4 * DIM,                     # x, dy, dconv, dxmv, dz in; dx out
+    }
+    ACT_B = 4                                                                         # bytes per element of the saved act / z / xm
+    impl_token_bytes = {
+        "vil_pre_fwd": 4 * DIM + 3 * E * 2 + 8 * 4 + 3 * E * ACT_B,                   # ... + xm saved for the backward
+        "vil_post_fwd": E * 2 + 2 * E * ACT_B + 4 * DIM + 4 * DIM,
+        "vil_post_bwd": 4 * DIM + E * 2 + 2 * E * ACT_B + E * 2 + 2 * E * 2,
+        "vil_pre_bwd_a": E * ACT_B + 3 * E * 2 + 8 * 4 + E * 2 + 2 * E * 2,
+        "vil_pre_bwd_b": 4 * DIM + 4 * DIM + 3 * E * 2 + 4 * DIM,
     }
     # cell kernels, per token-head: MINIMUM bytes in the sense of SURVEY 8d -- bf16 q,k,v (dh) in, bf16 h (dq,dk,dv) out, fp32
     # gates / stabiliser / normaliser; carried states, hi/lo pairs and fp32 gradient rows are implementation traffic and do
@@ -511,12 +521,13 @@ def run_gpu(args):
         "mlstm_state_scan": 2 * st_tok,
         "mlstm_chunk_out": 6 * DHP + 8 + st_tok + 2 * DHP + 8,
         "mlstm_chunk_rstate": 6 * DHP + 12 + st_tok,
-        "mlstm_chunk_grad": 10 * DHP + 16 + 2 * st_tok + 12 * DHP + 8,                # fp32 dq,dk,dv rows, hi/lo states C and R
+        "mlstm_chunk_grad": 10 * DHP + 16 + 2 * st_tok + 6 * DHP + 8,                 # + hi/lo states C and R
         "mlstm_gate_finish": 12,
     }
     bytes_per_launch = {k: v * tokens for k, v in per_token_bytes.items()}
     bytes_per_launch.update({k: v * tokens_heads for k, v in per_tokenhead_bytes.items()})
     impl_bytes_per_launch = {k: v * tokens_heads for k, v in impl_tokenhead_bytes.items()}
+    impl_bytes_per_launch.update({k: v * tokens for k, v in impl_token_bytes.items()})
     # PoE per latent element: 4 x (mu, logvar) in (the constant prior is never read) + noise; mu^, logvar^, z out;
     # backward: the same 32 B + noise + g_z in, 32 B of gradients out.  One launch per step covers the 4 latent levels.
     bytes_per_step = {"poe_fwd": n_lat * (32 + 4 + 12), "poe_bwd": n_lat * (32 + 4 + 4 + 32)}
@@ -543,7 +554,7 @@ def run_gpu(args):
                "avg_launch_ms": round(ms / cnt, 5), "peak_source": peaks["src"]}
         if name in impl_bytes_per_launch:
             hbm["implementation_bytes_per_launch"] = int(impl_bytes_per_launch[name])
-            hbm["note_bytes"] = "algorithmic = minimum bytes (bf16 operands / results, fp32 gates); implementation bytes add carried states and fp32 gradient rows"
+            hbm["note_bytes"] = "algorithmic = minimum bytes (bf16 operands / intermediates / results, fp32 gates and x / y); implementation bytes add carried states, the saved xm and whatever is still fp32 between kernels"
         if not nflop:
             return hbm
         # cell kernels: both roofs side by side -- HBM on minimum bytes (frac) and bf16 tensor peak on useful FLOP (tensor_frac)

@@ -156,12 +156,13 @@ int xhved_mlstm_fwd(const void* q_tiles, const void* k_tiles, const void* v_tile
                     float* ws_g, float* ws_amax, void* states, float* m_prev, void* stream);
 
 /* Backward.  dh_tiles: bf16 tiles of dL/dh.  states/m_prev/m/den/h_tiles as produced by the forward.
- * Outputs: dq, dk, dv fp32 (BH, nc*128, dhp) row-major; dig, dfg fp32 (BH, nc*128).
+ * Outputs: dq, dk, dv as bf16 tiles in the layout of q, k, v (their consumers -- xhved_vil_pre_bwd, the weight-gradient
+ * MMAs -- take bf16 operands; xhved_mlstm_unpack turns them into fp32 (BH,S,dh)); dig, dfg fp32 (BH, nc*128).
  * Scratch: ws_dstate/ws_g/ws_amax as in the forward, rstates bf16 2*BH*nc*dhp*(dhp+16), mu_next fp32 BH*nc,
  * ws_dc fp32 (BH, nc*128).  The (~1e-6 relative) gradient through the row-max stabiliser is dropped. */
 int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig_padded, const float* fg_padded,
                     const void* h_tiles, const void* dh_tiles, const float* m, const float* den, const void* states,
-                    const float* m_prev, int BH, int nc, int dh, int dhp, float eps, float* dq, float* dk, float* dv, float* dig,
+                    const float* m_prev, int BH, int nc, int dh, int dhp, float eps, void* dq, void* dk, void* dv, float* dig,
                     float* dfg, float* ws_dstate, float* ws_g, float* ws_amax, void* rstates, float* mu_next, float* ws_dc,
                     void* stream);
 
@@ -169,28 +170,28 @@ int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const void* v_tile
 int xhved_mlstm_pack(const float* src /* (BH,S,dh) */, int BH, int S, int dh, int dhp, void* tiles, void* stream);
 int xhved_mlstm_pack_gates(const float* ig, const float* fg /* (BH,S) */, int BH, int S, float* ig_padded, float* fg_padded, void* stream);
 int xhved_mlstm_unpack(const void* tiles, int BH, int S, int dh, int dhp, float* dst /* (BH,S,dh) */, void* stream);
-/* fp32 (BH, nc*128, dhp) row-major -> (BH, S, dh) contiguous (gradients of the stand-alone entry point) */
-int xhved_mlstm_unpad_rows(const float* src, int BH, int S, int dh, int dhp, float* dst, void* stream);
 
 /* Sizes of the caller-allocated buffers (host-only queries, no device needed).  The library never allocates: outputs, saved
  * state and scratch are passed in, and these two functions are the single source of truth for how large they must be.
- *   tile_bytes    each of q, k, v, h, dh tiles                 (BH * nc * 128 * dhp bf16)
+ *   tile_bytes    each of q, k, v, h, dh, dq, dk, dv tiles     (BH * nc * 128 * dhp bf16)
  *   row_bytes     each of ig, fg, m, den, dig, dfg, ws_dc       (BH * nc * 128 fp32)
  *   dstate_bytes  ws_dstate                                     (BH * nc * dhp * (dhp+16) fp32)
  *   chunk_bytes   each of ws_g, ws_amax, m_prev, mu_next        (BH * nc fp32)
- *   states_bytes  each of states, rstates                       (BH * nc bf16 hi/lo pairs of dhp * (dhp+16))
- *   grad_bytes    each of dq, dk, dv                            (BH * nc * 128 * dhp fp32) */
+ *   states_bytes  each of states, rstates                       (BH * nc bf16 hi/lo pairs of dhp * (dhp+16)) */
 typedef struct {
   int nc, dhp;
-  int64_t tile_bytes, row_bytes, dstate_bytes, chunk_bytes, states_bytes, grad_bytes;
+  int64_t tile_bytes, row_bytes, dstate_bytes, chunk_bytes, states_bytes;
 } xhved_mlstm_workspace;
 int xhved_mlstm_workspace_query(int BH, int S, int dh, xhved_mlstm_workspace* out);
 /* ViL block of width C on B sequences of S tokens: its cell runs with BH = 4*B, dh = C/2;
- *   token_minor_bytes   each of act, z, xm, d_act, dz, ws_dconv, ws_dxmv   (B * nc * 2C * 128 fp32)
+ *   token_minor_bytes   each of act, z, xm                                  (B * nc * 2C * 128 fp32, saved by the forward)
+ *   token_tile_bytes    each of d_act, dz, ws_dconv, ws_dxmv                (B * nc bf16 "token tiles" [128][2C]: the backward's
+ *                       kernel-to-kernel tensors, tile-native layout with R = 128 tokens, tile index b*nc + chunk)
  *   grad_replica_stride floats per replica of the flat parameter-gradient buffer (sum of the 14 parameter sizes, padded) */
 typedef struct {
   xhved_mlstm_workspace cell;
   int64_t token_minor_bytes;
+  int64_t token_tile_bytes;
   int64_t grad_replica_stride;
 } xhved_vil_workspace;
 int xhved_vil_workspace_query(int B, int S, int C, xhved_vil_workspace* out);
@@ -273,18 +274,20 @@ int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, const xhved_vil
 /* K3: outnorm(h) + skip*act, * silu(z), proj_down, + x residual -> y (same geometry family as x). */
 int xhved_vil_post_fwd(const float* x, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
                        const xhved_vil_shape* sh, float* y, void* stream);
-/* K3 backward: from dy computes dh (bf16 tiles), d_act_skip, dz (fp32 (B,nc,E,128)), dx_residual is dy itself;
- * accumulates outnorm / skip / proj_down gradients. */
+/* K3 backward: from dy computes dh (bf16 tiles), d_act_skip, dz (bf16 token tiles [128][E], token_tile_bytes each),
+ * dx_residual is dy itself; accumulates outnorm / skip / proj_down gradients. */
 int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
-                       const xhved_vil_shape* sh, void* dh_tiles, float* d_act, float* dz, const xhved_vil_grads* g, void* stream);
-/* K2 backward: from the forward's saved xm, dq, dk, dv (fp32 (BH, nc*128, dhp)), dig, dfg (padded), d_act (skip path) and
- * dz computes dx = dy + d(branch)/dx (dy and dx both use the y_* strides of sh) and accumulates parameter gradients.
- * q_tiles / k_tiles / v_tiles are accepted for ABI stability and not read: the gate-weight gradient is taken through the
- * block-diagonal projections ([dig|dfg]^T q = ([dig|dfg]^T act) Wq^T).  Scratch: ws_dconv, ws_dxmv fp32 (B, nc, E, 128) each. */
+                       const xhved_vil_shape* sh, void* dh_tiles, void* d_act, void* dz, const xhved_vil_grads* g, void* stream);
+/* K2 backward: from the forward's saved xm, the cell's dq, dk, dv (bf16 tiles), dig, dfg (padded), d_act (skip path) and
+ * dz (bf16 token tiles) computes dx = dy + d(branch)/dx (dy and dx both use the y_* strides of sh) and accumulates parameter
+ * gradients.  q_tiles / k_tiles / v_tiles are accepted for ABI stability and not read: the gate-weight gradient is taken
+ * through the block-diagonal projections ([dig|dfg]^T q = ([dig|dfg]^T act) Wq^T).  Scratch: ws_dconv, ws_dxmv, bf16 token
+ * tiles (token_tile_bytes each).  Every kernel-to-kernel tensor of the backward is bf16: its consumers round to bf16 MMA
+ * operands anyway, and the fp32 versions were 2.9 KB of HBM traffic per token and block. */
 int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const void* q_tiles, const void* k_tiles, const void* v_tiles,
-                      const float* dq, const float* dk, const float* dv, const float* dig, const float* dfg, const float* d_act,
-                      const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx, const xhved_vil_grads* g,
-                      float* ws_dconv, float* ws_dxmv, void* stream);
+                      const void* dq, const void* dk, const void* dv, const float* dig, const float* dfg, const void* d_act,
+                      const void* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx, const xhved_vil_grads* g,
+                      void* ws_dconv, void* ws_dxmv, void* stream);
 
 /* One whole ViL block per call (ViLBlock.forward, vision_lstm.py:494-502, and its backward): K2 -> cell -> K3 enqueued on
  * `stream` into caller-allocated blobs.  xhved_vil_block_workspace reports the blob sizes: `saved` is written by the forward

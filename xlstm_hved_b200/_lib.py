@@ -54,11 +54,12 @@ class PoeOpts(Structure):             # xhved_poe_opts
 
 class MlstmWorkspace(Structure):      # xhved_mlstm_workspace
     _fields_ = [("nc", c_int), ("dhp", c_int), ("tile_bytes", c_int64), ("row_bytes", c_int64), ("dstate_bytes", c_int64),
-                ("chunk_bytes", c_int64), ("states_bytes", c_int64), ("grad_bytes", c_int64)]
+                ("chunk_bytes", c_int64), ("states_bytes", c_int64)]
 
 
 class VilWorkspaceSizes(Structure):   # xhved_vil_workspace
-    _fields_ = [("cell", MlstmWorkspace), ("token_minor_bytes", c_int64), ("grad_replica_stride", c_int64)]
+    _fields_ = [("cell", MlstmWorkspace), ("token_minor_bytes", c_int64), ("token_tile_bytes", c_int64),
+                ("grad_replica_stride", c_int64)]
 
 
 # every symbol include/xhved.h declares -> argtypes (None = not yet bound with a signature)
@@ -84,7 +85,6 @@ SYMBOLS = {
     "xhved_mlstm_pack": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_mlstm_pack_gates": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_unpack": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
-    "xhved_mlstm_unpad_rows": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "xhved_mlstm_workspace_query": [c_int, c_int, c_int, POINTER(MlstmWorkspace)],
     "xhved_vil_workspace_query": [c_int, c_int, c_int, POINTER(VilWorkspaceSizes)],
     "xhved_profile_enable": [c_int],

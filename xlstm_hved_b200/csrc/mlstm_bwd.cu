@@ -26,12 +26,12 @@ int launch_state_scan(int dhp, const float* dstate, const float* g, const float*
                       float* m_prev, cudaStream_t st);
 int launch_chunk_grad_ws(int dhp, const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig,
                          const float* fg, const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
-                         const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
+                         const float* mu_next, int BH, int nc, float scale, float eps, void* dq, void* dk, void* dv, float* dig,
                          float* dc, float* dc_tot, cudaStream_t st);
 
 int launch_chunk_grad_wide(const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig, const float* fg,
                            const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
-                           const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
+                           const float* mu_next, int BH, int nc, float scale, float eps, void* dq, void* dk, void* dv, float* dig,
                            float* dc, float* dc_tot, cudaStream_t st);
 
 // Which chunk_grad kernel runs: the persistent kernel with balanced roles and P^T in tensor memory (mlstm_bwd_ws.cu) where it
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_grad_kernel(
     const unsigned char* __restrict__ h_tiles, const unsigned char* __restrict__ dh_tiles, const float* __restrict__ ig,
     const float* __restrict__ fg, const float* __restrict__ m_in, const float* __restrict__ den_in,
     const unsigned char* __restrict__ states, const float* __restrict__ m_prev, const unsigned char* __restrict__ rstates,
-    const float* __restrict__ mu_next, int nc, float scale, float eps, float* __restrict__ dq, float* __restrict__ dk,
-    float* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out, float* __restrict__ dc_tot) {
+    const float* __restrict__ mu_next, int nc, float scale, float eps, unsigned char* __restrict__ dq, unsigned char* __restrict__ dk,
+    unsigned char* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out, float* __restrict__ dc_tot) {
   using L = BwdSmem<DHP>;
   constexpr int NE = L::NE;
   constexpr uint32_t TILE = L::TILE, ST1 = L::ST, ST_BYTES = 2 * L::ST;   // hi + lo tiles
@@ -329,9 +329,10 @@ __global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_grad_kernel(
   }
   // ---- epilogue: combine intra/inter, write dq/dk/dv rows, gate-gradient dot products; one pass per product ----
   float q_dq = 0.f, k_dk = 0.f;
-  float* dq_row = dq + grow * DHP;
-  float* dk_row = dk + grow * DHP;
-  float* dv_row = dv + grow * DHP;
+  // dq / dk / dv leave as bf16 tiles in the layout of q / k / v
+  unsigned char* dq_t = dq + static_cast<size_t>(tile) * TILE;
+  unsigned char* dk_t = dk + static_cast<size_t>(tile) * TILE;
+  unsigned char* dv_t = dv + static_cast<size_t>(tile) * TILE;
   if (hsel == 0) {
   mbar_wait(&bar_q, 0);
   tc_fence_after();
@@ -351,8 +352,7 @@ __global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_grad_kernel(
 #pragma unroll
       for (int i = 0; i < 8; ++i) q_dq += f[i] * a[half * 8 + i];
     }
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dq_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+    store16_bf16_tile(dq_t, kL, tid, c0, a);
   }
   mbar_wait(&bar_k, 0);
   tc_fence_after();
@@ -372,8 +372,7 @@ __global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_grad_kernel(
 #pragma unroll
       for (int i = 0; i < 8; ++i) k_dk += f[i] * a[half * 8 + i];
     }
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dk_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+    store16_bf16_tile(dk_t, kL, tid, c0, a);
   }
   dig[grow] = k_dk;
   } else {
@@ -388,8 +387,7 @@ __global__ void __launch_bounds__(2 * kThreads) mlstm_chunk_grad_kernel(
 #pragma unroll
       for (int i = 0; i < 16; ++i) a[i] += fac * bb[i];
     }
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dv_row + c0 + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+    store16_bf16_tile(dv_t, kL, tid, c0, a);
   }
   }
   {
@@ -425,21 +423,10 @@ __global__ void __launch_bounds__(kThreads) mlstm_gate_finish_kernel(const float
   dfg[o] = (dc_suffix[o] + carry) * (1.f / (1.f + __expf(fg[o])));
 }
 
-// fp32 (BH, nc*128, dhp) -> (BH, S, dh)
-__global__ void mlstm_unpad_rows_kernel(const float* __restrict__ src, int S, int Sp, int dh, int dhp, float* __restrict__ dst, size_t total) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int d = i % dh;
-  const size_t row = i / dh;
-  const int t = row % S;
-  const size_t bh = row / S;
-  dst[i] = src[(bh * Sp + t) * dhp + d];
-}
-
 template <int DHP>
 static int launch_bwd(const void* q, const void* k, const void* v, const float* ig, const float* fg, const void* h, const void* dh_t,
                       const float* m, const float* den, const void* states, const float* m_prev, int BH, int nc, int dh, float eps,
-                      float* dq, float* dk, float* dv, float* dig, float* dfg, float* ws_dstate, float* ws_g, float* ws_lam,
+                      void* dq, void* dk, void* dv, float* dig, float* dfg, float* ws_dstate, float* ws_g, float* ws_lam,
                       void* rstates, float* mu_next, float* ws_dc, cudaStream_t st) {
   constexpr int NE = ext_cols(DHP);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
@@ -470,7 +457,8 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
     ProfScope ps(K_CHUNK_GRAD, st);
     mlstm_chunk_grad_kernel<DHP><<<ntiles, 2 * kThreads, smem, st>>>(
         (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, (const unsigned char*)h, (const unsigned char*)dh_t, ig, fg,
-        m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, scale, eps, dq, dk, dv, dig, ws_dc,
+        m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, scale, eps, (unsigned char*)dq,
+        (unsigned char*)dk, (unsigned char*)dv, dig, ws_dc,
         ws_lam /* free again after the reverse scan: receives the per-chunk totals of dc */);
   }
   {
@@ -486,7 +474,7 @@ using namespace xhved;
 
 extern "C" int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const void* v_tiles, const float* ig, const float* fg,
                                const void* h_tiles, const void* dh_tiles, const float* m, const float* den, const void* states,
-                               const float* m_prev, int BH, int nc, int dh, int dhp, float eps, float* dq, float* dk, float* dv, float* dig,
+                               const float* m_prev, int BH, int nc, int dh, int dhp, float eps, void* dq, void* dk, void* dv, float* dig,
                                float* dfg, float* ws_dstate, float* ws_g, float* ws_amax, void* rstates, float* mu_next, float* ws_dc,
                                void* stream) {
   if (BH <= 0 || nc <= 0 || dh <= 0 || dh > dhp) return XHVED_ERR_BAD_SHAPE;
@@ -498,13 +486,4 @@ extern "C" int xhved_mlstm_bwd(const void* q_tiles, const void* k_tiles, const v
     case 128: return launch_bwd<128>(q_tiles, k_tiles, v_tiles, ig, fg, h_tiles, dh_tiles, m, den, states, m_prev, BH, nc, dh, eps, dq, dk, dv, dig, dfg, ws_dstate, ws_g, ws_amax, rstates, mu_next, ws_dc, st);
     default: return XHVED_ERR_UNSUPPORTED_DH;
   }
-}
-
-extern "C" int xhved_mlstm_unpad_rows(const float* src, int BH, int S, int dh, int dhp, float* dst, void* stream) {
-  if (BH <= 0 || S <= 0 || dh <= 0 || dh > dhp) return XHVED_ERR_BAD_SHAPE;
-  const int Sp = (S + kL - 1) / kL * kL;
-  const size_t total = static_cast<size_t>(BH) * S * dh;
-  ProfScope ps(K_UNPACK, static_cast<cudaStream_t>(stream));
-  mlstm_unpad_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, S, Sp, dh, dhp, dst, total);
-  return (int)cudaGetLastError();
 }

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlstm_chunk_grad_wide_kernel(
     const unsigned char* __restrict__ h_tiles, const unsigned char* __restrict__ dh_tiles, const float* __restrict__ ig,
     const float* __restrict__ fg, const float* __restrict__ m_in, const float* __restrict__ den_in,
     const unsigned char* __restrict__ states, const float* __restrict__ m_prev, const unsigned char* __restrict__ rstates,
-    const float* __restrict__ mu_next, int nc, int ntiles, float scale, float eps, float* __restrict__ dout, float* __restrict__ dig,
+    const float* __restrict__ mu_next, int nc, int ntiles, float scale, float eps, unsigned char* __restrict__ dout, float* __restrict__ dig,
     float* __restrict__ dc_out, float* __restrict__ dc_tot) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* aux = reinterpret_cast<float*>(smem + OFF_AUX);
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlstm_chunk_grad_wide_kernel(
       mbar_wait(&bar_m2, it & 1);
       tc_fence_after();
       float dot = 0.f;
-      float* orow = dout + grow * DHP;
+      unsigned char* otile = dout + static_cast<size_t>(tile) * TILE;      // bf16 tile in the layout of q / k / v
 #pragma unroll 1
       for (int c0 = 0; c0 < DHP; c0 += 16) {
         uint32_t a[16], bb[16];
@@ -345,8 +345,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlstm_chunk_grad_wide_kernel(
             for (int i = 0; i < 8; ++i) dot += qv[i] * f[half * 8 + i];
           }
         }
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        store16_bf16_tile(otile, kL, r, c0, f);
       }
       tc_fence_before();
       mbar_arrive(&bar_tfree);
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlstm_chunk_grad_wide_kernel(
 template <int PART>
 static int launch_part(const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig, const float* fg,
                        const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
-                       const float* mu_next, int BH, int nc, float scale, float eps, float* dout, float* dig, float* dc, float* dc_tot,
+                       const float* mu_next, int BH, int nc, float scale, float eps, void* dout, float* dig, float* dc, float* dc_tot,
                        cudaStream_t st) {
   const int ntiles = BH * nc;
   cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_grad_wide_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -392,7 +391,8 @@ static int launch_part(const void* q, const void* k, const void* v, const void* 
   const int grid = ntiles < sm_count_cached() ? ntiles : sm_count_cached();
   mlstm_chunk_grad_wide_kernel<PART><<<grid, NTHREADS, SMEM, st>>>(
       (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, (const unsigned char*)h, (const unsigned char*)dh_t, ig, fg,
-      m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, ntiles, scale, eps, dout, dig, dc, dc_tot);
+      m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, ntiles, scale, eps, (unsigned char*)dout, dig, dc,
+      dc_tot);
   return (int)cudaGetLastError();
 }
 
@@ -401,7 +401,7 @@ static int launch_part(const void* q, const void* k, const void* v, const void* 
 // phase B3 of the backward at dhp = 128: three part-kernels (dQ, then dK -- which consumes q.dQ --, then dV)
 int launch_chunk_grad_wide(const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig, const float* fg,
                            const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
-                           const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
+                           const float* mu_next, int BH, int nc, float scale, float eps, void* dq, void* dk, void* dv, float* dig,
                            float* dc, float* dc_tot, cudaStream_t st) {
   ProfScope ps(K_CHUNK_GRAD, st);
   if (int rc = wide::launch_part<wide::PART_Q>(q, k, v, h, dh_t, ig, fg, m, den, states, m_prev, rstates, mu_next, BH, nc, scale, eps, dq,

@@ -107,8 +107,9 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
     const unsigned char* __restrict__ h_tiles, const unsigned char* __restrict__ dh_tiles, const float* __restrict__ ig,
     const float* __restrict__ fg, const float* __restrict__ m_in, const float* __restrict__ den_in,
     const unsigned char* __restrict__ states, const float* __restrict__ m_prev, const unsigned char* __restrict__ rstates,
-    const float* __restrict__ mu_next, int nc, int ntiles, float scale, float eps, float* __restrict__ dq, float* __restrict__ dk,
-    float* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out, float* __restrict__ dc_tot) {
+    const float* __restrict__ mu_next, int nc, int ntiles, float scale, float eps, unsigned char* __restrict__ dq,
+    unsigned char* __restrict__ dk, unsigned char* __restrict__ dv, float* __restrict__ dig, float* __restrict__ dc_out,
+    float* __restrict__ dc_tot) {
   using C = GradWs<DHP>;
   constexpr int NE = C::NE, NSTAGE = C::NSTAGE;
   constexpr bool PIPE = C::PIPE;
@@ -355,8 +356,9 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
       mbar_wait(&bar_ma, it & 1);
       tc_fence_after();
       float q_dq = 0.f, k_dk = 0.f;
-      float* dq_row = dq + grow * DHP;
-      float* dk_row = dk + grow * DHP;
+      // dq / dk / dv leave as bf16 tiles in the layout of q / k / v (the consumer, vil_pre_bwd_a, rounds them to bf16 operands anyway)
+      unsigned char* dq_t = dq + static_cast<size_t>(tile) * TILE;
+      unsigned char* dk_t = dk + static_cast<size_t>(tile) * TILE;
 #pragma unroll 1
       for (int c0 = 0; c0 < DHP; c0 += 16) {
         float f[16];
@@ -368,8 +370,7 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
 #pragma unroll
           for (int i = 0; i < 8; ++i) q_dq += qv[i] * f[half * 8 + i];
         }
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dq_row + c0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        store16_bf16_tile(dq_t, kL, r, c0, f);
         load_combine16(tmem + lane_base + C::T_DKI + c0, tmem + lane_base + C::T_DKX + c0, has_next, fac_cur, f);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -378,8 +379,7 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
 #pragma unroll
           for (int i = 0; i < 8; ++i) k_dk += kv[i] * f[half * 8 + i];
         }
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dk_row + c0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        store16_bf16_tile(dk_t, kL, r, c0, f);
       }
       tc_fence_before();
       mbar_arrive(&bar_tfree);
@@ -424,7 +424,6 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
       const int tile = blockIdx.x + it * gridDim.x;
       const int c = tile % nc;
       const bool has_next = c < nc - 1;
-      const size_t grow = static_cast<size_t>(tile) * kL + r;
       const float* ab = aux + (it & 1) * C::A_BUF;
       if (!PIPE) build_g(it);
       mbar_wait(&bar_prep, it & 1);          // the scans of this tile are published
@@ -479,13 +478,12 @@ __global__ void __launch_bounds__(GradWs<DHP>::NTHREADS, GradWs<DHP>::CTAS_PER_S
       // ---- epilogue: dV row of this lane ----
       mbar_wait(&bar_mb, it & 1);
       tc_fence_after();
-      float* dv_row = dv + grow * DHP;
+      unsigned char* dv_t = dv + static_cast<size_t>(tile) * TILE;
 #pragma unroll 1
       for (int c0 = 0; c0 < DHP; c0 += 16) {
         float f[16];
         load_combine16(tmem + lane_base + C::T_DVI + c0, tmem + lane_base + C::T_DVX + c0, has_next, fac, f);
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dv_row + c0 + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        store16_bf16_tile(dv_t, kL, r, c0, f);
       }
       tc_fence_before();
       mbar_arrive(&bar_tfree);
@@ -501,7 +499,7 @@ int sm_count_cached();
 template <int DHP>
 static int launch_grad_ws(const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig, const float* fg,
                           const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
-                          const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
+                          const float* mu_next, int BH, int nc, float scale, float eps, void* dq, void* dk, void* dv, float* dig,
                           float* dc, float* dc_tot, cudaStream_t st) {
   using C = GradWs<DHP>;
   const int ntiles = BH * nc;
@@ -512,15 +510,15 @@ static int launch_grad_ws(const void* q, const void* k, const void* v, const voi
   ProfScope ps(K_CHUNK_GRAD, st);
   mlstm_chunk_grad_ws_kernel<DHP><<<grid, C::NTHREADS, C::SMEM, st>>>(
       (const unsigned char*)q, (const unsigned char*)k, (const unsigned char*)v, (const unsigned char*)h, (const unsigned char*)dh_t, ig, fg,
-      m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, ntiles, scale, eps, dq, dk, dv, dig, dc,
-      dc_tot);
+      m, den, (const unsigned char*)states, m_prev, (const unsigned char*)rstates, mu_next, nc, ntiles, scale, eps, (unsigned char*)dq,
+      (unsigned char*)dk, (unsigned char*)dv, dig, dc, dc_tot);
   return (int)cudaGetLastError();
 }
 
 // phase B3 of the backward on the persistent kernel; dhp in {16, 32, 64}
 int launch_chunk_grad_ws(int dhp, const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig,
                          const float* fg, const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
-                         const float* mu_next, int BH, int nc, float scale, float eps, float* dq, float* dk, float* dv, float* dig,
+                         const float* mu_next, int BH, int nc, float scale, float eps, void* dq, void* dk, void* dv, float* dig,
                          float* dc, float* dc_tot, cudaStream_t st) {
   switch (dhp) {
     case 16: return launch_grad_ws<16>(q, k, v, h, dh_t, ig, fg, m, den, states, m_prev, rstates, mu_next, BH, nc, scale, eps, dq, dk, dv, dig, dc, dc_tot, st);

@@ -504,6 +504,12 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y, v[4] = c.x, v[5] = c.y, v[6] = d.x, v[7] = d.y;
 }
+// 16 fp32 values of row r, columns c0 .. c0+15, rounded to bf16 into a tile-native tile of R rows in GLOBAL memory: two
+// 16-byte groups; the 32 rows of a warp cover 512 contiguous bytes per group
+__device__ __forceinline__ void store16_bf16_tile(unsigned char* tile, int R, int r, int c0, const float* f) {
+  *reinterpret_cast<uint4*>(tile + tile_off16(R, r, c0 / 8)) = pack8_bf16(f);
+  *reinterpret_cast<uint4*>(tile + tile_off16(R, r, c0 / 8 + 1)) = pack8_bf16(f + 8);
+}
 
 // Stage a row-major fp32 matrix W[rows][cols] (global) as tile-native bf16 hi (+ optional lo) tiles with R = rows_tile
 // rows (rows beyond `rows` are zero-filled).  Cooperative over the CTA.  cols % 8 == 0.

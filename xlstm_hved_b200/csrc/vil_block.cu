@@ -45,8 +45,8 @@ struct Saved {
 };
 
 struct Scratch {
-  float *flat, *d_act, *dz, *dq, *dk, *dv, *dig, *dfg, *mu_next, *ws_dc, *ws_dconv, *ws_dxmv;
-  void *dh_tiles, *rstates;
+  float *flat, *dig, *dfg, *mu_next, *ws_dc;
+  void *dh_tiles, *rstates, *d_act, *dz, *dq, *dk, *dv, *ws_dconv, *ws_dxmv;      // bf16 tiles
   int64_t flat_bytes, bytes;
   Scratch(void* blob, const xhved_vil_workspace& w, int replicas) {
     Carver c(blob);
@@ -54,11 +54,11 @@ struct Scratch {
     flat_bytes = static_cast<int64_t>(replicas) * w.grad_replica_stride * 4;
     flat = c.take<float>(flat_bytes);
     dh_tiles = c.take<void>(cw.tile_bytes), rstates = c.take<void>(cw.states_bytes);
-    d_act = c.take<float>(w.token_minor_bytes), dz = c.take<float>(w.token_minor_bytes);
-    dq = c.take<float>(cw.grad_bytes), dk = c.take<float>(cw.grad_bytes), dv = c.take<float>(cw.grad_bytes);
+    d_act = c.take<void>(w.token_tile_bytes), dz = c.take<void>(w.token_tile_bytes);
+    dq = c.take<void>(cw.tile_bytes), dk = c.take<void>(cw.tile_bytes), dv = c.take<void>(cw.tile_bytes);
     dig = c.take<float>(cw.row_bytes), dfg = c.take<float>(cw.row_bytes), mu_next = c.take<float>(cw.chunk_bytes);
     ws_dc = c.take<float>(cw.row_bytes);
-    ws_dconv = c.take<float>(w.token_minor_bytes), ws_dxmv = c.take<float>(w.token_minor_bytes);
+    ws_dconv = c.take<void>(w.token_tile_bytes), ws_dxmv = c.take<void>(w.token_tile_bytes);
     bytes = c.off;
   }
 };

@@ -341,7 +341,8 @@ template <int C>
 __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
                                                                  const float* __restrict__ act, const float* __restrict__ z,
                                                                  xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
-                                                                 float* __restrict__ d_act, float* __restrict__ dz, xhved_vil_grads gr_base) {
+                                                                 unsigned char* __restrict__ d_act, unsigned char* __restrict__ dz,
+                                                                 xhved_vil_grads gr_base) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, head)
   using L = PostBwdTC<C>;
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
   const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
+  const size_t tt_base = (static_cast<size_t>(b) * g.nc + ch) * E * (kTok * 2);      // this tile's bf16 token tiles (dz, d_act)
   const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
   // all per-token global loads first: their latency overlaps the parameter staging below
   HeadInputs<DH> in;
@@ -409,21 +411,29 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
     tmem_ld8(tmem + lane_base + head * DH, dhg);
   }
   float gg[DH], r1[DH], r2[DH], mean_g = 0.f, mean_gx = 0.f;
+  // dz and the skip-path d_act leave as bf16 token tiles [128][E] (their consumers stage them as bf16 operands anyway)
 #pragma unroll
-  for (int d = 0; d < DH; ++d) {
-    const int e = head * DH + d;
-    const float a = in.a[d], zz = in.z[d];
-    float sz, dsz;
-    silu_both(zz, sz, dsz);
-    const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
-    const float dhs = valid ? dhg[d] * sz : 0.f;
-    dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsz : 0.f;
-    d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sk[d];
-    r1[d] = dhs * a;
-    r2[d] = dhs * xhat[d];
-    gg[d] = dhs * (1.f + ow[d]);
-    mean_g += gg[d];
-    mean_gx += gg[d] * xhat[d];
+  for (int cg = 0; cg < DH / 8; ++cg) {
+    float dz8[8], da8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int d = cg * 8 + i;
+      const float a = in.a[d], zz = in.z[d];
+      float sz, dsz;
+      silu_both(zz, sz, dsz);
+      const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
+      const float dhs = valid ? dhg[d] * sz : 0.f;
+      dz8[i] = valid ? dhg[d] * hs * dsz : 0.f;
+      da8[i] = dhs * sk[d];
+      r1[d] = dhs * a;
+      r2[d] = dhs * xhat[d];
+      gg[d] = dhs * (1.f + ow[d]);
+      mean_g += gg[d];
+      mean_gx += gg[d] * xhat[d];
+    }
+    const size_t o = tt_base + tile_off16(kTok, tok, head * (DH / 8) + cg);
+    *reinterpret_cast<uint4*>(dz + o) = pack8_bf16(dz8);
+    *reinterpret_cast<uint4*>(d_act + o) = pack8_bf16(da8);
   }
   mean_g *= (1.f / DH);
   mean_gx *= (1.f / DH);
@@ -512,8 +522,9 @@ template <int C>
 __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
                                                                             const float* __restrict__ act, const float* __restrict__ z,
                                                                             xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
-                                                                            float* __restrict__ d_act, float* __restrict__ dz,
-                                                                            xhved_vil_grads gr_base, int ntiles) {
+                                                                            unsigned char* __restrict__ d_act,
+                                                                            unsigned char* __restrict__ dz, xhved_vil_grads gr_base,
+                                                                            int ntiles) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
   using L = PostBwdPersist<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP;
@@ -575,7 +586,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const
     if (tid == 0 && nxt < ntiles) issue(nxt, s ^ 1);
     const int b = tile / g.nc, ch = tile % g.nc;
     const bool valid = ch * kTok + tok < g.S;
-    const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;
+    const size_t tt_base = static_cast<size_t>(tile) * E * (kTok * 2);      // this tile's bf16 token tiles (dz, d_act)
     if (it > 0) {     // the previous tile's weight-gradient product still reads the dy and gated tiles
       mbar_wait(&bar2, (it - 1) & 1);
       tc_fence_after();
@@ -615,21 +626,29 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const
       tmem_ld8(tmem + lane_base + head * DH, dhg);
     }
     float gg[DH], r1[DH], r2[DH], mean_g = 0.f, mean_gx = 0.f;
+    // dz and the skip-path d_act leave as bf16 token tiles [128][E] (their consumers stage them as bf16 operands anyway)
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      const int e = head * DH + d;
-      const float a = in.a[d], zz = in.z[d];
-      float sz, dsz;
-      silu_both(zz, sz, dsz);
-      const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
-      const float dhs = valid ? dhg[d] * sz : 0.f;
-      dz[tm_base + static_cast<size_t>(e) * kTok] = valid ? dhg[d] * hs * dsz : 0.f;
-      d_act[tm_base + static_cast<size_t>(e) * kTok] = dhs * sk[d];
-      r1[d] = dhs * a;
-      r2[d] = dhs * xhat[d];
-      gg[d] = dhs * (1.f + ow[d]);
-      mean_g += gg[d];
-      mean_gx += gg[d] * xhat[d];
+    for (int cg = 0; cg < DH / 8; ++cg) {
+      float dz8[8], da8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int d = cg * 8 + i;
+        const float a = in.a[d], zz = in.z[d];
+        float sz, dsz;
+        silu_both(zz, sz, dsz);
+        const float hs = xhat[d] * (1.f + ow[d]) + sk[d] * a;
+        const float dhs = valid ? dhg[d] * sz : 0.f;
+        dz8[i] = valid ? dhg[d] * hs * dsz : 0.f;
+        da8[i] = dhs * sk[d];
+        r1[d] = dhs * a;
+        r2[d] = dhs * xhat[d];
+        gg[d] = dhs * (1.f + ow[d]);
+        mean_g += gg[d];
+        mean_gx += gg[d] * xhat[d];
+      }
+      const size_t o = tt_base + tile_off16(kTok, tok, head * (DH / 8) + cg);
+      *reinterpret_cast<uint4*>(dz + o) = pack8_bf16(dz8);
+      *reinterpret_cast<uint4*>(d_act + o) = pack8_bf16(da8);
     }
     mean_g *= (1.f / DH);
     mean_gx *= (1.f / DH);
@@ -701,25 +720,26 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const
 
 template <int C>
 static int launch_post_bwd_persist(const float* dy, const void* h, const float* act, const float* z, const xhved_vil_params* p,
-                                   const VilGeom& g, void* dh, float* d_act, float* dz, const xhved_vil_grads* gr, cudaStream_t st) {
+                                   const VilGeom& g, void* dh, void* d_act, void* dz, const xhved_vil_grads* gr, cudaStream_t st) {
   const size_t smem = PostBwdPersist<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_persist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int ntiles = g.B * g.nc;
   ProfScope ps(K_VIL_POST_BWD, st);
   vil_post_bwd_persist_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g,
-                                                                                    (unsigned char*)dh, d_act, dz, *gr, ntiles);
+                                                                                    (unsigned char*)dh, (unsigned char*)d_act, (unsigned char*)dz, *gr, ntiles);
   return (int)cudaGetLastError();
 }
 
 template <int C>
 static int launch_post_bwd(const float* dy, const void* h, const float* act, const float* z, const xhved_vil_params* p, const VilGeom& g,
-                           void* dh, float* d_act, float* dz, const xhved_vil_grads* gr, cudaStream_t st) {
+                           void* dh, void* d_act, void* dz, const xhved_vil_grads* gr, cudaStream_t st) {
   const size_t smem = PostBwdTC<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_BWD, st);
-  vil_post_bwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g, (unsigned char*)dh, d_act, dz, *gr);
+  vil_post_bwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g, (unsigned char*)dh,
+                                                             (unsigned char*)d_act, (unsigned char*)dz, *gr);
   return (int)cudaGetLastError();
 }
 
@@ -742,7 +762,7 @@ extern "C" int xhved_vil_post_fwd(const float* x, const void* h_tiles, const flo
 }
 
 extern "C" int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
-                                  const xhved_vil_shape* sh, void* dh_tiles, float* d_act, float* dz, const xhved_vil_grads* g,
+                                  const xhved_vil_shape* sh, void* dh_tiles, void* d_act, void* dz, const xhved_vil_grads* g,
                                   void* stream) {
   VilGeom geo;
   if (int rc = vil_validate(sh, &geo)) return rc;

@@ -325,9 +325,9 @@ struct PreBwdBTC {
 template <int C>
 __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                                         xhved_vil_params p, VilGeom g,
-                                                                                        const float* __restrict__ dconv,
-                                                                                        const float* __restrict__ dxmv,
-                                                                                        const float* __restrict__ dz, float* __restrict__ dx,
+                                                                                        const unsigned char* __restrict__ dconv,
+                                                                                        const unsigned char* __restrict__ dxmv,
+                                                                                        const unsigned char* __restrict__ dz, float* __restrict__ dx,
                                                                                         xhved_vil_grads gr_base, int ntiles) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, part).  Every part owns CP channels of its token for the LayerNorm (statistics are
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int b = tile / g.nc, ch = tile % g.nc;
-    const size_t tm_chunk = static_cast<size_t>(tile) * E * kTok;
+    constexpr size_t TT = static_cast<size_t>(E) * kTok * 2;      // one [128][E] bf16 token tile
     const int tau = ch * kTok + tok;
     const bool valid = tau < g.S;
     const int n = g.reverse ? g.S - 1 - tau : tau;
@@ -405,26 +405,32 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_bwd_b_tc_
     }
     // ---- d[x_mlstm | z] row: transposed causal conv of dconv over tokens tau..tau+3 (vision_lstm.py:213-221) + the v path
     // the four taps read dconv of tokens tau..tau+3: this tile, or the first tokens of the next tile of the same sequence
-    const float* pk[4];
+    const unsigned char* pk[4];
     bool vk[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int t = tok + k;
       vk[k] = tau + k < g.S;
-      pk[k] = dconv + static_cast<size_t>(tile + (vk[k] ? (t >> 7) : 0)) * E * kTok + (t & (kTok - 1));
+      pk[k] = dconv + static_cast<size_t>(tile + (vk[k] ? (t >> 7) : 0)) * TT + (t & (kTok - 1)) * 16;
     }
-    const float* px = dxmv + tm_chunk + tok;
-    const float* pz = dz + tm_chunk + tok;
+    const unsigned char* px = dxmv + static_cast<size_t>(tile) * TT + tok * 16;
+    const unsigned char* pz = dz + static_cast<size_t>(tile) * TT + tok * 16;
     // every pass handles 8 conv channels and 8 z channels of this token, with all of their loads issued together
 #pragma unroll 1
     for (int o8 = part * 8; o8 < E; o8 += 32) {
       float dc[4][8], dzv[8], dxv[8];
+      {
+        const uint32_t cgo = static_cast<uint32_t>(o8 / 8) * (kTok * 16);      // column group o8/8 of the token tiles
+        uint4 u[6];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k) u[k] = vk[k] ? __ldg(reinterpret_cast<const uint4*>(pk[k] + cgo)) : make_uint4(0u, 0u, 0u, 0u);
+        u[4] = __ldg(reinterpret_cast<const uint4*>(px + cgo));
+        u[5] = __ldg(reinterpret_cast<const uint4*>(pz + cgo));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dc[k][i] = vk[k] ? __ldg(pk[k] + (o8 + i) * kTok) : 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dxv[i] = __ldg(px + (o8 + i) * kTok), dzv[i] = __ldg(pz + (o8 + i) * kTok);
+        for (int k = 0; k < 4; ++k) unpack8_bf16(u[k], dc[k]);
+        unpack8_bf16(u[4], dxv);
+        unpack8_bf16(u[5], dzv);
+      }
       float d8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -546,22 +552,25 @@ struct PreBwdATC {
   // per-group parameter slices and accumulators (restaged / flushed every sweep); the gate-bias sums once
   static constexpr int P_CW = 0, P_CB = EG * 4, P_WQ = P_CB + EG, P_WK = P_WQ + EG * 4, P_WV = P_WK + EG * 4, A_CW = P_WV + EG * 4,
                        A_CB = A_CW + EG * 4, A_GB = A_CB + EG, P_N = A_GB + 8;
-  // token-minor input blocks staged by bulk async copies: x_mlstm (two stages, each followed by the EG x 4 floats of the
-  // 3 tokens in front of the chunk) and d_act (one stage), EG x 128 fp32 each
-  static constexpr uint32_t BLK = EG * kTok * 4, HX_BYTES = EG * 4 * 4, XM_STRIDE = BLK + HX_BYTES;
+  // input blocks staged by bulk async copies: x_mlstm (token-minor fp32, two stages, each followed by the EG x 4 floats of the
+  // 3 tokens in front of the chunk) and d_act (one stage; a bf16 token tile, EG x 128 x 2 bytes)
+  static constexpr uint32_t BLK = EG * kTok * 4, HX_BYTES = EG * 4 * 4, XM_STRIDE = BLK + HX_BYTES, DA_BLK = EG * kTok * 2;
   static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + 2 * XM_STRIDE;
-  static constexpr uint32_t TOTAL = IN_DA + BLK;
+  static constexpr uint32_t TOTAL = IN_DA + DA_BLK;
   static constexpr uint32_t T_GQ = 0, T_DWQK = NQ, T_DWV = NQ + EG, T_DWGA = NQ + 2 * EG, T_DWGX = NQ + 3 * EG;
   static_assert(NQ + 4 * EG <= 512 && 2 * EG <= 128 && TOTAL <= 227 * 1024, "kernel A: a channel group must fit TMEM and shared memory");
 };
 
 template <int C>
 __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
-                                                                        const float* __restrict__ dq, const float* __restrict__ dk,
-                                                                        const float* __restrict__ dv, const float* __restrict__ dig,
-                                                                        const float* __restrict__ dfg, const float* __restrict__ d_act,
-                                                                        float* __restrict__ dconv_out, float* __restrict__ dxmv_out,
-                                                                        xhved_vil_grads gr_base, int ntiles) {
+                                                                        const unsigned char* __restrict__ dq,
+                                                                        const unsigned char* __restrict__ dk,
+                                                                        const unsigned char* __restrict__ dv, const float* __restrict__ dig,
+                                                                        const float* __restrict__ dfg,
+                                                                        const unsigned char* __restrict__ d_act,
+                                                                        unsigned char* __restrict__ dconv_out,
+                                                                        unsigned char* __restrict__ dxmv_out, xhved_vil_grads gr_base,
+                                                                        int ntiles) {
   const xhved_vil_grads gr = replica_of(gr_base, g);
   // 512 threads: thread = (token, quarter of the channel group); the four quarters of a token share its TMEM lane.
   // Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ... (once per channel group).  All parameter gradients
@@ -584,8 +593,9 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     bulk_g2s(smem + L::IN_XM + s * L::XM_STRIDE, xm + (static_cast<size_t>(tile) * E + ch0) * kTok, L::BLK, &bar_xm[s]);
   };
   auto issue_da = [&](int tile) {
-    mbar_expect_tx(&bar_da, L::BLK);
-    bulk_g2s(smem + L::IN_DA, d_act + (static_cast<size_t>(tile) * E + ch0) * kTok, L::BLK, &bar_da);
+    // channels ch0 .. ch0+EG of the [128][E] bf16 token tile are EG/8 consecutive 2 KB column groups
+    mbar_expect_tx(&bar_da, L::DA_BLK);
+    bulk_g2s(smem + L::IN_DA, d_act + (static_cast<size_t>(tile) * E + ch0) * (kTok * 2), L::DA_BLK, &bar_da);
   };
   // x_mlstm of the 3 tokens in front of chunk `tile` (zeros in front of the sequence) -> behind stage s
   auto load_halo = [&](int tile, int s) {
@@ -702,10 +712,10 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         mbar_wait(&bar2, (it - 1) & 1);
         tc_fence_after();
       }
-      const size_t tm_base = (static_cast<size_t>(tile) * E + ch0) * kTok + tok;
+      const size_t tt_base = (static_cast<size_t>(tile) * E + ch0) * (kTok * 2);      // this group's columns of the token tile
       const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE);
       const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE + L::BLK);
-      const float* s_da = reinterpret_cast<const float*>(smem + L::IN_DA);
+      const unsigned char* s_da = smem + L::IN_DA;
       bool first = true;
 #pragma unroll
       for (int e8 = quarter * CPT; e8 < (quarter + 1) * CPT; e8 += 8) {      // channel within the group
@@ -725,15 +735,10 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
               xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
         }
         float gq[8], gk[8], gv[8], dsk[8];
-        const size_t row = ((static_cast<size_t>(b) * 4 + hd0 + lh) * g.Sp + ch * kTok + tok) * DHP + d0;
-        {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(dq + row)), c = __ldg(reinterpret_cast<const float4*>(dq + row + 4));
-          gq[0] = a.x, gq[1] = a.y, gq[2] = a.z, gq[3] = a.w, gq[4] = c.x, gq[5] = c.y, gq[6] = c.z, gq[7] = c.w;
-          const float4 a2 = __ldg(reinterpret_cast<const float4*>(dk + row)), c2 = __ldg(reinterpret_cast<const float4*>(dk + row + 4));
-          gk[0] = a2.x, gk[1] = a2.y, gk[2] = a2.z, gk[3] = a2.w, gk[4] = c2.x, gk[5] = c2.y, gk[6] = c2.z, gk[7] = c2.w;
-          const float4 a3 = __ldg(reinterpret_cast<const float4*>(dv + row)), c3 = __ldg(reinterpret_cast<const float4*>(dv + row + 4));
-          gv[0] = a3.x, gv[1] = a3.y, gv[2] = a3.z, gv[3] = a3.w, gv[4] = c3.x, gv[5] = c3.y, gv[6] = c3.z, gv[7] = c3.w;
-        }
+        // the cell's dq / dk / dv: bf16 tiles in the layout of q / k / v (one 16-byte group per thread, 512 B per warp)
+        const size_t gt = ((static_cast<size_t>(b) * 4 + hd0 + lh) * g.nc + ch) * (kTok * DHP * 2) + tile_off16(kTok, tok, d0 / 8);
+        const uint4 uq = __ldg(reinterpret_cast<const uint4*>(dq + gt)), uk = __ldg(reinterpret_cast<const uint4*>(dk + gt)),
+                    uv = __ldg(reinterpret_cast<const uint4*>(dv + gt));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int e = e8 + j;
@@ -748,8 +753,10 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
           mbar_wait(&bar_da, it & 1);
           first = false;
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dsk[j] = s_da[(e8 + j) * kTok + tok];
+        unpack8_bf16(*reinterpret_cast<const uint4*>(s_da + tile_off16(kTok, tok, e8 / 8)), dsk);
+        unpack8_bf16(uq, gq);
+        unpack8_bf16(uk, gk);
+        unpack8_bf16(uv, gv);
         float t8[8];
         tmem_ld8(tmem + lane_base + L::T_GQ + (0 * HG + lh) * DHP + d0, t8);
 #pragma unroll
@@ -778,15 +785,15 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         float dc8[8], prod[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int e = e8 + j;
           float ds;
           silu_both(cv8[j], a8[j], ds);
           dc8[j] = valid ? (da8[j] + dsk[j]) * ds : 0.f;
-          dconv_out[tm_base + static_cast<size_t>(e) * kTok] = dc8[j];
-          dxmv_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? dxv8[j] : 0.f;
+          dxv8[j] = valid ? dxv8[j] : 0.f;
 #pragma unroll
           for (int k = 0; k < 4; ++k) prod[j * 4 + k] = dc8[j] * xr[k][j];
         }
+        *reinterpret_cast<uint4*>(dconv_out + tt_base + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(dc8);
+        *reinterpret_cast<uint4*>(dxmv_out + tt_base + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(dxv8);
         warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
         warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
         // operands of the weight-gradient GEMMs (bf16)
@@ -900,18 +907,20 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
 }
 
 template <int C>
-static int launch_pre_bwd(const float* x, const float* dy, const float* xm, const void* q, const void* k, const void* v, const float* dq,
-                          const float* dk, const float* dv, const float* dig, const float* dfg, const float* d_act, const float* dz,
-                          const xhved_vil_params* p, const VilGeom& g, float* dx, const xhved_vil_grads* gr, float* ws_dconv,
-                          float* ws_dxmv, cudaStream_t st) {
+static int launch_pre_bwd(const float* x, const float* dy, const float* xm, const void* q, const void* k, const void* v, const void* dq,
+                          const void* dk, const void* dv, const float* dig, const float* dfg, const void* d_act, const void* dz,
+                          const xhved_vil_params* p, const VilGeom& g, float* dx, const xhved_vil_grads* gr, void* ws_dconv,
+                          void* ws_dxmv, cudaStream_t st) {
+  auto u8 = [](const void* v_) { return static_cast<const unsigned char*>(v_); };
   {
     const size_t smem = PreBwdATC<C>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(vil_pre_bwd_a_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_A, st);
     const int ntiles = g.B * g.nc;
-    vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, xm, dq, dk, dv, dig, dfg, d_act, ws_dconv, ws_dxmv,
-                                                                                  *gr, ntiles);
+    vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, xm, u8(dq), u8(dk), u8(dv), dig, dfg, u8(d_act),
+                                                                                  static_cast<unsigned char*>(ws_dconv),
+                                                                                  static_cast<unsigned char*>(ws_dxmv), *gr, ntiles);
   }
   {
     const size_t smem = PreBwdBTC<C>::TOTAL;
@@ -919,8 +928,8 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_B, st);
     const int ntiles = g.B * g.nc;
-    vil_pre_bwd_b_tc_kernel<C><<<persistent_grid(ntiles, C <= 32 ? 2 : 1), 4 * kTok, smem, st>>>(x, dy, *p, g, ws_dconv, ws_dxmv, dz, dx, *gr,
-                                                                                                ntiles);
+    vil_pre_bwd_b_tc_kernel<C><<<persistent_grid(ntiles, C <= 32 ? 2 : 1), 4 * kTok, smem, st>>>(x, dy, *p, g, u8(ws_dconv), u8(ws_dxmv), u8(dz), dx,
+                                                                                                *gr, ntiles);
   }
   return (int)cudaGetLastError();
 }
@@ -944,9 +953,9 @@ extern "C" int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, cons
 }
 
 extern "C" int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const void* q_tiles, const void* k_tiles,
-                                 const void* v_tiles, const float* dq, const float* dk, const float* dv, const float* dig, const float* dfg,
-                                 const float* d_act, const float* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx,
-                                 const xhved_vil_grads* g, float* ws_dconv, float* ws_dxmv, void* stream) {
+                                 const void* v_tiles, const void* dq, const void* dk, const void* dv, const float* dig, const float* dfg,
+                                 const void* d_act, const void* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx,
+                                 const xhved_vil_grads* g, void* ws_dconv, void* ws_dxmv, void* stream) {
   VilGeom geo;
   if (int rc = vil_validate(sh, &geo)) return rc;
   if (!x || !dy || !xm || !q_tiles || !k_tiles || !v_tiles || !dq || !dk || !dv || !dig || !dfg || !d_act || !dz || !p || !dx || !g ||

@@ -349,9 +349,10 @@ class CellGradBuffers:
         nt = buf.BH * buf.nc
         ne = buf.dhp + 16
         e = lambda *s, dtype=torch.float32: torch.empty(*s, device=dev, dtype=dtype)
-        self.dq = e(buf.BH, buf.Sp, buf.dhp)
-        self.dk = e(buf.BH, buf.Sp, buf.dhp)
-        self.dv = e(buf.BH, buf.Sp, buf.dhp)
+        # bf16 tiles in the layout of q / k / v (xhved.h: xhved_mlstm_bwd)
+        self.dq = torch.empty_like(buf.q)
+        self.dk = torch.empty_like(buf.q)
+        self.dv = torch.empty_like(buf.q)
         self.dig = e(buf.BH, buf.Sp)
         self.dfg = e(buf.BH, buf.Sp)
         self.rstates = e(nt, 2 * buf.dhp * ne, dtype=torch.bfloat16)
@@ -370,12 +371,11 @@ def mlstm_bwd_tiles(buf: CellBuffers, dh_tiles: torch.Tensor, eps: float = 1e-6)
     return gb
 
 
-def _unpad_rows(src, BH, S, dh, dhp, shape):
-    if dh == dhp and S % CHUNK == 0:
-        return src.view(shape)                     # nothing is padded: the kernel's output IS the (B, NH, S, DH) tensor
+def _unpack_grad(tiles, BH, S, dh, dhp, shape):
+    """bf16 gradient tiles -> fp32 (B, NH, S, DH) (the stand-alone cell entry point returns what autograd expects)."""
     lib = _lib.load_library()
-    dst = torch.empty(shape, device=src.device, dtype=torch.float32)
-    check(lib.xhved_mlstm_unpad_rows(ptr(src), BH, S, dh, dhp, ptr(dst), stream()), "xhved_mlstm_unpad_rows")
+    dst = torch.empty(shape, device=tiles.device, dtype=torch.float32)
+    check(lib.xhved_mlstm_unpack(ptr(tiles), BH, S, dh, dhp, ptr(dst), stream()), "xhved_mlstm_unpack")
     return dst
 
 
@@ -401,9 +401,9 @@ class MLSTMCellFunction(torch.autograd.Function):
         dh_c = _f32c(dh)
         check(lib.xhved_mlstm_pack(ptr(dh_c), buf.BH, S, DH, buf.dhp, ptr(dh_tiles), stream()), "xhved_mlstm_pack")
         gb = mlstm_bwd_tiles(buf, dh_tiles, ctx.eps)
-        dq = _unpad_rows(gb.dq, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
-        dk = _unpad_rows(gb.dk, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
-        dv = _unpad_rows(gb.dv, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
+        dq = _unpack_grad(gb.dq, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
+        dk = _unpack_grad(gb.dk, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
+        dv = _unpack_grad(gb.dv, buf.BH, S, DH, buf.dhp, (B, NH, S, DH))
         dig = gb.dig.view(B, NH, buf.Sp)[:, :, :S].unsqueeze(-1).contiguous()
         dfg = gb.dfg.view(B, NH, buf.Sp)[:, :, :S].unsqueeze(-1).contiguous()
         return dq, dk, dv, dig, dfg, None
