@@ -499,7 +499,7 @@ def run_gpu(args):
         "vil_pre_bwd_a": E * 2 + 3 * E * 2 + 8 * 4 + E * 2 + 2 * E * 2,               # xm, dq,dk,dv, dgates, d_act in; dconv, dxmv out
         "vil_pre_bwd_b": 4 * DIM + 4 * DIM + 3 * E * 2 + 4 * DIM,                     # x, dy, dconv, dxmv, dz in; dx out
     }
-    ACT_B = 4                                                                         # bytes per element of the saved act / z / xm
+    ACT_B = 2                                                                         # bytes per element of the saved act / z / xm
     impl_token_bytes = {
         "vil_pre_fwd": 4 * DIM + 3 * E * 2 + 8 * 4 + 3 * E * ACT_B,                   # ... + xm saved for the backward
         "vil_post_fwd": E * 2 + 2 * E * ACT_B + 4 * DIM + 4 * DIM,

@@ -184,13 +184,12 @@ typedef struct {
 } xhved_mlstm_workspace;
 int xhved_mlstm_workspace_query(int BH, int S, int dh, xhved_mlstm_workspace* out);
 /* ViL block of width C on B sequences of S tokens: its cell runs with BH = 4*B, dh = C/2;
- *   token_minor_bytes   each of act, z, xm                                  (B * nc * 2C * 128 fp32, saved by the forward)
- *   token_tile_bytes    each of d_act, dz, ws_dconv, ws_dxmv                (B * nc bf16 "token tiles" [128][2C]: the backward's
- *                       kernel-to-kernel tensors, tile-native layout with R = 128 tokens, tile index b*nc + chunk)
+ *   token_tile_bytes    each of act, z, xm, d_act, dz, ws_dconv, ws_dxmv    (B * nc bf16 "token tiles" [128][2C]: every
+ *                       kernel-to-kernel tensor over the E = 2C inner channels, tile-native layout with R = 128 tokens of one
+ *                       chunk in traversal order, tile index b*nc + chunk)
  *   grad_replica_stride floats per replica of the flat parameter-gradient buffer (sum of the 14 parameter sizes, padded) */
 typedef struct {
   xhved_mlstm_workspace cell;
-  int64_t token_minor_bytes;
   int64_t token_tile_bytes;
   int64_t grad_replica_stride;
 } xhved_vil_workspace;
@@ -267,24 +266,24 @@ typedef struct xhved_vil_shape {
 } xhved_vil_shape;
 
 /* K2: LayerNorm -> proj_up -> causal conv -> SiLU -> q,k,v (tiles) + gates (padded) + act, z, xm.
- * act (conv activation), z (gate branch), xm (pre-conv x_mlstm, kept for the backward): fp32 (B, nc, E, 128) token-minor,
- * traversal order. */
+ * act (conv activation), z (gate branch), xm (pre-conv x_mlstm, kept for the backward): bf16 token tiles (SURVEY 8d counts
+ * the block's intermediates as bf16: 12 C + 16 E + 8 NH bytes per token for K2 + K3 forward). */
 int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, const xhved_vil_shape* sh, void* q_tiles, void* k_tiles,
-                      void* v_tiles, float* ig_padded, float* fg_padded, float* act, float* z, float* xm, void* stream);
+                      void* v_tiles, float* ig_padded, float* fg_padded, void* act, void* z, void* xm, void* stream);
 /* K3: outnorm(h) + skip*act, * silu(z), proj_down, + x residual -> y (same geometry family as x). */
-int xhved_vil_post_fwd(const float* x, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
+int xhved_vil_post_fwd(const float* x, const void* h_tiles, const void* act, const void* z, const xhved_vil_params* p,
                        const xhved_vil_shape* sh, float* y, void* stream);
 /* K3 backward: from dy computes dh (bf16 tiles), d_act_skip, dz (bf16 token tiles [128][E], token_tile_bytes each),
  * dx_residual is dy itself; accumulates outnorm / skip / proj_down gradients. */
-int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
+int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const void* act, const void* z, const xhved_vil_params* p,
                        const xhved_vil_shape* sh, void* dh_tiles, void* d_act, void* dz, const xhved_vil_grads* g, void* stream);
 /* K2 backward: from the forward's saved xm, the cell's dq, dk, dv (bf16 tiles), dig, dfg (padded), d_act (skip path) and
  * dz (bf16 token tiles) computes dx = dy + d(branch)/dx (dy and dx both use the y_* strides of sh) and accumulates parameter
  * gradients.  q_tiles / k_tiles / v_tiles are accepted for ABI stability and not read: the gate-weight gradient is taken
  * through the block-diagonal projections ([dig|dfg]^T q = ([dig|dfg]^T act) Wq^T).  Scratch: ws_dconv, ws_dxmv, bf16 token
  * tiles (token_tile_bytes each).  Every kernel-to-kernel tensor of the backward is bf16: its consumers round to bf16 MMA
- * operands anyway, and the fp32 versions were 2.9 KB of HBM traffic per token and block. */
-int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const void* q_tiles, const void* k_tiles, const void* v_tiles,
+ * operands anyway, and the fp32 versions were 2.9 KB of HBM traffic per token and block (dim 32). */
+int xhved_vil_pre_bwd(const float* x, const float* dy, const void* xm, const void* q_tiles, const void* k_tiles, const void* v_tiles,
                       const void* dq, const void* dk, const void* dv, const float* dig, const float* dfg, const void* d_act,
                       const void* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx, const xhved_vil_grads* g,
                       void* ws_dconv, void* ws_dxmv, void* stream);

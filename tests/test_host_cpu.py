@@ -154,7 +154,7 @@ def test_workspace_queries_match_the_host_layer():
         assert w.cell.tile_bytes == 4 * B * nc * 128 * dhp * 2
         assert w.cell.row_bytes == 4 * B * nc * 128 * 4 and w.cell.chunk_bytes == 4 * B * nc * 4
         assert w.cell.dstate_bytes == 4 * B * nc * dhp * (dhp + 16) * 4 == w.cell.states_bytes
-        assert w.token_minor_bytes == B * nc * E * 128 * 4 and w.token_tile_bytes == B * nc * E * 128 * 2
+        assert w.token_tile_bytes == B * nc * E * 128 * 2
         blk = xh.ViLBlock(dim, xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
         n_params = sum(p.numel() for p in xh.modules.vil_block_params(blk))
         assert w.grad_replica_stride == (n_params + 31) // 32 * 32
@@ -162,7 +162,7 @@ def test_workspace_queries_match_the_host_layer():
         sv, sc, npg = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         assert lib.xhved_vil_block_workspace(B, S, dim, 32, ctypes.byref(sv), ctypes.byref(sc), ctypes.byref(npg)) == 0
         assert npg.value == n_params
-        assert sv.value >= 4 * w.cell.tile_bytes + w.cell.states_bytes + 4 * w.cell.row_bytes + w.cell.dstate_bytes + 3 * w.token_minor_bytes
+        assert sv.value >= 4 * w.cell.tile_bytes + w.cell.states_bytes + 4 * w.cell.row_bytes + w.cell.dstate_bytes + 3 * w.token_tile_bytes
         assert sc.value >= 32 * w.grad_replica_stride * 4 + 4 * w.cell.tile_bytes + w.cell.states_bytes + 4 * w.token_tile_bytes
     bad = _lib.MlstmWorkspace()
     assert lib.xhved_mlstm_workspace_query(4, 100, 200, ctypes.byref(bad)) == -2      # XHVED_ERR_UNSUPPORTED_DH

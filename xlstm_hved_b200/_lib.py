@@ -58,8 +58,7 @@ class MlstmWorkspace(Structure):      # xhved_mlstm_workspace
 
 
 class VilWorkspaceSizes(Structure):   # xhved_vil_workspace
-    _fields_ = [("cell", MlstmWorkspace), ("token_minor_bytes", c_int64), ("token_tile_bytes", c_int64),
-                ("grad_replica_stride", c_int64)]
+    _fields_ = [("cell", MlstmWorkspace), ("token_tile_bytes", c_int64), ("grad_replica_stride", c_int64)]
 
 
 # every symbol include/xhved.h declares -> argtypes (None = not yet bound with a signature)

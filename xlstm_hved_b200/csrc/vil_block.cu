@@ -28,8 +28,8 @@ struct Carver {
 
 // everything the backward needs from the forward, plus the forward's own scratch (dstate / g / amax are reused by the backward)
 struct Saved {
-  void *q, *k, *v, *h, *states;
-  float *ig, *fg, *m, *den, *ws_dstate, *ws_g, *ws_amax, *m_prev, *act, *z, *xm;
+  void *q, *k, *v, *h, *states, *act, *z, *xm;      // act / z / xm: bf16 token tiles
+  float *ig, *fg, *m, *den, *ws_dstate, *ws_g, *ws_amax, *m_prev;
   int64_t bytes;
   Saved(void* blob, const xhved_vil_workspace& w) {
     Carver c(blob);
@@ -39,7 +39,7 @@ struct Saved {
     ig = c.take<float>(cw.row_bytes), fg = c.take<float>(cw.row_bytes), m = c.take<float>(cw.row_bytes), den = c.take<float>(cw.row_bytes);
     ws_dstate = c.take<float>(cw.dstate_bytes), ws_g = c.take<float>(cw.chunk_bytes), ws_amax = c.take<float>(cw.chunk_bytes);
     m_prev = c.take<float>(cw.chunk_bytes);
-    act = c.take<float>(w.token_minor_bytes), z = c.take<float>(w.token_minor_bytes), xm = c.take<float>(w.token_minor_bytes);
+    act = c.take<void>(w.token_tile_bytes), z = c.take<void>(w.token_tile_bytes), xm = c.take<void>(w.token_tile_bytes);
     bytes = c.off;
   }
 };

@@ -27,18 +27,28 @@ template <int DH>
 struct HeadInputs {
   uint4 h[DH / 8];
   float a[DH], z[DH];
-  __device__ __forceinline__ void load(const unsigned char* h_tile, int r, const float* act, const float* zp, size_t stride) {
+  // act_tile / z_tile: the [128][E] bf16 token tiles of this chunk; cg0 = first 16-byte column group of this head
+  __device__ __forceinline__ void load(const unsigned char* h_tile, int r, const unsigned char* act_tile, const unsigned char* z_tile,
+                                       int cg0) {
+    uint4 ua[DH / 8], uz[DH / 8];
 #pragma unroll
-    for (int cg = 0; cg < DH / 8; ++cg) h[cg] = __ldg(reinterpret_cast<const uint4*>(h_tile + tile_off16(kTok, r, cg)));
+    for (int cg = 0; cg < DH / 8; ++cg) {
+      h[cg] = __ldg(reinterpret_cast<const uint4*>(h_tile + tile_off16(kTok, r, cg)));
+      ua[cg] = __ldg(reinterpret_cast<const uint4*>(act_tile + tile_off16(kTok, r, cg0 + cg)));
+      uz[cg] = __ldg(reinterpret_cast<const uint4*>(z_tile + tile_off16(kTok, r, cg0 + cg)));
+    }
 #pragma unroll
-    for (int d = 0; d < DH; ++d) a[d] = __ldg(act + d * stride), z[d] = __ldg(zp + d * stride);
+    for (int cg = 0; cg < DH / 8; ++cg) unpack8_bf16(ua[cg], a + cg * 8), unpack8_bf16(uz[cg], z + cg * 8);
   }
-  // the same inputs from a TMA-staged tile: [4 heads][kTok x DHP] h tiles, [E][kTok] act and z
-  __device__ __forceinline__ void load_smem(const unsigned char* h_tile, int r, const float* act, const float* zp) {
+  // the same inputs from a TMA-staged tile: [4 heads][kTok x DHP] h tiles, [128][E] act and z token tiles
+  __device__ __forceinline__ void load_smem(const unsigned char* h_tile, int r, const unsigned char* act_tile,
+                                            const unsigned char* z_tile, int cg0) {
 #pragma unroll
-    for (int cg = 0; cg < DH / 8; ++cg) h[cg] = *reinterpret_cast<const uint4*>(h_tile + tile_off16(kTok, r, cg));
-#pragma unroll
-    for (int d = 0; d < DH; ++d) a[d] = act[d * kTok], z[d] = zp[d * kTok];
+    for (int cg = 0; cg < DH / 8; ++cg) {
+      h[cg] = *reinterpret_cast<const uint4*>(h_tile + tile_off16(kTok, r, cg));
+      unpack8_bf16(*reinterpret_cast<const uint4*>(act_tile + tile_off16(kTok, r, cg0 + cg)), a + cg * 8);
+      unpack8_bf16(*reinterpret_cast<const uint4*>(z_tile + tile_off16(kTok, r, cg0 + cg)), z + cg * 8);
+    }
   }
   // hg = (norm(h)*(1+ow) + sk*a) * silu(z); optionally xhat and rstd (vision_lstm.py:271-287, 437, 440)
   __device__ __forceinline__ void gated(const float* ow, const float* sk, float* hg, float* xhat, float* rstd_out) const {
@@ -65,7 +75,8 @@ struct HeadInputs {
 
 template <int C>
 __global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __restrict__ x, const unsigned char* __restrict__ h_tiles,
-                                                                 const float* __restrict__ act, const float* __restrict__ z,
+                                                                 const unsigned char* __restrict__ act,
+                                                                 const unsigned char* __restrict__ z,
                                                                  xhved_vil_params p, VilGeom g, float* __restrict__ y) {
   // 512 threads: thread = (token, head)
   using L = PostTC<C>;
@@ -80,11 +91,11 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __r
   const int tau = ch * kTok + tok;
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
+  const size_t tt_base = (static_cast<size_t>(b) * g.nc + ch) * E * (kTok * 2);      // this chunk's bf16 token tiles
   // all per-token global loads first: their latency overlaps the parameter staging below
   HeadInputs<DH> in;
-  in.load(h_tiles + ((static_cast<size_t>(b) * 4 + head) * g.nc + ch) * (kTok * DHP * 2), tok,
-          act + tm_base + static_cast<size_t>(head * DH) * kTok, z + tm_base + static_cast<size_t>(head * DH) * kTok, kTok);
+  in.load(h_tiles + ((static_cast<size_t>(b) * 4 + head) * g.nc + ch) * (kTok * DHP * 2), tok, act + tt_base, z + tt_base,
+          head * (DH / 8));
   float xres[8 * ((C + 31) / 32)];
 #pragma unroll
   for (int it = 0; it < (C + 31) / 32; ++it)
@@ -150,13 +161,14 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_fwd_kernel(const float* __r
 }
 
 template <int C>
-static int launch_post_fwd(const float* x, const void* h, const float* act, const float* z, const xhved_vil_params* p, const VilGeom& g,
+static int launch_post_fwd(const float* x, const void* h, const void* act, const void* z, const xhved_vil_params* p, const VilGeom& g,
                            float* y, cudaStream_t st) {
   const size_t smem = PostTC<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_FWD, st);
-  vil_post_fwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y);
+  vil_post_fwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, (const unsigned char*)act, (const unsigned char*)z, *p,
+                                                             g, y);
   return (int)cudaGetLastError();
 }
 
@@ -167,7 +179,7 @@ static int launch_post_fwd(const float* x, const void* h, const float* act, cons
 template <int C>
 struct PostPersist {
   static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH;
-  static constexpr uint32_t ACT_BYTES = E * kTok * 4, H1_BYTES = kTok * DHP * 2, STAGE_BYTES = 2 * ACT_BYTES + 4 * H1_BYTES;
+  static constexpr uint32_t ACT_BYTES = E * kTok * 2, H1_BYTES = kTok * DHP * 2, STAGE_BYTES = 2 * ACT_BYTES + 4 * H1_BYTES;
   static constexpr uint32_t S_ACT = 0, S_Z = ACT_BYTES, S_H = 2 * ACT_BYTES;
   static constexpr uint32_t HG_BYTES = kTok * E * 2, WD_BYTES = C * E * 2;
   static constexpr uint32_t HGHI = 2 * STAGE_BYTES, HGLO = HGHI + HG_BYTES, WDHI = HGLO + HG_BYTES, WDLO = WDHI + WD_BYTES,
@@ -179,7 +191,8 @@ struct PostPersist {
 
 template <int C>
 __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const float* __restrict__ x, const unsigned char* __restrict__ h_tiles,
-                                                                            const float* __restrict__ act, const float* __restrict__ z,
+                                                                            const unsigned char* __restrict__ act,
+                                                                            const unsigned char* __restrict__ z,
                                                                             xhved_vil_params p, VilGeom g, float* __restrict__ y, int ntiles) {
   using L = PostPersist<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NX = 8 * ((C + 31) / 32);
@@ -193,8 +206,8 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
   auto issue = [&](int tile, int s) {
     unsigned char* st = smem + s * L::STAGE_BYTES;
     mbar_expect_tx(&bar_full[s], L::STAGE_BYTES);
-    bulk_g2s(st + L::S_ACT, act + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
-    bulk_g2s(st + L::S_Z, z + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
+    bulk_g2s(st + L::S_ACT, act + static_cast<size_t>(tile) * L::ACT_BYTES, L::ACT_BYTES, &bar_full[s]);
+    bulk_g2s(st + L::S_Z, z + static_cast<size_t>(tile) * L::ACT_BYTES, L::ACT_BYTES, &bar_full[s]);
     const int b = tile / g.nc, ch = tile % g.nc;
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd)
@@ -266,8 +279,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
     {
       const unsigned char* st = smem + s * L::STAGE_BYTES;
       HeadInputs<DH> in;
-      in.load_smem(st + L::S_H + head * L::H1_BYTES, tok, reinterpret_cast<const float*>(st + L::S_ACT) + head * DH * kTok + tok,
-                   reinterpret_cast<const float*>(st + L::S_Z) + head * DH * kTok + tok);
+      in.load_smem(st + L::S_H + head * L::H1_BYTES, tok, st + L::S_ACT, st + L::S_Z, head * (DH / 8));
       float hg[DH];
       in.gated(par + L::P_OW + head * DH, par + L::P_SK + head * DH, hg, nullptr, nullptr);
       if (it > 0) {       // the previous product has read the gated tile and filled its accumulator
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
 }
 
 template <int C>
-static int launch_post_fwd_persist(const float* x, const void* h, const float* act, const float* z, const xhved_vil_params* p,
+static int launch_post_fwd_persist(const float* x, const void* h, const void* act, const void* z, const xhved_vil_params* p,
                                    const VilGeom& g, float* y, cudaStream_t st) {
   const size_t smem = PostPersist<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_fwd_persist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -318,7 +330,8 @@ static int launch_post_fwd_persist(const float* x, const void* h, const float* a
   const int ntiles = g.B * g.nc;
   const int grid = persistent_grid(ntiles, 1);
   ProfScope ps(K_VIL_POST_FWD, st);
-  vil_post_fwd_persist_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, act, z, *p, g, y, ntiles);
+  vil_post_fwd_persist_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, (const unsigned char*)h, (const unsigned char*)act, (const unsigned char*)z,
+                                                               *p, g, y, ntiles);
   return (int)cudaGetLastError();
 }
 
@@ -339,7 +352,8 @@ struct PostBwdTC {
 
 template <int C>
 __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
-                                                                 const float* __restrict__ act, const float* __restrict__ z,
+                                                                 const unsigned char* __restrict__ act,
+                                                                 const unsigned char* __restrict__ z,
                                                                  xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
                                                                  unsigned char* __restrict__ d_act, unsigned char* __restrict__ dz,
                                                                  xhved_vil_grads gr_base) {
@@ -357,13 +371,11 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
   const int tau = ch * kTok + tok;
   const bool valid = tau < g.S;
   const int n = g.reverse ? g.S - 1 - tau : tau;
-  const size_t tm_base = (static_cast<size_t>(b) * g.nc + ch) * E * kTok + tok;
-  const size_t tt_base = (static_cast<size_t>(b) * g.nc + ch) * E * (kTok * 2);      // this tile's bf16 token tiles (dz, d_act)
+  const size_t tt_base = (static_cast<size_t>(b) * g.nc + ch) * E * (kTok * 2);      // this tile's bf16 token tiles (act, z, dz, d_act)
   const size_t tile = (static_cast<size_t>(b) * 4 + head) * g.nc + ch;
   // all per-token global loads first: their latency overlaps the parameter staging below
   HeadInputs<DH> in;
-  in.load(h_tiles + tile * (kTok * DHP * 2), tok, act + tm_base + static_cast<size_t>(head * DH) * kTok,
-          z + tm_base + static_cast<size_t>(head * DH) * kTok, kTok);
+  in.load(h_tiles + tile * (kTok * DHP * 2), tok, act + tt_base, z + tt_base, head * (DH / 8));
   if (tid == 0) {
     mbar_init(&bar1, 1);
     mbar_init(&bar2, 1);
@@ -506,7 +518,7 @@ __global__ void __launch_bounds__(4 * kTok) vil_post_bwd_kernel(const float* __r
 template <int C>
 struct PostBwdPersist {
   static constexpr int E = 2 * C, DH = E / 4, DHP = DH < 16 ? 16 : DH;
-  static constexpr uint32_t ACT_BYTES = E * kTok * 4, H1_BYTES = kTok * DHP * 2, STAGE_BYTES = 2 * ACT_BYTES + 4 * H1_BYTES;
+  static constexpr uint32_t ACT_BYTES = E * kTok * 2, H1_BYTES = kTok * DHP * 2, STAGE_BYTES = 2 * ACT_BYTES + 4 * H1_BYTES;
   static constexpr uint32_t S_ACT = 0, S_Z = ACT_BYTES, S_H = 2 * ACT_BYTES;
   static constexpr uint32_t HG_BYTES = kTok * E * 2, DY_BYTES = kTok * C * 2, WD_BYTES = C * E * 2, DHT_BYTES = 4 * H1_BYTES;
   // HG is read as a 128-row MN-major A operand through a 32 KB window that runs on over the tiles behind it
@@ -520,7 +532,8 @@ struct PostBwdPersist {
 
 template <int C>
 __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ h_tiles,
-                                                                            const float* __restrict__ act, const float* __restrict__ z,
+                                                                            const unsigned char* __restrict__ act,
+                                                                            const unsigned char* __restrict__ z,
                                                                             xhved_vil_params p, VilGeom g, unsigned char* __restrict__ dh_tiles,
                                                                             unsigned char* __restrict__ d_act,
                                                                             unsigned char* __restrict__ dz, xhved_vil_grads gr_base,
@@ -538,8 +551,8 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const
   auto issue = [&](int tile, int s) {
     unsigned char* st = smem + s * L::STAGE_BYTES;
     mbar_expect_tx(&bar_full[s], L::STAGE_BYTES);
-    bulk_g2s(st + L::S_ACT, act + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
-    bulk_g2s(st + L::S_Z, z + static_cast<size_t>(tile) * E * kTok, L::ACT_BYTES, &bar_full[s]);
+    bulk_g2s(st + L::S_ACT, act + static_cast<size_t>(tile) * L::ACT_BYTES, L::ACT_BYTES, &bar_full[s]);
+    bulk_g2s(st + L::S_Z, z + static_cast<size_t>(tile) * L::ACT_BYTES, L::ACT_BYTES, &bar_full[s]);
     const int b = tile / g.nc, ch = tile % g.nc;
 #pragma unroll
     for (int hd = 0; hd < 4; ++hd)
@@ -612,8 +625,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const
     mbar_wait(&bar_full[s], (it >> 1) & 1);
     const unsigned char* st = smem + s * L::STAGE_BYTES;
     HeadInputs<DH> in;
-    in.load_smem(st + L::S_H + head * L::H1_BYTES, tok, reinterpret_cast<const float*>(st + L::S_ACT) + head * DH * kTok + tok,
-                 reinterpret_cast<const float*>(st + L::S_Z) + head * DH * kTok + tok);
+    in.load_smem(st + L::S_H + head * L::H1_BYTES, tok, st + L::S_ACT, st + L::S_Z, head * (DH / 8));
     float hg[DH], xhat[DH], rstd;
     in.gated(ow, sk, hg, xhat, &rstd);
     mbar_wait(&bar1, it & 1);
@@ -719,26 +731,28 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_bwd_persist_kernel(const
 }
 
 template <int C>
-static int launch_post_bwd_persist(const float* dy, const void* h, const float* act, const float* z, const xhved_vil_params* p,
+static int launch_post_bwd_persist(const float* dy, const void* h, const void* act, const void* z, const xhved_vil_params* p,
                                    const VilGeom& g, void* dh, void* d_act, void* dz, const xhved_vil_grads* gr, cudaStream_t st) {
   const size_t smem = PostBwdPersist<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_persist_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int ntiles = g.B * g.nc;
   ProfScope ps(K_VIL_POST_BWD, st);
-  vil_post_bwd_persist_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g,
+  vil_post_bwd_persist_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, (const unsigned char*)act,
+                                                                                    (const unsigned char*)z, *p, g,
                                                                                     (unsigned char*)dh, (unsigned char*)d_act, (unsigned char*)dz, *gr, ntiles);
   return (int)cudaGetLastError();
 }
 
 template <int C>
-static int launch_post_bwd(const float* dy, const void* h, const float* act, const float* z, const xhved_vil_params* p, const VilGeom& g,
+static int launch_post_bwd(const float* dy, const void* h, const void* act, const void* z, const xhved_vil_params* p, const VilGeom& g,
                            void* dh, void* d_act, void* dz, const xhved_vil_grads* gr, cudaStream_t st) {
   const size_t smem = PostBwdTC<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_post_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_POST_BWD, st);
-  vil_post_bwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, act, z, *p, g, (unsigned char*)dh,
+  vil_post_bwd_kernel<C><<<g.B * g.nc, 4 * kTok, smem, st>>>(dy, (const unsigned char*)h, (const unsigned char*)act, (const unsigned char*)z, *p, g,
+                                                             (unsigned char*)dh,
                                                              (unsigned char*)d_act, (unsigned char*)dz, *gr);
   return (int)cudaGetLastError();
 }
@@ -747,7 +761,7 @@ static int launch_post_bwd(const float* dy, const void* h, const float* act, con
 
 using namespace xhved;
 
-extern "C" int xhved_vil_post_fwd(const float* x, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
+extern "C" int xhved_vil_post_fwd(const float* x, const void* h_tiles, const void* act, const void* z, const xhved_vil_params* p,
                                   const xhved_vil_shape* sh, float* y, void* stream) {
   VilGeom g;
   if (int rc = vil_validate(sh, &g)) return rc;
@@ -761,7 +775,7 @@ extern "C" int xhved_vil_post_fwd(const float* x, const void* h_tiles, const flo
   }
 }
 
-extern "C" int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const float* act, const float* z, const xhved_vil_params* p,
+extern "C" int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const void* act, const void* z, const xhved_vil_params* p,
                                   const xhved_vil_shape* sh, void* dh_tiles, void* d_act, void* dz, const xhved_vil_grads* g,
                                   void* stream) {
   VilGeom geo;

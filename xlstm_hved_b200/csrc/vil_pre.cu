@@ -45,8 +45,9 @@ template <int C>
 __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_fwd_kernel(const float* __restrict__ x, xhved_vil_params p, VilGeom g,
                                                                 unsigned char* __restrict__ q_tiles, unsigned char* __restrict__ k_tiles,
                                                                 unsigned char* __restrict__ v_tiles, float* __restrict__ igp,
-                                                                float* __restrict__ fgp, float* __restrict__ act_out,
-                                                                float* __restrict__ z_out, float* __restrict__ xm_out, int ntiles) {
+                                                                float* __restrict__ fgp, unsigned char* __restrict__ act_out,
+                                                                unsigned char* __restrict__ z_out, unsigned char* __restrict__ xm_out,
+                                                                int ntiles) {
   // 512 threads: thread = (token, head); head group 0 additionally owns the LayerNorm and the gate read-out of its token
   using L = PreTC<C>;
   constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NQ = L::NQ;
@@ -194,20 +195,18 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_fwd_kerne
     }
     mbar_wait(&bar1, it & 1);
     tc_fence_after();
-    const size_t tm_base = static_cast<size_t>(tile) * E * kTok + tok;   // token-minor (B, nc, E, 128)
+    const size_t tt_base = static_cast<size_t>(tile) * E * (kTok * 2);   // this chunk's [128][E] bf16 token tiles (act, z, xm)
     // this head's DH channels of x_mlstm (columns head*DH..) and of z (columns E + head*DH..)
 #pragma unroll
     for (int c0 = 0; c0 < DH; c0 += 8) {
       float v[8];
       tmem_ld8(tmem + lane_base + head * DH + c0, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        xm_s[(tok + 3) * L::XM_LD + head * DH + c0 + i] = v[i];
-        xm_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
-      }
+      for (int i = 0; i < 8; ++i) xm_s[(tok + 3) * L::XM_LD + head * DH + c0 + i] = v[i];
+      const size_t o = tt_base + tile_off16(kTok, tok, (head * DH + c0) / 8);
+      *reinterpret_cast<uint4*>(xm_out + o) = pack8_bf16(v);
       tmem_ld8(tmem + lane_base + E + head * DH + c0, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) z_out[tm_base + static_cast<size_t>(head * DH + c0 + i) * kTok] = v[i];
+      *reinterpret_cast<uint4*>(z_out + o) = pack8_bf16(v);
     }
     tc_fence_before();
     __syncthreads();   // x_mlstm of all tokens visible; the token rows are dead -> the QKV tile may overwrite them
@@ -224,7 +223,12 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_fwd_kerne
                            w.w * xm0[3 * L::XM_LD + e];
         a8[j] = silu(conv);
         xm8[j] = xm0[3 * L::XM_LD + e];
-        act_out[tm_base + static_cast<size_t>(e) * kTok] = valid ? a8[j] : 0.f;
+      }
+      {
+        float ao[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ao[j] = valid ? a8[j] : 0.f;
+        *reinterpret_cast<uint4*>(act_out + tt_base + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(ao);
       }
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
@@ -294,15 +298,15 @@ __global__ void __launch_bounds__(4 * kTok, (C <= 32 ? 2 : 1)) vil_pre_fwd_kerne
 
 template <int C>
 static int launch_pre_fwd(const float* x, const xhved_vil_params* p, const VilGeom& g, void* q, void* k, void* v, float* ig, float* fg,
-                          float* act, float* z, float* xm, cudaStream_t st) {
+                          void* act, void* z, void* xm, cudaStream_t st) {
   const size_t smem = PreTC<C>::TOTAL;
   cudaError_t e = cudaFuncSetAttribute(vil_pre_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   ProfScope ps(K_VIL_PRE_FWD, st);
   const int ntiles = g.B * g.nc;
   const int grid = PreTC<C>::PERSIST ? persistent_grid(ntiles, 2) : ntiles;
-  vil_pre_fwd_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg, act, z, xm,
-                                                      ntiles);
+  vil_pre_fwd_kernel<C><<<grid, 4 * kTok, smem, st>>>(x, *p, g, (unsigned char*)q, (unsigned char*)k, (unsigned char*)v, ig, fg,
+                                                      (unsigned char*)act, (unsigned char*)z, (unsigned char*)xm, ntiles);
   return (int)cudaGetLastError();
 }
 
@@ -552,9 +556,9 @@ struct PreBwdATC {
   // per-group parameter slices and accumulators (restaged / flushed every sweep); the gate-bias sums once
   static constexpr int P_CW = 0, P_CB = EG * 4, P_WQ = P_CB + EG, P_WK = P_WQ + EG * 4, P_WV = P_WK + EG * 4, A_CW = P_WV + EG * 4,
                        A_CB = A_CW + EG * 4, A_GB = A_CB + EG, P_N = A_GB + 8;
-  // input blocks staged by bulk async copies: x_mlstm (token-minor fp32, two stages, each followed by the EG x 4 floats of the
-  // 3 tokens in front of the chunk) and d_act (one stage; a bf16 token tile, EG x 128 x 2 bytes)
-  static constexpr uint32_t BLK = EG * kTok * 4, HX_BYTES = EG * 4 * 4, XM_STRIDE = BLK + HX_BYTES, DA_BLK = EG * kTok * 2;
+  // input blocks staged by bulk async copies (EG / 8 consecutive 2 KB column groups of a [128][E] bf16 token tile):
+  // x_mlstm (two stages, each followed by the EG x 4 floats of the 3 tokens in front of the chunk) and d_act (one stage)
+  static constexpr uint32_t BLK = EG * kTok * 2, HX_BYTES = EG * 4 * 4, XM_STRIDE = BLK + HX_BYTES, DA_BLK = EG * kTok * 2;
   static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + 2 * XM_STRIDE;
   static constexpr uint32_t TOTAL = IN_DA + DA_BLK;
   static constexpr uint32_t T_GQ = 0, T_DWQK = NQ, T_DWV = NQ + EG, T_DWGA = NQ + 2 * EG, T_DWGX = NQ + 3 * EG;
@@ -562,7 +566,7 @@ struct PreBwdATC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const float* __restrict__ xm,
+__global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil_params p, VilGeom g, const unsigned char* __restrict__ xm,
                                                                         const unsigned char* __restrict__ dq,
                                                                         const unsigned char* __restrict__ dk,
                                                                         const unsigned char* __restrict__ dv, const float* __restrict__ dig,
@@ -590,7 +594,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
 
   auto issue_xm = [&](int tile, int s) {
     mbar_expect_tx(&bar_xm[s], L::BLK);
-    bulk_g2s(smem + L::IN_XM + s * L::XM_STRIDE, xm + (static_cast<size_t>(tile) * E + ch0) * kTok, L::BLK, &bar_xm[s]);
+    bulk_g2s(smem + L::IN_XM + s * L::XM_STRIDE, xm + (static_cast<size_t>(tile) * E + ch0) * (kTok * 2), L::BLK, &bar_xm[s]);
   };
   auto issue_da = [&](int tile) {
     // channels ch0 .. ch0+EG of the [128][E] bf16 token tile are EG/8 consecutive 2 KB column groups
@@ -603,7 +607,14 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     const int ch = tile % g.nc;
     for (int i = tid; i < EG * 4; i += blockDim.x) {
       const int e = i >> 2, k = i & 3;
-      hx[i] = (k < 3 && ch > 0) ? __ldg(xm + (static_cast<size_t>(tile - 1) * E + ch0 + e) * kTok + kTok - 3 + k) : 0.f;
+      // element (row 125 + k, column ch0 + e) of the previous chunk's token tile
+      float hv = 0.f;
+      if (k < 3 && ch > 0) {
+        const unsigned short* src = reinterpret_cast<const unsigned short*>(xm + static_cast<size_t>(tile - 1) * E * (kTok * 2) +
+                                                                             tile_off16(kTok, kTok - 3 + k, (ch0 + e) / 8)) + ((ch0 + e) & 7);
+        hv = __uint_as_float(static_cast<uint32_t>(__ldg(src)) << 16);
+      }
+      hx[i] = hv;
     }
   };
   // [dig | dfg] of this token (quarter 0 only)
@@ -713,7 +724,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         tc_fence_after();
       }
       const size_t tt_base = (static_cast<size_t>(tile) * E + ch0) * (kTok * 2);      // this group's columns of the token tile
-      const float* s_xm = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE);
+      const unsigned char* s_xm = smem + L::IN_XM + s * L::XM_STRIDE;
       const float* s_hx = reinterpret_cast<const float*>(smem + L::IN_XM + s * L::XM_STRIDE + L::BLK);
       const unsigned char* s_da = smem + L::IN_DA;
       bool first = true;
@@ -724,15 +735,17 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         // x_mlstm of tokens tau-3+k; only the first warp of a quarter reaches into the halo in front of the chunk
         if ((tok & ~31) != 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) xr[k][j] = s_xm[(e8 + j) * kTok + tok - 3 + k];
+          for (int k = 0; k < 4; ++k) unpack8_bf16(*reinterpret_cast<const uint4*>(s_xm + tile_off16(kTok, tok - 3 + k, e8 / 8)), xr[k]);
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < 4; ++k) {
+            if (tok - 3 + k >= 0) {
+              unpack8_bf16(*reinterpret_cast<const uint4*>(s_xm + tile_off16(kTok, tok - 3 + k, e8 / 8)), xr[k]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              xr[k][j] = (tok - 3 + k >= 0) ? s_xm[(e8 + j) * kTok + tok - 3 + k] : s_hx[(e8 + j) * 4 + tok + k];
+              for (int j = 0; j < 8; ++j) xr[k][j] = s_hx[(e8 + j) * 4 + tok + k];
+            }
+          }
         }
         float gq[8], gk[8], gv[8], dsk[8];
         // the cell's dq / dk / dv: bf16 tiles in the layout of q / k / v (one 16-byte group per thread, 512 B per warp)
@@ -907,7 +920,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
 }
 
 template <int C>
-static int launch_pre_bwd(const float* x, const float* dy, const float* xm, const void* q, const void* k, const void* v, const void* dq,
+static int launch_pre_bwd(const float* x, const float* dy, const void* xm, const void* q, const void* k, const void* v, const void* dq,
                           const void* dk, const void* dv, const float* dig, const float* dfg, const void* d_act, const void* dz,
                           const xhved_vil_params* p, const VilGeom& g, float* dx, const xhved_vil_grads* gr, void* ws_dconv,
                           void* ws_dxmv, cudaStream_t st) {
@@ -918,7 +931,7 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
     if (e != cudaSuccess) return (int)e;
     ProfScope ps(K_VIL_PRE_BWD_A, st);
     const int ntiles = g.B * g.nc;
-    vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, xm, u8(dq), u8(dk), u8(dv), dig, dfg, u8(d_act),
+    vil_pre_bwd_a_tc_kernel<C><<<persistent_grid(ntiles, 1), 4 * kTok, smem, st>>>(*p, g, u8(xm), u8(dq), u8(dk), u8(dv), dig, dfg, u8(d_act),
                                                                                   static_cast<unsigned char*>(ws_dconv),
                                                                                   static_cast<unsigned char*>(ws_dxmv), *gr, ntiles);
   }
@@ -939,7 +952,7 @@ static int launch_pre_bwd(const float* x, const float* dy, const float* xm, cons
 using namespace xhved;
 
 extern "C" int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, const xhved_vil_shape* sh, void* q_tiles, void* k_tiles,
-                                 void* v_tiles, float* ig_padded, float* fg_padded, float* act, float* z, float* xm, void* stream) {
+                                 void* v_tiles, float* ig_padded, float* fg_padded, void* act, void* z, void* xm, void* stream) {
   VilGeom g;
   if (int rc = vil_validate(sh, &g)) return rc;
   if (!x || !p || !q_tiles || !k_tiles || !v_tiles || !ig_padded || !fg_padded || !act || !z || !xm) return XHVED_ERR_BAD_ARG;
@@ -952,7 +965,7 @@ extern "C" int xhved_vil_pre_fwd(const float* x, const xhved_vil_params* p, cons
   }
 }
 
-extern "C" int xhved_vil_pre_bwd(const float* x, const float* dy, const float* xm, const void* q_tiles, const void* k_tiles,
+extern "C" int xhved_vil_pre_bwd(const float* x, const float* dy, const void* xm, const void* q_tiles, const void* k_tiles,
                                  const void* v_tiles, const void* dq, const void* dk, const void* dv, const float* dig, const float* dfg,
                                  const void* d_act, const void* dz, const xhved_vil_params* p, const xhved_vil_shape* sh, float* dx,
                                  const xhved_vil_grads* g, void* ws_dconv, void* ws_dxmv, void* stream) {

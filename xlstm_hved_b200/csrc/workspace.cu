@@ -31,7 +31,6 @@ extern "C" int xhved_vil_workspace_query(int B, int S, int C, xhved_vil_workspac
   if (C != 16 && C != 32 && C != 64) return XHVED_ERR_UNSUPPORTED_DIM;
   const int E = 2 * C;
   if (int rc = xhved_mlstm_workspace_query(4 * B, S, E / 4, &out->cell)) return rc;
-  out->token_minor_bytes = static_cast<int64_t>(B) * out->cell.nc * E * 128 * 4;
   out->token_tile_bytes = static_cast<int64_t>(B) * out->cell.nc * E * 128 * 2;
   // norm, proj_up, conv w/b, q/k/v, igate w/b, fgate w/b, outnorm, skip, proj_down (ops.VIL_PARAM_KEYS order)
   const int64_t params = C + 2LL * E * C + E * 4 + E + 3LL * E * 4 + 2 * (4LL * 3 * E + 4) + E + E + static_cast<int64_t>(C) * E;
