@@ -29,6 +29,10 @@ int launch_chunk_grad_ws(int dhp, const void* q, const void* k, const void* v, c
                          const float* mu_next, int BH, int nc, float scale, float eps, void* dq, void* dk, void* dv, float* dig,
                          float* dc, float* dc_tot, cudaStream_t st);
 
+int launch_chunk_rstate_ws(int dhp, const void* q, const void* dh_t, const void* h, const float* fg, const float* m, const float* den,
+                           int BH, int nc, float scale, float eps, float* dstate, float* g_out, float* lam_out, cudaStream_t st);
+bool state_ws_enabled(int dhp);
+
 int launch_chunk_grad_wide(const void* q, const void* k, const void* v, const void* h, const void* dh_t, const float* ig, const float* fg,
                            const float* m, const float* den, const void* states, const float* m_prev, const void* rstates,
                            const float* mu_next, int BH, int nc, float scale, float eps, void* dq, void* dk, void* dv, float* dig,
@@ -431,7 +435,9 @@ static int launch_bwd(const void* q, const void* k, const void* v, const float* 
   constexpr int NE = ext_cols(DHP);
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   const int ntiles = BH * nc;
-  {
+  if (state_ws_enabled(DHP)) {
+    if (int rc = launch_chunk_rstate_ws(DHP, q, dh_t, h, fg, m, den, BH, nc, scale, eps, ws_dstate, ws_g, ws_lam, st)) return rc;
+  } else {
     const size_t used = 3 * kL * DHP * 2 + kL * NE * 2, window = kL * DHP * 2 + 32768;
     const size_t smem = used > window ? used : window;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_rstate_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

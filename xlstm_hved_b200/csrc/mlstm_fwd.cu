@@ -99,84 +99,92 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
 }
 
 // ------------------------------------------------------------------ phase 2
-// One CTA per (b,head).  Thread owns elements idx = tid + k*blockDim of the DHP x NE state.
+// One (b,head) sequence per blockIdx.x; a thread owns one 16-byte group (8 consecutive columns of one row) of the DHP x NE
+// state, so every chunk costs it two 16-byte loads and two 16-byte stores (a warp covers 512 contiguous bytes of a tile).
 // Writes, for every chunk c, the state ENTERING chunk c as a PAIR of bf16 tile-native tiles (hi, lo = residual)
 // [DHP rows (key dim d)][NE cols (value dim e | n | 0)] plus its log-scale m_prev[c].
 // `reverse` runs the same recurrence from the last chunk to the first (backward pass).
+// (Measured and dropped: lane = chunk with shuffle scans of the affine maps acc -> D acc + V -- one round of memory latency
+// instead of nc/8, but 16-byte stores 4 KB apart: 14.2 vs 10.9 us per launch.)
 template <int DHP>
 __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __restrict__ dstate, const float* __restrict__ g_in,
                                                                 const float* __restrict__ amax_in, int nc, int reverse,
                                                                 unsigned char* __restrict__ states, float* __restrict__ m_prev) {
-  // grid = (B*NH, ceil(DHP*NE / 512)): the state elements are independent, so they are spread over several CTAs.  The
-  // scalar log-scale recurrence is run once per CTA (one thread, coefficients into shared memory); after that every element
-  // follows acc <- decay_c * acc + w_c * dstate_c, with the chunk contributions loaded eight chunks at a time so that the
-  // serial chain sees ~nc/8 memory latencies instead of nc.
+  // grid = (B*NH, ceil(groups / blockDim)).  The scalar log-scale recurrence m' = max(g + m, a) is a scan over the maps
+  // m -> max(G + m, A), which compose as (G1, A1) o (G2, A2) = (G1 + G2, max(A1 + G2, A2)): warp 0 runs it 32 chunks at a time
+  // (shuffles) and leaves the per-chunk coefficients in shared memory; after that every state element follows
+  // acc <- decay_c * acc + w_c * dstate_c, with the chunk contributions loaded eight chunks at a time so that the serial chain
+  // sees ~nc/8 memory latencies instead of nc.
   constexpr int NE = ext_cols(DHP);
-  constexpr int NEL = DHP * NE;
+  constexpr int NEL = DHP * NE, NG = NEL / 8, CGS = NE / 8;
   extern __shared__ float scan_smem[];
-  float* s_g = scan_smem;            // [nc] in scan order
-  float* s_a = s_g + nc;
-  float* s_dec = s_a + nc;
+  float* s_dec = scan_smem;          // [nc] in scan order
   float* s_w = s_dec + nc;
-  float* s_m = s_w + nc;
   const int bh = blockIdx.x, tid = threadIdx.x;
-  const int i0 = blockIdx.y * 512 + tid, i1 = i0 + 256;
-  const bool on0 = i0 < NEL, on1 = i1 < NEL;
-  const uint32_t off0 = on0 ? tile_off16(DHP, i0 / NE, (i0 % NE) / 8) + ((i0 % NE) % 8) * 2 : 0;
-  const uint32_t off1 = on1 ? tile_off16(DHP, i1 / NE, (i1 % NE) / 8) + ((i1 % NE) % 8) * 2 : 0;
   const size_t tile0 = static_cast<size_t>(bh) * nc;
-  for (int st = tid; st < nc; st += blockDim.x) {
-    const int c = reverse ? nc - 1 - st : st;
-    s_g[st] = g_in[tile0 + c];
-    s_a[st] = amax_in[tile0 + c];
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float m = -INFINITY;
-    for (int st = 0; st < nc; ++st) {
-      const float m_new = fmaxf(s_g[st] + m, s_a[st]);
-      s_m[st] = m;                                   // log-scale of the state ENTERING the chunk
-      s_dec[st] = __expf(s_g[st] + m - m_new);       // exp(-inf) = 0 on the first step
-      s_w[st] = __expf(s_a[st] - m_new);
-      m = m_new;
+  if (tid < 32) {
+    float cG = 0.f, cA = -INFINITY;                      // composition of all chunks in front of this block of 32
+    for (int s0 = 0; s0 < nc; s0 += 32) {
+      const int st = s0 + tid;
+      const bool on = st < nc;
+      const int c = reverse ? nc - 1 - st : st;
+      const float g = on ? g_in[tile0 + c] : 0.f, a = on ? amax_in[tile0 + c] : -INFINITY;      // off: the identity map
+      float G = g, A = a;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float Gp = __shfl_up_sync(0xffffffffu, G, o), Ap = __shfl_up_sync(0xffffffffu, A, o);
+        if (tid >= o) {
+          A = fmaxf(Ap + G, A);
+          G += Gp;
+        }
+      }
+      const float m_new = fmaxf(cA + G, A);               // log-scale after this chunk
+      float m_in = __shfl_up_sync(0xffffffffu, m_new, 1);  // log-scale of the state ENTERING the chunk
+      if (tid == 0) m_in = cA;
+      if (on) {
+        s_dec[st] = __expf(g + m_in - m_new);             // exp(-inf) = 0 on the first step
+        s_w[st] = __expf(a - m_new);
+        if (blockIdx.y == 0) m_prev[tile0 + c] = m_in;
+      }
+      cG += __shfl_sync(0xffffffffu, G, 31);
+      cA = __shfl_sync(0xffffffffu, m_new, 31);
     }
   }
   __syncthreads();
-  if (blockIdx.y == 0) {
-    for (int st = tid; st < nc; st += blockDim.x) m_prev[tile0 + (reverse ? nc - 1 - st : st)] = s_m[st];
-  }
-  float acc0 = 0.f, acc1 = 0.f;
+  const int gi = blockIdx.y * blockDim.x + tid;
+  if (gi >= NG) return;
+  const int d = gi / CGS, cg = gi % CGS;
+  const float* in = dstate + tile0 * NEL + d * NE + cg * 8;
+  unsigned char* out = states + tile0 * (NEL * 4) + tile_off16(DHP, d, cg);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   constexpr int PF = 8;
   for (int s0 = 0; s0 < nc; s0 += PF) {
-    float cur0[PF], cur1[PF];
+    float4 cur[PF][2];
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       const int st = s0 + j;
-      const int c = reverse ? nc - 1 - st : st;
-      const float* sn = dstate + (tile0 + (st < nc ? c : 0)) * NEL;
-      cur0[j] = (on0 && st < nc) ? __ldg(sn + i0) : 0.f;
-      cur1[j] = (on1 && st < nc) ? __ldg(sn + i1) : 0.f;
+      const int c = st < nc ? (reverse ? nc - 1 - st : st) : 0;
+      const float4* sn = reinterpret_cast<const float4*>(in + static_cast<size_t>(c) * NEL);
+      cur[j][0] = __ldg(sn);
+      cur[j][1] = __ldg(sn + 1);
     }
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       const int st = s0 + j;
       if (st < nc) {
         const int c = reverse ? nc - 1 - st : st;
-        // emit the state entering this chunk as a bf16 hi/lo pair
-        unsigned char* out = states + (tile0 + c) * (NEL * 4);
-        if (on0) {
-          const __nv_bfloat16 hi = __float2bfloat16(acc0);
-          *reinterpret_cast<__nv_bfloat16*>(out + off0) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(out + NEL * 2 + off0) = __float2bfloat16(acc0 - __bfloat162float(hi));
-        }
-        if (on1) {
-          const __nv_bfloat16 hi = __float2bfloat16(acc1);
-          *reinterpret_cast<__nv_bfloat16*>(out + off1) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(out + NEL * 2 + off1) = __float2bfloat16(acc1 - __bfloat162float(hi));
-        }
-        // fold this chunk in
-        acc0 = s_dec[st] * acc0 + s_w[st] * cur0[j];
-        acc1 = s_dec[st] * acc1 + s_w[st] * cur1[j];
+        // emit the state entering this chunk as a bf16 hi/lo pair, then fold the chunk in
+        uint4 hi, lo;
+        split8_hilo(acc, hi, lo);
+        unsigned char* o = out + static_cast<size_t>(c) * (NEL * 4);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + NEL * 2) = lo;
+        const float dec = s_dec[st], w = s_w[st];
+        const float v[8] = {cur[j][0].x, cur[j][0].y, cur[j][0].z, cur[j][0].w, cur[j][1].x, cur[j][1].y, cur[j][1].z, cur[j][1].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = dec * acc[i] + w * v[i];
       }
     }
   }
@@ -433,6 +441,18 @@ int launch_chunk_out_ws(int dhp, const void* q, const void* k, const void* v, co
                         const float* m_prev, int BH, int nc, float scale, float eps, void* h, float* m, float* den,
                         cudaStream_t st);
 
+int launch_chunk_state_ws(int dhp, const void* k, const void* v, const float* ig, const float* fg, int BH, int nc, float scale,
+                          float* dstate, float* g_out, float* amax_out, cudaStream_t st);
+// chunk_state / chunk_rstate on the persistent warp-specialised kernel (mlstm_state_ws.cu; dhp <= 32).  XHVED_STATE_WS=0 selects
+// the one-tile-per-CTA kernels for A/B measurements.  Read once.
+bool state_ws_enabled(int dhp) {
+  static const int on = [] {
+    const char* e = getenv("XHVED_STATE_WS");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on != 0 && dhp <= 32;
+}
+
 // Which chunk_out kernel runs: the persistent warp-specialised one with P kept in tensor memory (mlstm_fwd_ws.cu) -- the
 // faster of the two at every head dim on B200 (profiles/r02_cell_scaling.jsonl).  XHVED_CELL_WS=0 selects the
 // one-tile-per-CTA kernel above for A/B measurements.  Read once.
@@ -452,7 +472,9 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   const int ntiles = BH * nc;
   // phase 1
-  {
+  if (state_ws_enabled(DHP)) {
+    if (int rc = launch_chunk_state_ws(DHP, k, v, ig, fg, BH, nc, scale, ws_dstate, ws_g, ws_amax, st)) return rc;
+  } else {
     const size_t used = 2 * kL * DHP * 2 + kL * NE * 2, window = kL * DHP * 2 + 32768;
     const size_t smem = used > window ? used : window;
     cudaError_t e = cudaFuncSetAttribute(mlstm_chunk_state_kernel<DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -481,15 +503,16 @@ static int launch_fwd(const void* q, const void* k, const void* v, const float* 
 int launch_state_scan(int dhp, const float* dstate, const float* g, const float* amax, int BH, int nc, int reverse, void* states,
                       float* m_prev, cudaStream_t st) {
   ProfScope ps(K_STATE_SCAN, st);
-  const int nel = dhp * (dhp + 16);
-  const dim3 grid(BH, (nel + 511) / 512);
-  const size_t smem = static_cast<size_t>(nc) * 5 * sizeof(float);
+  const int groups = dhp * (dhp + 16) / 8;      // 16-byte groups of one state
+  const int threads = groups < 256 ? groups : 256;
+  const dim3 grid(BH, (groups + threads - 1) / threads);
+  const size_t smem = static_cast<size_t>(nc) * 2 * sizeof(float);
   if (smem > 48 * 1024) return XHVED_ERR_BAD_SHAPE;
   switch (dhp) {
-    case 16: mlstm_state_scan_kernel<16><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 32: mlstm_state_scan_kernel<32><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 64: mlstm_state_scan_kernel<64><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
-    case 128: mlstm_state_scan_kernel<128><<<grid, 256, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 16: mlstm_state_scan_kernel<16><<<grid, threads, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 32: mlstm_state_scan_kernel<32><<<grid, threads, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 64: mlstm_state_scan_kernel<64><<<grid, threads, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+    case 128: mlstm_state_scan_kernel<128><<<grid, threads, smem, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
     default: return XHVED_ERR_UNSUPPORTED_DH;
   }
   return (int)cudaGetLastError();

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_post_fwd_persist_kernel(const
                                                                             const unsigned char* __restrict__ z,
                                                                             xhved_vil_params p, VilGeom g, float* __restrict__ y, int ntiles) {
   using L = PostPersist<C>;
-  constexpr int E = L::E, DH = L::DH, DHP = L::DHP, NX = 8 * ((C + 31) / 32);
+  constexpr int E = L::E, DH = L::DH, NX = 8 * ((C + 31) / 32);
   extern __shared__ __align__(128) unsigned char smem[];
   float* par = reinterpret_cast<float*>(smem + L::PAR);
   __shared__ __align__(8) uint64_t bar_full[2], bar_mma;
