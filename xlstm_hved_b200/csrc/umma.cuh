@@ -86,6 +86,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Bounded SPINNING wait (no suspend-time hint): for short hand-offs between the roles of a warp-specialised kernel, where the
+// wake-up after a hinted sleep costs more than the phase being waited for.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((it & 1023u) == 0u) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- bulk copy (TMA unit, no tensor map)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
