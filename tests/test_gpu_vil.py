@@ -386,3 +386,106 @@ def test_patched_reference_block_wider_than_the_fused_kernels():
         xh.unpatch_model(model)
     assert vl.parallel_stabilized_simple.__module__.endswith("vision_lstm")
     assert rel_l2(y1 - x, y0 - x) < TOL_L2 and rel_l2(dx1 - gy, dx0 - gy) < 3e-2
+
+
+def _block_and_inputs(B, seed):
+    import xlstm_hved_b200 as xh
+    torch.manual_seed(seed)
+    wrap = xh.ViLLayer3D(dim=32).cuda()
+    with torch.no_grad():
+        for n, p in wrap.named_parameters():
+            if n.startswith("vil.") and p.dim() >= 1:
+                p.add_(0.05 * torch.randn_like(p))
+    xs = [torch.randn(B, 32, 8, 8, 8, device="cuda") for _ in range(2)]
+    gys = [torch.randn(B, 32, 8, 8, 8, device="cuda") for _ in range(2)]
+    return wrap, xs, gys
+
+
+def _run_two_forwards_then_backward(wrap, xs, gys):
+    """The access pattern of the reference's training step (train.py:222-239): two forwards, one backward through both."""
+    wrap.zero_grad(set_to_none=True)
+    leaves = [x.clone().requires_grad_() for x in xs]
+    ys = [wrap(l) for l in leaves]
+    (ys[0] * gys[0]).sum().add((ys[1] * gys[1]).sum()).backward()
+    return [y.detach() for y in ys], [l.grad for l in leaves], [p.grad.clone() for p in wrap.vil.parameters()]
+
+
+def test_block_graphs_match_the_plain_path_and_hold_two_forwards():
+    """Per-block CUDA graphs (ops.py: small batches are host-bound, one volume per step is the reference's real batch): the
+    graphed forward / backward give what the plain launches give -- same kernels, so the outputs are bit-identical and the
+    parameter gradients equal up to the order of their atomics -- with two forwards alive before the backward (two slots),
+    under no_grad (slot released at once) and when a forward's graph is dropped without a backward."""
+    from xlstm_hved_b200 import ops
+    wrap, xs, gys = _block_and_inputs(1, 11)
+    try:
+        ops.set_block_graphs(False)
+        ref = _run_two_forwards_then_backward(wrap, xs, gys)
+        ops.set_block_graphs("auto")
+        ops._GRAPH_POOLS.clear()
+        for it in range(3):                                  # first pass captures, later passes replay
+            got = _run_two_forwards_then_backward(wrap, xs, gys)
+            for a, b in zip(ref[0] + ref[1], got[0] + got[1]):
+                assert torch.equal(a, b), it
+            for a, b in zip(ref[2], got[2]):
+                assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), it
+        pools = list(ops._GRAPH_POOLS.values())
+        assert len(pools) == 1 and len(pools[0]) == 2 and not any(s.busy for s in pools[0])
+        with torch.no_grad():
+            y = wrap(xs[0])
+        assert torch.equal(y, ref[0][0]) and not any(s.busy for s in pools[0])
+        y = wrap(xs[0].clone().requires_grad_())             # graph of a forward that never runs backward
+        assert any(s.busy for s in pools[0])
+        del y
+        assert not any(s.busy for s in pools[0])
+        # a larger batch than the threshold takes the plain path
+        big = torch.randn(ops._GRAPH_MAX_TOKENS // 512 + 1, 32, 8, 8, 8, device="cuda")
+        wrap(big)
+        assert len(ops._GRAPH_POOLS) == 1
+    finally:
+        ops.set_block_graphs("auto")
+        ops._GRAPH_POOLS.clear()
+
+
+def test_block_graphs_from_two_threads_on_two_streams():
+    """Slots are handed out under a lock and replayed on the caller's stream: two threads with their own streams and inputs
+    (same module, as nn.DataParallel threads would on one device) get what the sequential run gives."""
+    import threading
+    from xlstm_hved_b200 import ops
+    wrap, xs, gys = _block_and_inputs(1, 12)
+    try:
+        ops.set_block_graphs(False)
+        seq = []
+        for i in range(2):
+            l = xs[i].clone().requires_grad_()
+            y = wrap(l)
+            y.backward(gys[i])
+            seq.append((y.detach(), l.grad))
+        ops.set_block_graphs(True)
+        ops._GRAPH_POOLS.clear()
+        par, errs = {}, []
+        streams = [torch.cuda.Stream() for _ in range(2)]
+
+        def worker(i):
+            try:
+                with torch.cuda.stream(streams[i]):
+                    for _ in range(6):
+                        l = xs[i].clone().requires_grad_()
+                        y = wrap(l)
+                        y.backward(gys[i])
+                        par[i] = (y.detach(), l.grad)
+                    streams[i].synchronize()
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+
+        torch.cuda.synchronize()
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errs, errs
+        for i in range(2):
+            assert torch.equal(seq[i][0], par[i][0]) and torch.equal(seq[i][1], par[i][1])
+    finally:
+        ops.set_block_graphs("auto")
+        ops._GRAPH_POOLS.clear()

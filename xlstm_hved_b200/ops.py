@@ -5,8 +5,10 @@ sm_100a kernels of libxhved.so on the current CUDA stream.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
+import threading
 from ctypes import c_float, c_uint32
 
 import torch
@@ -526,11 +528,15 @@ def vil_block_bwd(x_tok, dy_tok, params, reverse, ws: VilSaved, eps: float = 1e-
     sh.grad_replicas, sh.grad_replica_stride = GRAD_REPLICAS, ws.stride
     check(lib.xhved_vil_block_bwd(ptr(x_tok), ptr(dy_tok), ctypes.byref(ps), ctypes.byref(sh), eps, ptr(ws.blob), ptr(scratch), ptr(dx),
                                   ptr(out), stream()), "xhved_vil_block_bwd")
+    return dx, _split_param_grads(out, params)
+
+
+def _split_param_grads(flat, params):
     grads, off = [], 0
     for p in params:
-        grads.append(out[off:off + p.numel()].view(p.shape))
+        grads.append(flat[off:off + p.numel()].view(p.shape))
         off += p.numel()
-    return dx, grads
+    return grads
 
 
 class VilBlockFunction(torch.autograd.Function):
@@ -554,10 +560,146 @@ class VilBlockFunction(torch.autograd.Function):
         return (dx, None, None, *grads)
 
 
+# ----------------------------------------------------------------------------- per-block CUDA graphs (small batches)
+# At the reference's real batch (one volume, train.py:50) a block is ~14 launches of 5-30 us per direction: the kernels take
+# ~0.12 ms, the host side -- Python, ctypes structs, allocations, the launches themselves -- 0.5 ms.  For small blocks the
+# forward and the backward of a block are therefore captured ONCE into CUDA graphs over static buffers (x / dy are copied in,
+# y / dx / the flat parameter gradients cloned out: three small copies instead of ~28 launches) and replayed afterwards.
+#   * a "slot" = the static buffers + the two graphs of one (device, shape, strides, direction, parameter storage); a slot is
+#     busy from its forward until its backward (or until autograd frees the node), so the two forwards of a training step
+#     (train.py:222-225) use two slots; at most _SLOT_CAP slots per key, then the plain path runs;
+#   * nothing is graphed while the caller itself captures a stream (bench.py replays the whole step), for parameters that are
+#     not fp32 leaf tensors (nn.DataParallel replicas are re-broadcast every step), or above _GRAPH_MAX_TOKENS tokens (the
+#     kernels then outlast the host side anyway).
+# XHVED_BLOCK_GRAPHS=0 disables, =1 forces graphs at every size; default "auto".
+_GRAPH_MODE = os.environ.get("XHVED_BLOCK_GRAPHS", "auto")
+_GRAPH_MAX_TOKENS = 65536
+_SLOT_CAP = 4
+_MAX_KEYS = 16
+_GRAPH_LOCK = threading.Lock()
+_GRAPH_POOLS = collections.OrderedDict()      # key -> [slots], least recently used first
+
+
+def set_block_graphs(mode) -> None:
+    """"auto" (default), True / "1" (always), False / "0" (never): per-block CUDA graphs, see above."""
+    global _GRAPH_MODE
+    _GRAPH_MODE = {True: "1", False: "0"}.get(mode, str(mode))
+
+
+class _BlockGraphSlot:
+    def __init__(self, x_like, params, reverse, eps):
+        dev = x_like.device
+        self.params, self.reverse, self.eps = params, reverse, eps
+        self.busy, self.gen, self.bwd = False, 0, None
+        self.x_in = torch.empty_strided(x_like.shape, x_like.stride(), device=dev, dtype=torch.float32)
+        self.x_in.copy_(x_like)
+        self._warm(lambda: vil_block_fwd(self.x_in, params, reverse, eps))
+        self.fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd, capture_error_mode="thread_local"):
+            self.y, self.ws = vil_block_fwd(self.x_in, params, reverse, eps)
+
+    @staticmethod
+    def _warm(fn):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn()
+        cur.wait_stream(side)
+
+    def capture_bwd(self, dy):
+        self.dy_in = torch.empty_strided(self.y.shape, self.y.stride(), device=self.y.device, dtype=torch.float32)
+        self.dy_in.copy_(dy)
+        self._warm(lambda: self._bwd_raw())
+        self.bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.bwd, capture_error_mode="thread_local"):
+            self.dx, self.flat = self._bwd_raw()
+
+    def _bwd_raw(self):
+        dx, grads = vil_block_bwd(self.x_in, self.dy_in, self.params, self.reverse, self.ws, self.eps)
+        return dx, grads[0]._base if grads[0]._base is not None else grads[0]
+
+
+class _SlotRelease:
+    """Frees the slot when autograd drops the node (a forward whose backward never runs)."""
+
+    def __init__(self, slot, gen):
+        self.slot, self.gen = slot, gen
+
+    def __del__(self):
+        if self.slot.gen == self.gen:
+            self.slot.busy = False
+
+
+def _acquire_slot(x_tok, params, reverse, eps):
+    if _GRAPH_MODE == "0" or torch.cuda.is_current_stream_capturing():
+        return None
+    if _GRAPH_MODE != "1" and x_tok.shape[0] * x_tok.shape[1] > _GRAPH_MAX_TOKENS:
+        return None
+    if any(p.dtype != torch.float32 or not p.is_contiguous() or not p.is_leaf for p in params):
+        return None
+    key = (x_tok.device.index, tuple(x_tok.shape), tuple(x_tok.stride()), bool(reverse), float(eps), tuple(p.data_ptr() for p in params))
+    with _GRAPH_LOCK:
+        pool = _GRAPH_POOLS.get(key)
+        if pool is None:
+            while len(_GRAPH_POOLS) >= _MAX_KEYS:                  # forget the least recently used shape / parameter set
+                _GRAPH_POOLS.popitem(last=False)
+            pool = _GRAPH_POOLS[key] = []
+        else:
+            _GRAPH_POOLS.move_to_end(key)
+        slot = next((s for s in pool if not s.busy), None)
+        if slot is None:
+            if len(pool) >= _SLOT_CAP:
+                return None
+            slot = _BlockGraphSlot(x_tok, [p.detach() for p in params], bool(reverse), eps)
+            pool.append(slot)
+        slot.busy = True
+        slot.gen += 1
+        return slot
+
+
+class _GraphedVilBlockFunction(torch.autograd.Function):
+    """VilBlockFunction replayed from the CUDA graphs of a slot."""
+
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x_tok, slot, *params):
+        slot.x_in.copy_(x_tok)
+        slot.fwd.replay()
+        y = slot.y.clone()
+        ctx.slot, ctx.gen = slot, slot.gen
+        if any(ctx.needs_input_grad):
+            ctx.release = _SlotRelease(slot, slot.gen)
+        else:
+            slot.busy = False
+        return y
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dy):
+        slot = ctx.slot
+        if slot.gen != ctx.gen:
+            raise RuntimeError("xlstm_hved_b200: the saved state of this graphed ViL block has been reused by a later forward "
+                               "(backward twice through the same node?); set XHVED_BLOCK_GRAPHS=0 for that pattern")
+        if slot.bwd is None:
+            slot.capture_bwd(dy)
+        else:
+            slot.dy_in.copy_(dy)
+        slot.bwd.replay()
+        dx, flat = slot.dx.clone(), slot.flat.clone()
+        slot.busy = False
+        return (dx, None, *_split_param_grads(flat, slot.params))
+
+
 def vil_block(x_tok: torch.Tensor, params, reverse: bool = False, eps: float = 1e-6) -> torch.Tensor:
     """x_tok: (B,S,C) view of fp32 CUDA memory (any strides); params in VIL_PARAM_KEYS order."""
     if not x_tok.is_cuda:
         raise RuntimeError("xlstm_hved_b200 has no CPU path")
     if x_tok.dtype != torch.float32:
         x_tok = x_tok.float()
+    x_tok = _dense_view(x_tok)
+    with torch.cuda.device(x_tok.device):
+        slot = _acquire_slot(x_tok, params, reverse, eps)
+    if slot is not None:
+        return _GraphedVilBlockFunction.apply(x_tok, slot, *params)
     return VilBlockFunction.apply(x_tok, bool(reverse), eps, *params)
