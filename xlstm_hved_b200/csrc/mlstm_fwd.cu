@@ -104,8 +104,7 @@ __global__ void __launch_bounds__(kThreads) mlstm_chunk_state_kernel(const unsig
 // Writes, for every chunk c, the state ENTERING chunk c as a PAIR of bf16 tile-native tiles (hi, lo = residual)
 // [DHP rows (key dim d)][NE cols (value dim e | n | 0)] plus its log-scale m_prev[c].
 // `reverse` runs the same recurrence from the last chunk to the first (backward pass).
-// (Measured and dropped: lane = chunk with shuffle scans of the affine maps acc -> D acc + V -- one round of memory latency
-// instead of nc/8, but 16-byte stores 4 KB apart: 14.2 vs 10.9 us per launch.)
+// Sequences of 64 chunks and more take mlstm_state_scan_par_kernel below.
 template <int DHP>
 __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __restrict__ dstate, const float* __restrict__ g_in,
                                                                 const float* __restrict__ amax_in, int nc, int reverse,
@@ -187,6 +186,85 @@ __global__ void __launch_bounds__(256) mlstm_state_scan_kernel(const float* __re
         for (int i = 0; i < 8; ++i) acc[i] = dec * acc[i] + w * v[i];
       }
     }
+  }
+}
+
+// The same two recurrences for LONG sequences (nc >= 64: the 32^3 stage of SURVEY 8d config 5 has 256 chunks and few
+// sequences, where the serial chain above is nc/8 memory latencies long and leaves most SMs idle).  Both are scans of affine
+// maps, so a WARP runs them with lane = chunk:
+//   log-scale:  m' = max(g + m, a)            maps m -> max(G + m, A) compose as (G1 + G2, max(A1 + G2, A2))
+//   state:      acc' = dec * acc + w * dC     maps acc -> D acc + V  compose as (D1 D2, V1 D2 + V2)
+// One warp owns one 16-byte group of the state: every lane loads the contribution of ITS chunk (one round of memory latency
+// per 32 chunks), five shuffle steps give the inclusive scans, every lane writes the state entering its chunk; blocks of 32
+// chunks follow each other with a carry.  (At nc = 32 the 16-byte stores 4 KB apart make it slower than the kernel above:
+// 14.2 vs 10.9 us per launch, so it only runs for long sequences.)
+template <int DHP>
+__global__ void __launch_bounds__(256) mlstm_state_scan_par_kernel(const float* __restrict__ dstate, const float* __restrict__ g_in,
+                                                                    const float* __restrict__ amax_in, int nc, int reverse,
+                                                                    unsigned char* __restrict__ states, float* __restrict__ m_prev) {
+  constexpr int NE = ext_cols(DHP);
+  constexpr int NEL = DHP * NE, NG = NEL / 8, CGS = NE / 8;
+  const int bh = blockIdx.x, lane = threadIdx.x & 31;
+  const int gi = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);      // 16-byte group of this warp
+  if (gi >= NG) return;
+  const size_t tile0 = static_cast<size_t>(bh) * nc;
+  const int d = gi / CGS, cg = gi % CGS;
+  const float* in = dstate + tile0 * NEL + d * NE + cg * 8;
+  unsigned char* out = states + tile0 * (NEL * 4) + tile_off16(DHP, d, cg);
+  float cG = 0.f, cA = -INFINITY;                        // log-scale map of all chunks in front of this block of 32
+  float cV[8];                                           // state after all chunks in front of this block
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cV[i] = 0.f;
+  for (int s0 = 0; s0 < nc; s0 += 32) {
+    const int st = s0 + lane;
+    const bool on = st < nc;
+    const int c = on ? (reverse ? nc - 1 - st : st) : 0;
+    const float4* sn = reinterpret_cast<const float4*>(in + static_cast<size_t>(c) * NEL);
+    const float4 x0 = __ldg(sn), x1 = __ldg(sn + 1);
+    const float g = on ? g_in[tile0 + c] : 0.f, a = on ? amax_in[tile0 + c] : -INFINITY;      // off: the identity map
+    float G = g, A = a;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float Gp = __shfl_up_sync(0xffffffffu, G, o), Ap = __shfl_up_sync(0xffffffffu, A, o);
+      if (lane >= o) {
+        A = fmaxf(Ap + G, A);
+        G += Gp;
+      }
+    }
+    const float m_new = fmaxf(cA + G, A);                // log-scale after this chunk
+    float m_in = __shfl_up_sync(0xffffffffu, m_new, 1);  // log-scale of the state ENTERING the chunk
+    if (lane == 0) m_in = cA;
+    float D = on ? __expf(g + m_in - m_new) : 1.f;       // exp(-inf) = 0 on the first step
+    const float w = on ? __expf(a - m_new) : 0.f;
+    float V[8] = {w * x0.x, w * x0.y, w * x0.z, w * x0.w, w * x1.x, w * x1.y, w * x1.z, w * x1.w};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float Dp = __shfl_up_sync(0xffffffffu, D, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float Vp = __shfl_up_sync(0xffffffffu, V[i], o);
+        if (lane >= o) V[i] = Vp * D + V[i];
+      }
+      if (lane >= o) D *= Dp;
+    }
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      V[i] = D * cV[i] + V[i];                            // state after this chunk
+      e[i] = __shfl_up_sync(0xffffffffu, V[i], 1);        // ... and entering it
+      if (lane == 0) e[i] = cV[i];
+      cV[i] = __shfl_sync(0xffffffffu, V[i], 31);
+    }
+    if (on) {
+      uint4 hi, lo;
+      split8_hilo(e, hi, lo);
+      unsigned char* o = out + static_cast<size_t>(c) * (NEL * 4);
+      *reinterpret_cast<uint4*>(o) = hi;
+      *reinterpret_cast<uint4*>(o + NEL * 2) = lo;
+      if (gi == 0) m_prev[tile0 + c] = m_in;
+    }
+    cG += __shfl_sync(0xffffffffu, G, 31);
+    cA = __shfl_sync(0xffffffffu, m_new, 31);
   }
 }
 
@@ -504,6 +582,18 @@ int launch_state_scan(int dhp, const float* dstate, const float* g, const float*
                       float* m_prev, cudaStream_t st) {
   ProfScope ps(K_STATE_SCAN, st);
   const int groups = dhp * (dhp + 16) / 8;      // 16-byte groups of one state
+  if (nc >= 64) {                               // long sequences: lane = chunk, one warp per group
+    const int wpb = 8;
+    const dim3 pgrid(BH, (groups + wpb - 1) / wpb);
+    switch (dhp) {
+      case 16: mlstm_state_scan_par_kernel<16><<<pgrid, 32 * wpb, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+      case 32: mlstm_state_scan_par_kernel<32><<<pgrid, 32 * wpb, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+      case 64: mlstm_state_scan_par_kernel<64><<<pgrid, 32 * wpb, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+      case 128: mlstm_state_scan_par_kernel<128><<<pgrid, 32 * wpb, 0, st>>>(dstate, g, amax, nc, reverse, (unsigned char*)states, m_prev); break;
+      default: return XHVED_ERR_UNSUPPORTED_DH;
+    }
+    return (int)cudaGetLastError();
+  }
   const int threads = groups < 256 ? groups : 256;
   const dim3 grid(BH, (groups + threads - 1) / threads);
   const size_t smem = static_cast<size_t>(nc) * 2 * sizeof(float);
