@@ -548,9 +548,11 @@ struct PreBwdATC {
   // [dig|dfg] (double-buffered hi/lo pairs) is also read as a 128-row MN-major A operand: 32 KB window that runs on over
   // the tiles behind it; rows >= 16 of those products are never read
   static constexpr uint32_t DG0 = 0, DG_STRIDE = 2 * DG_BYTES, WGHI = 2 * DG_STRIDE, WGLO = WGHI + WG_BYTES;
-  // operands of the weight-gradient GEMMs.  GQK: [128][2 EG]; GV: 32 KB window covering ACT, XMT.
+  // operands of the weight-gradient GEMMs: A_1 = GQK [128][2 EG]; A_2 = [GV | DGC] (the bf16 [dig|dfg] of this tile right behind
+  // the g_v columns: ONE 128-row MN-major window whose rows [0, EG) are g_v and [EG, EG + 8) the gate gradients);
+  // B = [ACT | XMT] as one N = 2 EG operand
   static constexpr uint32_t GQK = WGLO + WG_BYTES;
-  static constexpr uint32_t GV = GQK + kTok * 2 * EG * 2, ACT = GV + T_BYTES, XMT = ACT + T_BYTES;
+  static constexpr uint32_t GV = GQK + kTok * 2 * EG * 2, DGC = GV + T_BYTES, ACT = DGC + DG_BYTES, XMT = ACT + T_BYTES;
   static constexpr uint32_t END2 = XMT + T_BYTES, END3 = GV + 32768, END4 = DG0 + DG_STRIDE + 32768;
   static constexpr uint32_t PAR = END2 > END3 ? (END2 > END4 ? END2 : END4) : (END3 > END4 ? END3 : END4);
   // per-group parameter slices and accumulators (restaged / flushed every sweep); the gate-bias sums once
@@ -559,9 +561,15 @@ struct PreBwdATC {
   // input blocks staged by bulk async copies (EG / 8 consecutive 2 KB column groups of a [128][E] bf16 token tile):
   // x_mlstm (two stages, each followed by the EG x 4 floats of the 3 tokens in front of the chunk) and d_act (one stage)
   static constexpr uint32_t BLK = EG * kTok * 2, HX_BYTES = EG * 4 * 4, XM_STRIDE = BLK + HX_BYTES, DA_BLK = EG * kTok * 2;
-  static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + 2 * XM_STRIDE;
-  static constexpr uint32_t TOTAL = IN_DA + DA_BLK;
-  static constexpr uint32_t T_GQ = 0, T_DWQK = NQ, T_DWV = NQ + EG, T_DWGA = NQ + 2 * EG, T_DWGX = NQ + 3 * EG;
+  // ... and the cell's dq / dk / dv tiles of the group's heads (one stage, refilled together with d_act)
+  static constexpr uint32_t TILE_B = kTok * DHP * 2, DQ_BLK = 3 * HG * TILE_B;
+  static constexpr uint32_t IN_XM = (PAR + P_N * 4 + 127) / 128 * 128, IN_DA = IN_XM + 2 * XM_STRIDE, IN_DQ = IN_DA + DA_BLK;
+  static constexpr uint32_t TOTAL = IN_DQ + DQ_BLK;
+  // accumulators: gate path | A_1^T B: columns [0, EG) = d[q_proj|k_proj] | A_2^T B: rows [0, EG) x columns [EG, 2 EG) = d v_proj,
+  // rows [EG, EG + 8) = [dig|dfg]^T act (columns [0, EG)) and [dig|dfg]^T x_mlstm (columns [EG, 2 EG)); the other blocks are not read
+  static constexpr uint32_t T_GQ = 0, T_W1 = NQ, T_W2 = NQ + 2 * EG;
+  static constexpr uint32_t T_DWQK = T_W1, T_DWV = T_W2 + EG, T_DWGA = T_W2, T_DWGX = T_W2 + EG;
+  static constexpr int DG_LANE = EG;                  // TMEM lane of gate row 0 in the second product
   static_assert(NQ + 4 * EG <= 512 && 2 * EG <= 128 && TOTAL <= 227 * 1024, "kernel A: a channel group must fit TMEM and shared memory");
 };
 
@@ -598,8 +606,16 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
   };
   auto issue_da = [&](int tile) {
     // channels ch0 .. ch0+EG of the [128][E] bf16 token tile are EG/8 consecutive 2 KB column groups
-    mbar_expect_tx(&bar_da, L::DA_BLK);
+    mbar_expect_tx(&bar_da, L::DA_BLK + L::DQ_BLK);
     bulk_g2s(smem + L::IN_DA, d_act + (static_cast<size_t>(tile) * E + ch0) * (kTok * 2), L::DA_BLK, &bar_da);
+    const int b = tile / g.nc, ch = tile % g.nc, hd0 = ch0 / DH;
+#pragma unroll 1
+    for (int lh = 0; lh < HG; ++lh) {
+      const size_t src = ((static_cast<size_t>(b) * 4 + hd0 + lh) * g.nc + ch) * L::TILE_B;
+      bulk_g2s(smem + L::IN_DQ + (0 * HG + lh) * L::TILE_B, dq + src, L::TILE_B, &bar_da);
+      bulk_g2s(smem + L::IN_DQ + (1 * HG + lh) * L::TILE_B, dk + src, L::TILE_B, &bar_da);
+      bulk_g2s(smem + L::IN_DQ + (2 * HG + lh) * L::TILE_B, dv + src, L::TILE_B, &bar_da);
+    }
   };
   // x_mlstm of the 3 tokens in front of chunk `tile` (zeros in front of the sequence) -> behind stage s
   auto load_halo = [&](int tile, int s) {
@@ -657,6 +673,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid < 8) par[L::A_GB + tid] = 0.f;
+  if (quarter == 0) *reinterpret_cast<uint4*>(smem + L::DGC + tile_off16(kTok, tok, 1)) = make_uint4(0, 0, 0, 0);      // stays zero
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -708,7 +725,7 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
-      const int b = tile / g.nc, ch = tile % g.nc;
+      const int ch = tile % g.nc;
       const int nxt = tile + gridDim.x;
       const bool has_next = nxt < ntiles;
       // one tile ahead: x_mlstm stage, halo and gate gradients of the next tile
@@ -748,10 +765,6 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
           }
         }
         float gq[8], gk[8], gv[8], dsk[8];
-        // the cell's dq / dk / dv: bf16 tiles in the layout of q / k / v (one 16-byte group per thread, 512 B per warp)
-        const size_t gt = ((static_cast<size_t>(b) * 4 + hd0 + lh) * g.nc + ch) * (kTok * DHP * 2) + tile_off16(kTok, tok, d0 / 8);
-        const uint4 uq = __ldg(reinterpret_cast<const uint4*>(dq + gt)), uk = __ldg(reinterpret_cast<const uint4*>(dk + gt)),
-                    uv = __ldg(reinterpret_cast<const uint4*>(dv + gt));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int e = e8 + j;
@@ -767,9 +780,13 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
           first = false;
         }
         unpack8_bf16(*reinterpret_cast<const uint4*>(s_da + tile_off16(kTok, tok, e8 / 8)), dsk);
-        unpack8_bf16(uq, gq);
-        unpack8_bf16(uk, gk);
-        unpack8_bf16(uv, gv);
+        {
+          // the cell's dq / dk / dv: bf16 tiles in the layout of q / k / v, staged together with d_act
+          const unsigned char* sq = smem + L::IN_DQ + lh * L::TILE_B + tile_off16(kTok, tok, d0 / 8);
+          unpack8_bf16(*reinterpret_cast<const uint4*>(sq), gq);
+          unpack8_bf16(*reinterpret_cast<const uint4*>(sq + HG * L::TILE_B), gk);
+          unpack8_bf16(*reinterpret_cast<const uint4*>(sq + 2 * HG * L::TILE_B), gv);
+        }
         float t8[8];
         tmem_ld8(tmem + lane_base + L::T_GQ + (0 * HG + lh) * DHP + d0, t8);
 #pragma unroll
@@ -820,22 +837,23 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         *reinterpret_cast<uint4*>(smem + L::ACT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(a8);
         *reinterpret_cast<uint4*>(smem + L::XMT + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(xm8);
       }
+      if (quarter == 0)       // this tile's bf16 [dig|dfg] behind the g_v columns (same thread staged it one tile ago)
+        *reinterpret_cast<uint4*>(smem + L::DGC + tile_off16(kTok, tok, 0)) =
+            *reinterpret_cast<const uint4*>(smem + L::DG0 + s * L::DG_STRIDE + tile_off16(kTok, tok, 0));
       if (has_next && quarter == 0) stage_dg(dgn, s ^ 1, grp == 0);      // [dig|dfg] of the next tile (its buffer was last read two tiles ago)
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
       if (tid == 0) {
-        const uint32_t dgs = smem_u32(smem + L::DG0 + s * L::DG_STRIDE);
         const uint32_t accu = first_tile ? 0u : 1u;
-        // d[q_proj|k_proj] as a dense (2 EG x EG) product g_{q|k}^T act; only its 4x4 diagonal blocks are read back
-        umma_gemm(tmem + L::T_DWQK, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
-                  umma_idesc(128, EG, true, true), kTok, accu);
-        umma_gemm(tmem + L::T_DWV, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16,
-                  umma_idesc(128, EG, true, true), kTok, accu);
-        // [dig|dfg]^T act and [dig|dfg]^T x_mlstm (rows hh = 0..7 of a 128-row window)
-        umma_gemm(tmem + L::T_DWGA, dgs, 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16, umma_idesc(128, EG, true, true), kTok, accu);
-        umma_gemm(tmem + L::T_DWGX, dgs, 128, kTok * 16, smem_u32(smem + L::XMT), 128, kTok * 16, umma_idesc(128, EG, true, true), kTok, accu);
+        // a tcgen05.mma costs ~80 cycles whatever its shape: TWO chains of eight against B = [act | x_mlstm] (N = 2 EG) give
+        // all four token reductions -- d[q_proj|k_proj] = g_{q|k}^T act (dense 2 EG x EG, only its 4x4 diagonal blocks are read
+        // back), d v_proj = g_v^T x_mlstm, [dig|dfg]^T act and [dig|dfg]^T x_mlstm -- and two blocks nobody reads
+        umma_gemm(tmem + L::T_W1, smem_u32(smem + L::GQK), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
+                  umma_idesc(128, 2 * EG, true, true), kTok, accu);
+        umma_gemm(tmem + L::T_W2, smem_u32(smem + L::GV), 128, kTok * 16, smem_u32(smem + L::ACT), 128, kTok * 16,
+                  umma_idesc(128, 2 * EG, true, true), kTok, accu);
         umma_commit(&bar2);
         if (has_next) {
           issue_mma1(tmem, s ^ 1);      // the gate-path accumulator has been drained by everybody (sync above)
@@ -847,16 +865,17 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
     mbar_wait(&bar2, (it - 1) & 1);
     tc_fence_after();
     // ---- flush the parameter gradients of this channel group
-    // rows hh = 0..7 of the two gate reductions live in TMEM lanes 0..7: warps 0, 4, 8, 12 (quadrant 0) share the columns,
+    // rows hh = 0..7 of the two gate reductions live in TMEM lanes EG..EG+7: the four warps of that quadrant share the columns,
     // 16 (= four 4x4 blocks) at a time; the block-diagonal projections are applied here
-    if ((warp & 3) == 0) {
+    if ((warp & 3) == L::DG_LANE / 32) {
+      const int hh = tok & 31;
 #pragma unroll 1
       for (int c0 = quarter * 16; c0 < EG; c0 += 64) {
         float ga[16], gx[16];
         tmem_ld16(tmem + lane_base + L::T_DWGA + c0, ga);
         tmem_ld16(tmem + lane_base + L::T_DWGX + c0, gx);
-        if (tok < 8) {
-          float* W = tok < 4 ? gr.igate_weight + tok * 3 * E : gr.fgate_weight + (tok - 4) * 3 * E;
+        if (hh < 8) {
+          float* W = hh < 4 ? gr.igate_weight + hh * 3 * E : gr.fgate_weight + (hh - 4) * 3 * E;
 #pragma unroll
           for (int blk = 0; blk < 4; ++blk) {
             const int wb = ((c0 >> 2) + blk) * 16;

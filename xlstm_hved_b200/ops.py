@@ -663,15 +663,15 @@ class _GraphedVilBlockFunction(torch.autograd.Function):
 
     @staticmethod
     @_lib.on_device
-    def forward(ctx, x_tok, slot, *params):
+    def forward(ctx, x_tok, slot, will_backward, *params):
         slot.x_in.copy_(x_tok)
         slot.fwd.replay()
         y = slot.y.clone()
         ctx.slot, ctx.gen = slot, slot.gen
-        if any(ctx.needs_input_grad):
+        if will_backward:
             ctx.release = _SlotRelease(slot, slot.gen)
         else:
-            slot.busy = False
+            slot.busy = False               # no graph is recorded (no_grad / nothing requires grad): the saved state is not needed
         return y
 
     @staticmethod
@@ -688,7 +688,7 @@ class _GraphedVilBlockFunction(torch.autograd.Function):
         slot.bwd.replay()
         dx, flat = slot.dx.clone(), slot.flat.clone()
         slot.busy = False
-        return (dx, None, *_split_param_grads(flat, slot.params))
+        return (dx, None, None, *_split_param_grads(flat, slot.params))
 
 
 def vil_block(x_tok: torch.Tensor, params, reverse: bool = False, eps: float = 1e-6) -> torch.Tensor:
@@ -701,5 +701,6 @@ def vil_block(x_tok: torch.Tensor, params, reverse: bool = False, eps: float = 1
     with torch.cuda.device(x_tok.device):
         slot = _acquire_slot(x_tok, params, reverse, eps)
     if slot is not None:
-        return _GraphedVilBlockFunction.apply(x_tok, slot, *params)
+        will_backward = torch.is_grad_enabled() and (x_tok.requires_grad or any(p.requires_grad for p in params))
+        return _GraphedVilBlockFunction.apply(x_tok, slot, will_backward, *params)
     return VilBlockFunction.apply(x_tok, bool(reverse), eps, *params)
