@@ -594,8 +594,11 @@ class _BlockGraphSlot:
         self.x_in = torch.empty_strided(x_like.shape, x_like.stride(), device=dev, dtype=torch.float32)
         self.x_in.copy_(x_like)
         self._warm(lambda: vil_block_fwd(self.x_in, params, reverse, eps))
+        # captures are serialised by _GRAPH_LOCK (the caller holds it) and run on a stream of their own: torch.cuda.graph's default
+        # capture stream is shared by all threads
+        self.cap_stream = torch.cuda.Stream()
         self.fwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.fwd, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.fwd, stream=self.cap_stream, capture_error_mode="thread_local"):
             self.y, self.ws = vil_block_fwd(self.x_in, params, reverse, eps)
 
     @staticmethod
@@ -608,12 +611,14 @@ class _BlockGraphSlot:
         cur.wait_stream(side)
 
     def capture_bwd(self, dy):
-        self.dy_in = torch.empty_strided(self.y.shape, self.y.stride(), device=self.y.device, dtype=torch.float32)
-        self.dy_in.copy_(dy)
-        self._warm(lambda: self._bwd_raw())
-        self.bwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.bwd, capture_error_mode="thread_local"):
-            self.dx, self.flat = self._bwd_raw()
+        with _GRAPH_LOCK:
+            self.dy_in = torch.empty_strided(self.y.shape, self.y.stride(), device=self.y.device, dtype=torch.float32)
+            self.dy_in.copy_(dy)
+            self._warm(lambda: self._bwd_raw())
+            bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(bwd, stream=self.cap_stream, capture_error_mode="thread_local"):
+                self.dx, self.flat = self._bwd_raw()
+            self.bwd = bwd
 
     def _bwd_raw(self):
         dx, grads = vil_block_bwd(self.x_in, self.dy_in, self.params, self.reverse, self.ws, self.eps)
