@@ -336,6 +336,8 @@ def run_gpu(args):
     device = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local, world)          # before any pinned allocation
     if world > 1:
+        # NCCL writes its version banner (and whatever NCCL_DEBUG asks for) to stdout by default: stdout carries the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     from xlstm_hved_b200 import _lib
     lib = _lib.load_library()
