@@ -301,6 +301,31 @@ int xhved_vil_block_fwd(const float* x, const xhved_vil_params* p, const xhved_v
 int xhved_vil_block_bwd(const float* x, const float* dy, const xhved_vil_params* p, const xhved_vil_shape* sh, float eps, void* saved,
                         void* scratch, float* dx, float* param_grads, void* stream);
 
+/* ---------------------------------------------------------------- ViL blocks wider than the fused K2 / K3 kernels
+ * dim 128 / 256 (E = 256 / 512, head dim 64 / 128).  The block's three Linear layers (LayerNorm +
+ * proj_up, proj_down) stay plain GEMMs on the caller's side; these four kernels fuse everything between them and the cell.
+ * Row-major tensors are in NATURAL token order (B, S, .), the direction flip is an index map (reverse != 0).
+ *   up     (B, S, 2E) fp32   proj_up output [x_mlstm | z] (vision_lstm.py:427-428);  d_up: its gradient, same layout
+ *   act    (B, S, E)  fp32   SiLU(conv(x_mlstm)), kept for the skip (437) and the backward
+ *   hg     (B, S, E)  fp32   (outnorm(h) + skip * act) * SiLU(z): the row proj_down multiplies (437-443)
+ *   q / k / v / h / dh / dq / dk / dv tiles, padded gates: as for xhved_mlstm_fwd / _bwd (dhp = E / 4)
+ *   dg_rm  (B, S, 8)  fp32   [dig | dfg] in token order: the caller takes [dig|dfg]^T act and [dig|dfg]^T x_mlstm as two plain
+ *                            GEMMs and applies the 4x4 projections to get the gate-weight gradient (as vil_pre.cu does)
+ * Parameter gradients (g_*) are accumulated with atomics: zero them first. */
+int xhved_vil_wide_pre_fwd(const float* up, const float* conv_w, const float* conv_b, const float* qw, const float* kw, const float* vw,
+                           const float* igw, const float* igb, const float* fgw, const float* fgb, int B, int S, int E, int reverse,
+                           void* q_tiles, void* k_tiles, void* v_tiles, float* ig_padded, float* fg_padded, float* act, void* stream);
+int xhved_vil_wide_post_fwd(const void* h_tiles, const float* act, const float* up, const float* outnorm_w, const float* skip, int B,
+                            int S, int E, int reverse, float* hg, void* stream);
+int xhved_vil_wide_post_bwd(const float* dhg, const void* h_tiles, const float* act, const float* up, const float* outnorm_w,
+                            const float* skip, int B, int S, int E, int reverse, void* dh_tiles, float* d_act, float* d_up,
+                            float* g_outnorm_w, float* g_skip, void* stream);
+int xhved_vil_wide_pre_bwd(const float* up, const float* conv_w, const float* conv_b, const float* qw, const float* kw, const float* vw,
+                           const float* igw, const float* fgw, int B, int S, int E, int reverse, const void* dq_tiles,
+                           const void* dk_tiles, const void* dv_tiles, const float* dig, const float* dfg, const float* d_act,
+                           float* d_up, float* dg_rm, float* g_conv_w, float* g_conv_b, float* g_qw, float* g_kw, float* g_vw,
+                           void* stream);
+
 /* dst[i] = sum_r src[r*stride + i], i < n  (reduction of the gradient replicas above). */
 int xhved_reduce_replicas(const float* src, int replicas, int64_t stride, int64_t n, float* dst, void* stream);
 

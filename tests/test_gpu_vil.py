@@ -325,15 +325,16 @@ def test_vil_block_reentrant_on_two_streams_from_two_threads():
             assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("dim,S", [(128, 300), (256, 200)])
-def test_wide_block_cell_on_kernels_vs_oracle(dim, S):
-    """blocks of f_maps 16 / 32 (dim 128 / 256, head dim 64 / 128).  K2 / K3 are not fused at these
-    widths: the cell (forward AND backward, dhp = 64 / 128) runs on the tcgen05 kernels, the per-token glue as torch ops.
-    Forward and all gradients against the fp64 oracle of the whole block."""
+@pytest.mark.parametrize("dim,S,rev", [(128, 300, True), (256, 200, True), (128, 257, False), (256, 128, False), (128, 2, False)])
+def test_wide_block_cell_on_kernels_vs_oracle(dim, S, rev):
+    """blocks of f_maps 16 / 32 (dim 128 / 256, head dim 64 / 128).  The three Linear layers are
+    library GEMMs at these widths; the cell (forward AND backward, dhp = 64 / 128) runs on the tcgen05 kernels and everything
+    between the GEMMs and the cell on the fused glue kernels of csrc/vil_wide.cu (ops.vil_block_wide), both directions, ragged
+    and tiny lengths.  Forward and all gradients against the fp64 oracle of the whole block."""
     import xlstm_hved_b200 as xh
     from xlstm_hved_b200 import ops
     torch.manual_seed(dim)
-    blk = xh.ViLBlock(dim, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT).cuda()
+    blk = xh.ViLBlock(dim, xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT if rev else xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT).cuda()
     with torch.no_grad():
         for n, p in blk.named_parameters():
             if n.endswith(("igate.weight", "fgate.weight")):
@@ -350,7 +351,7 @@ def test_wide_block_cell_on_kernels_vs_oracle(dim, S):
     grads = torch.autograd.grad(y, [xc] + [named[k] for k in keys], gy.cuda())
     p64 = {k: v.double().requires_grad_() for k, v in sd.items()}
     x64 = x.double().requires_grad_()
-    ref = restate.vil_block(x64, p64, reverse=True, cell=lambda *a: restate.mlstm_chunkwise(*a, chunk=128))
+    ref = restate.vil_block(x64, p64, reverse=rev, cell=lambda *a: restate.mlstm_chunkwise(*a, chunk=128))
     ref_grads = torch.autograd.grad(ref, [x64] + [p64[k] for k in keys], gy.double())
     br, br_ref = y.detach().cpu().double() - x.double(), ref.detach() - x.double()
     print(dim, "branch rel_l2", rel_l2(br, br_ref))

@@ -229,11 +229,11 @@ FUSED_DIMS = (16, 32, 64)        # model dims the fused K2 / K3 kernels are buil
 def vil_block_forward(block, x: torch.Tensor) -> torch.Tensor:
     """ViLBlock.forward (vision_lstm.py:499-502): x + layer(norm(x)) for a (B,S,C) token tensor or view.
 
-    dims 16 / 32 / 64: the fused pre / cell / post kernels.  Wider blocks (f_maps 16 / 32: dim 128 / 256, head dim 64 / 128,
-    SURVEY 8d config 2 (iii)) are not fused yet: their S x S-shaped work -- the mLSTM cell, forward and backward -- runs on
-    the same tcgen05 kernels, the per-token glue around it (norm, projections, 4-tap conv, gate Linear) as device-side torch
-    ops: the mirror modules' own forwards, or, for a patched reference block, the reference's own ``forward`` with
-    ``parallel_stabilized_simple`` rebound to the kernels (patch.py)."""
+    dims 16 / 32 / 64: the fused pre / cell / post kernels.  dims 128 / 256 (f_maps 16 / 32, head dim 64 / 128, SURVEY 8d
+    config 2 (iii)): ``ops.vil_block_wide`` -- the three Linear layers as library GEMMs, the cell on the tcgen05 kernels and
+    everything between them on the fused glue kernels of csrc/vil_wide.cu.  Any other width: the cell on the kernels, the
+    per-token glue as device-side torch ops (the mirror modules' own forwards, or, for a patched reference block, the
+    reference's own ``forward`` with ``parallel_stabilized_simple`` rebound to the kernels, patch.py)."""
     _require_device(x)
     dp = getattr(block.drop_path, "drop_prob", 0.0)
     if dp != 0.0 and block.training:
@@ -242,6 +242,8 @@ def vil_block_forward(block, x: torch.Tensor) -> torch.Tensor:
         raise NotImplementedError("fused ViL block: qkv_block_size must be 4 and the norm bias-free (reference defaults)")
     if x.shape[-1] in FUSED_DIMS:
         return ops.vil_block(x, vil_block_params(block), reverse=_is_reverse(block.direction))
+    if x.shape[-1] in ops.WIDE_DIMS:                    # the three Linear layers as library GEMMs, the rest fused (csrc/vil_wide.cu)
+        return ops.vil_block_wide(x, vil_block_params(block), reverse=_is_reverse(block.direction))
     stock = getattr(type(block), "_xhved_base", None)
     if stock is not None:                               # a patched reference block: its own glue, our cell
         return stock.forward(block, x)

@@ -709,3 +709,82 @@ def vil_block(x_tok: torch.Tensor, params, reverse: bool = False, eps: float = 1
         will_backward = torch.is_grad_enabled() and (x_tok.requires_grad or any(p.requires_grad for p in params))
         return _GraphedVilBlockFunction.apply(x_tok, slot, will_backward, *params)
     return VilBlockFunction.apply(x_tok, bool(reverse), eps, *params)
+
+
+# ----------------------------------------------------------------------------- ViL blocks wider than the fused kernels
+WIDE_DIMS = (128, 256)        # f_maps 16 / 32: E = 256 / 512, head dim 64 / 128 (csrc/vil_wide.cu)
+
+
+class _WideCoreFunction(torch.autograd.Function):
+    """Everything of a wide ViL block between proj_up and proj_down (vision_lstm.py:428-440): conv, SiLU, block-diagonal q / k / v,
+    gates, the cell, per-head norm, skip and z gate -- four fused glue kernels (csrc/vil_wide.cu) around the tcgen05 cell kernels.
+    up: (B, S, 2E) fp32 contiguous in natural token order; returns hg (B, S, E)."""
+
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, up, reverse, eps, conv_w, conv_b, qw, kw, vw, igw, igb, fgw, fgb, ow, sk):
+        lib = _lib.load_library()
+        B, S, E2 = up.shape
+        E = E2 // 2
+        prm = [_f32c(t.detach()) for t in (conv_w, conv_b, qw, kw, vw, igw, igb, fgw, fgb, ow, sk)]
+        buf = CellBuffers(4 * B, S, E // 4, up.device)
+        act = torch.empty(B, S, E, device=up.device, dtype=torch.float32)
+        check(lib.xhved_vil_wide_pre_fwd(ptr(up), *[ptr(t) for t in prm[:9]], B, S, E, int(reverse), ptr(buf.q), ptr(buf.k), ptr(buf.v),
+                                         ptr(buf.ig), ptr(buf.fg), ptr(act), stream()), "xhved_vil_wide_pre_fwd")
+        mlstm_fwd_tiles(buf, eps)
+        hg = torch.empty(B, S, E, device=up.device, dtype=torch.float32)
+        check(lib.xhved_vil_wide_post_fwd(ptr(buf.h), ptr(act), ptr(up), ptr(prm[9]), ptr(prm[10]), B, S, E, int(reverse), ptr(hg), stream()),
+              "xhved_vil_wide_post_fwd")
+        ctx.buf, ctx.reverse, ctx.eps = buf, bool(reverse), eps
+        ctx.save_for_backward(up, act, *prm)
+        return hg
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dhg):
+        lib = _lib.load_library()
+        up, act, *prm = ctx.saved_tensors
+        conv_w, conv_b, qw, kw, vw, igw, igb, fgw, fgb, ow, sk = prm
+        buf = ctx.buf
+        B, S, E2 = up.shape
+        E = E2 // 2
+        dev = up.device
+        dhg = _f32c(dhg)
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+        d_up, d_act, dh_tiles = torch.empty_like(up), torch.empty_like(act), torch.empty_like(buf.h)
+        g_ow, g_sk = z(E), z(E)
+        check(lib.xhved_vil_wide_post_bwd(ptr(dhg), ptr(buf.h), ptr(act), ptr(up), ptr(ow), ptr(sk), B, S, E, int(ctx.reverse), ptr(dh_tiles),
+                                          ptr(d_act), ptr(d_up), ptr(g_ow), ptr(g_sk), stream()), "xhved_vil_wide_post_bwd")
+        gb = mlstm_bwd_tiles(buf, dh_tiles, ctx.eps)
+        dg_rm = torch.empty(B, S, 8, device=dev, dtype=torch.float32)
+        g_cw, g_cb, g_qw, g_kw, g_vw = z(*conv_w.shape), z(E), z(*qw.shape), z(*kw.shape), z(*vw.shape)
+        check(lib.xhved_vil_wide_pre_bwd(ptr(up), ptr(conv_w), ptr(conv_b), ptr(qw), ptr(kw), ptr(vw), ptr(igw), ptr(fgw), B, S, E,
+                                         int(ctx.reverse), ptr(gb.dq), ptr(gb.dk), ptr(gb.dv), ptr(gb.dig), ptr(gb.dfg), ptr(d_act), ptr(d_up),
+                                         ptr(dg_rm), ptr(g_cw), ptr(g_cb), ptr(g_qw), ptr(g_kw), ptr(g_vw), stream()), "xhved_vil_wide_pre_bwd")
+        # gate Linear(3E -> 4) x 2: d bias = sum over tokens; d weight THROUGH the 4x4 projections (csrc/vil_pre.cu):
+        # [dig|dfg]^T q = ([dig|dfg]^T act) Wq^T (k alike; v with x_mlstm and Wv): two plain (8 x T)(T x E) GEMMs
+        dg2 = dg_rm.view(-1, 8)
+        r_a = (dg2.t() @ act.view(-1, E)).view(8, E // 4, 4)
+        r_x = (dg2.t() @ up.view(-1, E2)[:, :E]).view(8, E // 4, 4)
+        g_w = torch.cat([torch.einsum("gbd,bod->gbo", r_a, qw).reshape(8, E), torch.einsum("gbd,bod->gbo", r_a, kw).reshape(8, E),
+                         torch.einsum("gbd,bod->gbo", r_x, vw).reshape(8, E)], dim=1)
+        g_b = dg2.sum(0)
+        return (d_up, None, None, g_cw, g_cb, g_qw, g_kw, g_vw, g_w[:4].contiguous(), g_b[:4].contiguous(), g_w[4:].contiguous(),
+                g_b[4:].contiguous(), g_ow, g_sk)
+
+
+def vil_block_wide(x_tok: torch.Tensor, params, reverse: bool = False, eps: float = 1e-6) -> torch.Tensor:
+    """ViLBlock.forward (vision_lstm.py:499-502) at dim 128 / 256: LayerNorm + proj_up and proj_down + residual are plain library
+    GEMMs / torch ops (per token, so the direction flip does not touch them), everything between them is _WideCoreFunction."""
+    if not x_tok.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    if x_tok.shape[-1] not in WIDE_DIMS:
+        raise RuntimeError(f"vil_block_wide covers dims {WIDE_DIMS}")
+    if x_tok.dtype != torch.float32:
+        x_tok = x_tok.float()
+    norm_w, up_w, conv_w, conv_b, qw, kw, vw, igw, igb, fgw, fgb, ow, sk, down_w = params
+    C = x_tok.shape[-1]
+    xn = torch.nn.functional.layer_norm(x_tok, (C,), weight=1.0 + norm_w, bias=None, eps=1e-5)
+    up = torch.nn.functional.linear(xn, up_w).contiguous()
+    hg = _WideCoreFunction.apply(up, bool(reverse), eps, conv_w, conv_b, qw, kw, vw, igw, igb, fgw, fgb, ow, sk)
+    return x_tok + torch.nn.functional.linear(hg, down_w)
