@@ -326,6 +326,12 @@ int xhved_vil_wide_pre_bwd(const float* up, const float* conv_w, const float* co
                            float* d_up, float* dg_rm, float* g_conv_w, float* g_conv_b, float* g_qw, float* g_kw, float* g_vw,
                            void* stream);
 
+/* fp32 (rows, cols) row-major -> bf16 (rows, 3 cols): [hi | lo | hi] (b_side = 0) or [hi | hi | lo] (b_side != 0), hi = the value
+ * rounded to bf16, lo = the rounded residual.  One bf16 GEMM of an a-side and a b-side operand over the tripled contraction
+ * dimension is the 3-product hi*hi + lo*hi + hi*lo with fp32 accumulation (~16 mantissa bits): how the plain Linear layers of
+ * the wide blocks run on the tensor cores through the library GEMM.  cols % 8 == 0. */
+int xhved_split_hilo_cat(const float* x, int64_t rows, int cols, int b_side, void* out, void* stream);
+
 /* dst[i] = sum_r src[r*stride + i], i < n  (reduction of the gradient replicas above). */
 int xhved_reduce_replicas(const float* src, int replicas, int64_t stride, int64_t n, float* dst, void* stream);
 

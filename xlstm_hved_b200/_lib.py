@@ -97,6 +97,7 @@ SYMBOLS = {
     "xhved_vil_wide_post_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 2,
     "xhved_vil_wide_post_bwd": [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 6,
     "xhved_vil_wide_pre_bwd": [c_void_p] * 8 + [c_int] * 4 + [c_void_p] * 14,
+    "xhved_split_hilo_cat": [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p],
     "xhved_vil_block_workspace": [c_int, c_int, c_int, c_int, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)],
     "xhved_vil_block_fwd": [c_void_p, POINTER(VilParams), POINTER(VilShape), c_float, c_void_p, c_void_p, c_void_p],
     "xhved_vil_block_bwd": [c_void_p, c_void_p, POINTER(VilParams), POINTER(VilShape), c_float, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -510,6 +510,24 @@ __global__ void __launch_bounds__(kTok* NP, 1) vil_wide_pre_bwd_kernel(const flo
   for (int i = tid; i < E; i += kTok * NP) atomicAdd(g_cb + i, sm[M::A_CB + i]);
 }
 
+// fp32 (rows, cols) -> bf16 (rows, 3 cols): [hi | lo | hi] (b_side = 0) or [hi | hi | lo] (b_side != 0), so that ONE bf16
+// tensor-core GEMM over the tripled contraction dimension gives hi*hi + lo*hi + hi*lo with fp32 accumulation (~16 mantissa bits)
+__global__ void split_hilo_cat_kernel(const float* __restrict__ x, int64_t rows, int cols, int b_side, unsigned char* __restrict__ out) {
+  const int64_t groups = rows * (cols / 8);
+  for (int64_t gi = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; gi < groups; gi += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = gi / (cols / 8);
+    const int c = static_cast<int>(gi % (cols / 8)) * 8;
+    float v[8];
+    ld8(x + r * cols + c, v);
+    uint4 hi, lo;
+    split8_hilo(v, hi, lo);
+    unsigned char* o = out + (r * 3 * cols + c) * 2;
+    *reinterpret_cast<uint4*>(o) = hi;
+    *reinterpret_cast<uint4*>(o + cols * 2) = b_side ? hi : lo;
+    *reinterpret_cast<uint4*>(o + 2 * cols * 2) = b_side ? lo : hi;
+  }
+}
+
 static int make_geom(int B, int S, int reverse, Geom* g) {
   if (B <= 0 || S <= 0) return XHVED_ERR_BAD_SHAPE;
   g->B = B, g->S = S, g->nc = (S + kTok - 1) / kTok, g->Sp = g->nc * kTok, g->reverse = reverse;
@@ -620,4 +638,12 @@ extern "C" int xhved_vil_wide_pre_bwd(const float* up, const float* conv_w, cons
     case 512: return launch_pre_bwd<512>(up, p, g, dq_tiles, dk_tiles, dv_tiles, dig, dfg, d_act, d_up, dg_rm, g_conv_w, g_conv_b, g_qw, g_kw, g_vw, st);
     default: return XHVED_ERR_UNSUPPORTED_DIM;
   }
+}
+
+extern "C" int xhved_split_hilo_cat(const float* x, int64_t rows, int cols, int b_side, void* out, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0 || cols % 8) return XHVED_ERR_BAD_ARG;
+  const int64_t groups = rows * (cols / 8);
+  const int grid = static_cast<int>(groups / 256 + 1 < 148 * 16 ? groups / 256 + 1 : 148 * 16);
+  split_hilo_cat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols, b_side, static_cast<unsigned char*>(out));
+  return (int)cudaGetLastError();
 }

@@ -773,6 +773,45 @@ class _WideCoreFunction(torch.autograd.Function):
                 g_b[4:].contiguous(), g_ow, g_sk)
 
 
+def _split_hilo_cat(x2d: torch.Tensor, b_side: bool = False) -> torch.Tensor:
+    """fp32 (rows, cols) -> bf16 (rows, 3 cols) = [hi | lo | hi] (or [hi | hi | lo] for the b side), see xhved_split_hilo_cat."""
+    lib = _lib.load_library()
+    x2d = _f32c(x2d)
+    rows, cols = x2d.shape
+    out = torch.empty(rows, 3 * cols, device=x2d.device, dtype=torch.bfloat16)
+    check(lib.xhved_split_hilo_cat(ptr(x2d), rows, cols, int(b_side), ptr(out), stream()), "xhved_split_hilo_cat")
+    return out
+
+
+class _HiLoLinearFunction(torch.autograd.Function):
+    """y = x W^T (nn.Linear without bias) as bf16 tensor-core GEMMs with fp32-class accuracy: the operands are split into bf16
+    hi + lo and ONE library GEMM over the tripled contraction dimension gives hi*hi + lo*hi + hi*lo with fp32 accumulation
+    (the 3-product of csrc/umma.cuh, ~16 mantissa bits).  x: (T, K) fp32, W: (N, K) fp32 -> (T, N) fp32."""
+
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, w):
+        xc = _split_hilo_cat(x)                                   # (T, 3K)  [hi | lo | hi]
+        wc = _split_hilo_cat(w, b_side=True)                      # (N, 3K)  [hi | hi | lo]
+        ctx.save_for_backward(xc, w)
+        return torch.mm(xc, wc.t(), out_dtype=torch.float32)
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dy):
+        xc, w = ctx.saved_tensors
+        n, k = w.shape
+        dyc = _split_hilo_cat(dy)                                 # (T, 3N)  [hi | lo | hi]
+        # dx = dy W: contraction over N, the b side stacked along it ([hi ; hi ; lo] rows)
+        wr = _split_hilo_cat(w.t().contiguous(), b_side=True).t().contiguous()        # (3N, K)
+        dx = torch.mm(dyc, wr, out_dtype=torch.float32)
+        # dW = dy^T x: contraction over the tokens, the three products separately (their outputs are small)
+        dyh, dyl, xh, xl = dyc[:, :n], dyc[:, n:2 * n], xc[:, :k], xc[:, k:2 * k]
+        dw = (torch.mm(dyh.t(), xh, out_dtype=torch.float32) + torch.mm(dyl.t(), xh, out_dtype=torch.float32) +
+              torch.mm(dyh.t(), xl, out_dtype=torch.float32))
+        return dx, dw
+
+
 def vil_block_wide(x_tok: torch.Tensor, params, reverse: bool = False, eps: float = 1e-6) -> torch.Tensor:
     """ViLBlock.forward (vision_lstm.py:499-502) at dim 128 / 256: LayerNorm + proj_up and proj_down + residual are plain library
     GEMMs / torch ops (per token, so the direction flip does not touch them), everything between them is _WideCoreFunction."""
@@ -785,6 +824,7 @@ def vil_block_wide(x_tok: torch.Tensor, params, reverse: bool = False, eps: floa
     norm_w, up_w, conv_w, conv_b, qw, kw, vw, igw, igb, fgw, fgb, ow, sk, down_w = params
     C = x_tok.shape[-1]
     xn = torch.nn.functional.layer_norm(x_tok, (C,), weight=1.0 + norm_w, bias=None, eps=1e-5)
-    up = torch.nn.functional.linear(xn, up_w).contiguous()
+    Bq, Sq = x_tok.shape[:2]
+    up = _HiLoLinearFunction.apply(xn.reshape(-1, C), up_w).view(Bq, Sq, -1)
     hg = _WideCoreFunction.apply(up, bool(reverse), eps, conv_w, conv_b, qw, kw, vw, igw, igb, fgw, fgb, ow, sk)
-    return x_tok + torch.nn.functional.linear(hg, down_w)
+    return x_tok + _HiLoLinearFunction.apply(hg.reshape(-1, hg.shape[-1]), down_w).view(Bq, Sq, C)
