@@ -80,15 +80,21 @@ def randomise_like_init_weights(mod, ns, seed):
                 p.add_(0.1 * torch.randn_like(p))
 
 
-def gen_block(ns):
+BLOCK_CASES = {
+    "dim32_s200_fwd": (32, 200, 2, False, 10),
+    "dim32_s200_rev": (32, 200, 2, True, 11),
+    "dim16_s150_fwd": (16, 150, 1, False, 12),      # 32^3-stage dims: E=32, DH=8
+    "dim64_s140_rev": (64, 140, 1, True, 13),       # class default f_maps=8: DH=32
+}
+WIDE_BLOCK_CASES = {
+    "dim128_s160_rev": (128, 160, 1, True, 14),     # f_maps = 16: E = 256, DH = 64
+}
+
+
+def gen_block(ns, table=None, fname="vil_block.pt"):
     vl = ns.vision_lstm
     cases = {}
-    for name, (dim, S, B, rev, seed) in {
-        "dim32_s200_fwd": (32, 200, 2, False, 10),
-        "dim32_s200_rev": (32, 200, 2, True, 11),
-        "dim16_s150_fwd": (16, 150, 1, False, 12),      # 32^3-stage dims: E=32, DH=8
-        "dim64_s140_rev": (64, 140, 1, True, 13),       # class default f_maps=8: DH=32
-    }.items():
+    for name, (dim, S, B, rev, seed) in (table or BLOCK_CASES).items():
         direction = vl.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT if rev else vl.SequenceTraversal.ROWWISE_FROM_TOP_LEFT
         blk = vl.ViLBlock(dim=dim, direction=direction).double()
         randomise_like_init_weights(blk, ns, seed)
@@ -102,7 +108,11 @@ def gen_block(ns):
             dim=dim, reverse=rev, x=x.detach(), y=y.detach(), dy=dy, dx=grads[0],
             state_dict={k_: v_.detach().clone() for k_, v_ in blk.state_dict().items()},
             param_grads={n: g for n, g in zip(params.keys(), grads[1:])})
-    torch.save(cases, os.path.join(OUT, "vil_block.pt"))
+    torch.save(cases, os.path.join(OUT, fname))
+
+
+def gen_block_wide(ns):
+    gen_block(ns, WIDE_BLOCK_CASES, "vil_block_wide.pt")
 
 
 def gen_wrapper(ns):
@@ -257,7 +267,7 @@ def main():
     assert ns is not None, "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]            # e.g. `python oracle/make_golden.py smvae_extras` regenerates one file
-    gens = dict(cell=gen_cell, vil_block=gen_block, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras, losses=gen_losses,
+    gens = dict(cell=gen_cell, vil_block=gen_block, vil_block_wide=gen_block_wide, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras, losses=gen_losses,
                 model_boundary=gen_model_boundary)
     for name, fn in gens.items():
         if not only or name in only:

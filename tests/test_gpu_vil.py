@@ -503,3 +503,24 @@ def test_block_graphs_from_two_threads_on_two_streams():
     finally:
         ops.set_block_graphs("auto")
         ops._GRAPH_POOLS.clear()
+
+
+def test_wide_block_matches_reference_golden_dim128():
+    """A block of dim 128 (f_maps 16) against the fixture the REAL reference wrote (oracle/make_golden.py vil_block_wide: fp64
+    vision_lstm.ViLBlock forward + autograd gradients): the reference's state_dict loads into the mirror module unchanged
+    (strict), output and all 15 gradients within the bf16 budget."""
+    import xlstm_hved_b200 as xh
+    c = load_golden("vil_block_wide.pt")["dim128_s160_rev"]
+    blk = xh.ViLBlock(c["dim"], xh.SequenceTraversal.ROWWISE_FROM_BOT_RIGHT if c["reverse"] else xh.SequenceTraversal.ROWWISE_FROM_TOP_LEFT)
+    blk.load_state_dict({k: v.float() for k, v in c["state_dict"].items()}, strict=True)
+    blk = blk.cuda()
+    x = c["x"].float().cuda().requires_grad_()
+    y = blk(x)
+    named = dict(blk.named_parameters())
+    names = list(c["param_grads"])
+    grads = torch.autograd.grad(y, [x] + [named[n] for n in names], c["dy"].float().cuda())
+    br, br_ref = y.detach().cpu().double() - c["x"], c["y"] - c["x"]
+    assert rel_l2(br, br_ref) < TOL_L2
+    assert rel_l2(grads[0].cpu().double() - c["dy"], c["dx"] - c["dy"]) < 3e-2
+    for g, n in zip(grads[1:], names):
+        assert rel_l2(g, c["param_grads"][n]) < 3e-2, n
