@@ -192,3 +192,27 @@ def test_cell_backward_widest_head_vs_oracle(B, NH, S, DH):
     for a, b, n in zip(got, emu, ("dq", "dk", "dv", "dig", "dfg")):
         print("unit variance", n, rel_l2(a, b))
         assert rel_l2(a, b) < 3e-2, n
+
+
+@pytest.mark.parametrize("NH,S,DH", [(2, 8320, 64), (1, 8200, 128), (2, 8193, 32)])
+def test_cell_long_sequence_wide_heads_fwd_bwd_vs_oracle(NH, S, DH):
+    """Sequences of 64 chunks and more take the lane = chunk state scan (mlstm_state_scan_par_kernel: warp scans of the affine
+    maps, blocks of 32 chunks with a carry): 65 chunks -- two full blocks and a ragged third -- at the head dims of the wide
+    blocks (and dhp 32, where the persistent chunk-state kernel feeds it), forward and backward against the fp64 oracle."""
+    from xlstm_hved_b200 import ops
+    B = 1
+    g = torch.Generator().manual_seed(S + DH)
+    q, k, v = [0.06 * torch.randn(B, NH, S, DH, generator=g), 0.06 * torch.randn(B, NH, S, DH, generator=g),
+               0.12 * torch.randn(B, NH, S, DH, generator=g)]
+    ig, fg = -0.67 + 0.48 * torch.randn(B, NH, S, 1, generator=g), 0.41 + 1.03 * torch.randn(B, NH, S, 1, generator=g)
+    dh = torch.randn(B, NH, S, DH, generator=g)
+    leaves = [t.double().requires_grad_() for t in (q, k, v, ig, fg)]
+    h_ref = restate.mlstm_chunkwise(*leaves, chunk=512)
+    ref = torch.autograd.grad(h_ref, leaves, dh.double())
+    cl = [t.cuda().requires_grad_() for t in (q, k, v, ig, fg)]
+    h = ops.parallel_stabilized_simple(*cl)
+    assert rel_l2(h, h_ref.detach()) < 2e-2
+    got = torch.autograd.grad(h, cl, dh.cuda())
+    for a, b, n in zip(got, ref, ("dq", "dk", "dv", "dig", "dfg")):
+        print(S, DH, n, rel_l2(a, b))
+        assert rel_l2(a, b) < 2e-2, n
