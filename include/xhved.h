@@ -281,7 +281,9 @@ int xhved_vil_post_bwd(const float* dy, const void* h_tiles, const void* act, co
  * dz (bf16 token tiles) computes dx = dy + d(branch)/dx (dy and dx both use the y_* strides of sh) and accumulates parameter
  * gradients.  q_tiles / k_tiles / v_tiles are accepted for ABI stability and not read: the gate-weight gradient is taken
  * through the block-diagonal projections ([dig|dfg]^T q = ([dig|dfg]^T act) Wq^T).  Scratch: ws_dconv, ws_dxmv, bf16 token
- * tiles (token_tile_bytes each).  Every kernel-to-kernel tensor of the backward is bf16: its consumers round to bf16 MMA
+ * tiles (token_tile_bytes each).  Rows of dq / dk / dv / dig / dfg / d_act behind the end of a sequence (S not a multiple
+ * of 128) must be zero, as xhved_mlstm_bwd and xhved_vil_post_bwd write them: the kernel does not mask them again.
+ * Every kernel-to-kernel tensor of the backward is bf16: its consumers round to bf16 MMA
  * operands anyway, and the fp32 versions were 2.9 KB of HBM traffic per token and block (dim 32). */
 int xhved_vil_pre_bwd(const float* x, const float* dy, const void* xm, const void* q_tiles, const void* k_tiles, const void* v_tiles,
                       const void* dq, const void* dk, const void* dv, const float* dig, const float* dfg, const void* d_act,

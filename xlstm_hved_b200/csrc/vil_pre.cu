@@ -734,7 +734,6 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         load_halo(nxt, s ^ 1);
         if (quarter == 0) load_dg(nxt, dgn);
       }
-      const bool valid = ch * kTok + tok < g.S;
       mbar_wait(&bar_xm[s], (it >> 1) & 1);
       if (!first_tile) {      // the previous tile's weight-gradient products still read the operand tiles this loop rewrites
         mbar_wait(&bar2, (it - 1) & 1);
@@ -787,38 +786,43 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
           unpack8_bf16(*reinterpret_cast<const uint4*>(sq + HG * L::TILE_B), gk);
           unpack8_bf16(*reinterpret_cast<const uint4*>(sq + 2 * HG * L::TILE_B), gv);
         }
+        // Rows beyond the end of a sequence need no masking here: every upstream gradient is exactly zero there (the cell writes
+        // zero dq / dk / dv / dig / dfg for rows whose gates are the padding values, vil_post_bwd zero d_act), x_mlstm is zero and
+        // the activation finite, so dconv, dxmv and the token reductions vanish by themselves (xhved.h: xhved_vil_pre_bwd).
         float t8[8];
         tmem_ld8(tmem + lane_base + L::T_GQ + (0 * HG + lh) * DHP + d0, t8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gq[j] = valid ? gq[j] + t8[j] : 0.f;
+        for (int j = 0; j < 8; ++j) gq[j] += t8[j];
         tmem_ld8(tmem + lane_base + L::T_GQ + (1 * HG + lh) * DHP + d0, t8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gk[j] = valid ? gk[j] + t8[j] : 0.f;
+        for (int j = 0; j < 8; ++j) gk[j] += t8[j];
         tmem_ld8(tmem + lane_base + L::T_GQ + (2 * HG + lh) * DHP + d0, t8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gv[j] = valid ? gv[j] + t8[j] : 0.f;
+        for (int j = 0; j < 8; ++j) gv[j] += t8[j];
+        // transposed 4x4 blocks: d act = Wq^T g_q + Wk^T g_k, d x_mlstm (v path) = Wv^T g_v; weight rows as 128-bit loads
         float da8[8], dxv8[8];
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
           const int wb = ((e8 >> 2) + blk) * 16;
+          float sa[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int d = 0; d < 4; ++d) {
-            float sa = 0.f, sv = 0.f;
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              sa += par[L::P_WQ + wb + o * 4 + d] * gq[blk * 4 + o] + par[L::P_WK + wb + o * 4 + d] * gk[blk * 4 + o];
-              sv += par[L::P_WV + wb + o * 4 + d] * gv[blk * 4 + o];
-            }
-            da8[blk * 4 + d] = sa, dxv8[blk * 4 + d] = sv;
+          for (int o = 0; o < 4; ++o) {
+            const float4 wq = *reinterpret_cast<const float4*>(par + L::P_WQ + wb + o * 4);
+            const float4 wk = *reinterpret_cast<const float4*>(par + L::P_WK + wb + o * 4);
+            const float4 wv = *reinterpret_cast<const float4*>(par + L::P_WV + wb + o * 4);
+            const float a = gq[blk * 4 + o], b2 = gk[blk * 4 + o], c2 = gv[blk * 4 + o];
+            sa[0] += wq.x * a + wk.x * b2, sa[1] += wq.y * a + wk.y * b2, sa[2] += wq.z * a + wk.z * b2, sa[3] += wq.w * a + wk.w * b2;
+            sv[0] += wv.x * c2, sv[1] += wv.y * c2, sv[2] += wv.z * c2, sv[3] += wv.w * c2;
           }
+#pragma unroll
+          for (int d = 0; d < 4; ++d) da8[blk * 4 + d] = sa[d], dxv8[blk * 4 + d] = sv[d];
         }
         float dc8[8], prod[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float ds;
           silu_both(cv8[j], a8[j], ds);
-          dc8[j] = valid ? (da8[j] + dsk[j]) * ds : 0.f;
-          dxv8[j] = valid ? dxv8[j] : 0.f;
+          dc8[j] = (da8[j] + dsk[j]) * ds;
 #pragma unroll
           for (int k = 0; k < 4; ++k) prod[j * 4 + k] = dc8[j] * xr[k][j];
         }
@@ -827,10 +831,6 @@ __global__ void __launch_bounds__(4 * kTok, 1) vil_pre_bwd_a_tc_kernel(xhved_vil
         warp_acc_vec<32>(acc + L::A_CW + e8 * 4, prod);     // d conv.weight[e][k], 8 channels x 4 taps
         warp_acc_vec<8>(acc + L::A_CB + e8, dc8);           // d conv.bias
         // operands of the weight-gradient GEMMs (bf16)
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a8[j] = 0.f, xm8[j] = 0.f;
-        }
         *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gq);
         *reinterpret_cast<uint4*>(smem + L::GQK + tile_off16(kTok, tok, (EG + e8) / 8)) = pack8_bf16(gk);
         *reinterpret_cast<uint4*>(smem + L::GV + tile_off16(kTok, tok, e8 / 8)) = pack8_bf16(gv);
