@@ -139,6 +139,34 @@ int xhved_dice_sums(const float* p, const float* t, int N, int C, int64_t spatia
 int xhved_dice_bwd(const float* p, const float* t, const float* sums, const float* g_dice, int N, int C, int64_t spatial, float eps,
                    float* dp, void* stream);
 
+/* ---------------------------------------------------------------- InstanceNorm3d / BatchNorm3d + LeakyReLU (K6)
+ * The normalisation of the convolution path fused with the LeakyReLU that follows it: SingleConv order 'ilc'
+ * (buildingblocks.py:400-462: nn.InstanceNorm3d -> nn.LeakyReLU(0.01) -> Conv3d), BasicConv (buildingblocks.py:11-31), the
+ * BatchNorm3d layers of modules/DuSFE.py:17-36,108-110,187.  x, y, dy, dx: (N, C, spatial) contiguous, element type `dtype`
+ * (0 fp32, 1 fp16, 2 bf16: the types autocast hands over, train.py:207); statistics, gamma, beta in fp32.
+ *   y = lrelu_slope((x - mean_g) * rstd_g * gamma_c + beta_c),  rstd_g = 1 / sqrt(biased var_g + eps);  slope = 1: no activation
+ *   mode 0 (instance): group g = (n, c), mean / rstd are OUTPUTS of N*C entries;
+ *   mode 1 (batch, training): group g = c over all samples, OUTPUTS of C entries (the caller updates running statistics);
+ *   mode 2 (frozen, eval-mode BatchNorm): mean / rstd are INPUTS of C entries.
+ * gamma / beta may be NULL (InstanceNorm3d's default affine=False).  partials: device scratch of
+ * xhved_norm_act_workspace(...) bytes (not needed in mode 2 forward).
+ * Backward recomputes the activation mask from x and the saved mean / rstd:
+ *   g = dy * (pre > 0 ? 1 : slope);  dx = gamma_c rstd_g (g - mean_g(g) - xhat mean_g(g xhat))   (mode 2: dx = gamma_c rstd_c g)
+ *   dgamma_c += sum g xhat, dbeta_c += sum g   (optional; fp32[C], zeroed by the caller). */
+typedef struct xhved_norm_shape {
+  int N, C;
+  int64_t spatial;
+  int mode;
+  int dtype;
+  float eps;
+  float slope;
+} xhved_norm_shape;
+int64_t xhved_norm_act_workspace(int N, int C, int64_t spatial, int dtype);
+int xhved_norm_act_fwd(const void* x, const float* gamma, const float* beta, const xhved_norm_shape* shape, float* mean, float* rstd,
+                       void* partials, void* y, void* stream);
+int xhved_norm_act_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                       const xhved_norm_shape* shape, void* partials, void* dx, float* dgamma, float* dbeta, void* stream);
+
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
 int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);

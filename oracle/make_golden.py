@@ -229,6 +229,71 @@ def gen_losses(ns):
     torch.save(dict(p=p, t=t, loss=val.detach(), per_channel=per, dp=dp), os.path.join(OUT, "losses.pt"))
 
 
+def gen_conv_norm(ns):
+    """The normalisation + activation layers of the convolution path, run through the REAL reference modules on CPU in fp64:
+    SingleConv order 'ilc' (buildingblocks.py:444-462), BasicConv (buildingblocks.py:11-31) and DuSEAttention with its two
+    BatchNorm3d layers (modules/DuSFE.py:87-154) in train and eval mode.  Forward values and gradients."""
+    import importlib
+    bb = ns.buildingblocks
+    dusfe = importlib.import_module("modules.DuSFE")
+    g = torch.Generator().manual_seed(11)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float32).double()
+    out = {}
+
+    torch.manual_seed(3)
+    sc = bb.SingleConv(4, 6, kernel_size=3, order="ilc", padding=1).double()
+    x = (rn(2, 4, 9, 10, 12) * 1.7 + 0.3).requires_grad_()                 # spatial 1080: not a multiple of a 16-byte vector of fp16
+    mid = sc.LeakyReLU(sc.instancenorm(x))                                  # in-place on the norm output, as in the Sequential
+    gm = rn(*mid.shape)
+    (dx_mid,) = torch.autograd.grad(mid, x, gm, retain_graph=False)
+    x2 = x.detach().clone().requires_grad_()
+    y = sc(x2)
+    gy = rn(*y.shape)
+    grads = torch.autograd.grad(y, [x2, sc.conv.weight, sc.conv.bias], gy)
+    out["single_conv_ilc"] = dict(x=x.detach(), mid=mid.detach(), gm=gm, dx_mid=dx_mid, y=y.detach(), gy=gy, dx=grads[0],
+                                  dconv_weight=grads[1], dconv_bias=grads[2], slope=sc.LeakyReLU.negative_slope,
+                                  state_dict={k: v.detach().clone() for k, v in sc.state_dict().items()})
+
+    torch.manual_seed(4)
+    bc = bb.BasicConv(3, 5, 3, padding=1).double()
+    x = rn(1, 3, 8, 8, 16).requires_grad_()
+    y = bc(x)
+    gy = rn(*y.shape)
+    grads = torch.autograd.grad(y, [x, bc.conv.weight], gy)
+    out["basic_conv"] = dict(x=x.detach(), y=y.detach(), gy=gy, dx=grads[0], dconv_weight=grads[1], slope=bc.relu.negative_slope,
+                             state_dict={k: v.detach().clone() for k, v in bc.state_dict().items()})
+
+    torch.manual_seed(5)
+    att = dusfe.DuSEAttention(4).double()
+    with torch.no_grad():
+        for bn in (att.bn_fuse_ch1, att.bn_fuse_ch2):                       # non-trivial affine parameters and running statistics
+            bn.weight.copy_(1 + 0.3 * rn(4)), bn.bias.copy_(0.2 * rn(4))
+            bn.running_mean.copy_(0.1 * rn(4)), bn.running_var.copy_(1 + 0.2 * torch.rand(4, generator=g).double())
+    sd0 = {k: v.detach().clone() for k, v in att.state_dict().items()}
+    a, b = (rn(3, 4, 6, 8, 8) + 0.5).requires_grad_(), (0.7 * rn(3, 4, 6, 8, 8)).requires_grad_()
+    rec = {}
+    def record(m, i, o):
+        rec["train" if m.training else "eval"] = (i[0].detach().clone(), o.detach().clone())
+
+    hook = att.bn_fuse_ch1.register_forward_hook(record)
+    att.train()
+    y1, y2 = att(a, b)
+    g1, g2 = rn(*y1.shape), rn(*y2.shape)
+    params = [att.bn_fuse_ch1.weight, att.bn_fuse_ch1.bias, att.bn_fuse_ch2.weight, att.bn_fuse_ch2.bias]
+    grads = torch.autograd.grad([y1, y2], [a, b] + params, [g1, g2])
+    sd1 = {k: v.detach().clone() for k, v in att.state_dict().items()}
+    att.eval()
+    e1, e2 = att(a, b)
+    egrads = torch.autograd.grad([e1, e2], [a, b] + params, [g1, g2])
+    hook.remove()
+    out["duse_attention"] = dict(a=a.detach(), b=b.detach(), g1=g1, g2=g2, state_dict_before=sd0, state_dict_after_train=sd1,
+                                 train_y1=y1.detach(), train_y2=y2.detach(), train_grads=[t.detach() for t in grads],
+                                 eval_y1=e1.detach(), eval_y2=e2.detach(), eval_grads=[t.detach() for t in egrads],
+                                 bn1_train_in=rec["train"][0], bn1_train_out=rec["train"][1], bn1_eval_in=rec["eval"][0],
+                                 bn1_eval_out=rec["eval"][1])
+    torch.save(out, os.path.join(OUT, "conv_norm.pt"))
+
+
 def gen_model_boundary(ns):
     """Run the full XLSTM_HVED on a small seeded volume and record the tensors
     that cross the hot-path boundary (RA_HVED.py:588-597 and 623-626)."""
@@ -268,7 +333,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]            # e.g. `python oracle/make_golden.py smvae_extras` regenerates one file
     gens = dict(cell=gen_cell, vil_block=gen_block, vil_block_wide=gen_block_wide, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras, losses=gen_losses,
-                model_boundary=gen_model_boundary)
+                conv_norm=gen_conv_norm, model_boundary=gen_model_boundary)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ns)

@@ -358,6 +358,47 @@ def zero_rows(x, alpha):
     return y
 
 
+def instance_norm_lrelu(x, weight=None, bias=None, eps: float = 1e-5, slope: float = 1.0):
+    """nn.InstanceNorm3d followed by nn.LeakyReLU(slope) -- SingleConv order 'ilc' (buildingblocks.py:414-416, 430-431; the
+    Sequential runs them in order, 462) and BasicConv.forward (buildingblocks.py:23-31).  The arithmetic lives in PyTorch
+    (torch.nn.functional.instance_norm, torch 2.11: affine=False, track_running_stats=False by default): per (sample, channel)
+    plane, y = (x - mean) / sqrt(biased var + eps) [* weight + bias]; LeakyReLU: v > 0 ? v : slope v.  slope = 1: no activation."""
+    N, C = x.shape[:2]
+    flat = x.reshape(N, C, -1)
+    mean = flat.mean(-1, keepdim=True)
+    var = ((flat - mean) ** 2).mean(-1, keepdim=True)
+    y = (flat - mean) / torch.sqrt(var + eps)
+    if weight is not None:
+        y = y * weight.reshape(1, C, 1)
+    if bias is not None:
+        y = y + bias.reshape(1, C, 1)
+    y = torch.where(y > 0, y, y * slope)
+    return y.reshape(x.shape)
+
+
+def batch_norm_lrelu(x, weight, bias, running_mean=None, running_var=None, training: bool = True, momentum: float = 0.1,
+                     eps: float = 1e-5, slope: float = 1.0):
+    """nn.BatchNorm3d (modules/DuSFE.py:108-110 used at 151-152; 17-36, 187) [+ LeakyReLU].  torch.nn.functional.batch_norm:
+    training = statistics per channel over (N, *spatial) with the biased variance, running statistics moved by ``momentum``
+    towards the batch mean / UNBIASED variance; eval = running statistics.  Returns (y, new_running_mean, new_running_var)."""
+    C = x.shape[1]
+    flat = x.transpose(0, 1).reshape(C, -1)
+    if training:
+        mean = flat.mean(-1)
+        var = ((flat - mean[:, None]) ** 2).mean(-1)
+        n = flat.shape[1]
+        if running_mean is not None:
+            running_mean = (1 - momentum) * running_mean + momentum * mean.detach()
+            running_var = (1 - momentum) * running_var + momentum * var.detach() * n / max(n - 1, 1)
+    else:
+        mean, var = running_mean, running_var
+    shape = [1, C] + [1] * (x.dim() - 2)
+    y = (x - mean.reshape(shape)) / torch.sqrt(var.reshape(shape) + eps)
+    y = y * weight.reshape(shape) + bias.reshape(shape)
+    y = torch.where(y > 0, y, y * slope)
+    return y, running_mean, running_var
+
+
 def poe_backward(mu, logvar, mod_list, g_mu, g_lv, eps: float = 1e-8):
     """Manual backward of :func:`poe` w.r.t. the 4 modality experts (SURVEY.md
     8a-note).  Returns (dmu, dlogvar) of shape (4,...) -- zeros for experts not

@@ -15,6 +15,17 @@ from oracle import ref_loader
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    """The bar is measured against the reference computing in fp32.  PyTorch runs cuDNN convolutions in TF32 by default; at that
+    precision the STOCK model disagrees with its own fp64 evaluation on 0.27 % of the voxels (argmax, 64x96x64, subset 7;
+    0.04 % in fp32: tools/diag_conv_norm.py), which would make "99.9 % identical to stock" a statement about that noise."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def test_model_boundary_fixture_vil_and_poe():
     """Tensors recorded at the hot-path boundary of a real reference forward (48^3 volume, subset 12)."""
     import xlstm_hved_b200 as xh
@@ -61,6 +72,21 @@ def test_full_model_segmentation_parity(model, size, subset):
     same_arg = (seg_ref.argmax(1) == seg_new.argmax(1)).float().mean().item()
     print(size, subset, "mask agreement", same_mask, "argmax agreement", same_arg, "max |dp|", (seg_ref - seg_new).abs().max().item())
     assert same_mask >= 0.999 and same_arg >= 0.999
+    assert counts["InstanceNorm3d"] == 80 and counts["BatchNorm3d"] == 18 and counts["fused_LeakyReLU"] == 80
+    if size[0] <= 64:
+        # against the truth: the stock model evaluated in fp64.  The patched model (ViL / S-MVAE kernels + the conv path's fused
+        # normalisation) must agree with it at least as well as the stock fp32 model does.
+        import copy
+        m64 = copy.deepcopy(model).double()
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            seg64, _ = m64(x.double(), [subset], valid=True)
+        del m64
+        agree = lambda p: (((p.double() > 0.5) == (seg64 > 0.5)).double().mean().item(),
+                           (p.argmax(1) == seg64.argmax(1)).double().mean().item())
+        (m_ref, a_ref), (m_new, a_new) = agree(seg_ref), agree(seg_new)
+        print("vs fp64: stock", m_ref, a_ref, "patched", m_new, a_new)
+        assert m_new >= m_ref - 3e-4 and a_new >= a_ref - 3e-4
+        assert m_new >= 0.999 and a_new >= 0.999
 
 
 def test_full_model_training_gradients_parity(model):

@@ -149,3 +149,38 @@ def test_dice_loss_matches_reference():
     assert abs(val.item() - c["loss"].item()) < 1e-14
     assert rel_linf(restate.dice_per_channel(c["p"], c["t"]), c["per_channel"]) < 1e-14 and rel_linf(dp, c["dp"]) < 1e-13
     assert c["per_channel"][3].item() == 0.0 and c["dp"][:, 3].abs().max().item() == 0.0
+
+
+# ------------------------------------------------------------------ conv path: InstanceNorm3d / BatchNorm3d + LeakyReLU (K6)
+@pytest.fixture(scope="module")
+def conv_norm():
+    return load_golden("conv_norm.pt")
+
+
+def test_instance_norm_lrelu_matches_reference_single_conv(conv_norm):
+    c = conv_norm["single_conv_ilc"]
+    x = c["x"].clone().requires_grad_()
+    mid = restate.instance_norm_lrelu(x, slope=c["slope"])
+    assert rel_linf(mid, c["mid"]) < 1e-12
+    (dx,) = torch.autograd.grad(mid, x, c["gm"])
+    assert rel_linf(dx, c["dx_mid"]) < 1e-10
+
+
+def test_instance_norm_lrelu_matches_reference_basic_conv(conv_norm):
+    c = conv_norm["basic_conv"]
+    w = c["state_dict"]["conv.weight"]
+    y = restate.instance_norm_lrelu(torch.nn.functional.conv3d(c["x"], w, padding=1), slope=c["slope"])
+    assert rel_linf(y, c["y"]) < 1e-12
+
+
+def test_batch_norm_matches_reference_duse_attention(conv_norm):
+    c = conv_norm["duse_attention"]
+    sd0, sd1 = c["state_dict_before"], c["state_dict_after_train"]
+    w, b = sd0["bn_fuse_ch1.weight"], sd0["bn_fuse_ch1.bias"]
+    y, rm, rv = restate.batch_norm_lrelu(c["bn1_train_in"], w, b, sd0["bn_fuse_ch1.running_mean"], sd0["bn_fuse_ch1.running_var"],
+                                         training=True)
+    assert rel_linf(y, c["bn1_train_out"]) < 1e-12
+    assert rel_linf(rm, sd1["bn_fuse_ch1.running_mean"]) < 1e-12 and rel_linf(rv, sd1["bn_fuse_ch1.running_var"]) < 1e-12
+    y, _, _ = restate.batch_norm_lrelu(c["bn1_eval_in"], w, b, sd1["bn_fuse_ch1.running_mean"], sd1["bn_fuse_ch1.running_var"],
+                                       training=False)
+    assert rel_linf(y, c["bn1_eval_out"]) < 1e-12

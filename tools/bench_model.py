@@ -51,9 +51,11 @@ def main():
         y = model.mViL(feat)
         y.sum().backward()
 
-    for tag in ("stock", "patched"):
+    for tag in ("stock", "patched", "patched_conv_norm"):
         if tag == "patched":
-            xh.patch_model(model)
+            xh.patch_model(model, conv_path=False)          # the ViL / S-MVAE hot path only
+        elif tag == "patched_conv_norm":
+            out["patch_counts"] = {k: v for k, v in xh.patch_model(model).items() if isinstance(v, int)}    # + K6
         model.eval()
         out[f"{tag}_infer_ms"] = round(timeit(infer), 2)
         model.train()

@@ -52,6 +52,10 @@ class PoeOpts(Structure):             # xhved_poe_opts
     _fields_ = [("eps", c_float), ("flags", c_int), ("clip_lo", c_float), ("clip_hi", c_float)]
 
 
+class NormShape(Structure):           # xhved_norm_shape
+    _fields_ = [("N", c_int), ("C", c_int), ("spatial", c_int64), ("mode", c_int), ("dtype", c_int), ("eps", c_float), ("slope", c_float)]
+
+
 class MlstmWorkspace(Structure):      # xhved_mlstm_workspace
     _fields_ = [("nc", c_int), ("dhp", c_int), ("tile_bytes", c_int64), ("row_bytes", c_int64), ("dstate_bytes", c_int64),
                 ("chunk_bytes", c_int64), ("states_bytes", c_int64)]
@@ -77,6 +81,10 @@ SYMBOLS = {
     "xhved_zero_rows": [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p],
     "xhved_dice_sums": [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p],
     "xhved_dice_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p, c_void_p],
+    "xhved_norm_act_workspace": [c_int, c_int, c_int64, c_int],
+    "xhved_norm_act_fwd": [c_void_p, c_void_p, c_void_p, POINTER(NormShape), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "xhved_norm_act_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(NormShape), c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p],
     "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,
@@ -129,7 +137,8 @@ def load_library() -> ctypes.CDLL:
                 missing.append(name)
                 continue
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == "xhved_profile_kernel_name" else c_int
+            fn.restype = (ctypes.c_char_p if name == "xhved_profile_kernel_name" else
+                          c_int64 if name == "xhved_norm_act_workspace" else c_int)
         if missing:
             raise RuntimeError(f"{LIB_PATH} lacks symbols declared in include/xhved.h: {missing}; rebuild it")
         _lib = lib

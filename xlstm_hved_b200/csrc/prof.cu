@@ -46,7 +46,7 @@ void prof_end(int id, cudaEvent_t begin, cudaStream_t st) {
 static const char* kNames[K_COUNT] = {
     "poe_fwd", "poe_bwd", "reparam_fwd", "reparam_bwd", "vil_pre_fwd", "mlstm_chunk_state", "mlstm_state_scan",
     "mlstm_chunk_out", "vil_post_fwd", "vil_post_bwd", "mlstm_chunk_rstate", "mlstm_chunk_grad", "mlstm_gate_finish",
-    "vil_pre_bwd_a", "vil_pre_bwd_b", "pack", "unpack"};
+    "vil_pre_bwd_a", "vil_pre_bwd_b", "pack", "unpack", "norm_act_fwd", "norm_act_bwd"};
 
 }  // namespace xhved
 

@@ -9,7 +9,7 @@ enum KernelId {
   K_POE_FWD = 0, K_POE_BWD, K_REPARAM_FWD, K_REPARAM_BWD,
   K_VIL_PRE_FWD, K_CHUNK_STATE, K_STATE_SCAN, K_CHUNK_OUT, K_VIL_POST_FWD,
   K_VIL_POST_BWD, K_CHUNK_RSTATE, K_CHUNK_GRAD, K_GATE_FINISH, K_VIL_PRE_BWD_A, K_VIL_PRE_BWD_B,
-  K_PACK, K_UNPACK, K_COUNT
+  K_PACK, K_UNPACK, K_NORM_FWD, K_NORM_BWD, K_COUNT
 };
 
 bool prof_enabled();

@@ -483,3 +483,110 @@ def compute_KLD(mu_list, logvar_list, subset_index_list=[14], choices=[0, 1, 2, 
     lv5 = logvar_list.transpose(1, 0).float().contiguous()
     subsets = [SUBSETS_MODALITIES[i] for i in range(len(SUBSETS_MODALITIES)) if i in subset_index_list]
     return _KLDFunction.apply(mu5, lv5, subsets)
+
+
+# ----------------------------------------------------------------------------- conv path: normalisation + LeakyReLU (K6)
+class _NormActFunction(torch.autograd.Function):
+    """InstanceNorm3d / BatchNorm3d with the LeakyReLU that follows fused in (csrc/norm_act.cu).  Saves x and the group statistics
+    only: the backward recomputes the activation mask."""
+
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, gamma, beta, mode, eps, slope, mean_in, rstd_in):
+        y, mean, rstd = ops.norm_act_fwd(x, gamma, beta, mode, eps, slope, mean_in, rstd_in)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.cfg = (mode, eps, slope)
+        ctx.mark_non_differentiable(mean, rstd)
+        return y, mean, rstd
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dy, _dmean, _drstd):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        mode, eps, slope = ctx.cfg
+        want = gamma is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        dx, dg, db = ops.norm_act_bwd(x, dy, mean, rstd, gamma, beta, mode, eps, slope, want_param_grads=want)
+        if want:
+            dg, db = dg.to(gamma.dtype), (db.to(beta.dtype) if beta is not None else None)
+        return dx, dg, db, None, None, None, None, None
+
+
+def _ncs(x, num_features):
+    """(N, C, *spatial) view of a batched or unbatched input (nn.InstanceNorm3d accepts (C, D, H, W) too)."""
+    if x.dim() == 4 and x.shape[0] == num_features:
+        return x.unsqueeze(0), True
+    return x, False
+
+
+def instance_norm_act(x, weight=None, bias=None, eps: float = 1e-5, slope: float = 1.0):
+    """F.instance_norm(x, weight=weight, bias=bias, eps=eps) followed by F.leaky_relu(., slope) (slope = 1: none) in one pass
+    pair over x: statistics per (sample, channel) plane, biased variance."""
+    _require_device(x)
+    return _NormActFunction.apply(x, weight, bias, ops.NORM_INSTANCE, float(eps), float(slope), None, None)[0]
+
+
+def batch_norm_act(x, weight, bias, running_mean, running_var, training: bool, momentum, eps: float = 1e-5, slope: float = 1.0):
+    """F.batch_norm (+ LeakyReLU).  Training: batch statistics over (N, *spatial), running statistics updated in place with
+    ``momentum`` and the unbiased variance; eval: the running statistics."""
+    _require_device(x)
+    if training:
+        y, mean, rstd = _NormActFunction.apply(x, weight, bias, ops.NORM_BATCH, float(eps), float(slope), None, None)
+        if running_mean is not None and momentum:
+            with torch.no_grad():
+                n = x.numel() // x.shape[1]
+                var = rstd.double().pow(-2).sub_(eps).clamp_(min=0).mul_(n / max(n - 1, 1))
+                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1 - momentum).add_(var.to(running_var.dtype), alpha=momentum)
+        return y
+    rstd = torch.rsqrt(running_var.float() + eps)
+    return _NormActFunction.apply(x, weight, bias, ops.NORM_FROZEN, float(eps), float(slope), running_mean.float(), rstd)[0]
+
+
+class InstanceNorm3d(nn.InstanceNorm3d):
+    """nn.InstanceNorm3d (the 'i' of SingleConv's order string, buildingblocks.py:430-431; BasicConv.norm, buildingblocks.py:20)
+    on the fused kernel.  ``fused_slope`` is the negative slope of a LeakyReLU folded in by ``patch_model`` (None = none)."""
+    fused_slope = None
+
+    def forward(self, input):
+        return instance_norm_forward(self, input)
+
+
+def instance_norm_forward(mod, input):
+    if mod.track_running_stats:
+        raise NotImplementedError("xlstm_hved_b200.InstanceNorm3d: track_running_stats=True is not supported (the reference never sets it)")
+    x, unbatched = _ncs(input, mod.num_features)
+    slope = getattr(mod, "fused_slope", None)
+    y = instance_norm_act(x, mod.weight, mod.bias, mod.eps, 1.0 if slope is None else slope)
+    return y.squeeze(0) if unbatched else y
+
+
+class BatchNorm3d(nn.BatchNorm3d):
+    """nn.BatchNorm3d (modules/DuSFE.py:17-36, 108-110, 187) on the fused kernel."""
+    fused_slope = None
+
+    def forward(self, input):
+        return batch_norm_forward(self, input)
+
+
+def batch_norm_forward(mod, input):
+    """torch.nn.modules.batchnorm._BatchNorm.forward's bookkeeping (momentum None = cumulative average) around batch_norm_act."""
+    if input.dim() != 5:
+        raise ValueError(f"expected 5D input (got {input.dim()}D input)")
+    momentum = 0.0 if mod.momentum is None else mod.momentum
+    if mod.training and mod.track_running_stats and mod.num_batches_tracked is not None:
+        mod.num_batches_tracked.add_(1)
+        if mod.momentum is None:
+            momentum = 1.0 / float(mod.num_batches_tracked)
+    training = mod.training or (mod.running_mean is None and mod.running_var is None)
+    use_running = (not mod.training) or mod.track_running_stats
+    slope = getattr(mod, "fused_slope", None)
+    return batch_norm_act(input, mod.weight, mod.bias, mod.running_mean if use_running else None,
+                          mod.running_var if use_running else None, training, momentum, mod.eps, 1.0 if slope is None else slope)
+
+
+class FusedAwayLeakyReLU(nn.LeakyReLU):
+    """A LeakyReLU whose work happens inside the preceding normalisation kernel (``patch_model`` sets that layer's
+    ``fused_slope``): the forward hands its input through."""
+
+    def forward(self, input):
+        return input

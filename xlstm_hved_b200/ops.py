@@ -272,6 +272,63 @@ def reparam_bwd(logvar, noise, g_z):
     return d_mu, d_lv
 
 
+# ----------------------------------------------------------------------------- InstanceNorm3d / BatchNorm3d + LeakyReLU (K6)
+NORM_INSTANCE, NORM_BATCH, NORM_FROZEN = 0, 1, 2
+_NORM_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_NORM_WS = {}            # (N, C, spatial, dtype code) -> partials bytes: host-only query, cached
+
+
+def _norm_shape(x, mode, eps, slope):
+    if x.dtype not in _NORM_DTYPES:
+        raise RuntimeError(f"xlstm_hved_b200 norm_act: unsupported dtype {x.dtype}")
+    sh = _lib.NormShape()
+    sh.N, sh.C, sh.spatial = x.shape[0], x.shape[1], x[0, 0].numel()
+    sh.mode, sh.dtype, sh.eps, sh.slope = mode, _NORM_DTYPES[x.dtype], eps, slope
+    key = (sh.N, sh.C, sh.spatial, sh.dtype)
+    if key not in _NORM_WS:
+        _NORM_WS[key] = _lib.load_library().xhved_norm_act_workspace(*key)
+    return sh, _NORM_WS[key]
+
+
+def norm_act_fwd(x, gamma=None, beta=None, mode: int = NORM_INSTANCE, eps: float = 1e-5, slope: float = 1.0, mean=None, rstd=None):
+    """x: (N, C, *spatial) contiguous fp32 / fp16 / bf16.  Returns (y, mean, rstd): the statistics are fp32 of N*C (instance) or C
+    (batch) entries; with mode = NORM_FROZEN they are inputs (C entries).  slope = 1: no activation."""
+    lib = _lib.load_library()
+    if not x.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    x = x.contiguous()
+    sh, ws_bytes = _norm_shape(x, mode, eps, slope)
+    groups = sh.N * sh.C if mode == NORM_INSTANCE else sh.C
+    if mode == NORM_FROZEN:
+        mean, rstd = _f32c(mean), _f32c(rstd)
+        part = None
+    else:
+        mean = torch.empty(groups, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(groups, device=x.device, dtype=torch.float32)
+        part = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    y = torch.empty_like(x)
+    check(lib.xhved_norm_act_fwd(ptr(x), ptr(_f32c(gamma)) if gamma is not None else None, ptr(_f32c(beta)) if beta is not None else None,
+                                 ctypes.byref(sh), ptr(mean), ptr(rstd), ptr(part), ptr(y), stream()), "xhved_norm_act_fwd")
+    return y, mean, rstd
+
+
+def norm_act_bwd(x, dy, mean, rstd, gamma=None, beta=None, mode: int = NORM_INSTANCE, eps: float = 1e-5, slope: float = 1.0,
+                 want_param_grads: bool = False):
+    """Backward of norm_act_fwd.  Returns (dx, dgamma, dbeta); the last two are None unless want_param_grads."""
+    lib = _lib.load_library()
+    x = x.contiguous()
+    dy = dy.to(x.dtype).contiguous()
+    sh, ws_bytes = _norm_shape(x, mode, eps, slope)
+    part = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    dx = torch.empty_like(x)
+    dgb = torch.zeros(2, sh.C, device=x.device, dtype=torch.float32) if want_param_grads else None
+    check(lib.xhved_norm_act_bwd(ptr(x), ptr(dy), ptr(_f32c(gamma)) if gamma is not None else None,
+                                 ptr(_f32c(beta)) if beta is not None else None, ptr(mean), ptr(rstd), ctypes.byref(sh), ptr(part), ptr(dx),
+                                 ptr(dgb[0]) if want_param_grads else None, ptr(dgb[1]) if want_param_grads else None, stream()),
+          "xhved_norm_act_bwd")
+    return (dx, dgb[0], dgb[1]) if want_param_grads else (dx, None, None)
+
+
 # ----------------------------------------------------------------------------- mLSTM cell
 class CellBuffers:
     """Device buffers of one chunkwise cell invocation (tiles + saved-for-backward state)."""

@@ -22,6 +22,8 @@ from __future__ import annotations
 import copyreg
 import sys
 
+import torch.nn as nn
+
 from . import modules
 
 _PATCHED = {}          # (original class, kind) -> patched subclass
@@ -32,6 +34,8 @@ def _reduce_as_base(self, protocol):
     """Pickle a patched module as an instance of the reference's own class (stdlib reconstructor + the instance state:
     nothing of this package is needed to load the checkpoint)."""
     state = object.__reduce_ex__(self, 2)[2]
+    if isinstance(state, dict) and "fused_slope" in state:          # patch-time annotation of the conv-path norms
+        state = {k: v for k, v in state.items() if k != "fused_slope"}
     return (copyreg._reconstructor, (type(self)._xhved_base, object, None), state)
 
 
@@ -47,7 +51,20 @@ def _poe2_forward(self, mu, logvar, drop, eps=1e-8):
     return modules.product_of_experts_drop(mu, logvar, drop, eps)
 
 
-_FORWARDS = {"ViLBlock": _vil_forward, "ProductOfExperts": _poe_forward, "ProductOfExperts2": _poe2_forward}
+def _inorm_forward(self, input):
+    return modules.instance_norm_forward(self, input)
+
+
+def _bnorm_forward(self, input):
+    return modules.batch_norm_forward(self, input)
+
+
+def _identity_forward(self, input):
+    return input
+
+
+_FORWARDS = {"ViLBlock": _vil_forward, "ProductOfExperts": _poe_forward, "ProductOfExperts2": _poe2_forward,
+             "InstanceNorm3d": _inorm_forward, "BatchNorm3d": _bnorm_forward, "FusedAwayLeakyReLU": _identity_forward}
 
 
 def _patched_class(cls, kind):
@@ -66,7 +83,34 @@ def _kind_of(m):
         return "ViLBlock"
     if name in ("ProductOfExperts", "ProductOfExperts2") and type(m).__module__ != modules.__name__:
         return name
+    if type(m).__module__ != modules.__name__:
+        # the conv path's normalisation layers: exact torch classes only, the mirrors already run the kernels
+        if type(m) is nn.InstanceNorm3d and not m.track_running_stats:
+            return "InstanceNorm3d"
+        if type(m) is nn.BatchNorm3d:
+            return "BatchNorm3d"
     return None
+
+
+def _fuse_activations(model):
+    """InstanceNorm3d / BatchNorm3d immediately followed by a LeakyReLU -- consecutive children of an nn.Sequential (SingleConv
+    order 'ilc' / 'cil', buildingblocks.py:400-462; discriminator_block, buildingblocks.py:345-357) or the norm / relu pair of
+    BasicConv (buildingblocks.py:11-31): the slope moves into the norm layer's kernel and the LeakyReLU hands its input through.
+    Returns the number of fused pairs."""
+    n = 0
+    for parent in model.modules():
+        if not (isinstance(parent, nn.Sequential) or type(parent).__name__ == "BasicConv"):
+            continue
+        kids = list(parent._modules.values())
+        for norm, act in zip(kids, kids[1:]):
+            if norm is None or act is None or getattr(type(norm), "_xhved_base", None) not in (nn.InstanceNorm3d, nn.BatchNorm3d):
+                continue
+            if type(act) is not nn.LeakyReLU or norm.__dict__.get("fused_slope") is not None:
+                continue
+            norm.fused_slope = float(act.negative_slope)
+            act.__class__ = _patched_class(nn.LeakyReLU, "FusedAwayLeakyReLU")
+            n += 1
+    return n
 
 
 def _rebind_everywhere(original, replacement, attr):
@@ -82,15 +126,21 @@ def _rebind_everywhere(original, replacement, attr):
     return n
 
 
-def patch_model(model, patch_globals: bool = True):
+def patch_model(model, patch_globals: bool = True, conv_path: bool = True):
     """Returns a dict with the number of patched objects per kind; ``globals`` counts (module, name) bindings rebound and
-    ``rebound`` lists them as "module.name"."""
-    counts = {"ViLBlock": 0, "ProductOfExperts": 0, "ProductOfExperts2": 0, "globals": 0, "rebound": []}
+    ``rebound`` lists them as "module.name".  ``conv_path=False`` leaves the normalisation layers of the convolution path
+    (InstanceNorm3d / BatchNorm3d and the LeakyReLU fused into them) on PyTorch."""
+    counts = {"ViLBlock": 0, "ProductOfExperts": 0, "ProductOfExperts2": 0, "InstanceNorm3d": 0, "BatchNorm3d": 0,
+              "fused_LeakyReLU": 0, "globals": 0, "rebound": []}
     for m in model.modules():
         kind = _kind_of(m)
+        if kind in ("InstanceNorm3d", "BatchNorm3d") and not conv_path:
+            continue
         if kind is not None:
             m.__class__ = _patched_class(type(m), kind)
             counts[kind] += 1
+    if conv_path:
+        counts["fused_LeakyReLU"] = _fuse_activations(model)
     if patch_globals:
         before = len(_GLOBALS)
         ra, ls, bb = sys.modules.get("RA_HVED"), sys.modules.get("loss"), sys.modules.get("buildingblocks")
@@ -116,6 +166,7 @@ def unpatch_model(model):
         base = getattr(type(m), "_xhved_base", None)
         if base is not None:
             m.__class__ = base
+            m.__dict__.pop("fused_slope", None)
     while _GLOBALS:
         mod, attr, orig = _GLOBALS.pop()
         setattr(mod, attr, orig)
