@@ -167,6 +167,20 @@ int xhved_norm_act_fwd(const void* x, const float* gamma, const float* beta, con
 int xhved_norm_act_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean, const float* rstd,
                        const xhved_norm_shape* shape, void* partials, void* dx, float* dgamma, float* dbeta, void* stream);
 
+/* ---------------------------------------------------------------- spatial gate of AttenModule2 (K7)
+ * buildingblocks.py:259-301: gate = sigmoid(conv1x1x1(depthwise_conv7x7x7(x)))  (enc_spatial -> enc_spatial2 at 283-285,
+ * seg_spatial -> seg_spatial2 at 294-296).  The caller composes the two linear layers into ONE dense G -> 1 convolution,
+ * w[g][kd][kh][kw] = sum_j w2[e g + j] W1[e g + j][kd][kh][kw] (e = channel expansion), bias = sum_o w2[o] b1[o] + b2:
+ *   gate[n][v] = sigmoid(bias + sum_g sum_tap x[n][g][v + tap - 3] w[g][tap])      zero padding 3, stride 1
+ * x: (N, G, D, H, W) fp32 contiguous, w: (G, 343) fp32, bias: device float[1] or NULL, gate / dgate: (N, 1, D, H, W).
+ * Backward: dpre = dgate gate (1 - gate); dx (optional) = the transposed convolution of dpre; dw (optional, (G, 343)) and
+ * dbias (optional, [1]) need `partials`, a device scratch of xhved_gate7_workspace(...) bytes (per-tile partial sums, reduced in a
+ * second launch: deterministic). */
+int64_t xhved_gate7_workspace(int N, int G, int D, int H, int W);
+int xhved_gate7_fwd(const float* x, const float* w, const float* bias, int N, int G, int D, int H, int W, float* gate, void* stream);
+int xhved_gate7_bwd(const float* x, const float* w, const float* gate, const float* dgate, int N, int G, int D, int H, int W,
+                    void* partials, float* dx, float* dw, float* dbias, void* stream);
+
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
 int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);

@@ -294,6 +294,27 @@ def gen_conv_norm(ns):
     torch.save(out, os.path.join(OUT, "conv_norm.pt"))
 
 
+def gen_atten(ns):
+    """AttenModule2 (buildingblocks.py:259-301) of the real reference on CPU in fp64: output and the gradients w.r.t. both inputs and
+    all eight parameters.  Spatial size (9, 11, 37): ragged against the kernel's 8 x 8 x 32 tiles in every dimension."""
+    bb = ns.buildingblocks
+    g = torch.Generator().manual_seed(13)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float32).double()
+    torch.manual_seed(6)
+    att = bb.AttenModule2(8, 4).double()
+    with torch.no_grad():
+        for q in att.parameters():                     # larger than the default init so that the gates leave the linear regime
+            q.mul_(4.0)
+    seg_x, enc_x = rn(2, 3, 9, 11, 37).requires_grad_(), rn(2, 5, 9, 11, 37).requires_grad_()
+    y = att(seg_x, enc_x)
+    gy = rn(*y.shape)
+    names = [n for n, _ in att.named_parameters()]
+    grads = torch.autograd.grad(y, [seg_x, enc_x] + list(att.parameters()), gy)
+    torch.save(dict(seg_x=seg_x.detach(), enc_x=enc_x.detach(), y=y.detach(), gy=gy, d_seg_x=grads[0], d_enc_x=grads[1],
+                    param_grads=dict(zip(names, grads[2:])), state_dict={k: v.detach().clone() for k, v in att.state_dict().items()}),
+               os.path.join(OUT, "atten_module2.pt"))
+
+
 def gen_model_boundary(ns):
     """Run the full XLSTM_HVED on a small seeded volume and record the tensors
     that cross the hot-path boundary (RA_HVED.py:588-597 and 623-626)."""
@@ -333,7 +354,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]            # e.g. `python oracle/make_golden.py smvae_extras` regenerates one file
     gens = dict(cell=gen_cell, vil_block=gen_block, vil_block_wide=gen_block_wide, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras, losses=gen_losses,
-                conv_norm=gen_conv_norm, model_boundary=gen_model_boundary)
+                conv_norm=gen_conv_norm, atten_module2=gen_atten, model_boundary=gen_model_boundary)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ns)

@@ -399,6 +399,26 @@ def batch_norm_lrelu(x, weight, bias, running_mean=None, running_var=None, train
     return y, running_mean, running_var
 
 
+def channel_pool(x):
+    """ChannelPool.forward -- buildingblocks.py:136-138: (max over channels, mean over channels)."""
+    return torch.cat((x.max(1)[0].unsqueeze(1), x.mean(1).unsqueeze(1)), dim=1)
+
+
+def atten_module2(seg_x, enc_x, p: dict):
+    """AttenModule2.forward -- buildingblocks.py:277-301 (recon_x = None, the only way the model calls it): two spatial gates,
+    each a depthwise 7x7x7 convolution (4 output channels per input channel, buildingblocks.py:271, 273) followed by a 1x1x1
+    convolution to one channel (272, 274) and a sigmoid; p = the module's state_dict."""
+    import torch.nn.functional as F
+    spa = channel_pool(seg_x)
+    enc_spa = torch.cat([spa, channel_pool(enc_x)], 1)
+    e = F.conv3d(enc_spa, p["enc_spatial.weight"], p["enc_spatial.bias"], padding=3, groups=enc_spa.shape[1])
+    e = torch.sigmoid(F.conv3d(e, p["enc_spatial2.weight"], p["enc_spatial2.bias"]))
+    s_enc = enc_x + enc_x * e
+    g = F.conv3d(spa, p["seg_spatial.weight"], p["seg_spatial.bias"], padding=3, groups=spa.shape[1])
+    g = torch.sigmoid(F.conv3d(g, p["seg_spatial2.weight"], p["seg_spatial2.bias"]))
+    return torch.cat([seg_x * (1 + g), s_enc], 1)
+
+
 def poe_backward(mu, logvar, mod_list, g_mu, g_lv, eps: float = 1e-8):
     """Manual backward of :func:`poe` w.r.t. the 4 modality experts (SURVEY.md
     8a-note).  Returns (dmu, dlogvar) of shape (4,...) -- zeros for experts not

@@ -184,3 +184,15 @@ def test_batch_norm_matches_reference_duse_attention(conv_norm):
     y, _, _ = restate.batch_norm_lrelu(c["bn1_eval_in"], w, b, sd1["bn_fuse_ch1.running_mean"], sd1["bn_fuse_ch1.running_var"],
                                        training=False)
     assert rel_linf(y, c["bn1_eval_out"]) < 1e-12
+
+
+def test_atten_module2_matches_reference():
+    c = load_golden("atten_module2.pt")
+    seg_x, enc_x = c["seg_x"].clone().requires_grad_(), c["enc_x"].clone().requires_grad_()
+    p = {k: v.clone().requires_grad_() for k, v in c["state_dict"].items()}
+    y = restate.atten_module2(seg_x, enc_x, p)
+    assert rel_linf(y, c["y"]) < 1e-12
+    grads = torch.autograd.grad(y, [seg_x, enc_x] + [p[k] for k in c["param_grads"]], c["gy"])
+    assert rel_linf(grads[0], c["d_seg_x"]) < 1e-10 and rel_linf(grads[1], c["d_enc_x"]) < 1e-10
+    for g, k in zip(grads[2:], c["param_grads"]):
+        assert rel_linf(g, c["param_grads"][k]) < 1e-10, k

@@ -590,3 +590,60 @@ class FusedAwayLeakyReLU(nn.LeakyReLU):
 
     def forward(self, input):
         return input
+
+
+# ----------------------------------------------------------------------------- conv path: AttenModule2's spatial gate (K7)
+class _Gate7Function(torch.autograd.Function):
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, w, b):
+        gate = ops.gate7_fwd(x, w, b)
+        ctx.save_for_backward(x, w, gate)
+        return gate
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dgate):
+        x, w, gate = ctx.saved_tensors
+        dx, dw, db = ops.gate7_bwd(x, w, gate, dgate, want_dx=ctx.needs_input_grad[0],
+                                   want_dw=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        return dx, dw, db
+
+
+def gate_convs_supported(dw, pw) -> bool:
+    """A depthwise 7^3 convolution (stride 1, zero padding 3, any channel expansion) followed by a 1x1x1 convolution to one channel."""
+    return (isinstance(dw, nn.Conv3d) and isinstance(pw, nn.Conv3d) and dw.kernel_size == (7, 7, 7) and dw.stride == (1, 1, 1)
+            and dw.padding == (3, 3, 3) and dw.dilation == (1, 1, 1) and dw.groups == dw.in_channels and dw.padding_mode == "zeros"
+            and dw.out_channels % dw.in_channels == 0 and pw.kernel_size == (1, 1, 1) and pw.stride == (1, 1, 1)
+            and pw.padding == (0, 0, 0) and pw.groups == 1 and pw.in_channels == dw.out_channels and pw.out_channels == 1)
+
+
+def spatial_gate(x, dw, pw):
+    """sigmoid(pw(dw(x))) of AttenModule2 (buildingblocks.py:283-285, 294-296) as ONE dense G -> 1 convolution + sigmoid kernel:
+    the two linear layers are composed here (two small torch ops; autograd carries the gradient back to both layers' parameters)."""
+    _require_device(x)
+    if not gate_convs_supported(dw, pw):
+        raise NotImplementedError("xlstm_hved_b200.spatial_gate: expects a depthwise 7x7x7 conv followed by a 1x1x1 conv to one channel")
+    G, e = dw.in_channels, dw.out_channels // dw.in_channels
+    w2 = pw.weight.reshape(G, e, 1).float()
+    w = (dw.weight.reshape(G, e, 343).float() * w2).sum(1)
+    b = None
+    if dw.bias is not None:
+        b = (pw.weight.reshape(-1).float() * dw.bias.float()).sum().reshape(1)
+    if pw.bias is not None:
+        b = pw.bias.float().reshape(1) if b is None else b + pw.bias.float().reshape(1)
+    return _Gate7Function.apply(x.float(), w, b).to(x.dtype)
+
+
+def atten_module2_forward(mod, seg_x, enc_x, recon_x=None):
+    """AttenModule2.forward (buildingblocks.py:277-301) with both spatial gates on the fused kernel; everything else as written
+    there (ChannelPool, the two scalings, the concatenation)."""
+    spa_comp = mod.compress(seg_x)
+    enc_spa = torch.cat([spa_comp, mod.compress(enc_x)], 1)
+    enc_scale = spatial_gate(enc_spa, mod.enc_spatial, mod.enc_spatial2)
+    s_enc_x = enc_x + enc_x * enc_scale
+    if recon_x is not None:
+        raise NameError("name 'comp_x' is not defined")        # buildingblocks.py:289-290: the reference fails here too
+    seg_scale = spatial_gate(spa_comp, mod.seg_spatial, mod.seg_spatial2)
+    scaled_seg_x = seg_x * (1 + seg_scale)
+    return torch.cat([scaled_seg_x, s_enc_x], 1)

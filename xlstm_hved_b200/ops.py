@@ -329,6 +329,39 @@ def norm_act_bwd(x, dy, mean, rstd, gamma=None, beta=None, mode: int = NORM_INST
     return (dx, dgb[0], dgb[1]) if want_param_grads else (dx, None, None)
 
 
+# ----------------------------------------------------------------------------- spatial gate of AttenModule2 (K7)
+def gate7_fwd(x, w, bias=None):
+    """x: (N, G, D, H, W) fp32, w: (G, 343) composed weights, bias: one-element tensor or None.  Returns sigmoid(conv + bias),
+    (N, 1, D, H, W)."""
+    lib = _lib.load_library()
+    if not x.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    x, w = _f32c(x), _f32c(w)
+    N, G, D, H, W = x.shape
+    if w.numel() != G * 343:
+        raise RuntimeError(f"gate7: weights of {w.numel()} elements for {G} channels")
+    gate = torch.empty(N, 1, D, H, W, device=x.device, dtype=torch.float32)
+    check(lib.xhved_gate7_fwd(ptr(x), ptr(w), ptr(_f32c(bias)) if bias is not None else None, N, G, D, H, W, ptr(gate), stream()),
+          "xhved_gate7_fwd")
+    return gate
+
+
+def gate7_bwd(x, w, gate, dgate, want_dx: bool = True, want_dw: bool = True):
+    """Returns (dx, dw, dbias); dx is None unless want_dx, dw / dbias are None unless want_dw."""
+    lib = _lib.load_library()
+    x, w, gate, dgate = _f32c(x), _f32c(w), _f32c(gate), _f32c(dgate)
+    N, G, D, H, W = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    dw = db = part = None
+    if want_dw:
+        dw = torch.empty(G, 343, device=x.device, dtype=torch.float32)
+        db = torch.empty(1, device=x.device, dtype=torch.float32)
+        part = torch.empty(lib.xhved_gate7_workspace(N, G, D, H, W), device=x.device, dtype=torch.uint8)
+    check(lib.xhved_gate7_bwd(ptr(x), ptr(w), ptr(gate), ptr(dgate), N, G, D, H, W, ptr(part), ptr(dx), ptr(dw), ptr(db), stream()),
+          "xhved_gate7_bwd")
+    return dx, dw, db
+
+
 # ----------------------------------------------------------------------------- mLSTM cell
 class CellBuffers:
     """Device buffers of one chunkwise cell invocation (tiles + saved-for-backward state)."""
