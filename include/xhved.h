@@ -181,6 +181,17 @@ int xhved_gate7_fwd(const float* x, const float* w, const float* bias, int N, in
 int xhved_gate7_bwd(const float* x, const float* w, const float* gate, const float* dgate, int N, int G, int D, int H, int W,
                     void* partials, float* dx, float* dw, float* dbias, void* stream);
 
+/* ---------------------------------------------------------------- depthwise 3x3x3 convolution (K8)
+ * nn.Conv3d(C, C, 3, padding=1, groups=C) -- the conv of BasicConv(C, C, 3, padding=1, groups=C), RA_HVED.py:406,
+ * buildingblocks.py:11-31.  x, y, dy, dx: (N, C, D, H, W) fp32 contiguous; w: (C, 27); bias: (C) or NULL.
+ *   y[n][c][v] = bias[c] + sum_tap x[n][c][v + tap - 1] w[c][tap]           stride 1, zero padding 1
+ * Backward: dx (optional) = correlation of dy with the flipped kernel; dw (optional, (C, 27)) and dbias (optional, (C)) need
+ * `partials`, a device scratch of xhved_dwconv3_workspace(...) bytes (per-tile partial sums reduced in a second launch). */
+int64_t xhved_dwconv3_workspace(int N, int C, int D, int H, int W);
+int xhved_dwconv3_fwd(const float* x, const float* w, const float* bias, int N, int C, int D, int H, int W, float* y, void* stream);
+int xhved_dwconv3_bwd(const float* x, const float* w, const float* dy, int N, int C, int D, int H, int W, void* partials, float* dx,
+                      float* dw, float* dbias, void* stream);
+
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
 int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);

@@ -315,6 +315,26 @@ def gen_atten(ns):
                os.path.join(OUT, "atten_module2.pt"))
 
 
+def gen_dwconv3(ns):
+    """BasicConv(C, C, 3, padding=1, groups=C) of the real reference (the latent levels' conv_block, RA_HVED.py:406) on CPU in fp64:
+    the depthwise convolution's output, the block's output and the gradients; spatial size ragged against 8 x 8 x 32 tiles."""
+    bb = ns.buildingblocks
+    g = torch.Generator().manual_seed(17)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float32).double()
+    torch.manual_seed(7)
+    bc = bb.BasicConv(4, 4, 3, padding=1, groups=4).double()
+    x = rn(2, 4, 9, 11, 37).requires_grad_()
+    conv_out = bc.conv(x)
+    y = bc(x)
+    gy = rn(*y.shape)
+    grads = torch.autograd.grad(y, [x, bc.conv.weight], gy)
+    gc = rn(*conv_out.shape)
+    cgrads = torch.autograd.grad(conv_out, [x, bc.conv.weight], gc)
+    torch.save(dict(x=x.detach(), conv_out=conv_out.detach(), y=y.detach(), gy=gy, dx=grads[0], dconv_weight=grads[1], gc=gc,
+                    conv_dx=cgrads[0], conv_dweight=cgrads[1], state_dict={k: v.detach().clone() for k, v in bc.state_dict().items()}),
+               os.path.join(OUT, "dwconv3.pt"))
+
+
 def gen_model_boundary(ns):
     """Run the full XLSTM_HVED on a small seeded volume and record the tensors
     that cross the hot-path boundary (RA_HVED.py:588-597 and 623-626)."""
@@ -354,7 +374,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]            # e.g. `python oracle/make_golden.py smvae_extras` regenerates one file
     gens = dict(cell=gen_cell, vil_block=gen_block, vil_block_wide=gen_block_wide, vil_wrapper=gen_wrapper, poe=gen_poe, smvae_extras=gen_smvae_extras, losses=gen_losses,
-                conv_norm=gen_conv_norm, atten_module2=gen_atten, model_boundary=gen_model_boundary)
+                conv_norm=gen_conv_norm, atten_module2=gen_atten, dwconv3=gen_dwconv3, model_boundary=gen_model_boundary)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ns)

@@ -399,6 +399,21 @@ def batch_norm_lrelu(x, weight, bias, running_mean=None, running_var=None, train
     return y, running_mean, running_var
 
 
+def basic_conv_depthwise(x, weight, slope: float = 0.01):
+    """BasicConv(C, C, 3, padding=1, groups=C).forward -- buildingblocks.py:23-31 as instantiated at RA_HVED.py:406: depthwise
+    3x3x3 convolution without bias (zero padding 1), InstanceNorm3d, LeakyReLU(0.01).  Written out tap by tap."""
+    import torch.nn.functional as F
+    C = x.shape[1]
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    D, H, W = x.shape[2:]
+    y = torch.zeros_like(x)
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                y = y + xp[:, :, kd:kd + D, kh:kh + H, kw:kw + W] * weight[:, 0, kd, kh, kw].reshape(1, C, 1, 1, 1)
+    return instance_norm_lrelu(y, slope=slope), y
+
+
 def channel_pool(x):
     """ChannelPool.forward -- buildingblocks.py:136-138: (max over channels, mean over channels)."""
     return torch.cat((x.max(1)[0].unsqueeze(1), x.mean(1).unsqueeze(1)), dim=1)

@@ -112,3 +112,64 @@ def test_gate7_full_size_vs_pytorch_kernels():
     logit = lambda t: torch.log(t) - torch.log1p(-t)
     l1, l2, l12 = (logit(ops.gate7_fwd(t, w).double()) for t in (x, x2, 0.5 * x - 1.5 * x2))
     assert (l12 - (0.5 * l1 - 1.5 * l2)).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------ K8: depthwise 3x3x3 convolution (csrc/dwconv3.cu)
+class BasicConv(nn.Module):
+    """Structure of buildingblocks.BasicConv (buildingblocks.py:11-31) as RA_HVED.py:406 instantiates it."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv3d(c, c, 3, padding=1, groups=c, bias=False)
+        self.norm = nn.InstanceNorm3d(c)
+        self.relu = nn.LeakyReLU(negative_slope=1e-2, inplace=True)
+
+    def forward(self, x):
+        return self.relu(self.norm(self.conv(x)))
+
+
+def test_patched_depthwise_basic_conv_golden():
+    """The reference's BasicConv(4, 4, 3, padding=1, groups=4): conv on K8, norm + LeakyReLU on K6, against the reference's values."""
+    import xlstm_hved_b200 as xh
+    from xlstm_hved_b200 import ops
+    c = load_golden("dwconv3.pt")
+    bc = BasicConv(4)
+    bc.load_state_dict({k: v.float() for k, v in c["state_dict"].items()}, strict=True)
+    bc.cuda()
+    counts = xh.patch_model(bc)
+    assert counts["DepthwiseConv3d"] == 1 and counts["InstanceNorm3d"] == 1 and counts["fused_LeakyReLU"] == 1
+    x = c["x"].float().cuda().requires_grad_()
+    conv_out = bc.conv(x)
+    assert rel_linf(conv_out, c["conv_out"]) < 1e-5
+    dx, dw = torch.autograd.grad(conv_out, [x, bc.conv.weight], c["gc"].float().cuda())
+    assert rel_linf(dx, c["conv_dx"]) < 1e-5 and rel_linf(dw, c["conv_dweight"]) < 1e-4
+    y = bc(x)
+    assert rel_linf(y, c["y"]) < 5e-5
+    dx, dw = torch.autograd.grad(y, [x, bc.conv.weight], c["gy"].float().cuda())
+    assert rel_linf(dx, c["dx"]) < 5e-4 and rel_linf(dw, c["dconv_weight"]) < 5e-4
+    xh.unpatch_model(bc)
+    assert type(bc.conv) is nn.Conv3d
+
+
+@pytest.mark.parametrize("shape,bias", [((1, 4, 16, 16, 32), False), ((2, 3, 5, 7, 3), True), ((1, 8, 24, 17, 70), True),
+                                        ((1, 1, 9, 8, 33), True), ((1, 4, 128, 128, 128), False)])
+def test_dwconv3_vs_pytorch_fp64(shape, bias):
+    """Forward, input gradient, weight and bias gradients against F.conv3d in fp64 (on the GPU for the full-size case)."""
+    from xlstm_hved_b200 import modules
+    C = shape[1]
+    torch.manual_seed(sum(shape))
+    conv = nn.Conv3d(C, C, 3, padding=1, groups=C, bias=bias).cuda()
+    x = torch.randn(shape, device="cuda")
+    gy = torch.randn(shape, device="cuda")
+    params = list(conv.parameters())
+    x64 = x.double().requires_grad_()
+    p64 = [p.detach().double().requires_grad_() for p in params]
+    ref = F.conv3d(x64, p64[0], p64[1] if bias else None, padding=1, groups=C)
+    ref_grads = torch.autograd.grad(ref, [x64] + p64, gy.double())
+    xc = x.clone().requires_grad_()
+    assert modules.dwconv3_supported(conv)
+    got = modules.depthwise_conv3_forward(conv, xc)
+    assert rel_linf(got, ref) < 1e-5
+    grads = torch.autograd.grad(got, [xc] + params, gy)
+    for a, r in zip(grads, ref_grads):
+        assert rel_linf(a, r) < 1e-4

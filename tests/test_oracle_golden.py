@@ -196,3 +196,12 @@ def test_atten_module2_matches_reference():
     assert rel_linf(grads[0], c["d_seg_x"]) < 1e-10 and rel_linf(grads[1], c["d_enc_x"]) < 1e-10
     for g, k in zip(grads[2:], c["param_grads"]):
         assert rel_linf(g, c["param_grads"][k]) < 1e-10, k
+
+
+def test_depthwise_basic_conv_matches_reference():
+    c = load_golden("dwconv3.pt")
+    x, w = c["x"].clone().requires_grad_(), c["state_dict"]["conv.weight"].clone().requires_grad_()
+    y, conv_out = restate.basic_conv_depthwise(x, w)
+    assert rel_linf(conv_out, c["conv_out"]) < 1e-12 and rel_linf(y, c["y"]) < 1e-11
+    dx, dw = torch.autograd.grad(y, [x, w], c["gy"])
+    assert rel_linf(dx, c["dx"]) < 1e-9 and rel_linf(dw, c["dconv_weight"]) < 1e-9

@@ -610,6 +610,14 @@ class _Gate7Function(torch.autograd.Function):
         return dx, dw, db
 
 
+def _conv_out_dtype(x):
+    """What a PyTorch convolution would return for this input: the autocast type inside an autocast region (train.py:207),
+    the input's type otherwise."""
+    if x.is_cuda and torch.is_autocast_enabled():
+        return torch.get_autocast_gpu_dtype()
+    return x.dtype
+
+
 def gate_convs_supported(dw, pw) -> bool:
     """A depthwise 7^3 convolution (stride 1, zero padding 3, any channel expansion) followed by a 1x1x1 convolution to one channel."""
     return (isinstance(dw, nn.Conv3d) and isinstance(pw, nn.Conv3d) and dw.kernel_size == (7, 7, 7) and dw.stride == (1, 1, 1)
@@ -632,7 +640,7 @@ def spatial_gate(x, dw, pw):
         b = (pw.weight.reshape(-1).float() * dw.bias.float()).sum().reshape(1)
     if pw.bias is not None:
         b = pw.bias.float().reshape(1) if b is None else b + pw.bias.float().reshape(1)
-    return _Gate7Function.apply(x.float(), w, b).to(x.dtype)
+    return _Gate7Function.apply(x.float(), w, b).to(_conv_out_dtype(x))
 
 
 def atten_module2_forward(mod, seg_x, enc_x, recon_x=None):
@@ -647,3 +655,38 @@ def atten_module2_forward(mod, seg_x, enc_x, recon_x=None):
     seg_scale = spatial_gate(spa_comp, mod.seg_spatial, mod.seg_spatial2)
     scaled_seg_x = seg_x * (1 + seg_scale)
     return torch.cat([scaled_seg_x, s_enc_x], 1)
+
+
+# ----------------------------------------------------------------------------- conv path: depthwise 3x3x3 convolution (K8)
+class _DwConv3Function(torch.autograd.Function):
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, w, b):
+        y = ops.dwconv3_fwd(x, w, b)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw, db = ops.dwconv3_bwd(x, w, dy, want_dx=ctx.needs_input_grad[0], want_dw=ctx.needs_input_grad[1],
+                                     want_db=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dw, db
+
+
+def dwconv3_supported(conv) -> bool:
+    """nn.Conv3d(C, C, 3, stride 1, zero padding 1, groups = C): the conv of BasicConv(C, C, 3, padding=1, groups=C), RA_HVED.py:406."""
+    return (isinstance(conv, nn.Conv3d) and conv.kernel_size == (3, 3, 3) and conv.stride == (1, 1, 1) and conv.padding == (1, 1, 1)
+            and conv.dilation == (1, 1, 1) and conv.padding_mode == "zeros" and conv.groups == conv.in_channels == conv.out_channels)
+
+
+def depthwise_conv3_forward(conv, x):
+    """nn.Conv3d.forward of a depthwise 3x3x3 layer on the fused kernels (forward, input gradient, weight gradient)."""
+    _require_device(x)
+    unbatched = x.dim() == 4
+    xb = x.unsqueeze(0) if unbatched else x
+    y = _DwConv3Function.apply(xb.float(), conv.weight.float(), conv.bias.float() if conv.bias is not None else None)
+    y = y.to(_conv_out_dtype(x))
+    return y.squeeze(0) if unbatched else y

@@ -362,6 +362,37 @@ def gate7_bwd(x, w, gate, dgate, want_dx: bool = True, want_dw: bool = True):
     return dx, dw, db
 
 
+# ----------------------------------------------------------------------------- depthwise 3x3x3 convolution (K8)
+def dwconv3_fwd(x, w, bias=None):
+    """x: (N, C, D, H, W) fp32; w: (C, 1, 3, 3, 3) or (C, 27); bias: (C) or None."""
+    lib = _lib.load_library()
+    if not x.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    x, w = _f32c(x), _f32c(w)
+    N, C, D, H, W = x.shape
+    if w.numel() != C * 27:
+        raise RuntimeError(f"dwconv3: weights of {w.numel()} elements for {C} channels")
+    y = torch.empty_like(x)
+    check(lib.xhved_dwconv3_fwd(ptr(x), ptr(w), ptr(_f32c(bias)) if bias is not None else None, N, C, D, H, W, ptr(y), stream()),
+          "xhved_dwconv3_fwd")
+    return y
+
+
+def dwconv3_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: bool = False):
+    """Returns (dx, dw, dbias) -- None where not wanted; dw has the shape of w."""
+    lib = _lib.load_library()
+    x, wc, dy = _f32c(x), _f32c(w), _f32c(dy)
+    N, C, D, H, W = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    dw = db = part = None
+    if want_dw or want_db:
+        dw = torch.empty(w.shape, device=x.device, dtype=torch.float32)
+        db = torch.empty(C, device=x.device, dtype=torch.float32) if want_db else None
+        part = torch.empty(lib.xhved_dwconv3_workspace(N, C, D, H, W), device=x.device, dtype=torch.uint8)
+    check(lib.xhved_dwconv3_bwd(ptr(x), ptr(wc), ptr(dy), N, C, D, H, W, ptr(part), ptr(dx), ptr(dw), ptr(db), stream()), "xhved_dwconv3_bwd")
+    return dx, (dw if want_dw else None), db
+
+
 # ----------------------------------------------------------------------------- mLSTM cell
 class CellBuffers:
     """Device buffers of one chunkwise cell invocation (tiles + saved-for-backward state)."""
