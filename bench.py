@@ -459,6 +459,10 @@ def run_gpu(args):
                                 "frac": round(gbs / peaks0["hbm"], 4), "algorithmic_bytes_per_launch": bytes_c3,
                                 "note": "32 B in (4 modality posteriors; the constant prior is declared, not read) + 15 x 8 B out per latent element"}}
 
+    conv_path = None
+    if rank == 0 and not args.no_conv_path:
+        conv_path = conv_path_block(device, load_peaks())
+
     # ---- per-kernel attribution (separate pass, CUDA events on the launching stream)
     nk = lib.xhved_profile_kernel_count()
     names = [lib.xhved_profile_kernel_name(i).decode() for i in range(nk)]
@@ -634,7 +638,7 @@ def run_gpu(args):
                         "latent levels and the loss term (own stream, full duplex with the next step's inputs).  The gradients w.r.t. the "
                         "posteriors (d_mu, d_logvar: 8 x the z bytes) and the 28 parameter gradients stay on the device, where the encoder "
                         "backward / the optimizer consume them.  PCIe-bound"},
-        "sustained": sustained, "config3": config3, "gpu_eager_reference": eager_ref,
+        "sustained": sustained, "config3": config3, "conv_path": conv_path, "gpu_eager_reference": eager_ref,
         "gpu_launches": launches, "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
         "kernel_ms_per_step_total": round(sum(v[0] for v in kern.values()) / K, 4), "kernel_time_share": shares, "roofline": roof, "roofline_secondary": secondary,
         "clocks": clocks, "mlstm_cell_tensor_peak": cell,
@@ -647,6 +651,55 @@ def run_gpu(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU / reference arm
+def conv_path_block(device, peaks, n_vol=8, iters=10, warm=3):
+    """SURVEY 8f rank 1 (the callers either side of the path): the conv path's normalisation / gate / depthwise kernels (K6, K7, K8)
+    alone, at the first encoder level's shape for `n_vol` volumes -- (n_vol, 4, 128^3) fp32 = 268 MB per tensor, larger than L2.
+    CUDA events on the launching stream, rank-local (no collective).  HBM fractions are on algorithmic bytes."""
+    from xlstm_hved_b200 import ops as xops
+    g = torch.Generator(device=device).manual_seed(3)
+    shape = (n_vol, 4, 128, 128, 128)
+    x = torch.rand(shape, device=device, generator=g)
+    dy = torch.randn(shape, device=device, generator=g)
+    elems = x.numel()
+
+    def t(fn):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / iters
+
+    def hbm(ms, nbytes):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac": round(gbs / peaks["hbm"], 4), "algorithmic_bytes": nbytes}
+
+    out = {"workload": f"conv path of XLSTM_HVED at the first encoder level, {n_vol} volumes: tensors ({n_vol}, 4, 128^3) fp32 (> L2)",
+           "peak": peaks["hbm"], "unit": "GB/s"}
+    y, mean, rstd = xops.norm_act_fwd(x, slope=0.01)
+    out["norm_act_fwd"] = hbm(t(lambda: xops.norm_act_fwd(x, slope=0.01)), 8 * elems)
+    out["norm_act_bwd"] = hbm(t(lambda: xops.norm_act_bwd(x, dy, mean, rstd, slope=0.01)), 12 * elems)
+    out["pytorch_instance_norm_leaky_relu_fwd_ms"] = round(t(lambda: torch.nn.functional.leaky_relu_(torch.nn.functional.instance_norm(x), 0.01)), 3)
+    w3 = torch.randn(4, 27, device=device, generator=g) * 0.2
+    out["dwconv3_fwd"] = hbm(t(lambda: xops.dwconv3_fwd(x, w3)), 8 * elems)
+    out["dwconv3_bwd"] = hbm(t(lambda: xops.dwconv3_bwd(x, w3, dy)), 16 * elems)          # dgrad: dy in, dx out; wgrad: x, dy in
+    w7 = torch.randn(4, 343, device=device, generator=g) * 0.02
+    dgate = dy[:, :1].contiguous()
+    gate = xops.gate7_fwd(x, w7)
+    fl = 2.0 * 343 * elems                                                                   # one FMA per tap and input element
+    ms_f, ms_b = t(lambda: xops.gate7_fwd(x, w7)), t(lambda: xops.gate7_bwd(x, w7, gate, dgate))
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                                              # nominal CUDA-core fp32 (no measured figure)
+    out["gate7_fwd"] = {"ms": round(ms_f, 4), "TFLOP/s": round(fl / (ms_f * 1e-3) / 1e12, 2), "frac_of_nominal_fp32": round(fl / (ms_f * 1e-3) / 1e12 / fp32_peak, 4)}
+    out["gate7_bwd"] = {"ms": round(ms_b, 4), "TFLOP/s": round(2 * fl / (ms_b * 1e-3) / 1e12, 2),
+                        "frac_of_nominal_fp32": round(2 * fl / (ms_b * 1e-3) / 1e12 / fp32_peak, 4)}
+    out["nominal_fp32_TFLOP/s"] = round(fp32_peak, 1)
+    return out
+
+
 def cpu_hot_path_one_volume(params_f, params_r, x, mus, lvs, gy, gzs):
     """The reference's algorithm for the same hot path on the CPU (oracle port: fp32, O(S^2) parallel cell with the
     reference's op sequence, PoE as buildingblocks.py:853-866), forward + backward through autograd."""
@@ -817,6 +870,7 @@ def main():
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained loop")
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2], help="2: S-MVAE fusion on a side stream next to the ViL pair")
     ap.add_argument("--no-eager-ref", action="store_true", help="skip timing the reference's PyTorch classes on the GPU")
+    ap.add_argument("--no-conv-path", action="store_true", help="skip the K6 / K7 / K8 block (conv-path kernels alone)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured step")
     args = ap.parse_args()
     if args.impl == "reference":

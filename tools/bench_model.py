@@ -61,6 +61,26 @@ def main():
         model.train()
         out[f"{tag}_train_fwd_bwd_ms"] = round(timeit(train_step, iters=3, warm=1), 2)
         out[f"{tag}_mViL_fwd_bwd_ms"] = round(timeit(vil_alone, iters=10), 3)
+    # the patched inference forward replayed as ONE CUDA graph (eager it is bound by ~900 launches from Python)
+    model.eval()
+    static_x = x.clone()
+    # per-sample drop mask handed over as a device tensor: the subset-index form builds it on the host and copies it inside the
+    # forward (RA_HVED.py:515-520), which a stream capture refuses
+    drop = torch.zeros(1, 4, dtype=torch.bool, device="cuda")
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                model(static_x, [14], instance_missing=True, drop=drop, valid=True)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            seg_static, _ = model(static_x, [14], instance_missing=True, drop=drop, valid=True)
+        eager_seg, _ = model(x, [14], valid=True)
+    graph.replay()
+    out["patched_conv_norm_graph_infer_same_mask"] = ((seg_static > 0.5) == (eager_seg > 0.5)).float().mean().item()
+    out["patched_conv_norm_graph_infer_ms"] = round(timeit(graph.replay, iters=10), 2)
     xh.unpatch_model(model)
     out["note"] = "reference XLSTM_HVED f_maps=4, one 128^3 volume, fp32 eager on one B200; mViL = the bottleneck ViL wrapper alone"
     print(json.dumps(out))

@@ -63,7 +63,11 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--stock", action="store_true", help="leave the reference's PyTorch ViL / PoE path in place (A/B)")
     ap.add_argument("--no-amp", action="store_true")
+    ap.add_argument("--truth", action="store_true", help="grads mode: also run the stock model in fp64 and compare both fp32 paths with it")
+    ap.add_argument("--no-tf32", action="store_true", help="cuDNN / cuBLAS in plain fp32 (PyTorch's default lets convolutions use TF32)")
     args = ap.parse_args()
+    if args.no_tf32:
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -127,13 +131,47 @@ def main():
             return flat, loss.item(), none
         gs, ls, n0 = grads_of("stock")
         gp, lp, n1 = grads_of("patched")
+        truth = None
+        if args.truth:
+            # the same step through the STOCK model in fp64 (fp32 noise draws, widened): which of the two fp32 paths is nearer?
+            import copy
+            xh.unpatch_model(model)
+            m64 = copy.deepcopy(model).double().train()
+            ra = sys.modules["RA_HVED"]
+            orig_rep = ra.reparametrize
+
+            def rep64(mu, logvar, valid=False):
+                if valid:
+                    return mu
+                std = logvar.mul(0.5).exp()
+                return torch.empty(std.size(), dtype=torch.float32, device=std.device).normal_().double() * std + mu
+            ra.reparametrize = rep64
+            try:
+                torch.manual_seed(77 + rank)
+                with quiet():
+                    f_out, _, _ = m64(x.double(), [14], recon=True)
+                    m_out, (mu, logvar), m_rec = m64(x.double(), [5], recon=True)
+                    kld = sum(ns.loss.compute_KLD(mu[l], logvar[l], [5]) for l in range(len(mu))) / len(mu)
+                    loss = train_step.dice(f_out, mask.double()) + train_step.dice(m_out, mask.double()) + \
+                        0.2 * torch.nn.functional.mse_loss(torch.cat(m_rec, 1), x.double()) + 0.2 * kld
+                loss.backward()
+            finally:
+                ra.reparametrize = orig_rep
+            g64 = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in m64.parameters()])
+            if world > 1:
+                dist.all_reduce(g64)
+                g64 /= world
+            rl = lambda a: ((a.double() - g64).norm() / g64.norm()).item()
+            truth = {"rel_l2_stock_fp32_vs_fp64": rl(gs), "rel_l2_patched_vs_fp64": rl(gp), "loss_fp64": loss.item()}
+            del m64
         if args.stock:
             xh.unpatch_model(model)
         rel = ((gp.double() - gs.double()).norm() / gs.double().norm()).item()
         cos = torch.nn.functional.cosine_similarity(gp.double(), gs.double(), dim=0).item()
         if rank == 0:
             print(json.dumps({"mode": "grads", **common, "grad_elements": gs.numel(), "rel_l2_patched_vs_stock": rel, "cosine": cos,
-                              "loss_stock": ls, "loss_patched": lp, "params_without_grad": [n0, n1],
+                              "loss_stock": ls, "loss_patched": lp, "params_without_grad": [n0, n1], "fp64_truth": truth,
+                              "tf32_convs": torch.backends.cudnn.allow_tf32,
                               "note": "one training step (subsets [14] and [5], seeded noise), fp32, all gradients of the model in one flat "
                                       "bucket averaged over the ranks; bf16 tensor-core operands in the patched ViL cell"}))
 
