@@ -687,6 +687,20 @@ def conv_path_block(device, peaks, n_vol=8, iters=10, warm=3):
     w3 = torch.randn(4, 27, device=device, generator=g) * 0.2
     out["dwconv3_fwd"] = hbm(t(lambda: xops.dwconv3_fwd(x, w3)), 8 * elems)
     out["dwconv3_bwd"] = hbm(t(lambda: xops.dwconv3_bwd(x, w3, dy)), 16 * elems)          # dgrad: dy in, dx out; wgrad: x, dy in
+    w1, b1 = torch.randn(4, 4, device=device, generator=g) * 0.5, torch.randn(4, device=device, generator=g)
+    out["pwconv_fwd"] = hbm(t(lambda: xops.pwconv_fwd(x, w1, b1)), 8 * elems)
+    out["pwconv_bwd"] = hbm(t(lambda: xops.pwconv_bwd(x, w1, dy, want_db=True)), 16 * elems)       # dgrad: dy in, dx out; wgrad: x, dy in
+    xh16, dyh16 = x.half(), dy.half()
+    out["pwconv_fwd_fp16"] = hbm(t(lambda: xops.pwconv_fwd(xh16, w1, b1)), 4 * elems)
+    out["pwconv_bwd_fp16"] = hbm(t(lambda: xops.pwconv_bwd(xh16, w1, dyh16, want_db=True)), 8 * elems)
+    conv16 = torch.nn.Conv3d(4, 4, 1).to(device).half()
+    xg16 = xh16[:1].clone().requires_grad_()
+
+    def stock16():
+        conv16.zero_grad(set_to_none=True)
+        torch.autograd.grad(conv16(xg16), [xg16] + list(conv16.parameters()), dyh16[:1])
+    out["pytorch_conv1x1x1_fp16_fwd_bwd_ms_ONE_volume"] = round(t(stock16), 3)
+    del xh16, dyh16
     w7 = torch.randn(4, 343, device=device, generator=g) * 0.02
     dgate = dy[:, :1].contiguous()
     gate = xops.gate7_fwd(x, w7)

@@ -192,6 +192,19 @@ int xhved_dwconv3_fwd(const float* x, const float* w, const float* bias, int N, 
 int xhved_dwconv3_bwd(const float* x, const float* w, const float* dy, int N, int C, int D, int H, int W, void* partials, float* dx,
                       float* dw, float* dbias, void* stream);
 
+/* ---------------------------------------------------------------- 1x1x1 convolution (K9)
+ * nn.Conv3d(Cin, Cout, 1): the squeeze / fuse layers of DuSEAttention (modules/DuSFE.py:100-104), the 1x1x1 layers of the VU blocks and
+ * final_conv (RA_HVED.py:483, 567-605); Cin, Cout <= 32 (XHVED_ERR_UNSUPPORTED_DIM above).  x: (N, Cin, vol), y / dy: (N, Cout, vol)
+ * contiguous, element type `dtype` (0 fp32, 1 fp16, 2 bf16); w: (Cout, Cin) fp32, bias: (Cout) fp32 or NULL; fp32 accumulation.
+ *   y[n][o][v] = bias[o] + sum_i w[o][i] x[n][i][v]
+ * Backward: dx (optional, type `dtype`), dw (optional, (Cout, Cin) fp32), dbias (optional, (Cout) fp32); `partials`: device scratch of
+ * xhved_pwconv_workspace(...) bytes, needed for dw / dbias when Cin, Cout <= 8. */
+int64_t xhved_pwconv_workspace(int N, int Cin, int Cout, int64_t vol);
+int xhved_pwconv_fwd(const void* x, const float* w, const float* bias, int N, int Cin, int Cout, int64_t vol, int dtype, void* y,
+                     void* stream);
+int xhved_pwconv_bwd(const void* x, const float* w, const void* dy, int N, int Cin, int Cout, int64_t vol, int dtype, void* partials,
+                     void* dx, float* dw, float* dbias, void* stream);
+
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
 int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);

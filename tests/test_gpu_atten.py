@@ -173,3 +173,59 @@ def test_dwconv3_vs_pytorch_fp64(shape, bias):
     grads = torch.autograd.grad(got, [xc] + params, gy)
     for a, r in zip(grads, ref_grads):
         assert rel_linf(a, r) < 1e-4
+
+
+# ------------------------------------------------------------------ K9: 1x1x1 convolution (csrc/pwconv.cu)
+@pytest.mark.parametrize("cin,cout,shape,bias", [(4, 4, (16, 16, 32), True), (4, 1, (5, 7, 3), True), (4, 3, (9, 11, 37), True),
+                                                 (8, 32, (8, 8, 8), False), (16, 16, (6, 5, 7), True), (32, 32, (4, 4, 4), False),
+                                                 (8, 8, (12, 10, 18), True), (16, 1, (8, 8, 8), True), (4, 4, (128, 128, 128), True)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 3e-3)])
+def test_pwconv_vs_fp64(cin, cout, shape, bias, dtype, tol):
+    """Forward, input gradient, weight and bias gradients of the 1x1x1 convolution against an fp64 einsum (on the GPU): register
+    tiles of 1 / 4 / 8 / 16 / 32 output channels, both weight-gradient strategies, aligned and ragged volumes, fp32 and fp16 I/O."""
+    from xlstm_hved_b200 import modules
+    N = 1 if shape[0] == 128 else 2
+    torch.manual_seed(cin * 100 + cout + sum(shape))
+    conv = nn.Conv3d(cin, cout, 1, bias=bias).cuda()
+    x = torch.randn(N, cin, *shape, device="cuda").to(dtype)
+    gy = torch.randn(N, cout, *shape, device="cuda").to(dtype)
+    params = list(conv.parameters())
+    x64 = x.double().requires_grad_()
+    p64 = [p.detach().double().requires_grad_() for p in params]
+    ref = torch.einsum("oi,nidhw->nodhw", p64[0].reshape(cout, cin), x64)
+    if bias:
+        ref = ref + p64[1].reshape(1, cout, 1, 1, 1)
+    ref_grads = torch.autograd.grad(ref, [x64] + p64, gy.double())
+    xc = x.clone().requires_grad_()
+    assert modules.pwconv_supported(conv)
+    got = modules.pointwise_conv_forward(conv, xc)
+    assert got.dtype == dtype and rel_linf(got, ref) < tol
+    grads = torch.autograd.grad(got, [xc] + params, gy)
+    assert grads[0].dtype == dtype and grads[1].dtype == torch.float32
+    for a, r in zip(grads, ref_grads):
+        assert rel_linf(a, r) < (tol if dtype == torch.float16 else 1e-4)
+
+
+def test_patched_pointwise_conv_under_autocast_matches_pytorch():
+    """Inside an fp16 autocast region (train.py:207) the patched 1x1x1 layer takes an fp32 input as fp16 and returns fp16, like
+    PyTorch's convolution; values and gradients agree with the stock layer to fp16 accuracy."""
+    import copy
+    import xlstm_hved_b200 as xh
+    torch.manual_seed(1)
+    stock = nn.Sequential(nn.Conv3d(4, 4, 1), nn.Conv3d(4, 1, 1)).cuda()
+    mine = copy.deepcopy(stock)
+    counts = xh.patch_model(mine)
+    assert counts["PointwiseConv3d"] == 2
+    x = torch.randn(1, 4, 32, 32, 32, device="cuda")
+    outs = []
+    for m in (stock, mine):
+        xin = x.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=torch.float16):
+            y = m(xin)
+        assert y.dtype == torch.float16
+        g = torch.autograd.grad(y.float().square().sum(), [xin] + list(m.parameters()))
+        outs.append((y, g))
+    assert rel_linf(outs[1][0], outs[0][0]) < 5e-3
+    for a, r in zip(outs[1][1], outs[0][1]):
+        assert a.dtype == r.dtype and rel_linf(a, r) < 1e-2
+    xh.unpatch_model(mine)

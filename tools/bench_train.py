@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--stock", action="store_true", help="leave the reference's PyTorch ViL / PoE path in place (A/B)")
     ap.add_argument("--no-amp", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="train mode: print a torch.profiler kernel table of one step to stderr")
     ap.add_argument("--truth", action="store_true", help="grads mode: also run the stock model in fp64 and compare both fp32 paths with it")
     ap.add_argument("--no-tf32", action="store_true", help="cuDNN / cuBLAS in plain fp32 (PyTorch's default lets convolutions use TF32)")
     args = ap.parse_args()
@@ -187,6 +188,14 @@ def main():
             return train_step(ns, model, opt, scaler, bucket, x, mask, idx, amp=not args.no_amp)
         for _ in range(args.warmup):
             step()
+        if args.profile and rank == 0:
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+                step()
+                torch.cuda.synchronize()
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=80), file=sys.stderr)
+            print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=34,
+                                                                     max_shapes_column_width=110), file=sys.stderr)
         ms = timed(step, args.steps)
         if rank == 0:
             print(json.dumps({"mode": "train", **common, "steps": args.steps, "ms_per_step": round(ms / args.steps, 2),

@@ -91,6 +91,9 @@ SYMBOLS = {
     "xhved_dwconv3_workspace": [c_int] * 5,
     "xhved_dwconv3_fwd": [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p, c_void_p],
     "xhved_dwconv3_bwd": [c_void_p] * 3 + [c_int] * 5 + [c_void_p] * 5,
+    "xhved_pwconv_workspace": [c_int, c_int, c_int, c_int64],
+    "xhved_pwconv_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_void_p, c_void_p],
+    "xhved_pwconv_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int] + [c_void_p] * 5,
     "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,
@@ -144,7 +147,7 @@ def load_library() -> ctypes.CDLL:
                 continue
             fn.argtypes = argtypes
             fn.restype = (ctypes.c_char_p if name == "xhved_profile_kernel_name" else
-                          c_int64 if name in ("xhved_norm_act_workspace", "xhved_gate7_workspace", "xhved_dwconv3_workspace") else c_int)
+                          c_int64 if name in ("xhved_norm_act_workspace", "xhved_gate7_workspace", "xhved_dwconv3_workspace", "xhved_pwconv_workspace") else c_int)
         if missing:
             raise RuntimeError(f"{LIB_PATH} lacks symbols declared in include/xhved.h: {missing}; rebuild it")
         _lib = lib

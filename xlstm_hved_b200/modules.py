@@ -613,8 +613,8 @@ class _Gate7Function(torch.autograd.Function):
 def _conv_out_dtype(x):
     """What a PyTorch convolution would return for this input: the autocast type inside an autocast region (train.py:207),
     the input's type otherwise."""
-    if x.is_cuda and torch.is_autocast_enabled():
-        return torch.get_autocast_gpu_dtype()
+    if x.is_cuda and torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda")
     return x.dtype
 
 
@@ -689,4 +689,42 @@ def depthwise_conv3_forward(conv, x):
     xb = x.unsqueeze(0) if unbatched else x
     y = _DwConv3Function.apply(xb.float(), conv.weight.float(), conv.bias.float() if conv.bias is not None else None)
     y = y.to(_conv_out_dtype(x))
+    return y.squeeze(0) if unbatched else y
+
+
+# ----------------------------------------------------------------------------- conv path: 1x1x1 convolution (K9)
+class _PwConvFunction(torch.autograd.Function):
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, w, b):
+        y = ops.pwconv_fwd(x, w, b)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw, db = ops.pwconv_bwd(x, w, dy, want_dx=ctx.needs_input_grad[0], want_dw=ctx.needs_input_grad[1],
+                                    want_db=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, (dw.to(w.dtype) if dw is not None else None), db
+
+
+def pwconv_supported(conv) -> bool:
+    """nn.Conv3d(Cin, Cout, 1) with stride 1, no padding, one group, at most 32 channels on either side."""
+    return (isinstance(conv, nn.Conv3d) and conv.kernel_size == (1, 1, 1) and conv.stride == (1, 1, 1) and conv.padding == (0, 0, 0)
+            and conv.dilation == (1, 1, 1) and conv.groups == 1 and conv.in_channels <= 32 and conv.out_channels <= 32)
+
+
+def pointwise_conv_forward(conv, x):
+    """nn.Conv3d.forward of a 1x1x1 layer on the fused kernels.  Inside an autocast region the input is taken (and the output
+    returned) in the autocast type, as PyTorch's convolution would (train.py:207); weights, bias and accumulation stay fp32."""
+    _require_device(x)
+    unbatched = x.dim() == 4
+    xb = x.unsqueeze(0) if unbatched else x
+    xb = xb.to(_conv_out_dtype(xb))
+    if xb.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        xb = xb.float()
+    y = _PwConvFunction.apply(xb, conv.weight.float(), conv.bias.float() if conv.bias is not None else None)
     return y.squeeze(0) if unbatched else y

@@ -393,6 +393,41 @@ def dwconv3_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: b
     return dx, (dw if want_dw else None), db
 
 
+# ----------------------------------------------------------------------------- 1x1x1 convolution (K9)
+def pwconv_fwd(x, w, bias=None):
+    """x: (N, Cin, *spatial) fp32 / fp16 / bf16; w: (Cout, Cin[, 1, 1, 1]); bias: (Cout) or None.  Output in x's type."""
+    lib = _lib.load_library()
+    if not x.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    if x.dtype not in _NORM_DTYPES:
+        raise RuntimeError(f"xlstm_hved_b200 pwconv: unsupported dtype {x.dtype}")
+    x, w = x.contiguous(), _f32c(w)
+    N, Cin = x.shape[:2]
+    Cout, vol = w.shape[0], x[0, 0].numel()
+    y = torch.empty((N, Cout) + tuple(x.shape[2:]), device=x.device, dtype=x.dtype)
+    check(lib.xhved_pwconv_fwd(ptr(x), ptr(w), ptr(_f32c(bias)) if bias is not None else None, N, Cin, Cout, vol, _NORM_DTYPES[x.dtype],
+                               ptr(y), stream()), "xhved_pwconv_fwd")
+    return y
+
+
+def pwconv_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: bool = False):
+    """Returns (dx in x's type, dw fp32 in w's shape, dbias fp32) -- None where not wanted."""
+    lib = _lib.load_library()
+    x, wc = x.contiguous(), _f32c(w)
+    dy = dy.to(x.dtype).contiguous()
+    N, Cin = x.shape[:2]
+    Cout, vol = w.shape[0], x[0, 0].numel()
+    dx = torch.empty_like(x) if want_dx else None
+    dw = torch.empty(w.shape, device=x.device, dtype=torch.float32) if want_dw else None
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if want_db else None
+    part = None
+    if (want_dw or want_db) and Cin <= 8 and Cout <= 8:
+        part = torch.empty(lib.xhved_pwconv_workspace(N, Cin, Cout, vol), device=x.device, dtype=torch.uint8)
+    check(lib.xhved_pwconv_bwd(ptr(x), ptr(wc), ptr(dy), N, Cin, Cout, vol, _NORM_DTYPES[x.dtype], ptr(part), ptr(dx), ptr(dw), ptr(db),
+                               stream()), "xhved_pwconv_bwd")
+    return dx, dw, db
+
+
 # ----------------------------------------------------------------------------- mLSTM cell
 class CellBuffers:
     """Device buffers of one chunkwise cell invocation (tiles + saved-for-backward state)."""
