@@ -13,4 +13,7 @@ for _ in range(3):
     ops.dwconv3_bwd(x, w3, dy)
     gate = ops.gate7_fwd(x, w7)
     ops.gate7_bwd(x, w7, gate, dy[:, :1].contiguous())
+    w1 = w3[:, :4].contiguous()
+    ops.pwconv_fwd(x, w1)
+    ops.pwconv_bwd(x, w1, dy, want_db=True)
 torch.cuda.synchronize()
