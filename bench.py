@@ -701,6 +701,14 @@ def conv_path_block(device, peaks, n_vol=8, iters=10, warm=3):
         torch.autograd.grad(conv16(xg16), [xg16] + list(conv16.parameters()), dyh16[:1])
     out["pytorch_conv1x1x1_fp16_fwd_bwd_ms_ONE_volume"] = round(t(stock16), 3)
     del xh16, dyh16
+    wd = torch.randn(4, 4, 3, 3, 3, device=device, generator=g) * 0.1
+    fl3 = 2.0 * 27 * 4 * elems                                                               # 27 taps x 4 input channels per output element
+    ms_f, ms_b = t(lambda: xops.conv3_fwd(x, wd, b1)), t(lambda: xops.conv3_bwd(x, wd, dy, want_db=True))
+    fp32_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+    out["conv3_fwd"] = {**hbm(ms_f, 8 * elems), "TFLOP/s": round(fl3 / (ms_f * 1e-3) / 1e12, 2),
+                        "frac_of_nominal_fp32": round(fl3 / (ms_f * 1e-3) / 1e12 / fp32_nominal, 4)}
+    out["conv3_bwd"] = {**hbm(ms_b, 16 * elems), "TFLOP/s": round(2 * fl3 / (ms_b * 1e-3) / 1e12, 2),
+                        "frac_of_nominal_fp32": round(2 * fl3 / (ms_b * 1e-3) / 1e12 / fp32_nominal, 4)}
     w7 = torch.randn(4, 343, device=device, generator=g) * 0.02
     dgate = dy[:, :1].contiguous()
     gate = xops.gate7_fwd(x, w7)

@@ -205,6 +205,19 @@ int xhved_pwconv_fwd(const void* x, const float* w, const float* bias, int N, in
 int xhved_pwconv_bwd(const void* x, const float* w, const void* dy, int N, int Cin, int Cout, int64_t vol, int dtype, void* partials,
                      void* dx, float* dw, float* dbias, void* stream);
 
+/* ---------------------------------------------------------------- dense 3x3x3 convolution, few channels (K10)
+ * nn.Conv3d(Cin, Cout, 3, stride 1, padding 1), one group, Cin, Cout <= 64 (XHVED_ERR_UNSUPPORTED_DIM above): the SingleConv /
+ * DoubleConv layers of the encoders and decoders (buildingblocks.py:444-507).  x: (N, Cin, D, H, W), y / dy: (N, Cout, D, H, W)
+ * contiguous, element type `dtype` (0 fp32, 1 fp16, 2 bf16); w: (Cout, Cin, 27) fp32; bias: (Cout) fp32 or NULL; fp32 accumulation.
+ *   y[n][o][v] = bias[o] + sum_i sum_tap x[n][i][v + tap - 1] w[o][i][tap]
+ * Backward: dx (optional, type `dtype`), dw (optional, (Cout, Cin, 27) fp32), dbias (optional); dw / dbias need `partials`, a device
+ * scratch of xhved_conv3_workspace(...) bytes. */
+int64_t xhved_conv3_workspace(int N, int Cin, int Cout, int D, int H, int W);
+int xhved_conv3_fwd(const void* x, const float* w, const float* bias, int N, int Cin, int Cout, int D, int H, int W, int dtype, void* y,
+                    void* stream);
+int xhved_conv3_bwd(const void* x, const float* w, const void* dy, int N, int Cin, int Cout, int D, int H, int W, int dtype, void* partials,
+                    void* dx, float* dw, float* dbias, void* stream);
+
 /* reparametrize (RA_HVED.py:741-747): z = mu + noise * exp(0.5 logvar); and its backward. */
 int xhved_reparam_fwd(const float* mu, const float* logvar, const float* noise, int64_t n, float* z, void* stream);
 int xhved_reparam_bwd(const float* logvar, const float* noise, const float* g_z, int64_t n, float* d_mu, float* d_logvar, void* stream);

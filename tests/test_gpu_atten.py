@@ -229,3 +229,32 @@ def test_patched_pointwise_conv_under_autocast_matches_pytorch():
     for a, r in zip(outs[1][1], outs[0][1]):
         assert a.dtype == r.dtype and rel_linf(a, r) < 1e-2
     xh.unpatch_model(mine)
+
+
+# ------------------------------------------------------------------ K10: dense 3x3x3 convolution with few channels (csrc/conv3.cu)
+@pytest.mark.parametrize("cin,cout,shape,bias", [(4, 4, (16, 16, 32), True), (12, 4, (9, 11, 37), True), (4, 8, (8, 8, 33), True),
+                                                 (24, 8, (12, 10, 18), False), (48, 16, (8, 9, 10), True), (16, 32, (5, 7, 3), True),
+                                                 (3, 5, (40, 8, 32), True), (4, 4, (128, 128, 128), True)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 4e-3)])
+def test_conv3_vs_pytorch_fp64(cin, cout, shape, bias, dtype, tol):
+    """Forward, input gradient, weight and bias gradients against F.conv3d in fp64 (on the GPU): both register tiles, several
+    output-channel groups, ragged volumes, more than four tiles along d (two weight-gradient super-tiles), fp32 and fp16 I/O."""
+    from xlstm_hved_b200 import modules
+    N = 1 if shape[0] == 128 else 2
+    torch.manual_seed(cin * 100 + cout + sum(shape))
+    conv = nn.Conv3d(cin, cout, 3, padding=1, bias=bias).cuda()
+    x = torch.randn(N, cin, *shape, device="cuda").to(dtype)
+    gy = torch.randn(N, cout, *shape, device="cuda").to(dtype)
+    params = list(conv.parameters())
+    x64 = x.double().requires_grad_()
+    p64 = [p.detach().double().requires_grad_() for p in params]
+    ref = F.conv3d(x64, p64[0], p64[1] if bias else None, padding=1)
+    ref_grads = torch.autograd.grad(ref, [x64] + p64, gy.double())
+    xc = x.clone().requires_grad_()
+    assert modules.conv3_supported(conv)
+    got = modules.dense_conv3_forward(conv, xc)
+    assert got.dtype == dtype and rel_linf(got, ref) < tol
+    grads = torch.autograd.grad(got, [xc] + params, gy)
+    assert grads[0].dtype == dtype and grads[1].dtype == torch.float32
+    for a, r in zip(grads, ref_grads):
+        assert rel_linf(a, r) < (tol if dtype == torch.float16 else 1e-4)

@@ -94,6 +94,9 @@ SYMBOLS = {
     "xhved_pwconv_workspace": [c_int, c_int, c_int, c_int64],
     "xhved_pwconv_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_void_p, c_void_p],
     "xhved_pwconv_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int] + [c_void_p] * 5,
+    "xhved_conv3_workspace": [c_int] * 6,
+    "xhved_conv3_fwd": [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p, c_void_p],
+    "xhved_conv3_bwd": [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p] * 5,
     "xhved_reparam_fwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "xhved_reparam_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "xhved_mlstm_fwd": [c_void_p] * 5 + [c_int] * 4 + [c_float] + [c_void_p] * 9,
@@ -147,7 +150,7 @@ def load_library() -> ctypes.CDLL:
                 continue
             fn.argtypes = argtypes
             fn.restype = (ctypes.c_char_p if name == "xhved_profile_kernel_name" else
-                          c_int64 if name in ("xhved_norm_act_workspace", "xhved_gate7_workspace", "xhved_dwconv3_workspace", "xhved_pwconv_workspace") else c_int)
+                          c_int64 if name in ("xhved_norm_act_workspace", "xhved_gate7_workspace", "xhved_dwconv3_workspace", "xhved_pwconv_workspace", "xhved_conv3_workspace") else c_int)
         if missing:
             raise RuntimeError(f"{LIB_PATH} lacks symbols declared in include/xhved.h: {missing}; rebuild it")
         _lib = lib

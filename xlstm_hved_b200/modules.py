@@ -728,3 +728,42 @@ def pointwise_conv_forward(conv, x):
         xb = xb.float()
     y = _PwConvFunction.apply(xb, conv.weight.float(), conv.bias.float() if conv.bias is not None else None)
     return y.squeeze(0) if unbatched else y
+
+
+# ----------------------------------------------------------------------------- conv path: dense 3x3x3 convolution, few channels (K10)
+class _Conv3Function(torch.autograd.Function):
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, w, b):
+        y = ops.conv3_fwd(x, w, b)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw, db = ops.conv3_bwd(x, w, dy, want_dx=ctx.needs_input_grad[0], want_dw=ctx.needs_input_grad[1],
+                                   want_db=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, (dw.to(w.dtype) if dw is not None else None), db
+
+
+def conv3_supported(conv) -> bool:
+    """nn.Conv3d(Cin, Cout, 3, stride 1, zero padding 1), one group, at most 64 channels on either side."""
+    return (isinstance(conv, nn.Conv3d) and conv.kernel_size == (3, 3, 3) and conv.stride == (1, 1, 1) and conv.padding == (1, 1, 1)
+            and conv.dilation == (1, 1, 1) and conv.padding_mode == "zeros" and conv.groups == 1 and conv.in_channels <= 64
+            and conv.out_channels <= 64)
+
+
+def dense_conv3_forward(conv, x):
+    """nn.Conv3d.forward of a small-channel 3x3x3 layer on the direct-convolution kernels; autocast behaviour as in
+    pointwise_conv_forward."""
+    _require_device(x)
+    unbatched = x.dim() == 4
+    xb = x.unsqueeze(0) if unbatched else x
+    xb = xb.to(_conv_out_dtype(xb))
+    if xb.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        xb = xb.float()
+    y = _Conv3Function.apply(xb, conv.weight.float(), conv.bias.float() if conv.bias is not None else None)
+    return y.squeeze(0) if unbatched else y

@@ -428,6 +428,43 @@ def pwconv_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: bo
     return dx, dw, db
 
 
+# ----------------------------------------------------------------------------- dense 3x3x3 convolution, few channels (K10)
+def conv3_fwd(x, w, bias=None):
+    """x: (N, Cin, D, H, W) fp32 / fp16 / bf16; w: (Cout, Cin, 3, 3, 3); bias: (Cout) or None.  Output in x's type."""
+    lib = _lib.load_library()
+    if not x.is_cuda:
+        raise RuntimeError("xlstm_hved_b200 has no CPU path")
+    if x.dtype not in _NORM_DTYPES:
+        raise RuntimeError(f"xlstm_hved_b200 conv3: unsupported dtype {x.dtype}")
+    x, w = x.contiguous(), _f32c(w)
+    N, Cin, D, H, W = x.shape
+    Cout = w.shape[0]
+    if w.numel() != Cout * Cin * 27:
+        raise RuntimeError(f"conv3: weight {tuple(w.shape)} does not fit {Cin} input channels")
+    y = torch.empty(N, Cout, D, H, W, device=x.device, dtype=x.dtype)
+    check(lib.xhved_conv3_fwd(ptr(x), ptr(w), ptr(_f32c(bias)) if bias is not None else None, N, Cin, Cout, D, H, W, _NORM_DTYPES[x.dtype],
+                              ptr(y), stream()), "xhved_conv3_fwd")
+    return y
+
+
+def conv3_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: bool = False):
+    """Returns (dx in x's type, dw fp32 in w's shape, dbias fp32) -- None where not wanted."""
+    lib = _lib.load_library()
+    x, wc = x.contiguous(), _f32c(w)
+    dy = dy.to(x.dtype).contiguous()
+    N, Cin, D, H, W = x.shape
+    Cout = w.shape[0]
+    dx = torch.empty_like(x) if want_dx else None
+    dw = torch.empty(w.shape, device=x.device, dtype=torch.float32) if want_dw else None
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if want_db else None
+    part = None
+    if want_dw or want_db:
+        part = torch.empty(lib.xhved_conv3_workspace(N, Cin, Cout, D, H, W), device=x.device, dtype=torch.uint8)
+    check(lib.xhved_conv3_bwd(ptr(x), ptr(wc), ptr(dy), N, Cin, Cout, D, H, W, _NORM_DTYPES[x.dtype], ptr(part), ptr(dx), ptr(dw), ptr(db),
+                              stream()), "xhved_conv3_bwd")
+    return dx, dw, db
+
+
 # ----------------------------------------------------------------------------- mLSTM cell
 class CellBuffers:
     """Device buffers of one chunkwise cell invocation (tiles + saved-for-backward state)."""

@@ -71,6 +71,10 @@ def _pwconv_forward(self, input):
     return modules.pointwise_conv_forward(self, input)
 
 
+def _conv3_forward(self, input):
+    return modules.dense_conv3_forward(self, input)
+
+
 def _atten2_forward(self, seg_x, enc_x, recon_x=None):
     return modules.atten_module2_forward(self, seg_x, enc_x, recon_x)
 
@@ -78,7 +82,7 @@ def _atten2_forward(self, seg_x, enc_x, recon_x=None):
 _FORWARDS = {"ViLBlock": _vil_forward, "ProductOfExperts": _poe_forward, "ProductOfExperts2": _poe2_forward,
              "InstanceNorm3d": _inorm_forward, "BatchNorm3d": _bnorm_forward, "FusedAwayLeakyReLU": _identity_forward,
              "AttenModule2": _atten2_forward, "DepthwiseConv3d": _dwconv3_forward,
-             "PointwiseConv3d": _pwconv_forward}
+             "PointwiseConv3d": _pwconv_forward, "DenseConv3d": _conv3_forward}
 
 
 def _patched_class(cls, kind):
@@ -107,6 +111,8 @@ def _kind_of(m):
             return "DepthwiseConv3d"
         if type(m) is nn.Conv3d and modules.pwconv_supported(m):
             return "PointwiseConv3d"
+        if type(m) is nn.Conv3d and modules.conv3_supported(m):
+            return "DenseConv3d"
         if (name == "AttenModule2" and all(hasattr(m, a) for a in ("compress", "enc_spatial", "enc_spatial2", "seg_spatial", "seg_spatial2"))
                 and modules.gate_convs_supported(m.enc_spatial, m.enc_spatial2) and modules.gate_convs_supported(m.seg_spatial, m.seg_spatial2)):
             return "AttenModule2"
@@ -152,10 +158,10 @@ def patch_model(model, patch_globals: bool = True, conv_path: bool = True):
     ``rebound`` lists them as "module.name".  ``conv_path=False`` leaves the normalisation layers of the convolution path
     (InstanceNorm3d / BatchNorm3d and the LeakyReLU fused into them) on PyTorch."""
     counts = {"ViLBlock": 0, "ProductOfExperts": 0, "ProductOfExperts2": 0, "InstanceNorm3d": 0, "BatchNorm3d": 0,
-              "AttenModule2": 0, "DepthwiseConv3d": 0, "PointwiseConv3d": 0, "fused_LeakyReLU": 0, "globals": 0, "rebound": []}
+              "AttenModule2": 0, "DepthwiseConv3d": 0, "PointwiseConv3d": 0, "DenseConv3d": 0, "fused_LeakyReLU": 0, "globals": 0, "rebound": []}
     for m in model.modules():
         kind = _kind_of(m)
-        if kind in ("InstanceNorm3d", "BatchNorm3d", "AttenModule2", "DepthwiseConv3d", "PointwiseConv3d") and not conv_path:
+        if kind in ("InstanceNorm3d", "BatchNorm3d", "AttenModule2", "DepthwiseConv3d", "PointwiseConv3d", "DenseConv3d") and not conv_path:
             continue
         if kind is not None:
             m.__class__ = _patched_class(type(m), kind)
