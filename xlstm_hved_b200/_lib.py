@@ -188,6 +188,8 @@ def on_device(fn):
     def wrapped(*args, **kwargs):
         for a in args:
             if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():      # the common case: no context switch (~10 us per call)
+                    return fn(*args, **kwargs)
                 with torch.cuda.device(a.device):
                     return fn(*args, **kwargs)
         return fn(*args, **kwargs)
