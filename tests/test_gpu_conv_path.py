@@ -1,4 +1,4 @@
-"""GPU parity of K7 (the spatial gate of AttenModule2: depthwise 7^3 conv + 1x1x1 conv + sigmoid as one dense G -> 1 convolution
+"""GPU parity of the conv-path kernels K7 - K10.  K7 (the spatial gate of AttenModule2: depthwise 7^3 conv + 1x1x1 conv + sigmoid as one dense G -> 1 convolution
 kernel, csrc/gate7.cu) through the C ABI: against the fixture the REAL reference module produced (tests/golden/atten_module2.pt),
 the fp64 oracle on ragged shapes, and PyTorch's own convolution kernels at the model's full size."""
 import pytest

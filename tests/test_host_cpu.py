@@ -167,3 +167,66 @@ def test_workspace_queries_match_the_host_layer():
     bad = _lib.MlstmWorkspace()
     assert lib.xhved_mlstm_workspace_query(4, 100, 200, ctypes.byref(bad)) == -2      # XHVED_ERR_UNSUPPORTED_DH
     assert lib.xhved_vil_workspace_query(1, 100, 48, ctypes.byref(_lib.VilWorkspaceSizes())) == -4   # XHVED_ERR_UNSUPPORTED_DIM
+
+
+def test_conv_path_patching_host_logic():
+    """patch_model's conv-path kinds (K6 - K10) on CPU: what is taken over and what is left alone, the LeakyReLU folding, idempotence,
+    conv_path=False, pickling as the stock classes, unpatch -- and that a patched layer refuses CPU tensors (no fallback)."""
+    import io
+    import torch.nn as nn
+    import xlstm_hved_b200 as xh
+
+    def build():
+        return nn.Sequential(
+            nn.Sequential(nn.InstanceNorm3d(4), nn.LeakyReLU(0.01, inplace=True), nn.Conv3d(4, 4, 3, padding=1)),      # SingleConv 'ilc'
+            nn.Conv3d(4, 4, 3, padding=1, groups=4, bias=False),          # depthwise (K8)
+            nn.Conv3d(4, 1, 1),                                            # 1x1x1 (K9)
+            nn.Conv3d(4, 2, 3, stride=2, padding=1),                       # stride 2: stays on cuDNN
+            nn.Conv3d(4, 4, 3, padding=1, padding_mode="replicate"),       # not zero padding: left alone
+            nn.Conv3d(128, 8, 3, padding=1),                               # too many input channels: left alone
+            nn.InstanceNorm3d(4, affine=True), nn.ReLU(),                  # norm taken, ReLU not fused
+            nn.BatchNorm3d(4), nn.GroupNorm(2, 4))
+    m = build()
+    counts = xh.patch_model(m)
+    assert (counts["InstanceNorm3d"], counts["BatchNorm3d"], counts["fused_LeakyReLU"]) == (2, 1, 1)
+    assert (counts["DenseConv3d"], counts["DepthwiseConv3d"], counts["PointwiseConv3d"]) == (1, 1, 1)
+    assert m[0][0].fused_slope == pytest.approx(0.01) and getattr(m[6], "fused_slope", None) is None
+    for keep in (m[3], m[4], m[5], m[9]):
+        assert not hasattr(type(keep), "_xhved_base")
+    assert isinstance(m[0][1], nn.LeakyReLU) and type(m[0][1]) is not nn.LeakyReLU
+    again = xh.patch_model(m)
+    assert all(again[k] == 0 for k in ("InstanceNorm3d", "BatchNorm3d", "DenseConv3d", "fused_LeakyReLU"))      # idempotent
+    with pytest.raises(RuntimeError):
+        m[0](torch.zeros(1, 4, 4, 4, 4))                                   # CPU tensor: the patched layers have no fallback
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert all(type(a) is type(b) for a, b in zip(back.modules(), build().modules()))
+    keys = set(m.state_dict().keys())
+    xh.unpatch_model(m)
+    assert all(type(a) is type(b) for a, b in zip(m.modules(), build().modules())) and set(m.state_dict().keys()) == keys
+    assert "fused_slope" not in m[0][0].__dict__
+    m2 = build()
+    off = xh.patch_model(m2, conv_path=False)
+    assert all(off[k] == 0 for k in ("InstanceNorm3d", "BatchNorm3d", "DenseConv3d", "DepthwiseConv3d", "PointwiseConv3d", "fused_LeakyReLU"))
+
+
+def test_conv_path_patch_counts_on_the_reference_model():
+    from oracle import ref_loader
+    if ref_loader.find_reference() is None:
+        pytest.skip("reference tree not present on this machine")
+    import xlstm_hved_b200 as xh
+    model = ref_loader.build_model()
+    keys = set(model.state_dict().keys())
+    counts = xh.patch_model(model, patch_globals=False)
+    try:
+        assert counts["InstanceNorm3d"] == 80 and counts["fused_LeakyReLU"] == 80 and counts["BatchNorm3d"] == 18
+        assert counts["AttenModule2"] == 3 and counts["DepthwiseConv3d"] == 18 and counts["PointwiseConv3d"] == 44
+        assert counts["DenseConv3d"] == 62
+        assert set(model.state_dict().keys()) == keys
+    finally:
+        xh.unpatch_model(model)
+    with torch.no_grad():
+        seg, _ = model.eval()(torch.rand(1, 4, 32, 32, 32), [14], valid=True)   # stock path still runs after unpatch
+    assert seg.shape == (1, 3, 32, 32, 32)
