@@ -25,7 +25,7 @@ constexpr int K = 3, TAPS = 27;
 constexpr int TD = 8, TH = 8, TW = 32;
 constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
 constexpr int THREADS = TH * TW;
-constexpr int WG_CO = 4, WG_TILES = 4, PST = 28;
+constexpr int WG_CO = 2, WG_TILES = 4, PST = 28;
 
 template <typename T> struct Cvt;
 template <> struct Cvt<float> {
