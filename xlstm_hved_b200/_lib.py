@@ -171,11 +171,17 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise RuntimeError("xlstm_hved_b200 ops need CUDA tensors (no CPU fallback)")
-    return c_void_p(t.data_ptr())
+    return t.data_ptr()          # a plain int: ctypes converts it for the c_void_p parameter (0 would be NULL: never a live tensor)
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of the calling thread's current stream on the current device, as an integer (None = the legacy default)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device()) or None
+    return torch.cuda.current_stream().cuda_stream or None
 
 
 def on_device(fn):

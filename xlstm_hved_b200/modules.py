@@ -486,29 +486,68 @@ def compute_KLD(mu_list, logvar_list, subset_index_list=[14], choices=[0, 1, 2, 
 
 
 # ----------------------------------------------------------------------------- conv path: normalisation + LeakyReLU (K6)
+def _norm_forward(ctx, x, gamma, beta, mode, eps, slope, mean_in, rstd_in):
+    x = x if x.is_contiguous() else x.contiguous()
+    gamma = ops._f32c(gamma) if gamma is not None else None
+    beta = ops._f32c(beta) if beta is not None else None
+    plan = ops.norm_plan(x, mode, eps, slope)
+    y, stats = ops.norm_act_fwd_raw(x, gamma, beta, plan, mean_in, rstd_in)
+    ctx.plan = plan
+    if stats is None:
+        ctx.save_for_backward(x, gamma, beta, mean_in, rstd_in)
+    else:
+        ctx.save_for_backward(x, gamma, beta, stats)
+    return y, stats
+
+
+def _norm_backward(ctx, dy):
+    saved = ctx.saved_tensors
+    x, gamma, beta = saved[0], saved[1], saved[2]
+    if dy.dtype != x.dtype:
+        dy = dy.to(x.dtype)
+    if not dy.is_contiguous():
+        dy = dy.contiguous()
+    want = gamma is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+    if len(saved) == 4:
+        dx, dgb = ops.norm_act_bwd_raw(x, dy, gamma, beta, ctx.plan, stats=saved[3], want_param_grads=want)
+    else:
+        dx, dgb = ops.norm_act_bwd_raw(x, dy, gamma, beta, ctx.plan, mean=saved[3], rstd=saved[4], want_param_grads=want)
+    if want:
+        return dx, dgb[0].to(gamma.dtype), (dgb[1].to(beta.dtype) if beta is not None else None)
+    return dx, None, None
+
+
 class _NormActFunction(torch.autograd.Function):
-    """InstanceNorm3d / BatchNorm3d with the LeakyReLU that follows fused in (csrc/norm_act.cu).  Saves x and the group statistics
-    only: the backward recomputes the activation mask."""
+    """InstanceNorm3d / BatchNorm3d with the LeakyReLU that follows fused in (csrc/norm_act.cu).  Saves x and ONE small buffer
+    (mean | rstd | the kernel's scratch) only: the backward recomputes the activation mask."""
 
     @staticmethod
     @_lib.on_device
     def forward(ctx, x, gamma, beta, mode, eps, slope, mean_in, rstd_in):
-        y, mean, rstd = ops.norm_act_fwd(x, gamma, beta, mode, eps, slope, mean_in, rstd_in)
-        ctx.save_for_backward(x, gamma, beta, mean, rstd)
-        ctx.cfg = (mode, eps, slope)
+        return _norm_forward(ctx, x, gamma, beta, mode, eps, slope, mean_in, rstd_in)[0]
+
+    @staticmethod
+    @_lib.on_device
+    def backward(ctx, dy):
+        return (*_norm_backward(ctx, dy), None, None, None, None, None)
+
+
+class _NormActStatsFunction(torch.autograd.Function):
+    """The same, also returning the batch statistics (mean, rstd) that train-mode BatchNorm folds into its running statistics."""
+
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, x, gamma, beta, mode, eps, slope):
+        y, stats = _norm_forward(ctx, x, gamma, beta, mode, eps, slope, None, None)
+        g = ctx.plan.groups
+        mean, rstd = stats[:g], stats[g:2 * g]
         ctx.mark_non_differentiable(mean, rstd)
         return y, mean, rstd
 
     @staticmethod
     @_lib.on_device
     def backward(ctx, dy, _dmean, _drstd):
-        x, gamma, beta, mean, rstd = ctx.saved_tensors
-        mode, eps, slope = ctx.cfg
-        want = gamma is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
-        dx, dg, db = ops.norm_act_bwd(x, dy, mean, rstd, gamma, beta, mode, eps, slope, want_param_grads=want)
-        if want:
-            dg, db = dg.to(gamma.dtype), (db.to(beta.dtype) if beta is not None else None)
-        return dx, dg, db, None, None, None, None, None
+        return (*_norm_backward(ctx, dy), None, None, None)
 
 
 def _ncs(x, num_features):
@@ -522,7 +561,7 @@ def instance_norm_act(x, weight=None, bias=None, eps: float = 1e-5, slope: float
     """F.instance_norm(x, weight=weight, bias=bias, eps=eps) followed by F.leaky_relu(., slope) (slope = 1: none) in one pass
     pair over x: statistics per (sample, channel) plane, biased variance."""
     _require_device(x)
-    return _NormActFunction.apply(x, weight, bias, ops.NORM_INSTANCE, float(eps), float(slope), None, None)[0]
+    return _NormActFunction.apply(x, weight, bias, ops.NORM_INSTANCE, float(eps), float(slope), None, None)
 
 
 def batch_norm_act(x, weight, bias, running_mean, running_var, training: bool, momentum, eps: float = 1e-5, slope: float = 1.0):
@@ -530,7 +569,7 @@ def batch_norm_act(x, weight, bias, running_mean, running_var, training: bool, m
     ``momentum`` and the unbiased variance; eval: the running statistics."""
     _require_device(x)
     if training:
-        y, mean, rstd = _NormActFunction.apply(x, weight, bias, ops.NORM_BATCH, float(eps), float(slope), None, None)
+        y, mean, rstd = _NormActStatsFunction.apply(x, weight, bias, ops.NORM_BATCH, float(eps), float(slope))
         if running_mean is not None and momentum:
             with torch.no_grad():
                 n = x.numel() // x.shape[1]
@@ -539,7 +578,7 @@ def batch_norm_act(x, weight, bias, running_mean, running_var, training: bool, m
                 running_var.mul_(1 - momentum).add_(var.to(running_var.dtype), alpha=momentum)
         return y
     rstd = torch.rsqrt(running_var.float() + eps)
-    return _NormActFunction.apply(x, weight, bias, ops.NORM_FROZEN, float(eps), float(slope), running_mean.float(), rstd)[0]
+    return _NormActFunction.apply(x, weight, bias, ops.NORM_FROZEN, float(eps), float(slope), running_mean.float().contiguous(), rstd)
 
 
 class InstanceNorm3d(nn.InstanceNorm3d):

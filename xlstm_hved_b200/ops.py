@@ -275,57 +275,99 @@ def reparam_bwd(logvar, noise, g_z):
 # ----------------------------------------------------------------------------- InstanceNorm3d / BatchNorm3d + LeakyReLU (K6)
 NORM_INSTANCE, NORM_BATCH, NORM_FROZEN = 0, 1, 2
 _NORM_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
-_NORM_WS = {}            # (N, C, spatial, dtype code) -> partials bytes: host-only query, cached
+_NORM_PLANS = {}         # (N, C, spatial, dtype, mode, eps, slope) -> NormPlan: the shape struct and the host-only workspace query, cached
 
 
-def _norm_shape(x, mode, eps, slope):
-    if x.dtype not in _NORM_DTYPES:
-        raise RuntimeError(f"xlstm_hved_b200 norm_act: unsupported dtype {x.dtype}")
-    sh = _lib.NormShape()
-    sh.N, sh.C, sh.spatial = x.shape[0], x.shape[1], x[0, 0].numel()
-    sh.mode, sh.dtype, sh.eps, sh.slope = mode, _NORM_DTYPES[x.dtype], eps, slope
-    key = (sh.N, sh.C, sh.spatial, sh.dtype)
-    if key not in _NORM_WS:
-        _NORM_WS[key] = _lib.load_library().xhved_norm_act_workspace(*key)
-    return sh, _NORM_WS[key]
+class NormPlan:
+    """Everything about one normalisation call that depends on the shape only: the C struct (never modified afterwards, so shared
+    between calls and threads), the number of statistics groups, the size of the partials scratch in floats."""
+    __slots__ = ("sh", "ref", "groups", "ws_floats", "C", "mode")
+
+    def __init__(self, N, C, spatial, dtype, mode, eps, slope):
+        sh = _lib.NormShape()
+        sh.N, sh.C, sh.spatial, sh.mode, sh.dtype, sh.eps, sh.slope = N, C, spatial, mode, _NORM_DTYPES[dtype], eps, slope
+        self.sh, self.ref, self.C, self.mode = sh, ctypes.byref(sh), C, mode
+        self.groups = N * C if mode == NORM_INSTANCE else C
+        self.ws_floats = (_lib.load_library().xhved_norm_act_workspace(N, C, spatial, sh.dtype) + 3) // 4
+
+
+def norm_plan(x, mode, eps, slope) -> NormPlan:
+    shape = x.shape
+    spatial = 1
+    for d in shape[2:]:
+        spatial *= d
+    key = (shape[0], shape[1], spatial, x.dtype, mode, eps, slope)
+    plan = _NORM_PLANS.get(key)
+    if plan is None:
+        if x.dtype not in _NORM_DTYPES:
+            raise RuntimeError(f"xlstm_hved_b200 norm_act: unsupported dtype {x.dtype}")
+        if len(_NORM_PLANS) > 4096:
+            _NORM_PLANS.clear()
+        plan = _NORM_PLANS[key] = NormPlan(shape[0], shape[1], spatial, x.dtype, mode, eps, slope)
+    return plan
+
+
+def norm_act_fwd_raw(x, gamma, beta, plan: NormPlan, mean=None, rstd=None):
+    """The lean form behind the autograd function: x contiguous CUDA; gamma / beta fp32 contiguous or None.  Returns (y, stats):
+    ONE fp32 buffer holding mean [groups] | rstd [groups] | the partials scratch (frozen statistics: stats is None, mean / rstd are
+    the given tensors)."""
+    lib = _lib.load_library()
+    y = torch.empty_like(x)
+    g = plan.groups
+    if plan.mode == NORM_FROZEN:
+        stats, pm, pr, pp = None, mean.data_ptr(), rstd.data_ptr(), None
+    else:
+        stats = torch.empty(2 * g + plan.ws_floats, device=x.device, dtype=torch.float32)
+        pm = stats.data_ptr()
+        pr, pp = pm + 4 * g, pm + 8 * g
+    check(lib.xhved_norm_act_fwd(x.data_ptr(), gamma.data_ptr() if gamma is not None else None, beta.data_ptr() if beta is not None else None,
+                                 plan.ref, pm, pr, pp, y.data_ptr(), stream()), "xhved_norm_act_fwd")
+    return y, stats
+
+
+def norm_act_bwd_raw(x, dy, gamma, beta, plan: NormPlan, stats=None, mean=None, rstd=None, want_param_grads: bool = False):
+    """Backward of norm_act_fwd_raw: `stats` as returned there (its partials region is reused as this call's scratch), or mean / rstd
+    tensors for frozen statistics.  Returns (dx, dgb): dgb = fp32 (2, C) = (dgamma, dbeta) or None."""
+    lib = _lib.load_library()
+    dx = torch.empty_like(x)
+    g = plan.groups
+    if stats is not None:
+        pm = stats.data_ptr()
+        pr, pp, scratch = pm + 4 * g, pm + 8 * g, None
+    else:
+        scratch = torch.empty(max(plan.ws_floats, 1), device=x.device, dtype=torch.float32)
+        pm, pr, pp = mean.data_ptr(), rstd.data_ptr(), scratch.data_ptr()
+    dgb = torch.zeros(2, plan.C, device=x.device, dtype=torch.float32) if want_param_grads else None
+    pg = dgb.data_ptr() if want_param_grads else None
+    check(lib.xhved_norm_act_bwd(x.data_ptr(), dy.data_ptr(), gamma.data_ptr() if gamma is not None else None,
+                                 beta.data_ptr() if beta is not None else None, pm, pr, plan.ref, pp, dx.data_ptr(), pg,
+                                 pg + 4 * plan.C if want_param_grads else None, stream()), "xhved_norm_act_bwd")
+    return dx, dgb
 
 
 def norm_act_fwd(x, gamma=None, beta=None, mode: int = NORM_INSTANCE, eps: float = 1e-5, slope: float = 1.0, mean=None, rstd=None):
-    """x: (N, C, *spatial) contiguous fp32 / fp16 / bf16.  Returns (y, mean, rstd): the statistics are fp32 of N*C (instance) or C
-    (batch) entries; with mode = NORM_FROZEN they are inputs (C entries).  slope = 1: no activation."""
-    lib = _lib.load_library()
+    """x: (N, C, *spatial) fp32 / fp16 / bf16.  Returns (y, mean, rstd): the statistics are fp32 of N*C (instance) or C (batch)
+    entries; with mode = NORM_FROZEN they are inputs (C entries).  slope = 1: no activation."""
     if not x.is_cuda:
         raise RuntimeError("xlstm_hved_b200 has no CPU path")
     x = x.contiguous()
-    sh, ws_bytes = _norm_shape(x, mode, eps, slope)
-    groups = sh.N * sh.C if mode == NORM_INSTANCE else sh.C
+    plan = norm_plan(x, mode, eps, slope)
+    gamma, beta = (_f32c(gamma) if gamma is not None else None), (_f32c(beta) if beta is not None else None)
     if mode == NORM_FROZEN:
         mean, rstd = _f32c(mean), _f32c(rstd)
-        part = None
-    else:
-        mean = torch.empty(groups, device=x.device, dtype=torch.float32)
-        rstd = torch.empty(groups, device=x.device, dtype=torch.float32)
-        part = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
-    y = torch.empty_like(x)
-    check(lib.xhved_norm_act_fwd(ptr(x), ptr(_f32c(gamma)) if gamma is not None else None, ptr(_f32c(beta)) if beta is not None else None,
-                                 ctypes.byref(sh), ptr(mean), ptr(rstd), ptr(part), ptr(y), stream()), "xhved_norm_act_fwd")
-    return y, mean, rstd
+        return norm_act_fwd_raw(x, gamma, beta, plan, mean, rstd)[0], mean, rstd
+    y, stats = norm_act_fwd_raw(x, gamma, beta, plan)
+    return y, stats[:plan.groups], stats[plan.groups:2 * plan.groups]
 
 
 def norm_act_bwd(x, dy, mean, rstd, gamma=None, beta=None, mode: int = NORM_INSTANCE, eps: float = 1e-5, slope: float = 1.0,
                  want_param_grads: bool = False):
     """Backward of norm_act_fwd.  Returns (dx, dgamma, dbeta); the last two are None unless want_param_grads."""
-    lib = _lib.load_library()
     x = x.contiguous()
     dy = dy.to(x.dtype).contiguous()
-    sh, ws_bytes = _norm_shape(x, mode, eps, slope)
-    part = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
-    dx = torch.empty_like(x)
-    dgb = torch.zeros(2, sh.C, device=x.device, dtype=torch.float32) if want_param_grads else None
-    check(lib.xhved_norm_act_bwd(ptr(x), ptr(dy), ptr(_f32c(gamma)) if gamma is not None else None,
-                                 ptr(_f32c(beta)) if beta is not None else None, ptr(mean), ptr(rstd), ctypes.byref(sh), ptr(part), ptr(dx),
-                                 ptr(dgb[0]) if want_param_grads else None, ptr(dgb[1]) if want_param_grads else None, stream()),
-          "xhved_norm_act_bwd")
+    plan = norm_plan(x, mode, eps, slope)
+    gamma, beta = (_f32c(gamma) if gamma is not None else None), (_f32c(beta) if beta is not None else None)
+    dx, dgb = norm_act_bwd_raw(x, dy, gamma, beta, plan, None, _f32c(mean), _f32c(rstd), want_param_grads)
     return (dx, dgb[0], dgb[1]) if want_param_grads else (dx, None, None)
 
 
@@ -403,7 +445,7 @@ def pwconv_fwd(x, w, bias=None):
         raise RuntimeError(f"xlstm_hved_b200 pwconv: unsupported dtype {x.dtype}")
     x, w = x.contiguous(), _f32c(w)
     N, Cin = x.shape[:2]
-    Cout, vol = w.shape[0], x[0, 0].numel()
+    Cout, vol = w.shape[0], x.numel() // (N * Cin)
     y = torch.empty((N, Cout) + tuple(x.shape[2:]), device=x.device, dtype=x.dtype)
     check(lib.xhved_pwconv_fwd(ptr(x), ptr(w), ptr(_f32c(bias)) if bias is not None else None, N, Cin, Cout, vol, _NORM_DTYPES[x.dtype],
                                ptr(y), stream()), "xhved_pwconv_fwd")
@@ -416,7 +458,7 @@ def pwconv_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: bo
     x, wc = x.contiguous(), _f32c(w)
     dy = dy.to(x.dtype).contiguous()
     N, Cin = x.shape[:2]
-    Cout, vol = w.shape[0], x[0, 0].numel()
+    Cout, vol = w.shape[0], x.numel() // (N * Cin)
     dx = torch.empty_like(x) if want_dx else None
     dw = torch.empty(w.shape, device=x.device, dtype=torch.float32) if want_dw else None
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if want_db else None
