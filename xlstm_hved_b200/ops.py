@@ -371,6 +371,19 @@ def norm_act_bwd(x, dy, mean, rstd, gamma=None, beta=None, mode: int = NORM_INST
     return (dx, dgb[0], dgb[1]) if want_param_grads else (dx, None, None)
 
 
+_WS_CACHE = {}           # (entry point name, *shape) -> bytes: the workspace queries are host-only functions of the shape
+
+
+def _workspace(name, *shape):
+    key = (name, *shape)
+    n = _WS_CACHE.get(key)
+    if n is None:
+        if len(_WS_CACHE) > 4096:
+            _WS_CACHE.clear()
+        n = _WS_CACHE[key] = getattr(_lib.load_library(), name)(*shape)
+    return n
+
+
 # ----------------------------------------------------------------------------- spatial gate of AttenModule2 (K7)
 def gate7_fwd(x, w, bias=None):
     """x: (N, G, D, H, W) fp32, w: (G, 343) composed weights, bias: one-element tensor or None.  Returns sigmoid(conv + bias),
@@ -398,7 +411,7 @@ def gate7_bwd(x, w, gate, dgate, want_dx: bool = True, want_dw: bool = True):
     if want_dw:
         dw = torch.empty(G, 343, device=x.device, dtype=torch.float32)
         db = torch.empty(1, device=x.device, dtype=torch.float32)
-        part = torch.empty(lib.xhved_gate7_workspace(N, G, D, H, W), device=x.device, dtype=torch.uint8)
+        part = torch.empty(_workspace("xhved_gate7_workspace", N, G, D, H, W), device=x.device, dtype=torch.uint8)
     check(lib.xhved_gate7_bwd(ptr(x), ptr(w), ptr(gate), ptr(dgate), N, G, D, H, W, ptr(part), ptr(dx), ptr(dw), ptr(db), stream()),
           "xhved_gate7_bwd")
     return dx, dw, db
@@ -430,7 +443,7 @@ def dwconv3_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: b
     if want_dw or want_db:
         dw = torch.empty(w.shape, device=x.device, dtype=torch.float32)
         db = torch.empty(C, device=x.device, dtype=torch.float32) if want_db else None
-        part = torch.empty(lib.xhved_dwconv3_workspace(N, C, D, H, W), device=x.device, dtype=torch.uint8)
+        part = torch.empty(_workspace("xhved_dwconv3_workspace", N, C, D, H, W), device=x.device, dtype=torch.uint8)
     check(lib.xhved_dwconv3_bwd(ptr(x), ptr(wc), ptr(dy), N, C, D, H, W, ptr(part), ptr(dx), ptr(dw), ptr(db), stream()), "xhved_dwconv3_bwd")
     return dx, (dw if want_dw else None), db
 
@@ -464,7 +477,7 @@ def pwconv_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: bo
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if want_db else None
     part = None
     if (want_dw or want_db) and Cin <= 8 and Cout <= 8:
-        part = torch.empty(lib.xhved_pwconv_workspace(N, Cin, Cout, vol), device=x.device, dtype=torch.uint8)
+        part = torch.empty(_workspace("xhved_pwconv_workspace", N, Cin, Cout, vol), device=x.device, dtype=torch.uint8)
     check(lib.xhved_pwconv_bwd(ptr(x), ptr(wc), ptr(dy), N, Cin, Cout, vol, _NORM_DTYPES[x.dtype], ptr(part), ptr(dx), ptr(dw), ptr(db),
                                stream()), "xhved_pwconv_bwd")
     return dx, dw, db
@@ -501,7 +514,7 @@ def conv3_bwd(x, w, dy, want_dx: bool = True, want_dw: bool = True, want_db: boo
     db = torch.empty(Cout, device=x.device, dtype=torch.float32) if want_db else None
     part = None
     if want_dw or want_db:
-        part = torch.empty(lib.xhved_conv3_workspace(N, Cin, Cout, D, H, W), device=x.device, dtype=torch.uint8)
+        part = torch.empty(_workspace("xhved_conv3_workspace", N, Cin, Cout, D, H, W), device=x.device, dtype=torch.uint8)
     check(lib.xhved_conv3_bwd(ptr(x), ptr(wc), ptr(dy), N, Cin, Cout, D, H, W, _NORM_DTYPES[x.dtype], ptr(part), ptr(dx), ptr(dw), ptr(db),
                               stream()), "xhved_conv3_bwd")
     return dx, dw, db
