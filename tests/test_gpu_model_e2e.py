@@ -200,3 +200,33 @@ def test_all_subsets_in_one_batch_matches_15_forwards(model):
     print("all subsets in one batch: same (p>0.5)", same_mask, "same argmax", same_arg, "max abs diff", (ref - got).abs().max().item())
     assert same_mask >= 0.999 and same_arg >= 0.999
     assert ((got8 > 0.5) == (got > 0.5)).float().mean().item() >= 0.999          # (cuDNN picks algorithms per batch size)
+
+
+def test_graphed_subsets_forward_replays_the_patched_model(model):
+    """xh.GraphedSubsetsForward: the patched evaluation forward recorded once per shape and replayed on refilled static buffers must
+    give what the eager batched forward gives -- first use (recording), a second input (pure replay), another subset list (a second
+    graph) -- and the stock subset-index forward's masks."""
+    import xlstm_hved_b200 as xh
+    ns = ref_loader.load_reference()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    xs = [torch.rand(1, 4, 64, 64, 64, device="cuda", generator=g) for _ in range(2)]
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        x7 = xs[1].clone()
+        for m in range(4):
+            if m not in ns.RA_HVED.SUBSETS_MODALITIES[7]:
+                x7[:, m] = 0
+        stock7, _ = model(x7, [7], valid=True)
+    xh.patch_model(model)
+    try:
+        fwd = xh.GraphedSubsetsForward(model)
+        for x in xs:
+            got = fwd(x, subsets=[14, 7])
+            ref = xh.all_subsets_forward(model, x, subsets=[14, 7])
+            assert got.shape == ref.shape == (2, 1, 3, 64, 64, 64)
+            assert (got - ref).abs().max().item() < 1e-4
+        assert len(fwd._graphs) == 1
+        assert ((got[1] > 0.5) == (stock7 > 0.5)).float().mean().item() >= 0.999
+        one = fwd(xs[0], subsets=[3])
+        assert len(fwd._graphs) == 2 and (one - xh.all_subsets_forward(model, xs[0], subsets=[3])).abs().max().item() < 1e-4
+    finally:
+        xh.unpatch_model(model)

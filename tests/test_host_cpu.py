@@ -230,3 +230,16 @@ def test_conv_path_patch_counts_on_the_reference_model():
     with torch.no_grad():
         seg, _ = model.eval()(torch.rand(1, 4, 32, 32, 32), [14], valid=True)   # stock path still runs after unpatch
     assert seg.shape == (1, 3, 32, 32, 32)
+
+
+def test_shared_activation_module_is_not_folded():
+    """One LeakyReLU instance registered under two parents: folding it into the first norm would silently remove the activation
+    of the second chain, so neither is folded (the norms still move onto the kernel)."""
+    import torch.nn as nn
+    import xlstm_hved_b200 as xh
+    act = nn.LeakyReLU(0.01)
+    m = nn.Sequential(nn.Sequential(nn.InstanceNorm3d(2), act), nn.Sequential(nn.Conv3d(2, 2, 5), act))
+    counts = xh.patch_model(m)
+    assert counts["InstanceNorm3d"] == 1 and counts["fused_LeakyReLU"] == 0 and type(act) is nn.LeakyReLU
+    assert getattr(m[0][0], "fused_slope", None) is None
+    xh.unpatch_model(m)

@@ -231,6 +231,19 @@ def main():
             print(json.dumps({"mode": "infer_batched", **common, "steps": args.steps, "ms_per_volume_all_15_subsets": round(ms_b / args.steps / B, 2),
                               "volumes_per_s": round(world * B * args.steps / (ms_b * 1e-3), 3), "speedup_vs_15_forwards": round(ms / ms_b, 3),
                               "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)}))
+        if not args.stock:
+            # ... and replayed as one CUDA graph (xh.GraphedSubsetsForward)
+            gfwd = xh.GraphedSubsetsForward(model)
+            gfwd(x)
+            ms_g = timed(lambda: gfwd(x), args.steps)
+            one = lambda: gfwd(x, subsets=[14])
+            one()
+            ms_1 = timed(one, args.steps)
+            if rank == 0:
+                print(json.dumps({"mode": "infer_graphed", **common, "steps": args.steps,
+                                  "ms_per_volume_all_15_subsets": round(ms_g / args.steps / B, 2),
+                                  "volumes_per_s": round(world * B * args.steps / (ms_g * 1e-3), 3),
+                                  "ms_per_single_forward_graphed": round(ms_1 / args.steps / B, 2)}))
     if world > 1:
         dist.destroy_process_group()
 

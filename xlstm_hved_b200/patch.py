@@ -125,6 +125,13 @@ def _fuse_activations(model):
     BasicConv (buildingblocks.py:11-31): the slope moves into the norm layer's kernel and the LeakyReLU hands its input through.
     Returns the number of fused pairs."""
     n = 0
+    # a module instance registered in more than one place (a shared activation, a norm reused by two branches) is left alone:
+    # folding would change what its other users compute
+    uses = {}
+    for parent in model.modules():
+        for kid in parent._modules.values():
+            if kid is not None:
+                uses[id(kid)] = uses.get(id(kid), 0) + 1
     for parent in model.modules():
         if not (isinstance(parent, nn.Sequential) or type(parent).__name__ == "BasicConv"):
             continue
@@ -133,6 +140,8 @@ def _fuse_activations(model):
             if norm is None or act is None or getattr(type(norm), "_xhved_base", None) not in (nn.InstanceNorm3d, nn.BatchNorm3d):
                 continue
             if type(act) is not nn.LeakyReLU or norm.__dict__.get("fused_slope") is not None:
+                continue
+            if uses.get(id(norm), 0) != 1 or uses.get(id(act), 0) != 1:
                 continue
             norm.fused_slope = float(act.negative_slope)
             act.__class__ = _patched_class(nn.LeakyReLU, "FusedAwayLeakyReLU")
