@@ -46,14 +46,21 @@ struct Dims {
   int tiles_d, tiles_h, tiles_w;
 };
 
+// one thread per (h, w) column of the halo tile, walking along d: the h / w bounds and the address arithmetic are taken once per
+// column, the HD loads of a column are independent (and consecutive lanes read consecutive w)
 template <typename T>
 __device__ __forceinline__ void load_halo(float* __restrict__ tile, const T* __restrict__ src, const Dims& s, int d0, int h0, int w0) {
-  for (int i = threadIdx.x; i < HD * HH * HW; i += THREADS) {
-    const int dz = i / (HH * HW), rem = i - dz * (HH * HW), hy = rem / HW, wx = rem - hy * HW;
-    const int d = d0 + dz - 1, h = h0 + hy - 1, w = w0 + wx - 1;
-    float v = 0.f;
-    if (d >= 0 && d < s.D && h >= 0 && h < s.H && w >= 0 && w < s.W) v = Cvt<T>::to_f(src[(static_cast<int64_t>(d) * s.H + h) * s.W + w]);
-    tile[i] = v;
+  const int64_t plane = static_cast<int64_t>(s.H) * s.W;
+  for (int col = threadIdx.x; col < HH * HW; col += THREADS) {
+    const int hy = col / HW, wx = col - hy * HW;
+    const int h = h0 + hy - 1, w = w0 + wx - 1;
+    const bool ok = h >= 0 && h < s.H && w >= 0 && w < s.W;
+    const T* p = src + static_cast<int64_t>(ok ? h : 0) * s.W + (ok ? w : 0);
+#pragma unroll
+    for (int dz = 0; dz < HD; ++dz) {
+      const int d = d0 + dz - 1;
+      tile[dz * HH * HW + col] = (ok && d >= 0 && d < s.D) ? Cvt<T>::to_f(p[d * plane]) : 0.f;
+    }
   }
 }
 

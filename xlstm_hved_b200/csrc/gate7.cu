@@ -39,23 +39,30 @@ __device__ __forceinline__ void tile_origin(const Dims& s, int& n, int& d0, int&
 }
 
 // halo tile of one (sample, channel) volume, zero outside the volume.  DPRE: the value is dgate * gate * (1 - gate).
+// One thread per (h, w) column walking along d: bounds and address arithmetic once per column, HD independent loads.
 template <bool DPRE>
 __device__ __forceinline__ void load_halo(float* __restrict__ tile, const float* __restrict__ a, const float* __restrict__ b, const Dims& s,
                                           int d0, int h0, int w0) {
-  for (int i = threadIdx.x; i < HD * HH * HW; i += THREADS) {
-    const int dz = i / (HH * HW), rem = i - dz * (HH * HW), hy = rem / HW, wx = rem - hy * HW;
-    const int d = d0 + dz - R, h = h0 + hy - R, w = w0 + wx - R;
-    float v = 0.f;
-    if (d >= 0 && d < s.D && h >= 0 && h < s.H && w >= 0 && w < s.W) {
-      const int64_t at = (static_cast<int64_t>(d) * s.H + h) * s.W + w;
-      if constexpr (DPRE) {
-        const float g = __ldg(a + at);
-        v = __ldg(b + at) * g * (1.f - g);
-      } else {
-        v = __ldg(a + at);
+  const int64_t plane = static_cast<int64_t>(s.H) * s.W;
+  for (int col = threadIdx.x; col < HH * HW; col += THREADS) {
+    const int hy = col / HW, wx = col - hy * HW;
+    const int h = h0 + hy - R, w = w0 + wx - R;
+    const bool ok = h >= 0 && h < s.H && w >= 0 && w < s.W;
+    const int64_t base = static_cast<int64_t>(ok ? h : 0) * s.W + (ok ? w : 0);
+#pragma unroll
+    for (int dz = 0; dz < HD; ++dz) {
+      const int d = d0 + dz - R;
+      float v = 0.f;
+      if (ok && d >= 0 && d < s.D) {
+        if constexpr (DPRE) {
+          const float g = __ldg(a + base + d * plane);
+          v = __ldg(b + base + d * plane) * g * (1.f - g);
+        } else {
+          v = __ldg(a + base + d * plane);
+        }
       }
+      tile[dz * HH * HW + col] = v;
     }
-    tile[i] = v;
   }
 }
 
