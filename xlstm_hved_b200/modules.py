@@ -29,6 +29,7 @@ import torch
 from torch import nn
 
 import torch.nn.functional as F
+from torch.autograd.function import once_differentiable
 
 from . import _lib, ops
 from .ops import SUBSETS_MODALITIES, parallel_stabilized_simple  # noqa: F401  (re-exported drop-in)
@@ -527,6 +528,7 @@ class _NormActFunction(torch.autograd.Function):
         return _norm_forward(ctx, x, gamma, beta, mode, eps, slope, mean_in, rstd_in)[0]
 
     @staticmethod
+    @once_differentiable
     @_lib.on_device
     def backward(ctx, dy):
         return (*_norm_backward(ctx, dy), None, None, None, None, None)
@@ -545,6 +547,7 @@ class _NormActStatsFunction(torch.autograd.Function):
         return y, mean, rstd
 
     @staticmethod
+    @once_differentiable
     @_lib.on_device
     def backward(ctx, dy, _dmean, _drstd):
         return (*_norm_backward(ctx, dy), None, None, None)
@@ -641,6 +644,7 @@ class _Gate7Function(torch.autograd.Function):
         return gate
 
     @staticmethod
+    @once_differentiable
     @_lib.on_device
     def backward(ctx, dgate):
         x, w, gate = ctx.saved_tensors
@@ -707,6 +711,7 @@ class _DwConv3Function(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     @_lib.on_device
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
@@ -742,6 +747,7 @@ class _PwConvFunction(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     @_lib.on_device
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
@@ -780,6 +786,7 @@ class _Conv3Function(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     @_lib.on_device
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
