@@ -16,7 +16,9 @@ Prints ONE JSON line (see the task contract): value = device-resident throughput
 with host (pinned) inputs copied every step and the step's outputs (y, dx, z, KL) copied back, roofline for the dominant
 kernel (CUDA-event timed, separate pass; HBM roof on MINIMUM bytes and tensor roof side by side for the cell kernels),
 sustained = the same step looped for >= 2 s, config3 = BASELINE configs[2]'s fusion (4 levels x 15 missing-modality subsets
-in one launch), gpu_eager_reference = the reference's own PyTorch classes on the same GPU (the competitor a user has today),
+in one launch), conv_path = the conv-path kernels of SURVEY 8f rank 1 alone (K6 - K10: norm + LeakyReLU, spatial gate, depthwise /
+1x1x1 / dense 3^3 convolutions at (8, 4, 128^3), rank 0, outside every timed region),
+gpu_eager_reference = the reference's own PyTorch classes on the same GPU (the competitor a user has today),
 cpu_baseline = the reference's own classes (baseline/_ref, when it travelled with the repo) or else the oracle port of its
 algorithm, on the host cores (bounded sample).  `--impl reference` times that CPU path as its own arm.
 """
