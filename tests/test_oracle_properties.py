@@ -4,6 +4,7 @@ autograd of the forward, the flipped direction is the anti-causal scan, PoE grad
 import pytest
 import torch
 
+from conftest import rel_linf
 from oracle import restate
 
 
@@ -81,3 +82,48 @@ def test_dropped_modalities_equal_the_complementary_subset():
     c, d = restate.poe(mu, lv, (0, 2, 3))
     assert (a - c).abs().max() < 1e-12 and (b - d).abs().max() < 1e-12
     assert (mu_after[2] == 0).all() and torch.equal(mu_after[1], mu[1])      # the reference zeroes mu[m+1] of dropped modalities
+
+
+# ------------------------------------------------------------------ conv path (K6 - K10): identities the kernels rely on
+def test_spatial_gate_composition_identity():
+    """K7 composes AttenModule2's depthwise 7^3 convolution (expansion 4) and the 1x1x1 convolution that follows into ONE dense G -> 1
+    convolution: W[g] = sum_j w2[4g + j] W1[4g + j], b = sum_o w2[o] b1[o] + b2 (csrc/gate7.cu, modules.spatial_gate).  Checked in fp64
+    against the two convolutions run one after the other, as the reference does (buildingblocks.py:283-285)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    G, e = 4, 4
+    x = torch.randn(2, G, 9, 8, 11, generator=g, dtype=torch.float64)
+    w1, b1 = torch.randn(G * e, 1, 7, 7, 7, generator=g, dtype=torch.float64), torch.randn(G * e, generator=g, dtype=torch.float64)
+    w2, b2 = torch.randn(1, G * e, 1, 1, 1, generator=g, dtype=torch.float64), torch.randn(1, generator=g, dtype=torch.float64)
+    ref = F.conv3d(F.conv3d(x, w1, b1, padding=3, groups=G), w2, b2)
+    w = (w1.reshape(G, e, 343) * w2.reshape(G, e, 1)).sum(1).reshape(1, G, 7, 7, 7)
+    b = (w2.reshape(-1) * b1).sum() + b2
+    assert rel_linf(F.conv3d(x, w, b, padding=3), ref) < 1e-12
+
+
+def test_instance_norm_restatement_properties():
+    """Invariance of the normalisation to a per-plane shift and positive scale of its input; batch statistics over one sample equal
+    instance statistics; the LeakyReLU commutes with nothing but is applied after the affine map (slope 1 = identity)."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 5, 6, 7, generator=g, dtype=torch.float64) * 3 + 1
+    y = restate.instance_norm_lrelu(x, eps=0.0)
+    scale = torch.tensor([0.5, 2.0, 7.0], dtype=torch.float64).reshape(1, 3, 1, 1, 1)
+    assert rel_linf(restate.instance_norm_lrelu(x * scale + 4.0, eps=0.0), y) < 1e-12
+    assert y.reshape(6, -1).mean(-1).abs().max() < 1e-12 and (y.reshape(6, -1).var(-1, unbiased=False) - 1).abs().max() < 1e-12
+    w, b = torch.ones(3, dtype=torch.float64), torch.zeros(3, dtype=torch.float64)
+    one = x[:1]
+    yb, _, _ = restate.batch_norm_lrelu(one, w, b, training=True, slope=0.2)
+    assert rel_linf(yb, restate.instance_norm_lrelu(one, slope=0.2)) < 1e-12
+    pre = restate.instance_norm_lrelu(x)
+    act = restate.instance_norm_lrelu(x, slope=0.01)
+    assert torch.equal(act, torch.where(pre > 0, pre, pre * 0.01))
+
+
+def test_depthwise_restatement_is_a_grouped_convolution():
+    """restate.basic_conv_depthwise writes the 27 taps out; it must equal F.conv3d with groups = channels (what the reference runs)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 4, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 1, 3, 3, 3, generator=g, dtype=torch.float64)
+    _, conv = restate.basic_conv_depthwise(x, w)
+    assert rel_linf(conv, F.conv3d(x, w, padding=1, groups=4)) < 1e-12
