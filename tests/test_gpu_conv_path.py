@@ -258,3 +258,62 @@ def test_conv3_vs_pytorch_fp64(cin, cout, shape, bias, dtype, tol):
     assert grads[0].dtype == dtype and grads[1].dtype == torch.float32
     for a, r in zip(grads, ref_grads):
         assert rel_linf(a, r) < (tol if dtype == torch.float16 else 1e-4)
+
+
+# ------------------------------------------------------------------ K9 + K6 inside the reference's DuSEAttention (fixture from the real module)
+class DuSEAttention(nn.Module):
+    """Parameters and forward of modules/DuSFE.py:87-154 (dual squeeze-and-excitation with two BatchNorm3d layers), restated so that the
+    fixture recorded from the REAL module can be replayed on the GPU box, where the reference tree does not exist."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.avg_pool_ch1, self.avg_pool_ch2 = nn.AdaptiveAvgPool3d((1, 1, 1)), nn.AdaptiveAvgPool3d((1, 1, 1))
+        self.fc_comb, self.fc_ch1, self.fc_ch2 = nn.Linear(2 * c, c), nn.Linear(c, c), nn.Linear(c, c)
+        self.conv_squeeze_ch1, self.conv_squeeze_ch2 = nn.Conv3d(c, 1, 1), nn.Conv3d(c, 1, 1)
+        self.conv_comb = nn.Conv3d(2, 1, 1)
+        self.conv_adjust_ch1, self.conv_adjust_ch2 = nn.Conv3d(1, 1, 3, padding=1), nn.Conv3d(1, 1, 3, padding=1)
+        self.conv_fuse_ch1, self.bn_fuse_ch1 = nn.Conv3d(3 * c, c, 3, padding=1), nn.BatchNorm3d(c)
+        self.conv_fuse_ch2, self.bn_fuse_ch2 = nn.Conv3d(3 * c, c, 3, padding=1), nn.BatchNorm3d(c)
+
+    def forward(self, a, b):
+        B, C, D, H, W = a.size()
+        s = torch.cat((self.avg_pool_ch1(a).view(B, C), self.avg_pool_ch2(b).view(B, C)), 1)
+        f = self.fc_comb(s)
+        f1, f2 = torch.sigmoid(self.fc_ch1(f)), torch.sigmoid(self.fc_ch2(f))
+        a_sc, b_sc = a * f1.view(B, C, 1, 1, 1), b * f2.view(B, C, 1, 1, 1)
+        comb = self.conv_comb(torch.cat((self.conv_squeeze_ch1(a), self.conv_squeeze_ch2(b)), 1))
+        g1, g2 = torch.sigmoid(self.conv_adjust_ch1(comb)), torch.sigmoid(self.conv_adjust_ch2(comb))
+        a_cs, b_cs = a * g1.view(B, 1, D, H, W), b * g2.view(B, 1, D, H, W)
+        return self.bn_fuse_ch1(a + a_sc + a_cs), self.bn_fuse_ch2(b + b_sc + b_cs)
+
+
+def test_patched_duse_attention_golden():
+    """The whole DuSEAttention of the reference with its 1x1x1 convolutions on K9, the 1 -> 1 3x3x3 ones on K8 and both BatchNorm3d
+    layers on K6: train mode (values, gradients w.r.t. both inputs and the BatchNorm parameters, running statistics) and eval mode."""
+    import xlstm_hved_b200 as xh
+    c = load_golden("conv_norm.pt")["duse_attention"]
+    att = DuSEAttention(4)
+    att.load_state_dict({k: v.float() for k, v in c["state_dict_before"].items()}, strict=True)
+    att.cuda()
+    counts = xh.patch_model(att)
+    assert counts["BatchNorm3d"] == 2 and counts["PointwiseConv3d"] == 3 and counts["DepthwiseConv3d"] == 2
+    a, b = c["a"].float().cuda().requires_grad_(), c["b"].float().cuda().requires_grad_()
+    g1, g2 = c["g1"].float().cuda(), c["g2"].float().cuda()
+    params = [att.bn_fuse_ch1.weight, att.bn_fuse_ch1.bias, att.bn_fuse_ch2.weight, att.bn_fuse_ch2.bias]
+    att.train()
+    y1, y2 = att(a, b)
+    assert rel_linf(y1, c["train_y1"]) < 5e-5 and rel_linf(y2, c["train_y2"]) < 5e-5
+    grads = torch.autograd.grad([y1, y2], [a, b] + params, [g1, g2])
+    for got, ref in zip(grads, c["train_grads"]):
+        assert rel_linf(got, ref) < 5e-4
+    after = c["state_dict_after_train"]
+    for name in ("bn_fuse_ch1", "bn_fuse_ch2"):
+        bn = getattr(att, name)
+        assert rel_linf(bn.running_mean, after[name + ".running_mean"]) < 1e-5 and rel_linf(bn.running_var, after[name + ".running_var"]) < 1e-5
+    att.eval()
+    e1, e2 = att(a, b)
+    assert rel_linf(e1, c["eval_y1"]) < 5e-5 and rel_linf(e2, c["eval_y2"]) < 5e-5
+    egrads = torch.autograd.grad([e1, e2], [a, b] + params, [g1, g2])
+    for got, ref in zip(egrads, c["eval_grads"]):
+        assert rel_linf(got, ref) < 5e-4
+    xh.unpatch_model(att)
