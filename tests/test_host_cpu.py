@@ -41,6 +41,16 @@ def test_no_cpu_fallback():
         xh.ViLLayer3D(dim=32)(torch.zeros(1, 32, 2, 2, 2))
     with pytest.raises(RuntimeError):
         xh.ProductOfExperts()(torch.zeros(5, 1, 1, 2, 2, 2), torch.zeros(5, 1, 1, 2, 2, 2), (0, 1))
+    # the conv-path ops and the graphed driver refuse as well
+    with pytest.raises(RuntimeError):
+        xh.instance_norm_act(torch.zeros(1, 2, 4, 4, 4))
+    with pytest.raises(RuntimeError):
+        xh.spatial_gate(torch.zeros(1, 2, 4, 4, 4), torch.nn.Conv3d(2, 8, 7, padding=3, groups=2), torch.nn.Conv3d(8, 1, 1))
+    with pytest.raises(RuntimeError):
+        xh.ops.conv3_fwd(torch.zeros(1, 2, 4, 4, 4), torch.zeros(2, 2, 3, 3, 3))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            xh.GraphedSubsetsForward(torch.nn.Identity().eval())
 
 
 def test_patch_and_unpatch_reference_model():
